@@ -1,0 +1,134 @@
+"""Pin the oracle (oracle/cswin_oracle.py) to the golden vectors produced by the unmodified reference."""
+import numpy as np
+import pytest
+import torch
+
+from cswin_unet_b200 import synth
+from oracle import cswin_oracle as O
+from tests import golden_util as G
+
+
+def T(a, dtype=torch.float64):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dtype)
+
+
+def lepe_inputs(cb, reso, idx, B, dtype=torch.float64):
+    full_c = cb if idx == -1 else 2 * cb
+    base = T(synth.synth_qkv(B, reso, full_c, seed=0), dtype)
+    off = cb if idx == 1 else 0
+    qkv = base.permute(2, 0, 1, 3)[..., off:off + cb]
+    w = T(synth.synth_tensor(f"lepe/{cb}/{reso}/{idx}/get_v.weight", (cb, 1, 3, 3), 1), dtype)
+    b = T(synth.synth_tensor(f"lepe/{cb}/{reso}/{idx}/get_v.bias", (cb,), 1), dtype)
+    return qkv, w, b
+
+
+LEPE_EXTRA = ((32, 16, 0, 2, 1), (64, 16, 1, 2, 2), (64, 8, -1, 8, 2), (128, 16, 0, 8, 4), (48, 12, 1, 3, 3))
+
+
+@pytest.mark.parametrize("tag,cfgs,B", [("t224", synth.LEPE_CONFIGS_T224, 1), ("extra", LEPE_EXTRA, 2)])
+def test_lepe_attention_vectorised_matches_reference(tag, cfgs, B):
+    z = G.load(f"lepe_{tag}")
+    for (cb, reso, idx, split, heads) in cfgs:
+        qkv, w, b = lepe_inputs(cb, reso, idx, B)
+        y = O.lepe_attention(qkv[0], qkv[1], qkv[2], w, b, reso, idx, split, heads)
+        G.compare(z, f"c{cb}_r{reso}_i{idx}_s{split}_h{heads}", y.numpy(), atol=2e-6)
+
+
+def test_lepe_attention_loops_matches_reference():
+    z = G.load("lepe_extra")
+    for (cb, reso, idx, split, heads) in LEPE_EXTRA[:3] + LEPE_EXTRA[4:]:
+        qkv, w, b = lepe_inputs(cb, reso, idx, 2)
+        y = O.lepe_attention_loops(qkv[0].numpy(), qkv[1].numpy(), qkv[2].numpy(), w.numpy(), b.numpy(),
+                                   reso, idx, split, heads)
+        G.compare(z, f"c{cb}_r{reso}_i{idx}_s{split}_h{heads}", y, atol=2e-6)
+
+
+def test_lepe_attention_backward_via_autograd_matches_reference():
+    """The oracle's autograd is the truth for the CUDA backward; pin it to the reference's autograd."""
+    z = G.load("lepe_extra")
+    for (cb, reso, idx, split, heads) in LEPE_EXTRA:
+        qkv, w, b = lepe_inputs(cb, reso, idx, 2)
+        q, k, v = (t.clone().requires_grad_(True) for t in qkv)
+        w = w.requires_grad_(True); b = b.requires_grad_(True)
+        y = O.lepe_attention(q, k, v, w, b, reso, idx, split, heads)
+        key = f"c{cb}_r{reso}_i{idx}_s{split}_h{heads}"
+        gup = T(synth.synth_tensor(f"lepe_grad/{key}", tuple(y.shape), 2))
+        gq, gk, gv, gw, gb = torch.autograd.grad(y, [q, k, v, w, b], gup)
+        G.compare(z, key + "_dqkv", torch.cat([gq, gk, gv], 0).numpy(), atol=5e-6)
+        G.compare(z, key + "_dw", gw.reshape(cb, 9).numpy(), atol=1e-4, rtol=1e-6)
+        G.compare(z, key + "_db", gb.reshape(1, cb).numpy(), atol=1e-4, rtol=1e-6)
+
+
+def test_block_matches_reference():
+    z = G.load("block")
+    for (dim, reso, heads, split, last) in ((64, 56, 2, 1, False), (128, 28, 4, 2, False), (256, 14, 8, 7, False), (512, 7, 16, 7, True)):
+        shapes = {k: v for k, v in O.state_dict_shapes().items()}
+        stage = {64: "stage1.0.", 128: "stage2.0.", 256: "stage3.0.", 512: "stage4.0."}[dim]
+        sd = {k[len(stage):]: T(synth.synth_tensor(f"block/{dim}/" + k[len(stage):], s, 3))
+              for k, s in shapes.items() if k.startswith(stage)}
+        x = T(synth.synth_tensor(f"block_in/{dim}", (2, reso * reso, dim), 4))
+        y = O.cswin_block(sd, "", x, reso, heads, split, last)
+        G.compare(z, f"d{dim}", y.numpy(), atol=1e-5)
+
+
+def test_merge_and_carafe_match_reference():
+    z = G.load("merge_carafe")
+    for (dim, reso) in ((64, 56), (128, 28), (256, 14)):
+        shp = {"conv.weight": (2 * dim, dim, 3, 3), "conv.bias": (2 * dim,), "norm.weight": (2 * dim,), "norm.bias": (2 * dim,)}
+        sd = {k: T(synth.synth_tensor(f"merge/{dim}/" + k, s, 5)) for k, s in shp.items()}
+        x = T(synth.synth_tensor(f"merge_in/{dim}", (2, reso * reso, dim), 6))
+        G.compare(z, f"merge_d{dim}", O.merge_block(sd, "", x).numpy(), atol=1e-5)
+    for (dim, dout, reso, up) in ((512, 256, 7, 2), (128, 64, 28, 2), (64, 64, 14, 4)):
+        shp = {"down.weight": (dim // 4, dim, 1, 1), "down.bias": (dim // 4,),
+               "encoder.weight": (9 * up * up, dim // 4, 3, 3), "encoder.bias": (9 * up * up,),
+               "out.weight": (dout, dim, 1, 1), "out.bias": (dout,)}
+        sd = {k: T(synth.synth_tensor(f"carafe/{dim}/{up}/" + k, s, 7)) for k, s in shp.items()}
+        x = T(synth.synth_tensor(f"carafe_in/{dim}/{up}", (2, reso * reso, dim), 8))
+        G.compare(z, f"carafe_d{dim}_u{up}", O.carafe(sd, "", x, up).numpy(), atol=1e-5)
+
+
+def test_state_dict_contract_matches_reference():
+    z = G.load("model_t224")
+    shapes = O.state_dict_shapes()
+    assert list(shapes.keys()) == [str(k) for k in z["keys"]]
+    assert [",".join(map(str, s)) for s in shapes.values()] == [str(s) for s in z["key_shapes"]]
+    assert sum(int(np.prod(s)) for s in shapes.values()) == int(z["n_params"]) == 23_568_492
+
+
+def test_full_model_matches_reference():
+    z = G.load("model_t224")
+    shapes = O.state_dict_shapes()
+    sd = {k: T(v) for k, v in synth.synth_state_dict(shapes, seed=1234).items()}
+    x = T(synth.synth_image_batch(2, 3, 224, seed=0, kind="randn"))
+    taps = {}
+    with torch.no_grad():
+        logits = O.cswin_unet_forward(sd, x, taps=taps)
+    G.compare(z, "tap_x1", taps["stage1"].numpy(), atol=1e-6, rtol=1e-6)
+    G.compare(z, "tap_x3", taps["stage3"].numpy(), atol=1e-6, rtol=1e-6)
+    G.compare(z, "tap_up", None if False else O._ln(taps["stage_up1"], sd["norm_up.weight"], sd["norm_up.bias"], 1e-5).numpy(),
+              atol=1e-6, rtol=1e-6)
+    G.compare(z, "logits_randn", logits.permute(0, 2, 3, 1).numpy(), atol=1e-6, rtol=1e-6)
+    assert (logits.argmax(1).numpy() == z["argmax_randn"]).mean() > 0.99999
+
+
+def test_loss_matches_reference():
+    z = G.load("loss")
+    logits = T(synth.synth_tensor("loss/logits", (2, 9, 32, 32), 9)).requires_grad_(True)
+    labels = torch.from_numpy(synth.synth_labels(2, 32, 9, seed=9))
+    loss = O.seg_loss(logits, labels, 9)
+    assert abs(loss.item() - float(z["loss"])) < 1e-9
+    (g,) = torch.autograd.grad(loss, logits)
+    assert np.abs(g.numpy() - z["grad"]).max() < 1e-8
+
+
+def test_metrics_fallback_rules():
+    a = np.zeros((4, 8, 8), bool); b = np.zeros((4, 8, 8), bool)
+    assert O.dice_hd95_percase(a, b) == (0.0, 0.0)
+    a[1, 2:5, 2:5] = True
+    assert O.dice_hd95_percase(a, b) == (1.0, 0.0)
+    assert O.dice_hd95_percase(b, a) == (0.0, 0.0)
+    d, h = O.dice_hd95_percase(a, a)
+    assert d == 1.0 and h == 0.0
+    b[1, 3:6, 2:5] = True
+    d, h = O.dice_hd95_percase(a, b)
+    assert abs(d - 2 * 6 / 18) < 1e-12 and h == 1.0
