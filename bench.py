@@ -1,0 +1,343 @@
+#!/usr/bin/env python
+"""bench.py — CSWin-UNet-tiny 224^2 slices/sec on B200 (BASELINE.json metric), one process per GPU.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 ... bench.py --gpus N ...
+
+native arm  : a "step" is one bf16 forward of cswin_tiny_224_lite over one batch of 24 synthetic 3x224x224 slices
+              per GPU through the native kernels (libcswin_b200.so), replayed as a CUDA graph.
+              `value`  = slices/s with the inputs resident in HBM (16 rotating batches = 231 MB > L2),
+              `e2e`    = same metric through the public nn.Module call with HOST (pinned) inputs: H2D copy of the
+                         batch, forward, argmax label map, D2H of the label map, every step,
+              `roofline` = fused LePE attention kernel family: algorithmic bytes / CUDA-event time vs measured HBM peak,
+              `cpu_baseline` = the CPU oracle (port of the reference's PyTorch path) on this box's host cores.
+reference arm: the reference's CPU path (oracle port; /root/reference cannot travel to the GPU box) on all host cores,
+              same metric / config; rank 0 only.
+Slices are independent, so N GPUs = N replicas each running its own batches: weak scaling, no collective on the
+data path; timing = max over ranks of the device time, bracketed by barrier + synchronize.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "CSWin-UNet-tiny 224^2 slices/sec (bf16 fwd)"
+UNIT = "slices/s"
+BATCH = 24
+GFLOP_PER_SLICE_FWD = 10.028       # BASELINE.md section 2 (FlopCounterMode on the unmodified reference)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"], "bf16_tflops_sustained": d.get("bf16_tflops_sustained"),
+                "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons of one GPU with NVML during the timed region."""
+
+    def __init__(self, index: int, period: float = 0.02):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._halt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and vis.split(",")[index].isdigit() else index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    NAMES = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+             0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+             0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+    def run(self):
+        if not self.ok:
+            return
+        while not self._halt.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                r = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for bit, name in self.NAMES.items():
+                    if r & bit and name != "gpu_idle":
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._halt.wait(self.period)
+
+    def stop(self):
+        self._halt.set()
+        self.join(timeout=2)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU oracle legs
+# --------------------------------------------------------------------------------------------------
+def oracle_model():
+    from oracle import cswin_oracle as O          # test infrastructure; used here only as the CPU baseline
+    from cswin_unet_b200 import synth
+    shapes = O.state_dict_shapes()
+    sd = {k: torch.from_numpy(v) for k, v in synth.synth_state_dict(shapes, seed=1234).items()}
+    return O, sd
+
+
+def cpu_forward_rate(budget_s: float, batch: int, min_iters: int = 2):
+    from cswin_unet_b200 import synth
+    O, sd = oracle_model()
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    x = torch.from_numpy(synth.synth_image_batch(batch, 3, 224, seed=0, kind="ct"))
+    with torch.no_grad():
+        O.cswin_unet_forward(sd, x[:2])                        # warm-up
+        t0 = time.perf_counter(); n = 0
+        while n < min_iters or (time.perf_counter() - t0) < budget_s:
+            O.cswin_unet_forward(sd, x)
+            n += 1
+        dt = time.perf_counter() - t0
+    return n * batch / dt, cores, n, dt
+
+
+def run_reference(args):
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return 0
+    from cswin_unet_b200 import synth
+    O, sd = oracle_model()
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    # bounded sample per step so that K+W steps end within minutes on any host: a batch of 24 slices is ~1.5 s on 8 cores
+    sample = BATCH
+    x = torch.from_numpy(synth.synth_image_batch(sample, 3, 224, seed=0, kind="ct"))
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            O.cswin_unet_forward(sd, x)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            O.cswin_unet_forward(sd, x)
+        dt = time.perf_counter() - t0
+    value = args.steps * sample / dt
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"cswin_tiny_224_lite eval forward, batch {sample} per step, 3x224x224 synthetic slices, "
+                                   "CPU port of the reference PyTorch path (oracle/cswin_oracle.py), fp32"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{args.steps} steps x {sample} slices, torch CPU fp32, {cores} threads"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+    return 0
+
+
+# --------------------------------------------------------------------------------------------------
+# native arm
+# --------------------------------------------------------------------------------------------------
+def attention_bytes_per_image():
+    """Ideal traffic of the fused LePE attention per image, bf16: read q,k,v once + write out once."""
+    per_block = {1: 3136 * 64, 2: 784 * 128, 3: 196 * 256, 4: 49 * 512}
+    blocks = {1: 2, 2: 4, 3: 18, 4: 2}
+    return sum(4 * per_block[s] * 2 * blocks[s] for s in per_block)       # = 14,049,280 B
+
+
+def run_native(args):
+    import cswin_unet_b200 as cw
+    from cswin_unet_b200 import ops, synth
+
+    rank, world, local = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (native arm) needs a CUDA device: the product has no CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    cw.lib()                                                       # fail loudly if the extension is missing
+
+    model = cw.cswin_tiny_224(num_classes=9).eval()
+    shapes = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+    model.load_state_dict({k: torch.from_numpy(v) for k, v in synth.synth_state_dict(shapes, seed=1234).items()}, strict=True)
+    model = model.to(dev)
+    model.compute_dtype = torch.bfloat16
+
+    B = args.batch
+    n_rot = 16
+    host = torch.from_numpy(synth.synth_image_batch(B, 3, 224, seed=1000 + rank, kind="ct"))
+    pool = [(host + 0.001 * i).to(dev) for i in range(n_rot)]      # 16 x 14.4 MB fp32 = 231 MB > 126 MB L2
+    static_x = pool[0].clone()
+
+    with torch.no_grad():
+        n0 = cw.launch_count()
+        model(static_x)
+        launches_per_fwd = cw.launch_count() - n0
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(2):
+                model(static_x)
+        torch.cuda.current_stream().wait_stream(s)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            static_y = model(static_x)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def step(i):
+        static_x.copy_(pool[i % n_rot], non_blocking=True)
+        graph.replay()
+
+    # ---- value: device-resident inputs ----
+    for i in range(args.warmup):
+        step(i)
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        step(i)
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * args.steps * B / (ms * 1e-3)
+
+    # ---- e2e: host buffers through the public module call ----
+    pinned = [host.clone().pin_memory() for _ in range(2)]
+    out_host = torch.empty((B, 224, 224), dtype=torch.uint8).pin_memory()
+
+    def e2e_step(i):
+        x = pinned[i % 2].to(dev, non_blocking=True)
+        with torch.no_grad():
+            logits = model(x)
+        out_host.copy_(logits.argmax(1).to(torch.uint8), non_blocking=True)
+
+    for i in range(max(args.warmup, 3)):
+        e2e_step(i)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        e2e_step(i)
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms_e2e], device=dev)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        ms_e2e = float(t.item())
+    e2e_value = world * args.steps * B / (ms_e2e * 1e-3)
+
+    # ---- roofline: per-kernel CUDA-event timing of the fused attention launches (eager pass, same workload) ----
+    pk = peaks()
+    att_ms = []
+    orig_att = ops.lepe_attention_fwd
+
+    def timed(fn, sink):
+        def wrapper(*a, **k):
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            r = fn(*a, **k)
+            a1.record()
+            sink.append((a0, a1))
+            return r
+        return wrapper
+
+    reps = 5
+    try:
+        ops.lepe_attention_fwd = timed(orig_att, att_ms)
+        with torch.no_grad():
+            for i in range(reps):
+                model(pool[i % n_rot])
+        torch.cuda.synchronize()
+    finally:
+        ops.lepe_attention_fwd = orig_att
+    att_total_ms = sum(a.elapsed_time(b) for a, b in att_ms) / reps            # per forward: 26 launches
+    att_bytes = attention_bytes_per_image() * B
+    att_gbs = att_bytes / (att_total_ms * 1e-3) / 1e9
+    roofline = {"kernel": "lepe_attention_fwd (26 launches per forward, both branches per launch)", "bound": "hbm",
+                "achieved": att_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": att_gbs / pk["hbm_gbs"],
+                "traffic": None, "peak_source": pk["source"], "bytes_per_forward": att_bytes,
+                "ms_per_forward": att_total_ms, "launches_per_forward": len(att_ms) // reps}
+    model_tflops = value / world * GFLOP_PER_SLICE_FWD / 1e3
+    roofline_model = {"bound": "tensor", "achieved": model_tflops, "peak": pk["bf16_tflops_sustained"] or pk["bf16_tflops"],
+                      "unit": "TFLOP/s", "frac": model_tflops / (pk["bf16_tflops_sustained"] or pk["bf16_tflops"]),
+                      "note": "whole forward, 10.028 GFLOP/slice algorithmic, per GPU, vs sustained bf16 peak"}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"cswin_tiny_224_lite (9 classes) eval forward, batch {B}/GPU, 3x224x224 synthetic CT-like "
+                                   "slices, synthetic weights; BASELINE configs[2] shapes, forward pass",
+                       "global_batch": B * world, "parallelism": f"slice-sharded replicas x{world}, no collective",
+                       "l2": f"inputs rotate over {n_rot} batches = {n_rot * host.numel() * 4 / 1e6:.0f} MB > 126 MB L2",
+                       "launch": "CUDA graph replay of the native forward"},
+            "clocks": clocks, "gpu_launches": int(launches_per_fwd * args.steps),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(host.numel() * 4),
+                    "d2h_bytes_per_step": int(out_host.numel()), "ms_per_step": ms_e2e / args.steps,
+                    "path": "pinned host fp32 batch -> H2D -> CSWinTransformer.forward (eager launches) -> argmax -> D2H uint8 labels"},
+            "roofline": roofline, "roofline_model": roofline_model}
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, cores, n, dt = cpu_forward_rate(args.cpu_budget, BATCH)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": f"{n} forwards of batch {BATCH} in {dt:.1f} s, oracle (torch CPU fp32), {cores} threads"}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU-oracle work for cpu_baseline")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_native(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

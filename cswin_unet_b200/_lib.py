@@ -1,0 +1,126 @@
+"""ctypes binding of libcswin_b200.so (C ABI declared in include/cswin_b200.h).
+
+The product has no CPU path and no fallback: if the shared library is missing or a call fails, an
+exception is raised.  `build()` compiles the library in-tree with nvcc for sm_100a (cross-compiles
+without a GPU); the built .so is git-ignored but travels to the GPU box with the repo snapshot.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC_DIR = os.path.join(_HERE, "csrc")
+LIB_PATH = os.path.join(_HERE, "libcswin_b200.so")
+HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "cswin_b200.h")
+
+F32, BF16 = 0, 1
+ABI_VERSION = 1
+
+c_void_p, c_int32, c_int64, c_float = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+
+
+class LepeBranch(C.Structure):
+    _fields_ = [
+        ("q", c_void_p), ("k", c_void_p), ("v", c_void_p),
+        ("q_bs", c_int64), ("q_ts", c_int64), ("k_bs", c_int64), ("k_ts", c_int64),
+        ("v_bs", c_int64), ("v_ts", c_int64),
+        ("out", c_void_p), ("o_bs", c_int64), ("o_ts", c_int64),
+        ("conv_w", c_void_p), ("conv_b", c_void_p), ("lse", c_void_p),
+        ("C_b", c_int32), ("heads", c_int32), ("H_sp", c_int32), ("W_sp", c_int32),
+    ]
+
+
+class LepeBranchGrad(C.Structure):
+    _fields_ = [
+        ("fwd", LepeBranch),
+        ("dout", c_void_p), ("do_bs", c_int64), ("do_ts", c_int64),
+        ("dq", c_void_p), ("dk", c_void_p), ("dv", c_void_p),
+        ("dq_bs", c_int64), ("dq_ts", c_int64), ("dk_bs", c_int64), ("dk_ts", c_int64),
+        ("dv_bs", c_int64), ("dv_ts", c_int64),
+        ("dconv_w", c_void_p), ("dconv_b", c_void_p),
+    ]
+
+
+class LinearArgs(C.Structure):
+    _fields_ = [
+        ("a", c_void_p), ("lda", c_int64), ("K1", c_int32),
+        ("a2", c_void_p), ("lda2", c_int64), ("K2", c_int32),
+        ("w", c_void_p), ("ldw", c_int64),
+        ("bias", c_void_p),
+        ("ln_gamma", c_void_p), ("ln_beta", c_void_p), ("ln_eps", c_float),
+        ("residual", c_void_p), ("ldr", c_int64),
+        ("sample_scale", c_void_p), ("rows_per_sample", c_int32),
+        ("out", c_void_p), ("ldo", c_int64),
+        ("M", c_int64), ("N", c_int32),
+        ("act", c_int32),
+    ]
+
+
+# symbol -> (restype, argtypes); every symbol include/cswin_b200.h declares
+SIGNATURES = {
+    "cswin_abi_version": (c_int32, []),
+    "cswin_last_error": (C.c_char_p, []),
+    "cswin_launch_count": (C.c_uint64, []),
+    "cswin_lepe_attention_fwd": (c_int32, [C.POINTER(LepeBranch), c_int32, c_int32, c_int32, c_float, c_int32, c_void_p]),
+    "cswin_lepe_attention_bwd": (c_int32, [C.POINTER(LepeBranchGrad), c_int32, c_int32, c_int32, c_float, c_int32, c_void_p]),
+    "cswin_layernorm_fwd": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int32,
+                                      c_float, c_void_p, c_void_p, c_int32, c_void_p]),
+    "cswin_linear_fwd": (c_int32, [C.POINTER(LinearArgs), c_int32, c_void_p]),
+    "cswin_im2col_tokens": (c_int32, [c_void_p, c_int64, c_int64, c_void_p, c_int64] + [c_int32] * 9 + [c_void_p]),
+    "cswin_im2col_nchw": (c_int32, [c_void_p, c_int32, c_void_p, c_int64] + [c_int32] * 9 + [c_void_p]),
+    "cswin_carafe_reassemble_fwd": (c_int32, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64]
+                                    + [c_int32] * 8 + [c_void_p]),
+}
+
+_lib = None
+_lock = threading.Lock()
+
+
+class CswinError(RuntimeError):
+    pass
+
+
+def build(verbose: bool = False) -> str:
+    """Compile libcswin_b200.so in-tree for sm_100a (make -C csrc). Returns the library path."""
+    proc = subprocess.run(["make", "-C", CSRC_DIR, "-j", str(os.cpu_count() or 4)],
+                          stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if verbose or proc.returncode != 0:
+        print(proc.stdout)
+    if proc.returncode != 0:
+        raise CswinError("building libcswin_b200.so failed (see output above)")
+    return LIB_PATH
+
+
+def lib() -> C.CDLL:
+    """The loaded library; raises CswinError if it has not been built (there is no fallback path)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise CswinError(
+                    f"{LIB_PATH} is missing: the CUDA extension is the only execution path of cswin_unet_b200. "
+                    "Build it with `python -c 'import __graft_entry__ as g; g.build()'` or `make -C cswin_unet_b200/csrc`.")
+            handle = C.CDLL(LIB_PATH)
+            for name, (res, args) in SIGNATURES.items():
+                fn = getattr(handle, name)     # AttributeError if the .so does not export a declared symbol
+                fn.restype, fn.argtypes = res, args
+            got = handle.cswin_abi_version()
+            if got != ABI_VERSION:
+                raise CswinError(f"libcswin_b200.so ABI version {got} != binding version {ABI_VERSION}; rebuild")
+            _lib = handle
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib().cswin_last_error()
+        raise CswinError(f"{what} failed (code {rc}): {msg.decode() if msg else '?'}")
+
+
+def launch_count() -> int:
+    return int(lib().cswin_launch_count())

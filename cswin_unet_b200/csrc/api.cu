@@ -1,0 +1,125 @@
+// api.cu — extern "C" boundary of libcswin_b200.so (declared in include/cswin_b200.h).
+// Argument validation, dtype / kernel-family selection, thread-local error text.  No torch types, no allocation,
+// no synchronisation: every entry point only enqueues kernels on the caller's stream.
+#include <mutex>
+
+#include "common.cuh"
+
+namespace cswin {
+
+std::atomic<uint64_t> g_launches{0};
+
+namespace {
+thread_local char t_err[512] = "";
+std::mutex g_dev_mu;
+int g_sm_count[64] = {0};
+}  // namespace
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(t_err, sizeof(t_err), fmt, ap);
+  va_end(ap);
+}
+
+int sm_count() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  std::lock_guard<std::mutex> lk(g_dev_mu);
+  if (g_sm_count[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    g_sm_count[dev] = n;
+  }
+  return g_sm_count[dev];
+}
+
+static bool valid_dtype(int dtype) { return dtype == CSWIN_F32 || dtype == CSWIN_BF16; }
+
+}  // namespace cswin
+
+using namespace cswin;
+
+extern "C" {
+
+int cswin_abi_version(void) { return CSWIN_ABI_VERSION; }
+const char* cswin_last_error(void) { return t_err; }
+uint64_t cswin_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int cswin_lepe_attention_fwd(const cswin_lepe_branch_t* branches, int32_t n_branches, int32_t B, int32_t reso,
+                             float scale, int32_t dtype, cswin_stream_t stream) {
+  CSWIN_REQUIRE(valid_dtype(dtype), CSWIN_ERR_INVALID, "lepe_attention_fwd: bad dtype %d", dtype);
+  CSWIN_REQUIRE(branches && (n_branches == 1 || n_branches == 2), CSWIN_ERR_INVALID, "lepe_attention_fwd: n_branches must be 1 or 2");
+  CSWIN_REQUIRE(B >= 0 && reso > 0, CSWIN_ERR_INVALID, "lepe_attention_fwd: bad B=%d reso=%d", B, reso);
+  if (B == 0) return CSWIN_OK;
+  if (dtype == CSWIN_BF16) {
+    bool handled = false;
+    int rc = lepe_attention_fwd_tc(branches, n_branches, B, reso, scale, (cudaStream_t)stream, &handled);
+    if (rc != CSWIN_OK || handled) return rc;
+  }
+  return lepe_attention_fwd_simt(branches, n_branches, B, reso, scale, dtype, (cudaStream_t)stream);
+}
+
+int cswin_lepe_attention_bwd(const cswin_lepe_branch_grad_t* branches, int32_t n_branches, int32_t B, int32_t reso,
+                             float scale, int32_t dtype, cswin_stream_t stream) {
+  CSWIN_REQUIRE(valid_dtype(dtype), CSWIN_ERR_INVALID, "lepe_attention_bwd: bad dtype %d", dtype);
+  CSWIN_REQUIRE(branches && (n_branches == 1 || n_branches == 2), CSWIN_ERR_INVALID, "lepe_attention_bwd: n_branches must be 1 or 2");
+  CSWIN_REQUIRE(B >= 0 && reso > 0, CSWIN_ERR_INVALID, "lepe_attention_bwd: bad B=%d reso=%d", B, reso);
+  if (B == 0) return CSWIN_OK;
+  return lepe_attention_bwd_simt(branches, n_branches, B, reso, scale, dtype, (cudaStream_t)stream);
+}
+
+int cswin_layernorm_fwd(const void* x, int64_t ldx, const void* gamma, const void* beta, void* y, int64_t ldy,
+                        int64_t M, int32_t C, float eps, float* mean_out, float* rstd_out, int32_t dtype,
+                        cswin_stream_t stream) {
+  CSWIN_REQUIRE(valid_dtype(dtype), CSWIN_ERR_INVALID, "layernorm_fwd: bad dtype %d", dtype);
+  CSWIN_REQUIRE(M >= 0, CSWIN_ERR_INVALID, "layernorm_fwd: negative M");
+  return layernorm_fwd(x, ldx, gamma, beta, y, ldy, M, C, eps, mean_out, rstd_out, dtype, (cudaStream_t)stream);
+}
+
+int cswin_linear_fwd(const cswin_linear_args_t* a, int32_t dtype, cswin_stream_t stream) {
+  CSWIN_REQUIRE(valid_dtype(dtype), CSWIN_ERR_INVALID, "linear_fwd: bad dtype %d", dtype);
+  CSWIN_REQUIRE(a && a->a && a->w && a->out, CSWIN_ERR_INVALID, "linear_fwd: null pointer");
+  CSWIN_REQUIRE(a->M >= 0 && a->N > 0 && a->K1 > 0 && a->K2 >= 0, CSWIN_ERR_INVALID, "linear_fwd: bad M/N/K");
+  CSWIN_REQUIRE((a->a2 != nullptr) == (a->K2 > 0), CSWIN_ERR_INVALID, "linear_fwd: a2 and K2 must be given together");
+  CSWIN_REQUIRE(a->lda >= a->K1 && a->ldw >= a->K1 + a->K2 && a->ldo >= a->N, CSWIN_ERR_INVALID, "linear_fwd: leading dimension too small");
+  CSWIN_REQUIRE(!a->a2 || a->lda2 >= a->K2, CSWIN_ERR_INVALID, "linear_fwd: lda2 too small");
+  CSWIN_REQUIRE(!a->residual || a->ldr >= a->N, CSWIN_ERR_INVALID, "linear_fwd: ldr too small");
+  CSWIN_REQUIRE((a->ln_gamma != nullptr) == (a->ln_beta != nullptr), CSWIN_ERR_INVALID, "linear_fwd: ln_gamma and ln_beta must be given together");
+  CSWIN_REQUIRE(!a->ln_gamma || !a->a2, CSWIN_ERR_INVALID, "linear_fwd: LayerNorm prologue needs a single A source");
+  CSWIN_REQUIRE(!a->sample_scale || a->rows_per_sample > 0, CSWIN_ERR_INVALID, "linear_fwd: rows_per_sample must be > 0");
+  CSWIN_REQUIRE(a->act == 0 || a->act == 1, CSWIN_ERR_INVALID, "linear_fwd: act must be 0 (none) or 1 (GELU)");
+  if (a->M == 0) return CSWIN_OK;
+  if (dtype == CSWIN_BF16) {
+    bool handled = false;
+    int rc = linear_fwd_tc(a, (cudaStream_t)stream, &handled);
+    if (rc != CSWIN_OK || handled) return rc;
+  }
+  return linear_fwd_simt(a, dtype, (cudaStream_t)stream);
+}
+
+int cswin_im2col_tokens(const void* x, int64_t x_bs, int64_t x_ts, void* col, int64_t ldcol, int32_t B, int32_t H,
+                        int32_t W, int32_t C, int32_t KH, int32_t KW, int32_t stride, int32_t pad, int32_t dtype,
+                        cswin_stream_t stream) {
+  CSWIN_REQUIRE(valid_dtype(dtype), CSWIN_ERR_INVALID, "im2col_tokens: bad dtype %d", dtype);
+  CSWIN_REQUIRE(B >= 0 && H > 0 && W > 0 && C > 0 && KH > 0 && KW > 0 && stride > 0 && pad >= 0, CSWIN_ERR_INVALID, "im2col_tokens: bad shape");
+  return im2col_tokens(x, x_bs, x_ts, col, ldcol, B, H, W, C, KH, KW, stride, pad, dtype, (cudaStream_t)stream);
+}
+
+int cswin_im2col_nchw(const void* x, int32_t x_is_f32, void* col, int64_t ldcol, int32_t B, int32_t C, int32_t H,
+                      int32_t W, int32_t KH, int32_t KW, int32_t stride, int32_t pad, int32_t dtype,
+                      cswin_stream_t stream) {
+  CSWIN_REQUIRE(valid_dtype(dtype), CSWIN_ERR_INVALID, "im2col_nchw: bad dtype %d", dtype);
+  CSWIN_REQUIRE(B >= 0 && H > 0 && W > 0 && C > 0 && KH > 0 && KW > 0 && stride > 0 && pad >= 0, CSWIN_ERR_INVALID, "im2col_nchw: bad shape");
+  return im2col_nchw(x, x_is_f32, col, ldcol, B, C, H, W, KH, KW, stride, pad, dtype, (cudaStream_t)stream);
+}
+
+int cswin_carafe_reassemble_fwd(const void* enc, int64_t ldenc, const void* z, int64_t ldz, const void* bias,
+                                void* y, int64_t ldy, int32_t nchw_out, int32_t y_is_f32, int32_t B, int32_t H,
+                                int32_t W, int32_t C, int32_t up, int32_t dtype, cswin_stream_t stream) {
+  CSWIN_REQUIRE(valid_dtype(dtype), CSWIN_ERR_INVALID, "carafe_reassemble_fwd: bad dtype %d", dtype);
+  CSWIN_REQUIRE(B >= 0 && H > 0 && W > 0 && C > 0, CSWIN_ERR_INVALID, "carafe_reassemble_fwd: bad shape");
+  return carafe_reassemble_fwd(enc, ldenc, z, ldz, bias, y, ldy, nchw_out, y_is_f32, B, H, W, C, up, dtype, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,86 @@
+// common.cuh — shared helpers for libcswin_b200.so (sm_100a only).
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+
+#include "../../include/cswin_b200.h"
+
+namespace cswin {
+
+// ---- error plumbing (thread-local message, never throws across the ABI) ----
+void set_error(const char* fmt, ...);
+extern std::atomic<uint64_t> g_launches;
+
+#define CSWIN_REQUIRE(cond, code, ...)            \
+  do {                                            \
+    if (!(cond)) {                                \
+      ::cswin::set_error(__VA_ARGS__);            \
+      return (code);                              \
+    }                                             \
+  } while (0)
+
+#define CSWIN_CUDA_OK(expr)                                                               \
+  do {                                                                                    \
+    cudaError_t _e = (expr);                                                              \
+    if (_e != cudaSuccess) {                                                              \
+      ::cswin::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return CSWIN_ERR_CUDA;                                                              \
+    }                                                                                     \
+  } while (0)
+
+// after a <<<>>> launch: count it and surface launch-configuration errors
+#define CSWIN_LAUNCH_CHECK()                      \
+  do {                                            \
+    ::cswin::g_launches.fetch_add(1, std::memory_order_relaxed); \
+    CSWIN_CUDA_OK(cudaGetLastError());            \
+  } while (0)
+
+int sm_count();   // SM count of the current device (cached)
+
+// ---- element access: T in {float, __nv_bfloat16}, arithmetic always fp32 ----
+template <typename T> __device__ __forceinline__ float ldf(const T* p);
+template <> __device__ __forceinline__ float ldf<float>(const float* p) { return *p; }
+template <> __device__ __forceinline__ float ldf<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+
+template <typename T> __device__ __forceinline__ void stf(T* p, float v);
+template <> __device__ __forceinline__ void stf<float>(float* p, float v) { *p = v; }
+template <> __device__ __forceinline__ void stf<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---- per-op launchers (defined in the .cu files, called by api.cu) ----
+int lepe_attention_fwd_simt(const cswin_lepe_branch_t* br, int nb, int B, int reso, float scale, int dtype, cudaStream_t s);
+int lepe_attention_fwd_tc(const cswin_lepe_branch_t* br, int nb, int B, int reso, float scale, cudaStream_t s, bool* handled);
+int lepe_attention_bwd_simt(const cswin_lepe_branch_grad_t* br, int nb, int B, int reso, float scale, int dtype, cudaStream_t s);
+int layernorm_fwd(const void* x, int64_t ldx, const void* g, const void* b, void* y, int64_t ldy, int64_t M, int C,
+                  float eps, float* mean, float* rstd, int dtype, cudaStream_t s);
+int linear_fwd_simt(const cswin_linear_args_t* a, int dtype, cudaStream_t s);
+int linear_fwd_tc(const cswin_linear_args_t* a, cudaStream_t s, bool* handled);
+int im2col_tokens(const void* x, int64_t x_bs, int64_t x_ts, void* col, int64_t ldcol, int B, int H, int W, int C, int KH,
+                  int KW, int stride, int pad, int dtype, cudaStream_t s);
+int im2col_nchw(const void* x, int x_is_f32, void* col, int64_t ldcol, int B, int C, int H, int W, int KH, int KW,
+                int stride, int pad, int dtype, cudaStream_t s);
+int carafe_reassemble_fwd(const void* enc, int64_t ldenc, const void* z, int64_t ldz, const void* bias, void* y,
+                          int64_t ldy, int nchw_out, int y_is_f32, int B, int H, int W, int C, int up, int dtype,
+                          cudaStream_t s);
+
+}  // namespace cswin

@@ -1,0 +1,182 @@
+// conv.cu — gathers that turn the convolutions of the hot path into Linear calls, and the CARAFE reassembly.
+//
+//  im2col_tokens : Merge_Block.conv (3x3 s2 p1, networks/cswin_unet.py:216) and CARAFE.encoder (3x3 s1 p1, :241)
+//                  straight from the token-major (B, L, C) activation — the reference first materialises an NCHW
+//                  copy (:214, :235); here channels stay innermost so every access is a contiguous C-vector.
+//  im2col_nchw   : stem conv (7x7 s4 p2, :339) from the NCHW network input.
+//  carafe_reassemble : pixel_shuffle + softmax over the 9 taps + 3x3 neighbourhood re-assembly + pixel_shuffle
+//                  (:242-263 / :292-313), run on the output of the 1x1 `out` conv taken at LOW resolution (see
+//                  cswin_b200.h).  All three are HBM-bound streaming kernels.
+#include "common.cuh"
+
+namespace cswin {
+namespace {
+
+template <typename T>
+__global__ void __launch_bounds__(256) im2col_tokens_kernel(const T* __restrict__ x, int64_t x_bs, int64_t x_ts,
+                                                             T* __restrict__ col, int64_t ldcol, int B, int H, int W,
+                                                             int C, int KH, int KW, int stride, int pad, int Ho, int Wo) {
+  // one thread per (output pixel, tap, 8-channel chunk); C % 8 == 0 is guaranteed by the launcher
+  const int cv = C >> 3;
+  const int64_t total = (int64_t)B * Ho * Wo * KH * KW * cv;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % cv);
+    int64_t r = i / cv;
+    const int tap = (int)(r % (KH * KW)); r /= (KH * KW);
+    const int ox = (int)(r % Wo); r /= Wo;
+    const int oy = (int)(r % Ho);
+    const int b = (int)(r / Ho);
+    const int ky = tap / KW, kx = tap - ky * KW;
+    const int iy = oy * stride - pad + ky, ix = ox * stride - pad + kx;
+    T* dst = col + ((int64_t)(b * Ho + oy) * Wo + ox) * ldcol + (int64_t)tap * C + c8 * 8;
+    if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
+      const T* src = x + (int64_t)b * x_bs + ((int64_t)iy * W + ix) * x_ts + c8 * 8;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dst[j] = src[j];
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) stf(dst + j, 0.f);
+    }
+  }
+}
+
+template <typename TI, typename T>
+__global__ void __launch_bounds__(256) im2col_nchw_kernel(const TI* __restrict__ x, T* __restrict__ col, int64_t ldcol,
+                                                           int B, int C, int H, int W, int KH, int KW, int stride,
+                                                           int pad, int Ho, int Wo) {
+  const int K = C * KH * KW;
+  const int64_t total = (int64_t)B * Ho * Wo * ldcol;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int k = (int)(i % ldcol);
+    int64_t r = i / ldcol;
+    const int ox = (int)(r % Wo); r /= Wo;
+    const int oy = (int)(r % Ho);
+    const int b = (int)(r / Ho);
+    float v = 0.f;
+    if (k < K) {
+      const int c = k / (KH * KW);
+      const int t = k - c * KH * KW;
+      const int ky = t / KW, kx = t - ky * KW;
+      const int iy = oy * stride - pad + ky, ix = ox * stride - pad + kx;
+      if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = ldf(x + (((int64_t)b * C + c) * H + iy) * W + ix);
+    }
+    stf(col + i, v);
+  }
+}
+
+// One CTA per low-resolution pixel: its 9 neighbour rows of z and its 9 s^2 encoder logits are staged once in
+// shared memory and feed the s^2 output pixels it owns.
+template <typename T, typename TO>
+__global__ void __launch_bounds__(128) carafe_reassemble_kernel(const T* __restrict__ enc, int64_t ldenc,
+                                                                 const T* __restrict__ z, int64_t ldz,
+                                                                 const T* __restrict__ bias, TO* __restrict__ y,
+                                                                 int64_t ldy, int nchw_out, int B, int H, int W, int C,
+                                                                 int up) {
+  extern __shared__ float sm[];
+  const int s2 = up * up;
+  float* Zs = sm;                 // [9][C]
+  float* Kp = Zs + 9 * C;         // [s2][9] softmaxed taps
+  const int pix = blockIdx.x;     // (b, y, x)
+  const int x0 = pix % W;
+  const int y0 = (pix / W) % H;
+  const int b = pix / (W * H);
+  const int tid = threadIdx.x;
+
+  for (int i = tid; i < 9 * C; i += blockDim.x) {
+    const int t = i / C, c = i - t * C;
+    const int yy = y0 + t / 3 - 1, xx = x0 + t % 3 - 1;
+    float v = 0.f;
+    if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = ldf(z + ((int64_t)(b * H + yy) * W + xx) * ldz + c);
+    Zs[i] = v;
+  }
+  if (tid < s2) {
+    const T* e = enc + (int64_t)pix * ldenc + tid;        // channel t*s2 + (a*up+e)
+    float l[9];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) { l[t] = ldf(e + t * s2); mx = fmaxf(mx, l[t]); }
+    float sum = 0.f;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) { l[t] = expf(l[t] - mx); sum += l[t]; }
+    const float inv = 1.0f / sum;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) Kp[tid * 9 + t] = l[t] * inv;
+  }
+  __syncthreads();
+
+  const int Ho = H * up, Wo = W * up;
+  for (int i = tid; i < s2 * C; i += blockDim.x) {
+    const int ae = i / C, c = i - ae * C;
+    const int a = ae / up, e = ae - a * up;
+    float acc = ldf(bias + c);
+#pragma unroll
+    for (int t = 0; t < 9; ++t) acc = fmaf(Kp[ae * 9 + t], Zs[t * C + c], acc);
+    const int oy = y0 * up + a, ox = x0 * up + e;
+    if (nchw_out) stf(y + (((int64_t)b * C + c) * Ho + oy) * Wo + ox, acc);
+    else          stf(y + ((int64_t)(b * Ho + oy) * Wo + ox) * ldy + c, acc);
+  }
+}
+
+}  // namespace
+
+int im2col_tokens(const void* x, int64_t x_bs, int64_t x_ts, void* col, int64_t ldcol, int B, int H, int W, int C, int KH,
+                  int KW, int stride, int pad, int dtype, cudaStream_t s) {
+  CSWIN_REQUIRE(x && col, CSWIN_ERR_INVALID, "im2col_tokens: null pointer");
+  CSWIN_REQUIRE(C % 8 == 0, CSWIN_ERR_UNSUPPORTED, "im2col_tokens: C=%d must be a multiple of 8", C);
+  CSWIN_REQUIRE(ldcol >= (int64_t)KH * KW * C, CSWIN_ERR_INVALID, "im2col_tokens: ldcol too small");
+  const int Ho = (H + 2 * pad - KH) / stride + 1, Wo = (W + 2 * pad - KW) / stride + 1;
+  const int64_t total = (int64_t)B * Ho * Wo * KH * KW * (C / 8);
+  if (total == 0) return CSWIN_OK;
+  const unsigned grid = (unsigned)std::min<int64_t>(ceil_div64(total, 256), (int64_t)sm_count() * 16);
+  if (dtype == CSWIN_F32)
+    im2col_tokens_kernel<float><<<grid, 256, 0, s>>>((const float*)x, x_bs, x_ts, (float*)col, ldcol, B, H, W, C, KH, KW, stride, pad, Ho, Wo);
+  else
+    im2col_tokens_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)x, x_bs, x_ts, (__nv_bfloat16*)col, ldcol, B, H, W, C, KH, KW, stride, pad, Ho, Wo);
+  CSWIN_LAUNCH_CHECK();
+  return CSWIN_OK;
+}
+
+int im2col_nchw(const void* x, int x_is_f32, void* col, int64_t ldcol, int B, int C, int H, int W, int KH, int KW,
+                int stride, int pad, int dtype, cudaStream_t s) {
+  CSWIN_REQUIRE(x && col, CSWIN_ERR_INVALID, "im2col_nchw: null pointer");
+  CSWIN_REQUIRE(ldcol >= (int64_t)C * KH * KW, CSWIN_ERR_INVALID, "im2col_nchw: ldcol too small");
+  const int Ho = (H + 2 * pad - KH) / stride + 1, Wo = (W + 2 * pad - KW) / stride + 1;
+  const int64_t total = (int64_t)B * Ho * Wo * ldcol;
+  if (total == 0) return CSWIN_OK;
+  const unsigned grid = (unsigned)std::min<int64_t>(ceil_div64(total, 256), (int64_t)sm_count() * 16);
+  if (dtype == CSWIN_F32) {
+    CSWIN_REQUIRE(x_is_f32, CSWIN_ERR_INVALID, "im2col_nchw: fp32 path needs an fp32 image");
+    im2col_nchw_kernel<float, float><<<grid, 256, 0, s>>>((const float*)x, (float*)col, ldcol, B, C, H, W, KH, KW, stride, pad, Ho, Wo);
+  } else if (x_is_f32) {
+    im2col_nchw_kernel<float, __nv_bfloat16><<<grid, 256, 0, s>>>((const float*)x, (__nv_bfloat16*)col, ldcol, B, C, H, W, KH, KW, stride, pad, Ho, Wo);
+  } else {
+    im2col_nchw_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)col, ldcol, B, C, H, W, KH, KW, stride, pad, Ho, Wo);
+  }
+  CSWIN_LAUNCH_CHECK();
+  return CSWIN_OK;
+}
+
+int carafe_reassemble_fwd(const void* enc, int64_t ldenc, const void* z, int64_t ldz, const void* bias, void* y,
+                          int64_t ldy, int nchw_out, int y_is_f32, int B, int H, int W, int C, int up, int dtype,
+                          cudaStream_t s) {
+  CSWIN_REQUIRE(enc && z && bias && y, CSWIN_ERR_INVALID, "carafe_reassemble: null pointer");
+  CSWIN_REQUIRE(up >= 1 && up * up <= 128, CSWIN_ERR_UNSUPPORTED, "carafe_reassemble: up=%d not supported", up);
+  CSWIN_REQUIRE(ldenc >= 9 * up * up && ldz >= C, CSWIN_ERR_INVALID, "carafe_reassemble: leading dimension too small");
+  const int64_t pixels = (int64_t)B * H * W;
+  if (pixels == 0) return CSWIN_OK;
+  const size_t smem = sizeof(float) * ((size_t)9 * C + (size_t)up * up * 9);
+  CSWIN_REQUIRE(smem <= 48 * 1024, CSWIN_ERR_UNSUPPORTED, "carafe_reassemble: C=%d too large", C);
+  const unsigned grid = (unsigned)pixels;
+  if (dtype == CSWIN_F32) {
+    CSWIN_REQUIRE(y_is_f32, CSWIN_ERR_INVALID, "carafe_reassemble: fp32 path writes fp32");
+    carafe_reassemble_kernel<float, float><<<grid, 128, smem, s>>>((const float*)enc, ldenc, (const float*)z, ldz, (const float*)bias, (float*)y, ldy, nchw_out, B, H, W, C, up);
+  } else if (y_is_f32) {
+    carafe_reassemble_kernel<__nv_bfloat16, float><<<grid, 128, smem, s>>>((const __nv_bfloat16*)enc, ldenc, (const __nv_bfloat16*)z, ldz, (const __nv_bfloat16*)bias, (float*)y, ldy, nchw_out, B, H, W, C, up);
+  } else {
+    carafe_reassemble_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 128, smem, s>>>((const __nv_bfloat16*)enc, ldenc, (const __nv_bfloat16*)z, ldz, (const __nv_bfloat16*)bias, (__nv_bfloat16*)y, ldy, nchw_out, B, H, W, C, up);
+  }
+  CSWIN_LAUNCH_CHECK();
+  return CSWIN_OK;
+}
+
+}  // namespace cswin

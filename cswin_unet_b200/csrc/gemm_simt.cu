@@ -1,0 +1,143 @@
+// gemm_simt.cu — fp32-arithmetic Linear with fused LayerNorm prologue and bias / GELU / residual / DropPath epilogue.
+//
+// The exact-arithmetic (CSWIN_F32) path of cswin_linear_fwd, and the general-shape path for operand layouts the
+// tcgen05 kernel (gemm_tc.cu) does not take.  C[M,N] = A[M,K] W[N,K]^T with both operands K-contiguous; a
+// 64x64x16 tile per 256-thread CTA, 4x4 register micro-tile per thread, operands transposed into shared memory
+// as [k][m] so the inner product reads float4s.
+//
+// Replaces nn.Linear and the element-wise ops the reference runs as separate kernels around it:
+// networks/cswin_unet.py:168-169 (norm1+qkv), :177-178 (proj, +res, DropPath), :179 + Mlp :22-26 (norm2, fc1, GELU,
+// fc2, +res, DropPath), :509-510 etc. (cat + concat_linear as a two-source K loop).
+#include "common.cuh"
+
+namespace cswin {
+namespace {
+
+constexpr int BM = 64, BN = 64, BK = 16, PADM = 4;
+
+template <typename T>
+struct GemmParams {
+  const T* a; int64_t lda; int K1;
+  const T* a2; int64_t lda2; int K2;
+  const T* w; int64_t ldw;
+  const T* bias;
+  const T* ln_g; const T* ln_b; float ln_eps;
+  const T* res; int64_t ldr;
+  const float* sscale; int rps;
+  T* out; int64_t ldo;
+  int64_t M; int N; int act;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) linear_simt_kernel(const GemmParams<T> P) {
+  __shared__ float As[BK][BM + PADM];
+  __shared__ float Ws[BK][BN + PADM];
+  __shared__ float s_mean[BM], s_rstd[BM];
+
+  const int tid = threadIdx.x;
+  const int64_t m0 = (int64_t)blockIdx.x * BM;
+  const int n0 = blockIdx.y * BN;
+  const int K = P.K1 + P.K2;
+
+  if (P.ln_g != nullptr) {                       // LayerNorm prologue: per-row statistics over K1
+    const int lane = tid & 31, w = tid >> 5;
+    for (int r = w; r < BM; r += 8) {
+      const int64_t m = m0 + r;
+      float mean = 0.f, rstd = 0.f;
+      if (m < P.M) {
+        const T* ar = P.a + m * P.lda;
+        float s = 0.f;
+        for (int k = lane; k < P.K1; k += 32) s += ldf(ar + k);
+        mean = warp_sum(s) / (float)P.K1;
+        float q = 0.f;
+        for (int k = lane; k < P.K1; k += 32) { const float dlt = ldf(ar + k) - mean; q = fmaf(dlt, dlt, q); }
+        rstd = rsqrtf(warp_sum(q) / (float)P.K1 + P.ln_eps);
+      }
+      if (lane == 0) { s_mean[r] = mean; s_rstd[r] = rstd; }
+    }
+    __syncthreads();
+  }
+
+  const int tx = tid & 15, ty = tid >> 4;        // micro-tile: rows ty*4.., cols tx*4..
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  const int lr = tid >> 2;                       // 0..63 : tile row loaded by this thread
+  const int lk = (tid & 3) * 4;                  // 0,4,8,12 : first of its 4 k's
+  for (int k0 = 0; k0 < K; k0 += BK) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int k = k0 + lk + i;
+      const int64_t m = m0 + lr;
+      float va = 0.f;
+      if (m < P.M && k < K) {
+        if (k < P.K1) {
+          va = ldf(P.a + m * P.lda + k);
+          if (P.ln_g != nullptr) va = (va - s_mean[lr]) * s_rstd[lr] * ldf(P.ln_g + k) + ldf(P.ln_b + k);
+        } else {
+          va = ldf(P.a2 + m * P.lda2 + (k - P.K1));
+        }
+      }
+      As[lk + i][lr] = va;
+      const int n = n0 + lr;
+      Ws[lk + i][lr] = (n < P.N && k < K) ? ldf(P.w + (int64_t)n * P.ldw + k) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      const float4 av = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+      const float4 wv = *reinterpret_cast<const float4*>(&Ws[kk][tx * 4]);
+      const float a4[4] = {av.x, av.y, av.z, av.w};
+      const float w4[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a4[i], w4[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t m = m0 + ty * 4 + i;
+    if (m >= P.M) continue;
+    const float sc = P.sscale ? P.sscale[m / P.rps] : 1.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= P.N) continue;
+      float t = acc[i][j] + (P.bias ? ldf(P.bias + n) : 0.f);
+      if (P.act == 1) t = gelu_erf(t);
+      t *= sc;
+      if (P.res) t += ldf(P.res + m * P.ldr + n);
+      stf(P.out + m * P.ldo + n, t);
+    }
+  }
+}
+
+template <typename T>
+int launch(const cswin_linear_args_t* a, cudaStream_t s) {
+  GemmParams<T> P;
+  P.a = (const T*)a->a; P.lda = a->lda; P.K1 = a->K1;
+  P.a2 = (const T*)a->a2; P.lda2 = a->lda2; P.K2 = a->K2;
+  P.w = (const T*)a->w; P.ldw = a->ldw; P.bias = (const T*)a->bias;
+  P.ln_g = (const T*)a->ln_gamma; P.ln_b = (const T*)a->ln_beta; P.ln_eps = a->ln_eps;
+  P.res = (const T*)a->residual; P.ldr = a->ldr; P.sscale = a->sample_scale; P.rps = a->rows_per_sample;
+  P.out = (T*)a->out; P.ldo = a->ldo; P.M = a->M; P.N = a->N; P.act = a->act;
+  dim3 grid((unsigned)ceil_div64(a->M, BM), (unsigned)((a->N + BN - 1) / BN));
+  linear_simt_kernel<T><<<grid, 256, 0, s>>>(P);
+  CSWIN_LAUNCH_CHECK();
+  return CSWIN_OK;
+}
+
+}  // namespace
+
+int linear_fwd_simt(const cswin_linear_args_t* a, int dtype, cudaStream_t s) {
+  if (dtype == CSWIN_F32) return launch<float>(a, s);
+  return launch<__nv_bfloat16>(a, s);
+}
+
+}  // namespace cswin

@@ -1,0 +1,204 @@
+"""Host graph of CSWin-UNet built from the native modules.
+
+`CSWinTransformer` keeps the reference's constructor signature, sub-module names and the exact 463-key
+state_dict of /root/reference/networks/cswin_unet.py:322-554 (checked against the reference's key list in
+tests/golden/model_t224.npz), so checkpoints move both ways with `strict=True`.  The reference file cannot be
+shipped to the GPU box, so this assembly is what bench.py and the parity tests run there; in a checkout of the
+reference, `cswin_unet_b200.install()` swaps the hot-path classes into the reference's own assembly instead.
+
+Differences in *how* (not what) the forward is computed, all exact in real arithmetic:
+  * stem conv 7x7/4 as an im2col gather + Linear + LayerNorm (:338-342);
+  * skip `torch.cat` + `concat_linear` as one Linear with two A sources (:509-510, :518-519, :526-527);
+  * head: CARAFE4 `out` (64->64, bias) and `output` (64->classes, no bias) are folded into one 64->classes map
+    applied at 56x56 before the re-assembly, which writes NCHW logits directly (:536-544).
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import ops
+from .modules import CARAFE, CARAFE4, CSWinBlock, Merge_Block, _Native, _no_autograd
+
+Tensor = torch.Tensor
+
+
+class CSWinTransformer(_Native):
+    def __init__(self, img_size=224, patch_size=16, in_chans=3, num_classes=8, embed_dim=64, depth=[1, 2, 9, 1],
+                 split_size=[1, 2, 7, 7], num_heads=12, mlp_ratio=4., qkv_bias=True, qk_scale=None, drop_rate=0.,
+                 attn_drop_rate=0., drop_path_rate=0, hybrid_backbone=None, norm_layer=nn.LayerNorm, use_chk=False):
+        super().__init__()
+        if use_chk:
+            raise NotImplementedError("use_chk: activation checkpointing is never enabled by the reference wrapper")
+        self.use_chk = use_chk
+        self.compute_dtype: Optional[torch.dtype] = None   # None: follow the input dtype; torch.bfloat16: tcgen05 path
+        self.img_size = img_size
+        self.num_classes = num_classes
+        self.num_features = self.embed_dim = embed_dim
+        heads = num_heads
+        depth = list(depth)
+
+        self.stage1_conv_embed = nn.Sequential(
+            nn.Conv2d(in_chans, embed_dim, 7, 4, 2),
+            nn.Identity(),                       # the reference's einops Rearrange('b c h w -> b (h w) c') (no params)
+            nn.LayerNorm(embed_dim))
+        self.pos_drop = nn.Dropout(p=drop_rate)
+        dpr = [x.item() for x in torch.linspace(0, drop_path_rate, int(np.sum(depth)))]
+
+        def blocks(dim, heads_i, reso, split, first, n, last=False):
+            return nn.ModuleList([
+                CSWinBlock(dim=dim, num_heads=heads_i, reso=reso, mlp_ratio=mlp_ratio, qkv_bias=qkv_bias,
+                           qk_scale=qk_scale, split_size=split, drop=drop_rate, attn_drop=attn_drop_rate,
+                           drop_path=dpr[first + i], norm_layer=norm_layer, last_stage=last) for i in range(n)])
+
+        off = [0, depth[0], depth[0] + depth[1], depth[0] + depth[1] + depth[2]]
+        d = embed_dim
+        self.stage1 = blocks(d, heads[0], img_size // 4, split_size[0], off[0], depth[0])
+        self.merge1 = Merge_Block(d, d * 2)
+        self.stage2 = blocks(d * 2, heads[1], img_size // 8, split_size[1], off[1], depth[1])
+        self.merge2 = Merge_Block(d * 2, d * 4)
+        self.stage3 = blocks(d * 4, heads[2], img_size // 16, split_size[2], off[2], depth[2])
+        self.merge3 = Merge_Block(d * 4, d * 8)
+        self.stage4 = blocks(d * 8, heads[3], img_size // 32, split_size[-1], off[3], depth[-1], last=True)
+        self.norm = norm_layer(d * 8)
+
+        self.stage_up4 = blocks(d * 8, heads[3], img_size // 32, split_size[-1], off[3], depth[-1], last=True)
+        self.upsample4 = CARAFE(d * 8, d * 4)
+        self.concat_linear4 = nn.Linear(512, 256)          # hard-coded in the reference (:404) -> embed_dim is 64
+        self.stage_up3 = blocks(d * 4, heads[2], img_size // 16, split_size[2], off[2], depth[2])
+        self.upsample3 = CARAFE(d * 4, d * 2)
+        self.concat_linear3 = nn.Linear(256, 128)
+        self.stage_up2 = blocks(d * 2, heads[1], img_size // 8, split_size[1], off[1], depth[1])
+        self.upsample2 = CARAFE(d * 2, d)
+        self.concat_linear2 = nn.Linear(128, 64)
+        self.stage_up1 = blocks(d, heads[0], img_size // 4, split_size[0], off[0], depth[0])
+        self.upsample1 = CARAFE4(d, 64)
+        self.norm_up = norm_layer(embed_dim)
+        self.output = nn.Conv2d(in_channels=embed_dim, out_channels=self.num_classes, kernel_size=1, bias=False)
+        self.apply(self._init_weights)
+
+    def _init_weights(self, m):
+        if isinstance(m, nn.Linear):
+            nn.init.trunc_normal_(m.weight, std=.02)
+            if m.bias is not None:
+                nn.init.constant_(m.bias, 0)
+        elif isinstance(m, nn.LayerNorm):
+            nn.init.constant_(m.bias, 0)
+            nn.init.constant_(m.weight, 1.0)
+
+    # ---- pieces -------------------------------------------------------------------------------
+    def _stem(self, x: Tensor, dt: torch.dtype) -> Tensor:
+        conv, ln = self.stage1_conv_embed[0], self.stage1_conv_embed[2]
+        B = x.shape[0]
+        K = conv.weight[0].numel()
+        Kp = (K + 7) // 8 * 8                               # row pitch multiple of 16 B for the bf16 TMA path
+        wk = self._w("stem.w", conv.weight, dt, lambda t: torch.nn.functional.pad(t.reshape(t.shape[0], -1), (0, Kp - K)))
+        col = ops.im2col_nchw(x, 7, 7, 4, 2, Kp, dt)
+        y = ops.linear(col, wk, self._w("stem.b", conv.bias, dt))
+        y = ops.layernorm(y, self._w("stem.n.w", ln.weight, dt), self._w("stem.n.b", ln.bias, dt), ln.eps)
+        return y.view(B, -1, y.shape[-1])
+
+    def _skip_linear(self, lin: nn.Linear, skip: Tensor, x: Tensor, key: str) -> Tensor:
+        dt = x.dtype
+        return ops.linear(skip, self._w(key + ".w", lin.weight, dt), self._w(key + ".b", lin.bias, dt), a2=x)
+
+    def _ln(self, ln: nn.LayerNorm, x: Tensor, key: str) -> Tensor:
+        dt = x.dtype
+        return ops.layernorm(x, self._w(key + ".w", ln.weight, dt), self._w(key + ".b", ln.bias, dt), ln.eps)
+
+    def forward_features(self, x: Tensor) -> Tensor:
+        dt = self.compute_dtype or x.dtype
+        if dt not in (torch.float32, torch.bfloat16):
+            raise TypeError(f"compute dtype must be float32 or bfloat16, got {dt}")
+        x = self._stem(x, dt)
+        for blk in self.stage1:
+            x = blk(x)
+        self.x1 = x
+        x = self.merge1(x)
+        for blk in self.stage2:
+            x = blk(x)
+        self.x2 = x
+        x = self.merge2(x)
+        for blk in self.stage3:
+            x = blk(x)
+        self.x3 = x
+        x = self.merge3(x)
+        for blk in self.stage4:
+            x = blk(x)
+        return self._ln(self.norm, x, "norm")
+
+    def forward_up_features(self, x: Tensor) -> Tensor:
+        for blk in self.stage_up4:
+            x = blk(x)
+        x = self._skip_linear(self.concat_linear4, self.x3, self.upsample4(x), "cl4")
+        for blk in self.stage_up3:
+            x = blk(x)
+        x = self._skip_linear(self.concat_linear3, self.x2, self.upsample3(x), "cl3")
+        for blk in self.stage_up2:
+            x = blk(x)
+        x = self._skip_linear(self.concat_linear2, self.x1, self.upsample2(x), "cl2")
+        for blk in self.stage_up1:
+            x = blk(x)
+        return self._ln(self.norm_up, x, "norm_up")
+
+    def up_x4(self, x: Tensor, logits_dtype: Optional[torch.dtype] = None) -> Tensor:
+        """CARAFE4 + output conv with the two 1x1 maps folded; returns NCHW logits (B, classes, 4H, 4W)."""
+        B, L, Cn = x.shape
+        H = W = int(round(L ** 0.5))
+        up = self.upsample1
+        dt = x.dtype
+        enc = up._kernel_logits(x, H, W)
+        wo = self.output.weight
+        wf = self._w("head.w", (wo, up.out.weight), dt,
+                     lambda o, u: o.reshape(o.shape[0], -1).float() @ u.reshape(u.shape[0], -1).float())
+        bf = self._w("head.b", (wo, up.out.bias), dt, lambda o, b: o.reshape(o.shape[0], -1).float() @ b.float())
+        z = ops.linear(x, wf)                                                   # (B, L, classes)
+        return ops.carafe_reassemble(enc, z.view(B * L, -1), bf, B, H, W, up.up_factor, nchw_out=True,
+                                     out_dtype=logits_dtype or dt)
+
+    def forward(self, x: Tensor) -> Tensor:
+        _no_autograd(x, self.output.weight)
+        x = self.forward_features(x)
+        x = self.forward_up_features(x)
+        return self.up_x4(x)
+
+
+class CSwinUnet(nn.Module):
+    """Counterpart of networks/vision_transformer.py:17-43 without the yacs dependency: takes either a config
+    object with the reference's attribute tree or plain keyword hyper-parameters (cswin_tiny_224_lite defaults:
+    configs/cswin_tiny_224_lite.yaml:4-10, config.py:49-66).  Unlike the reference it does not write
+    `cswin_unet.pth` into the CWD at construction."""
+
+    def __init__(self, config=None, img_size=224, num_classes=9, zero_head=False, vis=False, **kw):
+        super().__init__()
+        self.num_classes = num_classes
+        self.zero_head = zero_head
+        self.config = config
+        if config is not None:
+            c = config.MODEL.CSWIN
+            hp = dict(img_size=config.DATA.IMG_SIZE, patch_size=c.PATCH_SIZE, in_chans=c.IN_CHANS, embed_dim=c.EMBED_DIM,
+                      depth=c.DEPTH, split_size=c.SPLIT_SIZE, num_heads=c.NUM_HEADS, mlp_ratio=c.MLP_RATIO,
+                      qkv_bias=c.QKV_BIAS, qk_scale=c.QK_SCALE, drop_rate=config.MODEL.DROP_RATE,
+                      drop_path_rate=config.MODEL.DROP_PATH_RATE)
+        else:
+            hp = dict(img_size=img_size, patch_size=4, in_chans=3, embed_dim=64, depth=[1, 2, 9, 1],
+                      split_size=[1, 2, 7, 7], num_heads=[2, 4, 8, 16], mlp_ratio=4., qkv_bias=True, qk_scale=None,
+                      drop_rate=0., drop_path_rate=0.2)
+        hp.update(kw)
+        self.cswin_unet = CSWinTransformer(num_classes=self.num_classes, **hp)
+
+    def forward(self, x: Tensor) -> Tensor:
+        if x.size()[1] == 1:
+            x = x.repeat(1, 3, 1, 1)
+        return self.cswin_unet(x)
+
+
+def cswin_tiny_224(num_classes: int = 9, img_size: int = 224, **kw) -> CSWinTransformer:
+    hp = dict(img_size=img_size, patch_size=4, in_chans=3, num_classes=num_classes, embed_dim=64, depth=[1, 2, 9, 1],
+              split_size=[1, 2, 7, 7], num_heads=[2, 4, 8, 16], mlp_ratio=4., qkv_bias=True, qk_scale=None,
+              drop_rate=0., drop_path_rate=0.2)
+    hp.update(kw)
+    return CSWinTransformer(**hp)

@@ -1,0 +1,371 @@
+"""Drop-in nn.Modules for the CSWin-UNet hot path, backed by libcswin_b200.so.
+
+Same class names, constructor signatures / defaults, public attributes, sub-module names and
+state_dict keys as the reference classes in /root/reference/networks/cswin_unet.py
+(`LePEAttention` :31-109, `CSWinBlock` :112-181, `Mlp` :12-28, `Merge_Block` :205-220,
+`CARAFE` :222-269, `CARAFE4` :272-319, free functions `img2windows` :184-191 / `windows2img`
+:194-202), so `load_state_dict(strict=True)` works both ways and `install()` (install.py) can
+rebind them inside the reference's own module.  Parameters are ordinary nn.Parameters held by
+nn.Linear / nn.Conv2d / nn.LayerNorm containers that are never *called*: every forward goes
+through the C ABI.  Compute dtype = dtype of the incoming activation (float32 -> exact SIMT
+path, bfloat16 -> tcgen05 path); parameters of another dtype are cast through a cache keyed on
+`param._version` (re-derived every call in training mode, where in-place `.data` writes are
+common and do not bump the version).
+"""
+from __future__ import annotations
+
+import math
+from typing import Callable, Dict, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import ops
+
+Tensor = torch.Tensor
+
+
+# ------------------------------------------------------------------------------------------
+# helpers
+# ------------------------------------------------------------------------------------------
+class DropPath(nn.Module):
+    """Stochastic depth with timm's semantics and RNG consumption (one bernoulli_ of shape (B,1,..,1) in x.dtype)."""
+
+    def __init__(self, drop_prob: float = 0., scale_by_keep: bool = True):
+        super().__init__()
+        self.drop_prob = drop_prob
+        self.scale_by_keep = scale_by_keep
+
+    def sample_scale(self, x: Tensor) -> Optional[Tensor]:
+        """fp32 (B,) per-sample factor m_b/(1-p), or None when inactive (eval or p == 0)."""
+        if self.drop_prob == 0. or not self.training:
+            return None
+        keep = 1.0 - self.drop_prob
+        m = x.new_empty((x.shape[0],) + (1,) * (x.ndim - 1)).bernoulli_(keep)
+        if keep > 0.0 and self.scale_by_keep:
+            m.div_(keep)
+        return m.reshape(-1).float()
+
+    def forward(self, x: Tensor) -> Tensor:      # only used if someone calls the module directly
+        s = self.sample_scale(x)
+        return x if s is None else x * s.to(x.dtype).view((-1,) + (1,) * (x.ndim - 1))
+
+    def extra_repr(self):
+        return f"drop_prob={round(self.drop_prob, 3):0.3f}"
+
+
+class _Derived:
+    """Cache of tensors derived from parameters (dtype casts, re-packed conv weights)."""
+
+    def __init__(self):
+        self._d: Dict[str, Tuple[tuple, Tensor]] = {}
+
+    def get(self, key: str, params, dtype: torch.dtype, fn: Optional[Callable] = None, fresh: bool = False) -> Tensor:
+        if isinstance(params, Tensor):
+            params = (params,)
+        if fn is None and params[0].dtype == dtype and params[0].is_contiguous():
+            return params[0].detach()                    # read the parameter in place: can never go stale
+        sig = tuple((p._version, p.data_ptr(), p.device) for p in params) + (dtype,)
+        hit = self._d.get(key)
+        if not fresh and hit is not None and hit[0] == sig:
+            return hit[1]
+        with torch.no_grad():
+            src = [p.detach() for p in params]
+            t = fn(*src) if fn is not None else src[0]
+            t = t.to(dtype).contiguous()
+        self._d[key] = (sig, t)
+        return t
+
+    def clear(self):
+        self._d.clear()
+
+
+class _Native(nn.Module):
+    """Base: owns a derived-weight cache that is not part of state_dict and is dropped on deepcopy / pickling."""
+
+    def __init__(self):
+        super().__init__()
+        object.__setattr__(self, "_derived", _Derived())
+
+    def _w(self, key: str, params, dtype, fn=None) -> Tensor:
+        return self._derived.get(key, params, dtype, fn, fresh=self.training)
+
+    def __getstate__(self):
+        st = self.__dict__.copy()
+        st.pop("_derived", None)
+        return st
+
+    def __setstate__(self, st):
+        self.__dict__.update(st)
+        object.__setattr__(self, "_derived", _Derived())
+
+    def __deepcopy__(self, memo):
+        import copy
+        cls = self.__class__
+        new = cls.__new__(cls)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            if k != "_derived":
+                new.__dict__[k] = copy.deepcopy(v, memo)
+        object.__setattr__(new, "_derived", _Derived())
+        return new
+
+    def _replicate_for_data_parallel(self):
+        rep = super()._replicate_for_data_parallel()
+        object.__setattr__(rep, "_derived", _Derived())
+        return rep
+
+
+def _no_autograd(*ts: Tensor):
+    if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in ts):
+        raise NotImplementedError(
+            "cswin_unet_b200: this op has no native backward kernel yet; run it under torch.no_grad() "
+            "(there is deliberately no autograd fallback through library ops)")
+
+
+def img2windows(img: Tensor, H_sp: int, W_sp: int) -> Tensor:
+    """(B,C,H,W) -> (B*nWin, H_sp*W_sp, C); window id b*nH*nW + ih*nW + iw, token id r*W_sp + c.
+    API-compat helper (cswin_unet.py:184-191); the kernels never materialise this layout."""
+    B, Cn, H, W = img.shape
+    t = img.reshape(B, Cn, H // H_sp, H_sp, W // W_sp, W_sp)
+    return t.permute(0, 2, 4, 3, 5, 1).reshape(-1, H_sp * W_sp, Cn)
+
+
+def windows2img(img_splits_hw: Tensor, H_sp: int, W_sp: int, H: int, W: int) -> Tensor:
+    """Inverse of img2windows, returning (B,H,W,C) (cswin_unet.py:194-202)."""
+    nwin = (H // H_sp) * (W // W_sp)
+    B = img_splits_hw.shape[0] // nwin
+    t = img_splits_hw.reshape(B, H // H_sp, W // W_sp, H_sp, W_sp, -1)
+    return t.permute(0, 1, 3, 2, 4, 5).reshape(B, H, W, -1)
+
+
+# ------------------------------------------------------------------------------------------
+# LePEAttention
+# ------------------------------------------------------------------------------------------
+class LePEAttention(_Native):
+    """Cross-shaped-window attention branch with locally-enhanced positional encoding (cswin_unet.py:31-109)."""
+
+    def __init__(self, dim, resolution, idx, split_size, dim_out=None, num_heads=9, attn_drop=0., proj_drop=0.,
+                 qk_scale=None):
+        super().__init__()
+        self.dim = dim
+        self.dim_out = dim_out or dim
+        self.resolution = resolution
+        self.split_size = split_size
+        self.num_heads = num_heads
+        head_dim = dim // num_heads
+        self.scale = qk_scale or head_dim ** -0.5
+        if idx == -1:
+            H_sp, W_sp = resolution, resolution
+        elif idx == 0:
+            H_sp, W_sp = resolution, split_size
+        elif idx == 1:
+            W_sp, H_sp = resolution, split_size
+        else:
+            raise ValueError(f"LePEAttention: idx must be -1, 0 or 1 (got {idx})")   # reference prints and exit(0)s
+        self.idx = idx
+        self.H_sp = H_sp
+        self.W_sp = W_sp
+        self.get_v = nn.Conv2d(dim, dim, kernel_size=3, stride=1, padding=1, groups=dim)   # parameter container
+        self.attn_drop = nn.Dropout(attn_drop)
+
+    def _check(self, L: int):
+        H = W = self.resolution
+        assert L == H * W, "flatten img_tokens has wrong size"
+        if H % self.H_sp or W % self.W_sp:
+            raise RuntimeError(f"LePEAttention: resolution {H} is not divisible by the stripe window "
+                               f"{self.H_sp}x{self.W_sp}")
+        if self.training and self.attn_drop.p > 0:
+            raise NotImplementedError("LePEAttention: attn_drop > 0 is not supported by the fused kernel "
+                                      "(the reference never sets it: vision_transformer.py:23-35)")
+
+    def branch_desc(self, q: Tensor, k: Tensor, v: Tensor, out: Tensor, lse: Optional[Tensor] = None) -> dict:
+        dt = q.dtype
+        return dict(q=q, k=k, v=v, out=out, conv_w=self._w("cw", self.get_v.weight, dt),
+                    conv_b=self._w("cb", self.get_v.bias, dt), heads=self.num_heads, H_sp=self.H_sp, W_sp=self.W_sp,
+                    lse=lse)
+
+    def forward(self, qkv: Tensor) -> Tensor:
+        """qkv: (3, B, L, C) view of any strides (the reference passes a strided slice of the qkv Linear output)."""
+        q, k, v = qkv[0], qkv[1], qkv[2]
+        B, L, Cn = q.shape
+        self._check(L)
+        _no_autograd(qkv, self.get_v.weight)
+        out = torch.empty((B, L, Cn), dtype=q.dtype, device=q.device)
+        ops.lepe_attention_fwd([self.branch_desc(q, k, v, out)], B, self.resolution, float(self.scale), q.dtype)
+        return out
+
+
+# ------------------------------------------------------------------------------------------
+# CSWinBlock
+# ------------------------------------------------------------------------------------------
+class Mlp(nn.Module):
+    """Parameter container with the reference's names (cswin_unet.py:12-28); CSWinBlock runs it fused."""
+
+    def __init__(self, in_features, hidden_features=None, out_features=None, act_layer=nn.GELU, drop=0.):
+        super().__init__()
+        out_features = out_features or in_features
+        hidden_features = hidden_features or in_features
+        self.fc1 = nn.Linear(in_features, hidden_features)
+        self.act = act_layer()
+        self.fc2 = nn.Linear(hidden_features, out_features)
+        self.drop = nn.Dropout(drop)
+
+    def forward(self, x: Tensor) -> Tensor:
+        _no_autograd(x, self.fc1.weight)
+        dt = x.dtype
+        h = ops.linear(x, self.fc1.weight.detach().to(dt), self.fc1.bias.detach().to(dt), act=1)
+        return ops.linear(h, self.fc2.weight.detach().to(dt), self.fc2.bias.detach().to(dt))
+
+
+class CSWinBlock(_Native):
+    """Pre-norm CSWin transformer block (cswin_unet.py:112-181) as 5 fused launches:
+    [LN1+qkv] -> [both LePE stripe-attention branches, written straight into the concat layout] ->
+    [proj + residual + DropPath] -> [LN2 + fc1 + GELU] -> [fc2 + residual + DropPath]."""
+
+    def __init__(self, dim, reso, num_heads, split_size, mlp_ratio=4., qkv_bias=False, qk_scale=None, drop=0.,
+                 attn_drop=0., drop_path=0., act_layer=nn.GELU, norm_layer=nn.LayerNorm, last_stage=False):
+        super().__init__()
+        if norm_layer is not nn.LayerNorm or act_layer is not nn.GELU:
+            raise NotImplementedError("CSWinBlock: the fused kernels implement nn.LayerNorm and nn.GELU only")
+        self.dim = dim
+        self.num_heads = num_heads
+        self.patches_resolution = reso
+        self.split_size = split_size
+        self.mlp_ratio = mlp_ratio
+        self.qkv = nn.Linear(dim, dim * 3, bias=qkv_bias)
+        self.norm1 = norm_layer(dim)
+        if self.patches_resolution == split_size:
+            last_stage = True
+        self.branch_num = 1 if last_stage else 2
+        self.proj = nn.Linear(dim, dim)
+        self.proj_drop = nn.Dropout(drop)
+        if last_stage:
+            self.attns = nn.ModuleList([
+                LePEAttention(dim, resolution=self.patches_resolution, idx=-1, split_size=split_size,
+                              num_heads=num_heads, dim_out=dim, qk_scale=qk_scale, attn_drop=attn_drop, proj_drop=drop)
+                for _ in range(self.branch_num)])
+        else:
+            self.attns = nn.ModuleList([
+                LePEAttention(dim // 2, resolution=self.patches_resolution, idx=i, split_size=split_size,
+                              num_heads=num_heads // 2, dim_out=dim // 2, qk_scale=qk_scale, attn_drop=attn_drop,
+                              proj_drop=drop)
+                for i in range(self.branch_num)])
+        mlp_hidden_dim = int(dim * mlp_ratio)
+        self.drop_path = DropPath(drop_path) if drop_path > 0. else nn.Identity()
+        self.mlp = Mlp(in_features=dim, hidden_features=mlp_hidden_dim, out_features=dim, act_layer=act_layer, drop=drop)
+        self.norm2 = norm_layer(dim)
+        if drop > 0:
+            raise NotImplementedError("CSWinBlock: drop > 0 (proj/MLP dropout) is not fused; the reference uses 0")
+
+    def _sample_scale(self, x: Tensor) -> Optional[Tensor]:
+        return self.drop_path.sample_scale(x) if isinstance(self.drop_path, DropPath) else None
+
+    def forward(self, x: Tensor) -> Tensor:
+        H = W = self.patches_resolution
+        B, L, Cn = x.shape
+        assert L == H * W, "flatten img_tokens has wrong size"
+        _no_autograd(x, self.qkv.weight)
+        dt = x.dtype
+        w = self._w
+        qkv = ops.linear(x, w("qkv.w", self.qkv.weight, dt),
+                         None if self.qkv.bias is None else w("qkv.b", self.qkv.bias, dt),
+                         ln=(w("n1.w", self.norm1.weight, dt), w("n1.b", self.norm1.bias, dt), self.norm1.eps))
+        att = torch.empty((B, L, Cn), dtype=dt, device=x.device)
+        q, k, v = qkv[..., :Cn], qkv[..., Cn:2 * Cn], qkv[..., 2 * Cn:]
+        if self.branch_num == 2:
+            h = Cn // 2
+            descs = []
+            for i, a in enumerate(self.attns):
+                a._check(L)
+                sl = slice(i * h, (i + 1) * h)
+                descs.append(a.branch_desc(q[..., sl], k[..., sl], v[..., sl], att[..., sl]))
+            scale = float(self.attns[0].scale)
+        else:
+            self.attns[0]._check(L)
+            descs = [self.attns[0].branch_desc(q, k, v, att)]
+            scale = float(self.attns[0].scale)
+        ops.lepe_attention_fwd(descs, B, H, scale, dt)
+        x1 = ops.linear(att, w("proj.w", self.proj.weight, dt), w("proj.b", self.proj.bias, dt), residual=x,
+                        sample_scale=self._sample_scale(x), rows_per_sample=L)
+        hid = ops.linear(x1, w("fc1.w", self.mlp.fc1.weight, dt), w("fc1.b", self.mlp.fc1.bias, dt),
+                         ln=(w("n2.w", self.norm2.weight, dt), w("n2.b", self.norm2.bias, dt), self.norm2.eps), act=1)
+        return ops.linear(hid, w("fc2.w", self.mlp.fc2.weight, dt), w("fc2.b", self.mlp.fc2.bias, dt), residual=x1,
+                          sample_scale=self._sample_scale(x), rows_per_sample=L)
+
+
+# ------------------------------------------------------------------------------------------
+# Merge_Block / CARAFE / CARAFE4
+# ------------------------------------------------------------------------------------------
+def _side(L: int) -> int:
+    r = int(round(math.sqrt(L)))
+    assert r * r == L, "token count is not a square image"
+    return r
+
+
+class Merge_Block(_Native):
+    """Stage down-sampling (cswin_unet.py:205-220): 3x3 stride-2 conv on the token image + LayerNorm, as a
+    channel-innermost im2col gather -> Linear (weights re-packed to (2C, ky, kx, C)) -> LayerNorm."""
+
+    def __init__(self, dim, dim_out, norm_layer=nn.LayerNorm):
+        super().__init__()
+        if norm_layer is not nn.LayerNorm:
+            raise NotImplementedError("Merge_Block: only nn.LayerNorm is implemented")
+        self.conv = nn.Conv2d(dim, dim_out, 3, 2, 1)
+        self.norm = norm_layer(dim_out)
+
+    def forward(self, x: Tensor) -> Tensor:
+        B, L, Cn = x.shape
+        H = W = _side(L)
+        _no_autograd(x, self.conv.weight)
+        dt = x.dtype
+        wk = self._w("conv.w", self.conv.weight, dt, lambda t: t.permute(0, 2, 3, 1).reshape(t.shape[0], -1))
+        col = ops.im2col_tokens(x, H, W, 3, 3, 2, 1)
+        y = ops.linear(col, wk, self._w("conv.b", self.conv.bias, dt))
+        y = ops.layernorm(y, self._w("n.w", self.norm.weight, dt), self._w("n.b", self.norm.bias, dt), self.norm.eps)
+        Ho = (H + 2 - 3) // 2 + 1
+        return y.view(B, Ho * Ho, -1)
+
+
+class CARAFE(_Native):
+    """Content-aware re-assembly up-sampling (cswin_unet.py:222-269).  The 1x1 `out` conv is applied at LOW
+    resolution (it commutes with the convex re-assembly; see include/cswin_b200.h) and the softmax / pixel
+    shuffles / 3x3 gather run in one kernel."""
+
+    def __init__(self, dim, dim_out, kernel_size=3, up_factor=2):
+        super().__init__()
+        if kernel_size != 3:
+            raise NotImplementedError("CARAFE: only kernel_size=3 is implemented (the reference never uses another)")
+        self.kernel_size = kernel_size
+        self.up_factor = up_factor
+        self.down = nn.Conv2d(dim, dim // 4, 1)
+        self.encoder = nn.Conv2d(dim // 4, self.up_factor ** 2 * self.kernel_size ** 2, self.kernel_size, 1,
+                                 self.kernel_size // 2)
+        self.out = nn.Conv2d(dim, dim_out, 1)
+
+    def _kernel_logits(self, x: Tensor, H: int, W: int) -> Tensor:
+        dt = x.dtype
+        B = x.shape[0]
+        d = ops.linear(x, self._w("down.w", self.down.weight, dt, lambda t: t.reshape(t.shape[0], -1)),
+                       self._w("down.b", self.down.bias, dt))                           # (B, L, C/4)
+        col = ops.im2col_tokens(d, H, W, 3, 3, 1, 1)
+        return ops.linear(col, self._w("enc.w", self.encoder.weight, dt,
+                                       lambda t: t.permute(0, 2, 3, 1).reshape(t.shape[0], -1)),
+                          self._w("enc.b", self.encoder.bias, dt))                      # (B*L, 9 s^2)
+
+    def forward(self, x: Tensor) -> Tensor:
+        B, L, Cn = x.shape
+        H = W = _side(L)
+        _no_autograd(x, self.down.weight)
+        dt = x.dtype
+        enc = self._kernel_logits(x, H, W)
+        z = ops.linear(x, self._w("out.w", self.out.weight, dt, lambda t: t.reshape(t.shape[0], -1)))   # no bias yet
+        return ops.carafe_reassemble(enc, z.view(B * L, -1), self._w("out.b", self.out.bias, dt), B, H, W,
+                                     self.up_factor)
+
+
+class CARAFE4(CARAFE):
+    """x4 variant (cswin_unet.py:272-319): identical code in the reference, only `up_factor` differs."""
+
+    def __init__(self, dim, dim_out, kernel_size=3, up_factor=4):
+        super().__init__(dim, dim_out, kernel_size, up_factor)

@@ -1,0 +1,215 @@
+"""Tensor-level wrappers over the C ABI (include/cswin_b200.h): torch is used for device memory and
+streams only.  CUDA tensors only — there is no CPU path; CPU tensors raise.
+
+Every function enqueues on `torch.cuda.current_stream()` and allocates outputs / workspaces with
+`torch.empty`, so calls are CUDA-graph capturable.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import BF16, F32, LepeBranch, LepeBranchGrad, LinearArgs, check, lib
+
+Tensor = torch.Tensor
+
+
+def _dtype_code(t: Tensor) -> int:
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise TypeError(f"cswin_unet_b200 computes in float32 or bfloat16, got {t.dtype}")
+
+
+def _need_cuda(*ts: Optional[Tensor]) -> None:
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("cswin_unet_b200 has no CPU path: tensors must live on a CUDA device "
+                               "(the reference's CPU path is only restated in oracle/ for testing)")
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _rows(t: Tensor) -> Tuple[Tensor, int, int]:
+    """View a (..., K) tensor with uniform row pitch as (M, K) rows: returns (t, M, ld). Copies only if it must."""
+    if t.stride(-1) != 1:
+        t = t.contiguous()
+    K = t.shape[-1]
+    if t.dim() == 1:
+        return t, 1, K
+    if t.dim() == 2:
+        return t, t.shape[0], t.stride(0)
+    lead = t.shape[:-1]
+    ld = t.stride(-2)
+    # rows are uniformly spaced iff every outer stride equals the product of inner extents times ld
+    expect = ld
+    ok = True
+    for size, stride in zip(reversed(lead), reversed(t.stride()[:-1])):
+        if size != 1 and stride != expect:
+            ok = False
+            break
+        expect *= size
+    if not ok:
+        t = t.contiguous()
+        ld = K
+    M = 1
+    for s in lead:
+        M *= s
+    return t, M, ld
+
+
+# ----------------------------------------------------------------------------------------------
+# LePE attention
+# ----------------------------------------------------------------------------------------------
+def _branch(q: Tensor, k: Tensor, v: Tensor, out: Tensor, conv_w: Tensor, conv_b: Tensor, heads: int,
+            H_sp: int, W_sp: int, lse: Optional[Tensor]) -> LepeBranch:
+    br = LepeBranch()
+    br.q, br.k, br.v = q.data_ptr(), k.data_ptr(), v.data_ptr()
+    br.q_bs, br.q_ts = q.stride(0), q.stride(1)
+    br.k_bs, br.k_ts = k.stride(0), k.stride(1)
+    br.v_bs, br.v_ts = v.stride(0), v.stride(1)
+    br.out, br.o_bs, br.o_ts = out.data_ptr(), out.stride(0), out.stride(1)
+    br.conv_w, br.conv_b = conv_w.data_ptr(), conv_b.data_ptr()
+    br.lse = _ptr(lse)
+    br.C_b, br.heads, br.H_sp, br.W_sp = q.shape[-1], heads, H_sp, W_sp
+    return br
+
+
+def _unit_channel_stride(t: Tensor) -> Tensor:
+    return t if t.stride(-1) == 1 else t.contiguous()
+
+
+def lepe_attention_fwd(branches: Sequence[dict], B: int, reso: int, scale: float, dtype: torch.dtype) -> None:
+    """branches: [{q,k,v:(B,L,C_b) views, out:(B,L,C_b) view, conv_w:(C_b,1,3,3), conv_b:(C_b), heads, H_sp, W_sp, lse}]."""
+    arr = (LepeBranch * len(branches))()
+    keep = []
+    for i, b in enumerate(branches):
+        q, k, v = (_unit_channel_stride(b[n]) for n in ("q", "k", "v"))
+        out = b["out"]
+        assert out.stride(-1) == 1
+        cw, cb = b["conv_w"].contiguous(), b["conv_b"].contiguous()
+        _need_cuda(q, k, v, out, cw, cb)
+        keep += [q, k, v, cw, cb]
+        arr[i] = _branch(q, k, v, out, cw, cb, b["heads"], b["H_sp"], b["W_sp"], b.get("lse"))
+    code = F32 if dtype == torch.float32 else BF16
+    check(lib().cswin_lepe_attention_fwd(arr, len(branches), B, reso, C.c_float(scale), code, _stream()),
+          "cswin_lepe_attention_fwd")
+
+
+# ----------------------------------------------------------------------------------------------
+# LayerNorm / Linear
+# ----------------------------------------------------------------------------------------------
+def layernorm(x: Tensor, gamma: Tensor, beta: Tensor, eps: float = 1e-5, out: Optional[Tensor] = None,
+              stats: bool = False):
+    _need_cuda(x, gamma, beta)
+    x2, M, ldx = _rows(x)
+    Cn = x.shape[-1]
+    y = torch.empty(x.shape, dtype=x.dtype, device=x.device) if out is None else out
+    y2, _, ldy = _rows(y)
+    assert y2.data_ptr() == y.data_ptr()
+    mean = rstd = None
+    if stats:
+        mean = torch.empty(M, dtype=torch.float32, device=x.device)
+        rstd = torch.empty(M, dtype=torch.float32, device=x.device)
+    check(lib().cswin_layernorm_fwd(x2.data_ptr(), ldx, gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), ldy, M, Cn,
+                                    C.c_float(eps), _ptr(mean), _ptr(rstd), _dtype_code(x), _stream()),
+          "cswin_layernorm_fwd")
+    return (y, mean, rstd) if stats else y
+
+
+def linear(a: Tensor, w: Tensor, bias: Optional[Tensor] = None, *, a2: Optional[Tensor] = None,
+           ln: Optional[Tuple[Tensor, Tensor, float]] = None, act: int = 0, residual: Optional[Tensor] = None,
+           sample_scale: Optional[Tensor] = None, rows_per_sample: int = 0, out: Optional[Tensor] = None,
+           n_out: Optional[int] = None) -> Tensor:
+    """out = residual + sample_scale[row // rows_per_sample] * act(LN?([a | a2]) @ w[:n_out].T + bias)."""
+    _need_cuda(a, w, bias, a2, residual, sample_scale)
+    a_, M, lda = _rows(a)
+    K1 = a.shape[-1]
+    args = LinearArgs()
+    args.a, args.lda, args.K1 = a_.data_ptr(), lda, K1
+    keep = [a_]
+    K2 = 0
+    if a2 is not None:
+        a2_, M2, lda2 = _rows(a2)
+        assert M2 == M
+        K2 = a2.shape[-1]
+        args.a2, args.lda2, args.K2 = a2_.data_ptr(), lda2, K2
+        keep.append(a2_)
+    assert w.dim() == 2 and w.stride(1) == 1 and w.shape[1] == K1 + K2, (w.shape, K1, K2)
+    N = w.shape[0] if n_out is None else n_out
+    args.w, args.ldw = w.data_ptr(), w.stride(0)
+    args.bias = _ptr(bias)
+    if ln is not None:
+        args.ln_gamma, args.ln_beta, args.ln_eps = ln[0].data_ptr(), ln[1].data_ptr(), ln[2]
+    if out is None:
+        out = torch.empty(a.shape[:-1] + (N,), dtype=a.dtype, device=a.device)
+    o_, Mo, ldo = _rows(out)
+    assert o_.data_ptr() == out.data_ptr() and Mo == M
+    if residual is not None:
+        r_, Mr, ldr = _rows(residual)
+        assert Mr == M and residual.shape[-1] == N
+        args.residual, args.ldr = r_.data_ptr(), ldr
+        keep.append(r_)
+    if sample_scale is not None:
+        assert sample_scale.dtype == torch.float32 and rows_per_sample > 0
+        args.sample_scale, args.rows_per_sample = sample_scale.data_ptr(), rows_per_sample
+    args.out, args.ldo, args.M, args.N, args.act = out.data_ptr(), ldo, M, N, act
+    check(lib().cswin_linear_fwd(C.byref(args), _dtype_code(a), _stream()), "cswin_linear_fwd")
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# conv gathers / CARAFE reassembly
+# ----------------------------------------------------------------------------------------------
+def im2col_tokens(x: Tensor, H: int, W: int, KH: int, KW: int, stride: int, pad: int) -> Tensor:
+    """x: (B, H*W, C) token-major -> (B*Ho*Wo, KH*KW*C), column index (ky*KW+kx)*C + c."""
+    _need_cuda(x)
+    x = _unit_channel_stride(x)
+    B, L, Cn = x.shape
+    assert L == H * W
+    Ho, Wo = (H + 2 * pad - KH) // stride + 1, (W + 2 * pad - KW) // stride + 1
+    col = torch.empty((B * Ho * Wo, KH * KW * Cn), dtype=x.dtype, device=x.device)
+    check(lib().cswin_im2col_tokens(x.data_ptr(), x.stride(0), x.stride(1), col.data_ptr(), col.stride(0), B, H, W, Cn,
+                                    KH, KW, stride, pad, _dtype_code(x), _stream()), "cswin_im2col_tokens")
+    return col
+
+
+def im2col_nchw(x: Tensor, KH: int, KW: int, stride: int, pad: int, ldcol: int, dtype: torch.dtype) -> Tensor:
+    """x: (B, C, H, W) fp32 or bf16 -> (B*Ho*Wo, ldcol) of `dtype`, column (c*KH+ky)*KW+kx, zero padded to ldcol."""
+    _need_cuda(x)
+    x = x.contiguous()
+    B, Cn, H, W = x.shape
+    Ho, Wo = (H + 2 * pad - KH) // stride + 1, (W + 2 * pad - KW) // stride + 1
+    col = torch.empty((B * Ho * Wo, ldcol), dtype=dtype, device=x.device)
+    code = F32 if dtype == torch.float32 else BF16
+    check(lib().cswin_im2col_nchw(x.data_ptr(), int(x.dtype == torch.float32), col.data_ptr(), ldcol, B, Cn, H, W, KH,
+                                  KW, stride, pad, code, _stream()), "cswin_im2col_nchw")
+    return col
+
+
+def carafe_reassemble(enc: Tensor, z: Tensor, bias: Tensor, B: int, H: int, W: int, up: int, *, nchw_out: bool = False,
+                      out_dtype: Optional[torch.dtype] = None) -> Tensor:
+    """enc: (B*H*W, 9 up^2) logits, z: (B*H*W, C) -> (B, up^2 H W, C) token-major, or (B, C, up H, up W) if nchw_out."""
+    _need_cuda(enc, z, bias)
+    Cn = z.shape[-1]
+    od = out_dtype or z.dtype
+    if nchw_out:
+        y = torch.empty((B, Cn, H * up, W * up), dtype=od, device=z.device)
+        ldy = 0
+    else:
+        y = torch.empty((B, H * up * W * up, Cn), dtype=od, device=z.device)
+        ldy = Cn
+    check(lib().cswin_carafe_reassemble_fwd(enc.data_ptr(), enc.stride(0), z.data_ptr(), z.stride(0), bias.data_ptr(),
+                                            y.data_ptr(), ldy, int(nchw_out), int(od == torch.float32), B, H, W, Cn, up,
+                                            _dtype_code(z), _stream()), "cswin_carafe_reassemble_fwd")
+    return y

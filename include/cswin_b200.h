@@ -1,0 +1,158 @@
+/*
+ * cswin_b200.h — C ABI of libcswin_b200.so: the B200 (sm_100a) kernels behind the CSWin-UNet hot path.
+ *
+ * The reference (BoloniniD/CSWin-UNet) is pure PyTorch: its "FFI" for this path is the set of ATen calls
+ * made by networks/cswin_unet.py.  Every entry point below replaces one fused group of those calls and cites
+ * the reference lines it stands in for.  The drop-in nn.Modules in cswin_unet_b200/ (same constructor
+ * arguments, attribute names and state_dict keys as the reference classes) bind these symbols with ctypes;
+ * INTEGRATION.md shows the binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *  - Plain pointers and sizes only.  Every pointer is a DEVICE pointer owned by the caller (torch allocates all
+ *    inputs, outputs and workspaces); the library allocates no device memory and keeps no state except a
+ *    mutex-guarded per-device attribute cache.
+ *  - All work is enqueued on `stream` of the CURRENT device; nothing synchronises, allocates or calls
+ *    cudaSetDevice, so every call is CUDA-graph capturable and re-entrant (autograd / DataParallel threads).
+ *  - `dtype`: CSWIN_F32 (fp32 storage, fp32 SIMT arithmetic — the <=1e-4 parity path) or CSWIN_BF16 (bf16
+ *    storage, tcgen05 tensor-core contractions with fp32 accumulation, fp32 softmax / LayerNorm / GELU).
+ *    LayerNorm / conv-bias / LePE parameters are passed in the same dtype as the activations.
+ *  - Strides and leading dimensions are in ELEMENTS.  Channel (innermost) stride is always 1.
+ *  - Return value: 0 on success, otherwise a CSWIN_ERR_* code; cswin_last_error() returns a thread-local
+ *    message.  Nothing exits, throws or asserts across the ABI.
+ */
+#ifndef CSWIN_B200_H_
+#define CSWIN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CSWIN_ABI_VERSION 1
+
+typedef struct CUstream_st* cswin_stream_t; /* == cudaStream_t */
+
+enum { CSWIN_F32 = 0, CSWIN_BF16 = 1 };
+
+enum {
+  CSWIN_OK = 0,
+  CSWIN_ERR_INVALID = 1,     /* bad shape / stride / alignment / null pointer */
+  CSWIN_ERR_UNSUPPORTED = 2, /* valid request outside the implemented envelope */
+  CSWIN_ERR_CUDA = 3         /* a CUDA runtime / driver call failed */
+};
+
+int cswin_abi_version(void);
+const char* cswin_last_error(void);
+/* number of kernels this library has launched in the calling process (for bench.py's gpu_launches) */
+uint64_t cswin_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * LePE cross-shaped-window attention.
+ * Replaces LePEAttention.forward, networks/cswin_unet.py:82-109, including im2cswin :59-65, get_lepe :67-80,
+ * get_v depthwise conv :55, img2windows :184-191, windows2img :194-202 and the branch concat of
+ * CSWinBlock.forward :172-176 (each branch writes its channel slice of the (B,L,C) output directly).
+ *
+ * For every batch b, window (ih,iw), head g:   out = softmax(scale * q k^T) v + dwconv3x3_windowpad(v) + bias
+ * q/k/v point at element (b=0, token=0, first channel of the branch); token t = y*reso + x.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct {
+  const void* q; const void* k; const void* v;
+  int64_t q_bs, q_ts;   /* batch stride, token stride of q (elements) */
+  int64_t k_bs, k_ts;
+  int64_t v_bs, v_ts;
+  void* out;            /* element (b=0, token=0, first channel of the branch) of the (B,L,C) output */
+  int64_t o_bs, o_ts;
+  const void* conv_w;   /* get_v.weight, (C_b,1,3,3) contiguous */
+  const void* conv_b;   /* get_v.bias, (C_b) */
+  float* lse;           /* optional (B, L, heads) fp32 log-sum-exp of the scaled scores, or NULL */
+  int32_t C_b;          /* channels of this branch */
+  int32_t heads;        /* heads of this branch; head_dim = C_b / heads */
+  int32_t H_sp, W_sp;   /* stripe window shape (cswin_unet.py:43-53) */
+} cswin_lepe_branch_t;
+
+int cswin_lepe_attention_fwd(const cswin_lepe_branch_t* branches, int32_t n_branches, int32_t B, int32_t reso,
+                             float scale, int32_t dtype, cswin_stream_t stream);
+
+/* Backward of the above (autograd of cswin_unet.py:82-109; formulas in SURVEY.md Appendix A).
+ * dout has the layout of `out`; dq/dk/dv the layouts of q/k/v (may alias a (B,L,3C) buffer);
+ * dconv_w (C_b,9) / dconv_b (C_b) are fp32 and ACCUMULATED into (caller zeroes them). */
+typedef struct {
+  cswin_lepe_branch_t fwd;      /* same description as the forward call (out/lse = forward results) */
+  const void* dout; int64_t do_bs, do_ts;
+  void* dq; void* dk; void* dv;
+  int64_t dq_bs, dq_ts, dk_bs, dk_ts, dv_bs, dv_ts;
+  float* dconv_w; float* dconv_b;
+} cswin_lepe_branch_grad_t;
+
+int cswin_lepe_attention_bwd(const cswin_lepe_branch_grad_t* branches, int32_t n_branches, int32_t B, int32_t reso,
+                             float scale, int32_t dtype, cswin_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * LayerNorm over the last dimension.  Replaces nn.LayerNorm calls: norm1/norm2 (cswin_unet.py:168,179),
+ * Merge_Block.norm :218, stem LN :341, norm :497, norm_up :533.   y = (x-mean)/sqrt(var+eps)*gamma+beta
+ * mean_out / rstd_out: optional fp32 (M) saved statistics for the backward.
+ * ------------------------------------------------------------------------------------------------ */
+int cswin_layernorm_fwd(const void* x, int64_t ldx, const void* gamma, const void* beta, void* y, int64_t ldy,
+                        int64_t M, int32_t C, float eps, float* mean_out, float* rstd_out, int32_t dtype,
+                        cswin_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Linear with fused prologue/epilogue.  Replaces nn.Linear + the ops fused around it:
+ *   qkv :169 (LayerNorm prologue :168), proj + residual + DropPath :177-178, fc1 + GELU (Mlp :22-23, norm2 :179),
+ *   fc2 + residual + DropPath :179, concat_linear{4,3,2} on cat([skip,x]) :509-510/:518-519/:526-527 (two A
+ *   sources, no cat), and every 1x1 / im2col'ed conv (Merge_Block.conv :216, CARAFE down/encoder/out :240-241,:264,
+ *   stem conv :339, output conv :542).
+ *
+ *   acc[m,n] = sum_k A[m,k] W[n,k]        A = [a | a2] along K (a2 optional), optionally LayerNorm'ed per row first
+ *   t        = act(acc + bias[n])          act: 0 none, 1 GELU(erf)
+ *   out[m,n] = residual[m,n] + sample_scale[m / rows_per_sample] * t        (residual / sample_scale optional)
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct {
+  const void* a;  int64_t lda;  int32_t K1;
+  const void* a2; int64_t lda2; int32_t K2;       /* a2 == NULL -> K2 must be 0 */
+  const void* w;  int64_t ldw;                     /* (N, K1+K2) row-major */
+  const void* bias;                                /* (N) or NULL */
+  const void* ln_gamma; const void* ln_beta; float ln_eps;   /* LayerNorm prologue over K1 (a2 must be NULL) or NULL */
+  const void* residual; int64_t ldr;               /* (M,N) or NULL */
+  const float* sample_scale; int32_t rows_per_sample;  /* DropPath m_b/(1-p), fp32 (M/rows_per_sample) or NULL */
+  void* out; int64_t ldo;
+  int64_t M; int32_t N;
+  int32_t act;
+} cswin_linear_args_t;
+
+int cswin_linear_fwd(const cswin_linear_args_t* args, int32_t dtype, cswin_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * im2col gathers feeding cswin_linear_fwd (convolutions as GEMMs).
+ *  tokens variant: x is token-major (B, H*W, C) (what every block produces; the reference instead makes an NCHW copy,
+ *                  cswin_unet.py:214,235) ; col[(b,oy,ox), (ky*KW+kx)*C + c], zero padded.  Used by Merge_Block.conv
+ *                  (3x3 s2 p1, :216) and CARAFE.encoder (3x3 s1 p1, :241).
+ *  nchw variant:   x is (B, C, H, W) (the network input) ; col[(b,oy,ox), (c*KH+ky)*KW + kx] padded with zeros to
+ *                  ldcol columns.  Used by the stem conv (7x7 s4 p2, :339).
+ * ------------------------------------------------------------------------------------------------ */
+int cswin_im2col_tokens(const void* x, int64_t x_bs, int64_t x_ts, void* col, int64_t ldcol, int32_t B, int32_t H,
+                        int32_t W, int32_t C, int32_t KH, int32_t KW, int32_t stride, int32_t pad, int32_t dtype,
+                        cswin_stream_t stream);
+int cswin_im2col_nchw(const void* x, int32_t x_is_f32, void* col, int64_t ldcol, int32_t B, int32_t C, int32_t H,
+                      int32_t W, int32_t KH, int32_t KW, int32_t stride, int32_t pad, int32_t dtype,
+                      cswin_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * CARAFE content-aware reassembly.  Replaces cswin_unet.py:242-263 (pixel_shuffle, softmax over the 9 taps,
+ * pad + unfold + matmul, pixel_shuffle) of CARAFE / CARAFE4 (:222-319), applied AFTER the 1x1 `out` conv (:264):
+ * the conv is linear and per-pixel, so out(sum_t k_t X_t) + b = sum_t k_t out_nobias(X_t) + b; running it at low
+ * resolution costs s^2 times fewer FLOPs and removes the (B, s^2 L, C) intermediate.
+ *   enc  (B*H*W, 9 s^2): encoder logits, channel t*s^2 + a*s + e
+ *   z    (B*H*W, C):     out-conv (no bias) of the low-resolution pixels
+ *   y:   token-major (B, sH*sW, C) with leading dim ldy, or NCHW (B, C, sH, sW) when nchw_out != 0
+ * ------------------------------------------------------------------------------------------------ */
+int cswin_carafe_reassemble_fwd(const void* enc, int64_t ldenc, const void* z, int64_t ldz, const void* bias,
+                                void* y, int64_t ldy, int32_t nchw_out, int32_t y_is_f32, int32_t B, int32_t H,
+                                int32_t W, int32_t C, int32_t up, int32_t dtype, cswin_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CSWIN_B200_H_ */

@@ -180,6 +180,28 @@ def main():
     model.float()
     save("model_t224", **out)
 
+    # ---------------- whole model with the reference's init DISTRIBUTIONS (bf16 tolerance is quoted on these) -----
+    sd = {k: T(v) for k, v in synth.synth_state_dict(shapes, seed=1234, mode="refinit").items()}
+    model.load_state_dict(sd, strict=True)
+    out = {}
+    for kind in ("randn", "ct"):
+        x = T(synth.synth_image_batch(2, 3, 224, seed=0, kind=kind))
+        with torch.no_grad():
+            logits64 = model.double()(x.double())
+            model.float()
+            logits32 = model(x)
+            lbf = model.bfloat16()(x.bfloat16()).double()
+            model.float()
+        out[f"logits_{kind}"] = pack(logits64.permute(0, 2, 3, 1), stride_if_big=7)
+        out[f"argmax_{kind}"] = logits64.argmax(1).to(torch.uint8).numpy()
+        srt = logits64.sort(dim=1, descending=True).values
+        out[f"margin_{kind}"] = (srt[:, 0] - srt[:, 1]).float().numpy().astype(np.float16)
+        out[f"fp32_vs_fp64_maxabs_{kind}"] = np.float64((logits32.double() - logits64).abs().max())
+        # yard-stick: the reference's OWN bf16 path (CPU) against its fp64 path
+        out[f"refbf16_maxabs_{kind}"] = np.float64((lbf - logits64).abs().max())
+        out[f"refbf16_argmax_agree_{kind}"] = np.float64((lbf.argmax(1) == logits64.argmax(1)).double().mean())
+    save("model_refinit", **out)
+
     # ---------------- loss (trainer.py:55-57 with utils.DiceLoss) ----------------
     import utils as ref_utils
     logits = T(synth.synth_tensor("loss/logits", (2, 9, 32, 32), 9)).double().requires_grad_(True)

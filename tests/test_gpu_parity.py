@@ -1,0 +1,320 @@
+"""GPU parity tests (run on the B200 box: `pytest -m gpu`).  Every CUDA op is called through the C ABI
+(cswin_unet_b200.ops / modules -> ctypes -> libcswin_b200.so) and compared with
+
+  (i)  the golden vectors generated from the unmodified reference (tests/golden/*.npz), and
+  (ii) the CPU oracle (oracle/cswin_oracle.py) on the same seeded inputs.
+
+Tolerances (north_star): fp32 path max-abs <= 1e-4 against the fp32/fp64 reference; bf16 path max-abs <= 2e-2 on
+logits of the reference-init model; op-level bf16 tolerances are stated at each test and are relative to O(1)
+activations whose inputs were first rounded to bf16 (so only in-kernel rounding is measured).
+"""
+import numpy as np
+import pytest
+import torch
+
+import cswin_unet_b200 as cw
+from cswin_unet_b200 import ops, synth
+from oracle import cswin_oracle as O
+from tests import golden_util as G
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+LEPE_EXTRA = ((32, 16, 0, 2, 1), (64, 16, 1, 2, 2), (64, 8, -1, 8, 2), (128, 16, 0, 8, 4), (48, 12, 1, 3, 3))
+
+
+def T(a, dtype=torch.float32, device=DEV):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(device=device, dtype=dtype)
+
+
+def test_extension_is_loaded_and_counts_launches():
+    n0 = cw.launch_count()
+    x = torch.randn(64, 64, device=DEV)
+    ops.layernorm(x, torch.ones(64, device=DEV), torch.zeros(64, device=DEV))
+    assert cw.launch_count() == n0 + 1
+
+
+# ---------------------------------------------------------------------------------------------------
+# LePE attention
+# ---------------------------------------------------------------------------------------------------
+def lepe_case(cb, reso, idx, split, heads, B, dtype):
+    full_c = cb if idx == -1 else 2 * cb
+    base = T(synth.synth_qkv(B, reso, full_c, seed=0), dtype)
+    off = cb if idx == 1 else 0
+    qkv = base.permute(2, 0, 1, 3)[..., off:off + cb]              # the strided view the reference block passes
+    m = cw.LePEAttention(cb, resolution=reso, idx=idx, split_size=split, num_heads=heads).to(DEV).eval()
+    with torch.no_grad():
+        m.get_v.weight.copy_(T(synth.synth_tensor(f"lepe/{cb}/{reso}/{idx}/get_v.weight", (cb, 1, 3, 3), 1)))
+        m.get_v.bias.copy_(T(synth.synth_tensor(f"lepe/{cb}/{reso}/{idx}/get_v.bias", (cb,), 1)))
+    return m, qkv
+
+
+@pytest.mark.parametrize("tag,cfgs,B", [("t224", synth.LEPE_CONFIGS_T224, 1), ("extra", LEPE_EXTRA, 2)])
+def test_lepe_attention_fp32_vs_golden(tag, cfgs, B):
+    z = G.load(f"lepe_{tag}")
+    for (cb, reso, idx, split, heads) in cfgs:
+        m, qkv = lepe_case(cb, reso, idx, split, heads, B, torch.float32)
+        assert not qkv.is_contiguous()
+        with torch.no_grad():
+            y = m(qkv)
+        G.compare(z, f"c{cb}_r{reso}_i{idx}_s{split}_h{heads}", y.cpu().numpy(), atol=1e-4)
+
+
+@pytest.mark.parametrize("tag,cfgs,B", [("t224", synth.LEPE_CONFIGS_T224, 1), ("extra", LEPE_EXTRA, 2)])
+def test_lepe_attention_bf16_vs_oracle(tag, cfgs, B):
+    for (cb, reso, idx, split, heads) in cfgs:
+        m, qkv = lepe_case(cb, reso, idx, split, heads, B, torch.bfloat16)
+        with torch.no_grad():
+            y = m(qkv).float().cpu()
+        q, k, v = (qkv[i].float().cpu().double() for i in range(3))            # bf16-rounded inputs, exact in fp64
+        w = m.get_v.weight.detach().bfloat16().double().cpu()
+        b = m.get_v.bias.detach().bfloat16().double().cpu()
+        ref = O.lepe_attention(q, k, v, w, b, reso, idx, split, heads)
+        err = (y.double() - ref).abs().max().item()
+        # |out| is O(1..4): bf16 output rounding (2^-9 relative) + bf16 P rounding in the tensor-core path
+        assert err <= 3e-2, f"{(cb, reso, idx, split, heads)}: bf16 max-abs {err:.3e}"
+
+
+def test_lepe_attention_batch24_matches_oracle_fp32():
+    """BASELINE config 2 at the bench batch size: both branches of a stage-2 block in ONE launch."""
+    B, reso, C, heads, split = 24, 28, 128, 4, 2
+    base = T(synth.synth_qkv(B, reso, C, seed=3))
+    q, k, v = base[:, :, 0], base[:, :, 1], base[:, :, 2]
+    blk = cw.CSWinBlock(dim=C, reso=reso, num_heads=heads, split_size=split, qkv_bias=True).to(DEV).eval()
+    out = torch.empty(B, reso * reso, C, device=DEV)
+    h = C // 2
+    descs = [a.branch_desc(q[..., i * h:(i + 1) * h], k[..., i * h:(i + 1) * h], v[..., i * h:(i + 1) * h],
+                           out[..., i * h:(i + 1) * h]) for i, a in enumerate(blk.attns)]
+    ops.lepe_attention_fwd(descs, B, reso, float(blk.attns[0].scale), torch.float32)
+    qc, kc, vc = (t.cpu() for t in (q, k, v))
+    for i, a in enumerate(blk.attns):
+        sl = slice(i * h, (i + 1) * h)
+        ref = O.lepe_attention(qc[..., sl], kc[..., sl], vc[..., sl], a.get_v.weight.detach().cpu(),
+                               a.get_v.bias.detach().cpu(), reso, i, split, heads // 2)
+        assert (out[..., sl].cpu() - ref).abs().max().item() <= 1e-4
+
+
+def test_lepe_attention_rejects_bad_shapes():
+    m = cw.LePEAttention(32, resolution=8, idx=0, split_size=3, num_heads=1).to(DEV).eval()
+    with torch.no_grad(), pytest.raises(RuntimeError, match="not divisible"):
+        m(torch.zeros(3, 1, 64, 32, device=DEV))
+    m = cw.LePEAttention(32, resolution=8, idx=0, split_size=2, num_heads=1).to(DEV).eval()
+    with torch.no_grad():
+        assert m(torch.zeros(3, 0, 64, 32, device=DEV)).shape == (0, 64, 32)          # empty batch is a no-op
+
+
+# ---------------------------------------------------------------------------------------------------
+# LayerNorm / Linear
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-5), (torch.bfloat16, 2e-2)])
+@pytest.mark.parametrize("M,C", [(1000, 64), (333, 128), (77, 256), (49, 512), (5, 96)])
+def test_layernorm(dtype, tol, M, C):
+    g = torch.Generator().manual_seed(M * 7 + C)
+    x = (torch.randn(M, C, generator=g) * 2 + 0.5).to(dtype)
+    w = (1 + 0.1 * torch.randn(C, generator=g)).to(dtype)
+    b = (0.1 * torch.randn(C, generator=g)).to(dtype)
+    y = ops.layernorm(x.to(DEV), w.to(DEV), b.to(DEV), 1e-5)
+    ref = O._ln(x.double(), w.double(), b.double(), 1e-5)
+    assert (y.cpu().double() - ref).abs().max().item() <= tol
+
+
+LINEAR_CASES = [
+    # M, N, K1, K2, ln, act, res, drop
+    (3136, 192, 64, 0, True, 0, False, False),      # stage-1 LN+qkv
+    (3136, 64, 64, 0, False, 0, True, True),        # proj + residual + DropPath
+    (784, 512, 128, 0, True, 1, False, False),      # LN + fc1 + GELU
+    (784, 128, 512, 0, False, 0, True, False),      # fc2 + residual
+    (196, 256, 256, 256, False, 0, False, False),   # concat_linear on two sources
+    (98, 9, 64, 0, False, 0, False, False),         # folded head: N = 9 classes
+    (130, 36, 288, 0, False, 0, False, False),      # CARAFE encoder as GEMM (ragged M, N)
+    (201, 64, 152, 0, False, 0, False, False),      # stem conv as GEMM, K padded 147 -> 152
+    (49, 2048, 512, 0, True, 1, False, False),      # stage-4 fc1
+    (49, 512, 2048, 0, False, 0, True, True),       # stage-4 fc2
+]
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-4), (torch.bfloat16, 3e-2)])
+@pytest.mark.parametrize("M,N,K1,K2,ln,act,res,drop", LINEAR_CASES)
+def test_linear_fused(dtype, tol, M, N, K1, K2, ln, act, res, drop):
+    g = torch.Generator().manual_seed(M + N + K1)
+    rps = 49 if M % 49 == 0 else M
+    a = torch.randn(M, K1, generator=g).to(dtype)
+    a2 = torch.randn(M, K2, generator=g).to(dtype) if K2 else None
+    w = (torch.randn(N, K1 + K2, generator=g) / (K1 + K2) ** 0.5).to(dtype)
+    bias = (0.1 * torch.randn(N, generator=g)).to(dtype)
+    gam = (1 + 0.1 * torch.randn(K1, generator=g)).to(dtype)
+    bet = (0.1 * torch.randn(K1, generator=g)).to(dtype)
+    r = torch.randn(M, N, generator=g).to(dtype) if res else None
+    ss = (torch.bernoulli(torch.full((M // rps,), 0.8), generator=g) / 0.8).float() if drop else None
+    y = ops.linear(a.to(DEV), w.to(DEV), bias.to(DEV), a2=None if a2 is None else a2.to(DEV),
+                   ln=(gam.to(DEV), bet.to(DEV), 1e-5) if ln else None, act=act,
+                   residual=None if r is None else r.to(DEV), sample_scale=None if ss is None else ss.to(DEV),
+                   rows_per_sample=rps)
+    A = a.double()
+    if ln:
+        A = O._ln(A, gam.double(), bet.double(), 1e-5)
+        if dtype == torch.bfloat16:
+            A = A.bfloat16().double()                     # the tensor-core path rounds the normalised operand to bf16
+    if a2 is not None:
+        A = torch.cat([A, a2.double()], -1)
+    t = A @ w.double().T + bias.double()
+    if act:
+        t = O._gelu(t)
+    if ss is not None:
+        t = t * ss.double().repeat_interleave(rps).view(M, 1)
+    if r is not None:
+        t = t + r.double()
+    err = (y.cpu().double() - t).abs().max().item()
+    assert y.shape == (M, N) and err <= tol, f"max-abs {err:.3e}"
+
+
+# ---------------------------------------------------------------------------------------------------
+# block / merge / carafe vs golden
+# ---------------------------------------------------------------------------------------------------
+def load_named(module, prefix, seed):
+    sd = {k: T(synth.synth_tensor(prefix + k, tuple(v.shape), seed)) for k, v in module.state_dict().items()}
+    module.load_state_dict(sd, strict=True)
+
+
+BLOCKS = ((64, 56, 2, 1, False), (128, 28, 4, 2, False), (256, 14, 8, 7, False), (512, 7, 16, 7, True))
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-4), (torch.bfloat16, 1.5e-1)])
+def test_block_vs_golden(dtype, tol):
+    z = G.load("block")
+    for (dim, reso, heads, split, last) in BLOCKS:
+        m = cw.CSWinBlock(dim=dim, reso=reso, num_heads=heads, split_size=split, qkv_bias=True, last_stage=last).to(DEV).eval()
+        load_named(m, f"block/{dim}/", 3)
+        x = T(synth.synth_tensor(f"block_in/{dim}", (2, reso * reso, dim), 4), dtype)
+        with torch.no_grad():
+            y = m(x)
+        assert y.dtype == dtype
+        # bf16: inputs, weights, and 5 intermediate activations are rounded to bf16; |y| reaches ~8
+        G.compare(z, f"d{dim}", y.float().cpu().numpy(), atol=tol)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-4), (torch.bfloat16, 6e-2)])
+def test_merge_and_carafe_vs_golden(dtype, tol):
+    z = G.load("merge_carafe")
+    for (dim, reso) in ((64, 56), (128, 28), (256, 14)):
+        m = cw.Merge_Block(dim, dim * 2).to(DEV).eval()
+        load_named(m, f"merge/{dim}/", 5)
+        x = T(synth.synth_tensor(f"merge_in/{dim}", (2, reso * reso, dim), 6), dtype)
+        with torch.no_grad():
+            y = m(x)
+        G.compare(z, f"merge_d{dim}", y.float().cpu().numpy(), atol=tol)
+    for (cls, dim, dout, reso, up) in ((cw.CARAFE, 512, 256, 7, 2), (cw.CARAFE, 128, 64, 28, 2), (cw.CARAFE4, 64, 64, 14, 4)):
+        m = cls(dim, dout).to(DEV).eval()
+        load_named(m, f"carafe/{dim}/{up}/", 7)
+        x = T(synth.synth_tensor(f"carafe_in/{dim}/{up}", (2, reso * reso, dim), 8), dtype)
+        with torch.no_grad():
+            y = m(x)
+        G.compare(z, f"carafe_d{dim}_u{up}", y.float().cpu().numpy(), atol=tol)
+
+
+# ---------------------------------------------------------------------------------------------------
+# whole model
+# ---------------------------------------------------------------------------------------------------
+def build_model(mode):
+    m = cw.cswin_tiny_224(num_classes=9).eval()
+    shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in synth.synth_state_dict(shapes, seed=1234, mode=mode).items()}, strict=True)
+    return m.to(DEV)
+
+
+@pytest.mark.parametrize("mode,gold", [("alive", "model_t224"), ("refinit", "model_refinit")])
+def test_full_model_fp32_logits(mode, gold):
+    z = G.load(gold)
+    m = build_model(mode)
+    for kind in ("randn", "ct"):
+        x = T(synth.synth_image_batch(2, 3, 224, seed=0, kind=kind))
+        with torch.no_grad():
+            logits = m(x)
+        assert logits.shape == (2, 9, 224, 224) and logits.dtype == torch.float32
+        err = G.compare(z, f"logits_{kind}", logits.permute(0, 2, 3, 1).cpu().numpy(), atol=1e-4)
+        agree = (logits.argmax(1).cpu().numpy() == z[f"argmax_{kind}"]).mean()
+        print(f"[fp32 {mode}/{kind}] max-abs {err:.2e} argmax agreement {agree:.6f}")
+        assert agree >= 0.999
+
+
+def test_full_model_bf16_logits_reference_init():
+    """north_star: bf16 logits max-abs <= 2e-2 vs the fp32 reference (random-init distributions)."""
+    z = G.load("model_refinit")
+    m = build_model("refinit")
+    m.compute_dtype = torch.bfloat16
+    for kind in ("randn", "ct"):
+        x = T(synth.synth_image_batch(2, 3, 224, seed=0, kind=kind))
+        with torch.no_grad():
+            logits = m(x).float()
+        err = G.compare(z, f"logits_{kind}", logits.permute(0, 2, 3, 1).cpu().numpy(), atol=2e-2)
+        am = logits.argmax(1).cpu().numpy()
+        agree = (am == z[f"argmax_{kind}"]).mean()
+        decisive = z[f"margin_{kind}"].astype(np.float32) >= 0.01
+        agree_dec = (am == z[f"argmax_{kind}"])[decisive].mean()
+        print(f"[bf16 refinit/{kind}] max-abs {err:.2e} argmax agreement {agree:.5f} "
+              f"(reference's own bf16: {float(z[f'refbf16_argmax_agree_{kind}']):.5f}, max-abs "
+              f"{float(z[f'refbf16_maxabs_{kind}']):.2e}); on margin>=0.01 pixels {agree_dec:.6f}")
+        assert agree_dec >= 0.999
+        assert agree >= float(z[f"refbf16_argmax_agree_{kind}"]) - 0.003
+
+
+def test_full_model_bf16_logits_alive_weights():
+    z = G.load("model_t224")
+    m = build_model("alive")
+    m.compute_dtype = torch.bfloat16
+    x = T(synth.synth_image_batch(2, 3, 224, seed=0, kind="randn"))
+    with torch.no_grad():
+        logits = m(x).float()
+    # logits here have std ~1 and |max| ~2.8 (7x the reference-init scale): tolerance scaled accordingly
+    err = G.compare(z, "logits_randn", logits.permute(0, 2, 3, 1).cpu().numpy(), atol=1.5e-1)
+    am = logits.argmax(1).cpu().numpy()
+    decisive = z["margin_randn"].astype(np.float32) >= 0.05
+    print(f"[bf16 alive] max-abs {err:.2e} argmax agreement {(am == z['argmax_randn']).mean():.5f}")
+    assert (am == z["argmax_randn"])[decisive].mean() >= 0.999
+
+
+def test_batch_independence_and_cuda_graph_replay():
+    """Slices are independent (what makes slice-sharding legal) and the forward is CUDA-graph capturable."""
+    m = build_model("alive")
+    x = T(synth.synth_image_batch(4, 3, 224, seed=5, kind="ct"))
+    with torch.no_grad():
+        full = m(x)
+        part = m(x[1:3])
+    assert torch.equal(full[1:3], part)
+    static_x = x.clone()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s), torch.no_grad():
+        for _ in range(2):
+            m(static_x)
+    torch.cuda.current_stream().wait_stream(s)
+    graph = torch.cuda.CUDAGraph()
+    with torch.no_grad(), torch.cuda.graph(graph):
+        static_y = m(static_x)
+    static_x.copy_(torch.flip(x, dims=(0,)))
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(static_y, torch.flip(full, dims=(0,)))
+
+
+def test_droppath_training_forward_matches_oracle():
+    blk = cw.CSWinBlock(dim=128, reso=28, num_heads=4, split_size=2, qkv_bias=True, drop_path=0.3).to(DEV).train()
+    load_named(blk, "block/128/", 3)
+    x = T(synth.synth_tensor("block_in/128", (6, 784, 128), 4))
+    torch.manual_seed(11)
+    with torch.no_grad():
+        y = blk(x)
+    torch.manual_seed(11)
+    s1 = blk.drop_path.sample_scale(x); s2 = blk.drop_path.sample_scale(x)
+    sd = {k: v.detach().cpu() for k, v in blk.state_dict().items()}
+    xc = x.cpu()
+    # oracle with the two masks applied (x + s1*proj(.) ; x1 + s2*mlp(.)) — restated here because the oracle takes one mask
+    ref1 = O.cswin_block(sd, "", xc, 28, 4, 2, False, sample_scale=None)
+    assert not torch.allclose(y.cpu(), ref1, atol=1e-3)            # masks really were applied
+    u = O._ln(xc, sd["norm1.weight"], sd["norm1.bias"], 1e-5) @ sd["qkv.weight"].T + sd["qkv.bias"]
+    q, k, v = u[..., :128], u[..., 128:256], u[..., 256:]
+    a = torch.cat([O.lepe_attention(q[..., i * 64:(i + 1) * 64], k[..., i * 64:(i + 1) * 64], v[..., i * 64:(i + 1) * 64],
+                                    sd[f"attns.{i}.get_v.weight"], sd[f"attns.{i}.get_v.bias"], 28, i, 2, 2) for i in range(2)], -1)
+    x1 = xc + s1.cpu().view(-1, 1, 1) * (a @ sd["proj.weight"].T + sd["proj.bias"])
+    hdn = O._gelu(O._ln(x1, sd["norm2.weight"], sd["norm2.bias"], 1e-5) @ sd["mlp.fc1.weight"].T + sd["mlp.fc1.bias"])
+    ref = x1 + s2.cpu().view(-1, 1, 1) * (hdn @ sd["mlp.fc2.weight"].T + sd["mlp.fc2.bias"])
+    assert (y.cpu() - ref).abs().max().item() <= 1e-4
