@@ -190,8 +190,8 @@ def main():
             logits64 = model.double()(x.double())
             model.float()
             logits32 = model(x)
-            lbf = model.bfloat16()(x.bfloat16()).double()
-            model.float()
+            import copy
+            lbf = copy.deepcopy(model).bfloat16()(x.bfloat16()).double()      # a COPY: .bfloat16() rounds weights in place
         out[f"logits_{kind}"] = pack(logits64.permute(0, 2, 3, 1), stride_if_big=7)
         out[f"argmax_{kind}"] = logits64.argmax(1).to(torch.uint8).numpy()
         srt = logits64.sort(dim=1, descending=True).values
