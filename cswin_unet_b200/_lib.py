@@ -64,6 +64,7 @@ SIGNATURES = {
     "cswin_abi_version": (c_int32, []),
     "cswin_last_error": (C.c_char_p, []),
     "cswin_launch_count": (C.c_uint64, []),
+    "cswin_tc_launch_count": (C.c_uint64, []),
     "cswin_lepe_attention_fwd": (c_int32, [C.POINTER(LepeBranch), c_int32, c_int32, c_int32, c_float, c_int32, c_void_p]),
     "cswin_lepe_attention_bwd": (c_int32, [C.POINTER(LepeBranchGrad), c_int32, c_int32, c_int32, c_float, c_int32, c_void_p]),
     "cswin_layernorm_fwd": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int32,
@@ -124,3 +125,8 @@ def check(rc: int, what: str) -> None:
 
 def launch_count() -> int:
     return int(lib().cswin_launch_count())
+
+
+def tc_launch_count() -> int:
+    """Launches of tcgen05 / TMEM / TMA kernels so far (subset of launch_count())."""
+    return int(lib().cswin_tc_launch_count())

@@ -1,12 +1,309 @@
-// attention_tc.cu — bf16 tcgen05 / TMEM / TMA LePE stripe attention (placeholder until the kernel lands).
+// attention_tc.cu — fused LePE cross-shaped-window attention, bf16, tcgen05 / TMEM / TMA (sm_100a).
+//
+// Replaces LePEAttention.forward and everything it calls (networks/cswin_unet.py:59-109, 184-202) plus the branch
+// concat of CSWinBlock.forward (:172-176).  Both stripe branches of a block run in ONE launch.
+//
+// Work unit ("tile") = 128 query rows = 128 TMEM lanes = 128 threads:
+//     windows of N <= 64 tokens   : two (window, head) problems per tile (rows 0..63 and 64..127),
+//     windows of 64 < N <= 128    : one problem per tile.
+// Per tile
+//   1. TMA gathers the stripe window straight out of the (B, H, W, 3C) qkv tensor: one 4-D box
+//      (32 channels, W_sp, H_sp, 1) per operand lands as [token][32 ch] rows of 64 B in the 64-byte-swizzled
+//      UMMA layout — the img2windows / head-split copies of the reference become address arithmetic in the
+//      tensor map;
+//   2. S = Q K^T: two tcgen05.mma (M128 x N<=128 x K16, both operands K-major from smem), fp32 in TMEM columns
+//      [0,128).  With two problems per tile the off-diagonal 64x64 blocks are computed and ignored;
+//   3. softmax: thread i reads row i of S from TMEM (tcgen05.ld 32x32b), exact max / exp2 / sum in fp32 with the
+//      qk scale folded into the exponent, writes bf16 P back into TMEM columns [0,64) (zeros for padded keys and
+//      for the other problem's keys);
+//   4. O = P V: tcgen05.mma with A = P from TMEM and B = V from smem (MN-major, the layout TMA delivered),
+//      N = 32, accumulating in TMEM columns [64,96);
+//   5. while that runs, thread i computes the LePE depthwise 3x3 conv for its token from the same V tile in smem
+//      (zero padding at the WINDOW border), then adds it to O / rowsum and stores 64 B straight into the
+//      (B, L, C) concat layout (windows2img + cat are address arithmetic).
+// HBM traffic = q, k, v read once + out written once; the N x N scores never leave TMEM.
 #include "common.cuh"
+#include "tc_common.cuh"
+
 namespace cswin {
-int lepe_attention_fwd_tc(const cswin_lepe_branch_t*, int, int, int, float, cudaStream_t, bool* handled) {
+namespace {
+
+using namespace tc;
+
+struct TcBranch {
+  __nv_bfloat16* out; const __nv_bfloat16* cw; const __nv_bfloat16* cb; float* lse;
+  int64_t o_bs, o_ts;
+  int heads, hs, ws, nww, nwin, N, tile_begin, nprob;
+};
+struct alignas(64) TcParams {
+  CUtensorMap map[2][3];     // [branch][q,k,v]
+  TcBranch br[2];
+  int nb, reso;
+  float scale, scale_log2e;
+};
+
+constexpr int kTileRows = 128;
+constexpr int kRowBytes = 64;                       // 32 bf16 channels of one head
+constexpr int kOperandBytes = kTileRows * kRowBytes;  // 8 KB
+constexpr uint32_t kTmemCols = 128;
+constexpr int kSmemBytes = 3 * kOperandBytes + 2 * 9 * 32 * 4 + 2 * 32 * 4 + 64 + 1024;
+
+__device__ __forceinline__ uint32_t v_chunk_addr(uint32_t vbase, int row, int chunk) {
+  return vbase + row * kRowBytes + (((chunk ^ (row >> 1)) & 3) << 4);          // Swizzle<2,4,3> (64-byte swizzle)
+}
+
+__global__ void __launch_bounds__(128, 4) lepe_attn_fwd_tc_kernel(const __grid_constant__ TcParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* Qs = smem;
+  uint8_t* Ks = smem + kOperandBytes;
+  uint8_t* Vs = smem + 2 * kOperandBytes;
+  float* Wt = reinterpret_cast<float*>(smem + 3 * kOperandBytes);     // [2][9][32]
+  float* Bc = Wt + 2 * 9 * 32;                                        // [2][32]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(Bc + 2 * 32);          // tma, s, o
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int bi = (P.nb > 1 && (int)blockIdx.x >= P.br[1].tile_begin) ? 1 : 0;
+  const TcBranch& br = P.br[bi];
+  const int tile = blockIdx.x - br.tile_begin;
+  const int N = br.N, hs = br.hs, ws = br.ws;
+  const int slots = (N <= 64) ? 2 : 1;
+  const int slot_rows = kTileRows / slots;
+  const int p0 = tile * slots;
+  const int np = min(slots, br.nprob - p0);
+  const int kext = (slots == 2) ? 128 : ((N + 15) & ~15);            // kv extent fed to the P.V MMA
+
+  const int slot = tid / slot_rows;            // warp-uniform
+  const int n = tid - slot * slot_rows;        // token index inside the window
+
+  // decode the (batch, window, head) of both slots (cheap; every thread needs its own, thread 0 needs both)
+  int pb[2], pih[2], piw[2], phead[2];
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {
+    int local = p0 + min(s, np - 1);
+    phead[s] = local % br.heads; local /= br.heads;
+    const int win = local % br.nwin;
+    pb[s] = local / br.nwin;
+    pih[s] = win / br.nww; piw[s] = win - pih[s] * br.nww;
+  }
+
+  const uint32_t bar_tma = smem_u32(&bars[0]), bar_s = smem_u32(&bars[1]), bar_o = smem_u32(&bars[2]);
+  if (warp == 0) { tmem_alloc(smem_u32(tmem_slot), kTmemCols); tmem_relinquish(); }
+  if (tid == 32) { mbar_init(bar_tma, 1); mbar_init(bar_s, 1); mbar_init(bar_o, 1); fence_barrier_init(); }
+
+  // zero the V rows the P.V MMA reads but TMA does not write (0 * stale-NaN would poison O)
+  for (int i = tid; i < kTileRows * 4; i += 128) {
+    const int row = i >> 2;
+    const int s = row / slot_rows, rn = row - s * slot_rows;
+    if (row < kext && (s >= np || rn >= N)) *reinterpret_cast<uint4*>(Vs + i * 16) = make_uint4(0, 0, 0, 0);
+  }
+  // stage the LePE weights of the head(s) of this tile: Wt[slot][tap][ch], Bc[slot][ch]
+  for (int i = tid; i < np * 288; i += 128) {
+    const int s = i / 288, r = i - s * 288;
+    const int ch = r / 9, t = r - ch * 9;
+    Wt[(s * 9 + t) * 32 + ch] = __bfloat162float(br.cw[(phead[s] * 32 + ch) * 9 + t]);
+  }
+  if (tid < np * 32) Bc[tid] = __bfloat162float(br.cb[phead[tid >> 5] * 32 + (tid & 31)]);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (tid == 0) {
+    mbar_expect_tx(bar_tma, (uint32_t)(np * 3 * N * kRowBytes));
+    for (int s = 0; s < np; ++s) {
+      const int c0 = phead[s] * 32, c1 = piw[s] * ws, c2 = pih[s] * hs, c3 = pb[s];
+      const uint32_t off = s * slot_rows * kRowBytes;
+      tma_load_4d(smem_u32(Qs) + off, &P.map[bi][0], bar_tma, c0, c1, c2, c3);
+      tma_load_4d(smem_u32(Ks) + off, &P.map[bi][1], bar_tma, c0, c1, c2, c3);
+      tma_load_4d(smem_u32(Vs) + off, &P.map[bi][2], bar_tma, c0, c1, c2, c3);
+    }
+  }
+  mbar_wait(bar_tma, 0);
+
+  if (tid == 0) {
+    tc_fence_after();
+    const uint64_t qd = make_smem_desc(smem_u32(Qs), 16, 8 * kRowBytes, kLayoutSw64);
+    const uint64_t kd = make_smem_desc(smem_u32(Ks), 16, 8 * kRowBytes, kLayoutSw64);
+    const uint32_t idesc = make_idesc_bf16(128, kext, 0, 0);
+    mma_ss(tmem_base, qd, kd, idesc, false);
+    mma_ss(tmem_base, qd + 2, kd + 2, idesc, true);          // +32 B along K inside the swizzled row
+    tc_commit(bar_s);
+  }
+  mbar_wait(bar_s, 0);
+  tc_fence_after();
+
+  // ---- softmax on row `tid` of S ----
+  const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
+  const int col0 = slot * slot_rows;                         // first S column of my problem
+  const int nchunks = (slots == 2) ? 2 : (kext + 31) / 32;
+  float mx = -INFINITY;
+  for (int c = 0; c < nchunks; ++c) {
+    uint32_t v[32];
+    tmem_ld32(trow + col0 + 32 * c, v);
+    tmem_wait_ld();
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (32 * c + j < N) mx = fmaxf(mx, __uint_as_float(v[j]));
+  }
+  float sum = 0.f;
+  const float mxs = mx * P.scale_log2e;
+  for (int c = 0; c < nchunks; ++c) {
+    uint32_t v[32], pk[16];
+    tmem_ld32(trow + col0 + 32 * c, v);
+    tmem_wait_ld();
+#pragma unroll
+    for (int j = 0; j < 32; j += 2) {
+      float e0 = 0.f, e1 = 0.f;
+      if (32 * c + j < N) e0 = exp2f(fmaf(__uint_as_float(v[j]), P.scale_log2e, -mxs));
+      if (32 * c + j + 1 < N) e1 = exp2f(fmaf(__uint_as_float(v[j + 1]), P.scale_log2e, -mxs));
+      // sum what the MMA will actually see (bf16-rounded probabilities) so rows stay normalised
+      const uint32_t pr = pack_bf16x2(e0, e1);
+      sum += bf16_lo(pr) + bf16_hi(pr);
+      pk[j >> 1] = pr;
+    }
+    tmem_st16(trow + (col0 >> 1) + 16 * c, pk);
+  }
+  if (slots == 2) {                                          // keys of the other problem: P = 0
+    uint32_t z[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) z[j] = 0u;
+    tmem_st32(trow + ((1 - slot) * 32), z);
+  }
+  tmem_wait_st();
+  tc_fence_before();
+  __syncthreads();
+
+  if (tid == 0) {
+    tc_fence_after();
+    const uint64_t vd = make_smem_desc(smem_u32(Vs), 8 * kRowBytes, 8 * kRowBytes, kLayoutSw64);
+    const uint32_t idesc = make_idesc_bf16(128, 32, 0, 1);   // B = V is MN-major
+    for (int k = 0; k < kext / 16; ++k)
+      mma_ts(tmem_base + 64, tmem_base + 8 * k, vd + (uint64_t)k * ((16 * kRowBytes) >> 4), idesc, k > 0);
+    tc_commit(bar_o);
+  }
+
+  // ---- LePE for my token, overlapped with the P.V MMA ----
+  const bool valid = slot < np && n < N;
+  float lp[32];
+  {
+    const float* bc = Bc + min(slot, np - 1) * 32;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) lp[j] = bc[j];
+  }
+  if (valid) {
+    const int r = n / ws, c = n - r * ws;
+    const uint32_t vbase = smem_u32(Vs);
+    const float* wt = Wt + slot * 9 * 32;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const int rr = r + t / 3 - 1, cc = c + t % 3 - 1;
+      if (rr >= 0 && rr < hs && cc >= 0 && cc < ws) {
+        const int row = slot * slot_rows + rr * ws + cc;
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          uint4 vv;
+          asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(vv.x), "=r"(vv.y), "=r"(vv.z), "=r"(vv.w)
+                       : "r"(v_chunk_addr(vbase, row, ch)));
+          const float4 w0 = *reinterpret_cast<const float4*>(wt + t * 32 + ch * 8);
+          const float4 w1 = *reinterpret_cast<const float4*>(wt + t * 32 + ch * 8 + 4);
+          lp[ch * 8 + 0] = fmaf(w0.x, bf16_lo(vv.x), lp[ch * 8 + 0]);
+          lp[ch * 8 + 1] = fmaf(w0.y, bf16_hi(vv.x), lp[ch * 8 + 1]);
+          lp[ch * 8 + 2] = fmaf(w0.z, bf16_lo(vv.y), lp[ch * 8 + 2]);
+          lp[ch * 8 + 3] = fmaf(w0.w, bf16_hi(vv.y), lp[ch * 8 + 3]);
+          lp[ch * 8 + 4] = fmaf(w1.x, bf16_lo(vv.z), lp[ch * 8 + 4]);
+          lp[ch * 8 + 5] = fmaf(w1.y, bf16_hi(vv.z), lp[ch * 8 + 5]);
+          lp[ch * 8 + 6] = fmaf(w1.z, bf16_lo(vv.w), lp[ch * 8 + 6]);
+          lp[ch * 8 + 7] = fmaf(w1.w, bf16_hi(vv.w), lp[ch * 8 + 7]);
+        }
+      }
+    }
+  }
+
+  mbar_wait(bar_o, 0);
+  tc_fence_after();
+  {
+    uint32_t o[32];
+    tmem_ld32(trow + 64, o);
+    tmem_wait_ld();
+    if (valid) {
+      const float inv = 1.0f / sum;
+      const int r = n / ws, c = n - r * ws;
+      const int64_t tok = (int64_t)(pih[slot] * hs + r) * P.reso + (piw[slot] * ws + c);
+      __nv_bfloat16* dst = br.out + (int64_t)pb[slot] * br.o_bs + tok * br.o_ts + phead[slot] * 32;
+      uint32_t w[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        w[j] = pack_bf16x2(fmaf(__uint_as_float(o[2 * j]), inv, lp[2 * j]), fmaf(__uint_as_float(o[2 * j + 1]), inv, lp[2 * j + 1]));
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        *reinterpret_cast<uint4*>(dst + 8 * j) = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+      if (br.lse != nullptr)
+        br.lse[((int64_t)pb[slot] * P.reso * P.reso + tok) * br.heads + phead[slot]] = mx * P.scale + logf(sum);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace
+
+int lepe_attention_fwd_tc(const cswin_lepe_branch_t* brs, int nb, int B, int reso, float scale, cudaStream_t stream,
+                          bool* handled) {
   *handled = false;
+  // eligibility: head_dim 32, window <= 128 tokens, TMA-compatible strides / alignment; otherwise the SIMT kernel runs
+  for (int i = 0; i < nb; ++i) {
+    const cswin_lepe_branch_t& s = brs[i];
+    if (!s.q || !s.k || !s.v || !s.out || !s.conv_w || !s.conv_b) return CSWIN_OK;     // SIMT path reports the error
+    if (s.heads <= 0 || s.C_b != s.heads * 32) return CSWIN_OK;
+    if (s.H_sp <= 0 || s.W_sp <= 0 || reso % s.H_sp || reso % s.W_sp) return CSWIN_OK;
+    if (s.H_sp * s.W_sp > 128 || s.H_sp > 256 || s.W_sp > 256) return CSWIN_OK;
+    const int64_t strides[] = {s.q_bs, s.q_ts, s.k_bs, s.k_ts, s.v_bs, s.v_ts, s.o_bs, s.o_ts};
+    for (int64_t st : strides) if (st <= 0 || (st * 2) % 16 != 0) return CSWIN_OK;
+    if (!aligned16(s.q) || !aligned16(s.k) || !aligned16(s.v) || !aligned16(s.out)) return CSWIN_OK;
+  }
+  if (tc::encode_tiled_fn() == nullptr) return CSWIN_OK;
+
+  TcParams P;
+  P.nb = nb; P.reso = reso; P.scale = scale; P.scale_log2e = scale * 1.4426950408889634f;
+  int tiles = 0;
+  for (int i = 0; i < nb; ++i) {
+    const cswin_lepe_branch_t& s = brs[i];
+    TcBranch& d = P.br[i];
+    d.out = (__nv_bfloat16*)s.out; d.cw = (const __nv_bfloat16*)s.conv_w; d.cb = (const __nv_bfloat16*)s.conv_b;
+    d.lse = s.lse; d.o_bs = s.o_bs; d.o_ts = s.o_ts;
+    d.heads = s.heads; d.hs = s.H_sp; d.ws = s.W_sp; d.nww = reso / s.W_sp;
+    d.nwin = (reso / s.H_sp) * (reso / s.W_sp); d.N = s.H_sp * s.W_sp;
+    d.nprob = B * d.nwin * d.heads;
+    d.tile_begin = tiles;
+    const int slots = d.N <= 64 ? 2 : 1;
+    tiles += (d.nprob + slots - 1) / slots;
+    const void* ptr[3] = {s.q, s.k, s.v};
+    const int64_t bs[3] = {s.q_bs, s.k_bs, s.v_bs}, ts[3] = {s.q_ts, s.k_ts, s.v_ts};
+    for (int j = 0; j < 3; ++j) {
+      const uint64_t dims[4] = {(uint64_t)s.C_b, (uint64_t)reso, (uint64_t)reso, (uint64_t)B};
+      const uint64_t str[3] = {(uint64_t)ts[j] * 2, (uint64_t)ts[j] * 2 * reso, (uint64_t)bs[j] * 2};
+      const uint32_t box[4] = {32, (uint32_t)s.W_sp, (uint32_t)s.H_sp, 1};
+      if (!tc::make_tensor_map_bf16(&P.map[i][j], ptr[j], 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B)) return CSWIN_ERR_CUDA;
+    }
+  }
+  if (nb == 1) P.br[1] = P.br[0];
+  static_assert(kSmemBytes <= 48 * 1024, "dynamic smem must stay under the no-opt-in limit");
+  lepe_attn_fwd_tc_kernel<<<tiles, 128, kSmemBytes, stream>>>(P);
+  CSWIN_LAUNCH_CHECK();
+  g_tc_launches.fetch_add(1, std::memory_order_relaxed);
+  *handled = true;
   return CSWIN_OK;
 }
+
 int lepe_attention_bwd_simt(const cswin_lepe_branch_grad_t*, int, int, int, float, int, cudaStream_t) {
   set_error("lepe_attention_bwd: not implemented yet");
   return CSWIN_ERR_UNSUPPORTED;
 }
+
 }  // namespace cswin

@@ -16,6 +16,7 @@ namespace cswin {
 // ---- error plumbing (thread-local message, never throws across the ABI) ----
 void set_error(const char* fmt, ...);
 extern std::atomic<uint64_t> g_launches;
+extern std::atomic<uint64_t> g_tc_launches;
 
 #define CSWIN_REQUIRE(cond, code, ...)            \
   do {                                            \

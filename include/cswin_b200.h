@@ -47,6 +47,8 @@ int cswin_abi_version(void);
 const char* cswin_last_error(void);
 /* number of kernels this library has launched in the calling process (for bench.py's gpu_launches) */
 uint64_t cswin_launch_count(void);
+/* ... of which tcgen05 / TMEM / TMA kernels (attention_tc.cu, gemm_tc.cu); lets tests assert the tensor-core path ran */
+uint64_t cswin_tc_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------------
  * LePE cross-shaped-window attention.

@@ -63,8 +63,11 @@ def test_lepe_attention_fp32_vs_golden(tag, cfgs, B):
 def test_lepe_attention_bf16_vs_oracle(tag, cfgs, B):
     for (cb, reso, idx, split, heads) in cfgs:
         m, qkv = lepe_case(cb, reso, idx, split, heads, B, torch.bfloat16)
+        t0 = cw.tc_launch_count()
         with torch.no_grad():
             y = m(qkv).float().cpu()
+        if cb // heads == 32 and m.H_sp * m.W_sp <= 128:
+            assert cw.tc_launch_count() == t0 + 1, "the tcgen05 attention kernel must serve head_dim 32, N <= 128"
         q, k, v = (qkv[i].float().cpu().double() for i in range(3))            # bf16-rounded inputs, exact in fp64
         w = m.get_v.weight.detach().bfloat16().double().cpu()
         b = m.get_v.bias.detach().bfloat16().double().cpu()
