@@ -1,8 +1,247 @@
-// gemm_tc.cu — bf16 tcgen05 / TMEM / TMA Linear (placeholder until the kernel lands).
+// gemm_tc.cu — bf16 Linear on tcgen05 / TMEM / TMA with the fused epilogue of cswin_linear_fwd (sm_100a).
+//
+//   out[m,n] = residual[m,n] + sample_scale[m / rps] * act( sum_k [a | a2][m,k] * w[n,k] + bias[n] )
+//
+// Replaces nn.Linear and the separate element-wise kernels of the reference around it (networks/cswin_unet.py:169,
+// :177-178, Mlp :22-26 + :179, concat_linear :509-527, and the 1x1 / im2col'ed convs :216, :240-241, :264, :339, :542).
+//
+// One 128 x BN output tile per CTA (BN = 16..256, picked so that the grid covers the 148 SMs at least twice where the
+// problem allows), K consumed in 64-wide blocks (128-byte rows, 128-byte swizzle) through a 1..4 stage TMA -> smem
+// ring.  Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread tcgen05.mma issuer,
+// warps 2..5 = epilogue.  The two-source form ([skip | x] for the decoder's concat Linears) switches tensor maps
+// at the K1 boundary, so the concatenated activation is never materialised.  Ragged M / N / K tails are handled by
+// TMA out-of-bounds zero fill on the loads and by predicated stores.
+//
+// Epilogue (per warp = 32 accumulator rows, 64 columns at a time): tcgen05.ld -> bias / GELU(erf) / DropPath scale in
+// fp32 registers -> fp32 staging tile in shared memory (XOR-swizzled 16-byte chunks, conflict-free) -> read back
+// row-contiguous so that the residual load and the output store are fully coalesced 16-byte accesses.
 #include "common.cuh"
+#include "tc_common.cuh"
+
 namespace cswin {
-int linear_fwd_tc(const cswin_linear_args_t*, cudaStream_t, bool* handled) {
+namespace {
+
+using namespace tc;
+
+constexpr int BM = 128, BK = 64;
+constexpr int kMaxStages = 4;
+constexpr int kThreads = 192;
+constexpr int kStageEpiBytes = 4 * 32 * 64 * 4;        // 4 warps x (32 rows x 64 cols fp32) = 32 KB
+
+struct alignas(64) GemmTcParams {
+  CUtensorMap map_a, map_a2, map_w;
+  const __nv_bfloat16* bias;
+  const __nv_bfloat16* res; int64_t ldr;
+  const float* sscale; int rps;
+  __nv_bfloat16* out; int64_t ldo;
+  int64_t M; int N; int K1; int K2;
+  int BN, stages, nkb, nkb1, act, tmem_cols, vec_ok;
+};
+
+__global__ void __launch_bounds__(kThreads) linear_tc_kernel(const __grid_constant__ GemmTcParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int BN = P.BN, S = P.stages;
+  const uint32_t a_bytes = BM * BK * 2, w_bytes = (uint32_t)BN * BK * 2;
+  uint8_t* As = smem;                                   // [S][128][64] bf16, SW128
+  uint8_t* Ws = As + (size_t)S * a_bytes;               // [S][BN][64]
+  float* Epi = reinterpret_cast<float*>(Ws + (size_t)S * w_bytes);       // [4][32][64] fp32 (swizzled)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(Epi) + kStageEpiBytes);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t m0 = (int64_t)blockIdx.x * BM;
+  const int n0 = blockIdx.y * BN;
+
+  auto full = [&](int s) { return smem_u32(&bars[s]); };
+  auto empty = [&](int s) { return smem_u32(&bars[kMaxStages + s]); };
+  const uint32_t bar_acc = smem_u32(&bars[2 * kMaxStages]);
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
+    mbar_init(bar_acc, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&P.map_a); tma_prefetch_desc(&P.map_w);
+    if (P.K2 > 0) tma_prefetch_desc(&P.map_a2);
+  }
+  if (warp == 1) { tmem_alloc(smem_u32(tmem_slot), (uint32_t)P.tmem_cols); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {                                    // ---- TMA producer ----
+      for (int kb = 0; kb < P.nkb; ++kb) {
+        const int s = kb % S;
+        if (kb >= S) mbar_wait(empty(s), ((kb / S) - 1) & 1);
+        mbar_expect_tx(full(s), a_bytes + w_bytes);
+        if (kb < P.nkb1) tma_load_2d(smem_u32(As + (size_t)s * a_bytes), &P.map_a, full(s), kb * BK, (int)m0);
+        else             tma_load_2d(smem_u32(As + (size_t)s * a_bytes), &P.map_a2, full(s), (kb - P.nkb1) * BK, (int)m0);
+        tma_load_2d(smem_u32(Ws + (size_t)s * w_bytes), &P.map_w, full(s), kb * BK, n0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {                                    // ---- MMA issuer ----
+      const uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
+      for (int kb = 0; kb < P.nkb; ++kb) {
+        const int s = kb % S;
+        mbar_wait(full(s), (kb / S) & 1);
+        tc_fence_after();
+        const uint64_t ad = make_smem_desc(smem_u32(As + (size_t)s * a_bytes), 16, 1024, kLayoutSw128);
+        const uint64_t wd = make_smem_desc(smem_u32(Ws + (size_t)s * w_bytes), 16, 1024, kLayoutSw128);
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) mma_ss(tmem_base, ad + 2 * k, wd + 2 * k, idesc, (kb | k) != 0);
+        tc_commit(empty(s));                            // smem slot reusable once these MMAs have read it
+      }
+      tc_commit(bar_acc);                               // accumulator complete
+    }
+  } else {                                              // ---- epilogue warps 2..5 ----
+    const int q = warp & 3;                             // TMEM lane quadrant this warp may touch
+    float* stg = Epi + (warp - 2) * (32 * 64);
+    const int64_t mrow = m0 + q * 32 + lane;            // accumulator row held by this thread
+    const float sc = (P.sscale != nullptr && mrow < P.M) ? P.sscale[mrow / P.rps] : 1.0f;
+    mbar_wait(bar_acc, 0);
+    tc_fence_after();
+    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+    for (int g = 0; g * 64 < BN; ++g) {
+      // 1. accumulators -> registers -> bias / act / scale -> swizzled fp32 staging (row = lane)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint32_t v[32];
+        tmem_ld32(trow + g * 64 + h * 32, v);
+        tmem_wait_ld();
+        const int nb = n0 + g * 64 + h * 32;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          float t[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int n = nb + j + e;
+            float x = __uint_as_float(v[j + e]);
+            if (P.bias != nullptr && n < P.N) x += __bfloat162float(P.bias[n]);
+            if (P.act == 1) x = gelu_erf(x);
+            t[e] = x * sc;
+          }
+          const int chunk = (h * 32 + j) >> 2;          // 16-byte chunk index 0..15 inside the 256-byte row
+          *reinterpret_cast<float4*>(stg + lane * 64 + ((chunk ^ (lane & 7)) << 2)) = make_float4(t[0], t[1], t[2], t[3]);
+        }
+      }
+      __syncwarp();
+      // 2. read back row-contiguous: 8 lanes cover the 64 columns (8 each) of one row; 4 rows per pass, 8 passes
+#pragma unroll
+      for (int pass = 0; pass < 8; ++pass) {
+        const int r = pass * 4 + (lane >> 3);
+        const int c8 = lane & 7;                         // columns c8*8 .. c8*8+7
+        const int64_t m = m0 + q * 32 + r;
+        const int n = n0 + g * 64 + c8 * 8;
+        const float4 lo = *reinterpret_cast<const float4*>(stg + r * 64 + (((2 * c8) ^ (r & 7)) << 2));
+        const float4 hi = *reinterpret_cast<const float4*>(stg + r * 64 + (((2 * c8 + 1) ^ (r & 7)) << 2));
+        float f[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+        if (m < P.M && n < P.N && g * 64 + c8 * 8 < BN) {
+          __nv_bfloat16* dst = P.out + m * P.ldo + n;
+          if (P.vec_ok && n + 8 <= P.N) {
+            if (P.res != nullptr) {
+              const uint4 rv = *reinterpret_cast<const uint4*>(P.res + m * P.ldr + n);
+              f[0] += bf16_lo(rv.x); f[1] += bf16_hi(rv.x); f[2] += bf16_lo(rv.y); f[3] += bf16_hi(rv.y);
+              f[4] += bf16_lo(rv.z); f[5] += bf16_hi(rv.z); f[6] += bf16_lo(rv.w); f[7] += bf16_hi(rv.w);
+            }
+            *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
+                                                        pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+          } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              if (n + e < P.N) {
+                float x = f[e];
+                if (P.res != nullptr) x += __bfloat162float(P.res[m * P.ldr + n + e]);
+                dst[e] = __float2bfloat16_rn(x);
+              }
+            }
+          }
+        }
+      }
+      __syncwarp();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)P.tmem_cols);
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+int pick_bn(int64_t M, int N, int sms) {
+  if (N <= 64) return (N + 15) & ~15;
+  const int64_t mt = (M + BM - 1) / BM;
+  const int cands[] = {256, 192, 128, 64};
+  for (int bn : cands) {
+    if (bn > N && bn != 64) continue;
+    if (N % bn != 0 && !(bn == 64)) continue;
+    const int64_t tiles = mt * ((N + bn - 1) / bn);
+    if (tiles >= 2 * (int64_t)sms || bn == 64) return bn;
+  }
+  return 64;
+}
+
+}  // namespace
+
+int linear_fwd_tc(const cswin_linear_args_t* a, cudaStream_t stream, bool* handled) {
   *handled = false;
+  if (a->ln_gamma != nullptr) return CSWIN_OK;                               // LayerNorm prologue: SIMT kernel (host calls LN first on the bf16 path)
+  const int K = a->K1 + a->K2;
+  if (!aligned16(a->a) || !aligned16(a->w) || (a->lda * 2) % 16 || (a->ldw * 2) % 16) return CSWIN_OK;
+  if (a->K1 % 8 || K % 8) return CSWIN_OK;
+  if (a->a2 && (!aligned16(a->a2) || (a->lda2 * 2) % 16 || a->K1 % BK || a->K2 % 8)) return CSWIN_OK;
+  if (a->M > 0x7fffffff) return CSWIN_OK;
+  if (tc::encode_tiled_fn() == nullptr) return CSWIN_OK;
+
+  GemmTcParams P;
+  P.bias = (const __nv_bfloat16*)a->bias;
+  P.res = (const __nv_bfloat16*)a->residual; P.ldr = a->ldr;
+  P.sscale = a->sample_scale; P.rps = a->rows_per_sample > 0 ? a->rows_per_sample : 1;
+  P.out = (__nv_bfloat16*)a->out; P.ldo = a->ldo;
+  P.M = a->M; P.N = a->N; P.K1 = a->K1; P.K2 = a->K2; P.act = a->act;
+  P.BN = pick_bn(a->M, a->N, sm_count());
+  P.nkb1 = (a->K1 + BK - 1) / BK;
+  P.nkb = P.nkb1 + (a->K2 + BK - 1) / BK;
+  P.stages = P.nkb < kMaxStages ? P.nkb : (P.BN > 128 ? 3 : kMaxStages);
+  P.tmem_cols = P.BN <= 64 ? 64 : P.BN <= 128 ? 128 : 256;      // the epilogue reads whole 64-column groups
+  P.vec_ok = aligned16(a->out) && (a->ldo * 2) % 16 == 0 &&
+             (a->residual == nullptr || (aligned16(a->residual) && (a->ldr * 2) % 16 == 0));
+
+  {
+    const uint64_t dims[2] = {(uint64_t)a->K1, (uint64_t)a->M};
+    const uint64_t str[1] = {(uint64_t)a->lda * 2};
+    const uint32_t box[2] = {BK, BM};
+    if (!tc::make_tensor_map_bf16(&P.map_a, a->a, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return CSWIN_ERR_CUDA;
+  }
+  if (a->a2) {
+    const uint64_t dims[2] = {(uint64_t)a->K2, (uint64_t)a->M};
+    const uint64_t str[1] = {(uint64_t)a->lda2 * 2};
+    const uint32_t box[2] = {BK, BM};
+    if (!tc::make_tensor_map_bf16(&P.map_a2, a->a2, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return CSWIN_ERR_CUDA;
+  } else {
+    P.map_a2 = P.map_a;
+  }
+  {
+    const uint64_t dims[2] = {(uint64_t)K, (uint64_t)a->N};
+    const uint64_t str[1] = {(uint64_t)a->ldw * 2};
+    const uint32_t box[2] = {BK, (uint32_t)P.BN};
+    if (!tc::make_tensor_map_bf16(&P.map_w, a->w, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return CSWIN_ERR_CUDA;
+  }
+
+  const size_t smem = 1024 + (size_t)P.stages * (BM * BK * 2 + (size_t)P.BN * BK * 2) + kStageEpiBytes + 128;
+  static std::atomic<size_t> configured{0};
+  if (smem > configured.load(std::memory_order_relaxed)) {
+    CSWIN_CUDA_OK(cudaFuncSetAttribute(linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured.store(227 * 1024, std::memory_order_relaxed);
+  }
+  dim3 grid((unsigned)((a->M + BM - 1) / BM), (unsigned)((a->N + P.BN - 1) / P.BN));
+  linear_tc_kernel<<<grid, kThreads, smem, stream>>>(P);
+  CSWIN_LAUNCH_CHECK();
+  g_tc_launches.fetch_add(1, std::memory_order_relaxed);
+  *handled = true;
   return CSWIN_OK;
 }
+
 }  // namespace cswin

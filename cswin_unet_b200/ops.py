@@ -133,6 +133,11 @@ def linear(a: Tensor, w: Tensor, bias: Optional[Tensor] = None, *, a2: Optional[
            n_out: Optional[int] = None) -> Tensor:
     """out = residual + sample_scale[row // rows_per_sample] * act(LN?([a | a2]) @ w[:n_out].T + bias)."""
     _need_cuda(a, w, bias, a2, residual, sample_scale)
+    if ln is not None and a.dtype == torch.bfloat16:
+        # bf16 / tcgen05 path: the operand is normalised in fp32 and rounded to bf16 ONCE by the LayerNorm kernel,
+        # then streamed by TMA (the fp32 SIMT kernel fuses the normalisation into its operand load instead)
+        a = layernorm(a, ln[0], ln[1], ln[2])
+        ln = None
     a_, M, lda = _rows(a)
     K1 = a.shape[-1]
     args = LinearArgs()
