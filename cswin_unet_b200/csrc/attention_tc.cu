@@ -3,7 +3,8 @@
 // Replaces LePEAttention.forward and everything it calls (networks/cswin_unet.py:59-109, 184-202) plus the branch
 // concat of CSWinBlock.forward (:172-176).  Both stripe branches of a block run in ONE launch.
 //
-// Work unit ("tile") = 128 query rows = 128 TMEM lanes = 128 threads:
+// Work unit ("tile") = 128 query rows = 128 TMEM lanes, served by 256 threads (two threads per row, each owning
+// half of the row's key columns / output channels):
 //     windows of N <= 64 tokens   : two (window, head) problems per tile (rows 0..63 and 64..127),
 //     windows of 64 < N <= 128    : one problem per tile.
 // Per tile
@@ -13,14 +14,14 @@
 //      tensor map;
 //   2. S = Q K^T: two tcgen05.mma (M128 x N<=128 x K16, both operands K-major from smem), fp32 in TMEM columns
 //      [0,128).  With two problems per tile the off-diagonal 64x64 blocks are computed and ignored;
-//   3. softmax: thread i reads row i of S from TMEM (tcgen05.ld 32x32b), exact max / exp2 / sum in fp32 with the
-//      qk scale folded into the exponent, writes bf16 P back into TMEM columns [0,64) (zeros for padded keys and
-//      for the other problem's keys);
+//   3. softmax: the two threads of row i read their halves of S row i from TMEM (tcgen05.ld 32x32b), exchange the
+//      row max through smem, exponentiate in fp32 (ex2.approx with the qk scale folded in) and write bf16 P back
+//      into TMEM columns [0,64) (zeros for padded keys and for the other problem's keys);
 //   4. O = P V: tcgen05.mma with A = P from TMEM and B = V from smem (MN-major, the layout TMA delivered),
 //      N = 32, accumulating in TMEM columns [64,96);
-//   5. while that runs, thread i computes the LePE depthwise 3x3 conv for its token from the same V tile in smem
-//      (zero padding at the WINDOW border), then adds it to O / rowsum and stores 64 B straight into the
-//      (B, L, C) concat layout (windows2img + cat are address arithmetic).
+//   5. while that runs, each thread computes the LePE depthwise 3x3 conv of its token for its 16 channels from the
+//      same V tile in smem (zero padding at the WINDOW border), then adds it to O / rowsum and stores 32 B
+//      straight into the (B, L, C) concat layout (windows2img + cat are address arithmetic).
 // HBM traffic = q, k, v read once + out written once; the N x N scores never leave TMEM.
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -43,16 +44,23 @@ struct alignas(64) TcParams {
 };
 
 constexpr int kTileRows = 128;
-constexpr int kRowBytes = 64;                       // 32 bf16 channels of one head
+constexpr int kThreads = 256;
+constexpr int kRowBytes = 64;                         // 32 bf16 channels of one head
 constexpr int kOperandBytes = kTileRows * kRowBytes;  // 8 KB
 constexpr uint32_t kTmemCols = 128;
-constexpr int kSmemBytes = 3 * kOperandBytes + 2 * 9 * 32 * 4 + 2 * 32 * 4 + 64 + 1024;
+//                         Q,K,V               Wt[2][9][32]     Bc[2][32]    xchg[2][128]   barriers   align slack
+constexpr int kSmemBytes = 3 * kOperandBytes + 2 * 9 * 32 * 4 + 2 * 32 * 4 + 2 * 128 * 4 + 64 + 1024;
 
 __device__ __forceinline__ uint32_t v_chunk_addr(uint32_t vbase, int row, int chunk) {
   return vbase + row * kRowBytes + (((chunk ^ (row >> 1)) & 3) << 4);          // Swizzle<2,4,3> (64-byte swizzle)
 }
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
-__global__ void __launch_bounds__(128, 4) lepe_attn_fwd_tc_kernel(const __grid_constant__ TcParams P) {
+__global__ void __launch_bounds__(kThreads, 3) lepe_attn_fwd_tc_kernel(const __grid_constant__ TcParams P) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* Qs = smem;
@@ -60,10 +68,14 @@ __global__ void __launch_bounds__(128, 4) lepe_attn_fwd_tc_kernel(const __grid_c
   uint8_t* Vs = smem + 2 * kOperandBytes;
   float* Wt = reinterpret_cast<float*>(smem + 3 * kOperandBytes);     // [2][9][32]
   float* Bc = Wt + 2 * 9 * 32;                                        // [2][32]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(Bc + 2 * 32);          // tma, s, o
+  float* Xmax = Bc + 2 * 32;                                          // [2 halves][128 rows]
+  float* Xsum = Xmax;                                                 // reused after the max exchange
+  uint64_t* bars = reinterpret_cast<uint64_t*>(Xmax + 2 * 128);       // tma, s, o
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
 
   const int tid = threadIdx.x, warp = tid >> 5;
+  const int row = tid & 127;                   // tile row == TMEM lane
+  const int half = tid >> 7;                   // which half of the row's columns / channels this thread owns
   const int bi = (P.nb > 1 && (int)blockIdx.x >= P.br[1].tile_begin) ? 1 : 0;
   const TcBranch& br = P.br[bi];
   const int tile = blockIdx.x - br.tile_begin;
@@ -74,18 +86,17 @@ __global__ void __launch_bounds__(128, 4) lepe_attn_fwd_tc_kernel(const __grid_c
   const int np = min(slots, br.nprob - p0);
   const int kext = (slots == 2) ? 128 : ((N + 15) & ~15);            // kv extent fed to the P.V MMA
 
-  const int slot = tid / slot_rows;            // warp-uniform
-  const int n = tid - slot * slot_rows;        // token index inside the window
+  const int slot = row / slot_rows;            // warp-uniform
+  const int n = row - slot * slot_rows;        // token index inside the window
 
-  // decode the (batch, window, head) of both slots (cheap; every thread needs its own, thread 0 needs both)
-  int pb[2], pih[2], piw[2], phead[2];
-#pragma unroll
-  for (int s = 0; s < 2; ++s) {
-    int local = p0 + min(s, np - 1);
-    phead[s] = local % br.heads; local /= br.heads;
+  // (batch, window, head) of my slot, and of both slots for the TMA-issuing thread
+  int mb, mih, miw, mhead;
+  {
+    int local = p0 + min(slot, np - 1);
+    mhead = local % br.heads; local /= br.heads;
     const int win = local % br.nwin;
-    pb[s] = local / br.nwin;
-    pih[s] = win / br.nww; piw[s] = win - pih[s] * br.nww;
+    mb = local / br.nwin;
+    mih = win / br.nww; miw = win - mih * br.nww;
   }
 
   const uint32_t bar_tma = smem_u32(&bars[0]), bar_s = smem_u32(&bars[1]), bar_o = smem_u32(&bars[2]);
@@ -93,18 +104,29 @@ __global__ void __launch_bounds__(128, 4) lepe_attn_fwd_tc_kernel(const __grid_c
   if (tid == 32) { mbar_init(bar_tma, 1); mbar_init(bar_s, 1); mbar_init(bar_o, 1); fence_barrier_init(); }
 
   // zero the V rows the P.V MMA reads but TMA does not write (0 * stale-NaN would poison O)
-  for (int i = tid; i < kTileRows * 4; i += 128) {
-    const int row = i >> 2;
-    const int s = row / slot_rows, rn = row - s * slot_rows;
-    if (row < kext && (s >= np || rn >= N)) *reinterpret_cast<uint4*>(Vs + i * 16) = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < kTileRows * 4; i += kThreads) {
+    const int r = i >> 2;
+    const int s = r / slot_rows, rn = r - s * slot_rows;
+    if (r < kext && (s >= np || rn >= N)) *reinterpret_cast<uint4*>(Vs + i * 16) = make_uint4(0, 0, 0, 0);
   }
-  // stage the LePE weights of the head(s) of this tile: Wt[slot][tap][ch], Bc[slot][ch]
-  for (int i = tid; i < np * 288; i += 128) {
-    const int s = i / 288, r = i - s * 288;
-    const int ch = r / 9, t = r - ch * 9;
-    Wt[(s * 9 + t) * 32 + ch] = __bfloat162float(br.cw[(phead[s] * 32 + ch) * 9 + t]);
+  // stage the LePE weights of the head(s) of this tile: 288 contiguous bf16 per head -> Wt[slot][tap][ch] fp32
+  if (tid < np * 36) {
+    const int s = tid / 36, i = tid - s * 36;                         // 36 x 16-byte chunks per head
+    int local = p0 + s;
+    const int hd = local % br.heads;
+    const uint4 raw = *reinterpret_cast<const uint4*>(br.cw + (size_t)hd * 288 + i * 8);
+    const uint32_t w4[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int idx = i * 8 + e;                                       // = ch * 9 + tap
+      const int ch = idx / 9, t = idx - ch * 9;
+      Wt[(s * 9 + t) * 32 + ch] = (e & 1) ? bf16_hi(w4[e >> 1]) : bf16_lo(w4[e >> 1]);
+    }
+  } else if (tid >= 128 && tid < 128 + np * 32) {
+    const int s = (tid - 128) >> 5, ch = tid & 31;
+    const int hd = (p0 + s) % br.heads;
+    Bc[s * 32 + ch] = __bfloat162float(br.cb[hd * 32 + ch]);
   }
-  if (tid < np * 32) Bc[tid] = __bfloat162float(br.cb[phead[tid >> 5] * 32 + (tid & 31)]);
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
@@ -114,16 +136,18 @@ __global__ void __launch_bounds__(128, 4) lepe_attn_fwd_tc_kernel(const __grid_c
   if (tid == 0) {
     mbar_expect_tx(bar_tma, (uint32_t)(np * 3 * N * kRowBytes));
     for (int s = 0; s < np; ++s) {
-      const int c0 = phead[s] * 32, c1 = piw[s] * ws, c2 = pih[s] * hs, c3 = pb[s];
+      int local = p0 + s;
+      const int hd = local % br.heads; local /= br.heads;
+      const int win = local % br.nwin;
+      const int b = local / br.nwin;
+      const int ih = win / br.nww, iw = win - ih * br.nww;
+      const int c0 = hd * 32, c1 = iw * ws, c2 = ih * hs, c3 = b;
       const uint32_t off = s * slot_rows * kRowBytes;
       tma_load_4d(smem_u32(Qs) + off, &P.map[bi][0], bar_tma, c0, c1, c2, c3);
       tma_load_4d(smem_u32(Ks) + off, &P.map[bi][1], bar_tma, c0, c1, c2, c3);
       tma_load_4d(smem_u32(Vs) + off, &P.map[bi][2], bar_tma, c0, c1, c2, c3);
     }
-  }
-  mbar_wait(bar_tma, 0);
-
-  if (tid == 0) {
+    mbar_wait(bar_tma, 0);
     tc_fence_after();
     const uint64_t qd = make_smem_desc(smem_u32(Qs), 16, 8 * kRowBytes, kLayoutSw64);
     const uint64_t kd = make_smem_desc(smem_u32(Ks), 16, 8 * kRowBytes, kLayoutSw64);
@@ -135,43 +159,74 @@ __global__ void __launch_bounds__(128, 4) lepe_attn_fwd_tc_kernel(const __grid_c
   mbar_wait(bar_s, 0);
   tc_fence_after();
 
-  // ---- softmax on row `tid` of S ----
-  const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
-  const int col0 = slot * slot_rows;                         // first S column of my problem
-  const int nchunks = (slots == 2) ? 2 : (kext + 31) / 32;
+  // ---- softmax: this thread owns columns [cbeg, cbeg + hcols) of S row `row` (slot-local key index kbeg..) ----
+  const uint32_t trow = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+  const int hcols = slot_rows >> 1;                          // 32 (two problems) or 64 (one problem)
+  const int kbeg = half * hcols;                             // first slot-local key of my half
+  const int cbeg = slot * slot_rows + kbeg;                  // first S column of my half
+  const int nch = hcols >> 5;                                // chunks of 32 columns: 1 or 2
   float mx = -INFINITY;
-  for (int c = 0; c < nchunks; ++c) {
+  for (int c = 0; c < nch; ++c) {
+    if (kbeg + 32 * c >= kext) break;                        // (one-problem mode) chunk entirely beyond the keys
     uint32_t v[32];
-    tmem_ld32(trow + col0 + 32 * c, v);
+    tmem_ld32(trow + cbeg + 32 * c, v);
     tmem_wait_ld();
+    const int lim = N - (kbeg + 32 * c);                     // valid columns in this chunk
+    if (lim >= 32) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j)
-      if (32 * c + j < N) mx = fmaxf(mx, __uint_as_float(v[j]));
-  }
-  float sum = 0.f;
-  const float mxs = mx * P.scale_log2e;
-  for (int c = 0; c < nchunks; ++c) {
-    uint32_t v[32], pk[16];
-    tmem_ld32(trow + col0 + 32 * c, v);
-    tmem_wait_ld();
+      for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
+    } else {
 #pragma unroll
-    for (int j = 0; j < 32; j += 2) {
-      float e0 = 0.f, e1 = 0.f;
-      if (32 * c + j < N) e0 = exp2f(fmaf(__uint_as_float(v[j]), P.scale_log2e, -mxs));
-      if (32 * c + j + 1 < N) e1 = exp2f(fmaf(__uint_as_float(v[j + 1]), P.scale_log2e, -mxs));
-      // sum what the MMA will actually see (bf16-rounded probabilities) so rows stay normalised
-      const uint32_t pr = pack_bf16x2(e0, e1);
-      sum += bf16_lo(pr) + bf16_hi(pr);
-      pk[j >> 1] = pr;
+      for (int j = 0; j < 32; ++j) if (j < lim) mx = fmaxf(mx, __uint_as_float(v[j]));
     }
-    tmem_st16(trow + (col0 >> 1) + 16 * c, pk);
   }
-  if (slots == 2) {                                          // keys of the other problem: P = 0
-    uint32_t z[32];
+  Xmax[half * 128 + row] = mx;
+  __syncthreads();
+  mx = fmaxf(mx, Xmax[(half ^ 1) * 128 + row]);
+  const float mxs = mx * P.scale_log2e;
+  float sum = 0.f;
+  uint32_t pk[2][16];                                        // bf16 P of my columns, held until every S read is done
 #pragma unroll
-    for (int j = 0; j < 32; ++j) z[j] = 0u;
-    tmem_st32(trow + ((1 - slot) * 32), z);
+  for (int c = 0; c < 2; ++c) {
+    if (c < nch && kbeg + 32 * c < kext) {
+      uint32_t v[32];
+      tmem_ld32(trow + cbeg + 32 * c, v);
+      tmem_wait_ld();
+      const int lim = N - (kbeg + 32 * c);
+      if (lim >= 32) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          const float e0 = ex2_approx(fmaf(__uint_as_float(v[j]), P.scale_log2e, -mxs));
+          const float e1 = ex2_approx(fmaf(__uint_as_float(v[j + 1]), P.scale_log2e, -mxs));
+          const uint32_t pr = pack_bf16x2(e0, e1);
+          sum += bf16_lo(pr) + bf16_hi(pr);                  // sum what the MMA will see (bf16-rounded P)
+          pk[c][j >> 1] = pr;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          const float e0 = (j < lim) ? ex2_approx(fmaf(__uint_as_float(v[j]), P.scale_log2e, -mxs)) : 0.f;
+          const float e1 = (j + 1 < lim) ? ex2_approx(fmaf(__uint_as_float(v[j + 1]), P.scale_log2e, -mxs)) : 0.f;
+          const uint32_t pr = pack_bf16x2(e0, e1);
+          sum += bf16_lo(pr) + bf16_hi(pr);
+          pk[c][j >> 1] = pr;
+        }
+      }
+    }
   }
+  // P (bf16, TMEM columns [0,64)) aliases S columns that the partner thread of this row may still be reading:
+  // publish only after every thread has its S values in registers.
+  __syncthreads();
+#pragma unroll
+  for (int c = 0; c < 2; ++c)
+    if (c < nch && kbeg + 32 * c < kext) tmem_st16(trow + ((cbeg + 32 * c) >> 1), pk[c]);
+  if (slots == 2) {                                          // keys of the other problem: P = 0 (16 of its 32 cols each)
+    uint32_t z[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) z[j] = 0u;
+    tmem_st16(trow + ((1 - slot) * 32) + half * 16, z);
+  }
+  Xsum[half * 128 + row] = sum;
   tmem_wait_st();
   tc_fence_before();
   __syncthreads();
@@ -184,29 +239,31 @@ __global__ void __launch_bounds__(128, 4) lepe_attn_fwd_tc_kernel(const __grid_c
       mma_ts(tmem_base + 64, tmem_base + 8 * k, vd + (uint64_t)k * ((16 * kRowBytes) >> 4), idesc, k > 0);
     tc_commit(bar_o);
   }
+  sum += Xsum[(half ^ 1) * 128 + row];
 
-  // ---- LePE for my token, overlapped with the P.V MMA ----
+  // ---- LePE for my token, channels [16*half, 16*half+16), overlapped with the P.V MMA ----
+  mbar_wait(bar_tma, 0);                                     // (already complete) acquire the TMA-written V tile
   const bool valid = slot < np && n < N;
-  float lp[32];
+  const int r = n / ws, c = n - r * ws;
+  float lp[16];
   {
-    const float* bc = Bc + min(slot, np - 1) * 32;
+    const float* bc = Bc + min(slot, np - 1) * 32 + half * 16;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) lp[j] = bc[j];
+    for (int j = 0; j < 16; ++j) lp[j] = bc[j];
   }
   if (valid) {
-    const int r = n / ws, c = n - r * ws;
     const uint32_t vbase = smem_u32(Vs);
-    const float* wt = Wt + slot * 9 * 32;
+    const float* wt = Wt + slot * 9 * 32 + half * 16;
 #pragma unroll
     for (int t = 0; t < 9; ++t) {
       const int rr = r + t / 3 - 1, cc = c + t % 3 - 1;
       if (rr >= 0 && rr < hs && cc >= 0 && cc < ws) {
-        const int row = slot * slot_rows + rr * ws + cc;
+        const int vr = slot * slot_rows + rr * ws + cc;
 #pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
+        for (int ch = 0; ch < 2; ++ch) {
           uint4 vv;
           asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(vv.x), "=r"(vv.y), "=r"(vv.z), "=r"(vv.w)
-                       : "r"(v_chunk_addr(vbase, row, ch)));
+                       : "r"(v_chunk_addr(vbase, vr, half * 2 + ch)));
           const float4 w0 = *reinterpret_cast<const float4*>(wt + t * 32 + ch * 8);
           const float4 w1 = *reinterpret_cast<const float4*>(wt + t * 32 + ch * 8 + 4);
           lp[ch * 8 + 0] = fmaf(w0.x, bf16_lo(vv.x), lp[ch * 8 + 0]);
@@ -225,23 +282,25 @@ __global__ void __launch_bounds__(128, 4) lepe_attn_fwd_tc_kernel(const __grid_c
   mbar_wait(bar_o, 0);
   tc_fence_after();
   {
-    uint32_t o[32];
-    tmem_ld32(trow + 64, o);
+    uint32_t o[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(o[0]), "=r"(o[1]), "=r"(o[2]), "=r"(o[3]), "=r"(o[4]), "=r"(o[5]), "=r"(o[6]), "=r"(o[7]), "=r"(o[8]),
+          "=r"(o[9]), "=r"(o[10]), "=r"(o[11]), "=r"(o[12]), "=r"(o[13]), "=r"(o[14]), "=r"(o[15])
+        : "r"(trow + 64 + half * 16) : "memory");
     tmem_wait_ld();
     if (valid) {
       const float inv = 1.0f / sum;
-      const int r = n / ws, c = n - r * ws;
-      const int64_t tok = (int64_t)(pih[slot] * hs + r) * P.reso + (piw[slot] * ws + c);
-      __nv_bfloat16* dst = br.out + (int64_t)pb[slot] * br.o_bs + tok * br.o_ts + phead[slot] * 32;
-      uint32_t w[16];
+      const int64_t tok = (int64_t)(mih * hs + r) * P.reso + (miw * ws + c);
+      __nv_bfloat16* dst = br.out + (int64_t)mb * br.o_bs + tok * br.o_ts + mhead * 32 + half * 16;
+      uint32_t w[8];
 #pragma unroll
-      for (int j = 0; j < 16; ++j)
+      for (int j = 0; j < 8; ++j)
         w[j] = pack_bf16x2(fmaf(__uint_as_float(o[2 * j]), inv, lp[2 * j]), fmaf(__uint_as_float(o[2 * j + 1]), inv, lp[2 * j + 1]));
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        *reinterpret_cast<uint4*>(dst + 8 * j) = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
-      if (br.lse != nullptr)
-        br.lse[((int64_t)pb[slot] * P.reso * P.reso + tok) * br.heads + phead[slot]] = mx * P.scale + logf(sum);
+      *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+      *reinterpret_cast<uint4*>(dst + 8) = make_uint4(w[4], w[5], w[6], w[7]);
+      if (br.lse != nullptr && half == 0)
+        br.lse[((int64_t)mb * P.reso * P.reso + tok) * br.heads + mhead] = mx * P.scale + logf(sum);
     }
   }
   tc_fence_before();
@@ -265,7 +324,7 @@ int lepe_attention_fwd_tc(const cswin_lepe_branch_t* brs, int nb, int B, int res
     if (s.H_sp * s.W_sp > 128 || s.H_sp > 256 || s.W_sp > 256) return CSWIN_OK;
     const int64_t strides[] = {s.q_bs, s.q_ts, s.k_bs, s.k_ts, s.v_bs, s.v_ts, s.o_bs, s.o_ts};
     for (int64_t st : strides) if (st <= 0 || (st * 2) % 16 != 0) return CSWIN_OK;
-    if (!aligned16(s.q) || !aligned16(s.k) || !aligned16(s.v) || !aligned16(s.out)) return CSWIN_OK;
+    if (!aligned16(s.q) || !aligned16(s.k) || !aligned16(s.v) || !aligned16(s.out) || !aligned16(s.conv_w)) return CSWIN_OK;
   }
   if (tc::encode_tiled_fn() == nullptr) return CSWIN_OK;
 
@@ -294,7 +353,7 @@ int lepe_attention_fwd_tc(const cswin_lepe_branch_t* brs, int nb, int B, int res
   }
   if (nb == 1) P.br[1] = P.br[0];
   static_assert(kSmemBytes <= 48 * 1024, "dynamic smem must stay under the no-opt-in limit");
-  lepe_attn_fwd_tc_kernel<<<tiles, 128, kSmemBytes, stream>>>(P);
+  lepe_attn_fwd_tc_kernel<<<tiles, kThreads, kSmemBytes, stream>>>(P);
   CSWIN_LAUNCH_CHECK();
   g_tc_launches.fetch_add(1, std::memory_order_relaxed);
   *handled = true;

@@ -15,6 +15,9 @@
 // Epilogue (per warp = 32 accumulator rows, 64 columns at a time): tcgen05.ld -> bias / GELU(erf) / DropPath scale in
 // fp32 registers -> fp32 staging tile in shared memory (XOR-swizzled 16-byte chunks, conflict-free) -> read back
 // row-contiguous so that the residual load and the output store are fully coalesced 16-byte accesses.
+#include <climits>
+#include <cstdlib>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -24,9 +27,9 @@ namespace {
 using namespace tc;
 
 constexpr int BM = 128, BK = 64;
-constexpr int kMaxStages = 4;
+constexpr int kMaxStages = 8;
 constexpr int kThreads = 192;
-constexpr int kStageEpiBytes = 4 * 32 * 64 * 4;        // 4 warps x (32 rows x 64 cols fp32) = 32 KB
+constexpr int kStageEpiBytes = 4 * 32 * 64 * 4;        // 4 warps x (32 rows x 64 cols fp32) = 32 KB, ALIASED onto the operand ring
 
 struct alignas(64) GemmTcParams {
   CUtensorMap map_a, map_a2, map_w;
@@ -35,18 +38,38 @@ struct alignas(64) GemmTcParams {
   const float* sscale; int rps;
   __nv_bfloat16* out; int64_t ldo;
   int64_t M; int N; int K1; int K2;
-  int BN, stages, nkb, nkb1, act, tmem_cols, vec_ok;
+  int BN, stages, nkb, nkb1, act, tmem_cols, vec_ok, bias_vec;
 };
 
-__global__ void __launch_bounds__(kThreads) linear_tc_kernel(const __grid_constant__ GemmTcParams P) {
+// GELU(erf) with erf from Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, far below bf16 resolution): one ex2 + one rcp
+// instead of the ~40-instruction erff; the fp32 SIMT path keeps erff.
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
+  float poly = fmaf(t, 1.061405429f, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  poly *= t;
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-z * z * 1.4426950408889634f));
+  const float erf_abs = fmaf(-poly, e, 1.0f);
+  return 0.5f * x * (1.0f + copysignf(erf_abs, x));
+}
+
+__global__ void __launch_bounds__(kThreads, 3) linear_tc_kernel(const __grid_constant__ GemmTcParams P) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int BN = P.BN, S = P.stages;
   const uint32_t a_bytes = BM * BK * 2, w_bytes = (uint32_t)BN * BK * 2;
   uint8_t* As = smem;                                   // [S][128][64] bf16, SW128
   uint8_t* Ws = As + (size_t)S * a_bytes;               // [S][BN][64]
-  float* Epi = reinterpret_cast<float*>(Ws + (size_t)S * w_bytes);       // [4][32][64] fp32 (swizzled)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(Epi) + kStageEpiBytes);
+  // epilogue staging [4][32][64] fp32 (swizzled) re-uses the operand ring: it is only touched after bar_acc, i.e. after
+  // every TMA load has landed and every MMA has finished reading shared memory
+  float* Epi = reinterpret_cast<float*>(smem);
+  const size_t ring = (size_t)S * (a_bytes + w_bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (ring > (size_t)kStageEpiBytes ? ring : (size_t)kStageEpiBytes));
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -99,46 +122,56 @@ __global__ void __launch_bounds__(kThreads) linear_tc_kernel(const __grid_consta
   } else {                                              // ---- epilogue warps 2..5 ----
     const int q = warp & 3;                             // TMEM lane quadrant this warp may touch
     float* stg = Epi + (warp - 2) * (32 * 64);
-    const int64_t mrow = m0 + q * 32 + lane;            // accumulator row held by this thread
-    const float sc = (P.sscale != nullptr && mrow < P.M) ? P.sscale[mrow / P.rps] : 1.0f;
     mbar_wait(bar_acc, 0);
     tc_fence_after();
     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+    const int c8 = lane & 7;                              // this lane's 8 columns inside every 64-column group
     for (int g = 0; g * 64 < BN; ++g) {
-      // 1. accumulators -> registers -> bias / act / scale -> swizzled fp32 staging (row = lane)
+      // 1. accumulators -> swizzled fp32 staging (row = lane); no arithmetic here
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         uint32_t v[32];
         tmem_ld32(trow + g * 64 + h * 32, v);
         tmem_wait_ld();
-        const int nb = n0 + g * 64 + h * 32;
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
-          float t[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int n = nb + j + e;
-            float x = __uint_as_float(v[j + e]);
-            if (P.bias != nullptr && n < P.N) x += __bfloat162float(P.bias[n]);
-            if (P.act == 1) x = gelu_erf(x);
-            t[e] = x * sc;
-          }
-          const int chunk = (h * 32 + j) >> 2;          // 16-byte chunk index 0..15 inside the 256-byte row
-          *reinterpret_cast<float4*>(stg + lane * 64 + ((chunk ^ (lane & 7)) << 2)) = make_float4(t[0], t[1], t[2], t[3]);
+          const int chunk = (h * 32 + j) >> 2;            // 16-byte chunk index 0..15 inside the 256-byte row
+          *reinterpret_cast<uint4*>(stg + lane * 64 + ((chunk ^ (lane & 7)) << 2)) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
         }
       }
       __syncwarp();
-      // 2. read back row-contiguous: 8 lanes cover the 64 columns (8 each) of one row; 4 rows per pass, 8 passes
+      // 2. read back row-contiguous: 8 lanes cover the 64 columns (8 each) of one row, 4 rows per pass, 8 passes;
+      //    bias / GELU / DropPath scale / residual happen here so that every global access is a coalesced 16 B
+      const int n = n0 + g * 64 + c8 * 8;
+      const bool col_ok = n < P.N && g * 64 + c8 * 8 < BN;
+      float bv[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) bv[e] = 0.f;
+      if (P.bias != nullptr && col_ok) {
+        if (P.bias_vec && n + 8 <= P.N) {
+          const uint4 b4 = *reinterpret_cast<const uint4*>(P.bias + n);
+          bv[0] = bf16_lo(b4.x); bv[1] = bf16_hi(b4.x); bv[2] = bf16_lo(b4.y); bv[3] = bf16_hi(b4.y);
+          bv[4] = bf16_lo(b4.z); bv[5] = bf16_hi(b4.z); bv[6] = bf16_lo(b4.w); bv[7] = bf16_hi(b4.w);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) if (n + e < P.N) bv[e] = __bfloat162float(P.bias[n + e]);
+        }
+      }
 #pragma unroll
       for (int pass = 0; pass < 8; ++pass) {
         const int r = pass * 4 + (lane >> 3);
-        const int c8 = lane & 7;                         // columns c8*8 .. c8*8+7
         const int64_t m = m0 + q * 32 + r;
-        const int n = n0 + g * 64 + c8 * 8;
         const float4 lo = *reinterpret_cast<const float4*>(stg + r * 64 + (((2 * c8) ^ (r & 7)) << 2));
         const float4 hi = *reinterpret_cast<const float4*>(stg + r * 64 + (((2 * c8 + 1) ^ (r & 7)) << 2));
         float f[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
-        if (m < P.M && n < P.N && g * 64 + c8 * 8 < BN) {
+        if (m < P.M && col_ok) {
+          const float sc = (P.sscale != nullptr) ? P.sscale[m / P.rps] : 1.0f;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            float x = f[e] + bv[e];
+            if (P.act == 1) x = gelu_fast(x);
+            f[e] = x * sc;
+          }
           __nv_bfloat16* dst = P.out + m * P.ldo + n;
           if (P.vec_ok && n + 8 <= P.N) {
             if (P.res != nullptr) {
@@ -170,17 +203,45 @@ __global__ void __launch_bounds__(kThreads) linear_tc_kernel(const __grid_consta
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
-int pick_bn(int64_t M, int N, int sms) {
-  if (N <= 64) return (N + 15) & ~15;
+size_t smem_bytes(int bn, int stages) {
+  const size_t ring = (size_t)stages * (BM * BK * 2 + (size_t)bn * BK * 2);
+  return 1024 + (ring > (size_t)kStageEpiBytes ? ring : (size_t)kStageEpiBytes) + 128;
+}
+int tmem_cols_for(int bn) { return bn <= 64 ? 64 : bn <= 128 ? 128 : 256; }      // the epilogue reads whole 64-col groups
+
+struct TileCfg { int bn, stages; };
+
+// Tile-shape choice.  At cswin_tiny sizes a Linear is a handful of waves at most, so the launch is latency- not
+// throughput-bound: the model below (constants fitted to L2-warm CUDA-event timings on B200, microseconds) trades the
+// number of waves against per-tile latency = fixed setup + K-loop (faster with a deeper ring) + epilogue (per 64
+// columns; GELU costs ~2x).  The ring depth is whatever fits once the CTAs that must share an SM are accounted for.
+// CSWIN_GEMM_BN=<n> forces BN for experiments.
+TileCfg pick_tile(int64_t M, int N, int nkb, int act, int sms) {
+  static const int forced = [] { const char* e = getenv("CSWIN_GEMM_BN"); return e ? atoi(e) : 0; }();
+  const int n16 = (N + 15) & ~15;
   const int64_t mt = (M + BM - 1) / BM;
-  const int cands[] = {256, 192, 128, 64};
+  const int cands[] = {64, 96, 128, 192, 256};
+  TileCfg best{n16 < 64 ? n16 : 64, 1};
+  double best_t = 1e30;
   for (int bn : cands) {
-    if (bn > N && bn != 64) continue;
-    if (N % bn != 0 && !(bn == 64)) continue;
+    if (forced >= 16 && forced <= 256 && forced % 16 == 0) bn = forced;
+    if (bn > n16) bn = n16;
+    if (N % bn != 0 && bn > 64 && bn != n16) continue;
     const int64_t tiles = mt * ((N + bn - 1) / bn);
-    if (tiles >= 2 * (int64_t)sms || bn == 64) return bn;
+    int resident = 512 / tmem_cols_for(bn);
+    if (resident > 3) resident = 3;
+    while (resident > 1 && smem_bytes(bn, 2) * resident > 220 * 1024) --resident;
+    const int64_t waves = (tiles + (int64_t)sms * resident - 1) / ((int64_t)sms * resident);
+    int64_t share = (tiles + sms - 1) / sms;                    // CTAs that will actually share an SM
+    if (share > resident) share = resident;
+    int st = 1;
+    while (st < kMaxStages && st < nkb && smem_bytes(bn, st + 1) * share <= 220 * 1024) ++st;
+    const double t_tile = 2.0 + nkb * (0.10 + 0.7 / st) + (bn / 64.0) * (act ? 3.5 : 1.6);
+    const double t = waves * t_tile;
+    if (t < best_t - 1e-9) { best_t = t; best = TileCfg{bn, st}; }
+    if (forced) break;
   }
-  return 64;
+  return best;
 }
 
 }  // namespace
@@ -201,11 +262,13 @@ int linear_fwd_tc(const cswin_linear_args_t* a, cudaStream_t stream, bool* handl
   P.sscale = a->sample_scale; P.rps = a->rows_per_sample > 0 ? a->rows_per_sample : 1;
   P.out = (__nv_bfloat16*)a->out; P.ldo = a->ldo;
   P.M = a->M; P.N = a->N; P.K1 = a->K1; P.K2 = a->K2; P.act = a->act;
-  P.BN = pick_bn(a->M, a->N, sm_count());
   P.nkb1 = (a->K1 + BK - 1) / BK;
   P.nkb = P.nkb1 + (a->K2 + BK - 1) / BK;
-  P.stages = P.nkb < kMaxStages ? P.nkb : (P.BN > 128 ? 3 : kMaxStages);
-  P.tmem_cols = P.BN <= 64 ? 64 : P.BN <= 128 ? 128 : 256;      // the epilogue reads whole 64-column groups
+  const TileCfg cfg = pick_tile(a->M, a->N, P.nkb, a->act, sm_count());
+  P.BN = cfg.bn;
+  P.stages = cfg.stages;
+  P.tmem_cols = tmem_cols_for(P.BN);
+  P.bias_vec = a->bias != nullptr && aligned16(a->bias);
   P.vec_ok = aligned16(a->out) && (a->ldo * 2) % 16 == 0 &&
              (a->residual == nullptr || (aligned16(a->residual) && (a->ldr * 2) % 16 == 0));
 
@@ -230,7 +293,7 @@ int linear_fwd_tc(const cswin_linear_args_t* a, cudaStream_t stream, bool* handl
     if (!tc::make_tensor_map_bf16(&P.map_w, a->w, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return CSWIN_ERR_CUDA;
   }
 
-  const size_t smem = 1024 + (size_t)P.stages * (BM * BK * 2 + (size_t)P.BN * BK * 2) + kStageEpiBytes + 128;
+  const size_t smem = smem_bytes(P.BN, P.stages);
   static std::atomic<size_t> configured{0};
   if (smem > configured.load(std::memory_order_relaxed)) {
     CSWIN_CUDA_OK(cudaFuncSetAttribute(linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

@@ -28,6 +28,20 @@ def flush_l2():
 def time_op(fn, iters=20, warm=3):
     for _ in range(warm):
         fn()
+    if os.environ.get("BENCH_NOFLUSH"):          # L2-warm, 50 back-to-back launches captured in a CUDA graph
+        g = torch.cuda.CUDAGraph()
+        s = torch.cuda.Stream(); s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            fn()
+        torch.cuda.current_stream().wait_stream(s)
+        with torch.cuda.graph(g):
+            for _ in range(50):
+                fn()
+        g.replay(); torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); g.replay(); b.record(); torch.cuda.synchronize()
+        t = a.elapsed_time(b) * 1e-3 / 50
+        return t, t
     ts = []
     for _ in range(iters):
         flush_l2()
