@@ -35,6 +35,7 @@ METRIC = "CSWin-UNet-tiny 224^2 slices/sec (bf16 fwd)"
 UNIT = "slices/s"
 BATCH = 24
 GFLOP_PER_SLICE_FWD = 10.028       # BASELINE.md section 2 (FlopCounterMode on the unmodified reference)
+ATTN_DRAM_TRAFFIC_PER_FORWARD = None   # bytes, from the ncu --set full capture in profiles/ (per forward at batch 24); None = not captured yet
 
 
 def peaks():
@@ -237,62 +238,91 @@ def run_native(args):
         ms = float(t.item())
     value = world * args.steps * B / (ms * 1e-3)
 
-    # ---- e2e: host buffers through the public module call ----
-    pinned = [host.clone().pin_memory() for _ in range(2)]
-    out_host = torch.empty((B, 224, 224), dtype=torch.uint8).pin_memory()
+    # ---- e2e: HOST buffers through the public API (SliceEngine): every step copies its batch host->device from pinned
+    #      memory, runs the forward, and reads the uint8 label map back; copies of adjacent steps overlap the forward ----
+    engine = cw.SliceEngine(model, batch=B, compute_dtype=torch.bfloat16)
+    pinned = [(host + 0.001 * i).pin_memory() for i in range(4)]
+    h2d_bytes, d2h_bytes = engine.bytes_per_batch()
 
-    def e2e_step(i):
-        x = pinned[i % 2].to(dev, non_blocking=True)
-        with torch.no_grad():
-            logits = model(x)
-        out_host.copy_(logits.argmax(1).to(torch.uint8), non_blocking=True)
+    def e2e_run(n):
+        done = 0
+        for lab in engine.predict_stream(pinned[i % 4] for i in range(n)):
+            done += lab.shape[0]
+        return done
 
-    for i in range(max(args.warmup, 3)):
-        e2e_step(i)
+    e2e_run(max(args.warmup, 3))
     barrier()
+    t0 = time.perf_counter()
     e0.record()
-    for i in range(args.steps):
-        e2e_step(i)
+    n_done = e2e_run(args.steps)
     e1.record()
     barrier()
-    ms_e2e = e0.elapsed_time(e1)
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    ms_e2e = max(e0.elapsed_time(e1), wall_ms)                    # results are consumed on the host: wall clock bounds it
+    assert n_done == args.steps * B
     if world > 1:
         t = torch.tensor([ms_e2e], device=dev)
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
         ms_e2e = float(t.item())
     e2e_value = world * args.steps * B / (ms_e2e * 1e-3)
 
-    # ---- roofline: per-kernel CUDA-event timing of the fused attention launches (eager pass, same workload) ----
+    # ---- roofline: the kernel family is re-launched from a CUDA graph that contains ONLY those launches (same
+    #      arguments and buffers as one real forward, L2-warm like in the step), timed with CUDA events ----
     pk = peaks()
-    att_ms = []
-    orig_att = ops.lepe_attention_fwd
 
-    def timed(fn, sink):
-        def wrapper(*a, **k):
-            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a0.record()
-            r = fn(*a, **k)
-            a1.record()
-            sink.append((a0, a1))
-            return r
-        return wrapper
+    def family_ms(fn_name, reps=20):
+        calls = []
+        orig = getattr(ops, fn_name)
 
-    reps = 5
-    try:
-        ops.lepe_attention_fwd = timed(orig_att, att_ms)
-        with torch.no_grad():
-            for i in range(reps):
-                model(pool[i % n_rot])
+        def rec(*a, **k):
+            calls.append((a, k))
+            return orig(*a, **k)
+        setattr(ops, fn_name, rec)
+        try:
+            with torch.no_grad():
+                model(pool[0])
+        finally:
+            setattr(ops, fn_name, orig)
         torch.cuda.synchronize()
-    finally:
-        ops.lepe_attention_fwd = orig_att
-    att_total_ms = sum(a.elapsed_time(b) for a, b in att_ms) / reps            # per forward: 26 launches
+        g = torch.cuda.CUDAGraph()
+        s2 = torch.cuda.Stream()
+        s2.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s2), torch.no_grad():
+            for a, k in calls:
+                orig(*a, **k)
+        torch.cuda.current_stream().wait_stream(s2)
+        with torch.no_grad(), torch.cuda.graph(g):
+            for a, k in calls:
+                orig(*a, **k)
+        g.replay()
+        torch.cuda.synchronize()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(reps):
+            g.replay()
+        a1.record()
+        torch.cuda.synchronize()
+        return a0.elapsed_time(a1) / reps, calls
+
+    att_total_ms, att_calls = family_ms("lepe_attention_fwd")
     att_bytes = attention_bytes_per_image() * B
     att_gbs = att_bytes / (att_total_ms * 1e-3) / 1e9
-    roofline = {"kernel": "lepe_attention_fwd (26 launches per forward, both branches per launch)", "bound": "hbm",
-                "achieved": att_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": att_gbs / pk["hbm_gbs"],
-                "traffic": None, "peak_source": pk["source"], "bytes_per_forward": att_bytes,
-                "ms_per_forward": att_total_ms, "launches_per_forward": len(att_ms) // reps}
+    roofline = {"kernel": "lepe_attn_fwd_tc_kernel (fused LePE stripe attention; 26 launches per forward, both branches per launch)",
+                "bound": "hbm", "achieved": att_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": att_gbs / pk["hbm_gbs"],
+                "traffic": ATTN_DRAM_TRAFFIC_PER_FORWARD, "peak_source": pk["source"], "bytes_per_forward": att_bytes,
+                "ms_per_forward": att_total_ms, "launches_per_forward": len(att_calls),
+                "how": "CUDA graph of the 26 attention launches of one forward (real buffers, L2-warm as in the step), "
+                       "CUDA events over 20 replays"}
+    lin_total_ms, lin_calls = family_ms("linear")
+    lin_flops = 0.0
+    for a, k in lin_calls:
+        kk = a[1].shape[1]
+        m = a[0].numel() // a[0].shape[-1]
+        lin_flops += 2.0 * m * kk * (k.get("n_out") or a[1].shape[0])
+    roofline_linear = {"kernel": "linear_tc_kernel (tcgen05 Linear + fused epilogue)", "bound": "tensor",
+                       "achieved": lin_flops / (lin_total_ms * 1e-3) / 1e12, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
+                       "frac": lin_flops / (lin_total_ms * 1e-3) / 1e12 / pk["bf16_tflops"], "launches_per_forward": len(lin_calls),
+                       "ms_per_forward": lin_total_ms, "flops_per_forward": lin_flops}
     model_tflops = value / world * GFLOP_PER_SLICE_FWD / 1e3
     roofline_model = {"bound": "tensor", "achieved": model_tflops, "peak": pk["bf16_tflops_sustained"] or pk["bf16_tflops"],
                       "unit": "TFLOP/s", "frac": model_tflops / (pk["bf16_tflops_sustained"] or pk["bf16_tflops"]),
@@ -307,10 +337,11 @@ def run_native(args):
                        "l2": f"inputs rotate over {n_rot} batches = {n_rot * host.numel() * 4 / 1e6:.0f} MB > 126 MB L2",
                        "launch": "CUDA graph replay of the native forward"},
             "clocks": clocks, "gpu_launches": int(launches_per_fwd * args.steps),
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(host.numel() * 4),
-                    "d2h_bytes_per_step": int(out_host.numel()), "ms_per_step": ms_e2e / args.steps,
-                    "path": "pinned host fp32 batch -> H2D -> CSWinTransformer.forward (eager launches) -> argmax -> D2H uint8 labels"},
-            "roofline": roofline, "roofline_model": roofline_model}
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes),
+                    "d2h_bytes_per_step": int(d2h_bytes), "ms_per_step": ms_e2e / args.steps,
+                    "path": "SliceEngine.predict_stream: pinned host fp32 batch -> H2D -> graph-replayed forward with in-kernel "
+                            "argmax -> D2H uint8 label map; 2 buffer slots, copies overlap the neighbouring steps' forward"},
+            "roofline": roofline, "roofline_linear": roofline_linear, "roofline_model": roofline_model}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, cores, n, dt = cpu_forward_rate(args.cpu_budget, BATCH)

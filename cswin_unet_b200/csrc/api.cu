@@ -124,4 +124,12 @@ int cswin_carafe_reassemble_fwd(const void* enc, int64_t ldenc, const void* z, i
   return carafe_reassemble_fwd(enc, ldenc, z, ldz, bias, y, ldy, nchw_out, y_is_f32, B, H, W, C, up, dtype, (cudaStream_t)stream);
 }
 
+int cswin_carafe_head_fwd(const void* enc, int64_t ldenc, const void* z, int64_t ldz, const void* bias, void* logits,
+                          int32_t logits_is_f32, uint8_t* labels, int32_t B, int32_t H, int32_t W, int32_t C, int32_t up,
+                          int32_t dtype, cswin_stream_t stream) {
+  CSWIN_REQUIRE(valid_dtype(dtype), CSWIN_ERR_INVALID, "carafe_head_fwd: bad dtype %d", dtype);
+  CSWIN_REQUIRE(B >= 0 && H > 0 && W > 0 && C > 0, CSWIN_ERR_INVALID, "carafe_head_fwd: bad shape");
+  return carafe_head_fwd(enc, ldenc, z, ldz, bias, logits, logits_is_f32, labels, B, H, W, C, up, dtype, (cudaStream_t)stream);
+}
+
 }  // extern "C"

@@ -84,4 +84,7 @@ int carafe_reassemble_fwd(const void* enc, int64_t ldenc, const void* z, int64_t
                           int64_t ldy, int nchw_out, int y_is_f32, int B, int H, int W, int C, int up, int dtype,
                           cudaStream_t s);
 
+int carafe_head_fwd(const void* enc, int64_t ldenc, const void* z, int64_t ldz, const void* bias, void* logits,
+                    int logits_is_f32, uint8_t* labels, int B, int H, int W, int C, int up, int dtype, cudaStream_t s);
+
 }  // namespace cswin

@@ -15,7 +15,7 @@ namespace {
 template <typename T>
 __global__ void __launch_bounds__(256) im2col_tokens_kernel(const T* __restrict__ x, int64_t x_bs, int64_t x_ts,
                                                              T* __restrict__ col, int64_t ldcol, int B, int H, int W,
-                                                             int C, int KH, int KW, int stride, int pad, int Ho, int Wo) {
+                                                             int C, int KH, int KW, int stride, int pad, int Ho, int Wo, int vec) {
   // one thread per (output pixel, tap, 8-channel chunk); C % 8 == 0 is guaranteed by the launcher
   const int cv = C >> 3;
   const int64_t total = (int64_t)B * Ho * Wo * KH * KW * cv;
@@ -31,36 +31,64 @@ __global__ void __launch_bounds__(256) im2col_tokens_kernel(const T* __restrict_
     T* dst = col + ((int64_t)(b * Ho + oy) * Wo + ox) * ldcol + (int64_t)tap * C + c8 * 8;
     if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
       const T* src = x + (int64_t)b * x_bs + ((int64_t)iy * W + ix) * x_ts + c8 * 8;
+      if (vec) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) dst[j] = src[j];
+        for (int j = 0; j < (int)(8 * sizeof(T) / 16); ++j) reinterpret_cast<uint4*>(dst)[j] = reinterpret_cast<const uint4*>(src)[j];
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dst[j] = src[j];
+      }
     } else {
+      if (vec) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) stf(dst + j, 0.f);
+        for (int j = 0; j < (int)(8 * sizeof(T) / 16); ++j) reinterpret_cast<uint4*>(dst)[j] = make_uint4(0, 0, 0, 0);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) stf(dst + j, 0.f);
+      }
     }
   }
 }
 
+// One CTA per (batch, output row, 32-pixel segment): the KH input rows needed by the segment are staged in shared
+// memory with coalesced loads (fp32 or bf16 image), then each of the 32 col rows (ldcol elements, zero padded) is
+// written contiguously.  Column order (c*KH + ky)*KW + kx == flattening of conv.weight (N, C, KH, KW).
+constexpr int kI2cSeg = 32;
 template <typename TI, typename T>
 __global__ void __launch_bounds__(256) im2col_nchw_kernel(const TI* __restrict__ x, T* __restrict__ col, int64_t ldcol,
                                                            int B, int C, int H, int W, int KH, int KW, int stride,
                                                            int pad, int Ho, int Wo) {
+  extern __shared__ float patch[];                     // [C][KH][span]
+  const int segs = (Wo + kI2cSeg - 1) / kI2cSeg;
+  const int seg = blockIdx.x % segs;
+  const int oy = (blockIdx.x / segs) % Ho;
+  const int b = blockIdx.x / (segs * Ho);
+  const int ox0 = seg * kI2cSeg;
+  const int span = (kI2cSeg - 1) * stride + KW;
+  const int ix0 = ox0 * stride - pad, iy0 = oy * stride - pad;
+  for (int i = threadIdx.x; i < C * KH * span; i += blockDim.x) {
+    const int dx = i % span;
+    const int ky = (i / span) % KH;
+    const int c = i / (span * KH);
+    const int iy = iy0 + ky, ix = ix0 + dx;
+    float v = 0.f;
+    if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = ldf(x + (((int64_t)b * C + c) * H + iy) * W + ix);
+    patch[i] = v;
+  }
+  __syncthreads();
   const int K = C * KH * KW;
-  const int64_t total = (int64_t)B * Ho * Wo * ldcol;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int k = (int)(i % ldcol);
-    int64_t r = i / ldcol;
-    const int ox = (int)(r % Wo); r /= Wo;
-    const int oy = (int)(r % Ho);
-    const int b = (int)(r / Ho);
+  const int npix = min(kI2cSeg, Wo - ox0);
+  for (int i = threadIdx.x; i < npix * (int)ldcol; i += blockDim.x) {
+    const int k = i % (int)ldcol;
+    const int p = i / (int)ldcol;
     float v = 0.f;
     if (k < K) {
-      const int c = k / (KH * KW);
-      const int t = k - c * KH * KW;
-      const int ky = t / KW, kx = t - ky * KW;
-      const int iy = oy * stride - pad + ky, ix = ox * stride - pad + kx;
-      if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = ldf(x + (((int64_t)b * C + c) * H + iy) * W + ix);
+      const int kx = k % KW;
+      const int ky = (k / KW) % KH;
+      const int c = k / (KW * KH);
+      v = patch[(c * KH + ky) * span + p * stride + kx];
     }
-    stf(col + i, v);
+    stf(col + ((int64_t)(b * Ho + oy) * Wo + ox0 + p) * ldcol + k, v);
   }
 }
 
@@ -117,7 +145,77 @@ __global__ void __launch_bounds__(128) carafe_reassemble_kernel(const T* __restr
   }
 }
 
+// Segmentation head: CARAFE4 re-assembly of the folded (out o output) 1x1 map, one thread per OUTPUT pixel computing all
+// C <= 16 classes: NCHW logits are written coalesced along x, and the arg-max label map (what test_single_volume keeps,
+// utils.py:73-75 — softmax is monotone so argmax(softmax(l)) == argmax(l)) can be emitted directly as uint8.
+template <typename T, typename TO>
+__global__ void __launch_bounds__(256) carafe_head_kernel(const T* __restrict__ enc, int64_t ldenc, const T* __restrict__ z,
+                                                           int64_t ldz, const T* __restrict__ bias, TO* __restrict__ logits,
+                                                           uint8_t* __restrict__ labels, int B, int H, int W, int C, int up) {
+  const int Ho = H * up, Wo = W * up, s2 = up * up;
+  const int64_t total = (int64_t)B * Ho * Wo;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int ox = (int)(i % Wo);
+    const int oy = (int)((i / Wo) % Ho);
+    const int b = (int)(i / ((int64_t)Wo * Ho));
+    const int x0 = ox / up, y0 = oy / up;
+    const int ae = (oy - y0 * up) * up + (ox - x0 * up);
+    const int64_t pix = ((int64_t)b * H + y0) * W + x0;
+    float k[9];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) { k[t] = ldf(enc + pix * ldenc + t * s2 + ae); mx = fmaxf(mx, k[t]); }
+    float sum = 0.f;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) { k[t] = expf(k[t] - mx); sum += k[t]; }
+    const float inv = 1.0f / sum;
+    float acc[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) acc[c] = (c < C) ? ldf(bias + c) : -INFINITY;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const int yy = y0 + t / 3 - 1, xx = x0 + t % 3 - 1;
+      if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+        const T* zr = z + (((int64_t)b * H + yy) * W + xx) * ldz;
+        const float kt = k[t] * inv;
+#pragma unroll
+        for (int c = 0; c < 16; ++c) if (c < C) acc[c] = fmaf(kt, ldf(zr + c), acc[c]);
+      }
+    }
+    if (logits != nullptr) {
+#pragma unroll
+      for (int c = 0; c < 16; ++c) if (c < C) stf(logits + (((int64_t)b * C + c) * Ho + oy) * Wo + ox, acc[c]);
+    }
+    if (labels != nullptr) {
+      int best = 0; float bv = acc[0];
+#pragma unroll
+      for (int c = 1; c < 16; ++c) if (c < C && acc[c] > bv) { bv = acc[c]; best = c; }     // first maximum, like torch.argmax
+      labels[i] = (uint8_t)best;
+    }
+  }
+}
+
 }  // namespace
+
+int carafe_head_fwd(const void* enc, int64_t ldenc, const void* z, int64_t ldz, const void* bias, void* logits,
+                    int logits_is_f32, uint8_t* labels, int B, int H, int W, int C, int up, int dtype, cudaStream_t s) {
+  CSWIN_REQUIRE(enc && z && bias && (logits || labels), CSWIN_ERR_INVALID, "carafe_head: null pointer");
+  CSWIN_REQUIRE(C >= 1 && C <= 16, CSWIN_ERR_UNSUPPORTED, "carafe_head: %d classes (supported: 1..16)", C);
+  CSWIN_REQUIRE(up >= 1 && ldenc >= 9 * up * up && ldz >= C, CSWIN_ERR_INVALID, "carafe_head: bad up / leading dimension");
+  const int64_t total = (int64_t)B * H * up * W * up;
+  if (total == 0) return CSWIN_OK;
+  const unsigned grid = (unsigned)std::min<int64_t>(ceil_div64(total, 256), (int64_t)sm_count() * 32);
+  if (dtype == CSWIN_F32) {
+    CSWIN_REQUIRE(!logits || logits_is_f32, CSWIN_ERR_INVALID, "carafe_head: fp32 path writes fp32 logits");
+    carafe_head_kernel<float, float><<<grid, 256, 0, s>>>((const float*)enc, ldenc, (const float*)z, ldz, (const float*)bias, (float*)logits, labels, B, H, W, C, up);
+  } else if (logits_is_f32) {
+    carafe_head_kernel<__nv_bfloat16, float><<<grid, 256, 0, s>>>((const __nv_bfloat16*)enc, ldenc, (const __nv_bfloat16*)z, ldz, (const __nv_bfloat16*)bias, (float*)logits, labels, B, H, W, C, up);
+  } else {
+    carafe_head_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)enc, ldenc, (const __nv_bfloat16*)z, ldz, (const __nv_bfloat16*)bias, (__nv_bfloat16*)logits, labels, B, H, W, C, up);
+  }
+  CSWIN_LAUNCH_CHECK();
+  return CSWIN_OK;
+}
 
 int im2col_tokens(const void* x, int64_t x_bs, int64_t x_ts, void* col, int64_t ldcol, int B, int H, int W, int C, int KH,
                   int KW, int stride, int pad, int dtype, cudaStream_t s) {
@@ -128,10 +226,13 @@ int im2col_tokens(const void* x, int64_t x_bs, int64_t x_ts, void* col, int64_t 
   const int64_t total = (int64_t)B * Ho * Wo * KH * KW * (C / 8);
   if (total == 0) return CSWIN_OK;
   const unsigned grid = (unsigned)std::min<int64_t>(ceil_div64(total, 256), (int64_t)sm_count() * 16);
+  const int es = dtype == CSWIN_F32 ? 4 : 2;
+  const int vec = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(col)) % 16 == 0) && (x_bs * es) % 16 == 0 &&
+                  (x_ts * es) % 16 == 0 && (ldcol * es) % 16 == 0;
   if (dtype == CSWIN_F32)
-    im2col_tokens_kernel<float><<<grid, 256, 0, s>>>((const float*)x, x_bs, x_ts, (float*)col, ldcol, B, H, W, C, KH, KW, stride, pad, Ho, Wo);
+    im2col_tokens_kernel<float><<<grid, 256, 0, s>>>((const float*)x, x_bs, x_ts, (float*)col, ldcol, B, H, W, C, KH, KW, stride, pad, Ho, Wo, vec);
   else
-    im2col_tokens_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)x, x_bs, x_ts, (__nv_bfloat16*)col, ldcol, B, H, W, C, KH, KW, stride, pad, Ho, Wo);
+    im2col_tokens_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)x, x_bs, x_ts, (__nv_bfloat16*)col, ldcol, B, H, W, C, KH, KW, stride, pad, Ho, Wo, vec);
   CSWIN_LAUNCH_CHECK();
   return CSWIN_OK;
 }
@@ -139,18 +240,22 @@ int im2col_tokens(const void* x, int64_t x_bs, int64_t x_ts, void* col, int64_t 
 int im2col_nchw(const void* x, int x_is_f32, void* col, int64_t ldcol, int B, int C, int H, int W, int KH, int KW,
                 int stride, int pad, int dtype, cudaStream_t s) {
   CSWIN_REQUIRE(x && col, CSWIN_ERR_INVALID, "im2col_nchw: null pointer");
-  CSWIN_REQUIRE(ldcol >= (int64_t)C * KH * KW, CSWIN_ERR_INVALID, "im2col_nchw: ldcol too small");
+  CSWIN_REQUIRE(ldcol >= (int64_t)C * KH * KW && ldcol < (1 << 20), CSWIN_ERR_INVALID, "im2col_nchw: bad ldcol");
   const int Ho = (H + 2 * pad - KH) / stride + 1, Wo = (W + 2 * pad - KW) / stride + 1;
-  const int64_t total = (int64_t)B * Ho * Wo * ldcol;
-  if (total == 0) return CSWIN_OK;
-  const unsigned grid = (unsigned)std::min<int64_t>(ceil_div64(total, 256), (int64_t)sm_count() * 16);
+  if ((int64_t)B * Ho * Wo == 0) return CSWIN_OK;
+  const int span = (kI2cSeg - 1) * stride + KW;
+  const size_t smem = sizeof(float) * (size_t)C * KH * span;
+  CSWIN_REQUIRE(smem <= 48 * 1024, CSWIN_ERR_UNSUPPORTED, "im2col_nchw: C*KH*span=%zu floats exceed 48 KB of shared memory", smem / 4);
+  const int64_t ctas = (int64_t)B * Ho * ((Wo + kI2cSeg - 1) / kI2cSeg);
+  CSWIN_REQUIRE(ctas < (1ll << 31), CSWIN_ERR_UNSUPPORTED, "im2col_nchw: grid too large");
+  const unsigned grid = (unsigned)ctas;
   if (dtype == CSWIN_F32) {
     CSWIN_REQUIRE(x_is_f32, CSWIN_ERR_INVALID, "im2col_nchw: fp32 path needs an fp32 image");
-    im2col_nchw_kernel<float, float><<<grid, 256, 0, s>>>((const float*)x, (float*)col, ldcol, B, C, H, W, KH, KW, stride, pad, Ho, Wo);
+    im2col_nchw_kernel<float, float><<<grid, 256, smem, s>>>((const float*)x, (float*)col, ldcol, B, C, H, W, KH, KW, stride, pad, Ho, Wo);
   } else if (x_is_f32) {
-    im2col_nchw_kernel<float, __nv_bfloat16><<<grid, 256, 0, s>>>((const float*)x, (__nv_bfloat16*)col, ldcol, B, C, H, W, KH, KW, stride, pad, Ho, Wo);
+    im2col_nchw_kernel<float, __nv_bfloat16><<<grid, 256, smem, s>>>((const float*)x, (__nv_bfloat16*)col, ldcol, B, C, H, W, KH, KW, stride, pad, Ho, Wo);
   } else {
-    im2col_nchw_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)col, ldcol, B, C, H, W, KH, KW, stride, pad, Ho, Wo);
+    im2col_nchw_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, smem, s>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)col, ldcol, B, C, H, W, KH, KW, stride, pad, Ho, Wo);
   }
   CSWIN_LAUNCH_CHECK();
   return CSWIN_OK;

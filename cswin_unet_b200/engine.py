@@ -1,0 +1,110 @@
+"""Slice-inference engine: the call a user of the reference's `test_single_volume` loop makes, B200-style.
+
+The reference evaluates one slice at a time (utils.py:61-90: host zoom -> `.cuda()` -> forward -> argmax -> `.cpu()`).
+Slices are independent, so the engine batches them, keeps the forward in a CUDA graph, and pipelines
+host->device copy / forward / device->host copy of consecutive batches on three streams with two buffer slots:
+
+    eng = SliceEngine(model, batch=24)                 # model: CSWinTransformer on a CUDA device
+    labels = eng.predict(host_batch)                   # (B,3|1,H,W) float32 CPU tensor -> (B,H,W) uint8 CPU tensor
+    for labels in eng.predict_stream(iter_of_batches): ...   # pipelined; results come back in order
+
+Only a uint8 label map leaves the GPU (the arg-max is taken inside the head kernel).  Multi-GPU: one engine per
+process / GPU over a shard of the slices (`shard_slices`); there is no collective on this path.
+"""
+from __future__ import annotations
+
+from typing import Iterable, Iterator, List, Optional, Sequence, Tuple
+
+import torch
+
+Tensor = torch.Tensor
+
+
+def shard_slices(n_slices: int, world: int, rank: int) -> range:
+    """Contiguous shard [lo, hi) of slice indices for `rank` of `world` (sizes differ by at most one)."""
+    base, rem = divmod(n_slices, world)
+    lo = rank * base + min(rank, rem)
+    return range(lo, lo + base + (1 if rank < rem else 0))
+
+
+class SliceEngine:
+    def __init__(self, model, batch: int, img_size: Optional[int] = None, in_chans: int = 3,
+                 compute_dtype: torch.dtype = torch.bfloat16, device: Optional[torch.device] = None):
+        self.model = model.eval()
+        self.batch = batch
+        self.size = img_size or model.img_size
+        self.in_chans = in_chans
+        self.device = device or next(model.parameters()).device
+        if self.device.type != "cuda":
+            raise RuntimeError("SliceEngine needs a CUDA device: cswin_unet_b200 has no CPU path")
+        model.compute_dtype = compute_dtype
+        self.streams = {k: torch.cuda.Stream(self.device) for k in ("h2d", "compute", "d2h")}
+        shape = (batch, in_chans, self.size, self.size)
+        self.slots = []
+        with torch.cuda.device(self.device), torch.no_grad():
+            for _ in range(2):
+                x = torch.zeros(shape, dtype=torch.float32, device=self.device)
+                slot = {"x": x, "host_out": torch.empty((batch, self.size, self.size), dtype=torch.uint8).pin_memory(),
+                        "ev_in": torch.cuda.Event(), "ev_done": torch.cuda.Event(), "ev_out": torch.cuda.Event(),
+                        "ev_free": torch.cuda.Event()}
+                self.slots.append(slot)
+            cs = self.streams["compute"]
+            cs.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(cs):
+                for _ in range(2):                               # warm-up: derive cached weights, load kernels
+                    self.model.predict_labels(self.slots[0]["x"])
+            cs.synchronize()
+            pool = None
+            for slot in self.slots:                              # one graph per slot (static input / output buffers)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, pool=pool, stream=cs):
+                    slot["y"] = self.model.predict_labels(slot["x"])
+                pool = g.pool()
+                slot["graph"] = g
+        self._n = 0
+
+    # ---- one batch ------------------------------------------------------------------------------------
+    def _submit(self, host_x: Tensor) -> dict:
+        slot = self.slots[self._n % 2]
+        self._n += 1
+        n = host_x.shape[0]
+        if n > self.batch or tuple(host_x.shape[2:]) != (self.size, self.size):
+            raise ValueError(f"expected at most {self.batch} slices of {self.size}x{self.size}, got {tuple(host_x.shape)}")
+        if host_x.shape[1] == 1 and self.in_chans == 3:
+            host_x = host_x.expand(-1, 3, -1, -1)                  # vision_transformer.py:40-41 (1 -> 3 channel repeat)
+        h2d, cs, d2h = self.streams["h2d"], self.streams["compute"], self.streams["d2h"]
+        with torch.cuda.stream(h2d):
+            h2d.wait_event(slot["ev_done"])                        # previous forward on this slot has consumed x
+            slot["x"][:n].copy_(host_x, non_blocking=True)
+            slot["ev_in"].record(h2d)
+        with torch.cuda.stream(cs):
+            cs.wait_event(slot["ev_in"])
+            cs.wait_event(slot["ev_out"])                          # previous D2H of this slot's y has finished
+            slot["graph"].replay()
+            slot["ev_done"].record(cs)
+        with torch.cuda.stream(d2h):
+            d2h.wait_event(slot["ev_done"])
+            slot["host_out"].copy_(slot["y"], non_blocking=True)
+            slot["ev_out"].record(d2h)
+        slot["n"] = n
+        return slot
+
+    def _collect(self, slot: dict) -> Tensor:
+        slot["ev_out"].synchronize()
+        return slot["host_out"][:slot["n"]].clone()
+
+    def predict(self, host_x: Tensor) -> Tensor:
+        return self._collect(self._submit(host_x))
+
+    def predict_stream(self, batches: Iterable[Tensor]) -> Iterator[Tensor]:
+        """Pipelined: batch i+1 is copied in while batch i runs and batch i-1 is copied out."""
+        pending: List[dict] = []
+        for hx in batches:
+            if len(pending) == 2:
+                yield self._collect(pending.pop(0))
+            pending.append(self._submit(hx))
+        while pending:
+            yield self._collect(pending.pop(0))
+
+    def bytes_per_batch(self) -> Tuple[int, int]:
+        return self.batch * self.in_chans * self.size * self.size * 4, self.batch * self.size * self.size

@@ -144,8 +144,10 @@ class CSWinTransformer(_Native):
             x = blk(x)
         return self._ln(self.norm_up, x, "norm_up")
 
-    def up_x4(self, x: Tensor, logits_dtype: Optional[torch.dtype] = None) -> Tensor:
-        """CARAFE4 + output conv with the two 1x1 maps folded; returns NCHW logits (B, classes, 4H, 4W)."""
+    def up_x4(self, x: Tensor, logits_dtype: Optional[torch.dtype] = None, want_logits: bool = True,
+              want_labels: bool = False):
+        """CARAFE4 + output conv with the two 1x1 maps folded (cswin_unet.py:536-544).  Returns NCHW logits
+        (B, classes, 4H, 4W); with want_labels also / only the uint8 arg-max label map (utils.py:73-75)."""
         B, L, Cn = x.shape
         H = W = int(round(L ** 0.5))
         up = self.upsample1
@@ -156,14 +158,29 @@ class CSWinTransformer(_Native):
                      lambda o, u: o.reshape(o.shape[0], -1).float() @ u.reshape(u.shape[0], -1).float())
         bf = self._w("head.b", (wo, up.out.bias), dt, lambda o, b: o.reshape(o.shape[0], -1).float() @ b.float())
         z = ops.linear(x, wf)                                                   # (B, L, classes)
-        return ops.carafe_reassemble(enc, z.view(B * L, -1), bf, B, H, W, up.up_factor, nchw_out=True,
-                                     out_dtype=logits_dtype or dt)
+        if self.num_classes <= 16:
+            logits, labels = ops.carafe_head(enc, z.view(B * L, -1), bf, B, H, W, up.up_factor, want_logits=want_logits,
+                                             want_labels=want_labels, logits_dtype=logits_dtype or dt)
+        else:                                                                   # generic re-assembly, labels via torch
+            logits = ops.carafe_reassemble(enc, z.view(B * L, -1), bf, B, H, W, up.up_factor, nchw_out=True,
+                                           out_dtype=logits_dtype or dt)
+            labels = logits.argmax(1).to(torch.uint8) if want_labels else None
+        if want_labels:
+            return (logits, labels) if want_logits else labels
+        return logits
 
     def forward(self, x: Tensor) -> Tensor:
         _no_autograd(x, self.output.weight)
         x = self.forward_features(x)
         x = self.forward_up_features(x)
         return self.up_x4(x)
+
+    @torch.no_grad()
+    def predict_labels(self, x: Tensor) -> Tensor:
+        """argmax(softmax(forward(x)), 1) as uint8 (B, H, W), computed inside the head kernel (no logits written)."""
+        x = self.forward_features(x)
+        x = self.forward_up_features(x)
+        return self.up_x4(x, want_logits=False, want_labels=True)
 
 
 class CSwinUnet(nn.Module):

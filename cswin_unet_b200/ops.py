@@ -218,3 +218,17 @@ def carafe_reassemble(enc: Tensor, z: Tensor, bias: Tensor, B: int, H: int, W: i
                                             y.data_ptr(), ldy, int(nchw_out), int(od == torch.float32), B, H, W, Cn, up,
                                             _dtype_code(z), _stream()), "cswin_carafe_reassemble_fwd")
     return y
+
+
+def carafe_head(enc: Tensor, z: Tensor, bias: Tensor, B: int, H: int, W: int, up: int, *, want_logits: bool = True,
+                want_labels: bool = False, logits_dtype: Optional[torch.dtype] = None):
+    """Folded segmentation head: returns (logits (B,C,up H,up W) or None, labels uint8 (B,up H,up W) or None)."""
+    _need_cuda(enc, z, bias)
+    Cn = z.shape[-1]
+    ld = logits_dtype or z.dtype
+    logits = torch.empty((B, Cn, H * up, W * up), dtype=ld, device=z.device) if want_logits else None
+    labels = torch.empty((B, H * up, W * up), dtype=torch.uint8, device=z.device) if want_labels else None
+    check(lib().cswin_carafe_head_fwd(enc.data_ptr(), enc.stride(0), z.data_ptr(), z.stride(0), bias.data_ptr(),
+                                      _ptr(logits), int(ld == torch.float32), _ptr(labels), B, H, W, Cn, up,
+                                      _dtype_code(z), _stream()), "cswin_carafe_head_fwd")
+    return logits, labels

@@ -154,6 +154,18 @@ int cswin_carafe_reassemble_fwd(const void* enc, int64_t ldenc, const void* z, i
                                 void* y, int64_t ldy, int32_t nchw_out, int32_t y_is_f32, int32_t B, int32_t H,
                                 int32_t W, int32_t C, int32_t up, int32_t dtype, cswin_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Segmentation head.  Replaces CSWinTransformer.up_x4 (cswin_unet.py:536-544: CARAFE4 re-assembly + `out` conv + view /
+ * permute + `output` conv, with the two 1x1 maps folded by the caller into z = x (W_output W_out)^T and
+ * bias = W_output b_out) and, when `labels` is given, the argmax(softmax(.)) of utils.py:73-75 so that only a uint8
+ * label map has to leave the GPU.
+ *   enc (B*H*W, 9 up^2), z (B*H*W, C), bias (C), C <= 16
+ *   logits: (B, C, up H, up W) NCHW, fp32 or the compute dtype, or NULL;  labels: (B, up H, up W) uint8, or NULL
+ * ------------------------------------------------------------------------------------------------ */
+int cswin_carafe_head_fwd(const void* enc, int64_t ldenc, const void* z, int64_t ldz, const void* bias, void* logits,
+                          int32_t logits_is_f32, uint8_t* labels, int32_t B, int32_t H, int32_t W, int32_t C, int32_t up,
+                          int32_t dtype, cswin_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
