@@ -54,10 +54,13 @@ __global__ void __launch_bounds__(256) im2col_tokens_kernel(const T* __restrict_
 // memory with coalesced loads (fp32 or bf16 image), then each of the 32 col rows (ldcol elements, zero padded) is
 // written contiguously.  Column order (c*KH + ky)*KW + kx == flattening of conv.weight (N, C, KH, KW).
 constexpr int kI2cSeg = 32;
-template <typename TI, typename T>
-__global__ void __launch_bounds__(256) im2col_nchw_kernel(const TI* __restrict__ x, T* __restrict__ col, int64_t ldcol,
-                                                           int B, int C, int H, int W, int KH, int KW, int stride,
+// CK/CS > 0: compile-time kernel size / stride (the stem is 7x7 stride 4), so the index divisions become mul-shifts.
+template <typename TI, typename T, int CK, int CS>
+__global__ void __launch_bounds__(256) im2col_nchw_kernel(const TI* __restrict__ x, T* __restrict__ col, int64_t ldcol_,
+                                                           int B, int C, int H, int W, int KH_, int KW_, int stride_,
                                                            int pad, int Ho, int Wo) {
+  const int KH = CK > 0 ? CK : KH_, KW = CK > 0 ? CK : KW_, stride = CS > 0 ? CS : stride_;
+  const int ldcol = (int)ldcol_;
   extern __shared__ float patch[];                     // [C][KH][span]
   const int segs = (Wo + kI2cSeg - 1) / kI2cSeg;
   const int seg = blockIdx.x % segs;
@@ -78,9 +81,9 @@ __global__ void __launch_bounds__(256) im2col_nchw_kernel(const TI* __restrict__
   __syncthreads();
   const int K = C * KH * KW;
   const int npix = min(kI2cSeg, Wo - ox0);
-  for (int i = threadIdx.x; i < npix * (int)ldcol; i += blockDim.x) {
-    const int k = i % (int)ldcol;
-    const int p = i / (int)ldcol;
+  for (int i = threadIdx.x; i < npix * ldcol; i += blockDim.x) {
+    const int p = i / ldcol;
+    const int k = i - p * ldcol;
     float v = 0.f;
     if (k < K) {
       const int kx = k % KW;
@@ -88,7 +91,7 @@ __global__ void __launch_bounds__(256) im2col_nchw_kernel(const TI* __restrict__
       const int c = k / (KW * KH);
       v = patch[(c * KH + ky) * span + p * stride + kx];
     }
-    stf(col + ((int64_t)(b * Ho + oy) * Wo + ox0 + p) * ldcol + k, v);
+    stf(col + ((int64_t)(b * Ho + oy) * Wo + ox0) * ldcol + i, v);
   }
 }
 
@@ -145,13 +148,81 @@ __global__ void __launch_bounds__(128) carafe_reassemble_kernel(const T* __restr
   }
 }
 
+// bf16, token-major output: one WARP per low-resolution pixel, lane owns V = C/32 consecutive channels (V in {2,4,8}):
+// the 9 neighbour rows of z are read once as 4..16-byte vectors into registers, the softmaxed taps of the s^2 sub-pixels
+// are computed by lanes < s^2 and broadcast with shuffles, and every output row (C channels) is one coalesced store.
+template <int V>
+__global__ void __launch_bounds__(256) carafe_reassemble_warp_kernel(const __nv_bfloat16* __restrict__ enc, int64_t ldenc,
+                                                                      const __nv_bfloat16* __restrict__ z, int64_t ldz,
+                                                                      const __nv_bfloat16* __restrict__ bias,
+                                                                      __nv_bfloat16* __restrict__ y, int64_t ldy, int64_t npix,
+                                                                      int H, int W, int up) {
+  const int lane = threadIdx.x & 31;
+  const int64_t pix = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (pix >= npix) return;
+  const int s2 = up * up;
+  const int x0 = (int)(pix % W);
+  const int y0 = (int)((pix / W) % H);
+  const int64_t b = pix / ((int64_t)W * H);
+  float zr[9][V];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const int yy = y0 + t / 3 - 1, xx = x0 + t % 3 - 1;
+    const bool in = yy >= 0 && yy < H && xx >= 0 && xx < W;
+    const __nv_bfloat16* src = z + ((b * H + yy) * W + xx) * ldz + lane * V;
+#pragma unroll
+    for (int e = 0; e < V; e += 2) {
+      uint32_t u = 0;
+      if (in) u = *reinterpret_cast<const uint32_t*>(src + e);
+      zr[t][e] = __uint_as_float(u << 16);
+      zr[t][e + 1] = __uint_as_float(u & 0xffff0000u);
+    }
+  }
+  float kt[9];
+  {
+    const int ae = lane < s2 ? lane : 0;
+    float mx = -INFINITY;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) { kt[t] = __bfloat162float(enc[pix * ldenc + t * s2 + ae]); mx = fmaxf(mx, kt[t]); }
+    float sum = 0.f;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) { kt[t] = expf(kt[t] - mx); sum += kt[t]; }
+    const float inv = 1.0f / sum;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) kt[t] *= inv;
+  }
+  float bv[V];
+#pragma unroll
+  for (int e = 0; e < V; ++e) bv[e] = __bfloat162float(bias[lane * V + e]);
+  const int Wo = W * up;
+  for (int ae = 0; ae < s2; ++ae) {
+    float acc[V];
+#pragma unroll
+    for (int e = 0; e < V; ++e) acc[e] = bv[e];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const float k = __shfl_sync(0xffffffffu, kt[t], ae);
+#pragma unroll
+      for (int e = 0; e < V; ++e) acc[e] = fmaf(k, zr[t][e], acc[e]);
+    }
+    const int oy = y0 * up + ae / up, ox = x0 * up + ae % up;
+    __nv_bfloat16* dst = y + ((b * H * up + oy) * Wo + ox) * ldy + lane * V;
+#pragma unroll
+    for (int e = 0; e < V; e += 2) {
+      const __nv_bfloat162 pk = __floats2bfloat162_rn(acc[e], acc[e + 1]);
+      *reinterpret_cast<__nv_bfloat162*>(dst + e) = pk;
+    }
+  }
+}
+
 // Segmentation head: CARAFE4 re-assembly of the folded (out o output) 1x1 map, one thread per OUTPUT pixel computing all
 // C <= 16 classes: NCHW logits are written coalesced along x, and the arg-max label map (what test_single_volume keeps,
 // utils.py:73-75 — softmax is monotone so argmax(softmax(l)) == argmax(l)) can be emitted directly as uint8.
 template <typename T, typename TO>
 __global__ void __launch_bounds__(256) carafe_head_kernel(const T* __restrict__ enc, int64_t ldenc, const T* __restrict__ z,
                                                            int64_t ldz, const T* __restrict__ bias, TO* __restrict__ logits,
-                                                           uint8_t* __restrict__ labels, int B, int H, int W, int C, int up) {
+                                                           uint8_t* __restrict__ labels, int B, int H, int W, int C, int up,
+                                                           int zvec) {
   const int Ho = H * up, Wo = W * up, s2 = up * up;
   const int64_t total = (int64_t)B * Ho * Wo;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -178,8 +249,16 @@ __global__ void __launch_bounds__(256) carafe_head_kernel(const T* __restrict__ 
       if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
         const T* zr = z + (((int64_t)b * H + yy) * W + xx) * ldz;
         const float kt = k[t] * inv;
+        if (sizeof(T) == 2 && zvec) {                       // rows padded to 16 bf16 (32 B): two 16-byte loads
+          const uint4 u0 = reinterpret_cast<const uint4*>(zr)[0], u1 = reinterpret_cast<const uint4*>(zr)[1];
+          const uint32_t w[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
 #pragma unroll
-        for (int c = 0; c < 16; ++c) if (c < C) acc[c] = fmaf(kt, ldf(zr + c), acc[c]);
+          for (int c = 0; c < 16; ++c)
+            if (c < C) acc[c] = fmaf(kt, __uint_as_float((c & 1) ? (w[c >> 1] & 0xffff0000u) : (w[c >> 1] << 16)), acc[c]);
+        } else {
+#pragma unroll
+          for (int c = 0; c < 16; ++c) if (c < C) acc[c] = fmaf(kt, ldf(zr + c), acc[c]);
+        }
       }
     }
     if (logits != nullptr) {
@@ -205,13 +284,14 @@ int carafe_head_fwd(const void* enc, int64_t ldenc, const void* z, int64_t ldz, 
   const int64_t total = (int64_t)B * H * up * W * up;
   if (total == 0) return CSWIN_OK;
   const unsigned grid = (unsigned)std::min<int64_t>(ceil_div64(total, 256), (int64_t)sm_count() * 32);
+  const int zvec = dtype == CSWIN_BF16 && ldz >= 16 && (ldz * 2) % 16 == 0 && reinterpret_cast<uintptr_t>(z) % 16 == 0;
   if (dtype == CSWIN_F32) {
     CSWIN_REQUIRE(!logits || logits_is_f32, CSWIN_ERR_INVALID, "carafe_head: fp32 path writes fp32 logits");
-    carafe_head_kernel<float, float><<<grid, 256, 0, s>>>((const float*)enc, ldenc, (const float*)z, ldz, (const float*)bias, (float*)logits, labels, B, H, W, C, up);
+    carafe_head_kernel<float, float><<<grid, 256, 0, s>>>((const float*)enc, ldenc, (const float*)z, ldz, (const float*)bias, (float*)logits, labels, B, H, W, C, up, zvec);
   } else if (logits_is_f32) {
-    carafe_head_kernel<__nv_bfloat16, float><<<grid, 256, 0, s>>>((const __nv_bfloat16*)enc, ldenc, (const __nv_bfloat16*)z, ldz, (const __nv_bfloat16*)bias, (float*)logits, labels, B, H, W, C, up);
+    carafe_head_kernel<__nv_bfloat16, float><<<grid, 256, 0, s>>>((const __nv_bfloat16*)enc, ldenc, (const __nv_bfloat16*)z, ldz, (const __nv_bfloat16*)bias, (float*)logits, labels, B, H, W, C, up, zvec);
   } else {
-    carafe_head_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)enc, ldenc, (const __nv_bfloat16*)z, ldz, (const __nv_bfloat16*)bias, (__nv_bfloat16*)logits, labels, B, H, W, C, up);
+    carafe_head_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)enc, ldenc, (const __nv_bfloat16*)z, ldz, (const __nv_bfloat16*)bias, (__nv_bfloat16*)logits, labels, B, H, W, C, up, zvec);
   }
   CSWIN_LAUNCH_CHECK();
   return CSWIN_OK;
@@ -251,11 +331,14 @@ int im2col_nchw(const void* x, int x_is_f32, void* col, int64_t ldcol, int B, in
   const unsigned grid = (unsigned)ctas;
   if (dtype == CSWIN_F32) {
     CSWIN_REQUIRE(x_is_f32, CSWIN_ERR_INVALID, "im2col_nchw: fp32 path needs an fp32 image");
-    im2col_nchw_kernel<float, float><<<grid, 256, smem, s>>>((const float*)x, (float*)col, ldcol, B, C, H, W, KH, KW, stride, pad, Ho, Wo);
+    if (KH == 7 && KW == 7 && stride == 4) im2col_nchw_kernel<float, float, 7, 4><<<grid, 256, smem, s>>>((const float*)x, (float*)col, ldcol, B, C, H, W, KH, KW, stride, pad, Ho, Wo);
+    else im2col_nchw_kernel<float, float, 0, 0><<<grid, 256, smem, s>>>((const float*)x, (float*)col, ldcol, B, C, H, W, KH, KW, stride, pad, Ho, Wo);
   } else if (x_is_f32) {
-    im2col_nchw_kernel<float, __nv_bfloat16><<<grid, 256, smem, s>>>((const float*)x, (__nv_bfloat16*)col, ldcol, B, C, H, W, KH, KW, stride, pad, Ho, Wo);
+    if (KH == 7 && KW == 7 && stride == 4) im2col_nchw_kernel<float, __nv_bfloat16, 7, 4><<<grid, 256, smem, s>>>((const float*)x, (__nv_bfloat16*)col, ldcol, B, C, H, W, KH, KW, stride, pad, Ho, Wo);
+    else im2col_nchw_kernel<float, __nv_bfloat16, 0, 0><<<grid, 256, smem, s>>>((const float*)x, (__nv_bfloat16*)col, ldcol, B, C, H, W, KH, KW, stride, pad, Ho, Wo);
   } else {
-    im2col_nchw_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, smem, s>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)col, ldcol, B, C, H, W, KH, KW, stride, pad, Ho, Wo);
+    if (KH == 7 && KW == 7 && stride == 4) im2col_nchw_kernel<__nv_bfloat16, __nv_bfloat16, 7, 4><<<grid, 256, smem, s>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)col, ldcol, B, C, H, W, KH, KW, stride, pad, Ho, Wo);
+    else im2col_nchw_kernel<__nv_bfloat16, __nv_bfloat16, 0, 0><<<grid, 256, smem, s>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)col, ldcol, B, C, H, W, KH, KW, stride, pad, Ho, Wo);
   }
   CSWIN_LAUNCH_CHECK();
   return CSWIN_OK;
@@ -271,6 +354,16 @@ int carafe_reassemble_fwd(const void* enc, int64_t ldenc, const void* z, int64_t
   if (pixels == 0) return CSWIN_OK;
   const size_t smem = sizeof(float) * ((size_t)9 * C + (size_t)up * up * 9);
   CSWIN_REQUIRE(smem <= 48 * 1024, CSWIN_ERR_UNSUPPORTED, "carafe_reassemble: C=%d too large", C);
+  if (dtype == CSWIN_BF16 && !nchw_out && !y_is_f32 && up * up <= 32 && (C == 64 || C == 128 || C == 256) &&
+      ldz % 2 == 0 && ldy % 2 == 0 && reinterpret_cast<uintptr_t>(z) % 4 == 0 && reinterpret_cast<uintptr_t>(y) % 4 == 0) {
+    const unsigned g2 = (unsigned)ceil_div64(pixels, 8);
+    const __nv_bfloat16 *e_ = (const __nv_bfloat16*)enc, *z_ = (const __nv_bfloat16*)z, *b_ = (const __nv_bfloat16*)bias;
+    if (C == 64) carafe_reassemble_warp_kernel<2><<<g2, 256, 0, s>>>(e_, ldenc, z_, ldz, b_, (__nv_bfloat16*)y, ldy, pixels, H, W, up);
+    else if (C == 128) carafe_reassemble_warp_kernel<4><<<g2, 256, 0, s>>>(e_, ldenc, z_, ldz, b_, (__nv_bfloat16*)y, ldy, pixels, H, W, up);
+    else carafe_reassemble_warp_kernel<8><<<g2, 256, 0, s>>>(e_, ldenc, z_, ldz, b_, (__nv_bfloat16*)y, ldy, pixels, H, W, up);
+    CSWIN_LAUNCH_CHECK();
+    return CSWIN_OK;
+  }
   const unsigned grid = (unsigned)pixels;
   if (dtype == CSWIN_F32) {
     CSWIN_REQUIRE(y_is_f32, CSWIN_ERR_INVALID, "carafe_reassemble: fp32 path writes fp32");

@@ -48,6 +48,79 @@ __global__ void __launch_bounds__(kRowsPerCta * 32) layernorm_kernel(const T* __
   }
 }
 
+// bf16 fast path: LPR lanes per row, each lane owns NV 16-byte vectors (8 bf16) -> C = LPR * NV * 8; 32/LPR rows per warp.
+// Two-pass fp32 statistics in registers, shuffle reductions inside the LPR-lane group.
+template <int LPR, int NV>
+__global__ void __launch_bounds__(256) layernorm_bf16_vec_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx,
+                                                                  const __nv_bfloat16* __restrict__ g,
+                                                                  const __nv_bfloat16* __restrict__ b,
+                                                                  __nv_bfloat16* __restrict__ y, int64_t ldy, int64_t M,
+                                                                  float eps, float* __restrict__ mean_out,
+                                                                  float* __restrict__ rstd_out) {
+  constexpr int C = LPR * NV * 8;
+  constexpr int RPW = 32 / LPR;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane % LPR;
+  const int64_t row = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW + lane / LPR;
+  const bool ok = row < M;
+  float v[NV * 8];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    uint4 u = make_uint4(0, 0, 0, 0);
+    if (ok) u = *reinterpret_cast<const uint4*>(x + row * ldx + (i * LPR + sub) * 8);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      v[i * 8 + 2 * e] = __uint_as_float(w[e] << 16);
+      v[i * 8 + 2 * e + 1] = __uint_as_float(w[e] & 0xffff0000u);
+      s += v[i * 8 + 2 * e] + v[i * 8 + 2 * e + 1];
+    }
+  }
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s * (1.0f / C);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV * 8; ++i) { const float d = v[i] - mean; q = fmaf(d, d, q); }
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q * (1.0f / C) + eps);
+  if (ok) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c0 = (i * LPR + sub) * 8;
+      const uint4 gu = *reinterpret_cast<const uint4*>(g + c0);
+      const uint4 bu = *reinterpret_cast<const uint4*>(b + c0);
+      const uint32_t gw[4] = {gu.x, gu.y, gu.z, gu.w}, bw[4] = {bu.x, bu.y, bu.z, bu.w};
+      uint32_t o[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float lo = (v[i * 8 + 2 * e] - mean) * rstd * __uint_as_float(gw[e] << 16) + __uint_as_float(bw[e] << 16);
+        const float hi = (v[i * 8 + 2 * e + 1] - mean) * rstd * __uint_as_float(gw[e] & 0xffff0000u) + __uint_as_float(bw[e] & 0xffff0000u);
+        const __nv_bfloat162 pk = __floats2bfloat162_rn(lo, hi);
+        o[e] = *reinterpret_cast<const uint32_t*>(&pk);
+      }
+      *reinterpret_cast<uint4*>(y + row * ldy + c0) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+    if (sub == 0) {
+      if (mean_out) mean_out[row] = mean;
+      if (rstd_out) rstd_out[row] = rstd;
+    }
+  }
+}
+
+template <int LPR, int NV>
+int launch_vec(const void* x, int64_t ldx, const void* g, const void* b, void* y, int64_t ldy, int64_t M, float eps,
+               float* mean, float* rstd, cudaStream_t s) {
+  constexpr int RPW = 32 / LPR;
+  const int64_t rows_per_cta = 8 * RPW;
+  layernorm_bf16_vec_kernel<LPR, NV><<<(unsigned)ceil_div64(M, rows_per_cta), 256, 0, s>>>(
+      (const __nv_bfloat16*)x, ldx, (const __nv_bfloat16*)g, (const __nv_bfloat16*)b, (__nv_bfloat16*)y, ldy, M, eps, mean, rstd);
+  CSWIN_LAUNCH_CHECK();
+  return CSWIN_OK;
+}
+
 template <typename T>
 int launch(const void* x, int64_t ldx, const void* g, const void* b, void* y, int64_t ldy, int64_t M, int C, float eps,
            float* mean, float* rstd, cudaStream_t s) {
@@ -74,6 +147,12 @@ int layernorm_fwd(const void* x, int64_t ldx, const void* g, const void* b, void
   CSWIN_REQUIRE(ldx >= C && ldy >= C, CSWIN_ERR_INVALID, "layernorm: leading dimension smaller than C");
   if (M == 0) return CSWIN_OK;
   if (dtype == CSWIN_F32) return launch<float>(x, ldx, g, b, y, ldy, M, C, eps, mean, rstd, s);
+  const bool vec = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(g) |
+                     reinterpret_cast<uintptr_t>(b)) % 16 == 0) && (ldx * 2) % 16 == 0 && (ldy * 2) % 16 == 0;
+  if (vec && C == 64) return launch_vec<8, 1>(x, ldx, g, b, y, ldy, M, eps, mean, rstd, s);
+  if (vec && C == 128) return launch_vec<16, 1>(x, ldx, g, b, y, ldy, M, eps, mean, rstd, s);
+  if (vec && C == 256) return launch_vec<32, 1>(x, ldx, g, b, y, ldy, M, eps, mean, rstd, s);
+  if (vec && C == 512) return launch_vec<32, 2>(x, ldx, g, b, y, ldy, M, eps, mean, rstd, s);
   return launch<__nv_bfloat16>(x, ldx, g, b, y, ldy, M, C, eps, mean, rstd, s);
 }
 

@@ -154,13 +154,18 @@ class CSWinTransformer(_Native):
         dt = x.dtype
         enc = up._kernel_logits(x, H, W)
         wo = self.output.weight
-        wf = self._w("head.w", (wo, up.out.weight), dt,
-                     lambda o, u: o.reshape(o.shape[0], -1).float() @ u.reshape(u.shape[0], -1).float())
+        npad = 16 if self.num_classes <= 16 else self.num_classes             # 16-column rows: vector loads in the head kernel
+
+        def fold_w(o, u):
+            w = o.reshape(o.shape[0], -1).float() @ u.reshape(u.shape[0], -1).float()
+            return torch.nn.functional.pad(w, (0, 0, 0, npad - w.shape[0]))
+        wf = self._w("head.w", (wo, up.out.weight), dt, fold_w)
         bf = self._w("head.b", (wo, up.out.bias), dt, lambda o, b: o.reshape(o.shape[0], -1).float() @ b.float())
-        z = ops.linear(x, wf)                                                   # (B, L, classes)
+        z = ops.linear(x, wf)                                                   # (B, L, npad); columns >= classes are 0
         if self.num_classes <= 16:
             logits, labels = ops.carafe_head(enc, z.view(B * L, -1), bf, B, H, W, up.up_factor, want_logits=want_logits,
-                                             want_labels=want_labels, logits_dtype=logits_dtype or dt)
+                                             want_labels=want_labels, logits_dtype=logits_dtype or dt,
+                                             n_classes=self.num_classes)
         else:                                                                   # generic re-assembly, labels via torch
             logits = ops.carafe_reassemble(enc, z.view(B * L, -1), bf, B, H, W, up.up_factor, nchw_out=True,
                                            out_dtype=logits_dtype or dt)

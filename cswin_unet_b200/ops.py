@@ -221,10 +221,11 @@ def carafe_reassemble(enc: Tensor, z: Tensor, bias: Tensor, B: int, H: int, W: i
 
 
 def carafe_head(enc: Tensor, z: Tensor, bias: Tensor, B: int, H: int, W: int, up: int, *, want_logits: bool = True,
-                want_labels: bool = False, logits_dtype: Optional[torch.dtype] = None):
-    """Folded segmentation head: returns (logits (B,C,up H,up W) or None, labels uint8 (B,up H,up W) or None)."""
+                want_labels: bool = False, logits_dtype: Optional[torch.dtype] = None, n_classes: Optional[int] = None):
+    """Folded segmentation head: returns (logits (B,C,up H,up W) or None, labels uint8 (B,up H,up W) or None).
+    z may be padded beyond n_classes columns (rows of 16 bf16 let the kernel use 16-byte loads)."""
     _need_cuda(enc, z, bias)
-    Cn = z.shape[-1]
+    Cn = n_classes or z.shape[-1]
     ld = logits_dtype or z.dtype
     logits = torch.empty((B, Cn, H * up, W * up), dtype=ld, device=z.device) if want_logits else None
     labels = torch.empty((B, H * up, W * up), dtype=torch.uint8, device=z.device) if want_labels else None
