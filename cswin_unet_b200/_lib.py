@@ -65,6 +65,7 @@ SIGNATURES = {
     "cswin_last_error": (C.c_char_p, []),
     "cswin_launch_count": (C.c_uint64, []),
     "cswin_tc_launch_count": (C.c_uint64, []),
+    "cswin_debug_set_trace": (None, [c_void_p]),
     "cswin_lepe_attention_fwd": (c_int32, [C.POINTER(LepeBranch), c_int32, c_int32, c_int32, c_float, c_int32, c_void_p]),
     "cswin_lepe_attention_bwd": (c_int32, [C.POINTER(LepeBranchGrad), c_int32, c_int32, c_int32, c_float, c_int32, c_void_p]),
     "cswin_layernorm_fwd": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int32,

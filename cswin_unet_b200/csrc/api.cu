@@ -9,6 +9,7 @@ namespace cswin {
 
 std::atomic<uint64_t> g_launches{0};
 std::atomic<uint64_t> g_tc_launches{0};
+std::atomic<unsigned long long*> g_trace{nullptr};
 
 namespace {
 thread_local char t_err[512] = "";
@@ -46,6 +47,7 @@ extern "C" {
 int cswin_abi_version(void) { return CSWIN_ABI_VERSION; }
 const char* cswin_last_error(void) { return t_err; }
 uint64_t cswin_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+void cswin_debug_set_trace(void* device_buffer) { g_trace.store((unsigned long long*)device_buffer); }
 uint64_t cswin_tc_launch_count(void) { return g_tc_launches.load(std::memory_order_relaxed); }
 
 int cswin_lepe_attention_fwd(const cswin_lepe_branch_t* branches, int32_t n_branches, int32_t B, int32_t reso,

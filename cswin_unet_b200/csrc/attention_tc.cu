@@ -41,6 +41,7 @@ struct alignas(64) TcParams {
   TcBranch br[2];
   int nb, reso;
   float scale, scale_log2e;
+  unsigned long long* trace;
 };
 
 constexpr int kTileRows = 128;
@@ -74,6 +75,7 @@ __global__ void __launch_bounds__(kThreads, 3) lepe_attn_fwd_tc_kernel(const __g
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
 
   const int tid = threadIdx.x, warp = tid >> 5;
+  if (tid == 0) trace_stamp(P.trace, 0);
   const int row = tid & 127;                   // tile row == TMEM lane
   const int half = tid >> 7;                   // which half of the row's columns / channels this thread owns
   const int bi = (P.nb > 1 && (int)blockIdx.x >= P.br[1].tile_begin) ? 1 : 0;
@@ -132,6 +134,7 @@ __global__ void __launch_bounds__(kThreads, 3) lepe_attn_fwd_tc_kernel(const __g
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (tid == 0) trace_stamp(P.trace, 1);                     // prologue done
 
   if (tid == 0) {
     mbar_expect_tx(bar_tma, (uint32_t)(np * 3 * N * kRowBytes));
@@ -148,6 +151,7 @@ __global__ void __launch_bounds__(kThreads, 3) lepe_attn_fwd_tc_kernel(const __g
       tma_load_4d(smem_u32(Vs) + off, &P.map[bi][2], bar_tma, c0, c1, c2, c3);
     }
     mbar_wait(bar_tma, 0);
+    trace_stamp(P.trace, 2);                                 // q,k,v landed
     tc_fence_after();
     const uint64_t qd = make_smem_desc(smem_u32(Qs), 16, 8 * kRowBytes, kLayoutSw64);
     const uint64_t kd = make_smem_desc(smem_u32(Ks), 16, 8 * kRowBytes, kLayoutSw64);
@@ -157,6 +161,7 @@ __global__ void __launch_bounds__(kThreads, 3) lepe_attn_fwd_tc_kernel(const __g
     tc_commit(bar_s);
   }
   mbar_wait(bar_s, 0);
+  if (tid == 0) trace_stamp(P.trace, 3);                     // S ready
   tc_fence_after();
 
   // ---- softmax: this thread owns columns [cbeg, cbeg + hcols) of S row `row` (slot-local key index kbeg..) ----
@@ -232,6 +237,7 @@ __global__ void __launch_bounds__(kThreads, 3) lepe_attn_fwd_tc_kernel(const __g
   __syncthreads();
 
   if (tid == 0) {
+    trace_stamp(P.trace, 4);                                 // P published
     tc_fence_after();
     const uint64_t vd = make_smem_desc(smem_u32(Vs), 8 * kRowBytes, 8 * kRowBytes, kLayoutSw64);
     const uint32_t idesc = make_idesc_bf16(128, 32, 0, 1);   // B = V is MN-major
@@ -279,7 +285,9 @@ __global__ void __launch_bounds__(kThreads, 3) lepe_attn_fwd_tc_kernel(const __g
     }
   }
 
+  if (tid == 0) trace_stamp(P.trace, 5);                     // LePE done
   mbar_wait(bar_o, 0);
+  if (tid == 0) trace_stamp(P.trace, 6);                     // O ready
   tc_fence_after();
   {
     uint32_t o[16];
@@ -305,6 +313,7 @@ __global__ void __launch_bounds__(kThreads, 3) lepe_attn_fwd_tc_kernel(const __g
   }
   tc_fence_before();
   __syncthreads();
+  if (tid == 0) trace_stamp(P.trace, 7);                     // exit
   if (warp == 0) tmem_dealloc(tmem_base, kTmemCols);
 }
 
@@ -330,6 +339,7 @@ int lepe_attention_fwd_tc(const cswin_lepe_branch_t* brs, int nb, int B, int res
 
   TcParams P;
   P.nb = nb; P.reso = reso; P.scale = scale; P.scale_log2e = scale * 1.4426950408889634f;
+  P.trace = g_trace.load(std::memory_order_relaxed);
   int tiles = 0;
   for (int i = 0; i < nb; ++i) {
     const cswin_lepe_branch_t& s = brs[i];

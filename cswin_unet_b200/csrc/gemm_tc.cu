@@ -39,6 +39,7 @@ struct alignas(64) GemmTcParams {
   __nv_bfloat16* out; int64_t ldo;
   int64_t M; int N; int K1; int K2;
   int BN, stages, nkb, nkb1, act, tmem_cols, vec_ok, bias_vec;
+  unsigned long long* trace;
 };
 
 // GELU(erf) with erf from Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, far below bf16 resolution): one ex2 + one rcp
@@ -73,6 +74,7 @@ __global__ void __launch_bounds__(kThreads, 3) linear_tc_kernel(const __grid_con
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) trace_stamp(P.trace, 0);                                   // kernel entry
   const int64_t m0 = (int64_t)blockIdx.x * BM;
   const int n0 = blockIdx.y * BN;
 
@@ -92,6 +94,7 @@ __global__ void __launch_bounds__(kThreads, 3) linear_tc_kernel(const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (tid == 0) trace_stamp(P.trace, 1);                                   // prologue done
 
   if (warp == 0) {
     if (lane == 0) {                                    // ---- TMA producer ----
@@ -103,6 +106,7 @@ __global__ void __launch_bounds__(kThreads, 3) linear_tc_kernel(const __grid_con
         else             tma_load_2d(smem_u32(As + (size_t)s * a_bytes), &P.map_a2, full(s), (kb - P.nkb1) * BK, (int)m0);
         tma_load_2d(smem_u32(Ws + (size_t)s * w_bytes), &P.map_w, full(s), kb * BK, n0);
       }
+      trace_stamp(P.trace, 2);                          // all TMA issued
     }
   } else if (warp == 1) {
     if (lane == 0) {                                    // ---- MMA issuer ----
@@ -110,6 +114,7 @@ __global__ void __launch_bounds__(kThreads, 3) linear_tc_kernel(const __grid_con
       for (int kb = 0; kb < P.nkb; ++kb) {
         const int s = kb % S;
         mbar_wait(full(s), (kb / S) & 1);
+        if (kb == 0) trace_stamp(P.trace, 3);           // first operands landed
         tc_fence_after();
         const uint64_t ad = make_smem_desc(smem_u32(As + (size_t)s * a_bytes), 16, 1024, kLayoutSw128);
         const uint64_t wd = make_smem_desc(smem_u32(Ws + (size_t)s * w_bytes), 16, 1024, kLayoutSw128);
@@ -118,11 +123,13 @@ __global__ void __launch_bounds__(kThreads, 3) linear_tc_kernel(const __grid_con
         tc_commit(empty(s));                            // smem slot reusable once these MMAs have read it
       }
       tc_commit(bar_acc);                               // accumulator complete
+      trace_stamp(P.trace, 4);                          // all MMAs issued
     }
   } else {                                              // ---- epilogue warps 2..5 ----
     const int q = warp & 3;                             // TMEM lane quadrant this warp may touch
     float* stg = Epi + (warp - 2) * (32 * 64);
     mbar_wait(bar_acc, 0);
+    if (warp == 2 && lane == 0) trace_stamp(P.trace, 5);  // accumulator ready
     tc_fence_after();
     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
     const int c8 = lane & 7;                              // this lane's 8 columns inside every 64-column group
@@ -195,9 +202,11 @@ __global__ void __launch_bounds__(kThreads, 3) linear_tc_kernel(const __grid_con
       }
       __syncwarp();
     }
+    if (warp == 2 && lane == 0) trace_stamp(P.trace, 6);  // epilogue done
   }
   tc_fence_before();
   __syncthreads();
+  if (tid == 0) trace_stamp(P.trace, 7);                                   // exit
   if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)P.tmem_cols);
 }
 
@@ -269,6 +278,7 @@ int linear_fwd_tc(const cswin_linear_args_t* a, cudaStream_t stream, bool* handl
   P.stages = cfg.stages;
   P.tmem_cols = tmem_cols_for(P.BN);
   P.bias_vec = a->bias != nullptr && aligned16(a->bias);
+  P.trace = g_trace.load(std::memory_order_relaxed);
   P.vec_ok = aligned16(a->out) && (a->ldo * 2) % 16 == 0 &&
              (a->residual == nullptr || (aligned16(a->residual) && (a->ldr * 2) % 16 == 0));
 

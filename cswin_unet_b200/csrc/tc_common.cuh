@@ -170,6 +170,15 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
       : "memory");
 }
 
+// debug stamps: slot = role/phase index 0..15 of this CTA
+__device__ __forceinline__ void trace_stamp(unsigned long long* trace, int slot) {
+  if (trace != nullptr && blockIdx.x + blockIdx.y * gridDim.x < 1024) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    trace[(size_t)(blockIdx.x + blockIdx.y * gridDim.x) * 16 + slot] = t;
+  }
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   uint32_t d;
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));     // d = {hi: upper 16, lo: lower 16}

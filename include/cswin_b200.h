@@ -49,6 +49,9 @@ const char* cswin_last_error(void);
 uint64_t cswin_launch_count(void);
 /* ... of which tcgen05 / TMEM / TMA kernels (attention_tc.cu, gemm_tc.cu); lets tests assert the tensor-core path ran */
 uint64_t cswin_tc_launch_count(void);
+/* debug / profiling aid: when non-NULL, the tcgen05 kernels write %globaltimer stamps of their phases for the first 1024
+ * CTAs of every launch into this device buffer (1024 x 16 uint64); NULL (default) disables it. Not part of the data path. */
+void cswin_debug_set_trace(void* device_buffer);
 
 /* ------------------------------------------------------------------------------------------------
  * LePE cross-shaped-window attention.
