@@ -28,8 +28,7 @@ using namespace tc;
 
 constexpr int BM = 128, BK = 64;
 constexpr int kMaxStages = 8;
-constexpr int kThreads = 192;
-constexpr int kStageEpiBytes = 4 * 32 * 64 * 4;        // 4 warps x (32 rows x 64 cols fp32) = 32 KB, ALIASED onto the operand ring
+constexpr int kThreads = 320;                          // warp 0 TMA, warp 1 MMA + TMEM, warps 2..9 epilogue
 
 struct alignas(64) GemmTcParams {
   CUtensorMap map_a, map_a2, map_w;
@@ -59,18 +58,20 @@ __device__ __forceinline__ float gelu_fast(float x) {
   return 0.5f * x * (1.0f + copysignf(erf_abs, x));
 }
 
-__global__ void __launch_bounds__(kThreads, 3) linear_tc_kernel(const __grid_constant__ GemmTcParams P) {
+__global__ void __launch_bounds__(kThreads, 2) linear_tc_kernel(const __grid_constant__ GemmTcParams P) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment for the 128-byte swizzle; plain pointer arithmetic keeps the shared address space (LDS/STS)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int BN = P.BN, S = P.stages;
   const uint32_t a_bytes = BM * BK * 2, w_bytes = (uint32_t)BN * BK * 2;
   uint8_t* As = smem;                                   // [S][128][64] bf16, SW128
   uint8_t* Ws = As + (size_t)S * a_bytes;               // [S][BN][64]
-  // epilogue staging [4][32][64] fp32 (swizzled) re-uses the operand ring: it is only touched after bar_acc, i.e. after
-  // every TMA load has landed and every MMA has finished reading shared memory
-  float* Epi = reinterpret_cast<float*>(smem);
+  // epilogue staging (8 warps x 32 rows x 64 B, bf16, swizzled) re-uses the operand ring: it is only touched after
+  // bar_acc, i.e. after every TMA load has landed and every MMA has finished reading shared memory
+  uint8_t* Epi = smem;
   const size_t ring = (size_t)S * (a_bytes + w_bytes);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (ring > (size_t)kStageEpiBytes ? ring : (size_t)kStageEpiBytes));
+  float* sBias = reinterpret_cast<float*>(smem + ring);                  // [256] fp32
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + 256);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -90,6 +91,10 @@ __global__ void __launch_bounds__(kThreads, 3) linear_tc_kernel(const __grid_con
     if (P.K2 > 0) tma_prefetch_desc(&P.map_a2);
   }
   if (warp == 1) { tmem_alloc(smem_u32(tmem_slot), (uint32_t)P.tmem_cols); tmem_relinquish(); }
+  if (warp >= 2) {                                      // bias of this tile's columns -> smem (fp32)
+    const int j = tid - 64, n = n0 + j;
+    sBias[j] = (P.bias != nullptr && j < BN && n < P.N) ? __bfloat162float(P.bias[n]) : 0.f;
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -125,74 +130,75 @@ __global__ void __launch_bounds__(kThreads, 3) linear_tc_kernel(const __grid_con
       tc_commit(bar_acc);                               // accumulator complete
       trace_stamp(P.trace, 4);                          // all MMAs issued
     }
-  } else {                                              // ---- epilogue warps 2..5 ----
-    const int q = warp & 3;                             // TMEM lane quadrant this warp may touch
-    float* stg = Epi + (warp - 2) * (32 * 64);
+  } else {
+    // ---- epilogue: warps 2..9.  TMEM lane quadrant q = warp % 4 (hardware rule); the two warps of a quadrant take the
+    //      even / odd 32-column units.  Per unit: tcgen05.ld -> bias / GELU / DropPath scale in registers -> bf16 ->
+    //      swizzled 2 KB staging tile -> row-contiguous read-back so the residual load and the store are coalesced 16 B.
+    const int q = warp & 3;
+    const int ch = (warp - 2) >> 2;
+    uint8_t* stg = Epi + (warp - 2) * 2048;
+    const uint32_t stg_u32 = smem_u32(stg);
+    const int64_t mrow = m0 + q * 32 + lane;            // accumulator row held by this thread in phase 1
+    const float sc = (P.sscale != nullptr && mrow < P.M) ? P.sscale[mrow / P.rps] : 1.0f;
+    const int nunits = (BN + 31) >> 5;
     mbar_wait(bar_acc, 0);
     if (warp == 2 && lane == 0) trace_stamp(P.trace, 5);  // accumulator ready
     tc_fence_after();
     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
-    const int c8 = lane & 7;                              // this lane's 8 columns inside every 64-column group
-    for (int g = 0; g * 64 < BN; ++g) {
-      // 1. accumulators -> swizzled fp32 staging (row = lane); no arithmetic here
+    for (int u = ch; u < nunits; u += 2) {
+      uint32_t v[32];
+      tmem_ld32(trow + u * 32, v);
+      tmem_wait_ld();
+      const float4* b4 = reinterpret_cast<const float4*>(sBias + u * 32);
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        uint32_t v[32];
-        tmem_ld32(trow + g * 64 + h * 32, v);
-        tmem_wait_ld();
+      for (int c = 0; c < 4; ++c) {                     // four 16-byte chunks of 8 columns
+        float f[8];
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const int chunk = (h * 32 + j) >> 2;            // 16-byte chunk index 0..15 inside the 256-byte row
-          *reinterpret_cast<uint4*>(stg + lane * 64 + ((chunk ^ (lane & 7)) << 2)) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        for (int h = 0; h < 2; ++h) {
+          const float4 bb = b4[c * 2 + h];
+          f[h * 4 + 0] = __uint_as_float(v[c * 8 + h * 4 + 0]) + bb.x;
+          f[h * 4 + 1] = __uint_as_float(v[c * 8 + h * 4 + 1]) + bb.y;
+          f[h * 4 + 2] = __uint_as_float(v[c * 8 + h * 4 + 2]) + bb.z;
+          f[h * 4 + 3] = __uint_as_float(v[c * 8 + h * 4 + 3]) + bb.w;
         }
+        if (P.act == 1) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) f[e] = gelu_fast(f[e]);
+        }
+        if (P.sscale != nullptr) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) f[e] *= sc;
+        }
+        const uint32_t addr = stg_u32 + lane * 64 + (((c ^ (lane >> 1)) & 3) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(pack_bf16x2(f[0], f[1])),
+                     "r"(pack_bf16x2(f[2], f[3])), "r"(pack_bf16x2(f[4], f[5])), "r"(pack_bf16x2(f[6], f[7])) : "memory");
       }
       __syncwarp();
-      // 2. read back row-contiguous: 8 lanes cover the 64 columns (8 each) of one row, 4 rows per pass, 8 passes;
-      //    bias / GELU / DropPath scale / residual happen here so that every global access is a coalesced 16 B
-      const int n = n0 + g * 64 + c8 * 8;
-      const bool col_ok = n < P.N && g * 64 + c8 * 8 < BN;
-      float bv[8];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) bv[e] = 0.f;
-      if (P.bias != nullptr && col_ok) {
-        if (P.bias_vec && n + 8 <= P.N) {
-          const uint4 b4 = *reinterpret_cast<const uint4*>(P.bias + n);
-          bv[0] = bf16_lo(b4.x); bv[1] = bf16_hi(b4.x); bv[2] = bf16_lo(b4.y); bv[3] = bf16_hi(b4.y);
-          bv[4] = bf16_lo(b4.z); bv[5] = bf16_hi(b4.z); bv[6] = bf16_lo(b4.w); bv[7] = bf16_hi(b4.w);
-        } else {
-#pragma unroll
-          for (int e = 0; e < 8; ++e) if (n + e < P.N) bv[e] = __bfloat162float(P.bias[n + e]);
-        }
-      }
-#pragma unroll
-      for (int pass = 0; pass < 8; ++pass) {
-        const int r = pass * 4 + (lane >> 3);
+      for (int pass = 0; pass < 4; ++pass) {            // 8 rows x 64 B per pass, 4 lanes per row
+        const int r = pass * 8 + (lane >> 2), c = lane & 3;
         const int64_t m = m0 + q * 32 + r;
-        const float4 lo = *reinterpret_cast<const float4*>(stg + r * 64 + (((2 * c8) ^ (r & 7)) << 2));
-        const float4 hi = *reinterpret_cast<const float4*>(stg + r * 64 + (((2 * c8 + 1) ^ (r & 7)) << 2));
-        float f[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
-        if (m < P.M && col_ok) {
-          const float sc = (P.sscale != nullptr) ? P.sscale[m / P.rps] : 1.0f;
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            float x = f[e] + bv[e];
-            if (P.act == 1) x = gelu_fast(x);
-            f[e] = x * sc;
-          }
+        const int n = n0 + u * 32 + c * 8;
+        uint4 w;
+        asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w)
+                     : "r"(stg_u32 + r * 64 + (((c ^ (r >> 1)) & 3) << 4)));
+        if (m < P.M && n < P.N && u * 32 + c * 8 < BN) {
           __nv_bfloat16* dst = P.out + m * P.ldo + n;
           if (P.vec_ok && n + 8 <= P.N) {
             if (P.res != nullptr) {
               const uint4 rv = *reinterpret_cast<const uint4*>(P.res + m * P.ldr + n);
-              f[0] += bf16_lo(rv.x); f[1] += bf16_hi(rv.x); f[2] += bf16_lo(rv.y); f[3] += bf16_hi(rv.y);
-              f[4] += bf16_lo(rv.z); f[5] += bf16_hi(rv.z); f[6] += bf16_lo(rv.w); f[7] += bf16_hi(rv.w);
+              w.x = pack_bf16x2(bf16_lo(w.x) + bf16_lo(rv.x), bf16_hi(w.x) + bf16_hi(rv.x));
+              w.y = pack_bf16x2(bf16_lo(w.y) + bf16_lo(rv.y), bf16_hi(w.y) + bf16_hi(rv.y));
+              w.z = pack_bf16x2(bf16_lo(w.z) + bf16_lo(rv.z), bf16_hi(w.z) + bf16_hi(rv.z));
+              w.w = pack_bf16x2(bf16_lo(w.w) + bf16_lo(rv.w), bf16_hi(w.w) + bf16_hi(rv.w));
             }
-            *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
-                                                        pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+            *reinterpret_cast<uint4*>(dst) = w;
           } else {
+            const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
               if (n + e < P.N) {
-                float x = f[e];
+                float x = (e & 1) ? bf16_hi(ww[e >> 1]) : bf16_lo(ww[e >> 1]);
                 if (P.res != nullptr) x += __bfloat162float(P.res[m * P.ldr + n + e]);
                 dst[e] = __float2bfloat16_rn(x);
               }
@@ -213,8 +219,8 @@ __global__ void __launch_bounds__(kThreads, 3) linear_tc_kernel(const __grid_con
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 size_t smem_bytes(int bn, int stages) {
-  const size_t ring = (size_t)stages * (BM * BK * 2 + (size_t)bn * BK * 2);
-  return 1024 + (ring > (size_t)kStageEpiBytes ? ring : (size_t)kStageEpiBytes) + 128;
+  const size_t ring = (size_t)stages * (BM * BK * 2 + (size_t)bn * BK * 2);     // >= 18 KB > the aliased 16 KB staging
+  return 1024 + ring + 1024 /* bias */ + 256 /* barriers, TMEM slot */;
 }
 int tmem_cols_for(int bn) { return bn <= 64 ? 64 : bn <= 128 ? 128 : 256; }      // the epilogue reads whole 64-col groups
 
@@ -238,7 +244,7 @@ TileCfg pick_tile(int64_t M, int N, int nkb, int act, int sms) {
     if (N % bn != 0 && bn > 64 && bn != n16) continue;
     const int64_t tiles = mt * ((N + bn - 1) / bn);
     int resident = 512 / tmem_cols_for(bn);
-    if (resident > 3) resident = 3;
+    if (resident > 2) resident = 2;                              // 320 threads x ~80 registers: two CTAs per SM
     while (resident > 1 && smem_bytes(bn, 2) * resident > 220 * 1024) --resident;
     const int64_t waves = (tiles + (int64_t)sms * resident - 1) / ((int64_t)sms * resident);
     int64_t share = (tiles + sms - 1) / sms;                    // CTAs that will actually share an SM
