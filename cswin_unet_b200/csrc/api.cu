@@ -1,6 +1,7 @@
 // api.cu — extern "C" boundary of libcswin_b200.so (declared in include/cswin_b200.h).
 // Argument validation, dtype / kernel-family selection, thread-local error text.  No torch types, no allocation,
 // no synchronisation: every entry point only enqueues kernels on the caller's stream.
+#include <cstdlib>
 #include <mutex>
 
 #include "common.cuh"
@@ -22,6 +23,11 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(t_err, sizeof(t_err), fmt, ap);
   va_end(ap);
+}
+
+bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("CSWIN_PDL"); return !(e && e[0] == '0'); }();
+  return on;
 }
 
 int sm_count() {

@@ -75,6 +75,7 @@ __global__ void __launch_bounds__(kThreads, 3) lepe_attn_fwd_tc_kernel(const __g
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
 
   const int tid = threadIdx.x, warp = tid >> 5;
+  pdl_trigger();
   if (tid == 0) trace_stamp(P.trace, 0);
   const int row = tid & 127;                   // tile row == TMEM lane
   const int half = tid >> 7;                   // which half of the row's columns / channels this thread owns
@@ -135,6 +136,7 @@ __global__ void __launch_bounds__(kThreads, 3) lepe_attn_fwd_tc_kernel(const __g
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (tid == 0) trace_stamp(P.trace, 1);                     // prologue done
+  pdl_wait();                                                // q, k, v (previous kernel's output) and `out` are safe from here
 
   if (tid == 0) {
     mbar_expect_tx(bar_tma, (uint32_t)(np * 3 * N * kRowBytes));
@@ -363,7 +365,7 @@ int lepe_attention_fwd_tc(const cswin_lepe_branch_t* brs, int nb, int B, int res
   }
   if (nb == 1) P.br[1] = P.br[0];
   static_assert(kSmemBytes <= 48 * 1024, "dynamic smem must stay under the no-opt-in limit");
-  lepe_attn_fwd_tc_kernel<<<tiles, kThreads, kSmemBytes, stream>>>(P);
+  CSWIN_CUDA_OK(launch_pdl(lepe_attn_fwd_tc_kernel, dim3(tiles), dim3(kThreads), (size_t)kSmemBytes, stream, P));
   CSWIN_LAUNCH_CHECK();
   g_tc_launches.fetch_add(1, std::memory_order_relaxed);
   *handled = true;

@@ -45,6 +45,28 @@ extern std::atomic<unsigned long long*> g_trace;   // debug: device buffer for i
 
 int sm_count();   // SM count of the current device (cached)
 
+// ---- programmatic dependent launch (PDL) ----
+// Every bf16 hot-path kernel starts with pdl_trigger() (lets the NEXT kernel in the stream begin its prologue: barrier
+// init, TMEM allocation, descriptor prefetch, weight staging) and executes pdl_wait() in EVERY thread before it touches
+// memory that an earlier kernel may still be writing or reading (activations in, outputs out).  Weights / biases are
+// never written on this path, so they may be fetched before the wait.  CSWIN_PDL=0 disables the launch attribute.
+bool pdl_enabled();
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+#endif
+
 // ---- element access: T in {float, __nv_bfloat16}, arithmetic always fp32 ----
 template <typename T> __device__ __forceinline__ float ldf(const T* p);
 template <> __device__ __forceinline__ float ldf<float>(const float* p) { return *p; }

@@ -17,6 +17,8 @@ __global__ void __launch_bounds__(256) im2col_tokens_kernel(const T* __restrict_
                                                              T* __restrict__ col, int64_t ldcol, int B, int H, int W,
                                                              int C, int KH, int KW, int stride, int pad, int Ho, int Wo, int vec) {
   // one thread per (output pixel, tap, 8-channel chunk); C % 8 == 0 is guaranteed by the launcher
+  pdl_trigger();
+  pdl_wait();
   const int cv = C >> 3;
   const int64_t total = (int64_t)B * Ho * Wo * KH * KW * cv;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -62,6 +64,8 @@ __global__ void __launch_bounds__(256) im2col_nchw_kernel(const TI* __restrict__
   const int KH = CK > 0 ? CK : KH_, KW = CK > 0 ? CK : KW_, stride = CS > 0 ? CS : stride_;
   const int ldcol = (int)ldcol_;
   extern __shared__ float patch[];                     // [C][KH][span]
+  pdl_trigger();
+  pdl_wait();
   const int segs = (Wo + kI2cSeg - 1) / kI2cSeg;
   const int seg = blockIdx.x % segs;
   const int oy = (blockIdx.x / segs) % Ho;
@@ -157,6 +161,8 @@ __global__ void __launch_bounds__(256) carafe_reassemble_warp_kernel(const __nv_
                                                                       const __nv_bfloat16* __restrict__ bias,
                                                                       __nv_bfloat16* __restrict__ y, int64_t ldy, int64_t npix,
                                                                       int H, int W, int up) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int64_t pix = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (pix >= npix) return;
@@ -223,6 +229,8 @@ __global__ void __launch_bounds__(256) carafe_head_kernel(const T* __restrict__ 
                                                            int64_t ldz, const T* __restrict__ bias, TO* __restrict__ logits,
                                                            uint8_t* __restrict__ labels, int B, int H, int W, int C, int up,
                                                            int zvec) {
+  pdl_trigger();
+  pdl_wait();
   const int Ho = H * up, Wo = W * up, s2 = up * up;
   const int64_t total = (int64_t)B * Ho * Wo;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -287,11 +295,11 @@ int carafe_head_fwd(const void* enc, int64_t ldenc, const void* z, int64_t ldz, 
   const int zvec = dtype == CSWIN_BF16 && ldz >= 16 && (ldz * 2) % 16 == 0 && reinterpret_cast<uintptr_t>(z) % 16 == 0;
   if (dtype == CSWIN_F32) {
     CSWIN_REQUIRE(!logits || logits_is_f32, CSWIN_ERR_INVALID, "carafe_head: fp32 path writes fp32 logits");
-    carafe_head_kernel<float, float><<<grid, 256, 0, s>>>((const float*)enc, ldenc, (const float*)z, ldz, (const float*)bias, (float*)logits, labels, B, H, W, C, up, zvec);
+    CSWIN_CUDA_OK(launch_pdl(carafe_head_kernel<float, float>, dim3(grid), dim3(256), (size_t)(0), s, (const float*)enc, ldenc, (const float*)z, ldz, (const float*)bias, (float*)logits, labels, B, H, W, C, up, zvec));
   } else if (logits_is_f32) {
-    carafe_head_kernel<__nv_bfloat16, float><<<grid, 256, 0, s>>>((const __nv_bfloat16*)enc, ldenc, (const __nv_bfloat16*)z, ldz, (const __nv_bfloat16*)bias, (float*)logits, labels, B, H, W, C, up, zvec);
+    CSWIN_CUDA_OK(launch_pdl(carafe_head_kernel<__nv_bfloat16, float>, dim3(grid), dim3(256), (size_t)(0), s, (const __nv_bfloat16*)enc, ldenc, (const __nv_bfloat16*)z, ldz, (const __nv_bfloat16*)bias, (float*)logits, labels, B, H, W, C, up, zvec));
   } else {
-    carafe_head_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)enc, ldenc, (const __nv_bfloat16*)z, ldz, (const __nv_bfloat16*)bias, (__nv_bfloat16*)logits, labels, B, H, W, C, up, zvec);
+    CSWIN_CUDA_OK(launch_pdl(carafe_head_kernel<__nv_bfloat16, __nv_bfloat16>, dim3(grid), dim3(256), (size_t)(0), s, (const __nv_bfloat16*)enc, ldenc, (const __nv_bfloat16*)z, ldz, (const __nv_bfloat16*)bias, (__nv_bfloat16*)logits, labels, B, H, W, C, up, zvec));
   }
   CSWIN_LAUNCH_CHECK();
   return CSWIN_OK;
@@ -310,9 +318,9 @@ int im2col_tokens(const void* x, int64_t x_bs, int64_t x_ts, void* col, int64_t 
   const int vec = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(col)) % 16 == 0) && (x_bs * es) % 16 == 0 &&
                   (x_ts * es) % 16 == 0 && (ldcol * es) % 16 == 0;
   if (dtype == CSWIN_F32)
-    im2col_tokens_kernel<float><<<grid, 256, 0, s>>>((const float*)x, x_bs, x_ts, (float*)col, ldcol, B, H, W, C, KH, KW, stride, pad, Ho, Wo, vec);
+    CSWIN_CUDA_OK(launch_pdl(im2col_tokens_kernel<float>, dim3(grid), dim3(256), (size_t)(0), s, (const float*)x, x_bs, x_ts, (float*)col, ldcol, B, H, W, C, KH, KW, stride, pad, Ho, Wo, vec));
   else
-    im2col_tokens_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)x, x_bs, x_ts, (__nv_bfloat16*)col, ldcol, B, H, W, C, KH, KW, stride, pad, Ho, Wo, vec);
+    CSWIN_CUDA_OK(launch_pdl(im2col_tokens_kernel<__nv_bfloat16>, dim3(grid), dim3(256), (size_t)(0), s, (const __nv_bfloat16*)x, x_bs, x_ts, (__nv_bfloat16*)col, ldcol, B, H, W, C, KH, KW, stride, pad, Ho, Wo, vec));
   CSWIN_LAUNCH_CHECK();
   return CSWIN_OK;
 }
@@ -331,14 +339,14 @@ int im2col_nchw(const void* x, int x_is_f32, void* col, int64_t ldcol, int B, in
   const unsigned grid = (unsigned)ctas;
   if (dtype == CSWIN_F32) {
     CSWIN_REQUIRE(x_is_f32, CSWIN_ERR_INVALID, "im2col_nchw: fp32 path needs an fp32 image");
-    if (KH == 7 && KW == 7 && stride == 4) im2col_nchw_kernel<float, float, 7, 4><<<grid, 256, smem, s>>>((const float*)x, (float*)col, ldcol, B, C, H, W, KH, KW, stride, pad, Ho, Wo);
-    else im2col_nchw_kernel<float, float, 0, 0><<<grid, 256, smem, s>>>((const float*)x, (float*)col, ldcol, B, C, H, W, KH, KW, stride, pad, Ho, Wo);
+    if (KH == 7 && KW == 7 && stride == 4) CSWIN_CUDA_OK(launch_pdl(im2col_nchw_kernel<float, float, 7, 4>, dim3(grid), dim3(256), (size_t)(smem), s, (const float*)x, (float*)col, ldcol, B, C, H, W, KH, KW, stride, pad, Ho, Wo));
+    else CSWIN_CUDA_OK(launch_pdl(im2col_nchw_kernel<float, float, 0, 0>, dim3(grid), dim3(256), (size_t)(smem), s, (const float*)x, (float*)col, ldcol, B, C, H, W, KH, KW, stride, pad, Ho, Wo));
   } else if (x_is_f32) {
-    if (KH == 7 && KW == 7 && stride == 4) im2col_nchw_kernel<float, __nv_bfloat16, 7, 4><<<grid, 256, smem, s>>>((const float*)x, (__nv_bfloat16*)col, ldcol, B, C, H, W, KH, KW, stride, pad, Ho, Wo);
-    else im2col_nchw_kernel<float, __nv_bfloat16, 0, 0><<<grid, 256, smem, s>>>((const float*)x, (__nv_bfloat16*)col, ldcol, B, C, H, W, KH, KW, stride, pad, Ho, Wo);
+    if (KH == 7 && KW == 7 && stride == 4) CSWIN_CUDA_OK(launch_pdl(im2col_nchw_kernel<float, __nv_bfloat16, 7, 4>, dim3(grid), dim3(256), (size_t)(smem), s, (const float*)x, (__nv_bfloat16*)col, ldcol, B, C, H, W, KH, KW, stride, pad, Ho, Wo));
+    else CSWIN_CUDA_OK(launch_pdl(im2col_nchw_kernel<float, __nv_bfloat16, 0, 0>, dim3(grid), dim3(256), (size_t)(smem), s, (const float*)x, (__nv_bfloat16*)col, ldcol, B, C, H, W, KH, KW, stride, pad, Ho, Wo));
   } else {
-    if (KH == 7 && KW == 7 && stride == 4) im2col_nchw_kernel<__nv_bfloat16, __nv_bfloat16, 7, 4><<<grid, 256, smem, s>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)col, ldcol, B, C, H, W, KH, KW, stride, pad, Ho, Wo);
-    else im2col_nchw_kernel<__nv_bfloat16, __nv_bfloat16, 0, 0><<<grid, 256, smem, s>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)col, ldcol, B, C, H, W, KH, KW, stride, pad, Ho, Wo);
+    if (KH == 7 && KW == 7 && stride == 4) CSWIN_CUDA_OK(launch_pdl(im2col_nchw_kernel<__nv_bfloat16, __nv_bfloat16, 7, 4>, dim3(grid), dim3(256), (size_t)(smem), s, (const __nv_bfloat16*)x, (__nv_bfloat16*)col, ldcol, B, C, H, W, KH, KW, stride, pad, Ho, Wo));
+    else CSWIN_CUDA_OK(launch_pdl(im2col_nchw_kernel<__nv_bfloat16, __nv_bfloat16, 0, 0>, dim3(grid), dim3(256), (size_t)(smem), s, (const __nv_bfloat16*)x, (__nv_bfloat16*)col, ldcol, B, C, H, W, KH, KW, stride, pad, Ho, Wo));
   }
   CSWIN_LAUNCH_CHECK();
   return CSWIN_OK;
@@ -358,9 +366,9 @@ int carafe_reassemble_fwd(const void* enc, int64_t ldenc, const void* z, int64_t
       ldz % 2 == 0 && ldy % 2 == 0 && reinterpret_cast<uintptr_t>(z) % 4 == 0 && reinterpret_cast<uintptr_t>(y) % 4 == 0) {
     const unsigned g2 = (unsigned)ceil_div64(pixels, 8);
     const __nv_bfloat16 *e_ = (const __nv_bfloat16*)enc, *z_ = (const __nv_bfloat16*)z, *b_ = (const __nv_bfloat16*)bias;
-    if (C == 64) carafe_reassemble_warp_kernel<2><<<g2, 256, 0, s>>>(e_, ldenc, z_, ldz, b_, (__nv_bfloat16*)y, ldy, pixels, H, W, up);
-    else if (C == 128) carafe_reassemble_warp_kernel<4><<<g2, 256, 0, s>>>(e_, ldenc, z_, ldz, b_, (__nv_bfloat16*)y, ldy, pixels, H, W, up);
-    else carafe_reassemble_warp_kernel<8><<<g2, 256, 0, s>>>(e_, ldenc, z_, ldz, b_, (__nv_bfloat16*)y, ldy, pixels, H, W, up);
+    if (C == 64) CSWIN_CUDA_OK(launch_pdl(carafe_reassemble_warp_kernel<2>, dim3(g2), dim3(256), (size_t)(0), s, e_, ldenc, z_, ldz, b_, (__nv_bfloat16*)y, ldy, pixels, H, W, up));
+    else if (C == 128) CSWIN_CUDA_OK(launch_pdl(carafe_reassemble_warp_kernel<4>, dim3(g2), dim3(256), (size_t)(0), s, e_, ldenc, z_, ldz, b_, (__nv_bfloat16*)y, ldy, pixels, H, W, up));
+    else CSWIN_CUDA_OK(launch_pdl(carafe_reassemble_warp_kernel<8>, dim3(g2), dim3(256), (size_t)(0), s, e_, ldenc, z_, ldz, b_, (__nv_bfloat16*)y, ldy, pixels, H, W, up));
     CSWIN_LAUNCH_CHECK();
     return CSWIN_OK;
   }

@@ -75,6 +75,7 @@ __global__ void __launch_bounds__(kThreads, 2) linear_tc_kernel(const __grid_con
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  pdl_trigger();
   if (tid == 0) trace_stamp(P.trace, 0);                                   // kernel entry
   const int64_t m0 = (int64_t)blockIdx.x * BM;
   const int n0 = blockIdx.y * BN;
@@ -101,15 +102,27 @@ __global__ void __launch_bounds__(kThreads, 2) linear_tc_kernel(const __grid_con
   const uint32_t tmem_base = *tmem_slot;
   if (tid == 0) trace_stamp(P.trace, 1);                                   // prologue done
 
+  // weights do not depend on the previous kernel: the W tiles of the first ring pass are requested before the PDL wait
+  const int npre = P.nkb < S ? P.nkb : S;
+  if (warp == 0 && lane == 0) {
+    for (int kb = 0; kb < npre; ++kb) {
+      mbar_expect_tx(full(kb), a_bytes + w_bytes);
+      tma_load_2d(smem_u32(Ws + (size_t)kb * w_bytes), &P.map_w, full(kb), kb * BK, n0);
+    }
+  }
+  pdl_wait();                                           // activations (A, residual) and the output buffer are safe from here
+
   if (warp == 0) {
     if (lane == 0) {                                    // ---- TMA producer ----
       for (int kb = 0; kb < P.nkb; ++kb) {
         const int s = kb % S;
-        if (kb >= S) mbar_wait(empty(s), ((kb / S) - 1) & 1);
-        mbar_expect_tx(full(s), a_bytes + w_bytes);
+        if (kb >= S) {
+          mbar_wait(empty(s), ((kb / S) - 1) & 1);
+          mbar_expect_tx(full(s), a_bytes + w_bytes);
+          tma_load_2d(smem_u32(Ws + (size_t)s * w_bytes), &P.map_w, full(s), kb * BK, n0);
+        }
         if (kb < P.nkb1) tma_load_2d(smem_u32(As + (size_t)s * a_bytes), &P.map_a, full(s), kb * BK, (int)m0);
         else             tma_load_2d(smem_u32(As + (size_t)s * a_bytes), &P.map_a2, full(s), (kb - P.nkb1) * BK, (int)m0);
-        tma_load_2d(smem_u32(Ws + (size_t)s * w_bytes), &P.map_w, full(s), kb * BK, n0);
       }
       trace_stamp(P.trace, 2);                          // all TMA issued
     }
@@ -316,7 +329,7 @@ int linear_fwd_tc(const cswin_linear_args_t* a, cudaStream_t stream, bool* handl
     configured.store(227 * 1024, std::memory_order_relaxed);
   }
   dim3 grid((unsigned)((a->M + BM - 1) / BM), (unsigned)((a->N + P.BN - 1) / P.BN));
-  linear_tc_kernel<<<grid, kThreads, smem, stream>>>(P);
+  CSWIN_CUDA_OK(launch_pdl(linear_tc_kernel, grid, dim3(kThreads), smem, stream, P));
   CSWIN_LAUNCH_CHECK();
   g_tc_launches.fetch_add(1, std::memory_order_relaxed);
   *handled = true;

@@ -59,6 +59,8 @@ __global__ void __launch_bounds__(256) layernorm_bf16_vec_kernel(const __nv_bflo
                                                                   float* __restrict__ rstd_out) {
   constexpr int C = LPR * NV * 8;
   constexpr int RPW = 32 / LPR;
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int sub = lane % LPR;
   const int64_t row = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW + lane / LPR;
@@ -115,8 +117,9 @@ int launch_vec(const void* x, int64_t ldx, const void* g, const void* b, void* y
                float* mean, float* rstd, cudaStream_t s) {
   constexpr int RPW = 32 / LPR;
   const int64_t rows_per_cta = 8 * RPW;
-  layernorm_bf16_vec_kernel<LPR, NV><<<(unsigned)ceil_div64(M, rows_per_cta), 256, 0, s>>>(
-      (const __nv_bfloat16*)x, ldx, (const __nv_bfloat16*)g, (const __nv_bfloat16*)b, (__nv_bfloat16*)y, ldy, M, eps, mean, rstd);
+  CSWIN_CUDA_OK(launch_pdl(layernorm_bf16_vec_kernel<LPR, NV>, dim3((unsigned)ceil_div64(M, rows_per_cta)), dim3(256), 0, s,
+                           (const __nv_bfloat16*)x, ldx, (const __nv_bfloat16*)g, (const __nv_bfloat16*)b, (__nv_bfloat16*)y,
+                           ldy, M, eps, mean, rstd));
   CSWIN_LAUNCH_CHECK();
   return CSWIN_OK;
 }
