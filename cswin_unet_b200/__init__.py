@@ -6,12 +6,12 @@ include/cswin_b200.h.  There is no CPU path and no library fallback.
 """
 from . import synth  # noqa: F401  (pure numpy; safe without the extension)
 from ._lib import CswinError, build, launch_count, lib, tc_launch_count  # noqa: F401
-from .engine import SliceEngine, shard_slices  # noqa: F401
+from .engine import SliceEngine, predict_volume, shard_slices  # noqa: F401
 from .install import install, uninstall  # noqa: F401
 from .model import CSWinTransformer, CSwinUnet, cswin_tiny_224  # noqa: F401
 from .modules import (CARAFE, CARAFE4, CSWinBlock, DropPath, LePEAttention, Merge_Block, Mlp,  # noqa: F401
                       img2windows, windows2img)
 
 __all__ = ["LePEAttention", "CSWinBlock", "Mlp", "Merge_Block", "CARAFE", "CARAFE4", "DropPath", "img2windows",
-           "windows2img", "CSWinTransformer", "CSwinUnet", "cswin_tiny_224", "SliceEngine", "shard_slices", "install", "uninstall", "build", "lib",
+           "windows2img", "CSWinTransformer", "CSwinUnet", "cswin_tiny_224", "SliceEngine", "shard_slices", "predict_volume", "install", "uninstall", "build", "lib",
            "launch_count", "tc_launch_count", "CswinError", "synth"]

@@ -108,3 +108,26 @@ class SliceEngine:
 
     def bytes_per_batch(self) -> Tuple[int, int]:
         return self.batch * self.in_chans * self.size * self.size * 4, self.batch * self.size * self.size
+
+
+def predict_volume(engine: "SliceEngine", image, order_in: int = 3, shard: Optional[Tuple[int, int]] = None):
+    """The slice loop of `test_single_volume` (utils.py:61-80) on the engine: every slice of the (D, H, W) float volume is
+    resized to the network resolution with scipy `zoom(order=3)` on the host (as the reference does), segmented in
+    batches, and the label map is resized back with `zoom(order=0)`.  `shard=(rank, world)` restricts the work to this
+    rank's contiguous slice range; returns (labels uint8 (n_local, H, W), range)."""
+    import numpy as np
+    from scipy.ndimage import zoom
+    image = np.asarray(image, dtype=np.float32)
+    D, H, W = image.shape
+    rng = shard_slices(D, shard[1], shard[0]) if shard else range(D)
+    P = engine.size
+    resized = np.empty((len(rng), 1, P, P), np.float32)
+    for j, d in enumerate(rng):
+        sl = image[d]
+        resized[j, 0] = zoom(sl, (P / H, P / W), order=order_in) if (H, W) != (P, P) else sl
+    host = torch.from_numpy(resized)
+    outs = list(engine.predict_stream(host[i:i + engine.batch] for i in range(0, len(rng), engine.batch)))
+    lab = torch.cat(outs, 0).numpy() if outs else np.zeros((0, P, P), np.uint8)
+    if (H, W) != (P, P):
+        lab = np.stack([zoom(l, (H / P, W / P), order=0) for l in lab]) if len(lab) else np.zeros((0, H, W), np.uint8)
+    return lab, rng

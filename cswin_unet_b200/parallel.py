@@ -1,0 +1,56 @@
+"""Multi-GPU plumbing (torch.distributed; one process per GPU, NCCL on GPUs, gloo in the CPU tests).
+
+Inference shards slices with no collective on the forward path; the only exchange is the gather of the uint8 label
+shards at the end of a volume.  Training (data parallel) has exactly one exchange per step: the gradient all-reduce
+(reference: single-process nn.DataParallel, trainer.py:37-38).
+"""
+from __future__ import annotations
+
+from typing import Iterable, List, Optional
+
+import torch
+import torch.distributed as dist
+
+from .engine import shard_slices  # noqa: F401  (re-export)
+
+Tensor = torch.Tensor
+
+
+def gather_label_shards(local: Tensor, n_total: int, group=None) -> Tensor:
+    """All-gather contiguous slice shards (n_local, H, W) uint8 -> (n_total, H, W) on every rank (shard_slices order)."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        assert local.shape[0] == n_total
+        return local
+    world = dist.get_world_size(group)
+    per = (n_total + world - 1) // world
+    pad = torch.zeros((per,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[: local.shape[0]] = local
+    parts = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(parts, pad, group=group)
+    out = [parts[r][: len(shard_slices(n_total, world, r))] for r in range(world)]
+    return torch.cat(out, dim=0)
+
+
+def allreduce_gradients(params: Iterable[Tensor], group=None, bucket_bytes: int = 25 << 20, average: bool = True) -> int:
+    """Bucketed gradient all-reduce (sum, then / world): flattens grads in REVERSE parameter order (the order backward
+    produces them) into ~25 MB buckets, one NCCL all-reduce per bucket.  Returns the number of collectives issued."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return 0
+    world = dist.get_world_size(group)
+    grads = [p.grad for p in reversed(list(params)) if p.grad is not None]
+    n_coll, i = 0, 0
+    while i < len(grads):
+        bucket: List[Tensor] = []
+        size = 0
+        dtype = grads[i].dtype
+        while i < len(grads) and grads[i].dtype == dtype and (not bucket or size + grads[i].numel() * grads[i].element_size() <= bucket_bytes):
+            bucket.append(grads[i]); size += grads[i].numel() * grads[i].element_size(); i += 1
+        flat = torch.cat([g.reshape(-1) for g in bucket])
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        if average:
+            flat.div_(world)
+        off = 0
+        for g in bucket:
+            g.copy_(flat[off: off + g.numel()].view_as(g)); off += g.numel()
+        n_coll += 1
+    return n_coll
