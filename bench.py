@@ -179,6 +179,7 @@ def run_native(args):
     dev = torch.device("cuda", local)
     if world > 1:
         import torch.distributed as dist
+        os.environ["NCCL_DEBUG"] = "WARN"                           # keep NCCL's version banner off stdout (one JSON line)
         dist.init_process_group("nccl", device_id=dev)
     cw.lib()                                                       # fail loudly if the extension is missing
 
