@@ -73,6 +73,17 @@ SIGNATURES = {
     "cswin_linear_fwd": (c_int32, [C.POINTER(LinearArgs), c_int32, c_void_p]),
     "cswin_im2col_tokens": (c_int32, [c_void_p, c_int64, c_int64, c_void_p, c_int64] + [c_int32] * 9 + [c_void_p]),
     "cswin_im2col_nchw": (c_int32, [c_void_p, c_int32, c_void_p, c_int64] + [c_int32] * 9 + [c_void_p]),
+    "cswin_act_fwd": (c_int32, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int32, c_int32, c_int32, c_void_p]),
+    "cswin_act_bwd": (c_int32, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int32, c_void_p, c_int64, c_int64, c_int32,
+                                c_int32, c_int32, c_void_p]),
+    "cswin_linear_wgrad": (c_int32, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int32,
+                                     c_int32, c_int32, c_void_p]),
+    "cswin_layernorm_bwd": (c_int32, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
+                                      c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p]),
+    "cswin_col2im_tokens": (c_int32, [c_void_p, c_int64, c_void_p, c_int64, c_int64] + [c_int32] * 9 + [c_void_p]),
+    "cswin_carafe_reassemble_bwd": (c_int32, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int32, c_int64, c_int64,
+                                              c_int64, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p]
+                                    + [c_int32] * 6 + [c_void_p]),
     "cswin_carafe_head_fwd": (c_int32, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int32, c_void_p]
                               + [c_int32] * 6 + [c_void_p]),
     "cswin_carafe_reassemble_fwd": (c_int32, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64]

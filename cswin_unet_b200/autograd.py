@@ -1,0 +1,190 @@
+"""torch.autograd.Functions that route the backward of the hot path through the native backward kernels
+(include/cswin_b200.h: cswin_lepe_attention_bwd, cswin_act_bwd, cswin_linear_wgrad, cswin_layernorm_bwd,
+cswin_col2im_tokens, cswin_carafe_reassemble_bwd; the data gradient of a Linear is a forward Linear on W^T).
+
+The reference has no backward source — it relies on torch.autograd through its eager ops (trainer.py:59).  Here
+autograd is only the tape: every node's forward and backward is one of our kernels.  Parameter gradients are
+accumulated in fp32 by the kernels and returned in the parameter's dtype (fp32 master weights + bf16 compute work).
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from . import ops
+
+Tensor = torch.Tensor
+
+
+def needs_grad(*ts) -> bool:
+    return torch.is_grad_enabled() and any(t is not None and torch.is_tensor(t) and t.requires_grad for t in ts)
+
+
+def _c(p: Optional[Tensor], dt: torch.dtype) -> Optional[Tensor]:
+    if p is None:
+        return None
+    p = p.detach()
+    return p if (p.dtype == dt and p.is_contiguous()) else p.to(dt).contiguous()
+
+
+class LayerNormFn(Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps):
+        dt = x.dtype
+        g, b = _c(gamma, dt), _c(beta, dt)
+        y, mean, rstd = ops.layernorm(x, g, b, eps, stats=True)
+        ctx.save_for_backward(x, g, mean, rstd)
+        ctx.pd = gamma.dtype
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        x, g, mean, rstd = ctx.saved_tensors
+        dx, dg, db = ops.layernorm_bwd(x, dy.contiguous(), g, mean, rstd)
+        return dx, dg.to(ctx.pd), db.to(ctx.pd), None
+
+
+class LinearFn(Function):
+    """out = residual + sample_scale[row // rps] * ([a | a2] @ w.T + bias)   (no activation: see GeluFn)."""
+
+    @staticmethod
+    def forward(ctx, a, w, bias, a2, residual, sample_scale, rps):
+        dt = a.dtype
+        wc, bc = _c(w, dt), _c(bias, dt)
+        out = ops.linear(a, wc, bc, a2=a2, residual=residual, sample_scale=sample_scale, rows_per_sample=rps)
+        ctx.save_for_backward(a, a2, wc, sample_scale)
+        ctx.rps, ctx.has_bias, ctx.has_res = rps, bias is not None, residual is not None
+        ctx.wd = w.dtype
+        ctx.bd = bias.dtype if bias is not None else None
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout):
+        a, a2, wc, ss = ctx.saved_tensors
+        dout = dout.contiguous()
+        dz = dout if ss is None else ops.act_bwd(dout, None, ss, ctx.rps, act=0)
+        K1 = a.shape[-1]
+        N, K = wc.shape
+        wt = wc.t().contiguous()                                   # (K, N): dA = dZ @ W is a forward Linear on W^T
+        need = ctx.needs_input_grad
+        da = ops.linear(dz, wt[:K1]) if need[0] else None
+        da2 = ops.linear(dz, wt[K1:]) if (a2 is not None and need[3]) else None
+        dw = db = None
+        if need[1] or need[2]:
+            dwf = torch.zeros((N, K), dtype=torch.float32, device=dz.device)
+            dbf = torch.zeros(N, dtype=torch.float32, device=dz.device) if ctx.has_bias else None
+            ops.linear_wgrad(dz, a, dwf[:, :K1], dbf)
+            if a2 is not None:
+                ops.linear_wgrad(dz, a2, dwf[:, K1:], None)
+            dw = dwf.to(ctx.wd)
+            db = dbf.to(ctx.bd) if ctx.has_bias else None
+        return da, dw, db, da2, (dout if ctx.has_res else None), None, None
+
+
+class GeluFn(Function):
+    @staticmethod
+    def forward(ctx, z):
+        ctx.save_for_backward(z)
+        return ops.act_fwd(z, act=1)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dh):
+        (z,) = ctx.saved_tensors
+        return ops.act_bwd(dh.contiguous(), z, None, 0, act=1)
+
+
+class LepeAttentionFn(Function):
+    """(B, L, 3C) qkv -> (B, L, C): one or two stripe branches (cswin_unet.py:172-176 + :82-109)."""
+
+    @staticmethod
+    def forward(ctx, qkv, cw0, cb0, cw1, cb1, meta):
+        B, L, C3 = qkv.shape
+        Cn = C3 // 3
+        dt = qkv.dtype
+        out = torch.empty((B, L, Cn), dtype=dt, device=qkv.device)
+        ws = [(_c(cw0, dt), _c(cb0, dt))] + ([(_c(cw1, dt), _c(cb1, dt))] if cw1 is not None else [])
+        ops.lepe_attention_fwd(LepeAttentionFn._descs(qkv, out, ws, meta, Cn), B, meta["reso"], meta["scale"], dt)
+        ctx.save_for_backward(qkv, *[t for pair in ws for t in pair])
+        ctx.meta, ctx.pd = meta, cw0.dtype
+        return out
+
+    @staticmethod
+    def _descs(qkv, out, ws, meta, Cn, extra=None):
+        q, k, v = qkv[..., :Cn], qkv[..., Cn:2 * Cn], qkv[..., 2 * Cn:]
+        nb = len(ws)
+        h = Cn // nb
+        descs = []
+        for i, (cw, cb) in enumerate(ws):
+            sl = slice(i * h, (i + 1) * h)
+            d = dict(q=q[..., sl], k=k[..., sl], v=v[..., sl], out=out[..., sl], conv_w=cw, conv_b=cb,
+                     heads=meta["heads"][i], H_sp=meta["win"][i][0], W_sp=meta["win"][i][1])
+            if extra is not None:
+                d.update(extra(i, sl))
+            descs.append(d)
+        return descs
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout):
+        qkv, *wflat = ctx.saved_tensors
+        ws = [(wflat[2 * i], wflat[2 * i + 1]) for i in range(len(wflat) // 2)]
+        meta = ctx.meta
+        B, L, C3 = qkv.shape
+        Cn = C3 // 3
+        dout = dout.contiguous()
+        dqkv = torch.empty_like(qkv)
+        dq, dk, dv = dqkv[..., :Cn], dqkv[..., Cn:2 * Cn], dqkv[..., 2 * Cn:]
+        h = Cn // len(ws)
+        gw = [torch.zeros((h, 9), dtype=torch.float32, device=qkv.device) for _ in ws]
+        gb = [torch.zeros(h, dtype=torch.float32, device=qkv.device) for _ in ws]
+
+        def extra(i, sl):
+            return dict(dout=dout[..., sl], dq=dq[..., sl], dk=dk[..., sl], dv=dv[..., sl], dconv_w=gw[i], dconv_b=gb[i])
+        descs = LepeAttentionFn._descs(qkv, dout, ws, meta, Cn, extra)
+        ops.lepe_attention_bwd(descs, B, meta["reso"], meta["scale"], qkv.dtype)
+        g0 = (gw[0].view(h, 1, 3, 3).to(ctx.pd), gb[0].to(ctx.pd))
+        g1 = (gw[1].view(h, 1, 3, 3).to(ctx.pd), gb[1].to(ctx.pd)) if len(ws) == 2 else (None, None)
+        return dqkv, g0[0], g0[1], g1[0], g1[1], None
+
+
+class Im2colTokensFn(Function):
+    @staticmethod
+    def forward(ctx, x, H, W, KH, KW, stride, pad):
+        ctx.geom = (x.shape[0], H, W, x.shape[-1], KH, KW, stride, pad)
+        return ops.im2col_tokens(x, H, W, KH, KW, stride, pad)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dcol):
+        B, H, W, Cn, KH, KW, stride, pad = ctx.geom
+        return ops.col2im_tokens(dcol, B, H, W, Cn, KH, KW, stride, pad), None, None, None, None, None, None
+
+
+class CarafeReassembleFn(Function):
+    """enc (B*H*W, 9 up^2), z (B*H*W, C), bias (C) -> (B, up^2 H W, C)."""
+
+    @staticmethod
+    def forward(ctx, enc, z, bias, B, H, W, up):
+        dt = z.dtype
+        y = ops.carafe_reassemble(enc, z, _c(bias, dt), B, H, W, up)
+        ctx.save_for_backward(enc, z)
+        ctx.geom, ctx.bd = (B, H, W, up), bias.dtype
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        enc, z = ctx.saved_tensors
+        B, H, W, up = ctx.geom
+        denc, dz, dbias = ops.carafe_reassemble_bwd(enc, z, dy, B, H, W, up)
+        return denc, dz, dbias.to(ctx.bd), None, None, None, None
+
+
+def linear(a, w, bias=None, a2=None, residual=None, sample_scale=None, rps=0):
+    return LinearFn.apply(a, w, bias, a2, residual, sample_scale, rps)

@@ -140,4 +140,47 @@ int cswin_carafe_head_fwd(const void* enc, int64_t ldenc, const void* z, int64_t
   return carafe_head_fwd(enc, ldenc, z, ldz, bias, logits, logits_is_f32, labels, B, H, W, C, up, dtype, (cudaStream_t)stream);
 }
 
+int cswin_act_fwd(const void* z, int64_t ldz, void* out, int64_t ldo, int64_t M, int32_t N, int32_t act, int32_t dtype,
+                  cswin_stream_t stream) {
+  CSWIN_REQUIRE(valid_dtype(dtype) && M >= 0 && N > 0 && (act == 0 || act == 1), CSWIN_ERR_INVALID, "act_fwd: bad arguments");
+  return act_fwd(z, ldz, out, ldo, M, N, act, dtype, (cudaStream_t)stream);
+}
+
+int cswin_act_bwd(const void* dout, int64_t ldd, const void* z, int64_t ldz, const float* sample_scale,
+                  int32_t rows_per_sample, void* dz, int64_t ldo, int64_t M, int32_t N, int32_t act, int32_t dtype,
+                  cswin_stream_t stream) {
+  CSWIN_REQUIRE(valid_dtype(dtype) && M >= 0 && N > 0 && (act == 0 || act == 1), CSWIN_ERR_INVALID, "act_bwd: bad arguments");
+  return act_bwd(dout, ldd, z, ldz, sample_scale, rows_per_sample, dz, ldo, M, N, act, dtype, (cudaStream_t)stream);
+}
+
+int cswin_linear_wgrad(const void* dz, int64_t ldz, const void* a, int64_t lda, float* dw, int64_t ldw, float* db, int64_t M,
+                       int32_t N, int32_t K, int32_t dtype, cswin_stream_t stream) {
+  CSWIN_REQUIRE(valid_dtype(dtype) && M >= 0 && N > 0 && K > 0, CSWIN_ERR_INVALID, "linear_wgrad: bad arguments");
+  CSWIN_REQUIRE(ldz >= N && lda >= K && ldw >= K, CSWIN_ERR_INVALID, "linear_wgrad: leading dimension too small");
+  return linear_wgrad(dz, ldz, a, lda, dw, ldw, db, M, N, K, dtype, (cudaStream_t)stream);
+}
+
+int cswin_layernorm_bwd(const void* x, int64_t ldx, const void* dy, int64_t ldy, const void* gamma, const float* mean,
+                        const float* rstd, void* dx, int64_t ldo, float* dgamma, float* dbeta, int64_t M, int32_t C,
+                        int32_t dtype, cswin_stream_t stream) {
+  CSWIN_REQUIRE(valid_dtype(dtype) && M >= 0, CSWIN_ERR_INVALID, "layernorm_bwd: bad arguments");
+  return layernorm_bwd(x, ldx, dy, ldy, gamma, mean, rstd, dx, ldo, dgamma, dbeta, M, C, dtype, (cudaStream_t)stream);
+}
+
+int cswin_col2im_tokens(const void* dcol, int64_t ldcol, void* dx, int64_t x_bs, int64_t x_ts, int32_t B, int32_t H, int32_t W,
+                        int32_t C, int32_t KH, int32_t KW, int32_t stride, int32_t pad, int32_t dtype, cswin_stream_t stream) {
+  CSWIN_REQUIRE(valid_dtype(dtype), CSWIN_ERR_INVALID, "col2im_tokens: bad dtype %d", dtype);
+  CSWIN_REQUIRE(B >= 0 && H > 0 && W > 0 && C > 0 && KH > 0 && KW > 0 && stride > 0 && pad >= 0, CSWIN_ERR_INVALID, "col2im_tokens: bad shape");
+  return col2im_tokens(dcol, ldcol, dx, x_bs, x_ts, B, H, W, C, KH, KW, stride, pad, dtype, (cudaStream_t)stream);
+}
+
+int cswin_carafe_reassemble_bwd(const void* enc, int64_t ldenc, const void* z, int64_t ldz, const void* dy, int32_t dy_is_f32,
+                                int64_t dy_sb, int64_t dy_sy, int64_t dy_sx, int64_t dy_sc, void* denc, int64_t lddenc,
+                                void* dz, int64_t lddz, float* dbias, float* kappa_ws, int32_t B, int32_t H, int32_t W,
+                                int32_t C, int32_t up, int32_t dtype, cswin_stream_t stream) {
+  CSWIN_REQUIRE(valid_dtype(dtype) && B >= 0 && H > 0 && W > 0, CSWIN_ERR_INVALID, "carafe_reassemble_bwd: bad arguments");
+  return carafe_reassemble_bwd(enc, ldenc, z, ldz, dy, dy_is_f32, dy_sb, dy_sy, dy_sx, dy_sc, denc, lddenc, dz, lddz, dbias,
+                               kappa_ws, B, H, W, C, up, dtype, (cudaStream_t)stream);
+}
+
 }  // extern "C"

@@ -169,6 +169,225 @@ int launch_fwd(const cswin_lepe_branch_t* brs, int nb, int B, int reso, float sc
   return CSWIN_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// backward (autograd of networks/cswin_unet.py:82-109; formulas: SURVEY.md Appendix A).  One CTA (8 warps) per
+// (batch, window, head).  Q, K, V and the upstream gradient G of the window are staged in shared memory as fp32.
+//   pass A (one warp per query row n):  P_n = softmax(scale q_n K^T) recomputed, dP = G_n V^T, delta_n = <P_n, dP>,
+//           dS = P o (dP - delta), dQ_n = scale dS K;  lse_n and delta_n are kept in shared memory;
+//   pass B (one warp per key row m):    column m of P and dS recomputed from lse / delta,
+//           dK_m = scale dS^T Q, dV_m = P^T G + depthwise-conv-transpose(G) with WINDOW-local zero padding;
+//   LePE parameters: d w[j,t] = sum_n G[n,j] V^[n+t, j], d b[j] = sum_n G[n,j], reduced per CTA then fp32 atomics.
+// ------------------------------------------------------------------------------------------------------------------
+template <typename T>
+struct BranchGradDev {
+  BranchDev<T> f;
+  const T* g; int64_t g_bs, g_ts;
+  T* dq; T* dk; T* dv;
+  int64_t dq_bs, dq_ts, dk_bs, dk_ts, dv_bs, dv_ts;
+  float* dcw; float* dcb;
+};
+template <typename T>
+struct AttnGradParams {
+  BranchGradDev<T> br[2];
+  int nb, B, reso;
+  float scale;
+};
+
+constexpr int kBwdWarps = 8;
+
+template <typename T, int MAXI>
+__global__ void __launch_bounds__(kBwdWarps * 32) lepe_attn_bwd_simt_kernel(const AttnGradParams<T> P) {
+  extern __shared__ float smem[];
+  const int p = blockIdx.x;
+  const int bi = (P.nb > 1 && p >= P.br[1].f.prob_begin) ? 1 : 0;
+  const BranchGradDev<T>& bg = P.br[bi];
+  const BranchDev<T>& br = bg.f;
+  int local = p - br.prob_begin;
+  const int head = local % br.heads; local /= br.heads;
+  const int win = local % br.nwin;
+  const int b = local / br.nwin;
+  const int ih = win / br.nww, iw = win % br.nww;
+  const int hs = br.hs, ws = br.ws, d = br.d, N = hs * ws, dp = d | 1;
+  const int W = P.reso;
+  const int ch0 = head * d;
+
+  float* Qs = smem;                       // [N][dp]
+  float* Ks = Qs + N * dp;
+  float* Vs = Ks + N * dp;
+  float* Gs = Vs + N * dp;
+  float* Lse = Gs + N * dp;               // [N]
+  float* Dl = Lse + N;                    // [N]
+  float* Ab = Dl + N;                     // [kBwdWarps][N]  dS row / column
+  float* Bb = Ab + kBwdWarps * N;         // [kBwdWarps][N]  P column
+  float* Wc = Bb + kBwdWarps * N;         // [d][9]
+  float* Part = Wc + d * 9;               // [kBwdWarps][d][10] partial d w / d b
+
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  auto tok_of = [&](int n) -> int64_t { const int r = n / ws, c = n - r * ws; return (int64_t)(ih * hs + r) * W + (iw * ws + c); };
+  for (int i = tid; i < N * d; i += kBwdWarps * 32) {
+    const int n = i / d, j = i - n * d;
+    const int64_t tok = tok_of(n);
+    Qs[n * dp + j] = ldf(br.q + (int64_t)b * br.q_bs + tok * br.q_ts + ch0 + j);
+    Ks[n * dp + j] = ldf(br.k + (int64_t)b * br.k_bs + tok * br.k_ts + ch0 + j);
+    Vs[n * dp + j] = ldf(br.v + (int64_t)b * br.v_bs + tok * br.v_ts + ch0 + j);
+    Gs[n * dp + j] = ldf(bg.g + (int64_t)b * bg.g_bs + tok * bg.g_ts + ch0 + j);
+  }
+  for (int i = tid; i < d * 9; i += kBwdWarps * 32) Wc[i] = ldf(br.cw + (int64_t)ch0 * 9 + i);
+  __syncthreads();
+
+  float* ab = Ab + w * N;
+  float* bb = Bb + w * N;
+  // ---- pass A: rows ----
+  for (int n = w; n < N; n += kBwdWarps) {
+    float sv[MAXI], dv_[MAXI];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < MAXI; ++i) {
+      const int m = lane + 32 * i;
+      float acc = -INFINITY, accd = 0.f;
+      if (m < N) {
+        acc = 0.f;
+        for (int j = 0; j < d; ++j) {
+          acc = fmaf(Qs[n * dp + j], Ks[m * dp + j], acc);
+          accd = fmaf(Gs[n * dp + j], Vs[m * dp + j], accd);
+        }
+        acc *= P.scale;
+      }
+      sv[i] = acc; dv_[i] = accd;
+      mx = fmaxf(mx, acc);
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXI; ++i) if (lane + 32 * i < N) sum += expf(sv[i] - mx);
+    sum = warp_sum(sum);
+    const float lse = mx + logf(sum);
+    float delta = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXI; ++i) if (lane + 32 * i < N) { sv[i] = expf(sv[i] - lse); delta = fmaf(sv[i], dv_[i], delta); }
+    delta = warp_sum(delta);
+#pragma unroll
+    for (int i = 0; i < MAXI; ++i) { const int m = lane + 32 * i; if (m < N) ab[m] = sv[i] * (dv_[i] - delta); }
+    if (lane == 0) { Lse[n] = lse; Dl[n] = delta; }
+    __syncwarp();
+    const int64_t tok = tok_of(n);
+    for (int j = lane; j < d; j += 32) {
+      float acc = 0.f;
+      for (int m = 0; m < N; ++m) acc = fmaf(ab[m], Ks[m * dp + j], acc);
+      stf(bg.dq + (int64_t)b * bg.dq_bs + tok * bg.dq_ts + ch0 + j, acc * P.scale);
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  // ---- pass B: columns ----
+  for (int m = w; m < N; m += kBwdWarps) {
+#pragma unroll
+    for (int i = 0; i < MAXI; ++i) {
+      const int n = lane + 32 * i;
+      if (n < N) {
+        float acc = 0.f, accd = 0.f;
+        for (int j = 0; j < d; ++j) {
+          acc = fmaf(Qs[n * dp + j], Ks[m * dp + j], acc);
+          accd = fmaf(Gs[n * dp + j], Vs[m * dp + j], accd);
+        }
+        const float pr = expf(acc * P.scale - Lse[n]);
+        bb[n] = pr;
+        ab[n] = pr * (accd - Dl[n]);
+      }
+    }
+    __syncwarp();
+    const int rm = m / ws, cm = m - rm * ws;
+    const int64_t tok = tok_of(m);
+    for (int j = lane; j < d; j += 32) {
+      float dk = 0.f, dvv = 0.f;
+      for (int n = 0; n < N; ++n) {
+        dk = fmaf(ab[n], Qs[n * dp + j], dk);
+        dvv = fmaf(bb[n], Gs[n * dp + j], dvv);
+      }
+      // conv-transpose: output position (rm - dr, cm - dc) read V at (rm, cm) through tap (dr, dc)
+#pragma unroll
+      for (int dr = -1; dr <= 1; ++dr)
+#pragma unroll
+        for (int dc = -1; dc <= 1; ++dc) {
+          const int rr = rm - dr, cc = cm - dc;
+          if (rr >= 0 && rr < hs && cc >= 0 && cc < ws)
+            dvv = fmaf(Wc[j * 9 + (dr + 1) * 3 + (dc + 1)], Gs[(rr * ws + cc) * dp + j], dvv);
+        }
+      stf(bg.dk + (int64_t)b * bg.dk_bs + tok * bg.dk_ts + ch0 + j, dk * P.scale);
+      stf(bg.dv + (int64_t)b * bg.dv_bs + tok * bg.dv_ts + ch0 + j, dvv);
+    }
+    __syncwarp();
+  }
+  // ---- LePE parameter gradients ----
+  for (int jj = 0; jj < d; jj += 32) {
+    const int j = jj + lane;
+    float acc[10];
+#pragma unroll
+    for (int t = 0; t < 10; ++t) acc[t] = 0.f;
+    if (j < d) {
+      for (int n = w; n < N; n += kBwdWarps) {
+        const int r = n / ws, c = n - r * ws;
+        const float g = Gs[n * dp + j];
+        acc[9] += g;
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+          const int rr = r + t / 3 - 1, cc = c + t % 3 - 1;
+          if (rr >= 0 && rr < hs && cc >= 0 && cc < ws) acc[t] = fmaf(g, Vs[(rr * ws + cc) * dp + j], acc[t]);
+        }
+      }
+#pragma unroll
+      for (int t = 0; t < 10; ++t) Part[(w * d + j) * 10 + t] = acc[t];
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < d * 10; i += kBwdWarps * 32) {
+    float s = 0.f;
+    for (int ww = 0; ww < kBwdWarps; ++ww) s += Part[ww * d * 10 + i];
+    const int j = i / 10, t = i - j * 10;
+    if (t < 9) atomicAdd(bg.dcw + (int64_t)(ch0 + j) * 9 + t, s);
+    else atomicAdd(bg.dcb + ch0 + j, s);
+  }
+}
+
+template <typename T>
+int launch_bwd(const cswin_lepe_branch_grad_t* gs, int nb, int B, int reso, float scale, cudaStream_t stream) {
+  cswin_lepe_branch_t fwd[2] = {};
+  for (int i = 0; i < nb; ++i) {
+    fwd[i] = gs[i].fwd;
+    if (fwd[i].out == nullptr) fwd[i].out = const_cast<void*>(gs[i].dout);          // `out` itself is not needed
+  }
+  AttnParams<T> F;
+  int total, max_n, max_d;
+  int rc = fill_params(F, fwd, nb, B, reso, scale, &total, &max_n, &max_d);
+  if (rc) return rc;
+  AttnGradParams<T> P;
+  P.nb = nb; P.B = B; P.reso = reso; P.scale = scale;
+  for (int i = 0; i < nb; ++i) {
+    const cswin_lepe_branch_grad_t& s = gs[i];
+    CSWIN_REQUIRE(s.dout && s.dq && s.dk && s.dv && s.dconv_w && s.dconv_b, CSWIN_ERR_INVALID, "lepe_attention_bwd: null pointer in branch %d", i);
+    BranchGradDev<T>& d = P.br[i];
+    d.f = F.br[i];
+    d.g = (const T*)s.dout; d.g_bs = s.do_bs; d.g_ts = s.do_ts;
+    d.dq = (T*)s.dq; d.dk = (T*)s.dk; d.dv = (T*)s.dv;
+    d.dq_bs = s.dq_bs; d.dq_ts = s.dq_ts; d.dk_bs = s.dk_bs; d.dk_ts = s.dk_ts; d.dv_bs = s.dv_bs; d.dv_ts = s.dv_ts;
+    d.dcw = s.dconv_w; d.dcb = s.dconv_b;
+  }
+  if (nb == 1) P.br[1] = P.br[0];
+  CSWIN_REQUIRE(max_d <= 128, CSWIN_ERR_UNSUPPORTED, "lepe_attention_bwd: head_dim %d > 128 not supported", max_d);
+  const int dp = max_d | 1;
+  const size_t smem = sizeof(float) * ((size_t)4 * max_n * dp + 2 * max_n + (size_t)2 * kBwdWarps * max_n + max_d * 9 +
+                                       (size_t)kBwdWarps * max_d * 10);
+  CSWIN_REQUIRE(max_n <= 512 && smem <= 227 * 1024, CSWIN_ERR_UNSUPPORTED,
+                "lepe_attention_bwd: window %d x head_dim %d needs %zu B smem (limit 227 KB)", max_n, max_d, smem);
+  if (total == 0) return CSWIN_OK;
+  auto kern = (max_n <= 256) ? lepe_attn_bwd_simt_kernel<T, 8> : lepe_attn_bwd_simt_kernel<T, 16>;
+  if (smem > 48 * 1024) CSWIN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<total, kBwdWarps * 32, smem, stream>>>(P);
+  CSWIN_LAUNCH_CHECK();
+  return CSWIN_OK;
+}
+
 }  // namespace
 
 int lepe_attention_fwd_simt(const cswin_lepe_branch_t* br, int nb, int B, int reso, float scale, int dtype, cudaStream_t s) {
@@ -176,4 +395,11 @@ int lepe_attention_fwd_simt(const cswin_lepe_branch_t* br, int nb, int B, int re
   return launch_fwd<__nv_bfloat16>(br, nb, B, reso, scale, s);
 }
 
+}  // namespace cswin
+
+namespace cswin {
+int lepe_attention_bwd_simt(const cswin_lepe_branch_grad_t* br, int nb, int B, int reso, float scale, int dtype, cudaStream_t s) {
+  if (dtype == CSWIN_F32) return launch_bwd<float>(br, nb, B, reso, scale, s);
+  return launch_bwd<__nv_bfloat16>(br, nb, B, reso, scale, s);
+}
 }  // namespace cswin

@@ -372,9 +372,4 @@ int lepe_attention_fwd_tc(const cswin_lepe_branch_t* brs, int nb, int B, int res
   return CSWIN_OK;
 }
 
-int lepe_attention_bwd_simt(const cswin_lepe_branch_grad_t*, int, int, int, float, int, cudaStream_t) {
-  set_error("lepe_attention_bwd: not implemented yet");
-  return CSWIN_ERR_UNSUPPORTED;
-}
-
 }  // namespace cswin

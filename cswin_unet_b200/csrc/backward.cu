@@ -1,0 +1,370 @@
+// backward.cu — backward kernels of the hot path other than attention (fp32 arithmetic, fp32 or bf16 storage).
+// The reference has no backward source: these are the autograd derivatives of networks/cswin_unet.py:160-181 (block),
+// :211-220 (Merge_Block), :232-269 / :282-319 (CARAFE) — checked against torch.autograd on the CPU oracle.
+//
+//   act_bwd              dZ = dOut * sample_scale * act'(Z)              (GELU(erf) derivative; DropPath scale)
+//   linear_wgrad         dW[N,K] += dZ^T A,  db[N] += colsum(dZ)         (fp32 accumulation into fp32 gradients)
+//   (linear dgrad = cswin_linear_fwd with the transposed weight: dA = dZ W)
+//   layernorm_bwd        dx, d gamma, d beta from saved mean / rstd
+//   col2im_tokens        adjoint of im2col_tokens (gather form, no atomics)
+//   carafe_reassemble_bwd  d enc (through the 9-tap softmax), d z, d bias
+#include "common.cuh"
+
+namespace cswin {
+namespace {
+
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) act_bwd_kernel(const T* __restrict__ dout, int64_t ldd, const T* __restrict__ z,
+                                                       int64_t ldz, const float* __restrict__ sscale, int rps,
+                                                       T* __restrict__ dz, int64_t ldo, int64_t M, int N, int act) {
+  const int64_t total = M * N;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t m = i / N;
+    const int n = (int)(i - m * N);
+    float g = ldf(dout + m * ldd + n);
+    if (sscale != nullptr) g *= sscale[m / rps];
+    if (act == 1) {
+      const float x = ldf(z + m * ldz + n);
+      const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+      const float pdf = 0.39894228040143267794f * expf(-0.5f * x * x);
+      g *= cdf + x * pdf;
+    }
+    stf(dz + m * ldo + n, g);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) act_fwd_kernel(const T* __restrict__ z, int64_t ldz, T* __restrict__ out, int64_t ldo,
+                                                       int64_t M, int N, int act) {
+  const int64_t total = M * N;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t m = i / N;
+    const int n = (int)(i - m * N);
+    const float x = ldf(z + m * ldz + n);
+    stf(out + m * ldo + n, act == 1 ? gelu_erf(x) : x);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// dW[n,k] += sum_m dZ[m,n] A[m,k] ; 64x64 (n,k) tile per CTA, M split over gridDim.z, fp32 atomics at the end.
+constexpr int WT = 64, WM = 16;
+template <typename T>
+__global__ void __launch_bounds__(256) linear_wgrad_kernel(const T* __restrict__ dz, int64_t ldz, const T* __restrict__ a,
+                                                            int64_t lda, float* __restrict__ dw, int64_t ldw,
+                                                            float* __restrict__ db, int64_t M, int N, int K, int64_t mchunk) {
+  __shared__ float Zs[WM][WT + 4];
+  __shared__ float As[WM][WT + 4];
+  const int n0 = blockIdx.x * WT, k0 = blockIdx.y * WT;
+  const int64_t mbeg = (int64_t)blockIdx.z * mchunk;
+  const int64_t mend = mbeg + mchunk < M ? mbeg + mchunk : M;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  float bsum[4] = {0.f, 0.f, 0.f, 0.f};
+  const int lr = tid >> 4;          // 0..15 row of the m-chunk
+  const int lc = (tid & 15) * 4;    // 0..60 first of 4 columns
+  for (int64_t m0 = mbeg; m0 < mend; m0 += WM) {
+    const int64_t m = m0 + lr;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int n = n0 + lc + e, k = k0 + lc + e;
+      Zs[lr][lc + e] = (m < mend && n < N) ? ldf(dz + m * ldz + n) : 0.f;
+      As[lr][lc + e] = (m < mend && k < K) ? ldf(a + m * lda + k) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int mm = 0; mm < WM; ++mm) {
+      const float4 zv = *reinterpret_cast<const float4*>(&Zs[mm][ty * 4]);
+      const float4 av = *reinterpret_cast<const float4*>(&As[mm][tx * 4]);
+      const float z4[4] = {zv.x, zv.y, zv.z, zv.w}, a4[4] = {av.x, av.y, av.z, av.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        bsum[i] += z4[i];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(z4[i], a4[j], acc[i][j]);
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int n = n0 + ty * 4 + i;
+    if (n >= N) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = k0 + tx * 4 + j;
+      if (k < K) atomicAdd(dw + (int64_t)n * ldw + k, acc[i][j]);
+    }
+    if (db != nullptr && blockIdx.y == 0 && tx == 0) atomicAdd(db + n, bsum[i]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T, int VPL>
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ dy,
+                                                             int64_t ldy, const T* __restrict__ gamma,
+                                                             const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                             T* __restrict__ dx, int64_t ldo, float* __restrict__ dgamma,
+                                                             float* __restrict__ dbeta, int64_t M, int C) {
+  __shared__ float red[8][32 * VPL * 2];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  float dg[VPL], dbt[VPL], gm[VPL];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) { dg[i] = 0.f; dbt[i] = 0.f; const int c = lane + 32 * i; gm[i] = c < C ? ldf(gamma + c) : 0.f; }
+  for (int64_t row = (int64_t)blockIdx.x * 8 + w; row < M; row += (int64_t)gridDim.x * 8) {
+    const float mu = mean[row], rs = rstd[row];
+    float xh[VPL], g[VPL];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int c = lane + 32 * i;
+      xh[i] = 0.f; g[i] = 0.f;
+      if (c < C) {
+        const float d = ldf(dy + row * ldy + c);
+        xh[i] = (ldf(x + row * ldx + c) - mu) * rs;
+        g[i] = d * gm[i];
+        dg[i] = fmaf(d, xh[i], dg[i]);
+        dbt[i] += d;
+        s1 += g[i];
+        s2 = fmaf(g[i], xh[i], s2);
+      }
+    }
+    s1 = warp_sum(s1) / (float)C;
+    s2 = warp_sum(s2) / (float)C;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int c = lane + 32 * i;
+      if (c < C) stf(dx + row * ldo + c, rs * (g[i] - s1 - xh[i] * s2));
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) { red[w][(lane + 32 * i) * 2] = dg[i]; red[w][(lane + 32 * i) * 2 + 1] = dbt[i]; }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int ww = 0; ww < 8; ++ww) { a += red[ww][c * 2]; b += red[ww][c * 2 + 1]; }
+    atomicAdd(dgamma + c, a);
+    atomicAdd(dbeta + c, b);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// dx[b, iy, ix, c] = sum over taps (ky,kx) with (iy + pad - ky) % stride == 0 ... of dcol[(b,oy,ox), (ky*KW+kx)*C + c]
+template <typename T>
+__global__ void __launch_bounds__(256) col2im_tokens_kernel(const T* __restrict__ dcol, int64_t ldcol, T* __restrict__ dx,
+                                                             int64_t x_bs, int64_t x_ts, int B, int H, int W, int C, int KH,
+                                                             int KW, int stride, int pad, int Ho, int Wo) {
+  const int64_t total = (int64_t)B * H * W * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    int64_t r = i / C;
+    const int ix = (int)(r % W); r /= W;
+    const int iy = (int)(r % H);
+    const int b = (int)(r / H);
+    float acc = 0.f;
+    for (int ky = 0; ky < KH; ++ky) {
+      const int ty = iy + pad - ky;
+      if (ty < 0 || ty % stride) continue;
+      const int oy = ty / stride;
+      if (oy >= Ho) continue;
+      for (int kx = 0; kx < KW; ++kx) {
+        const int tx = ix + pad - kx;
+        if (tx < 0 || tx % stride) continue;
+        const int ox = tx / stride;
+        if (ox >= Wo) continue;
+        acc += ldf(dcol + ((int64_t)(b * Ho + oy) * Wo + ox) * ldcol + (int64_t)(ky * KW + kx) * C + c);
+      }
+    }
+    stf(dx + (int64_t)b * x_bs + ((int64_t)iy * W + ix) * x_ts + c, acc);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// CARAFE re-assembly backward.  dy element (b, oy, ox, c) lives at dy + b*sb + oy*sy + ox*sx + c*sc (token-major or NCHW).
+// Kernel A (one warp per low-res pixel): kappa (recomputed), d kappa[ae][t] = <dy[ae], z^[t]>, d enc through the softmax,
+//          kappa saved to `kws` (pix, s2, 9) for kernel B, d bias partial sums.
+// Kernel B (one warp per low-res pixel p'): dz[p'] = sum_t sum_ae kappa[p'-off(t)][ae][t] * dy[p'-off(t), ae]  (gather).
+template <typename T, typename TG>
+__global__ void __launch_bounds__(256) carafe_bwd_a_kernel(const T* __restrict__ enc, int64_t ldenc, const T* __restrict__ z,
+                                                            int64_t ldz, const TG* __restrict__ dy, int64_t sb, int64_t sy,
+                                                            int64_t sx, int64_t sc, T* __restrict__ denc, int64_t lddenc,
+                                                            float* __restrict__ kws, float* __restrict__ dbias, int64_t npix,
+                                                            int H, int W, int C, int up) {
+  extern __shared__ float sdb[];                 // [C] per-CTA d bias
+  const int lane = threadIdx.x & 31;
+  const int s2 = up * up;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) sdb[c] = 0.f;
+  __syncthreads();
+  const int64_t pix = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (pix < npix) {
+    const int x0 = (int)(pix % W), y0 = (int)((pix / W) % H);
+    const int64_t b = pix / ((int64_t)W * H);
+    for (int ae = 0; ae < s2; ++ae) {
+      const int oy = y0 * up + ae / up, ox = x0 * up + ae % up;
+      float k[9];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int t = 0; t < 9; ++t) { k[t] = ldf(enc + pix * ldenc + t * s2 + ae); mx = fmaxf(mx, k[t]); }
+      float sum = 0.f;
+#pragma unroll
+      for (int t = 0; t < 9; ++t) { k[t] = expf(k[t] - mx); sum += k[t]; }
+      const float inv = 1.0f / sum;
+      float dk[9];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) { k[t] *= inv; dk[t] = 0.f; }
+      for (int c = lane; c < C; c += 32) {
+        const float g = ldf(dy + b * sb + oy * sy + ox * sx + c * sc);
+        atomicAdd(&sdb[c], g);
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+          const int yy = y0 + t / 3 - 1, xx = x0 + t % 3 - 1;
+          if (yy >= 0 && yy < H && xx >= 0 && xx < W) dk[t] = fmaf(g, ldf(z + ((b * H + yy) * W + xx) * ldz + c), dk[t]);
+        }
+      }
+      float dot = 0.f;
+#pragma unroll
+      for (int t = 0; t < 9; ++t) { dk[t] = warp_sum(dk[t]); dot = fmaf(k[t], dk[t], dot); }
+      if (lane < 9) {
+        float kv = 0.f, dv = 0.f;
+#pragma unroll
+        for (int t = 0; t < 9; ++t) if (t == lane) { kv = k[t]; dv = dk[t]; }
+        stf(denc + pix * lddenc + lane * s2 + ae, kv * (dv - dot));
+        kws[(pix * s2 + ae) * 9 + lane] = kv;
+      }
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) if (sdb[c] != 0.f) atomicAdd(dbias + c, sdb[c]);
+}
+
+template <typename T, typename TG>
+__global__ void __launch_bounds__(256) carafe_bwd_b_kernel(const TG* __restrict__ dy, int64_t sb, int64_t sy, int64_t sx,
+                                                            int64_t sc, const float* __restrict__ kws, T* __restrict__ dz,
+                                                            int64_t lddz, int64_t npix, int H, int W, int C, int up) {
+  const int lane = threadIdx.x & 31;
+  const int s2 = up * up;
+  const int64_t pix = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (pix >= npix) return;
+  const int x0 = (int)(pix % W), y0 = (int)((pix / W) % H);
+  const int64_t b = pix / ((int64_t)W * H);
+  for (int c = lane; c < C; c += 32) {
+    float acc = 0.f;
+    for (int t = 0; t < 9; ++t) {
+      const int py = y0 - (t / 3 - 1), px = x0 - (t % 3 - 1);          // the pixel whose tap t reads (y0, x0)
+      if (py < 0 || py >= H || px < 0 || px >= W) continue;
+      const int64_t pp = (b * H + py) * W + px;
+      for (int ae = 0; ae < s2; ++ae) {
+        const int oy = py * up + ae / up, ox = px * up + ae % up;
+        acc = fmaf(kws[(pp * s2 + ae) * 9 + t], ldf(dy + b * sb + oy * sy + ox * sx + c * sc), acc);
+      }
+    }
+    stf(dz + pix * lddz + c, acc);
+  }
+}
+
+unsigned grid_for(int64_t total, int per_cta) {
+  return (unsigned)std::min<int64_t>(ceil_div64(total, per_cta), (int64_t)sm_count() * 32);
+}
+
+}  // namespace
+
+int act_fwd(const void* z, int64_t ldz, void* out, int64_t ldo, int64_t M, int N, int act, int dtype, cudaStream_t s) {
+  CSWIN_REQUIRE(z && out, CSWIN_ERR_INVALID, "act_fwd: null pointer");
+  if (M * N == 0) return CSWIN_OK;
+  const unsigned grid = grid_for(M * N, 256);
+  if (dtype == CSWIN_F32) act_fwd_kernel<float><<<grid, 256, 0, s>>>((const float*)z, ldz, (float*)out, ldo, M, N, act);
+  else act_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)z, ldz, (__nv_bfloat16*)out, ldo, M, N, act);
+  CSWIN_LAUNCH_CHECK();
+  return CSWIN_OK;
+}
+
+int act_bwd(const void* dout, int64_t ldd, const void* z, int64_t ldz, const float* sscale, int rps, void* dz, int64_t ldo,
+            int64_t M, int N, int act, int dtype, cudaStream_t s) {
+  CSWIN_REQUIRE(dout && dz && (act == 0 || z), CSWIN_ERR_INVALID, "act_bwd: null pointer");
+  CSWIN_REQUIRE(!sscale || rps > 0, CSWIN_ERR_INVALID, "act_bwd: rows_per_sample must be > 0");
+  if (M * N == 0) return CSWIN_OK;
+  const unsigned grid = grid_for(M * N, 256);
+  if (dtype == CSWIN_F32) act_bwd_kernel<float><<<grid, 256, 0, s>>>((const float*)dout, ldd, (const float*)z, ldz, sscale, rps, (float*)dz, ldo, M, N, act);
+  else act_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)dout, ldd, (const __nv_bfloat16*)z, ldz, sscale, rps, (__nv_bfloat16*)dz, ldo, M, N, act);
+  CSWIN_LAUNCH_CHECK();
+  return CSWIN_OK;
+}
+
+int linear_wgrad(const void* dz, int64_t ldz, const void* a, int64_t lda, float* dw, int64_t ldw, float* db, int64_t M,
+                 int N, int K, int dtype, cudaStream_t s) {
+  CSWIN_REQUIRE(dz && a && dw, CSWIN_ERR_INVALID, "linear_wgrad: null pointer");
+  if (M == 0 || N == 0 || K == 0) return CSWIN_OK;
+  const int tiles = ((N + WT - 1) / WT) * ((K + WT - 1) / WT);
+  int split = (int)std::min<int64_t>((int64_t)std::max(1, 4 * sm_count() / tiles), ceil_div64(M, 256));
+  if (split < 1) split = 1;
+  if (split > 65535) split = 65535;
+  int64_t mchunk = ceil_div64(ceil_div64(M, split), WM) * WM;
+  split = (int)ceil_div64(M, mchunk);
+  dim3 grid((N + WT - 1) / WT, (K + WT - 1) / WT, split);
+  if (dtype == CSWIN_F32) linear_wgrad_kernel<float><<<grid, 256, 0, s>>>((const float*)dz, ldz, (const float*)a, lda, dw, ldw, db, M, N, K, mchunk);
+  else linear_wgrad_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)dz, ldz, (const __nv_bfloat16*)a, lda, dw, ldw, db, M, N, K, mchunk);
+  CSWIN_LAUNCH_CHECK();
+  return CSWIN_OK;
+}
+
+int layernorm_bwd(const void* x, int64_t ldx, const void* dy, int64_t ldy, const void* gamma, const float* mean,
+                  const float* rstd, void* dx, int64_t ldo, float* dgamma, float* dbeta, int64_t M, int C, int dtype,
+                  cudaStream_t s) {
+  CSWIN_REQUIRE(x && dy && gamma && mean && rstd && dx && dgamma && dbeta, CSWIN_ERR_INVALID, "layernorm_bwd: null pointer");
+  CSWIN_REQUIRE(C > 0 && C <= 512, CSWIN_ERR_UNSUPPORTED, "layernorm_bwd: C=%d outside (0, 512]", C);
+  if (M == 0) return CSWIN_OK;
+  const unsigned grid = (unsigned)std::min<int64_t>(ceil_div64(M, 8), (int64_t)sm_count() * 4);
+#define LNB(T, V) layernorm_bwd_kernel<T, V><<<grid, 256, 0, s>>>((const T*)x, ldx, (const T*)dy, ldy, (const T*)gamma, mean, rstd, (T*)dx, ldo, dgamma, dbeta, M, C)
+  if (dtype == CSWIN_F32) { if (C <= 128) LNB(float, 4); else LNB(float, 16); }
+  else { if (C <= 128) LNB(__nv_bfloat16, 4); else LNB(__nv_bfloat16, 16); }
+#undef LNB
+  CSWIN_LAUNCH_CHECK();
+  return CSWIN_OK;
+}
+
+int col2im_tokens(const void* dcol, int64_t ldcol, void* dx, int64_t x_bs, int64_t x_ts, int B, int H, int W, int C, int KH,
+                  int KW, int stride, int pad, int dtype, cudaStream_t s) {
+  CSWIN_REQUIRE(dcol && dx, CSWIN_ERR_INVALID, "col2im_tokens: null pointer");
+  const int Ho = (H + 2 * pad - KH) / stride + 1, Wo = (W + 2 * pad - KW) / stride + 1;
+  const int64_t total = (int64_t)B * H * W * C;
+  if (total == 0) return CSWIN_OK;
+  const unsigned grid = grid_for(total, 256);
+  if (dtype == CSWIN_F32) col2im_tokens_kernel<float><<<grid, 256, 0, s>>>((const float*)dcol, ldcol, (float*)dx, x_bs, x_ts, B, H, W, C, KH, KW, stride, pad, Ho, Wo);
+  else col2im_tokens_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)dcol, ldcol, (__nv_bfloat16*)dx, x_bs, x_ts, B, H, W, C, KH, KW, stride, pad, Ho, Wo);
+  CSWIN_LAUNCH_CHECK();
+  return CSWIN_OK;
+}
+
+int carafe_reassemble_bwd(const void* enc, int64_t ldenc, const void* z, int64_t ldz, const void* dy, int dy_is_f32,
+                          int64_t sb, int64_t sy, int64_t sx, int64_t sc, void* denc, int64_t lddenc, void* dz, int64_t lddz,
+                          float* dbias, float* kws, int B, int H, int W, int C, int up, int dtype, cudaStream_t s) {
+  CSWIN_REQUIRE(enc && z && dy && denc && dz && dbias && kws, CSWIN_ERR_INVALID, "carafe_reassemble_bwd: null pointer");
+  CSWIN_REQUIRE(up >= 1 && C > 0 && C <= 4096, CSWIN_ERR_UNSUPPORTED, "carafe_reassemble_bwd: bad up / C");
+  const int64_t npix = (int64_t)B * H * W;
+  if (npix == 0) return CSWIN_OK;
+  const unsigned grid = (unsigned)ceil_div64(npix, 8);
+  const size_t smem = sizeof(float) * C;
+  if (dtype == CSWIN_F32) {
+    CSWIN_REQUIRE(dy_is_f32, CSWIN_ERR_INVALID, "carafe_reassemble_bwd: fp32 path needs fp32 dy");
+    carafe_bwd_a_kernel<float, float><<<grid, 256, smem, s>>>((const float*)enc, ldenc, (const float*)z, ldz, (const float*)dy, sb, sy, sx, sc, (float*)denc, lddenc, kws, dbias, npix, H, W, C, up);
+    CSWIN_LAUNCH_CHECK();
+    carafe_bwd_b_kernel<float, float><<<grid, 256, 0, s>>>((const float*)dy, sb, sy, sx, sc, kws, (float*)dz, lddz, npix, H, W, C, up);
+  } else if (dy_is_f32) {
+    carafe_bwd_a_kernel<__nv_bfloat16, float><<<grid, 256, smem, s>>>((const __nv_bfloat16*)enc, ldenc, (const __nv_bfloat16*)z, ldz, (const float*)dy, sb, sy, sx, sc, (__nv_bfloat16*)denc, lddenc, kws, dbias, npix, H, W, C, up);
+    CSWIN_LAUNCH_CHECK();
+    carafe_bwd_b_kernel<__nv_bfloat16, float><<<grid, 256, 0, s>>>((const float*)dy, sb, sy, sx, sc, kws, (__nv_bfloat16*)dz, lddz, npix, H, W, C, up);
+  } else {
+    carafe_bwd_a_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, smem, s>>>((const __nv_bfloat16*)enc, ldenc, (const __nv_bfloat16*)z, ldz, (const __nv_bfloat16*)dy, sb, sy, sx, sc, (__nv_bfloat16*)denc, lddenc, kws, dbias, npix, H, W, C, up);
+    CSWIN_LAUNCH_CHECK();
+    carafe_bwd_b_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)dy, sb, sy, sx, sc, kws, (__nv_bfloat16*)dz, lddz, npix, H, W, C, up);
+  }
+  CSWIN_LAUNCH_CHECK();
+  return CSWIN_OK;
+}
+
+}  // namespace cswin

@@ -107,6 +107,19 @@ int carafe_reassemble_fwd(const void* enc, int64_t ldenc, const void* z, int64_t
                           int64_t ldy, int nchw_out, int y_is_f32, int B, int H, int W, int C, int up, int dtype,
                           cudaStream_t s);
 
+int act_fwd(const void* z, int64_t ldz, void* out, int64_t ldo, int64_t M, int N, int act, int dtype, cudaStream_t s);
+int act_bwd(const void* dout, int64_t ldd, const void* z, int64_t ldz, const float* sscale, int rps, void* dz, int64_t ldo,
+            int64_t M, int N, int act, int dtype, cudaStream_t s);
+int linear_wgrad(const void* dz, int64_t ldz, const void* a, int64_t lda, float* dw, int64_t ldw, float* db, int64_t M,
+                 int N, int K, int dtype, cudaStream_t s);
+int layernorm_bwd(const void* x, int64_t ldx, const void* dy, int64_t ldy, const void* gamma, const float* mean,
+                  const float* rstd, void* dx, int64_t ldo, float* dgamma, float* dbeta, int64_t M, int C, int dtype,
+                  cudaStream_t s);
+int col2im_tokens(const void* dcol, int64_t ldcol, void* dx, int64_t x_bs, int64_t x_ts, int B, int H, int W, int C, int KH,
+                  int KW, int stride, int pad, int dtype, cudaStream_t s);
+int carafe_reassemble_bwd(const void* enc, int64_t ldenc, const void* z, int64_t ldz, const void* dy, int dy_is_f32,
+                          int64_t sb, int64_t sy, int64_t sx, int64_t sc, void* denc, int64_t lddenc, void* dz, int64_t lddz,
+                          float* dbias, float* kws, int B, int H, int W, int C, int up, int dtype, cudaStream_t s);
 int carafe_head_fwd(const void* enc, int64_t ldenc, const void* z, int64_t ldz, const void* bias, void* logits,
                     int logits_is_f32, uint8_t* labels, int B, int H, int W, int C, int up, int dtype, cudaStream_t s);
 

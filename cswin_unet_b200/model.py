@@ -20,6 +20,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
+from . import autograd as ag
 from . import ops
 from .modules import CARAFE, CARAFE4, CSWinBlock, Merge_Block, _Native, _no_autograd
 
@@ -95,17 +96,25 @@ class CSWinTransformer(_Native):
         B = x.shape[0]
         K = conv.weight[0].numel()
         Kp = (K + 7) // 8 * 8                               # row pitch multiple of 16 B for the bf16 TMA path
+        col = ops.im2col_nchw(x, 7, 7, 4, 2, Kp, dt)                      # the network input needs no gradient
+        if ag.needs_grad(*self.stage1_conv_embed.parameters()):
+            wk = torch.nn.functional.pad(conv.weight.reshape(conv.weight.shape[0], -1), (0, Kp - K))
+            y = ag.LayerNormFn.apply(ag.linear(col, wk, conv.bias), ln.weight, ln.bias, ln.eps)
+            return y.view(B, -1, y.shape[-1])
         wk = self._w("stem.w", conv.weight, dt, lambda t: torch.nn.functional.pad(t.reshape(t.shape[0], -1), (0, Kp - K)))
-        col = ops.im2col_nchw(x, 7, 7, 4, 2, Kp, dt)
         y = ops.linear(col, wk, self._w("stem.b", conv.bias, dt))
         y = ops.layernorm(y, self._w("stem.n.w", ln.weight, dt), self._w("stem.n.b", ln.bias, dt), ln.eps)
         return y.view(B, -1, y.shape[-1])
 
     def _skip_linear(self, lin: nn.Linear, skip: Tensor, x: Tensor, key: str) -> Tensor:
+        if ag.needs_grad(skip, x, lin.weight):
+            return ag.linear(skip, lin.weight, lin.bias, a2=x)
         dt = x.dtype
         return ops.linear(skip, self._w(key + ".w", lin.weight, dt), self._w(key + ".b", lin.bias, dt), a2=x)
 
     def _ln(self, ln: nn.LayerNorm, x: Tensor, key: str) -> Tensor:
+        if ag.needs_grad(x, ln.weight):
+            return ag.LayerNormFn.apply(x, ln.weight, ln.bias, ln.eps)
         dt = x.dtype
         return ops.layernorm(x, self._w(key + ".w", ln.weight, dt), self._w(key + ".b", ln.bias, dt), ln.eps)
 
@@ -151,6 +160,13 @@ class CSWinTransformer(_Native):
         B, L, Cn = x.shape
         H = W = int(round(L ** 0.5))
         up = self.upsample1
+        if ag.needs_grad(x, self.output.weight, *up.parameters()):
+            # training: the reference's unfolded structure (CARAFE4 with its own `out` conv, then the `output` conv) so that
+            # every parameter receives its gradient from a native kernel; logits come back token-major and are viewed NCHW
+            y = up(x)                                                           # (B, 16 L, 64)
+            lg = ag.linear(y, self.output.weight.reshape(self.output.weight.shape[0], -1), None)
+            lg = lg.view(B, H * up.up_factor, W * up.up_factor, -1).permute(0, 3, 1, 2)
+            return lg.to(logits_dtype) if logits_dtype is not None else lg
         dt = x.dtype
         enc = up._kernel_logits(x, H, W)
         wo = self.output.weight
@@ -175,7 +191,6 @@ class CSWinTransformer(_Native):
         return logits
 
     def forward(self, x: Tensor) -> Tensor:
-        _no_autograd(x, self.output.weight)
         x = self.forward_features(x)
         x = self.forward_up_features(x)
         return self.up_x4(x)

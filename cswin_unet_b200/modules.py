@@ -20,6 +20,7 @@ from typing import Callable, Dict, Optional, Tuple
 import torch
 import torch.nn as nn
 
+from . import autograd as ag
 from . import ops
 
 Tensor = torch.Tensor
@@ -190,7 +191,10 @@ class LePEAttention(_Native):
         q, k, v = qkv[0], qkv[1], qkv[2]
         B, L, Cn = q.shape
         self._check(L)
-        _no_autograd(qkv, self.get_v.weight)
+        if ag.needs_grad(qkv, self.get_v.weight, self.get_v.bias):
+            packed = torch.cat([q, k, v], dim=-1)                       # (B, L, 3 C_b); torch.cat is the tape's job here
+            meta = dict(reso=self.resolution, scale=float(self.scale), heads=[self.num_heads], win=[(self.H_sp, self.W_sp)])
+            return ag.LepeAttentionFn.apply(packed, self.get_v.weight, self.get_v.bias, None, None, meta)
         out = torch.empty((B, L, Cn), dtype=q.dtype, device=q.device)
         ops.lepe_attention_fwd([self.branch_desc(q, k, v, out)], B, self.resolution, float(self.scale), q.dtype)
         return out
@@ -212,7 +216,8 @@ class Mlp(nn.Module):
         self.drop = nn.Dropout(drop)
 
     def forward(self, x: Tensor) -> Tensor:
-        _no_autograd(x, self.fc1.weight)
+        if ag.needs_grad(x, self.fc1.weight, self.fc2.weight):
+            return ag.linear(ag.GeluFn.apply(ag.linear(x, self.fc1.weight, self.fc1.bias)), self.fc2.weight, self.fc2.bias)
         dt = x.dtype
         h = ops.linear(x, self.fc1.weight.detach().to(dt), self.fc1.bias.detach().to(dt), act=1)
         return ops.linear(h, self.fc2.weight.detach().to(dt), self.fc2.bias.detach().to(dt))
@@ -265,7 +270,8 @@ class CSWinBlock(_Native):
         H = W = self.patches_resolution
         B, L, Cn = x.shape
         assert L == H * W, "flatten img_tokens has wrong size"
-        _no_autograd(x, self.qkv.weight)
+        if ag.needs_grad(x, *self.parameters()):
+            return self._forward_train(x)
         dt = x.dtype
         w = self._w
         qkv = ops.linear(x, w("qkv.w", self.qkv.weight, dt),
@@ -294,6 +300,26 @@ class CSWinBlock(_Native):
                           sample_scale=self._sample_scale(x), rows_per_sample=L)
 
 
+    def _forward_train(self, x: Tensor) -> Tensor:
+        """Same graph on the autograd tape: every node is a native forward / backward kernel pair (autograd.py)."""
+        H = self.patches_resolution
+        B, L, Cn = x.shape
+        for a in self.attns:
+            a._check(L)
+        u = ag.LayerNormFn.apply(x, self.norm1.weight, self.norm1.bias, self.norm1.eps)
+        qkv = ag.linear(u, self.qkv.weight, self.qkv.bias)
+        meta = dict(reso=H, scale=float(self.attns[0].scale), heads=[a.num_heads for a in self.attns],
+                    win=[(a.H_sp, a.W_sp) for a in self.attns])
+        a0 = self.attns[0]
+        a1 = self.attns[1] if self.branch_num == 2 else None
+        att = ag.LepeAttentionFn.apply(qkv, a0.get_v.weight, a0.get_v.bias, a1.get_v.weight if a1 else None,
+                                       a1.get_v.bias if a1 else None, meta)
+        x1 = ag.linear(att, self.proj.weight, self.proj.bias, residual=x, sample_scale=self._sample_scale(x), rps=L)
+        u2 = ag.LayerNormFn.apply(x1, self.norm2.weight, self.norm2.bias, self.norm2.eps)
+        hid = ag.GeluFn.apply(ag.linear(u2, self.mlp.fc1.weight, self.mlp.fc1.bias))
+        return ag.linear(hid, self.mlp.fc2.weight, self.mlp.fc2.bias, residual=x1, sample_scale=self._sample_scale(x), rps=L)
+
+
 # ------------------------------------------------------------------------------------------
 # Merge_Block / CARAFE / CARAFE4
 # ------------------------------------------------------------------------------------------
@@ -317,7 +343,11 @@ class Merge_Block(_Native):
     def forward(self, x: Tensor) -> Tensor:
         B, L, Cn = x.shape
         H = W = _side(L)
-        _no_autograd(x, self.conv.weight)
+        if ag.needs_grad(x, *self.parameters()):
+            wk = self.conv.weight.permute(0, 2, 3, 1).reshape(self.conv.weight.shape[0], -1)     # re-pack on the tape
+            y = ag.linear(ag.Im2colTokensFn.apply(x, H, W, 3, 3, 2, 1), wk, self.conv.bias)
+            y = ag.LayerNormFn.apply(y, self.norm.weight, self.norm.bias, self.norm.eps)
+            return y.view(B, ((H + 2 - 3) // 2 + 1) ** 2, -1)
         dt = x.dtype
         wk = self._w("conv.w", self.conv.weight, dt, lambda t: t.permute(0, 2, 3, 1).reshape(t.shape[0], -1))
         col = ops.im2col_tokens(x, H, W, 3, 3, 2, 1)
@@ -356,7 +386,13 @@ class CARAFE(_Native):
     def forward(self, x: Tensor) -> Tensor:
         B, L, Cn = x.shape
         H = W = _side(L)
-        _no_autograd(x, self.down.weight)
+        if ag.needs_grad(x, *self.parameters()):
+            rs = lambda t: t.reshape(t.shape[0], -1)
+            d = ag.linear(x, rs(self.down.weight), self.down.bias)
+            col = ag.Im2colTokensFn.apply(d, H, W, 3, 3, 1, 1)
+            enc = ag.linear(col, self.encoder.weight.permute(0, 2, 3, 1).reshape(self.encoder.weight.shape[0], -1), self.encoder.bias)
+            z = ag.linear(x, rs(self.out.weight), None)
+            return ag.CarafeReassembleFn.apply(enc, z.view(B * L, -1), self.out.bias, B, H, W, self.up_factor)
         dt = x.dtype
         enc = self._kernel_logits(x, H, W)
         z = ops.linear(x, self._w("out.w", self.out.weight, dt, lambda t: t.reshape(t.shape[0], -1)))   # no bias yet

@@ -233,3 +233,107 @@ def carafe_head(enc: Tensor, z: Tensor, bias: Tensor, B: int, H: int, W: int, up
                                       _ptr(logits), int(ld == torch.float32), _ptr(labels), B, H, W, Cn, up,
                                       _dtype_code(z), _stream()), "cswin_carafe_head_fwd")
     return logits, labels
+
+
+# ----------------------------------------------------------------------------------------------
+# backward ops (training step)
+# ----------------------------------------------------------------------------------------------
+def lepe_attention_bwd(branches: Sequence[dict], B: int, reso: int, scale: float, dtype: torch.dtype) -> None:
+    """branches: forward description + dout, dq, dk, dv (views with unit channel stride), dconv_w (C_b,9) / dconv_b (C_b) fp32."""
+    arr = (LepeBranchGrad * len(branches))()
+    keep = []
+    for i, b in enumerate(branches):
+        q, k, v = (_unit_channel_stride(b[n]) for n in ("q", "k", "v"))
+        cw, cb = b["conv_w"].contiguous(), b["conv_b"].contiguous()
+        dout = _unit_channel_stride(b["dout"])
+        _need_cuda(q, k, v, cw, cb, dout, b["dq"], b["dk"], b["dv"], b["dconv_w"], b["dconv_b"])
+        keep += [q, k, v, cw, cb, dout]
+        g = LepeBranchGrad()
+        g.fwd = _branch(q, k, v, dout, cw, cb, b["heads"], b["H_sp"], b["W_sp"], None)
+        g.dout, g.do_bs, g.do_ts = dout.data_ptr(), dout.stride(0), dout.stride(1)
+        for n in ("dq", "dk", "dv"):
+            t = b[n]
+            assert t.stride(-1) == 1
+            setattr(g, n, t.data_ptr()); setattr(g, n + "_bs", t.stride(0)); setattr(g, n + "_ts", t.stride(1))
+        assert b["dconv_w"].dtype == torch.float32 and b["dconv_b"].dtype == torch.float32
+        g.dconv_w, g.dconv_b = b["dconv_w"].data_ptr(), b["dconv_b"].data_ptr()
+        arr[i] = g
+    code = F32 if dtype == torch.float32 else BF16
+    check(lib().cswin_lepe_attention_bwd(arr, len(branches), B, reso, C.c_float(scale), code, _stream()),
+          "cswin_lepe_attention_bwd")
+
+
+def act_fwd(z: Tensor, act: int = 1) -> Tensor:
+    _need_cuda(z)
+    z2, M, ldz = _rows(z)
+    out = torch.empty(z.shape, dtype=z.dtype, device=z.device)
+    check(lib().cswin_act_fwd(z2.data_ptr(), ldz, out.data_ptr(), z.shape[-1], M, z.shape[-1], act, _dtype_code(z), _stream()),
+          "cswin_act_fwd")
+    return out
+
+
+def act_bwd(dout: Tensor, z: Optional[Tensor], sample_scale: Optional[Tensor], rows_per_sample: int, act: int) -> Tensor:
+    _need_cuda(dout, z, sample_scale)
+    d2, M, ldd = _rows(dout)
+    N = dout.shape[-1]
+    z2, ldz = (None, 0)
+    if z is not None:
+        z2, _, ldz = _rows(z)
+    dz = torch.empty(dout.shape, dtype=dout.dtype, device=dout.device)
+    check(lib().cswin_act_bwd(d2.data_ptr(), ldd, _ptr(z2), ldz, _ptr(sample_scale), rows_per_sample, dz.data_ptr(), N, M, N,
+                              act, _dtype_code(dout), _stream()), "cswin_act_bwd")
+    return dz
+
+
+def linear_wgrad(dz: Tensor, a: Tensor, dw: Tensor, db: Optional[Tensor]) -> None:
+    """dw (N, K) view of an fp32 buffer (unit column stride) += dz^T a ; db (N) fp32 += column sums of dz."""
+    _need_cuda(dz, a, dw, db)
+    d2, M, ldz = _rows(dz)
+    a2, Ma, lda = _rows(a)
+    assert Ma == M and dw.dtype == torch.float32 and dw.stride(1) == 1 and dz.dtype == a.dtype
+    check(lib().cswin_linear_wgrad(d2.data_ptr(), ldz, a2.data_ptr(), lda, dw.data_ptr(), dw.stride(0), _ptr(db), M,
+                                   dz.shape[-1], a.shape[-1], _dtype_code(dz), _stream()), "cswin_linear_wgrad")
+
+
+def layernorm_bwd(x: Tensor, dy: Tensor, gamma: Tensor, mean: Tensor, rstd: Tensor):
+    _need_cuda(x, dy, gamma, mean, rstd)
+    x2, M, ldx = _rows(x)
+    d2, _, ldy = _rows(dy)
+    Cn = x.shape[-1]
+    dx = torch.empty(x.shape, dtype=x.dtype, device=x.device)
+    dg = torch.zeros(Cn, dtype=torch.float32, device=x.device)
+    db = torch.zeros(Cn, dtype=torch.float32, device=x.device)
+    check(lib().cswin_layernorm_bwd(x2.data_ptr(), ldx, d2.data_ptr(), ldy, gamma.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                                    dx.data_ptr(), Cn, dg.data_ptr(), db.data_ptr(), M, Cn, _dtype_code(x), _stream()),
+          "cswin_layernorm_bwd")
+    return dx, dg, db
+
+
+def col2im_tokens(dcol: Tensor, B: int, H: int, W: int, Cn: int, KH: int, KW: int, stride: int, pad: int) -> Tensor:
+    _need_cuda(dcol)
+    dcol = dcol.contiguous()
+    dx = torch.empty((B, H * W, Cn), dtype=dcol.dtype, device=dcol.device)
+    check(lib().cswin_col2im_tokens(dcol.data_ptr(), dcol.stride(0), dx.data_ptr(), dx.stride(0), dx.stride(1), B, H, W, Cn,
+                                    KH, KW, stride, pad, _dtype_code(dcol), _stream()), "cswin_col2im_tokens")
+    return dx
+
+
+def carafe_reassemble_bwd(enc: Tensor, z: Tensor, dy: Tensor, B: int, H: int, W: int, up: int, nchw: bool = False):
+    """dy: (B, up^2 H W, C) token-major, or (B, C, up H, up W) if nchw.  Returns (d enc, d z, d bias fp32)."""
+    _need_cuda(enc, z, dy)
+    Cn = z.shape[-1]
+    dy = dy.contiguous()
+    Ho, Wo = H * up, W * up
+    if nchw:
+        sb, sy, sx, sc = Cn * Ho * Wo, Wo, 1, Ho * Wo
+    else:
+        sb, sy, sx, sc = Ho * Wo * Cn, Wo * Cn, Cn, 1
+    denc = torch.empty_like(enc)
+    dz = torch.empty_like(z)
+    dbias = torch.zeros(Cn, dtype=torch.float32, device=z.device)
+    kws = torch.empty(B * H * W * up * up * 9, dtype=torch.float32, device=z.device)
+    check(lib().cswin_carafe_reassemble_bwd(enc.data_ptr(), enc.stride(0), z.data_ptr(), z.stride(0), dy.data_ptr(),
+                                            int(dy.dtype == torch.float32), sb, sy, sx, sc, denc.data_ptr(), denc.stride(0),
+                                            dz.data_ptr(), dz.stride(0), dbias.data_ptr(), kws.data_ptr(), B, H, W, Cn, up,
+                                            _dtype_code(z), _stream()), "cswin_carafe_reassemble_bwd")
+    return denc, dz, dbias

@@ -169,6 +169,35 @@ int cswin_carafe_head_fwd(const void* enc, int64_t ldenc, const void* z, int64_t
                           int32_t logits_is_f32, uint8_t* labels, int32_t B, int32_t H, int32_t W, int32_t C, int32_t up,
                           int32_t dtype, cswin_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Backward kernels of the training step.  The reference has no backward source: these are the autograd derivatives of
+ * cswin_unet.py:160-181 (CSWinBlock: Linear / GELU / LayerNorm / residual / DropPath), :211-220 (Merge_Block conv as
+ * im2col) and :232-319 (CARAFE re-assembly), validated against torch.autograd on the oracle.  Parameter gradients are
+ * fp32 and ACCUMULATED into (the caller zeroes them); activation gradients use the compute dtype.
+ *   Linear  y = act(a W^T + b):   dZ = cswin_act_bwd(dY, Z)   (GELU' and / or DropPath scale)
+ *                                 dA = cswin_linear_fwd(dZ, W^T)          (data gradient = a forward Linear)
+ *                                 dW, db = cswin_linear_wgrad(dZ, a)
+ * ------------------------------------------------------------------------------------------------ */
+int cswin_act_fwd(const void* z, int64_t ldz, void* out, int64_t ldo, int64_t M, int32_t N, int32_t act, int32_t dtype,
+                  cswin_stream_t stream);
+int cswin_act_bwd(const void* dout, int64_t ldd, const void* z, int64_t ldz, const float* sample_scale,
+                  int32_t rows_per_sample, void* dz, int64_t ldo, int64_t M, int32_t N, int32_t act, int32_t dtype,
+                  cswin_stream_t stream);
+int cswin_linear_wgrad(const void* dz, int64_t ldz, const void* a, int64_t lda, float* dw, int64_t ldw, float* db, int64_t M,
+                       int32_t N, int32_t K, int32_t dtype, cswin_stream_t stream);
+int cswin_layernorm_bwd(const void* x, int64_t ldx, const void* dy, int64_t ldy, const void* gamma, const float* mean,
+                        const float* rstd, void* dx, int64_t ldo, float* dgamma, float* dbeta, int64_t M, int32_t C,
+                        int32_t dtype, cswin_stream_t stream);
+/* adjoint of cswin_im2col_tokens: dx (B, H*W, C) from dcol (B*Ho*Wo, KH*KW*C) */
+int cswin_col2im_tokens(const void* dcol, int64_t ldcol, void* dx, int64_t x_bs, int64_t x_ts, int32_t B, int32_t H, int32_t W,
+                        int32_t C, int32_t KH, int32_t KW, int32_t stride, int32_t pad, int32_t dtype, cswin_stream_t stream);
+/* backward of cswin_carafe_reassemble_fwd / cswin_carafe_head_fwd.  dy element (b, oy, ox, c) is read at
+ * dy + b*dy_sb + oy*dy_sy + ox*dy_sx + c*dy_sc (token-major or NCHW).  kappa_ws: fp32 workspace (B*H*W * up^2 * 9). */
+int cswin_carafe_reassemble_bwd(const void* enc, int64_t ldenc, const void* z, int64_t ldz, const void* dy, int32_t dy_is_f32,
+                                int64_t dy_sb, int64_t dy_sy, int64_t dy_sx, int64_t dy_sc, void* denc, int64_t lddenc,
+                                void* dz, int64_t lddz, float* dbias, float* kappa_ws, int32_t B, int32_t H, int32_t W,
+                                int32_t C, int32_t up, int32_t dtype, cswin_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

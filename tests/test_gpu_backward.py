@@ -1,0 +1,169 @@
+"""GPU tests of the native backward kernels (through the C ABI via cswin_unet_b200.autograd).  Truth = the reference's own
+autograd where golden vectors exist (LePEAttention: tests/golden/lepe_*.npz) and torch.autograd through the fp64 CPU oracle
+elsewhere.  fp32 path: relative L2 error per gradient tensor <= 1e-4; bf16 path: cosine similarity with the fp64 gradient."""
+import numpy as np
+import pytest
+import torch
+
+import cswin_unet_b200 as cw
+from cswin_unet_b200 import autograd as ag
+from cswin_unet_b200 import synth
+from oracle import cswin_oracle as O
+from tests import golden_util as G
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+LEPE_EXTRA = ((32, 16, 0, 2, 1), (64, 16, 1, 2, 2), (64, 8, -1, 8, 2), (128, 16, 0, 8, 4), (48, 12, 1, 3, 3))
+
+
+def T(a, dtype=torch.float32, device=DEV):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(device=device, dtype=dtype)
+
+
+def rel(a, b):
+    a = a.detach().double().cpu().reshape(-1); b = b.detach().double().cpu().reshape(-1)
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def cos(a, b):
+    a = a.detach().double().cpu().reshape(-1); b = b.detach().double().cpu().reshape(-1)
+    return float((a @ b) / (a.norm() * b.norm()).clamp_min(1e-30))
+
+
+@pytest.mark.parametrize("tag,cfgs,B", [("t224", synth.LEPE_CONFIGS_T224, 1), ("extra", LEPE_EXTRA, 2)])
+def test_lepe_attention_backward_fp32_vs_reference_autograd(tag, cfgs, B):
+    z = G.load(f"lepe_{tag}")
+    for (cb, reso, idx, split, heads) in cfgs:
+        full_c = cb if idx == -1 else 2 * cb
+        base = T(synth.synth_qkv(B, reso, full_c, seed=0)).requires_grad_(True)
+        off = cb if idx == 1 else 0
+        qkv = base.permute(2, 0, 1, 3)[..., off:off + cb]
+        m = cw.LePEAttention(cb, resolution=reso, idx=idx, split_size=split, num_heads=heads).to(DEV)
+        with torch.no_grad():
+            m.get_v.weight.copy_(T(synth.synth_tensor(f"lepe/{cb}/{reso}/{idx}/get_v.weight", (cb, 1, 3, 3), 1)))
+            m.get_v.bias.copy_(T(synth.synth_tensor(f"lepe/{cb}/{reso}/{idx}/get_v.bias", (cb,), 1)))
+        y = m(qkv)
+        key = f"c{cb}_r{reso}_i{idx}_s{split}_h{heads}"
+        gup = T(synth.synth_tensor(f"lepe_grad/{key}", tuple(y.shape), 2))
+        gb, gw, gbias = torch.autograd.grad(y, [base, m.get_v.weight, m.get_v.bias], gup)
+        dqkv = gb[..., off:off + cb].permute(2, 0, 1, 3).reshape(3 * B, reso * reso, cb)
+        G.compare(z, key + "_dqkv", dqkv.cpu().numpy(), atol=2e-5, rtol=1e-4)
+        G.compare(z, key + "_dw", gw.reshape(cb, 9).cpu().numpy(), atol=1e-3, rtol=1e-4)
+        G.compare(z, key + "_db", gbias.reshape(1, cb).cpu().numpy(), atol=1e-3, rtol=1e-4)
+
+
+def test_elementary_backward_ops_fp32_vs_oracle_autograd():
+    g = torch.Generator().manual_seed(5)
+    M, C, N = 203, 96, 72
+    x = torch.randn(M, C, generator=g, dtype=torch.float64)
+    gam = 1 + 0.1 * torch.randn(C, generator=g, dtype=torch.float64)
+    bet = 0.1 * torch.randn(C, generator=g, dtype=torch.float64)
+    w = torch.randn(N, C + 40, generator=g, dtype=torch.float64) / 10
+    b = 0.1 * torch.randn(N, generator=g, dtype=torch.float64)
+    a2 = torch.randn(M, 40, generator=g, dtype=torch.float64)
+    res = torch.randn(M, N, generator=g, dtype=torch.float64)
+    ss = (torch.bernoulli(torch.full((7,), 0.7), generator=g) / 0.7).double()
+    up = torch.randn(M, N, generator=g, dtype=torch.float64)
+    leaves = [t.clone().requires_grad_(True) for t in (x, gam, bet, w, b, a2, res)]
+    xo, go, bo, wo, bbo, a2o, ro = leaves
+    u = O._ln(xo, go, bo, 1e-5)
+    zz = torch.cat([u, a2o], -1) @ wo.T + bbo
+    out = ro + ss.repeat_interleave(29).view(M, 1) * O._gelu(zz)
+    ref = torch.autograd.grad(out, leaves, up)
+    # native: LN -> Linear (two sources) -> GELU -> scaled residual add expressed with the fused Functions
+    dl = [t.detach().float().to(DEV).requires_grad_(True) for t in (x, gam, bet, w, b, a2, res)]
+    xn, gn, bn, wn, bbn, a2n, rn = dl
+    un = ag.LayerNormFn.apply(xn, gn, bn, 1e-5)
+    zn = ag.linear(un, wn, bbn, a2=a2n)
+    hn = ag.GeluFn.apply(zn)
+    eye = torch.eye(N, device=DEV)
+    outn = ag.linear(hn, eye, None, residual=rn, sample_scale=ss.float().to(DEV), rps=29)      # res + s * h
+    got = torch.autograd.grad(outn, dl, up.float().to(DEV))
+    for name, a_, b_ in zip(("x", "gamma", "beta", "w", "b", "a2", "res"), got, ref):
+        assert rel(a_, b_) <= 1e-4, (name, rel(a_, b_))
+
+
+BLOCKS = ((64, 56, 2, 1, False), (128, 28, 4, 2, False), (256, 14, 8, 7, False), (512, 7, 16, 7, True))
+
+
+@pytest.mark.parametrize("dim,reso,heads,split,last", BLOCKS)
+def test_block_backward_fp32_vs_oracle_autograd(dim, reso, heads, split, last):
+    m = cw.CSWinBlock(dim=dim, reso=reso, num_heads=heads, split_size=split, qkv_bias=True, last_stage=last).to(DEV).train()
+    sd64 = {k: torch.from_numpy(synth.synth_tensor(f"block/{dim}/" + k, tuple(v.shape), 3)).double() for k, v in m.state_dict().items()}
+    m.load_state_dict({k: v.float() for k, v in sd64.items()}, strict=True)
+    B = 2
+    x64 = torch.from_numpy(synth.synth_tensor(f"block_in/{dim}", (B, reso * reso, dim), 4)).double()
+    gup = torch.from_numpy(synth.synth_tensor(f"block_gup/{dim}", (B, reso * reso, dim), 6)).double()
+    leaves = {k: v.clone().requires_grad_(True) for k, v in sd64.items()}
+    xo = x64.clone().requires_grad_(True)
+    yo = O.cswin_block(leaves, "", xo, reso, heads, split, last)
+    ref = torch.autograd.grad(yo, [xo] + list(leaves.values()), gup)
+    xn = x64.float().to(DEV).requires_grad_(True)
+    yn = m(xn)
+    assert rel(yn, yo) <= 1e-5
+    got = torch.autograd.grad(yn, [xn] + [dict(m.named_parameters())[k] for k in leaves], gup.float().to(DEV))
+    for name, a_, b_ in zip(["x"] + list(leaves), got, ref):
+        assert rel(a_, b_) <= 1e-4, (name, rel(a_, b_))
+
+
+def test_merge_and_carafe_backward_fp32_vs_oracle_autograd():
+    for kind, mk, dim, reso in (("merge", lambda: cw.Merge_Block(64, 128), 64, 28), ("carafe", lambda: cw.CARAFE(128, 64), 128, 14),
+                                ("carafe4", lambda: cw.CARAFE4(64, 64), 64, 14)):
+        m = mk().to(DEV).train()
+        sd64 = {k: torch.from_numpy(synth.synth_tensor(f"bw/{kind}/" + k, tuple(v.shape), 5)).double() for k, v in m.state_dict().items()}
+        m.load_state_dict({k: v.float() for k, v in sd64.items()}, strict=True)
+        x64 = torch.from_numpy(synth.synth_tensor(f"bw/{kind}/x", (2, reso * reso, dim), 6)).double()
+        leaves = {k: v.clone().requires_grad_(True) for k, v in sd64.items()}
+        xo = x64.clone().requires_grad_(True)
+        yo = O.merge_block(leaves, "", xo) if kind == "merge" else O.carafe(leaves, "", xo, 2 if kind == "carafe" else 4)
+        gup = torch.from_numpy(synth.synth_tensor(f"bw/{kind}/g", tuple(yo.shape), 7)).double()
+        ref = torch.autograd.grad(yo, [xo] + list(leaves.values()), gup)
+        xn = x64.float().to(DEV).requires_grad_(True)
+        yn = m(xn)
+        assert rel(yn, yo) <= 1e-5, kind
+        got = torch.autograd.grad(yn, [xn] + [dict(m.named_parameters())[k] for k in leaves], gup.float().to(DEV))
+        for name, a_, b_ in zip(["x"] + list(leaves), got, ref):
+            assert rel(a_, b_) <= 1e-4, (kind, name, rel(a_, b_))
+
+
+def _model_and_oracle_grads(compute_dtype):
+    m = cw.cswin_tiny_224(num_classes=9, drop_path_rate=0.0).train()
+    shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    sdn = synth.synth_state_dict(shapes, seed=1234)
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in sdn.items()}, strict=True)
+    m = m.to(DEV)
+    m.compute_dtype = compute_dtype
+    x = torch.from_numpy(synth.synth_image_batch(2, 3, 224, seed=0, kind="ct"))
+    y = torch.from_numpy(synth.synth_labels(2, 224, 9, seed=0))
+    logits = m(x.to(DEV))
+    loss = O.seg_loss(logits.float(), y.to(DEV), 9)          # trainer.py:55-57 (harness-level loss, plain torch)
+    loss.backward()
+    return m, sdn, x, y, float(loss)
+
+
+def test_full_model_train_step_gradients_fp32_vs_oracle_autograd():
+    m, sdn, x, y, loss = _model_and_oracle_grads(torch.float32)
+    leaves = {k: torch.from_numpy(v).double().requires_grad_(True) for k, v in sdn.items()}
+    lo = O.seg_loss(O.cswin_unet_forward(leaves, x.double()), y, 9)
+    lo.backward()
+    assert abs(loss - float(lo)) <= 1e-5
+    worst = ("", 0.0)
+    for k, p in m.named_parameters():
+        r = rel(p.grad, leaves[k].grad)
+        if r > worst[1]:
+            worst = (k, r)
+        assert r <= 2e-3, (k, r)
+    print(f"[train fp32] loss {loss:.6f} (oracle {float(lo):.6f}); worst relative gradient error {worst[1]:.2e} at {worst[0]}")
+
+
+def test_full_model_train_step_gradients_bf16_vs_oracle_autograd():
+    m, sdn, x, y, loss = _model_and_oracle_grads(torch.bfloat16)
+    leaves = {k: torch.from_numpy(v).double().requires_grad_(True) for k, v in sdn.items()}
+    lo = O.seg_loss(O.cswin_unet_forward(leaves, x.double()), y, 9)
+    lo.backward()
+    assert abs(loss - float(lo)) <= 2e-2
+    cs = {k: cos(p.grad, leaves[k].grad) for k, p in m.named_parameters() if p.numel() >= 4096}
+    worst = min(cs, key=cs.get)
+    print(f"[train bf16] loss {loss:.5f} (oracle {float(lo):.5f}); min cosine(grad) over weight matrices {cs[worst]:.4f} at {worst}")
+    assert cs[worst] >= 0.98
+    assert all(p.grad.dtype == p.dtype and torch.isfinite(p.grad).all() for p in m.parameters())
