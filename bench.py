@@ -344,6 +344,37 @@ def run_native(args):
                             "argmax -> D2H uint8 label map; 2 buffer slots, copies overlap the neighbouring steps' forward"},
             "roofline": roofline, "roofline_linear": roofline_linear, "roofline_model": roofline_model}
 
+    # ---- train step (BASELINE configs[2]): forward + native backward + gradient all-reduce (NCCL, N > 1) + SGD, bf16
+    #      compute with fp32 master weights, batch 24 per GPU, drop_path 0.2 active.  Reported next to the headline. ----
+    if not args.no_train:
+        import copy
+        tmodel = copy.deepcopy(model).train()
+        step_fn = cw.TrainStep(tmodel, lr=0.05, compute_dtype=torch.bfloat16)
+        timg = pool[0]
+        tlab = torch.from_numpy(synth.synth_labels(B, 224, 9, seed=rank)).to(dev)
+        tw, tk = 5, max(5, min(args.steps, 20))                     # warm-up: 3 eager steps + graph capture + 1 replay
+        for _ in range(tw):
+            step_fn(timg, tlab)
+        barrier()
+        n_tr0 = cw.launch_count()
+        e0.record()
+        for i in range(tk):
+            step_fn(pool[i % n_rot], tlab)
+        e1.record()
+        barrier()
+        ms_tr = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms_tr], device=dev)
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+            ms_tr = float(t.item())
+        line["train_step"] = {"value": world * tk * B / (ms_tr * 1e-3), "unit": UNIT, "ms_per_step": ms_tr / tk, "steps": tk,
+                              "warmup": tw, "batch_per_gpu": B, "dtype": "bf16 compute, fp32 master weights + gradients",
+                              "gpu_launches": int(cw.launch_count() - n_tr0),
+                              "what": "forward + native backward + bucketed NCCL gradient all-reduce (N>1) + torch SGD(momentum); "
+                                      "loss 0.4 CE + 0.6 Dice in torch; whole step replayed as a CUDA graph",
+                              "roofline_frac_tensor": world and (tk * B / (ms_tr * 1e-3)) * 33.231 / 1e3 / (pk["bf16_tflops_sustained"] or pk["bf16_tflops"])}
+        del tmodel, step_fn
+
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, cores, n, dt = cpu_forward_rate(args.cpu_budget, BATCH)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
@@ -364,6 +395,7 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU-oracle work for cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the train-step leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
     if args.impl == "reference":

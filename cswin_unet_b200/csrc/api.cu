@@ -157,6 +157,12 @@ int cswin_linear_wgrad(const void* dz, int64_t ldz, const void* a, int64_t lda, 
                        int32_t N, int32_t K, int32_t dtype, cswin_stream_t stream) {
   CSWIN_REQUIRE(valid_dtype(dtype) && M >= 0 && N > 0 && K > 0, CSWIN_ERR_INVALID, "linear_wgrad: bad arguments");
   CSWIN_REQUIRE(ldz >= N && lda >= K && ldw >= K, CSWIN_ERR_INVALID, "linear_wgrad: leading dimension too small");
+  if (M == 0) return CSWIN_OK;
+  if (dtype == CSWIN_BF16) {
+    bool handled = false;
+    int rc = linear_wgrad_tc(dz, ldz, a, lda, dw, ldw, db, M, N, K, (cudaStream_t)stream, &handled);
+    if (rc != CSWIN_OK || handled) return rc;
+  }
   return linear_wgrad(dz, ldz, a, lda, dw, ldw, db, M, N, K, dtype, (cudaStream_t)stream);
 }
 

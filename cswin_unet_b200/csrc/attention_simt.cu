@@ -163,7 +163,10 @@ int launch_fwd(const cswin_lepe_branch_t* brs, int nb, int B, int reso, float sc
   CSWIN_REQUIRE(smem <= 227 * 1024, CSWIN_ERR_UNSUPPORTED, "lepe_attention: window %d x head_dim %d needs %zu B smem", max_n, max_d, smem);
   if (total == 0) return CSWIN_OK;
   auto kern = (max_n <= 256) ? lepe_attn_fwd_simt_kernel<T, 8> : lepe_attn_fwd_simt_kernel<T, 16>;
-  if (smem > 48 * 1024) CSWIN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // opt in to large dynamic shared memory ONCE per kernel (not per launch: the call is not stream-capture safe)
+  static std::atomic<int> opted[2] = {{0}, {0}};
+  if (smem > 48 * 1024 && !opted[max_n <= 256].exchange(1))
+    CSWIN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   kern<<<total, kWarps * 32, smem, stream>>>(P);
   CSWIN_LAUNCH_CHECK();
   return CSWIN_OK;
@@ -382,7 +385,9 @@ int launch_bwd(const cswin_lepe_branch_grad_t* gs, int nb, int B, int reso, floa
                 "lepe_attention_bwd: window %d x head_dim %d needs %zu B smem (limit 227 KB)", max_n, max_d, smem);
   if (total == 0) return CSWIN_OK;
   auto kern = (max_n <= 256) ? lepe_attn_bwd_simt_kernel<T, 8> : lepe_attn_bwd_simt_kernel<T, 16>;
-  if (smem > 48 * 1024) CSWIN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static std::atomic<int> opted[2] = {{0}, {0}};
+  if (smem > 48 * 1024 && !opted[max_n <= 256].exchange(1))
+    CSWIN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   kern<<<total, kBwdWarps * 32, smem, stream>>>(P);
   CSWIN_LAUNCH_CHECK();
   return CSWIN_OK;

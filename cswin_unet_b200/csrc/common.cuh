@@ -112,6 +112,8 @@ int act_bwd(const void* dout, int64_t ldd, const void* z, int64_t ldz, const flo
             int64_t M, int N, int act, int dtype, cudaStream_t s);
 int linear_wgrad(const void* dz, int64_t ldz, const void* a, int64_t lda, float* dw, int64_t ldw, float* db, int64_t M,
                  int N, int K, int dtype, cudaStream_t s);
+int linear_wgrad_tc(const void* dz, int64_t ldz, const void* a, int64_t lda, float* dw, int64_t ldw, float* db, int64_t M,
+                    int N, int K, cudaStream_t s, bool* handled);
 int layernorm_bwd(const void* x, int64_t ldx, const void* dy, int64_t ldy, const void* gamma, const float* mean,
                   const float* rstd, void* dx, int64_t ldo, float* dgamma, float* dbeta, int64_t M, int C, int dtype,
                   cudaStream_t s);

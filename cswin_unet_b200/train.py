@@ -1,0 +1,109 @@
+"""Data-parallel training step of the reference's baseline trainer (trainer.py:42-60) on the native kernels.
+
+    step = TrainStep(model, lr=0.05)            # SGD(momentum .9, weight decay 1e-4), loss 0.4 CE + 0.6 Dice
+    loss = step(images, labels)                 # forward + backward (native kernels) + gradient all-reduce + SGD update
+
+One process per GPU; with torch.distributed initialised the only exchange is the bucketed NCCL all-reduce of the
+23.57 M gradients (`parallel.allreduce_gradients`) — the reference uses single-process nn.DataParallel
+(trainer.py:37-38).  Loss and optimizer are harness-level torch code (not yet fused); the Dice term is
+formed per rank (a ratio of sums over the LOCAL batch), as SURVEY 8e notes.
+The reference's logging `.item()` calls (>= 11 host syncs per step) are not reproduced: the step returns a device tensor.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.nn.functional as F
+
+from . import parallel
+
+Tensor = torch.Tensor
+
+
+def seg_loss(logits: Tensor, target: Tensor, n_classes: int) -> Tensor:
+    """0.4 * CrossEntropy + 0.6 * DiceLoss(softmax=True)   (trainer.py:55-57, utils.py:9-45)."""
+    logits = logits.float()
+    ce = F.cross_entropy(logits, target.long())
+    prob = torch.softmax(logits, dim=1)
+    # (F.one_hot validates its input with a host sync, which would break CUDA-graph capture of the step)
+    onehot = (target.long().unsqueeze(1) == torch.arange(n_classes, device=target.device).view(1, -1, 1, 1)).to(prob.dtype)
+    dims = (0, 2, 3)
+    inter = (prob * onehot).sum(dims)
+    zsum = (prob * prob).sum(dims)
+    ysum = onehot.sum(dims)
+    dice = (1.0 - (2 * inter + 1e-5) / (zsum + ysum + 1e-5)).mean()
+    return 0.4 * ce + 0.6 * dice
+
+
+class TrainStep:
+    """forward + backward + gradient all-reduce + SGD.  With `graph=True` (default) the whole step is captured once into a
+    CUDA graph (static input buffers; ~2000 launches per step would otherwise be bound by Python launch overhead) and
+    replayed; the NCCL all-reduce stays outside the graph (eager, bucketed) when more than one rank trains."""
+
+    def __init__(self, model, lr: float = 0.05, momentum: float = 0.9, weight_decay: float = 1e-4,
+                 compute_dtype: torch.dtype = torch.bfloat16, group=None, graph: bool = True, warmup: int = 3):
+        self.model = model.train()
+        self.model.compute_dtype = compute_dtype
+        self.n_classes = model.num_classes
+        self.group = group
+        self.opt = torch.optim.SGD(model.parameters(), lr=lr, momentum=momentum, weight_decay=weight_decay)
+        self.use_graph = graph
+        self.warmup = warmup
+        self._graphs = None
+        self._static = None
+        self._seen = 0
+        self._distributed = torch.distributed.is_available() and torch.distributed.is_initialized() and \
+            torch.distributed.get_world_size(group) > 1
+
+    def _fwd_bwd(self, images: Tensor, labels: Tensor) -> Tensor:
+        logits = self.model(images)
+        loss = seg_loss(logits, labels, self.n_classes)
+        loss.backward()
+        return loss.detach()
+
+    def _eager(self, images: Tensor, labels: Tensor) -> Tensor:
+        self.opt.zero_grad(set_to_none=True)
+        loss = self._fwd_bwd(images, labels)
+        parallel.allreduce_gradients(self.model.parameters(), self.group)
+        self.opt.step()
+        return loss
+
+    def _capture(self, images: Tensor, labels: Tensor) -> None:
+        self._static = (images.clone(), labels.clone())
+        sx, sy = self._static
+        self.opt.zero_grad(set_to_none=True)
+        g1 = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g1):                         # forward + backward (+ optimizer when single-rank)
+            self._loss = self._fwd_bwd(sx, sy)
+            if not self._distributed:
+                self.opt.step()
+        g2 = None
+        if self._distributed:                              # all-reduce eagerly between the two graphs
+            g2 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g2, pool=g1.pool()):
+                self.opt.step()
+        self._graphs = (g1, g2)
+
+    def __call__(self, images: Tensor, labels: Tensor) -> Tensor:
+        if not self.use_graph:
+            return self._eager(images, labels)
+        if self._graphs is None:
+            if self._seen < self.warmup:                   # eager warm-up steps (allocator, lazy state, momentum buffers),
+                self._seen += 1                            # on a side stream as CUDA-graph capture of autograd requires
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    loss = self._eager(images, labels)
+                torch.cuda.current_stream().wait_stream(side)
+                return loss
+            self._capture(images, labels)
+        sx, sy = self._static
+        sx.copy_(images, non_blocking=True)
+        sy.copy_(labels, non_blocking=True)
+        g1, g2 = self._graphs
+        g1.replay()
+        if g2 is not None:
+            parallel.allreduce_gradients(self.model.parameters(), self.group)
+            g2.replay()
+        return self._loss
