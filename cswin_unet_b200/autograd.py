@@ -109,8 +109,11 @@ class LepeAttentionFn(Function):
         dt = qkv.dtype
         out = torch.empty((B, L, Cn), dtype=dt, device=qkv.device)
         ws = [(_c(cw0, dt), _c(cb0, dt))] + ([(_c(cw1, dt), _c(cb1, dt))] if cw1 is not None else [])
-        ops.lepe_attention_fwd(LepeAttentionFn._descs(qkv, out, ws, meta, Cn), B, meta["reso"], meta["scale"], dt)
-        ctx.save_for_backward(qkv, *[t for pair in ws for t in pair])
+        # per-row log-sum-exp of the scaled scores, (B, L, heads_b) fp32 per branch: saved for the backward kernel
+        lses = [torch.empty((B, L, h), dtype=torch.float32, device=qkv.device) for h in meta["heads"]]
+        ops.lepe_attention_fwd(LepeAttentionFn._descs(qkv, out, ws, meta, Cn, lambda i, sl: dict(lse=lses[i])), B,
+                               meta["reso"], meta["scale"], dt)
+        ctx.save_for_backward(qkv, *[t for pair in ws for t in pair], *lses)
         ctx.meta, ctx.pd = meta, cw0.dtype
         return out
 
@@ -132,9 +135,11 @@ class LepeAttentionFn(Function):
     @staticmethod
     @once_differentiable
     def backward(ctx, dout):
-        qkv, *wflat = ctx.saved_tensors
-        ws = [(wflat[2 * i], wflat[2 * i + 1]) for i in range(len(wflat) // 2)]
         meta = ctx.meta
+        nbr = len(meta["heads"])
+        qkv, *rest = ctx.saved_tensors
+        wflat, lses = rest[:2 * nbr], rest[2 * nbr:]
+        ws = [(wflat[2 * i], wflat[2 * i + 1]) for i in range(nbr)]
         B, L, C3 = qkv.shape
         Cn = C3 // 3
         dout = dout.contiguous()
@@ -145,7 +150,8 @@ class LepeAttentionFn(Function):
         gb = [torch.zeros(h, dtype=torch.float32, device=qkv.device) for _ in ws]
 
         def extra(i, sl):
-            return dict(dout=dout[..., sl], dq=dq[..., sl], dk=dk[..., sl], dv=dv[..., sl], dconv_w=gw[i], dconv_b=gb[i])
+            return dict(dout=dout[..., sl], dq=dq[..., sl], dk=dk[..., sl], dv=dv[..., sl], dconv_w=gw[i], dconv_b=gb[i],
+                        lse=lses[i])
         descs = LepeAttentionFn._descs(qkv, dout, ws, meta, Cn, extra)
         ops.lepe_attention_bwd(descs, B, meta["reso"], meta["scale"], qkv.dtype)
         g0 = (gw[0].view(h, 1, 3, 3).to(ctx.pd), gb[0].to(ctx.pd))

@@ -76,6 +76,12 @@ int cswin_lepe_attention_bwd(const cswin_lepe_branch_grad_t* branches, int32_t n
   CSWIN_REQUIRE(branches && (n_branches == 1 || n_branches == 2), CSWIN_ERR_INVALID, "lepe_attention_bwd: n_branches must be 1 or 2");
   CSWIN_REQUIRE(B >= 0 && reso > 0, CSWIN_ERR_INVALID, "lepe_attention_bwd: bad B=%d reso=%d", B, reso);
   if (B == 0) return CSWIN_OK;
+  static const bool force_simt = [] { const char* e = getenv("CSWIN_ATTN_BWD_SIMT"); return e && e[0] == '1'; }();   // A/B debugging aid
+  if (dtype == CSWIN_BF16 && !force_simt) {
+    bool handled = false;
+    int rc = lepe_attention_bwd_tc(branches, n_branches, B, reso, scale, (cudaStream_t)stream, &handled);
+    if (rc != CSWIN_OK || handled) return rc;
+  }
   return lepe_attention_bwd_simt(branches, n_branches, B, reso, scale, dtype, (cudaStream_t)stream);
 }
 

@@ -94,6 +94,7 @@ static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b;
 // ---- per-op launchers (defined in the .cu files, called by api.cu) ----
 int lepe_attention_fwd_simt(const cswin_lepe_branch_t* br, int nb, int B, int reso, float scale, int dtype, cudaStream_t s);
 int lepe_attention_fwd_tc(const cswin_lepe_branch_t* br, int nb, int B, int reso, float scale, cudaStream_t s, bool* handled);
+int lepe_attention_bwd_tc(const cswin_lepe_branch_grad_t* br, int nb, int B, int reso, float scale, cudaStream_t s, bool* handled);
 int lepe_attention_bwd_simt(const cswin_lepe_branch_grad_t* br, int nb, int B, int reso, float scale, int dtype, cudaStream_t s);
 int layernorm_fwd(const void* x, int64_t ldx, const void* g, const void* b, void* y, int64_t ldy, int64_t M, int C,
                   float eps, float* mean, float* rstd, int dtype, cudaStream_t s);

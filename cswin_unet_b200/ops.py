@@ -249,7 +249,7 @@ def lepe_attention_bwd(branches: Sequence[dict], B: int, reso: int, scale: float
         _need_cuda(q, k, v, cw, cb, dout, b["dq"], b["dk"], b["dv"], b["dconv_w"], b["dconv_b"])
         keep += [q, k, v, cw, cb, dout]
         g = LepeBranchGrad()
-        g.fwd = _branch(q, k, v, dout, cw, cb, b["heads"], b["H_sp"], b["W_sp"], None)
+        g.fwd = _branch(q, k, v, dout, cw, cb, b["heads"], b["H_sp"], b["W_sp"], b.get("lse"))
         g.dout, g.do_bs, g.do_ts = dout.data_ptr(), dout.stride(0), dout.stride(1)
         for n in ("dq", "dk", "dv"):
             t = b[n]

@@ -183,3 +183,33 @@ def test_linear_wgrad_bf16_tensor_core_vs_fp64(M, N, K):
     ref_w = dz.double().T @ a.double()
     ref_b = dz.double().sum(0)
     assert rel(dw, ref_w) <= 1e-5 and rel(db, ref_b) <= 1e-5, (rel(dw, ref_w), rel(db, ref_b))
+
+
+@pytest.mark.parametrize("cfgs,B", [(synth.LEPE_CONFIGS_T224, 2), (LEPE_EXTRA, 2)])
+def test_lepe_attention_backward_bf16_tensor_core_vs_fp64(cfgs, B):
+    for (cb, reso, idx, split, heads) in cfgs:
+        full_c = cb if idx == -1 else 2 * cb
+        base64 = torch.from_numpy(synth.synth_qkv(B, reso, full_c, seed=0)).bfloat16().double()     # bf16-representable inputs
+        off = cb if idx == 1 else 0
+        w64 = torch.from_numpy(synth.synth_tensor(f"lepe/{cb}/{reso}/{idx}/get_v.weight", (cb, 1, 3, 3), 1)).bfloat16().double()
+        b64 = torch.from_numpy(synth.synth_tensor(f"lepe/{cb}/{reso}/{idx}/get_v.bias", (cb,), 1)).bfloat16().double()
+        key = f"c{cb}_r{reso}_i{idx}_s{split}_h{heads}"
+        gup64 = torch.from_numpy(synth.synth_tensor(f"lepe_grad/{key}", (B, reso * reso, cb), 2)).bfloat16().double()
+        # fp64 truth through the oracle
+        leaves = [t.clone().requires_grad_(True) for t in (base64, w64, b64)]
+        v = leaves[0].permute(2, 0, 1, 3)[..., off:off + cb]
+        yo = O.lepe_attention(v[0], v[1], v[2], leaves[1], leaves[2], reso, idx, split, heads)
+        ref = torch.autograd.grad(yo, leaves, gup64)
+        # native bf16
+        base = base64.to(DEV).bfloat16().requires_grad_(True)
+        m = cw.LePEAttention(cb, resolution=reso, idx=idx, split_size=split, num_heads=heads).to(DEV)
+        with torch.no_grad():
+            m.get_v.weight.copy_(w64.float()); m.get_v.bias.copy_(b64.float())
+        t0 = cw.tc_launch_count()
+        y = m(base.permute(2, 0, 1, 3)[..., off:off + cb])
+        gb, gw, gbias = torch.autograd.grad(y, [base, m.get_v.weight, m.get_v.bias], gup64.to(DEV).bfloat16())
+        if cb // heads == 32 and m.H_sp * m.W_sp <= 128:
+            assert cw.tc_launch_count() == t0 + 2, f"{key}: forward and backward must both run on tcgen05 kernels"
+        sl = (Ellipsis, slice(off, off + cb))
+        assert rel(gb[sl], ref[0][sl]) <= 2e-2, (key, "dqkv", rel(gb[sl], ref[0][sl]))
+        assert rel(gw, ref[1]) <= 2e-2 and rel(gbias, ref[2]) <= 2e-2, (key, rel(gw, ref[1]), rel(gbias, ref[2]))
