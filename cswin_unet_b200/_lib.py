@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(_HERE, "libcswin_b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "cswin_b200.h")
 
 F32, BF16 = 0, 1
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 c_void_p, c_int32, c_int64, c_float = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 
@@ -55,7 +55,7 @@ class LinearArgs(C.Structure):
         ("sample_scale", c_void_p), ("rows_per_sample", c_int32),
         ("out", c_void_p), ("ldo", c_int64),
         ("M", c_int64), ("N", c_int32),
-        ("act", c_int32),
+        ("act", c_int32), ("w_layout", c_int32),
     ]
 
 

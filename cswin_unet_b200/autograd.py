@@ -23,6 +23,10 @@ def needs_grad(*ts) -> bool:
     return torch.is_grad_enabled() and any(t is not None and torch.is_tensor(t) and t.requires_grad for t in ts)
 
 
+import os as _os
+_DGRAD_TRANSPOSE = _os.environ.get("CSWIN_DGRAD_TRANSPOSE") == "1"      # A/B switch: materialise W^T for the data gradient
+
+
 def _c(p: Optional[Tensor], dt: torch.dtype) -> Optional[Tensor]:
     if p is None:
         return None
@@ -70,10 +74,14 @@ class LinearFn(Function):
         dz = dout if ss is None else ops.act_bwd(dout, None, ss, ctx.rps, act=0)
         K1 = a.shape[-1]
         N, K = wc.shape
-        wt = wc.t().contiguous()                                   # (K, N): dA = dZ @ W is a forward Linear on W^T
-        need = ctx.needs_input_grad
-        da = ops.linear(dz, wt[:K1]) if need[0] else None
-        da2 = ops.linear(dz, wt[K1:]) if (a2 is not None and need[3]) else None
+        need = ctx.needs_input_grad                                # dA = dZ @ W: a forward Linear that reads W (N, K) as (K', N')
+        if _DGRAD_TRANSPOSE:                                       # A/B switch: materialise W^T instead
+            wt = wc.t().contiguous()
+            da = ops.linear(dz, wt[:K1]) if need[0] else None
+            da2 = ops.linear(dz, wt[K1:]) if (a2 is not None and need[3]) else None
+        else:
+            da = ops.linear(dz, wc[:, :K1], w_kn=True) if need[0] else None
+            da2 = ops.linear(dz, wc[:, K1:], w_kn=True) if (a2 is not None and need[3]) else None
         dw = db = None
         if need[1] or need[2]:
             dwf = torch.zeros((N, K), dtype=torch.float32, device=dz.device)

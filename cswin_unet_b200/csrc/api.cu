@@ -98,7 +98,8 @@ int cswin_linear_fwd(const cswin_linear_args_t* a, int32_t dtype, cswin_stream_t
   CSWIN_REQUIRE(a && a->a && a->w && a->out, CSWIN_ERR_INVALID, "linear_fwd: null pointer");
   CSWIN_REQUIRE(a->M >= 0 && a->N > 0 && a->K1 > 0 && a->K2 >= 0, CSWIN_ERR_INVALID, "linear_fwd: bad M/N/K");
   CSWIN_REQUIRE((a->a2 != nullptr) == (a->K2 > 0), CSWIN_ERR_INVALID, "linear_fwd: a2 and K2 must be given together");
-  CSWIN_REQUIRE(a->lda >= a->K1 && a->ldw >= a->K1 + a->K2 && a->ldo >= a->N, CSWIN_ERR_INVALID, "linear_fwd: leading dimension too small");
+  CSWIN_REQUIRE(a->w_layout == 0 || a->w_layout == 1, CSWIN_ERR_INVALID, "linear_fwd: w_layout must be 0 ((N,K)) or 1 ((K,N))");
+  CSWIN_REQUIRE(a->lda >= a->K1 && a->ldw >= (a->w_layout ? a->N : a->K1 + a->K2) && a->ldo >= a->N, CSWIN_ERR_INVALID, "linear_fwd: leading dimension too small");
   CSWIN_REQUIRE(!a->a2 || a->lda2 >= a->K2, CSWIN_ERR_INVALID, "linear_fwd: lda2 too small");
   CSWIN_REQUIRE(!a->residual || a->ldr >= a->N, CSWIN_ERR_INVALID, "linear_fwd: ldr too small");
   CSWIN_REQUIRE((a->ln_gamma != nullptr) == (a->ln_beta != nullptr), CSWIN_ERR_INVALID, "linear_fwd: ln_gamma and ln_beta must be given together");

@@ -46,6 +46,43 @@ __global__ void __launch_bounds__(256) act_fwd_kernel(const T* __restrict__ z, i
   }
 }
 
+// bf16, contiguous rows (ld == N), N % 8 == 0: 16-byte vectors, 8 elements per thread
+__device__ __forceinline__ float gelu_grad(float x) {
+  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+  return cdf + x * 0.39894228040143267794f * __expf(-0.5f * x * x);
+}
+__global__ void __launch_bounds__(256) act_bwd_bf16_vec_kernel(const uint4* __restrict__ dout, const uint4* __restrict__ z,
+                                                                const float* __restrict__ sscale, int64_t elems_per_sample,
+                                                                uint4* __restrict__ dz, int64_t nvec, int act) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint4 d = dout[i];
+    const float sc = sscale != nullptr ? sscale[(i * 8) / elems_per_sample] : 1.0f;
+    uint32_t dw[4] = {d.x, d.y, d.z, d.w}, zw[4] = {0, 0, 0, 0}, o[4];
+    if (act == 1) { const uint4 zz = z[i]; zw[0] = zz.x; zw[1] = zz.y; zw[2] = zz.z; zw[3] = zz.w; }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float lo = __uint_as_float(dw[e] << 16) * sc, hi = __uint_as_float(dw[e] & 0xffff0000u) * sc;
+      if (act == 1) { lo *= gelu_grad(__uint_as_float(zw[e] << 16)); hi *= gelu_grad(__uint_as_float(zw[e] & 0xffff0000u)); }
+      const __nv_bfloat162 pk = __floats2bfloat162_rn(lo, hi);
+      o[e] = *reinterpret_cast<const uint32_t*>(&pk);
+    }
+    dz[i] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+__global__ void __launch_bounds__(256) act_fwd_bf16_vec_kernel(const uint4* __restrict__ z, uint4* __restrict__ out, int64_t nvec) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint4 zz = z[i];
+    const uint32_t zw[4] = {zz.x, zz.y, zz.z, zz.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const __nv_bfloat162 pk = __floats2bfloat162_rn(gelu_erf(__uint_as_float(zw[e] << 16)), gelu_erf(__uint_as_float(zw[e] & 0xffff0000u)));
+      o[e] = *reinterpret_cast<const uint32_t*>(&pk);
+    }
+    out[i] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // dW[n,k] += sum_m dZ[m,n] A[m,k] ; 64x64 (n,k) tile per CTA, M split over gridDim.z, fp32 atomics at the end.
 constexpr int WT = 64, WM = 16;
@@ -276,6 +313,12 @@ unsigned grid_for(int64_t total, int per_cta) {
 int act_fwd(const void* z, int64_t ldz, void* out, int64_t ldo, int64_t M, int N, int act, int dtype, cudaStream_t s) {
   CSWIN_REQUIRE(z && out, CSWIN_ERR_INVALID, "act_fwd: null pointer");
   if (M * N == 0) return CSWIN_OK;
+  if (dtype == CSWIN_BF16 && act == 1 && ldz == N && ldo == N && N % 8 == 0 && (reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(out)) % 16 == 0) {
+    const int64_t nvec = M * N / 8;
+    act_fwd_bf16_vec_kernel<<<grid_for(nvec, 256), 256, 0, s>>>((const uint4*)z, (uint4*)out, nvec);
+    CSWIN_LAUNCH_CHECK();
+    return CSWIN_OK;
+  }
   const unsigned grid = grid_for(M * N, 256);
   if (dtype == CSWIN_F32) act_fwd_kernel<float><<<grid, 256, 0, s>>>((const float*)z, ldz, (float*)out, ldo, M, N, act);
   else act_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)z, ldz, (__nv_bfloat16*)out, ldo, M, N, act);
@@ -288,6 +331,13 @@ int act_bwd(const void* dout, int64_t ldd, const void* z, int64_t ldz, const flo
   CSWIN_REQUIRE(dout && dz && (act == 0 || z), CSWIN_ERR_INVALID, "act_bwd: null pointer");
   CSWIN_REQUIRE(!sscale || rps > 0, CSWIN_ERR_INVALID, "act_bwd: rows_per_sample must be > 0");
   if (M * N == 0) return CSWIN_OK;
+  if (dtype == CSWIN_BF16 && ldd == N && ldo == N && (act == 0 || ldz == N) && N % 8 == 0 && (!sscale || ((int64_t)rps * N) % 8 == 0) &&
+      (reinterpret_cast<uintptr_t>(dout) | reinterpret_cast<uintptr_t>(dz) | (act ? reinterpret_cast<uintptr_t>(z) : 0)) % 16 == 0) {
+    const int64_t nvec = M * N / 8;
+    act_bwd_bf16_vec_kernel<<<grid_for(nvec, 256), 256, 0, s>>>((const uint4*)dout, (const uint4*)z, sscale, (int64_t)rps * N, (uint4*)dz, nvec, act);
+    CSWIN_LAUNCH_CHECK();
+    return CSWIN_OK;
+  }
   const unsigned grid = grid_for(M * N, 256);
   if (dtype == CSWIN_F32) act_bwd_kernel<float><<<grid, 256, 0, s>>>((const float*)dout, ldd, (const float*)z, ldz, sscale, rps, (float*)dz, ldo, M, N, act);
   else act_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)dout, ldd, (const __nv_bfloat16*)z, ldz, sscale, rps, (__nv_bfloat16*)dz, ldo, M, N, act);

@@ -25,7 +25,7 @@ struct GemmParams {
   const T* res; int64_t ldr;
   const float* sscale; int rps;
   T* out; int64_t ldo;
-  int64_t M; int N; int act;
+  int64_t M; int N; int act; int w_kn;
 };
 
 template <typename T>
@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(256) linear_simt_kernel(const GemmParams<T> P)
       }
       As[lk + i][lr] = va;
       const int n = n0 + lr;
-      Ws[lk + i][lr] = (n < P.N && k < K) ? ldf(P.w + (int64_t)n * P.ldw + k) : 0.f;
+      Ws[lk + i][lr] = (n < P.N && k < K) ? ldf(P.w_kn ? P.w + (int64_t)k * P.ldw + n : P.w + (int64_t)n * P.ldw + k) : 0.f;
     }
     __syncthreads();
 #pragma unroll
@@ -126,7 +126,7 @@ int launch(const cswin_linear_args_t* a, cudaStream_t s) {
   P.w = (const T*)a->w; P.ldw = a->ldw; P.bias = (const T*)a->bias;
   P.ln_g = (const T*)a->ln_gamma; P.ln_b = (const T*)a->ln_beta; P.ln_eps = a->ln_eps;
   P.res = (const T*)a->residual; P.ldr = a->ldr; P.sscale = a->sample_scale; P.rps = a->rows_per_sample;
-  P.out = (T*)a->out; P.ldo = a->ldo; P.M = a->M; P.N = a->N; P.act = a->act;
+  P.out = (T*)a->out; P.ldo = a->ldo; P.M = a->M; P.N = a->N; P.act = a->act; P.w_kn = a->w_layout;
   dim3 grid((unsigned)ceil_div64(a->M, BM), (unsigned)((a->N + BN - 1) / BN));
   linear_simt_kernel<T><<<grid, 256, 0, s>>>(P);
   CSWIN_LAUNCH_CHECK();

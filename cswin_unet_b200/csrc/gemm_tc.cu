@@ -37,7 +37,7 @@ struct alignas(64) GemmTcParams {
   const float* sscale; int rps;
   __nv_bfloat16* out; int64_t ldo;
   int64_t M; int N; int K1; int K2;
-  int BN, stages, nkb, nkb1, act, tmem_cols, vec_ok, bias_vec;
+  int BN, stages, nkb, nkb1, act, tmem_cols, vec_ok, bias_vec, w_kn;
   unsigned long long* trace;
 };
 
@@ -107,7 +107,9 @@ __global__ void __launch_bounds__(kThreads, 2) linear_tc_kernel(const __grid_con
   if (warp == 0 && lane == 0) {
     for (int kb = 0; kb < npre; ++kb) {
       mbar_expect_tx(full(kb), a_bytes + w_bytes);
-      tma_load_2d(smem_u32(Ws + (size_t)kb * w_bytes), &P.map_w, full(kb), kb * BK, n0);
+      if (!P.w_kn) tma_load_2d(smem_u32(Ws + (size_t)kb * w_bytes), &P.map_w, full(kb), kb * BK, n0);
+      else for (int j = 0; j * 64 < BN; ++j)             // (K, N) weight: [64 k][64 n] boxes = MN-major B blocks
+        tma_load_2d(smem_u32(Ws + (size_t)kb * w_bytes + j * 8192), &P.map_w, full(kb), n0 + 64 * j, kb * BK);
     }
   }
   pdl_wait();                                           // activations (A, residual) and the output buffer are safe from here
@@ -119,7 +121,9 @@ __global__ void __launch_bounds__(kThreads, 2) linear_tc_kernel(const __grid_con
         if (kb >= S) {
           mbar_wait(empty(s), ((kb / S) - 1) & 1);
           mbar_expect_tx(full(s), a_bytes + w_bytes);
-          tma_load_2d(smem_u32(Ws + (size_t)s * w_bytes), &P.map_w, full(s), kb * BK, n0);
+          if (!P.w_kn) tma_load_2d(smem_u32(Ws + (size_t)s * w_bytes), &P.map_w, full(s), kb * BK, n0);
+          else for (int j = 0; j * 64 < BN; ++j)
+            tma_load_2d(smem_u32(Ws + (size_t)s * w_bytes + j * 8192), &P.map_w, full(s), n0 + 64 * j, kb * BK);
         }
         if (kb < P.nkb1) tma_load_2d(smem_u32(As + (size_t)s * a_bytes), &P.map_a, full(s), kb * BK, (int)m0);
         else             tma_load_2d(smem_u32(As + (size_t)s * a_bytes), &P.map_a2, full(s), (kb - P.nkb1) * BK, (int)m0);
@@ -128,16 +132,17 @@ __global__ void __launch_bounds__(kThreads, 2) linear_tc_kernel(const __grid_con
     }
   } else if (warp == 1) {
     if (lane == 0) {                                    // ---- MMA issuer ----
-      const uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
+      const uint32_t idesc = make_idesc_bf16(BM, BN, 0, P.w_kn);
+      const uint32_t wstep = P.w_kn ? (2048 >> 4) : 2;   // 16 contraction rows: 2 KB (MN-major) or 32 B (K-major) further
       for (int kb = 0; kb < P.nkb; ++kb) {
         const int s = kb % S;
         mbar_wait(full(s), (kb / S) & 1);
         if (kb == 0) trace_stamp(P.trace, 3);           // first operands landed
         tc_fence_after();
         const uint64_t ad = make_smem_desc(smem_u32(As + (size_t)s * a_bytes), 16, 1024, kLayoutSw128);
-        const uint64_t wd = make_smem_desc(smem_u32(Ws + (size_t)s * w_bytes), 16, 1024, kLayoutSw128);
+        const uint64_t wd = make_smem_desc(smem_u32(Ws + (size_t)s * w_bytes), P.w_kn ? 8192 : 16, 1024, kLayoutSw128);
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k) mma_ss(tmem_base, ad + 2 * k, wd + 2 * k, idesc, (kb | k) != 0);
+        for (int k = 0; k < BK / 16; ++k) mma_ss(tmem_base, ad + 2 * k, wd + (uint64_t)wstep * k, idesc, (kb | k) != 0);
         tc_commit(empty(s));                            // smem slot reusable once these MMAs have read it
       }
       tc_commit(bar_acc);                               // accumulator complete
@@ -244,16 +249,17 @@ struct TileCfg { int bn, stages; };
 // number of waves against per-tile latency = fixed setup + K-loop (faster with a deeper ring) + epilogue (per 64
 // columns; GELU costs ~2x).  The ring depth is whatever fits once the CTAs that must share an SM are accounted for.
 // CSWIN_GEMM_BN=<n> forces BN for experiments.
-TileCfg pick_tile(int64_t M, int N, int nkb, int act, int sms) {
+TileCfg pick_tile(int64_t M, int N, int nkb, int act, int sms, bool w_kn) {
   static const int forced = [] { const char* e = getenv("CSWIN_GEMM_BN"); return e ? atoi(e) : 0; }();
-  const int n16 = (N + 15) & ~15;
+  const int n16 = w_kn ? ((N + 63) & ~63) : ((N + 15) & ~15);      // (K,N) weights are fetched in 64-column boxes
   const int64_t mt = (M + BM - 1) / BM;
   const int cands[] = {64, 96, 128, 192, 256};
   TileCfg best{n16 < 64 ? n16 : 64, 1};
   double best_t = 1e30;
   for (int bn : cands) {
     if (forced >= 16 && forced <= 256 && forced % 16 == 0) bn = forced;
-    if (bn > n16) bn = n16;
+    if (w_kn && bn % 64) continue;
+    if (bn > n16) bn = n16 > 256 ? 256 : n16;
     if (N % bn != 0 && bn > 64 && bn != n16) continue;
     const int64_t tiles = mt * ((N + bn - 1) / bn);
     int resident = 512 / tmem_cols_for(bn);
@@ -292,7 +298,8 @@ int linear_fwd_tc(const cswin_linear_args_t* a, cudaStream_t stream, bool* handl
   P.M = a->M; P.N = a->N; P.K1 = a->K1; P.K2 = a->K2; P.act = a->act;
   P.nkb1 = (a->K1 + BK - 1) / BK;
   P.nkb = P.nkb1 + (a->K2 + BK - 1) / BK;
-  const TileCfg cfg = pick_tile(a->M, a->N, P.nkb, a->act, sm_count());
+  P.w_kn = a->w_layout;
+  const TileCfg cfg = pick_tile(a->M, a->N, P.nkb, a->act, sm_count(), a->w_layout != 0);
   P.BN = cfg.bn;
   P.stages = cfg.stages;
   P.tmem_cols = tmem_cols_for(P.BN);
@@ -316,10 +323,11 @@ int linear_fwd_tc(const cswin_linear_args_t* a, cudaStream_t stream, bool* handl
     P.map_a2 = P.map_a;
   }
   {
-    const uint64_t dims[2] = {(uint64_t)K, (uint64_t)a->N};
+    const uint64_t dims_nk[2] = {(uint64_t)K, (uint64_t)a->N}, dims_kn[2] = {(uint64_t)a->N, (uint64_t)K};
     const uint64_t str[1] = {(uint64_t)a->ldw * 2};
-    const uint32_t box[2] = {BK, (uint32_t)P.BN};
-    if (!tc::make_tensor_map_bf16(&P.map_w, a->w, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return CSWIN_ERR_CUDA;
+    const uint32_t box_nk[2] = {BK, (uint32_t)P.BN}, box_kn[2] = {64, BK};
+    if (!tc::make_tensor_map_bf16(&P.map_w, a->w, 2, a->w_layout ? dims_kn : dims_nk, str, a->w_layout ? box_kn : box_nk,
+                                  CU_TENSOR_MAP_SWIZZLE_128B)) return CSWIN_ERR_CUDA;
   }
 
   const size_t smem = smem_bytes(P.BN, P.stages);

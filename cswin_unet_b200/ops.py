@@ -130,7 +130,7 @@ def layernorm(x: Tensor, gamma: Tensor, beta: Tensor, eps: float = 1e-5, out: Op
 def linear(a: Tensor, w: Tensor, bias: Optional[Tensor] = None, *, a2: Optional[Tensor] = None,
            ln: Optional[Tuple[Tensor, Tensor, float]] = None, act: int = 0, residual: Optional[Tensor] = None,
            sample_scale: Optional[Tensor] = None, rows_per_sample: int = 0, out: Optional[Tensor] = None,
-           n_out: Optional[int] = None) -> Tensor:
+           n_out: Optional[int] = None, w_kn: bool = False) -> Tensor:
     """out = residual + sample_scale[row // rows_per_sample] * act(LN?([a | a2]) @ w[:n_out].T + bias)."""
     _need_cuda(a, w, bias, a2, residual, sample_scale)
     if ln is not None and a.dtype == torch.bfloat16:
@@ -150,8 +150,13 @@ def linear(a: Tensor, w: Tensor, bias: Optional[Tensor] = None, *, a2: Optional[
         K2 = a2.shape[-1]
         args.a2, args.lda2, args.K2 = a2_.data_ptr(), lda2, K2
         keep.append(a2_)
-    assert w.dim() == 2 and w.stride(1) == 1 and w.shape[1] == K1 + K2, (w.shape, K1, K2)
-    N = w.shape[0] if n_out is None else n_out
+    if w_kn:                                              # w is (K, N): out = a @ w  (dgrad reads nn.Linear.weight in place)
+        assert w.dim() == 2 and w.stride(1) == 1 and w.shape[0] == K1 + K2, (w.shape, K1, K2)
+        N = w.shape[1] if n_out is None else n_out
+        args.w_layout = 1
+    else:
+        assert w.dim() == 2 and w.stride(1) == 1 and w.shape[1] == K1 + K2, (w.shape, K1, K2)
+        N = w.shape[0] if n_out is None else n_out
     args.w, args.ldw = w.data_ptr(), w.stride(0)
     args.bias = _ptr(bias)
     if ln is not None:

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define CSWIN_ABI_VERSION 1
+#define CSWIN_ABI_VERSION 2
 
 typedef struct CUstream_st* cswin_stream_t; /* == cudaStream_t */
 
@@ -125,6 +125,8 @@ typedef struct {
   void* out; int64_t ldo;
   int64_t M; int32_t N;
   int32_t act;
+  int32_t w_layout;                                /* 0: w is (N, K) row-major (nn.Linear.weight);  1: w is (K, N) row-major, i.e.
+                                                      out = a w — the data gradient dA = dZ W reads W in place, no transpose */
 } cswin_linear_args_t;
 
 int cswin_linear_fwd(const cswin_linear_args_t* args, int32_t dtype, cswin_stream_t stream);

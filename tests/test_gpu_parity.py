@@ -383,3 +383,16 @@ def test_predict_volume_sharded_equals_unsharded():
     full, _ = cw.predict_volume(eng, vol)
     parts = [cw.predict_volume(eng, vol, shard=(r, 3))[0] for r in range(3)]
     assert np.array_equal(np.concatenate(parts, 0), full)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-4), (torch.bfloat16, 3e-2)])
+@pytest.mark.parametrize("M,N,K", [(3136, 64, 192), (784, 128, 512), (4704, 1024, 256), (201, 152, 64), (98, 40, 72)])
+def test_linear_kn_weight_layout(dtype, tol, M, N, K):
+    """w_layout = 1: out = a @ w with w (K, N) row-major — the data-gradient form dA = dZ W (a column slice of W works too)."""
+    g = torch.Generator().manual_seed(M + N + K)
+    a = torch.randn(M, K, generator=g).to(dtype)
+    wfull = (torch.randn(K, N + 16, generator=g) / K ** 0.5).to(dtype)
+    w = wfull[:, 8:8 + N]                                     # non-contiguous (K, N) view, 16-byte aligned rows
+    y = ops.linear(a.to(DEV), wfull.to(DEV)[:, 8:8 + N], None, w_kn=True)
+    ref = a.double() @ w.double()
+    assert y.shape == (M, N) and (y.cpu().double() - ref).abs().max().item() <= tol
