@@ -34,6 +34,7 @@ struct alignas(64) BwdParams {
   BwdBranch br[2];
   int nb, reso;
   float scale, scale_log2e;
+  unsigned long long* trace;
 };
 
 constexpr int kRows = 128, kThr = 256, kRowB = 64;
@@ -86,6 +87,7 @@ __global__ void __launch_bounds__(kThr, 2) lepe_attn_bwd_tc_kernel(const __grid_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
 
   const int tid = threadIdx.x, warp = tid >> 5;
+  if (tid == 0) trace_stamp(P.trace, 0);
   const int row = tid & 127, half = tid >> 7;
   const int bi = (P.nb > 1 && (int)blockIdx.x >= P.br[1].tile_begin) ? 1 : 0;
   const BwdBranch& br = P.br[bi];
@@ -138,6 +140,7 @@ __global__ void __launch_bounds__(kThr, 2) lepe_attn_bwd_tc_kernel(const __grid_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (tid == 0) trace_stamp(P.trace, 1);
 
   if (tid == 0) {
     mbar_expect_tx(bar_tma, (uint32_t)(np * 4 * N * kRowB));
@@ -164,6 +167,7 @@ __global__ void __launch_bounds__(kThr, 2) lepe_attn_bwd_tc_kernel(const __grid_
     tc_commit(bar_s);
   }
   mbar_wait(bar_s, 0);
+  if (tid == 0) trace_stamp(P.trace, 2);
   tc_fence_after();
 
   // ---- P, delta, dS for row `row`, key columns [kbeg, kbeg + hcols) of my slot ----
@@ -233,6 +237,7 @@ __global__ void __launch_bounds__(kThr, 2) lepe_attn_bwd_tc_kernel(const __grid_
   __syncthreads();                                      // S / dP fully consumed; P / dS visible to the tensor core
 
   if (tid == 0) {
+    trace_stamp(P.trace, 3);
     tc_fence_after();
     const uint32_t id_mn = make_idesc_bf16(128, 32, 1, 1);      // A = P / dS read MN-major (kv rows out), B MN-major
     const uint32_t id_k = make_idesc_bf16(128, 32, 0, 1);       // A = dS K-major (q rows out), B = K MN-major
@@ -277,25 +282,42 @@ __global__ void __launch_bounds__(kThr, 2) lepe_attn_bwd_tc_kernel(const __grid_
       }
     }
   }
-  // ---- d w[ch][tap] / d b[ch]: thread (slot s, tap t or bias, channel ch) sums over the window's tokens ----
+  if (tid == 0) trace_stamp(P.trace, 4);
+  // ---- d w[ch][tap] / d b[ch]: thread = (channel tid & 31, token group tid >> 5); every thread walks its share of the
+  //      window's tokens keeping the 9 tap sums + the bias sum in registers, groups are merged with shared-memory atomics
+  for (int s = 0; s < np; ++s) {
+    const int ch = tid & 31;
+    const int cchunk = ch >> 3, coff = (ch & 7) * 2;
+    float acc[10];
+#pragma unroll
+    for (int t = 0; t < 10; ++t) acc[t] = 0.f;
+    for (int nn = tid >> 5; nn < N; nn += kThr / 32) {
+      const int r = nn / ws, c = nn - r * ws;
+      const float g = lds_bf16(sw64(gsb, s * slot_rows + nn, cchunk) + coff);
+      acc[9] += g;
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        const int rr = r + t / 3 - 1, cc = c + t % 3 - 1;
+        if (rr >= 0 && rr < hs && cc >= 0 && cc < ws)
+          acc[t] = fmaf(g, lds_bf16(sw64(vsb, s * slot_rows + rr * ws + cc, cchunk) + coff), acc[t]);
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < 10; ++t) atomicAdd(&Part[(s * 10 + t) * 32 + ch], acc[t]);
+  }
+  __syncthreads();
   for (int o = tid; o < np * 320; o += kThr) {
     const int s = o / 320, rem = o - s * 320;
     const int t = rem >> 5, ch = rem & 31;                  // t = 9 -> bias
-    float acc = 0.f;
-    for (int nn = 0; nn < N; ++nn) {
-      const int gr = s * slot_rows + nn;
-      const float g = lds_bf16(sw64(gsb, gr, ch >> 3) + (ch & 7) * 2);
-      if (t == 9) { acc += g; continue; }
-      const int rr = nn / ws + t / 3 - 1, cc = nn % ws + t % 3 - 1;
-      if (rr >= 0 && rr < hs && cc >= 0 && cc < ws)
-        acc = fmaf(g, lds_bf16(sw64(vsb, s * slot_rows + rr * ws + cc, ch >> 3) + (ch & 7) * 2), acc);
-    }
     const int hd = (p0 + s) % br.heads;
-    if (t == 9) atomicAdd(br.dcb + hd * 32 + ch, acc);
-    else atomicAdd(br.dcw + (int64_t)(hd * 32 + ch) * 9 + t, acc);
+    const float v = Part[(s * 10 + t) * 32 + ch];
+    if (t == 9) atomicAdd(br.dcb + hd * 32 + ch, v);
+    else atomicAdd(br.dcw + (int64_t)(hd * 32 + ch) * 9 + t, v);
   }
 
+  if (tid == 0) trace_stamp(P.trace, 5);
   mbar_wait(bar_o, 0);
+  if (tid == 0) trace_stamp(P.trace, 6);
   tc_fence_after();
   {
     uint32_t q16[16], k16[16], v16[16];
@@ -322,6 +344,7 @@ __global__ void __launch_bounds__(kThr, 2) lepe_attn_bwd_tc_kernel(const __grid_
   }
   tc_fence_before();
   __syncthreads();
+  if (tid == 0) trace_stamp(P.trace, 7);
   if (warp == 0) tmem_dealloc(tmem_base, kTmem);
 }
 
@@ -345,6 +368,7 @@ int lepe_attention_bwd_tc(const cswin_lepe_branch_grad_t* gs, int nb, int B, int
   if (tc::encode_tiled_fn() == nullptr) return CSWIN_OK;
   BwdParams P;
   P.nb = nb; P.reso = reso; P.scale = scale; P.scale_log2e = scale * 1.4426950408889634f;
+  P.trace = g_trace.load(std::memory_order_relaxed);
   int tiles = 0;
   for (int i = 0; i < nb; ++i) {
     const cswin_lepe_branch_grad_t& g = gs[i];

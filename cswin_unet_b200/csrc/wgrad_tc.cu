@@ -25,7 +25,7 @@ constexpr int kWThreads = 192;    // warp 0 TMA, warp 1 MMA + TMEM, warps 2..5 e
 struct alignas(64) WgradParams {
   CUtensorMap map_z, map_a;
   float* dw; int64_t ldw;
-  int N, K, BN, nblk, tmem_cols;
+  int N, K, BN, nblk, tmem_cols, vec4;
   int64_t M, mchunk;
 };
 
@@ -104,9 +104,16 @@ __global__ void __launch_bounds__(kWThreads) linear_wgrad_tc_kernel(const __grid
       tmem_wait_ld();
       if (n < P.N && nmb > 0) {
         float* dst = P.dw + (int64_t)n * P.ldw + k0 + c * 32;
+        if (P.vec4 && k0 + c * 32 + 32 <= P.K) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (k0 + c * 32 + j < P.K) atomicAdd(dst + j, __uint_as_float(v[j]));
+          for (int j = 0; j < 32; j += 4)                // 16-byte vector reductions: 4x fewer L2 atomic operations
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(__uint_as_float(v[j])),
+                         "f"(__uint_as_float(v[j + 1])), "f"(__uint_as_float(v[j + 2])), "f"(__uint_as_float(v[j + 3])) : "memory");
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (k0 + c * 32 + j < P.K) atomicAdd(dst + j, __uint_as_float(v[j]));
+        }
       }
     }
   }
@@ -145,6 +152,7 @@ int linear_wgrad_tc(const void* dz, int64_t ldz, const void* a, int64_t lda, flo
   if (tc::encode_tiled_fn() == nullptr) return CSWIN_OK;
   WgradParams P;
   P.dw = dw; P.ldw = ldw; P.N = N; P.K = K; P.M = M;
+  P.vec4 = aligned16(dw) && (ldw * 4) % 16 == 0;
   P.nblk = K >= 256 ? 4 : (K + 63) / 64;
   P.BN = P.nblk * 64;
   P.tmem_cols = P.BN <= 64 ? 64 : P.BN <= 128 ? 128 : 256;
