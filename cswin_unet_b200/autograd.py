@@ -27,9 +27,49 @@ import os as _os
 _DGRAD_TRANSPOSE = _os.environ.get("CSWIN_DGRAD_TRANSPOSE") == "1"      # A/B switch: materialise W^T for the data gradient
 
 
+# SHADOW[id(param)] = compute-dtype copy of the parameter, refreshed once per step by ONE multi-tensor copy
+# (train.TrainStep) instead of a cast kernel per weight per use.  Empty outside a TrainStep.
+SHADOW: dict = {}
+
+
+class ZeroPool:
+    """Bump allocator over ONE flat fp32 buffer that train.TrainStep zeroes once per step: the weight-gradient kernels
+    accumulate into slices of it instead of ~460 separately zero-filled tensors."""
+
+    def __init__(self, numel: int, device):
+        self.buf = torch.zeros(numel, dtype=torch.float32, device=device)
+        self.off = 0
+
+    def reset(self):
+        self.buf.zero_()
+        self.off = 0
+
+    def take(self, shape) -> Optional[Tensor]:
+        n = 1
+        for s in shape:
+            n *= s
+        n4 = (n + 3) // 4 * 4
+        if self.off + n4 > self.buf.numel():
+            return None
+        v = self.buf[self.off:self.off + n].view(shape)
+        self.off += n4
+        return v
+
+
+POOL: Optional[ZeroPool] = None
+
+
+def _zeros(shape, device) -> Tensor:
+    v = POOL.take(shape) if POOL is not None else None
+    return v if v is not None else torch.zeros(shape, dtype=torch.float32, device=device)
+
+
 def _c(p: Optional[Tensor], dt: torch.dtype) -> Optional[Tensor]:
     if p is None:
         return None
+    sh = SHADOW.get(id(p))
+    if sh is not None and sh.dtype == dt:
+        return sh
     p = p.detach()
     return p if (p.dtype == dt and p.is_contiguous()) else p.to(dt).contiguous()
 
@@ -84,8 +124,8 @@ class LinearFn(Function):
             da2 = ops.linear(dz, wc[:, K1:], w_kn=True) if (a2 is not None and need[3]) else None
         dw = db = None
         if need[1] or need[2]:
-            dwf = torch.zeros((N, K), dtype=torch.float32, device=dz.device)
-            dbf = torch.zeros(N, dtype=torch.float32, device=dz.device) if ctx.has_bias else None
+            dwf = _zeros((N, K), dz.device)
+            dbf = _zeros((N,), dz.device) if ctx.has_bias else None
             ops.linear_wgrad(dz, a, dwf[:, :K1], dbf)
             if a2 is not None:
                 ops.linear_wgrad(dz, a2, dwf[:, K1:], None)

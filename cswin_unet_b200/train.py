@@ -16,6 +16,7 @@ from typing import Optional
 import torch
 import torch.nn.functional as F
 
+from . import autograd as ag
 from . import parallel
 
 Tensor = torch.Tensor
@@ -53,13 +54,37 @@ class TrainStep:
         self._graphs = None
         self._static = None
         self._seen = 0
+        self._make_shadow(compute_dtype)
+        import os
+        self._pool = None if os.environ.get("CSWIN_NO_POOL") == "1" else ag.ZeroPool(
+            sum(p.numel() + 4 for p in model.parameters()), next(model.parameters()).device)
         self._distributed = torch.distributed.is_available() and torch.distributed.is_initialized() and \
             torch.distributed.get_world_size(group) > 1
 
+    def _make_shadow(self, dtype: torch.dtype) -> None:
+        ps = [p for p in self.model.parameters() if p.dtype != dtype]
+        self._shadow_src = ps
+        n = sum(p.numel() + 8 for p in ps)                       # every view 16-byte aligned
+        flat = torch.empty(n, dtype=dtype, device=ps[0].device) if ps else None
+        self._shadow_views, off = [], 0
+        for p in ps:
+            self._shadow_views.append(flat[off:off + p.numel()].view(p.shape))
+            off += (p.numel() + 7) // 8 * 8
+
     def _fwd_bwd(self, images: Tensor, labels: Tensor) -> Tensor:
-        logits = self.model(images)
-        loss = seg_loss(logits, labels, self.n_classes)
-        loss.backward()
+        if self._shadow_src:                                     # one multi-tensor fp32 -> compute-dtype copy per step
+            torch._foreach_copy_(self._shadow_views, [p.detach() for p in self._shadow_src])
+            ag.SHADOW = {id(p): v for p, v in zip(self._shadow_src, self._shadow_views)}
+        if self._pool is not None:
+            self._pool.reset()
+            ag.POOL = self._pool
+        try:
+            logits = self.model(images)
+            loss = seg_loss(logits, labels, self.n_classes)
+            loss.backward()
+        finally:
+            ag.SHADOW = {}
+            ag.POOL = None
         return loss.detach()
 
     def _eager(self, images: Tensor, labels: Tensor) -> Tensor:
