@@ -226,7 +226,12 @@ __global__ void __launch_bounds__(256) col2im_tokens_kernel(const T* __restrict_
 // Kernel A (one warp per low-res pixel): kappa (recomputed), d kappa[ae][t] = <dy[ae], z^[t]>, d enc through the softmax,
 //          kappa saved to `kws` (pix, s2, 9) for kernel B, d bias partial sums.
 // Kernel B (one warp per low-res pixel p'): dz[p'] = sum_t sum_ae kappa[p'-off(t)][ae][t] * dy[p'-off(t), ae]  (gather).
-template <typename T, typename TG>
+// Kernel A.  One warp per low-res pixel, persistent over pixels.  Lane = (sub-pixel ae, channel group g): s2 = up^2
+// sub-pixels x G = 32/s2 groups of CPL = C/G channels.  Each lane reads its CPL channels of dy[ae] once (vector loads),
+// forms its share of d kappa[ae][t] = <dy[ae], z^[t]> against the 9 neighbour rows of z, the G partial sums of a
+// sub-pixel are combined with log2(G) shuffles, and the lane with g == 0 applies the softmax backward and writes d enc and
+// kappa.  d bias is accumulated in registers across all pixels of the warp and flushed once.
+template <typename T, typename TG, int CPL>
 __global__ void __launch_bounds__(256) carafe_bwd_a_kernel(const T* __restrict__ enc, int64_t ldenc, const T* __restrict__ z,
                                                             int64_t ldz, const TG* __restrict__ dy, int64_t sb, int64_t sy,
                                                             int64_t sx, int64_t sc, T* __restrict__ denc, int64_t lddenc,
@@ -234,15 +239,37 @@ __global__ void __launch_bounds__(256) carafe_bwd_a_kernel(const T* __restrict__
                                                             int H, int W, int C, int up) {
   extern __shared__ float sdb[];                 // [C] per-CTA d bias
   const int lane = threadIdx.x & 31;
-  const int s2 = up * up;
+  const int s2 = up * up, G = 32 / s2;
+  const int ae = lane / G, g = lane - ae * G;
+  const int c0 = g * CPL;
   for (int c = threadIdx.x; c < C; c += blockDim.x) sdb[c] = 0.f;
   __syncthreads();
-  const int64_t pix = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (pix < npix) {
+  float dbacc[CPL];
+#pragma unroll
+  for (int j = 0; j < CPL; ++j) dbacc[j] = 0.f;
+  const int64_t wstride = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t pix = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); pix < npix; pix += wstride) {
     const int x0 = (int)(pix % W), y0 = (int)((pix / W) % H);
     const int64_t b = pix / ((int64_t)W * H);
-    for (int ae = 0; ae < s2; ++ae) {
-      const int oy = y0 * up + ae / up, ox = x0 * up + ae % up;
+    const int oy = y0 * up + ae / up, ox = x0 * up + ae % up;
+    float gv[CPL];
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) { gv[j] = ldf(dy + b * sb + oy * sy + ox * sx + (int64_t)(c0 + j) * sc); dbacc[j] += gv[j]; }
+    float dk[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      dk[t] = 0.f;
+      const int yy = y0 + t / 3 - 1, xx = x0 + t % 3 - 1;
+      if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+        const T* zr = z + ((b * H + yy) * W + xx) * ldz + c0;
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) dk[t] = fmaf(gv[j], ldf(zr + j), dk[t]);
+      }
+    }
+    for (int o = G >> 1; o > 0; o >>= 1)
+#pragma unroll
+      for (int t = 0; t < 9; ++t) dk[t] += __shfl_xor_sync(0xffffffffu, dk[t], o);
+    if (g == 0) {
       float k[9];
       float mx = -INFINITY;
 #pragma unroll
@@ -251,57 +278,52 @@ __global__ void __launch_bounds__(256) carafe_bwd_a_kernel(const T* __restrict__
 #pragma unroll
       for (int t = 0; t < 9; ++t) { k[t] = expf(k[t] - mx); sum += k[t]; }
       const float inv = 1.0f / sum;
-      float dk[9];
-#pragma unroll
-      for (int t = 0; t < 9; ++t) { k[t] *= inv; dk[t] = 0.f; }
-      for (int c = lane; c < C; c += 32) {
-        const float g = ldf(dy + b * sb + oy * sy + ox * sx + c * sc);
-        atomicAdd(&sdb[c], g);
-#pragma unroll
-        for (int t = 0; t < 9; ++t) {
-          const int yy = y0 + t / 3 - 1, xx = x0 + t % 3 - 1;
-          if (yy >= 0 && yy < H && xx >= 0 && xx < W) dk[t] = fmaf(g, ldf(z + ((b * H + yy) * W + xx) * ldz + c), dk[t]);
-        }
-      }
       float dot = 0.f;
 #pragma unroll
-      for (int t = 0; t < 9; ++t) { dk[t] = warp_sum(dk[t]); dot = fmaf(k[t], dk[t], dot); }
-      if (lane < 9) {
-        float kv = 0.f, dv = 0.f;
+      for (int t = 0; t < 9; ++t) { k[t] *= inv; dot = fmaf(k[t], dk[t], dot); }
 #pragma unroll
-        for (int t = 0; t < 9; ++t) if (t == lane) { kv = k[t]; dv = dk[t]; }
-        stf(denc + pix * lddenc + lane * s2 + ae, kv * (dv - dot));
-        kws[(pix * s2 + ae) * 9 + lane] = kv;
+      for (int t = 0; t < 9; ++t) {
+        stf(denc + pix * lddenc + t * s2 + ae, k[t] * (dk[t] - dot));
+        kws[(pix * s2 + ae) * 9 + t] = k[t];
       }
     }
   }
+#pragma unroll
+  for (int j = 0; j < CPL; ++j) atomicAdd(&sdb[c0 + j], dbacc[j]);
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) if (sdb[c] != 0.f) atomicAdd(dbias + c, sdb[c]);
 }
 
-template <typename T, typename TG>
+// Kernel B (gather).  One warp per low-res pixel p', lane owns V = C/32 channels; UP is a template parameter so that the
+// 9 x UP^2 (kappa, dy) pairs are fully unrolled and their loads overlap.
+template <typename T, typename TG, int UP, int V>
 __global__ void __launch_bounds__(256) carafe_bwd_b_kernel(const TG* __restrict__ dy, int64_t sb, int64_t sy, int64_t sx,
                                                             int64_t sc, const float* __restrict__ kws, T* __restrict__ dz,
-                                                            int64_t lddz, int64_t npix, int H, int W, int C, int up) {
+                                                            int64_t lddz, int64_t npix, int H, int W, int C) {
+  constexpr int s2 = UP * UP;
   const int lane = threadIdx.x & 31;
-  const int s2 = up * up;
   const int64_t pix = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (pix >= npix) return;
   const int x0 = (int)(pix % W), y0 = (int)((pix / W) % H);
   const int64_t b = pix / ((int64_t)W * H);
-  for (int c = lane; c < C; c += 32) {
-    float acc = 0.f;
-    for (int t = 0; t < 9; ++t) {
-      const int py = y0 - (t / 3 - 1), px = x0 - (t % 3 - 1);          // the pixel whose tap t reads (y0, x0)
-      if (py < 0 || py >= H || px < 0 || px >= W) continue;
-      const int64_t pp = (b * H + py) * W + px;
-      for (int ae = 0; ae < s2; ++ae) {
-        const int oy = py * up + ae / up, ox = px * up + ae % up;
-        acc = fmaf(kws[(pp * s2 + ae) * 9 + t], ldf(dy + b * sb + oy * sy + ox * sx + c * sc), acc);
-      }
+  float acc[V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) acc[j] = 0.f;
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const int py = y0 - (t / 3 - 1), px = x0 - (t % 3 - 1);          // the pixel whose tap t reads (y0, x0)
+    if (py < 0 || py >= H || px < 0 || px >= W) continue;
+    const int64_t pp = (b * H + py) * W + px;
+#pragma unroll
+    for (int ae = 0; ae < s2; ++ae) {
+      const float kv = kws[(pp * s2 + ae) * 9 + t];
+      const TG* src = dy + b * sb + (int64_t)(py * UP + ae / UP) * sy + (int64_t)(px * UP + ae % UP) * sx + (int64_t)(lane * V) * sc;
+#pragma unroll
+      for (int j = 0; j < V; ++j) acc[j] = fmaf(kv, ldf(src + j * sc), acc[j]);
     }
-    stf(dz + pix * lddz + c, acc);
   }
+#pragma unroll
+  for (int j = 0; j < V; ++j) stf(dz + pix * lddz + lane * V + j, acc[j]);
 }
 
 unsigned grid_for(int64_t total, int per_cta) {
@@ -390,31 +412,46 @@ int col2im_tokens(const void* dcol, int64_t ldcol, void* dx, int64_t x_bs, int64
   return CSWIN_OK;
 }
 
+namespace {
+template <typename T, typename TG>
+int carafe_bwd_launch(const void* enc, int64_t ldenc, const void* z, int64_t ldz, const void* dy, int64_t sb, int64_t sy,
+                      int64_t sx, int64_t sc, void* denc, int64_t lddenc, void* dz, int64_t lddz, float* dbias, float* kws,
+                      int64_t npix, int H, int W, int C, int up, cudaStream_t s) {
+  const int G = 32 / (up * up), cpl = C / G, v = C / 32;
+  const unsigned ga = (unsigned)std::min<int64_t>(ceil_div64(npix, 8), (int64_t)sm_count() * 8);
+  const unsigned gb = (unsigned)ceil_div64(npix, 8);
+  const size_t smem = sizeof(float) * C;
+#define CSWIN_CA(CPL) carafe_bwd_a_kernel<T, TG, CPL><<<ga, 256, smem, s>>>((const T*)enc, ldenc, (const T*)z, ldz, (const TG*)dy, sb, sy, sx, sc, (T*)denc, lddenc, kws, dbias, npix, H, W, C, up)
+  if (cpl == 8) CSWIN_CA(8); else if (cpl == 16) CSWIN_CA(16); else if (cpl == 32) CSWIN_CA(32); else if (cpl == 64) CSWIN_CA(64);
+  else { set_error("carafe_reassemble_bwd: C=%d with up=%d is not supported", C, up); return CSWIN_ERR_UNSUPPORTED; }
+#undef CSWIN_CA
+  CSWIN_LAUNCH_CHECK();
+#define CSWIN_CB(UP, V) carafe_bwd_b_kernel<T, TG, UP, V><<<gb, 256, 0, s>>>((const TG*)dy, sb, sy, sx, sc, kws, (T*)dz, lddz, npix, H, W, C)
+  if (up == 2 && v == 2) CSWIN_CB(2, 2); else if (up == 2 && v == 4) CSWIN_CB(2, 4); else if (up == 2 && v == 8) CSWIN_CB(2, 8);
+  else if (up == 4 && v == 2) CSWIN_CB(4, 2); else if (up == 4 && v == 4) CSWIN_CB(4, 4); else if (up == 2 && v == 1) CSWIN_CB(2, 1);
+  else if (up == 4 && v == 1) CSWIN_CB(4, 1);
+  else { set_error("carafe_reassemble_bwd: C=%d with up=%d is not supported", C, up); return CSWIN_ERR_UNSUPPORTED; }
+#undef CSWIN_CB
+  CSWIN_LAUNCH_CHECK();
+  return CSWIN_OK;
+}
+}  // namespace
+
 int carafe_reassemble_bwd(const void* enc, int64_t ldenc, const void* z, int64_t ldz, const void* dy, int dy_is_f32,
                           int64_t sb, int64_t sy, int64_t sx, int64_t sc, void* denc, int64_t lddenc, void* dz, int64_t lddz,
                           float* dbias, float* kws, int B, int H, int W, int C, int up, int dtype, cudaStream_t s) {
   CSWIN_REQUIRE(enc && z && dy && denc && dz && dbias && kws, CSWIN_ERR_INVALID, "carafe_reassemble_bwd: null pointer");
-  CSWIN_REQUIRE(up >= 1 && C > 0 && C <= 4096, CSWIN_ERR_UNSUPPORTED, "carafe_reassemble_bwd: bad up / C");
+  CSWIN_REQUIRE((up == 2 || up == 4) && C >= 32 && C % 32 == 0 && C <= 256, CSWIN_ERR_UNSUPPORTED,
+                "carafe_reassemble_bwd: supported: up in {2,4}, C a multiple of 32 up to 256 (got up=%d C=%d)", up, C);
   const int64_t npix = (int64_t)B * H * W;
   if (npix == 0) return CSWIN_OK;
-  const unsigned grid = (unsigned)ceil_div64(npix, 8);
-  const size_t smem = sizeof(float) * C;
   if (dtype == CSWIN_F32) {
     CSWIN_REQUIRE(dy_is_f32, CSWIN_ERR_INVALID, "carafe_reassemble_bwd: fp32 path needs fp32 dy");
-    carafe_bwd_a_kernel<float, float><<<grid, 256, smem, s>>>((const float*)enc, ldenc, (const float*)z, ldz, (const float*)dy, sb, sy, sx, sc, (float*)denc, lddenc, kws, dbias, npix, H, W, C, up);
-    CSWIN_LAUNCH_CHECK();
-    carafe_bwd_b_kernel<float, float><<<grid, 256, 0, s>>>((const float*)dy, sb, sy, sx, sc, kws, (float*)dz, lddz, npix, H, W, C, up);
-  } else if (dy_is_f32) {
-    carafe_bwd_a_kernel<__nv_bfloat16, float><<<grid, 256, smem, s>>>((const __nv_bfloat16*)enc, ldenc, (const __nv_bfloat16*)z, ldz, (const float*)dy, sb, sy, sx, sc, (__nv_bfloat16*)denc, lddenc, kws, dbias, npix, H, W, C, up);
-    CSWIN_LAUNCH_CHECK();
-    carafe_bwd_b_kernel<__nv_bfloat16, float><<<grid, 256, 0, s>>>((const float*)dy, sb, sy, sx, sc, kws, (__nv_bfloat16*)dz, lddz, npix, H, W, C, up);
-  } else {
-    carafe_bwd_a_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, smem, s>>>((const __nv_bfloat16*)enc, ldenc, (const __nv_bfloat16*)z, ldz, (const __nv_bfloat16*)dy, sb, sy, sx, sc, (__nv_bfloat16*)denc, lddenc, kws, dbias, npix, H, W, C, up);
-    CSWIN_LAUNCH_CHECK();
-    carafe_bwd_b_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)dy, sb, sy, sx, sc, kws, (__nv_bfloat16*)dz, lddz, npix, H, W, C, up);
+    return carafe_bwd_launch<float, float>(enc, ldenc, z, ldz, dy, sb, sy, sx, sc, denc, lddenc, dz, lddz, dbias, kws, npix, H, W, C, up, s);
   }
-  CSWIN_LAUNCH_CHECK();
-  return CSWIN_OK;
+  if (dy_is_f32)
+    return carafe_bwd_launch<__nv_bfloat16, float>(enc, ldenc, z, ldz, dy, sb, sy, sx, sc, denc, lddenc, dz, lddz, dbias, kws, npix, H, W, C, up, s);
+  return carafe_bwd_launch<__nv_bfloat16, __nv_bfloat16>(enc, ldenc, z, ldz, dy, sb, sy, sx, sc, denc, lddenc, dz, lddz, dbias, kws, npix, H, W, C, up, s);
 }
 
 }  // namespace cswin
