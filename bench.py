@@ -35,7 +35,10 @@ METRIC = "CSWin-UNet-tiny 224^2 slices/sec (bf16 fwd)"
 UNIT = "slices/s"
 BATCH = 24
 GFLOP_PER_SLICE_FWD = 10.028       # BASELINE.md section 2 (FlopCounterMode on the unmodified reference)
-ATTN_DRAM_TRAFFIC_PER_FORWARD = None   # bytes, from the ncu --set full capture in profiles/ (per forward at batch 24); None = not captured yet
+# dram__bytes_read.sum + dram__bytes_write.sum of lepe_attn_fwd_tc_kernel, ncu --set full, batch 24, summed over the 26 launches
+# of one forward (2 x 28.95 MB + 4 x 14.50 MB + 18 x 7.28 MB + 2 x 3.67 MB read, ~0 written inside the kernel: the output
+# stays in L2): profiles/r01_ncu_full_summary_v2.txt.  Reads equal the algorithmic q,k,v bytes exactly (no re-reads).
+ATTN_DRAM_TRAFFIC_PER_FORWARD = 254_194_000
 
 
 def peaks():

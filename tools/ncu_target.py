@@ -23,6 +23,13 @@ if kind == "attn":
     else:
         descs = [blk.attns[0].branch_desc(q, k, v, out)]
     fn = lambda: ops.lepe_attention_fwd(descs, B, reso, float(blk.attns[0].scale), torch.bfloat16)
+elif kind == "block_train":          # forward + backward of one CSWinBlock (bf16): attention fwd/bwd, Linear fwd/dgrad/wgrad ...
+    stage, B = int(sys.argv[2]), int(sys.argv[3])
+    C, reso, heads, split, last = [(64, 56, 2, 1, False), (128, 28, 4, 2, False), (256, 14, 8, 7, False), (512, 7, 16, 7, True)][stage - 1]
+    blk = cw.CSWinBlock(dim=C, reso=reso, num_heads=heads, split_size=split, qkv_bias=True, last_stage=last).to(DEV).train()
+    x = torch.randn(B, reso * reso, C, device=DEV, dtype=torch.bfloat16, requires_grad=True)
+    def fn():
+        y = blk(x); y.sum().backward()
 else:
     M, N, K = int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])
     act = int(sys.argv[5]) if len(sys.argv) > 5 else 0
