@@ -31,9 +31,10 @@ def gather_label_shards(local: Tensor, n_total: int, group=None) -> Tensor:
     return torch.cat(out, dim=0)
 
 
-def allreduce_gradients(params: Iterable[Tensor], group=None, bucket_bytes: int = 25 << 20, average: bool = True) -> int:
-    """Bucketed gradient all-reduce (sum, then / world): flattens grads in REVERSE parameter order (the order backward
-    produces them) into ~25 MB buckets, one NCCL all-reduce per bucket.  Returns the number of collectives issued."""
+def allreduce_gradients(params: Iterable[Tensor], group=None, bucket_bytes: int = 32 << 20, average: bool = True) -> int:
+    """Bucketed gradient all-reduce (sum, then / world).  Gradients are packed in REVERSE parameter order (the order the
+    backward produces them) into flat ~32 MB buckets with one multi-tensor copy per bucket, reduced with one NCCL
+    all-reduce per bucket, and unpacked with one multi-tensor copy.  Returns the number of collectives issued."""
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         return 0
     world = dist.get_world_size(group)
@@ -45,12 +46,14 @@ def allreduce_gradients(params: Iterable[Tensor], group=None, bucket_bytes: int 
         dtype = grads[i].dtype
         while i < len(grads) and grads[i].dtype == dtype and (not bucket or size + grads[i].numel() * grads[i].element_size() <= bucket_bytes):
             bucket.append(grads[i]); size += grads[i].numel() * grads[i].element_size(); i += 1
-        flat = torch.cat([g.reshape(-1) for g in bucket])
+        flat = torch.empty(sum(g.numel() for g in bucket), dtype=dtype, device=bucket[0].device)
+        views, off = [], 0
+        for g in bucket:
+            views.append(flat[off: off + g.numel()].view(g.shape)); off += g.numel()
+        torch._foreach_copy_(views, bucket)
         dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
         if average:
             flat.div_(world)
-        off = 0
-        for g in bucket:
-            g.copy_(flat[off: off + g.numel()].view_as(g)); off += g.numel()
+        torch._foreach_copy_(bucket, views)
         n_coll += 1
     return n_coll

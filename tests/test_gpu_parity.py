@@ -396,3 +396,19 @@ def test_linear_kn_weight_layout(dtype, tol, M, N, K):
     y = ops.linear(a.to(DEV), wfull.to(DEV)[:, 8:8 + N], None, w_kn=True)
     ref = a.double() @ w.double()
     assert y.shape == (M, N) and (y.cpu().double() - ref).abs().max().item() <= tol
+
+
+def test_512px_config_blocks_fp32_and_bf16_vs_oracle():
+    """BASELINE configs[4]: 512^2 input with split [1,2,8,8] -> stripe windows of 128 / 128 / 256 / 256 tokens.  Windows of
+    256 tokens are outside the tcgen05 attention envelope (N <= 128) and must still be exact on the general SIMT kernel."""
+    for (dim, reso, heads, split, last) in ((64, 128, 2, 1, False), (256, 32, 8, 8, False), (512, 16, 16, 8, True)):
+        m = cw.CSWinBlock(dim=dim, reso=reso, num_heads=heads, split_size=split, qkv_bias=True, last_stage=last).to(DEV).eval()
+        load_named(m, f"block512/{dim}/", 3)
+        x = T(synth.synth_tensor(f"block512_in/{dim}", (1, reso * reso, dim), 4))
+        sd = {k: v.detach().cpu().double() for k, v in m.state_dict().items()}
+        ref = O.cswin_block(sd, "", x.cpu().double(), reso, heads, split, last)
+        with torch.no_grad():
+            y32 = m(x).cpu().double()
+            y16 = m(x.bfloat16()).float().cpu().double()
+        assert (y32 - ref).abs().max().item() <= 1e-4, dim
+        assert (y16 - ref).abs().max().item() <= 2e-1, dim
