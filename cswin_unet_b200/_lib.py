@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(_HERE, "libcswin_b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "cswin_b200.h")
 
 F32, BF16 = 0, 1
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 c_void_p, c_int32, c_int64, c_float = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 
@@ -56,10 +56,22 @@ class LinearArgs(C.Structure):
         ("out", c_void_p), ("ldo", c_int64),
         ("M", c_int64), ("N", c_int32),
         ("act", c_int32), ("w_layout", c_int32),
+        ("ln_stats", c_void_p), ("ln_stats_parts", c_int32), ("ln_C", c_int32),
+        ("ln_colsum", c_void_p), ("bias_f32", c_void_p), ("stats_out", c_void_p),
     ]
 
 
 # symbol -> (restype, argtypes); every symbol include/cswin_b200.h declares
+class MlpArgs(C.Structure):
+    """== cswin_mlp_args_t"""
+    _fields_ = [
+        ("x", c_void_p), ("ldx", c_int64), ("w1", c_void_p), ("ldw1", c_int64), ("ln_colsum", c_void_p), ("b1", c_void_p),
+        ("w2", c_void_p), ("ldw2", c_int64), ("b2", c_void_p), ("ln_stats", c_void_p), ("ln_stats_parts", c_int32),
+        ("ln_eps", C.c_float), ("out", c_void_p), ("ldo", c_int64), ("stats_out", c_void_p), ("M", c_int64),
+        ("C", c_int32), ("hidden", c_int32),
+    ]
+
+
 SIGNATURES = {
     "cswin_abi_version": (c_int32, []),
     "cswin_last_error": (C.c_char_p, []),
@@ -71,6 +83,10 @@ SIGNATURES = {
     "cswin_layernorm_fwd": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int32,
                                       c_float, c_void_p, c_void_p, c_int32, c_void_p]),
     "cswin_linear_fwd": (c_int32, [C.POINTER(LinearArgs), c_int32, c_void_p]),
+    "cswin_mlp_fwd": (c_int32, [C.POINTER(MlpArgs), c_int32, c_void_p]),
+    "cswin_mlp_stats_parts": (c_int32, [c_int32, c_int32]),
+    "cswin_linear_stats_parts": (c_int32, [c_int64, c_int32, c_int32, c_int32]),
+    "cswin_row_stats": (c_int32, [c_void_p, c_int64, c_int64, c_int32, c_void_p, c_int32, c_void_p]),
     "cswin_im2col_tokens": (c_int32, [c_void_p, c_int64, c_int64, c_void_p, c_int64] + [c_int32] * 9 + [c_void_p]),
     "cswin_im2col_nchw": (c_int32, [c_void_p, c_int32, c_void_p, c_int64] + [c_int32] * 9 + [c_void_p]),
     "cswin_act_fwd": (c_int32, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int32, c_int32, c_int32, c_void_p]),

@@ -107,11 +107,16 @@ int cswin_linear_fwd(const cswin_linear_args_t* a, int32_t dtype, cswin_stream_t
   CSWIN_REQUIRE(!a->sample_scale || a->rows_per_sample > 0, CSWIN_ERR_INVALID, "linear_fwd: rows_per_sample must be > 0");
   CSWIN_REQUIRE(a->act == 0 || a->act == 1, CSWIN_ERR_INVALID, "linear_fwd: act must be 0 (none) or 1 (GELU)");
   if (a->M == 0) return CSWIN_OK;
+  const bool folded = a->ln_colsum || a->ln_stats || a->stats_out || a->bias_f32;
+  CSWIN_REQUIRE(!folded || dtype == CSWIN_BF16, CSWIN_ERR_UNSUPPORTED, "linear_fwd: LayerNorm folding / stats_out / bias_f32 exist on the bf16 path only");
+  CSWIN_REQUIRE((a->ln_colsum != nullptr) == (a->ln_stats != nullptr), CSWIN_ERR_INVALID, "linear_fwd: ln_stats and ln_colsum must be given together");
+  CSWIN_REQUIRE(!a->ln_stats || (a->ln_stats_parts > 0 && a->ln_C > 0 && !a->a2 && !a->ln_gamma), CSWIN_ERR_INVALID, "linear_fwd: bad folded-LayerNorm arguments");
   if (dtype == CSWIN_BF16) {
     bool handled = false;
     int rc = linear_fwd_tc(a, (cudaStream_t)stream, &handled);
     if (rc != CSWIN_OK || handled) return rc;
   }
+  CSWIN_REQUIRE(!folded, CSWIN_ERR_UNSUPPORTED, "linear_fwd: operands are not TMA-compatible (16-byte aligned pointers / row pitches), which the folded-LayerNorm form requires");
   return linear_fwd_simt(a, dtype, (cudaStream_t)stream);
 }
 
@@ -194,6 +199,24 @@ int cswin_carafe_reassemble_bwd(const void* enc, int64_t ldenc, const void* z, i
   CSWIN_REQUIRE(valid_dtype(dtype) && B >= 0 && H > 0 && W > 0, CSWIN_ERR_INVALID, "carafe_reassemble_bwd: bad arguments");
   return carafe_reassemble_bwd(enc, ldenc, z, ldz, dy, dy_is_f32, dy_sb, dy_sy, dy_sx, dy_sc, denc, lddenc, dz, lddz, dbias,
                                kappa_ws, B, H, W, C, up, dtype, (cudaStream_t)stream);
+}
+
+int cswin_mlp_fwd(const cswin_mlp_args_t* a, int32_t dtype, cswin_stream_t stream) {
+  CSWIN_REQUIRE(a != nullptr, CSWIN_ERR_INVALID, "mlp_fwd: null args");
+  CSWIN_REQUIRE(dtype == CSWIN_BF16, CSWIN_ERR_UNSUPPORTED, "mlp_fwd: the fused MLP exists on the bf16 / tcgen05 path only");
+  CSWIN_REQUIRE(a->x && a->w1 && a->w2 && a->b1 && a->b2 && a->ln_colsum && a->ln_stats && a->out && a->M >= 0 && a->C > 0 &&
+                a->hidden > 0 && a->ln_stats_parts > 0 && a->ldx >= a->C && a->ldo >= a->C && a->ldw1 >= a->C && a->ldw2 >= a->hidden,
+                CSWIN_ERR_INVALID, "mlp_fwd: bad arguments");
+  return mlp_fwd_tc(a, (cudaStream_t)stream);
+}
+
+int32_t cswin_mlp_stats_parts(int32_t C, int32_t hidden) { return mlp_tc_stats_parts(C, hidden); }
+
+int32_t cswin_linear_stats_parts(int64_t M, int32_t N, int32_t K, int32_t act) { return linear_tc_stats_parts(M, N, K, act); }
+
+int cswin_row_stats(const void* x, int64_t ldx, int64_t M, int32_t C, float* stats, int32_t dtype, cswin_stream_t stream) {
+  CSWIN_REQUIRE(valid_dtype(dtype) && M >= 0, CSWIN_ERR_INVALID, "row_stats: bad arguments");
+  return row_stats(x, ldx, M, C, stats, dtype, (cudaStream_t)stream);
 }
 
 }  // extern "C"

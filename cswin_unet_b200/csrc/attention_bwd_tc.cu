@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(kThr, 2) lepe_attn_bwd_tc_kernel(const __grid_
   const uint32_t tmem_base = *tmem_slot;
   if (tid == 0) trace_stamp(P.trace, 1);
 
-  if (tid == 0) {
+  if (warp == 0 && elect_one()) {     // one elected lane, warp-uniform datapath for the TMA / tcgen05 issue
     mbar_expect_tx(bar_tma, (uint32_t)(np * 4 * N * kRowB));
     for (int s = 0; s < np; ++s) {
       int local = p0 + s;
@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(kThr, 2) lepe_attn_bwd_tc_kernel(const __grid_
   tc_fence_before();
   __syncthreads();                                      // S / dP fully consumed; P / dS visible to the tensor core
 
-  if (tid == 0) {
+  if (warp == 0 && elect_one()) {     // one elected lane, warp-uniform datapath for the TMA / tcgen05 issue
     trace_stamp(P.trace, 3);
     tc_fence_after();
     const uint32_t id_mn = make_idesc_bf16(128, 32, 1, 1);      // A = P / dS read MN-major (kv rows out), B MN-major

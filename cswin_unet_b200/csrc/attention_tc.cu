@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(kThreads, 3) lepe_attn_fwd_tc_kernel(const __g
   if (tid == 0) trace_stamp(P.trace, 1);                     // prologue done
   pdl_wait();                                                // q, k, v (previous kernel's output) and `out` are safe from here
 
-  if (tid == 0) {
+  if (warp == 0 && elect_one()) {     // one elected lane, warp-uniform datapath for the TMA / tcgen05 issue
     mbar_expect_tx(bar_tma, (uint32_t)(np * 3 * N * kRowBytes));
     for (int s = 0; s < np; ++s) {
       int local = p0 + s;
@@ -238,7 +238,7 @@ __global__ void __launch_bounds__(kThreads, 3) lepe_attn_fwd_tc_kernel(const __g
   tc_fence_before();
   __syncthreads();
 
-  if (tid == 0) {
+  if (warp == 0 && elect_one()) {     // one elected lane, warp-uniform datapath for the TMA / tcgen05 issue
     trace_stamp(P.trace, 4);                                 // P published
     tc_fence_after();
     const uint64_t vd = make_smem_desc(smem_u32(Vs), 8 * kRowBytes, 8 * kRowBytes, kLayoutSw64);

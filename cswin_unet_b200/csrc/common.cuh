@@ -98,6 +98,10 @@ int lepe_attention_bwd_tc(const cswin_lepe_branch_grad_t* br, int nb, int B, int
 int lepe_attention_bwd_simt(const cswin_lepe_branch_grad_t* br, int nb, int B, int reso, float scale, int dtype, cudaStream_t s);
 int layernorm_fwd(const void* x, int64_t ldx, const void* g, const void* b, void* y, int64_t ldy, int64_t M, int C,
                   float eps, float* mean, float* rstd, int dtype, cudaStream_t s);
+int row_stats(const void* x, int64_t ldx, int64_t M, int C, float* stats, int dtype, cudaStream_t s);
+int mlp_fwd_tc(const cswin_mlp_args_t* a, cudaStream_t stream);
+int mlp_tc_stats_parts(int C, int hidden);
+int linear_tc_stats_parts(int64_t M, int N, int K, int act);
 int linear_fwd_simt(const cswin_linear_args_t* a, int dtype, cudaStream_t s);
 int linear_fwd_tc(const cswin_linear_args_t* a, cudaStream_t s, bool* handled);
 int im2col_tokens(const void* x, int64_t x_bs, int64_t x_ts, void* col, int64_t ldcol, int B, int H, int W, int C, int KH,

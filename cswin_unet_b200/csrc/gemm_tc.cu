@@ -38,24 +38,12 @@ struct alignas(64) GemmTcParams {
   __nv_bfloat16* out; int64_t ldo;
   int64_t M; int N; int K1; int K2;
   int BN, stages, nkb, nkb1, act, tmem_cols, vec_ok, bias_vec, w_kn;
+  const float* ln_stats; int ln_parts; float ln_invC, ln_eps;
+  const float* ln_cs; const float* bias_f32; float* stats_out;
   unsigned long long* trace;
 };
 
-// GELU(erf) for the bf16 epilogue: x * Phi(x) with Phi(x) = 0.5 (1 + tanh(x (c0 + c1 x^2 + c2 x^4 + c3 x^6))), the odd
-// degree-7 minimax fit of atanh(erf(x / sqrt 2)) (max |dPhi| = 6.6e-6, max |dGELU| = 2.4e-5 over all x) evaluated with one
-// MUFU op (tanh.approx, relative error 2^-11): total error <= 2.5e-4 |x|, i.e. >= 16x below bf16 resolution, for
-// 7 FMA-pipe instructions + 1 MUFU instead of erff's ~40.  The fp32 SIMT path keeps erff.
-__device__ __forceinline__ float gelu_fast(float x) {
-  const float x2 = x * x;
-  float p = fmaf(x2, -1.36882761e-05f, -1.94451094e-04f);
-  p = fmaf(p, x2, 3.65466544e-02f);
-  p = fmaf(p, x2, 7.97820264e-01f);
-  float t;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(p * x));
-  const float h = 0.5f * x;
-  return fmaf(h, t, h);
-}
-
+template <bool kFold, bool kStats>
 __global__ void __launch_bounds__(kThreads, 2) linear_tc_kernel(const __grid_constant__ GemmTcParams P) {
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for the 128-byte swizzle; plain pointer arithmetic keeps the shared address space (LDS/STS)
@@ -69,7 +57,9 @@ __global__ void __launch_bounds__(kThreads, 2) linear_tc_kernel(const __grid_con
   uint8_t* Epi = smem;
   const size_t ring = (size_t)S * (a_bytes + w_bytes);
   float* sBias = reinterpret_cast<float*>(smem + ring);                  // [256] fp32
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + 256);
+  float* sCs = sBias + 256;                                              // [256] folded-LayerNorm column sums
+  float* sStat = sCs + 256;                                              // [128][2] per-row (sum, sum^2) of this tile's output
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sStat + 256);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -92,7 +82,10 @@ __global__ void __launch_bounds__(kThreads, 2) linear_tc_kernel(const __grid_con
   if (warp == 1) { tmem_alloc(smem_u32(tmem_slot), (uint32_t)P.tmem_cols); tmem_relinquish(); }
   if (warp >= 2) {                                      // bias of this tile's columns -> smem (fp32)
     const int j = tid - 64, n = n0 + j;
-    sBias[j] = (P.bias != nullptr && j < BN && n < P.N) ? __bfloat162float(P.bias[n]) : 0.f;
+    const bool in = j < BN && n < P.N;
+    sBias[j] = !in ? 0.f : P.bias_f32 != nullptr ? P.bias_f32[n] : P.bias != nullptr ? __bfloat162float(P.bias[n]) : 0.f;
+    if (kFold) sCs[j] = in ? P.ln_cs[n] : 0.f;
+    if (kStats) sStat[j] = 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -102,7 +95,7 @@ __global__ void __launch_bounds__(kThreads, 2) linear_tc_kernel(const __grid_con
 
   // weights do not depend on the previous kernel: the W tiles of the first ring pass are requested before the PDL wait
   const int npre = P.nkb < S ? P.nkb : S;
-  if (warp == 0 && lane == 0) {
+  if (warp == 0 && elect_one()) {
     for (int kb = 0; kb < npre; ++kb) {
       mbar_expect_tx(full(kb), a_bytes + w_bytes);
       if (!P.w_kn) tma_load_2d(smem_u32(Ws + (size_t)kb * w_bytes), &P.map_w, full(kb), kb * BK, n0);
@@ -113,11 +106,11 @@ __global__ void __launch_bounds__(kThreads, 2) linear_tc_kernel(const __grid_con
   pdl_wait();                                           // activations (A, residual) and the output buffer are safe from here
 
   if (warp == 0) {
-    if (lane == 0) {                                    // ---- TMA producer ----
+    if (elect_one()) {                                  // ---- TMA producer (elect.sync keeps the warp-uniform datapath) ----
+      int s = 0; uint32_t ph = 1;                       // ring slot and pass parity, advanced without div / mod
       for (int kb = 0; kb < P.nkb; ++kb) {
-        const int s = kb % S;
         if (kb >= S) {
-          mbar_wait(empty(s), ((kb / S) - 1) & 1);
+          mbar_wait(empty(s), ph);
           mbar_expect_tx(full(s), a_bytes + w_bytes);
           if (!P.w_kn) tma_load_2d(smem_u32(Ws + (size_t)s * w_bytes), &P.map_w, full(s), kb * BK, n0);
           else for (int j = 0; j * 64 < BN; ++j)
@@ -125,16 +118,17 @@ __global__ void __launch_bounds__(kThreads, 2) linear_tc_kernel(const __grid_con
         }
         if (kb < P.nkb1) tma_load_2d(smem_u32(As + (size_t)s * a_bytes), &P.map_a, full(s), kb * BK, (int)m0);
         else             tma_load_2d(smem_u32(As + (size_t)s * a_bytes), &P.map_a2, full(s), (kb - P.nkb1) * BK, (int)m0);
+        if (++s == S) { s = 0; ph ^= 1; }
       }
       trace_stamp(P.trace, 2);                          // all TMA issued
     }
   } else if (warp == 1) {
-    if (lane == 0) {                                    // ---- MMA issuer ----
+    if (elect_one()) {                                  // ---- MMA issuer ----
       const uint32_t idesc = make_idesc_bf16(BM, BN, 0, P.w_kn);
       const uint32_t wstep = P.w_kn ? (2048 >> 4) : 2;   // 16 contraction rows: 2 KB (MN-major) or 32 B (K-major) further
+      int s = 0; uint32_t ph = 0;
       for (int kb = 0; kb < P.nkb; ++kb) {
-        const int s = kb % S;
-        mbar_wait(full(s), (kb / S) & 1);
+        mbar_wait(full(s), ph);
         if (kb == 0) trace_stamp(P.trace, 3);           // first operands landed
         tc_fence_after();
         const uint64_t ad = make_smem_desc(smem_u32(As + (size_t)s * a_bytes), 16, 1024, kLayoutSw128);
@@ -142,6 +136,7 @@ __global__ void __launch_bounds__(kThreads, 2) linear_tc_kernel(const __grid_con
 #pragma unroll
         for (int k = 0; k < BK / 16; ++k) mma_ss(tmem_base, ad + 2 * k, wd + (uint64_t)wstep * k, idesc, (kb | k) != 0);
         tc_commit(empty(s));                            // smem slot reusable once these MMAs have read it
+        if (++s == S) { s = 0; ph ^= 1; }
       }
       tc_commit(bar_acc);                               // accumulator complete
       trace_stamp(P.trace, 4);                          // all MMAs issued
@@ -156,6 +151,13 @@ __global__ void __launch_bounds__(kThreads, 2) linear_tc_kernel(const __grid_con
     const uint32_t stg_u32 = smem_u32(stg);
     const int64_t mrow = m0 + q * 32 + lane;            // accumulator row held by this thread in phase 1
     const float sc = (P.sscale != nullptr && mrow < P.M) ? P.sscale[mrow / P.rps] : 1.0f;
+    float ln_mean = 0.f, ln_rstd = 1.f;                 // folded LayerNorm: row statistics from the producer's partial sums
+    if (kFold && mrow < P.M) {
+      float s1 = 0.f, s2 = 0.f;
+      for (int p = 0; p < P.ln_parts; ++p) { s1 += P.ln_stats[(mrow * P.ln_parts + p) * 2]; s2 += P.ln_stats[(mrow * P.ln_parts + p) * 2 + 1]; }
+      ln_mean = s1 * P.ln_invC;
+      ln_rstd = rsqrtf(fmaxf(fmaf(-ln_mean, ln_mean, s2 * P.ln_invC), 0.f) + P.ln_eps);
+    }
     const int nunits = (BN + 31) >> 5;
     mbar_wait(bar_acc, 0);
     if (warp == 2 && lane == 0) trace_stamp(P.trace, 5);  // accumulator ready
@@ -166,16 +168,25 @@ __global__ void __launch_bounds__(kThreads, 2) linear_tc_kernel(const __grid_con
       tmem_ld32(trow + u * 32, v);
       tmem_wait_ld();
       const float4* b4 = reinterpret_cast<const float4*>(sBias + u * 32);
+      const float4* c4 = reinterpret_cast<const float4*>(sCs + u * 32);
 #pragma unroll
       for (int c = 0; c < 4; ++c) {                     // four 16-byte chunks of 8 columns
         float f[8];
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           const float4 bb = b4[c * 2 + h];
-          f[h * 4 + 0] = __uint_as_float(v[c * 8 + h * 4 + 0]) + bb.x;
-          f[h * 4 + 1] = __uint_as_float(v[c * 8 + h * 4 + 1]) + bb.y;
-          f[h * 4 + 2] = __uint_as_float(v[c * 8 + h * 4 + 2]) + bb.z;
-          f[h * 4 + 3] = __uint_as_float(v[c * 8 + h * 4 + 3]) + bb.w;
+          if (kFold) {                                  // rstd * (acc - mean * colsum) + bias'
+            const float4 cc = c4[c * 2 + h];
+            f[h * 4 + 0] = fmaf(ln_rstd, fmaf(-ln_mean, cc.x, __uint_as_float(v[c * 8 + h * 4 + 0])), bb.x);
+            f[h * 4 + 1] = fmaf(ln_rstd, fmaf(-ln_mean, cc.y, __uint_as_float(v[c * 8 + h * 4 + 1])), bb.y);
+            f[h * 4 + 2] = fmaf(ln_rstd, fmaf(-ln_mean, cc.z, __uint_as_float(v[c * 8 + h * 4 + 2])), bb.z);
+            f[h * 4 + 3] = fmaf(ln_rstd, fmaf(-ln_mean, cc.w, __uint_as_float(v[c * 8 + h * 4 + 3])), bb.w);
+          } else {
+            f[h * 4 + 0] = __uint_as_float(v[c * 8 + h * 4 + 0]) + bb.x;
+            f[h * 4 + 1] = __uint_as_float(v[c * 8 + h * 4 + 1]) + bb.y;
+            f[h * 4 + 2] = __uint_as_float(v[c * 8 + h * 4 + 2]) + bb.z;
+            f[h * 4 + 3] = __uint_as_float(v[c * 8 + h * 4 + 3]) + bb.w;
+          }
         }
         if (P.act == 1) {
 #pragma unroll
@@ -190,39 +201,76 @@ __global__ void __launch_bounds__(kThreads, 2) linear_tc_kernel(const __grid_con
                      "r"(pack_bf16x2(f[2], f[3])), "r"(pack_bf16x2(f[4], f[5])), "r"(pack_bf16x2(f[6], f[7])) : "memory");
       }
       __syncwarp();
+      // 8 rows x 64 B per pass, 4 lanes per row; the four passes' shared-memory reads and residual loads are all issued
+      // before the first use so their latencies overlap
+      const int c = lane & 3;
+      const int n = n0 + u * 32 + c * 8;
+      const bool col_ok = n < P.N && u * 32 + c * 8 < BN;
+      const bool vec = P.vec_ok && n + 8 <= P.N;
+      uint4 w[4], rv[4];
 #pragma unroll
-      for (int pass = 0; pass < 4; ++pass) {            // 8 rows x 64 B per pass, 4 lanes per row
-        const int r = pass * 8 + (lane >> 2), c = lane & 3;
-        const int64_t m = m0 + q * 32 + r;
-        const int n = n0 + u * 32 + c * 8;
-        uint4 w;
-        asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w)
+      for (int pass = 0; pass < 4; ++pass) {
+        const int r = pass * 8 + (lane >> 2);
+        asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(w[pass].x), "=r"(w[pass].y), "=r"(w[pass].z), "=r"(w[pass].w)
                      : "r"(stg_u32 + r * 64 + (((c ^ (r >> 1)) & 3) << 4)));
-        if (m < P.M && n < P.N && u * 32 + c * 8 < BN) {
+      }
+      if (P.res != nullptr && vec && col_ok) {
+#pragma unroll
+        for (int pass = 0; pass < 4; ++pass) {
+          const int64_t m = m0 + q * 32 + pass * 8 + (lane >> 2);
+          rv[pass] = m < P.M ? *reinterpret_cast<const uint4*>(P.res + m * P.ldr + n) : make_uint4(0, 0, 0, 0);
+        }
+      }
+#pragma unroll
+      for (int pass = 0; pass < 4; ++pass) {
+        const int r = pass * 8 + (lane >> 2);
+        const int64_t m = m0 + q * 32 + r;
+        uint4 x = w[pass];
+        float st1 = 0.f, st2 = 0.f;
+        if (m < P.M && col_ok) {
           __nv_bfloat16* dst = P.out + m * P.ldo + n;
-          if (P.vec_ok && n + 8 <= P.N) {
+          if (vec) {
             if (P.res != nullptr) {
-              const uint4 rv = *reinterpret_cast<const uint4*>(P.res + m * P.ldr + n);
-              w.x = pack_bf16x2(bf16_lo(w.x) + bf16_lo(rv.x), bf16_hi(w.x) + bf16_hi(rv.x));
-              w.y = pack_bf16x2(bf16_lo(w.y) + bf16_lo(rv.y), bf16_hi(w.y) + bf16_hi(rv.y));
-              w.z = pack_bf16x2(bf16_lo(w.z) + bf16_lo(rv.z), bf16_hi(w.z) + bf16_hi(rv.z));
-              w.w = pack_bf16x2(bf16_lo(w.w) + bf16_lo(rv.w), bf16_hi(w.w) + bf16_hi(rv.w));
+              const uint4 y = rv[pass];
+              x.x = pack_bf16x2(bf16_lo(x.x) + bf16_lo(y.x), bf16_hi(x.x) + bf16_hi(y.x));
+              x.y = pack_bf16x2(bf16_lo(x.y) + bf16_lo(y.y), bf16_hi(x.y) + bf16_hi(y.y));
+              x.z = pack_bf16x2(bf16_lo(x.z) + bf16_lo(y.z), bf16_hi(x.z) + bf16_hi(y.z));
+              x.w = pack_bf16x2(bf16_lo(x.w) + bf16_lo(y.w), bf16_hi(x.w) + bf16_hi(y.w));
             }
-            *reinterpret_cast<uint4*>(dst) = w;
+            *reinterpret_cast<uint4*>(dst) = x;
+            if (kStats) {                               // (sum, sum^2) of the bf16 values just stored, for the next folded LN
+              const float e0 = bf16_lo(x.x), e1 = bf16_hi(x.x), e2 = bf16_lo(x.y), e3 = bf16_hi(x.y);
+              const float e4 = bf16_lo(x.z), e5 = bf16_hi(x.z), e6 = bf16_lo(x.w), e7 = bf16_hi(x.w);
+              st1 = ((e0 + e1) + (e2 + e3)) + ((e4 + e5) + (e6 + e7));
+              st2 = fmaf(e0, e0, fmaf(e1, e1, fmaf(e2, e2, fmaf(e3, e3, fmaf(e4, e4, fmaf(e5, e5, fmaf(e6, e6, e7 * e7)))))));
+            }
           } else {
-            const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+            const uint32_t ww[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
               if (n + e < P.N) {
-                float x = (e & 1) ? bf16_hi(ww[e >> 1]) : bf16_lo(ww[e >> 1]);
-                if (P.res != nullptr) x += __bfloat162float(P.res[m * P.ldr + n + e]);
-                dst[e] = __float2bfloat16_rn(x);
+                float t = (e & 1) ? bf16_hi(ww[e >> 1]) : bf16_lo(ww[e >> 1]);
+                if (P.res != nullptr) t += __bfloat162float(P.res[m * P.ldr + n + e]);
+                dst[e] = __float2bfloat16_rn(t);
               }
             }
           }
         }
+        if (kStats) {                                   // the 4 lanes of a row -> one shared-memory accumulate per row
+          st1 += __shfl_xor_sync(0xffffffffu, st1, 1); st2 += __shfl_xor_sync(0xffffffffu, st2, 1);
+          st1 += __shfl_xor_sync(0xffffffffu, st1, 2); st2 += __shfl_xor_sync(0xffffffffu, st2, 2);
+          if (c == 0) { atomicAdd(&sStat[(q * 32 + r) * 2], st1); atomicAdd(&sStat[(q * 32 + r) * 2 + 1], st2); }
+        }
       }
       __syncwarp();
+    }
+    if (kStats) {
+      asm volatile("bar.sync 1, 256;" ::: "memory");      // all 8 epilogue warps have accumulated their units
+      const int r = tid - 64;
+      if (r < BM && m0 + r < P.M) {
+        float* dst = P.stats_out + ((m0 + r) * gridDim.y + blockIdx.y) * 2;
+        dst[0] = sStat[r * 2]; dst[1] = sStat[r * 2 + 1];
+      }
     }
     if (warp == 2 && lane == 0) trace_stamp(P.trace, 6);  // epilogue done
   }
@@ -236,7 +284,7 @@ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 
 
 size_t smem_bytes(int bn, int stages) {
   const size_t ring = (size_t)stages * (BM * BK * 2 + (size_t)bn * BK * 2);     // >= 18 KB > the aliased 16 KB staging
-  return 1024 + ring + 1024 /* bias */ + 256 /* barriers, TMEM slot */;
+  return 1024 + ring + 3 * 1024 /* bias, column sums, row stats */ + 256 /* barriers, TMEM slot */;
 }
 int tmem_cols_for(int bn) { return bn <= 64 ? 64 : bn <= 128 ? 128 : 256; }      // the epilogue reads whole 64-col groups
 
@@ -278,6 +326,11 @@ TileCfg pick_tile(int64_t M, int N, int nkb, int act, int sms, bool w_kn) {
 
 }  // namespace
 
+int linear_tc_stats_parts(int64_t M, int N, int K, int act) {
+  const TileCfg cfg = pick_tile(M, N, (K + BK - 1) / BK, act, sm_count(), false);
+  return (N + cfg.bn - 1) / cfg.bn;
+}
+
 int linear_fwd_tc(const cswin_linear_args_t* a, cudaStream_t stream, bool* handled) {
   *handled = false;
   if (a->ln_gamma != nullptr) return CSWIN_OK;                               // LayerNorm prologue: SIMT kernel (host calls LN first on the bf16 path)
@@ -302,9 +355,12 @@ int linear_fwd_tc(const cswin_linear_args_t* a, cudaStream_t stream, bool* handl
   P.stages = cfg.stages;
   P.tmem_cols = tmem_cols_for(P.BN);
   P.bias_vec = a->bias != nullptr && aligned16(a->bias);
+  P.ln_stats = a->ln_stats; P.ln_parts = a->ln_stats_parts; P.ln_invC = a->ln_C > 0 ? 1.0f / (float)a->ln_C : 0.f;
+  P.ln_eps = a->ln_eps; P.ln_cs = a->ln_colsum; P.bias_f32 = a->bias_f32; P.stats_out = a->stats_out;
   P.trace = g_trace.load(std::memory_order_relaxed);
   P.vec_ok = aligned16(a->out) && (a->ldo * 2) % 16 == 0 &&
              (a->residual == nullptr || (aligned16(a->residual) && (a->ldr * 2) % 16 == 0));
+  if (a->stats_out != nullptr && !P.vec_ok) { set_error("linear_fwd: stats_out needs 16-byte aligned output rows"); return CSWIN_ERR_UNSUPPORTED; }
 
   {
     const uint64_t dims[2] = {(uint64_t)a->K1, (uint64_t)a->M};
@@ -329,13 +385,17 @@ int linear_fwd_tc(const cswin_linear_args_t* a, cudaStream_t stream, bool* handl
   }
 
   const size_t smem = smem_bytes(P.BN, P.stages);
-  static std::atomic<size_t> configured{0};
-  if (smem > configured.load(std::memory_order_relaxed)) {
-    CSWIN_CUDA_OK(cudaFuncSetAttribute(linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    configured.store(227 * 1024, std::memory_order_relaxed);
+  using Kern = void (*)(const GemmTcParams);
+  static const Kern kerns[4] = {linear_tc_kernel<false, false>, linear_tc_kernel<true, false>, linear_tc_kernel<false, true>,
+                                linear_tc_kernel<true, true>};
+  static std::atomic<int> configured{0};
+  if (!configured.load(std::memory_order_acquire)) {
+    for (Kern k : kerns) CSWIN_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured.store(1, std::memory_order_release);
   }
   dim3 grid((unsigned)((a->M + BM - 1) / BM), (unsigned)((a->N + P.BN - 1) / P.BN));
-  CSWIN_CUDA_OK(launch_pdl(linear_tc_kernel, grid, dim3(kThreads), smem, stream, P));
+  const Kern kern = kerns[(a->ln_stats != nullptr ? 1 : 0) | (a->stats_out != nullptr ? 2 : 0)];
+  CSWIN_CUDA_OK(launch_pdl(kern, grid, dim3(kThreads), smem, stream, P));
   CSWIN_LAUNCH_CHECK();
   g_tc_launches.fetch_add(1, std::memory_order_relaxed);
   *handled = true;

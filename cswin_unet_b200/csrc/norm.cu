@@ -141,7 +141,31 @@ int launch(const void* x, int64_t ldx, const void* g, const void* b, void* y, in
   return CSWIN_OK;
 }
 
+template <typename T>
+__global__ void __launch_bounds__(256) row_stats_kernel(const T* __restrict__ x, int64_t ldx, int64_t M, int C,
+                                                         float* __restrict__ stats) {
+  pdl_trigger();
+  pdl_wait();
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= M) return;
+  float s1 = 0.f, s2 = 0.f;
+  for (int c = lane; c < C; c += 32) { const float v = ldf(x + row * ldx + c); s1 += v; s2 = fmaf(v, v, s2); }
+  s1 = warp_sum(s1); s2 = warp_sum(s2);
+  if (lane == 0) { stats[row * 2] = s1; stats[row * 2 + 1] = s2; }
+}
+
 }  // namespace
+
+int row_stats(const void* x, int64_t ldx, int64_t M, int C, float* stats, int dtype, cudaStream_t s) {
+  CSWIN_REQUIRE(x && stats && C > 0 && ldx >= C, CSWIN_ERR_INVALID, "row_stats: bad arguments");
+  if (M == 0) return CSWIN_OK;
+  const dim3 grid((unsigned)ceil_div64(M, 8));
+  if (dtype == CSWIN_F32) CSWIN_CUDA_OK(launch_pdl(row_stats_kernel<float>, grid, dim3(256), 0, s, (const float*)x, ldx, M, C, stats));
+  else CSWIN_CUDA_OK(launch_pdl(row_stats_kernel<__nv_bfloat16>, grid, dim3(256), 0, s, (const __nv_bfloat16*)x, ldx, M, C, stats));
+  CSWIN_LAUNCH_CHECK();
+  return CSWIN_OK;
+}
 
 int layernorm_fwd(const void* x, int64_t ldx, const void* g, const void* b, void* y, int64_t ldy, int64_t M, int C,
                   float eps, float* mean, float* rstd, int dtype, cudaStream_t s) {

@@ -63,24 +63,25 @@ __global__ void __launch_bounds__(kWThreads) linear_wgrad_tc_kernel(const __grid
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
+      int s = 0; uint32_t ph = 1;
       for (int mb = 0; mb < nmb; ++mb) {
-        const int s = mb % kWStages;
-        if (mb >= kWStages) mbar_wait(empty(s), ((mb / kWStages) - 1) & 1);
+        if (mb >= kWStages) mbar_wait(empty(s), ph);
         mbar_expect_tx(full(s), z_bytes + a_bytes);
         const int m = (int)(mbeg + (int64_t)mb * MB);
         for (int j = 0; j < 2; ++j)
           tma_load_2d(smem_u32(Zs + (size_t)s * z_bytes + j * 8192), &P.map_z, full(s), n0 + 64 * j, m);
         for (int j = 0; j < P.nblk; ++j)
           tma_load_2d(smem_u32(As + (size_t)s * a_bytes + j * 8192), &P.map_a, full(s), k0 + 64 * j, m);
+        if (++s == kWStages) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t idesc = make_idesc_bf16(TN, BN, 1, 1);             // both operands MN-major
+      int s = 0; uint32_t ph = 0;
       for (int mb = 0; mb < nmb; ++mb) {
-        const int s = mb % kWStages;
-        mbar_wait(full(s), (mb / kWStages) & 1);
+        mbar_wait(full(s), ph);
         tc_fence_after();
         // MN-major, 128-byte swizzle: LBO = 8 KB (next 64-wide block along n / k), SBO = 1 KB (next 8 rows of m)
         const uint64_t zd = make_smem_desc(smem_u32(Zs + (size_t)s * z_bytes), 8192, 1024, kLayoutSw128);
@@ -89,6 +90,7 @@ __global__ void __launch_bounds__(kWThreads) linear_wgrad_tc_kernel(const __grid
         for (int k = 0; k < MB / 16; ++k)                                // 16 rows of m per MMA = 2 KB further
           mma_ss(tmem_base, zd + (uint64_t)k * (2048 >> 4), ad + (uint64_t)k * (2048 >> 4), idesc, (mb | k) != 0);
         tc_commit(empty(s));
+        if (++s == kWStages) { s = 0; ph ^= 1; }
       }
       tc_commit(bar_acc);
     }

@@ -15,6 +15,7 @@ common and do not bump the version).
 from __future__ import annotations
 
 import math
+import os
 from typing import Callable, Dict, Optional, Tuple
 
 import torch
@@ -53,6 +54,13 @@ class DropPath(nn.Module):
 
     def extra_repr(self):
         return f"drop_prob={round(self.drop_prob, 3):0.3f}"
+
+
+# fc1 + GELU + fc2 + residual as one tcgen05 kernel (needs FOLD_LN) for dim <= FUSE_MLP_MAX_DIM.  Measured per block on B200
+# (batch 24): dim 64 fused 71.3 us vs 76.8 us composed; dim 128 45.5 vs 44.3; dim 256 44.6 vs 38.8 -> default 64.
+FUSE_MLP = os.environ.get("CSWIN_FUSE_MLP", "1") != "0"
+FUSE_MLP_MAX_DIM = int(os.environ.get("CSWIN_FUSE_MLP_MAX_DIM", "64"))
+FOLD_LN = os.environ.get("CSWIN_FOLD_LN", "1") != "0"     # LayerNorm folded into the tcgen05 Linear epilogue (bf16 inference)
 
 
 class _Derived:
@@ -274,9 +282,19 @@ class CSWinBlock(_Native):
             return self._forward_train(x)
         dt = x.dtype
         w = self._w
-        qkv = ops.linear(x, w("qkv.w", self.qkv.weight, dt),
-                         None if self.qkv.bias is None else w("qkv.b", self.qkv.bias, dt),
-                         ln=(w("n1.w", self.norm1.weight, dt), w("n1.b", self.norm1.bias, dt), self.norm1.eps))
+        fold = dt == torch.bfloat16 and FOLD_LN
+        if fold:
+            # LayerNorm folded into the tcgen05 Linear: the GEMM reads the RAW rows; mean / rstd come from the (sum, sum^2)
+            # side channel the producing Linear's epilogue wrote (or one row_stats pass for a stage's first block)
+            st = getattr(x, "_cswin_stats", None)
+            if st is None or st.shape[0] != B * L:
+                st = ops.row_stats(x)
+            wq, csq, bq = self._folded("qkv", self.qkv, self.norm1)
+            qkv = ops.linear(x, wq, None, ln_fold=(st, csq, self.norm1.eps), bias_f32=bq)
+        else:
+            qkv = ops.linear(x, w("qkv.w", self.qkv.weight, dt),
+                             None if self.qkv.bias is None else w("qkv.b", self.qkv.bias, dt),
+                             ln=(w("n1.w", self.norm1.weight, dt), w("n1.b", self.norm1.bias, dt), self.norm1.eps))
         att = torch.empty((B, L, Cn), dtype=dt, device=x.device)
         q, k, v = qkv[..., :Cn], qkv[..., Cn:2 * Cn], qkv[..., 2 * Cn:]
         if self.branch_num == 2:
@@ -292,6 +310,22 @@ class CSWinBlock(_Native):
             descs = [self.attns[0].branch_desc(q, k, v, att)]
             scale = float(self.attns[0].scale)
         ops.lepe_attention_fwd(descs, B, H, scale, dt)
+        if fold:
+            x1, st1 = ops.linear(att, w("proj.w", self.proj.weight, dt), w("proj.b", self.proj.bias, dt), residual=x,
+                                 sample_scale=self._sample_scale(x), rows_per_sample=L, want_stats=True)
+            w1, cs1, b1 = self._folded("fc1", self.mlp.fc1, self.norm2)
+            if (FUSE_MLP and Cn <= FUSE_MLP_MAX_DIM and self._sample_scale(x) is None
+                    and ops.mlp_supported(Cn, self.mlp.fc1.out_features)):
+                # fc1 + GELU + fc2 + residual in one launch; the hidden activation stays in TMEM / shared memory
+                y, st2 = ops.mlp_fused(x1, w1, cs1, b1, w("fc2.w", self.mlp.fc2.weight, dt),
+                                       w("fc2.b32", self.mlp.fc2.bias, torch.float32), st1, self.norm2.eps)
+                y._cswin_stats = st2
+                return y
+            hid = ops.linear(x1, w1, None, ln_fold=(st1, cs1, self.norm2.eps), bias_f32=b1, act=1)
+            y, st2 = ops.linear(hid, w("fc2.w", self.mlp.fc2.weight, dt), w("fc2.b", self.mlp.fc2.bias, dt), residual=x1,
+                                sample_scale=self._sample_scale(x), rows_per_sample=L, want_stats=True)
+            y._cswin_stats = st2                        # rides along to the next block of the stage
+            return y
         x1 = ops.linear(att, w("proj.w", self.proj.weight, dt), w("proj.b", self.proj.bias, dt), residual=x,
                         sample_scale=self._sample_scale(x), rows_per_sample=L)
         hid = ops.linear(x1, w("fc1.w", self.mlp.fc1.weight, dt), w("fc1.b", self.mlp.fc1.bias, dt),
@@ -299,6 +333,15 @@ class CSWinBlock(_Native):
         return ops.linear(hid, w("fc2.w", self.mlp.fc2.weight, dt), w("fc2.b", self.mlp.fc2.bias, dt), residual=x1,
                           sample_scale=self._sample_scale(x), rows_per_sample=L)
 
+
+    def _folded(self, key: str, lin: nn.Linear, norm: nn.LayerNorm):
+        """(bf16 W o gamma, fp32 column sums of that bf16 matrix, fp32 b + W beta) for LN -> Linear (see cswin_b200.h)."""
+        ps = (lin.weight, norm.weight, norm.bias) + (() if lin.bias is None else (lin.bias,))
+        wf = self._w(key + ".fw", ps, torch.bfloat16, lambda W, g, b, *r: W.float() * g.float()[None, :])
+        cs = self._w(key + ".fcs", ps, torch.float32, lambda W, g, b, *r: (W.float() * g.float()[None, :]).bfloat16().float().sum(1))
+        bf = self._w(key + ".fb", ps, torch.float32,
+                     lambda W, g, b, *r: W.float() @ b.float() + (r[0].float() if r else 0.0))
+        return wf, cs, bf
 
     def _forward_train(self, x: Tensor) -> Tensor:
         """Same graph on the autograd tape: every node is a native forward / backward kernel pair (autograd.py)."""

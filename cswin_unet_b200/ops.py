@@ -12,7 +12,7 @@ from typing import Optional, Sequence, Tuple
 import torch
 
 from . import _lib
-from ._lib import BF16, F32, LepeBranch, LepeBranchGrad, LinearArgs, check, lib
+from ._lib import BF16, F32, LepeBranch, LepeBranchGrad, LinearArgs, MlpArgs, check, lib
 
 Tensor = torch.Tensor
 
@@ -130,8 +130,13 @@ def layernorm(x: Tensor, gamma: Tensor, beta: Tensor, eps: float = 1e-5, out: Op
 def linear(a: Tensor, w: Tensor, bias: Optional[Tensor] = None, *, a2: Optional[Tensor] = None,
            ln: Optional[Tuple[Tensor, Tensor, float]] = None, act: int = 0, residual: Optional[Tensor] = None,
            sample_scale: Optional[Tensor] = None, rows_per_sample: int = 0, out: Optional[Tensor] = None,
-           n_out: Optional[int] = None, w_kn: bool = False) -> Tensor:
-    """out = residual + sample_scale[row // rows_per_sample] * act(LN?([a | a2]) @ w[:n_out].T + bias)."""
+           n_out: Optional[int] = None, w_kn: bool = False, ln_fold=None, bias_f32: Optional[Tensor] = None,
+           want_stats: bool = False):
+    """out = residual + sample_scale[row // rows_per_sample] * act(LN?([a | a2]) @ w[:n_out].T + bias).
+
+    bf16 only: `ln_fold = (stats (M, parts, 2) fp32, colsum (N) fp32, eps)` applies LayerNorm algebraically in the
+    epilogue (w must already be W o gamma, bias_f32 = b + W beta — see include/cswin_b200.h); `want_stats=True`
+    returns (out, stats) where stats holds the per-row partial (sum, sum^2) of `out` for the next folded Linear."""
     _need_cuda(a, w, bias, a2, residual, sample_scale)
     if ln is not None and a.dtype == torch.bfloat16:
         # bf16 / tcgen05 path: the operand is normalised in fp32 and rounded to bf16 ONCE by the LayerNorm kernel,
@@ -174,8 +179,60 @@ def linear(a: Tensor, w: Tensor, bias: Optional[Tensor] = None, *, a2: Optional[
         assert sample_scale.dtype == torch.float32 and rows_per_sample > 0
         args.sample_scale, args.rows_per_sample = sample_scale.data_ptr(), rows_per_sample
     args.out, args.ldo, args.M, args.N, args.act = out.data_ptr(), ldo, M, N, act
+    if bias_f32 is not None:
+        assert bias_f32.dtype == torch.float32 and bias_f32.numel() >= N
+        args.bias_f32 = bias_f32.data_ptr()
+    if ln_fold is not None:
+        st, cs, eps = ln_fold
+        assert st.dtype == torch.float32 and st.is_contiguous() and st.shape[0] == M and st.shape[2] == 2
+        assert cs.dtype == torch.float32 and cs.numel() >= N and a2 is None
+        args.ln_stats, args.ln_stats_parts, args.ln_C = st.data_ptr(), st.shape[1], K1
+        args.ln_colsum, args.ln_eps = cs.data_ptr(), eps
+    stats = None
+    if want_stats:
+        parts = lib().cswin_linear_stats_parts(M, N, K1 + K2, act)
+        stats = torch.empty((M, parts, 2), dtype=torch.float32, device=a.device)
+        args.stats_out = stats.data_ptr()
     check(lib().cswin_linear_fwd(C.byref(args), _dtype_code(a), _stream()), "cswin_linear_fwd")
-    return out
+    return (out, stats) if want_stats else out
+
+
+def mlp_supported(C_: int, hidden: int) -> bool:
+    return lib().cswin_mlp_stats_parts(C_, hidden) > 0
+
+
+def mlp_fused(x: Tensor, w1f: Tensor, cs1: Tensor, b1f: Tensor, w2: Tensor, b2: Tensor, stats: Tensor, eps: float,
+              want_stats: bool = True):
+    """out = x + GELU(LN(x) W1^T + b1) W2^T + b2 in one tcgen05 launch (LayerNorm folded: w1f = W1 o gamma, cs1 its fp32 row
+    sums, b1f = b1 + W1 beta; `stats` = (M, parts, 2) row sums of x).  Returns (out, stats of out | None)."""
+    _need_cuda(x, w1f, cs1, b1f, w2, b2, stats)
+    assert x.dtype == torch.bfloat16 and w1f.dtype == torch.bfloat16 and w2.dtype == torch.bfloat16
+    assert cs1.dtype == b1f.dtype == b2.dtype == stats.dtype == torch.float32 and stats.is_contiguous()
+    x_, M, ldx = _rows(x)
+    Cn, hid = x.shape[-1], w1f.shape[0]
+    assert w1f.shape == (hid, Cn) and w2.shape == (Cn, hid) and w1f.stride(1) == 1 and w2.stride(1) == 1
+    assert stats.shape[0] == M and stats.shape[2] == 2 and cs1.numel() == hid and b1f.numel() == hid and b2.numel() == Cn
+    out = torch.empty(x.shape, dtype=x.dtype, device=x.device)
+    a = MlpArgs()
+    a.x, a.ldx, a.w1, a.ldw1 = x_.data_ptr(), ldx, w1f.data_ptr(), w1f.stride(0)
+    a.ln_colsum, a.b1, a.w2, a.ldw2, a.b2 = cs1.data_ptr(), b1f.data_ptr(), w2.data_ptr(), w2.stride(0), b2.data_ptr()
+    a.ln_stats, a.ln_stats_parts, a.ln_eps = stats.data_ptr(), stats.shape[1], eps
+    a.out, a.ldo, a.M, a.C, a.hidden = out.data_ptr(), Cn, M, Cn, hid
+    st = None
+    if want_stats:
+        st = torch.empty((M, lib().cswin_mlp_stats_parts(Cn, hid), 2), dtype=torch.float32, device=x.device)
+        a.stats_out = st.data_ptr()
+    check(lib().cswin_mlp_fwd(C.byref(a), _dtype_code(x), _stream()), "cswin_mlp_fwd")
+    return out, st
+
+
+def row_stats(x: Tensor) -> Tensor:
+    """(M, 1, 2) fp32 per-row (sum, sum^2) of a (..., C) activation — seeds the folded-LayerNorm chain."""
+    _need_cuda(x)
+    x_, M, ldx = _rows(x)
+    st = torch.empty((M, 1, 2), dtype=torch.float32, device=x.device)
+    check(lib().cswin_row_stats(x_.data_ptr(), ldx, M, x.shape[-1], st.data_ptr(), _dtype_code(x), _stream()), "cswin_row_stats")
+    return st
 
 
 # ----------------------------------------------------------------------------------------------

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define CSWIN_ABI_VERSION 2
+#define CSWIN_ABI_VERSION 3
 
 typedef struct CUstream_st* cswin_stream_t; /* == cudaStream_t */
 
@@ -127,9 +127,46 @@ typedef struct {
   int32_t act;
   int32_t w_layout;                                /* 0: w is (N, K) row-major (nn.Linear.weight);  1: w is (K, N) row-major, i.e.
                                                       out = a w — the data gradient dA = dZ W reads W in place, no transpose */
+  /* --- LayerNorm folded into the Linear (bf16 / tcgen05 path only; all NULL / 0 by default) ---------------------------
+   * LN(x) W^T + b  ==  rstd_m * (x (W o gamma)^T  -  mean_m * colsum_n)  +  (b + W beta)_n : the GEMM runs on the RAW rows
+   * with the caller-derived weight w = bf16(W o gamma); ln_colsum[n] = sum_k float(w[n,k]); bias_f32 = b + W beta (fp32);
+   * mean / rstd come from per-row partial sums (sum x, sum x^2) that the PRODUCER of x wrote: ln_stats is
+   * (M, ln_stats_parts, 2) fp32.  stats_out: if non-NULL this launch writes the same partial sums of ITS output rows,
+   * (M, gridDim.y = ceil(N / BN), 2) fp32, for the next folded Linear; cswin_linear_stats_parts() returns that count.
+   * No separate LayerNorm kernel and no normalised copy of the activation exist on this path. */
+  const float* ln_stats; int32_t ln_stats_parts; int32_t ln_C;
+  const float* ln_colsum;
+  const float* bias_f32;                           /* fp32 bias (used instead of `bias` when non-NULL) */
+  float* stats_out;
 } cswin_linear_args_t;
 
 int cswin_linear_fwd(const cswin_linear_args_t* args, int32_t dtype, cswin_stream_t stream);
+/* number of column tiles (= partial sums per row written to stats_out) the tcgen05 kernel will use for this problem */
+int32_t cswin_linear_stats_parts(int64_t M, int32_t N, int32_t K, int32_t act);
+/* ---- fused MLP half of a CSWinBlock (bf16 / tcgen05 only): out = x + GELU(LN(x) W1^T + b1) W2^T + b2 ------------------------
+ * replaces cswin_unet.py:179 `x = x + drop_path(mlp(norm2(x)))` with Mlp.forward :22-26 (eval: DropPath = identity) in ONE
+ * launch; the (M, 4C) hidden activation never reaches global memory.  LayerNorm is folded exactly as in
+ * cswin_linear_args_t: w1 = bf16(W1 o gamma), ln_colsum[h] = sum_k float(w1[h,k]), b1 = fc1.bias + W1 beta (fp32),
+ * ln_stats = (M, ln_stats_parts, 2) partial (sum, sum^2) of the rows of x written by the producer of x.
+ * stats_out (optional): (M, cswin_mlp_stats_parts(C, hidden), 2) partial sums of the rows of out.
+ * Supported: C in {64, 128, 256}, hidden = 4 C, 16-byte aligned rows; anything else returns CSWIN_ERR_UNSUPPORTED and the
+ * caller composes two cswin_linear_fwd calls instead. */
+typedef struct {
+  const void* x; int64_t ldx;                      /* (M, C) bf16: GEMM operand AND residual */
+  const void* w1; int64_t ldw1;                    /* (hidden, C) bf16, gamma-folded */
+  const float* ln_colsum; const float* b1;         /* (hidden) fp32 */
+  const void* w2; int64_t ldw2;                    /* (C, hidden) bf16 */
+  const float* b2;                                 /* (C) fp32 */
+  const float* ln_stats; int32_t ln_stats_parts; float ln_eps;
+  void* out; int64_t ldo;                          /* (M, C) bf16 */
+  float* stats_out;
+  int64_t M; int32_t C; int32_t hidden;
+} cswin_mlp_args_t;
+int cswin_mlp_fwd(const cswin_mlp_args_t* args, int32_t dtype, cswin_stream_t stream);
+int32_t cswin_mlp_stats_parts(int32_t C, int32_t hidden);   /* 0 if the shape is unsupported */
+
+/* per-row (sum x, sum x^2) of a (M, C) activation as one part: stats (M, 1, 2) fp32 — for inputs no Linear produced */
+int cswin_row_stats(const void* x, int64_t ldx, int64_t M, int32_t C, float* stats, int32_t dtype, cswin_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * im2col gathers feeding cswin_linear_fwd (convolutions as GEMMs).

@@ -412,3 +412,115 @@ def test_512px_config_blocks_fp32_and_bf16_vs_oracle():
             y16 = m(x.bfloat16()).float().cpu().double()
         assert (y32 - ref).abs().max().item() <= 1e-4, dim
         assert (y16 - ref).abs().max().item() <= 2e-1, dim
+
+
+@pytest.mark.parametrize("M,C,N,act,mean", [(3136 * 2, 64, 192, 0, 0.0), (784, 128, 512, 1, 0.7), (196 * 3, 256, 768, 0, -1.5),
+                                            (49 * 5, 512, 2048, 1, 3.0), (130, 64, 256, 1, 0.2)])
+def test_linear_folded_layernorm_chain(M, C, N, act, mean):
+    """LayerNorm folded into the tcgen05 Linear (cswin_unet.py:168-169, :179): the producer Linear's epilogue emits the
+    per-row (sum, sum^2) side channel, the consumer runs on the RAW rows with W o gamma and applies
+    rstd * (acc - mean * colsum) + (b + W beta).  Checked against fp64 LN -> Linear on the same bf16 activations."""
+    g = torch.Generator().manual_seed(M + C + N)
+    a0 = torch.randn(M, C, generator=g).bfloat16()
+    wp = (torch.randn(C, C, generator=g) / C ** 0.5).bfloat16()
+    bp = (torch.randn(C, generator=g) * 0.1 + mean).bfloat16()
+    res = torch.randn(M, C, generator=g).bfloat16()
+    gam = (1 + 0.2 * torch.randn(C, generator=g)).float()
+    bet = (0.2 * torch.randn(C, generator=g)).float()
+    W = (torch.randn(N, C, generator=g) / C ** 0.5).float()
+    b = (0.1 * torch.randn(N, generator=g)).float()
+    x1, st = ops.linear(a0.to(DEV), wp.to(DEV), bp.to(DEV), residual=res.to(DEV), want_stats=True)
+    # the side channel equals the row sums of the bf16 values actually stored
+    xs = x1.float().cpu().double()
+    s = st.cpu().double().sum(1)
+    assert (s[:, 0] - xs.sum(1)).abs().max().item() <= 1e-3 * max(1.0, abs(mean) * C)
+    assert ((s[:, 1] - (xs * xs).sum(1)).abs() / (xs * xs).sum(1)).max().item() <= 1e-5
+    assert (ops.row_stats(x1).cpu().double()[:, 0] - s).abs().max().item() <= 1e-3 * max(1.0, abs(mean) * C)
+    wf = (W * gam[None, :]).bfloat16()
+    cs = wf.float().sum(1)
+    bf = W @ bet + b
+    y = ops.linear(x1, wf.to(DEV), None, ln_fold=(st, cs.to(DEV), 1e-5), bias_f32=bf.to(DEV), act=act)
+    mu = xs.mean(1, keepdim=True)
+    var = xs.var(1, unbiased=False, keepdim=True)
+    ref = ((xs - mu) / (var + 1e-5).sqrt() * gam.double() + bet.double()) @ W.double().T + b.double()
+    if act:
+        ref = torch.nn.functional.gelu(ref)
+    err = (y.float().cpu().double() - ref).abs().max().item()
+    assert err <= 4e-2, err                                  # bf16 operands + bf16 output rounding (|y| up to ~6)
+    # against the unfused bf16 path (LayerNorm kernel -> Linear) the two agree to bf16 resolution
+    y2 = ops.linear(x1, W.bfloat16().to(DEV), b.bfloat16().to(DEV), ln=(gam.bfloat16().to(DEV), bet.bfloat16().to(DEV), 1e-5), act=act)
+    err2 = (y2.float().cpu().double() - ref).abs().max().item()
+    assert err <= 2.0 * err2 + 1e-2, (err, err2)
+
+
+def test_folded_layernorm_model_matches_unfolded():
+    """Whole-model bf16 logits with the LN fold on (default) and off agree with the fp32 logits equally well."""
+    from cswin_unet_b200 import modules as M_
+    m = build_model("refinit")
+    x = T(synth.synth_image_batch(2, 3, 224, seed=0, kind="ct"))
+    with torch.no_grad():
+        ref = m(x).float()
+        m.compute_dtype = torch.bfloat16
+        old = M_.FOLD_LN
+        try:
+            M_.FOLD_LN = True
+            n0 = cw._lib.launch_count()
+            y_f = m(x).float()
+            n_f = cw._lib.launch_count() - n0
+            M_.FOLD_LN = False
+            n0 = cw._lib.launch_count()
+            y_u = m(x).float()
+            n_u = cw._lib.launch_count() - n0
+        finally:
+            M_.FOLD_LN = old
+    e_f, e_u = (y_f - ref).abs().max().item(), (y_u - ref).abs().max().item()
+    assert e_f <= 2e-2 and e_u <= 2e-2, (e_f, e_u)
+    assert abs((y_f.argmax(1) == ref.argmax(1)).float().mean().item() - (y_u.argmax(1) == ref.argmax(1)).float().mean().item()) <= 3e-3
+    assert n_f <= n_u - 40, (n_f, n_u)                       # ~52 LayerNorm launches gone, 4 row_stats added, stage-1 MLPs fused                       # ~52 LayerNorm launches disappear, 4 row_stats appear
+
+
+@pytest.mark.parametrize("M,C,mean", [(300, 64, 0.0), (75264, 64, 0.3), (18816, 128, -0.5), (4704, 256, 0.7), (130, 256, 0.0),
+                                      (128 * 5 + 1, 128, 2.0)])
+def test_fused_mlp_vs_fp64(M, C, mean):
+    """cswin_mlp_fwd: x + fc2(GELU(fc1(LayerNorm(x)))) (cswin_unet.py:179, Mlp :22-26) in one tcgen05 launch, against fp64 on
+    the same bf16 inputs and against the composed (LayerNorm kernel -> Linear+GELU -> Linear+residual) bf16 path."""
+    g = torch.Generator().manual_seed(M + C)
+    hid = 4 * C
+    x = (torch.randn(M, C, generator=g) + mean).bfloat16()
+    gam = (1 + 0.2 * torch.randn(C, generator=g)).float()
+    bet = (0.2 * torch.randn(C, generator=g)).float()
+    W1 = (torch.randn(hid, C, generator=g) / C ** 0.5).float()
+    b1 = (0.1 * torch.randn(hid, generator=g)).float()
+    W2 = (torch.randn(C, hid, generator=g) / hid ** 0.5).bfloat16()
+    b2 = (0.1 * torch.randn(C, generator=g)).float()
+    xd = x.to(DEV)
+    st = ops.row_stats(xd)
+    w1f = (W1 * gam[None, :]).bfloat16()
+    y, st2 = ops.mlp_fused(xd, w1f.to(DEV), w1f.float().sum(1).to(DEV), (W1 @ bet + b1).to(DEV), W2.to(DEV), b2.to(DEV), st, 1e-5)
+    xs = x.double()
+    mu, var = xs.mean(1, keepdim=True), xs.var(1, unbiased=False, keepdim=True)
+    u = (xs - mu) / (var + 1e-5).sqrt() * gam.double() + bet.double()
+    h = torch.nn.functional.gelu(u @ W1.double().T + b1.double())
+    ref = xs + h @ W2.double().T + b2.double()
+    err = (y.float().cpu().double() - ref).abs().max().item()
+    # composed bf16 path on the same operands
+    u16 = ops.layernorm(xd, gam.bfloat16().to(DEV), bet.bfloat16().to(DEV), 1e-5)
+    h16 = ops.linear(u16, W1.bfloat16().to(DEV), b1.bfloat16().to(DEV), act=1)
+    y2 = ops.linear(h16, W2.to(DEV), b2.bfloat16().to(DEV), residual=xd)
+    err2 = (y2.float().cpu().double() - ref).abs().max().item()
+    print(f"[fused mlp M={M} C={C}] max-abs vs fp64: fused {err:.3e}, composed {err2:.3e}")
+    assert err <= 1.5 * err2 + 2e-2, (err, err2)
+    # the statistics side channel describes the stored rows
+    ys = y.float().cpu().double()
+    s = st2.cpu().double().sum(1)
+    assert (s[:, 0] - ys.sum(1)).abs().max().item() <= 1e-3 * C * max(1.0, abs(mean))
+    assert ((s[:, 1] - (ys * ys).sum(1)).abs() / (ys * ys).sum(1)).max().item() <= 1e-5
+
+
+def test_fused_mlp_rejects_unsupported():
+    x = torch.zeros(64, 512, device=DEV, dtype=torch.bfloat16)
+    assert not ops.mlp_supported(512, 2048) and not ops.mlp_supported(256, 512)
+    with pytest.raises(cw.CswinError):
+        ops.mlp_fused(x, torch.zeros(2048, 512, device=DEV, dtype=torch.bfloat16), torch.zeros(2048, device=DEV),
+                      torch.zeros(2048, device=DEV), torch.zeros(512, 2048, device=DEV, dtype=torch.bfloat16),
+                      torch.zeros(512, device=DEV), ops.row_stats(x), 1e-5, want_stats=False)

@@ -20,6 +20,16 @@ if kind == "attn":
              if blk.branch_num == 2 else [blk.attns[0].branch_desc(q, k, v, out)])
     fn = lambda: ops.lepe_attention_fwd(descs, B, reso, float(blk.attns[0].scale), torch.bfloat16)
     names = ["entry", "prologue", "qkv_landed", "S_ready", "P_published", "lepe_done", "O_ready", "exit"]
+elif kind == "mlp":
+    M, C = int(sys.argv[2]), int(sys.argv[3])
+    x = torch.randn(M, C, device=DEV, dtype=torch.bfloat16)
+    w1 = (torch.randn(4 * C, C, device=DEV) / C ** 0.5).bfloat16(); w2 = (torch.randn(C, 4 * C, device=DEV) / (4 * C) ** 0.5).bfloat16()
+    cs, b1, b2 = w1.float().sum(1), torch.randn(4 * C, device=DEV) * 0.1, torch.randn(C, device=DEV) * 0.1
+    st = ops.row_stats(x)
+    fn = lambda: ops.mlp_fused(x, w1, cs, b1, w2, b2, st, 1e-5)
+    names = ["entry", "prologue", "tma_issued", "x_landed", "mma_issued", "acc2_ready", "exchanged", "reduced",
+             "cyc:mma_wait_ring", "cyc:mma_wait_acc1free", "cyc:mma_wait_H", "cyc:mma_total",
+             "cyc:epi_wait_acc1", "cyc:issue_mma2", "cyc:commits", "cyc:issue_mma1"]
 else:
     M, N, K = int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])
     act = int(sys.argv[5]) if len(sys.argv) > 5 else 0
@@ -36,10 +46,19 @@ _lib.lib().cswin_debug_set_trace(buf.data_ptr())
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record(); fn(); e1.record(); torch.cuda.synchronize()
 _lib.lib().cswin_debug_set_trace(None)
-t = buf.cpu().numpy().reshape(1024, 16)[:, :8].astype(np.float64)
+NS = len(names)
+t = buf.cpu().numpy().reshape(1024, 16)[:, :max(NS, 8)].astype(np.float64)
 live = t[:, 0] > 0
 t = t[live]
 t0 = t[:, 0].min()
+if NS > 8:
+    print(f"{kind} {sys.argv[2:]}: {live.sum()} CTAs traced; kernel (events) {e0.elapsed_time(e1)*1e3:.1f} us; first entry -> last exit {(t[:,7].max()-t0)/1e3:.2f} us")
+    for i in range(8, NS):
+        print(f"  {names[i]:24s} median {np.median(t[:, i]):9.0f} cycles  (needs -DCSWIN_MLP_PROFILE)")
+    order = np.argsort(np.median(t[:, :8] - t0, axis=0))
+    for i in order:
+        print(f"  {names[i]:14s} median {np.median(t[:, i] - t0)/1e3:8.2f} us   (per-CTA since entry {np.median(t[:, i] - t[:, 0])/1e3:7.2f})")
+    sys.exit(0)
 print(f"{kind} {sys.argv[2:]}: {live.sum()} CTAs traced; kernel (events) {e0.elapsed_time(e1)*1e3:.1f} us; first entry -> last exit {(t[:,7].max()-t0)/1e3:.2f} us")
 print("phase          median-start(us)  median-dur-to-next(us)   [relative to first CTA entry]")
 for i, n in enumerate(names):
