@@ -60,7 +60,7 @@ constexpr int kI2cSeg = 32;
 template <typename TI, typename T, int CK, int CS>
 __global__ void __launch_bounds__(256) im2col_nchw_kernel(const TI* __restrict__ x, T* __restrict__ col, int64_t ldcol_,
                                                            int B, int C, int H, int W, int KH_, int KW_, int stride_,
-                                                           int pad, int Ho, int Wo) {
+                                                           int pad, int Ho, int Wo, int vec8) {
   const int KH = CK > 0 ? CK : KH_, KW = CK > 0 ? CK : KW_, stride = CS > 0 ? CS : stride_;
   const int ldcol = (int)ldcol_;
   extern __shared__ float patch[];                     // [C][KH][span]
@@ -85,6 +85,35 @@ __global__ void __launch_bounds__(256) im2col_nchw_kernel(const TI* __restrict__
   __syncthreads();
   const int K = C * KH * KW;
   const int npix = min(kI2cSeg, Wo - ox0);
+  T* crow = col + ((int64_t)(b * Ho + oy) * Wo + ox0) * ldcol;
+  if (sizeof(T) == 2 && vec8) {
+    // bf16, rows of ldcol = 8 n elements, 16-byte aligned: a per-column offset table (built once per CTA) turns every output
+    // element into two shared-memory loads, and each thread emits whole 16-byte stores
+    uint16_t* offs = reinterpret_cast<uint16_t*>(patch + ((C * KH * span + 3) & ~3));
+    for (int k = threadIdx.x; k < ldcol; k += blockDim.x) {
+      const int kx = k % KW, ky = (k / KW) % KH, c = k / (KW * KH);
+      offs[k] = (uint16_t)(k < K ? (c * KH + ky) * span + kx : 0);
+    }
+    __syncthreads();
+    const int nvec = ldcol >> 3;
+    for (int i = threadIdx.x; i < npix * nvec; i += blockDim.x) {
+      const int p = i / nvec, v = i - p * nvec;
+      const uint4 o = reinterpret_cast<const uint4*>(offs)[v];
+      const float* pp = patch + p * stride;
+      const int k0 = v * 8;
+      const uint32_t ow[4] = {o.x, o.y, o.z, o.w};
+      uint32_t w[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float lo = (k0 + 2 * e < K) ? pp[ow[e] & 0xffffu] : 0.f;
+        const float hi = (k0 + 2 * e + 1 < K) ? pp[ow[e] >> 16] : 0.f;
+        const __nv_bfloat162 h2 = __floats2bfloat162_rn(lo, hi);
+        w[e] = *reinterpret_cast<const uint32_t*>(&h2);
+      }
+      *reinterpret_cast<uint4*>(crow + (int64_t)p * ldcol + k0) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    return;
+  }
   for (int i = threadIdx.x; i < npix * ldcol; i += blockDim.x) {
     const int p = i / ldcol;
     const int k = i - p * ldcol;
@@ -95,7 +124,7 @@ __global__ void __launch_bounds__(256) im2col_nchw_kernel(const TI* __restrict__
       const int c = k / (KW * KH);
       v = patch[(c * KH + ky) * span + p * stride + kx];
     }
-    stf(col + ((int64_t)(b * Ho + oy) * Wo + ox0) * ldcol + i, v);
+    stf(crow + i, v);
   }
 }
 
@@ -282,6 +311,94 @@ __global__ void __launch_bounds__(256) carafe_head_kernel(const T* __restrict__ 
   }
 }
 
+// Segmentation head, up = 4, bf16, NC classes, z rows padded to 16: one warp per (batch, low-res row, 8 low-res pixels); lane =
+// (pixel xl = lane / 4, output sub-row ay = lane % 4) owns the 4 output pixels (4 x0 .. 4 x0 + 3) of output row 4 y0 + ay.  The 4
+// lanes of a pixel read one contiguous 32-byte sector of encoder logits per tap and share (broadcast) the 9 neighbour z rows;
+// labels leave as one 32-bit store per lane (8 lanes = 32 contiguous bytes of a label row), logits as 8 / 16-byte stores.
+template <int NC, typename TO>
+__global__ void __launch_bounds__(256) carafe_head_up4_kernel(const __nv_bfloat16* __restrict__ enc, int64_t ldenc,
+                                                               const __nv_bfloat16* __restrict__ z, int64_t ldz,
+                                                               const __nv_bfloat16* __restrict__ bias, TO* __restrict__ logits,
+                                                               uint8_t* __restrict__ labels, int B, int H, int W) {
+  pdl_trigger();
+  pdl_wait();
+  const int lane = threadIdx.x & 31;
+  const int xgroups = (W + 7) >> 3;
+  const int64_t wid = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (wid >= (int64_t)B * H * xgroups) return;
+  const int xg = (int)(wid % xgroups);
+  const int y0 = (int)((wid / xgroups) % H);
+  const int b = (int)(wid / ((int64_t)xgroups * H));
+  const int x0 = xg * 8 + (lane >> 2), ay = lane & 3;
+  if (x0 >= W) return;
+  const int64_t pix = ((int64_t)b * H + y0) * W + x0;
+  float k[9][4];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const uint2 u = *reinterpret_cast<const uint2*>(enc + pix * ldenc + t * 16 + ay * 4);
+    k[t][0] = __uint_as_float(u.x << 16); k[t][1] = __uint_as_float(u.x & 0xffff0000u);
+    k[t][2] = __uint_as_float(u.y << 16); k[t][3] = __uint_as_float(u.y & 0xffff0000u);
+  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    float mx = k[0][a];
+#pragma unroll
+    for (int t = 1; t < 9; ++t) mx = fmaxf(mx, k[t][a]);
+    float sum = 0.f;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) { k[t][a] = __expf(k[t][a] - mx); sum += k[t][a]; }
+    const float inv = 1.0f / sum;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) k[t][a] *= inv;
+  }
+  float acc[4][NC];
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    const float bv = __bfloat162float(bias[c]);
+#pragma unroll
+    for (int a = 0; a < 4; ++a) acc[a][c] = bv;
+  }
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const int yy = y0 + t / 3 - 1, xx = x0 + t % 3 - 1;
+    if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+      const uint4* zr = reinterpret_cast<const uint4*>(z + (((int64_t)b * H + yy) * W + xx) * ldz);
+      const uint4 u0 = zr[0], u1 = zr[1];
+      const uint32_t w[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        const float zc = __uint_as_float((c & 1) ? (w[c >> 1] & 0xffff0000u) : (w[c >> 1] << 16));
+#pragma unroll
+        for (int a = 0; a < 4; ++a) acc[a][c] = fmaf(k[t][a], zc, acc[a][c]);
+      }
+    }
+  }
+  const int Ho = H * 4, Wo = W * 4, oy = y0 * 4 + ay;
+  if (logits != nullptr) {
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      TO* dst = logits + (((int64_t)b * NC + c) * Ho + oy) * Wo + x0 * 4;
+      if (sizeof(TO) == 4) {
+        *reinterpret_cast<float4*>(dst) = make_float4(acc[0][c], acc[1][c], acc[2][c], acc[3][c]);
+      } else {
+        const __nv_bfloat162 p0 = __floats2bfloat162_rn(acc[0][c], acc[1][c]), p1 = __floats2bfloat162_rn(acc[2][c], acc[3][c]);
+        *reinterpret_cast<uint2*>(dst) = make_uint2(*reinterpret_cast<const uint32_t*>(&p0), *reinterpret_cast<const uint32_t*>(&p1));
+      }
+    }
+  }
+  if (labels != nullptr) {
+    uint32_t packed = 0;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      int best = 0; float bv = acc[a][0];
+#pragma unroll
+      for (int c = 1; c < NC; ++c) if (acc[a][c] > bv) { bv = acc[a][c]; best = c; }          // first maximum, like torch.argmax
+      packed |= (uint32_t)best << (8 * a);
+    }
+    *reinterpret_cast<uint32_t*>(labels + ((int64_t)b * Ho + oy) * Wo + x0 * 4) = packed;
+  }
+}
+
 }  // namespace
 
 int carafe_head_fwd(const void* enc, int64_t ldenc, const void* z, int64_t ldz, const void* bias, void* logits,
@@ -293,6 +410,15 @@ int carafe_head_fwd(const void* enc, int64_t ldenc, const void* z, int64_t ldz, 
   if (total == 0) return CSWIN_OK;
   const unsigned grid = (unsigned)std::min<int64_t>(ceil_div64(total, 256), (int64_t)sm_count() * 32);
   const int zvec = dtype == CSWIN_BF16 && ldz >= 16 && (ldz * 2) % 16 == 0 && reinterpret_cast<uintptr_t>(z) % 16 == 0;
+  if (zvec && up == 4 && C == 9 && (ldenc * 2) % 8 == 0 && reinterpret_cast<uintptr_t>(enc) % 8 == 0 &&
+      reinterpret_cast<uintptr_t>(logits) % 16 == 0 && reinterpret_cast<uintptr_t>(labels) % 4 == 0) {
+    const unsigned g4 = (unsigned)ceil_div64((int64_t)B * H * ((W + 7) / 8), 8);
+    const __nv_bfloat16 *e_ = (const __nv_bfloat16*)enc, *z_ = (const __nv_bfloat16*)z, *b_ = (const __nv_bfloat16*)bias;
+    if (logits_is_f32) CSWIN_CUDA_OK(launch_pdl(carafe_head_up4_kernel<9, float>, dim3(g4), dim3(256), (size_t)0, s, e_, ldenc, z_, ldz, b_, (float*)logits, labels, B, H, W));
+    else CSWIN_CUDA_OK(launch_pdl(carafe_head_up4_kernel<9, __nv_bfloat16>, dim3(g4), dim3(256), (size_t)0, s, e_, ldenc, z_, ldz, b_, (__nv_bfloat16*)logits, labels, B, H, W));
+    CSWIN_LAUNCH_CHECK();
+    return CSWIN_OK;
+  }
   if (dtype == CSWIN_F32) {
     CSWIN_REQUIRE(!logits || logits_is_f32, CSWIN_ERR_INVALID, "carafe_head: fp32 path writes fp32 logits");
     CSWIN_CUDA_OK(launch_pdl(carafe_head_kernel<float, float>, dim3(grid), dim3(256), (size_t)(0), s, (const float*)enc, ldenc, (const float*)z, ldz, (const float*)bias, (float*)logits, labels, B, H, W, C, up, zvec));
@@ -332,21 +458,22 @@ int im2col_nchw(const void* x, int x_is_f32, void* col, int64_t ldcol, int B, in
   const int Ho = (H + 2 * pad - KH) / stride + 1, Wo = (W + 2 * pad - KW) / stride + 1;
   if ((int64_t)B * Ho * Wo == 0) return CSWIN_OK;
   const int span = (kI2cSeg - 1) * stride + KW;
-  const size_t smem = sizeof(float) * (size_t)C * KH * span;
+  const int vec8 = dtype == CSWIN_BF16 && ldcol % 8 == 0 && reinterpret_cast<uintptr_t>(col) % 16 == 0 && (size_t)C * KH * span < 65536;
+  const size_t smem = sizeof(float) * (((size_t)C * KH * span + 3) & ~(size_t)3) + (vec8 ? 2 * (size_t)ldcol : 0);
   CSWIN_REQUIRE(smem <= 48 * 1024, CSWIN_ERR_UNSUPPORTED, "im2col_nchw: C*KH*span=%zu floats exceed 48 KB of shared memory", smem / 4);
   const int64_t ctas = (int64_t)B * Ho * ((Wo + kI2cSeg - 1) / kI2cSeg);
   CSWIN_REQUIRE(ctas < (1ll << 31), CSWIN_ERR_UNSUPPORTED, "im2col_nchw: grid too large");
   const unsigned grid = (unsigned)ctas;
   if (dtype == CSWIN_F32) {
     CSWIN_REQUIRE(x_is_f32, CSWIN_ERR_INVALID, "im2col_nchw: fp32 path needs an fp32 image");
-    if (KH == 7 && KW == 7 && stride == 4) CSWIN_CUDA_OK(launch_pdl(im2col_nchw_kernel<float, float, 7, 4>, dim3(grid), dim3(256), (size_t)(smem), s, (const float*)x, (float*)col, ldcol, B, C, H, W, KH, KW, stride, pad, Ho, Wo));
-    else CSWIN_CUDA_OK(launch_pdl(im2col_nchw_kernel<float, float, 0, 0>, dim3(grid), dim3(256), (size_t)(smem), s, (const float*)x, (float*)col, ldcol, B, C, H, W, KH, KW, stride, pad, Ho, Wo));
+    if (KH == 7 && KW == 7 && stride == 4) CSWIN_CUDA_OK(launch_pdl(im2col_nchw_kernel<float, float, 7, 4>, dim3(grid), dim3(256), (size_t)(smem), s, (const float*)x, (float*)col, ldcol, B, C, H, W, KH, KW, stride, pad, Ho, Wo, vec8));
+    else CSWIN_CUDA_OK(launch_pdl(im2col_nchw_kernel<float, float, 0, 0>, dim3(grid), dim3(256), (size_t)(smem), s, (const float*)x, (float*)col, ldcol, B, C, H, W, KH, KW, stride, pad, Ho, Wo, vec8));
   } else if (x_is_f32) {
-    if (KH == 7 && KW == 7 && stride == 4) CSWIN_CUDA_OK(launch_pdl(im2col_nchw_kernel<float, __nv_bfloat16, 7, 4>, dim3(grid), dim3(256), (size_t)(smem), s, (const float*)x, (__nv_bfloat16*)col, ldcol, B, C, H, W, KH, KW, stride, pad, Ho, Wo));
-    else CSWIN_CUDA_OK(launch_pdl(im2col_nchw_kernel<float, __nv_bfloat16, 0, 0>, dim3(grid), dim3(256), (size_t)(smem), s, (const float*)x, (__nv_bfloat16*)col, ldcol, B, C, H, W, KH, KW, stride, pad, Ho, Wo));
+    if (KH == 7 && KW == 7 && stride == 4) CSWIN_CUDA_OK(launch_pdl(im2col_nchw_kernel<float, __nv_bfloat16, 7, 4>, dim3(grid), dim3(256), (size_t)(smem), s, (const float*)x, (__nv_bfloat16*)col, ldcol, B, C, H, W, KH, KW, stride, pad, Ho, Wo, vec8));
+    else CSWIN_CUDA_OK(launch_pdl(im2col_nchw_kernel<float, __nv_bfloat16, 0, 0>, dim3(grid), dim3(256), (size_t)(smem), s, (const float*)x, (__nv_bfloat16*)col, ldcol, B, C, H, W, KH, KW, stride, pad, Ho, Wo, vec8));
   } else {
-    if (KH == 7 && KW == 7 && stride == 4) CSWIN_CUDA_OK(launch_pdl(im2col_nchw_kernel<__nv_bfloat16, __nv_bfloat16, 7, 4>, dim3(grid), dim3(256), (size_t)(smem), s, (const __nv_bfloat16*)x, (__nv_bfloat16*)col, ldcol, B, C, H, W, KH, KW, stride, pad, Ho, Wo));
-    else CSWIN_CUDA_OK(launch_pdl(im2col_nchw_kernel<__nv_bfloat16, __nv_bfloat16, 0, 0>, dim3(grid), dim3(256), (size_t)(smem), s, (const __nv_bfloat16*)x, (__nv_bfloat16*)col, ldcol, B, C, H, W, KH, KW, stride, pad, Ho, Wo));
+    if (KH == 7 && KW == 7 && stride == 4) CSWIN_CUDA_OK(launch_pdl(im2col_nchw_kernel<__nv_bfloat16, __nv_bfloat16, 7, 4>, dim3(grid), dim3(256), (size_t)(smem), s, (const __nv_bfloat16*)x, (__nv_bfloat16*)col, ldcol, B, C, H, W, KH, KW, stride, pad, Ho, Wo, vec8));
+    else CSWIN_CUDA_OK(launch_pdl(im2col_nchw_kernel<__nv_bfloat16, __nv_bfloat16, 0, 0>, dim3(grid), dim3(256), (size_t)(smem), s, (const __nv_bfloat16*)x, (__nv_bfloat16*)col, ldcol, B, C, H, W, KH, KW, stride, pad, Ho, Wo, vec8));
   }
   CSWIN_LAUNCH_CHECK();
   return CSWIN_OK;
