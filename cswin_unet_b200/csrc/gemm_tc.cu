@@ -26,6 +26,14 @@ namespace {
 
 using namespace tc;
 
+// -DCSWIN_GEMM_PROFILE: cycle stamps of the first epilogue unit of warp 2 into debug trace slots 8..15 (tools/trace_kernel.py)
+#ifdef CSWIN_GEMM_PROFILE
+#define PSTAMP(i) do { if (warp == 2 && lane == 0 && u == ch + 2 * CSWIN_GEMM_PROFILE && P.trace != nullptr && blockIdx.x + blockIdx.y * gridDim.x < 1024) \
+  P.trace[(size_t)(blockIdx.x + blockIdx.y * gridDim.x) * 16 + (i)] = clock64(); } while (0)
+#else
+#define PSTAMP(i) do { } while (0)
+#endif
+
 constexpr int BM = 128, BK = 64;
 constexpr int kMaxStages = 8;
 constexpr int kThreads = 320;                          // warp 0 TMA, warp 1 MMA + TMEM, warps 2..9 epilogue
@@ -72,37 +80,38 @@ __global__ void __launch_bounds__(kThreads, 2) linear_tc_kernel(const __grid_con
   auto empty = [&](int s) { return smem_u32(&bars[kMaxStages + s]); };
   const uint32_t bar_acc = smem_u32(&bars[2 * kMaxStages]);
 
-  if (warp == 0 && lane == 0) {
+  // One elected thread initialises the barriers and immediately requests the W tiles of the first ring pass: weights do not
+  // depend on the previous kernel (PDL) nor on the rest of this CTA's prologue (TMEM allocation, bias loads).
+  const int npre = P.nkb < S ? P.nkb : S;
+  if (warp == 0 && elect_one()) {
     for (int s = 0; s < S; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
     mbar_init(bar_acc, 1);
     fence_barrier_init();
-    tma_prefetch_desc(&P.map_a); tma_prefetch_desc(&P.map_w);
-    if (P.K2 > 0) tma_prefetch_desc(&P.map_a2);
-  }
-  if (warp == 1) { tmem_alloc(smem_u32(tmem_slot), (uint32_t)P.tmem_cols); tmem_relinquish(); }
-  if (warp >= 2) {                                      // bias of this tile's columns -> smem (fp32)
-    const int j = tid - 64, n = n0 + j;
-    const bool in = j < BN && n < P.N;
-    sBias[j] = !in ? 0.f : P.bias_f32 != nullptr ? P.bias_f32[n] : P.bias != nullptr ? __bfloat162float(P.bias[n]) : 0.f;
-    if (kFold) sCs[j] = in ? P.ln_cs[n] : 0.f;
-    if (kStats) sStat[j] = 0.f;
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  if (tid == 0) trace_stamp(P.trace, 1);                                   // prologue done
-
-  // weights do not depend on the previous kernel: the W tiles of the first ring pass are requested before the PDL wait
-  const int npre = P.nkb < S ? P.nkb : S;
-  if (warp == 0 && elect_one()) {
+    fence_proxy_async();
+    tma_prefetch_desc(&P.map_w);
     for (int kb = 0; kb < npre; ++kb) {
       mbar_expect_tx(full(kb), a_bytes + w_bytes);
       if (!P.w_kn) tma_load_2d(smem_u32(Ws + (size_t)kb * w_bytes), &P.map_w, full(kb), kb * BK, n0);
       else for (int j = 0; j * 64 < BN; ++j)             // (K, N) weight: [64 k][64 n] boxes = MN-major B blocks
         tma_load_2d(smem_u32(Ws + (size_t)kb * w_bytes + j * 8192), &P.map_w, full(kb), n0 + 64 * j, kb * BK);
     }
+    tma_prefetch_desc(&P.map_a);
+    if (P.K2 > 0) tma_prefetch_desc(&P.map_a2);
   }
+  if (warp == 1) { tmem_alloc(smem_u32(tmem_slot), (uint32_t)P.tmem_cols); tmem_relinquish(); }
+  float bias_r = 0.f, cs_r = 0.f;                       // per-column constants: loaded now, parked in smem by the epilogue warps
+  if (warp >= 2) {                                      // (the loads stay in flight across the CTA barrier)
+    const int j = tid - 64, n = n0 + j;
+    if (j < BN && n < P.N) {
+      bias_r = P.bias_f32 != nullptr ? P.bias_f32[n] : P.bias != nullptr ? __bfloat162float(P.bias[n]) : 0.f;
+      if (kFold) cs_r = P.ln_cs[n];
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (tid == 0) trace_stamp(P.trace, 1);                                   // prologue done
   pdl_wait();                                           // activations (A, residual) and the output buffer are safe from here
 
   if (warp == 0) {
@@ -147,6 +156,20 @@ __global__ void __launch_bounds__(kThreads, 2) linear_tc_kernel(const __grid_con
     //      swizzled 2 KB staging tile -> row-contiguous read-back so the residual load and the store are coalesced 16 B.
     const int q = warp & 3;
     const int ch = (warp - 2) >> 2;
+    sBias[tid - 64] = bias_r;
+    if (kFold) sCs[tid - 64] = cs_r;
+    if (kStats) sStat[tid - 64] = 0.f;
+    asm volatile("bar.sync 1, 256;" ::: "memory");      // the 8 epilogue warps only
+    if (P.res != nullptr && P.vec_ok) {                 // pull this thread's residual segments towards L1 while the MMAs run
+      for (int u = ch; u < ((BN + 31) >> 5); u += 2) {
+        const int n = n0 + u * 32 + (lane & 3) * 8;
+#pragma unroll
+        for (int pass = 0; pass < 4; ++pass) {
+          const int64_t m = m0 + q * 32 + pass * 8 + (lane >> 2);
+          if (m < P.M && n < P.N) asm volatile("prefetch.global.L1 [%0];" ::"l"(P.res + m * P.ldr + n));
+        }
+      }
+    }
     uint8_t* stg = Epi + (warp - 2) * 2048;
     const uint32_t stg_u32 = smem_u32(stg);
     const int64_t mrow = m0 + q * 32 + lane;            // accumulator row held by this thread in phase 1
@@ -165,8 +188,10 @@ __global__ void __launch_bounds__(kThreads, 2) linear_tc_kernel(const __grid_con
     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
     for (int u = ch; u < nunits; u += 2) {
       uint32_t v[32];
+      PSTAMP(8);
       tmem_ld32(trow + u * 32, v);
       tmem_wait_ld();
+      PSTAMP(9);
       const float4* b4 = reinterpret_cast<const float4*>(sBias + u * 32);
       const float4* c4 = reinterpret_cast<const float4*>(sCs + u * 32);
 #pragma unroll
@@ -201,6 +226,7 @@ __global__ void __launch_bounds__(kThreads, 2) linear_tc_kernel(const __grid_con
                      "r"(pack_bf16x2(f[2], f[3])), "r"(pack_bf16x2(f[4], f[5])), "r"(pack_bf16x2(f[6], f[7])) : "memory");
       }
       __syncwarp();
+      PSTAMP(10);
       // 8 rows x 64 B per pass, 4 lanes per row; the four passes' shared-memory reads and residual loads are all issued
       // before the first use so their latencies overlap
       const int c = lane & 3;
@@ -221,10 +247,12 @@ __global__ void __launch_bounds__(kThreads, 2) linear_tc_kernel(const __grid_con
           rv[pass] = m < P.M ? *reinterpret_cast<const uint4*>(P.res + m * P.ldr + n) : make_uint4(0, 0, 0, 0);
         }
       }
+      PSTAMP(11);
 #pragma unroll
       for (int pass = 0; pass < 4; ++pass) {
         const int r = pass * 8 + (lane >> 2);
         const int64_t m = m0 + q * 32 + r;
+        if (pass == 0 && P.res != nullptr) { PSTAMP(12 + (int)((rv[0].x & 1) & 0)); }
         uint4 x = w[pass];
         float st1 = 0.f, st2 = 0.f;
         if (m < P.M && col_ok) {
@@ -232,10 +260,8 @@ __global__ void __launch_bounds__(kThreads, 2) linear_tc_kernel(const __grid_con
           if (vec) {
             if (P.res != nullptr) {
               const uint4 y = rv[pass];
-              x.x = pack_bf16x2(bf16_lo(x.x) + bf16_lo(y.x), bf16_hi(x.x) + bf16_hi(y.x));
-              x.y = pack_bf16x2(bf16_lo(x.y) + bf16_lo(y.y), bf16_hi(x.y) + bf16_hi(y.y));
-              x.z = pack_bf16x2(bf16_lo(x.z) + bf16_lo(y.z), bf16_hi(x.z) + bf16_hi(y.z));
-              x.w = pack_bf16x2(bf16_lo(x.w) + bf16_lo(y.w), bf16_hi(x.w) + bf16_hi(y.w));
+              x.x = add_bf16x2(x.x, y.x); x.y = add_bf16x2(x.y, y.y);     // bf16 + bf16 -> bf16, one rounding (HADD2.BF16)
+              x.z = add_bf16x2(x.z, y.z); x.w = add_bf16x2(x.w, y.w);
             }
             *reinterpret_cast<uint4*>(dst) = x;
             if (kStats) {                               // (sum, sum^2) of the bf16 values just stored, for the next folded LN
@@ -262,6 +288,7 @@ __global__ void __launch_bounds__(kThreads, 2) linear_tc_kernel(const __grid_con
           if (c == 0) { atomicAdd(&sStat[(q * 32 + r) * 2], st1); atomicAdd(&sStat[(q * 32 + r) * 2 + 1], st2); }
         }
       }
+      PSTAMP(13);
       __syncwarp();
     }
     if (kStats) {

@@ -143,8 +143,9 @@ __global__ void __launch_bounds__(kThreads, 2) mlp_tc_kernel(const __grid_consta
       const uint32_t idesc1 = make_idesc_bf16(BM, HC, 0, 0), idesc2 = make_idesc_bf16(BM, C, 0, 0);
       const uint32_t acc2 = tmem_base + 128;
       int cs = 0; uint32_t cph = 0;                          // ring slot / parity of the next chunk to consume
+#ifdef CSWIN_MLP_PROFILE
       long long w_ring = 0, w_free = 0, w_h = 0, c_start = clock64(), i_m1 = 0, i_m2 = 0, i_cm = 0;
-      (void)w_ring; (void)w_free; (void)w_h; (void)c_start; (void)i_m1; (void)i_m2; (void)i_cm;
+#endif
       auto mma1 = [&](int j) {
         const int s = cs;
         PWAIT(w_ring, mbar_wait(bar(kFull + s), cph));
@@ -203,8 +204,9 @@ __global__ void __launch_bounds__(kThreads, 2) mlp_tc_kernel(const __grid_consta
       rstd = rsqrtf(fmaxf(fmaf(-mean, mean, s2 * P.ln_invC), 0.f) + P.ln_eps);
     }
     const float nmean = -mean;
-    long long e_acc = 0, e_hfree = 0, e_start = clock64();
-    (void)e_acc; (void)e_hfree; (void)e_start;
+#ifdef CSWIN_MLP_PROFILE
+    long long e_acc = 0, e_hfree = 0;
+#endif
     for (int j = 0; j < nsub; ++j) {
       const int b = j & 1;
       PWAIT(e_acc, mbar_wait(bar(kAcc1Full + b), (j >> 1) & 1));
@@ -303,10 +305,7 @@ __global__ void __launch_bounds__(kThreads, 2) mlp_tc_kernel(const __grid_consta
         const uint32_t y0 = pack_bf16x2(a0.x + bA.x, a0.y + bA.y), y1 = pack_bf16x2(a0.z + bA.z, a0.w + bA.w);
         const uint32_t y2 = pack_bf16x2(a1.x + bB.x, a1.y + bB.y), y3 = pack_bf16x2(a1.z + bB.z, a1.w + bB.w);
         uint4 w;
-        w.x = pack_bf16x2(bf16_lo(y0) + bf16_lo(rv.x), bf16_hi(y0) + bf16_hi(rv.x));
-        w.y = pack_bf16x2(bf16_lo(y1) + bf16_lo(rv.y), bf16_hi(y1) + bf16_hi(rv.y));
-        w.z = pack_bf16x2(bf16_lo(y2) + bf16_lo(rv.z), bf16_hi(y2) + bf16_hi(rv.z));
-        w.w = pack_bf16x2(bf16_lo(y3) + bf16_lo(rv.w), bf16_hi(y3) + bf16_hi(rv.w));
+        w.x = add_bf16x2(y0, rv.x); w.y = add_bf16x2(y1, rv.y); w.z = add_bf16x2(y2, rv.z); w.w = add_bf16x2(y3, rv.w);
         *reinterpret_cast<uint4*>(P.out + m * P.ldo + col) = w;
         const float e0 = bf16_lo(w.x), e1 = bf16_hi(w.x), e2 = bf16_lo(w.y), e3 = bf16_hi(w.y);
         const float e4 = bf16_lo(w.z), e5 = bf16_hi(w.z), e6 = bf16_lo(w.w), e7 = bf16_hi(w.w);

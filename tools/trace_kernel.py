@@ -64,4 +64,9 @@ print("phase          median-start(us)  median-dur-to-next(us)   [relative to fi
 for i, n in enumerate(names):
     d = np.median(t[:, i + 1] - t[:, i]) / 1e3 if i < 7 else 0.0
     print(f"  {n:14s} {np.median(t[:, i] - t0)/1e3:10.2f} {d:14.2f}")
+if os.environ.get("GEMM_PROFILE"):
+    tt = buf.cpu().numpy().reshape(1024, 16)[live].astype(np.float64)
+    lab = ["tmem_ld issue", "tmem_ld done", "math+st.shared+syncwarp", "lds+residual issued", "residual arrived", "stores done"]
+    for i in range(9, 14):
+        print(f"  cyc {lab[i-8]:28s} +{np.median(tt[:, i] - tt[:, i-1]):7.0f}")
 print(f"per-CTA lifetime median {np.median(t[:,7]-t[:,0])/1e3:.2f} us, max {np.max(t[:,7]-t[:,0])/1e3:.2f}; entry spread {np.ptp(t[:,0])/1e3:.2f} us")
