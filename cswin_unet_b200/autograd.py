@@ -64,6 +64,30 @@ def _zeros(shape, device) -> Tensor:
     return v if v is not None else torch.zeros(shape, dtype=torch.float32, device=device)
 
 
+def _tma_rows(t: Tensor) -> Tensor:
+    """Gradient rows laid out for the tcgen05 kernels: unit column stride and, for bf16, a row pitch that is a multiple of
+    16 bytes (N = 36 or 9 output channels would otherwise fall back to the SIMT dgrad / wgrad kernels)."""
+    n = t.shape[-1]
+    if t.dtype == torch.bfloat16 and n % 8 != 0:
+        ld = (n + 7) // 8 * 8
+        if not (t.dim() >= 2 and t.stride(-1) == 1 and t.stride(-2) == ld
+                and _uniform_rows(t, ld)):
+            buf = torch.empty(t.shape[:-1] + (ld,), dtype=t.dtype, device=t.device)[..., :n]
+            buf.copy_(t)
+            return buf
+        return t
+    return t.contiguous()
+
+
+def _uniform_rows(t: Tensor, ld: int) -> bool:
+    expect = ld
+    for size, stride in zip(reversed(t.shape[:-1]), reversed(t.stride()[:-1])):
+        if size != 1 and stride != expect:
+            return False
+        expect *= size
+    return True
+
+
 def _c(p: Optional[Tensor], dt: torch.dtype) -> Optional[Tensor]:
     if p is None:
         return None
@@ -88,7 +112,8 @@ class LayerNormFn(Function):
     @once_differentiable
     def backward(ctx, dy):
         x, g, mean, rstd = ctx.saved_tensors
-        dx, dg, db = ops.layernorm_bwd(x, dy.contiguous(), g, mean, rstd)
+        Cn = x.shape[-1]
+        dx, dg, db = ops.layernorm_bwd(x, dy.contiguous(), g, mean, rstd, _zeros((Cn,), x.device), _zeros((Cn,), x.device))
         return dx, dg.to(ctx.pd), db.to(ctx.pd), None
 
 
@@ -110,7 +135,7 @@ class LinearFn(Function):
     @once_differentiable
     def backward(ctx, dout):
         a, a2, wc, ss = ctx.saved_tensors
-        dout = dout.contiguous()
+        dout = _tma_rows(dout)
         dz = dout if ss is None else ops.act_bwd(dout, None, ss, ctx.rps, act=0)
         K1 = a.shape[-1]
         N, K = wc.shape
@@ -194,8 +219,8 @@ class LepeAttentionFn(Function):
         dqkv = torch.empty_like(qkv)
         dq, dk, dv = dqkv[..., :Cn], dqkv[..., Cn:2 * Cn], dqkv[..., 2 * Cn:]
         h = Cn // len(ws)
-        gw = [torch.zeros((h, 9), dtype=torch.float32, device=qkv.device) for _ in ws]
-        gb = [torch.zeros(h, dtype=torch.float32, device=qkv.device) for _ in ws]
+        gw = [_zeros((h, 9), qkv.device) for _ in ws]
+        gb = [_zeros((h,), qkv.device) for _ in ws]
 
         def extra(i, sl):
             return dict(dout=dout[..., sl], dq=dq[..., sl], dk=dk[..., sl], dv=dv[..., sl], dconv_w=gw[i], dconv_b=gb[i],

@@ -201,6 +201,11 @@ int cswin_carafe_reassemble_bwd(const void* enc, int64_t ldenc, const void* z, i
                                kappa_ws, B, H, W, C, up, dtype, (cudaStream_t)stream);
 }
 
+int cswin_sgd_momentum_step(const cswin_sgd_chunk_t* chunks, int32_t n_chunks, const float* lr, float momentum,
+                            float weight_decay, cswin_stream_t stream) {
+  return sgd_momentum_step(chunks, n_chunks, lr, momentum, weight_decay, (cudaStream_t)stream);
+}
+
 int cswin_mlp_fwd(const cswin_mlp_args_t* a, int32_t dtype, cswin_stream_t stream) {
   CSWIN_REQUIRE(a != nullptr, CSWIN_ERR_INVALID, "mlp_fwd: null args");
   CSWIN_REQUIRE(dtype == CSWIN_BF16, CSWIN_ERR_UNSUPPORTED, "mlp_fwd: the fused MLP exists on the bf16 / tcgen05 path only");

@@ -330,6 +330,50 @@ unsigned grid_for(int64_t total, int per_cta) {
   return (unsigned)std::min<int64_t>(ceil_div64(total, per_cta), (int64_t)sm_count() * 32);
 }
 
+// ---------------- fused SGD(momentum, weight decay) over every parameter + bf16 shadow refresh ----------------
+__global__ void __launch_bounds__(256) sgd_momentum_kernel(const cswin_sgd_chunk_t* __restrict__ chunks, const float* __restrict__ lr_p,
+                                                            float momentum, float wd) {
+  const cswin_sgd_chunk_t c = chunks[blockIdx.x];
+  const float lr = *lr_p;
+  const bool vec = ((reinterpret_cast<uintptr_t>(c.param) | reinterpret_cast<uintptr_t>(c.grad) | reinterpret_cast<uintptr_t>(c.momentum)) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(c.shadow) & 7) == 0;
+  const int64_t n4 = vec ? (c.n >> 2) : 0;
+  __nv_bfloat16* sh = reinterpret_cast<__nv_bfloat16*>(c.shadow);
+  for (int64_t i = threadIdx.x; i < n4; i += blockDim.x) {
+    float4 p = reinterpret_cast<float4*>(c.param)[i];
+    const float4 g = reinterpret_cast<const float4*>(c.grad)[i];
+    float4 m = reinterpret_cast<float4*>(c.momentum)[i];
+    m.x = fmaf(momentum, m.x, fmaf(wd, p.x, g.x)); m.y = fmaf(momentum, m.y, fmaf(wd, p.y, g.y));
+    m.z = fmaf(momentum, m.z, fmaf(wd, p.z, g.z)); m.w = fmaf(momentum, m.w, fmaf(wd, p.w, g.w));
+    p.x = fmaf(-lr, m.x, p.x); p.y = fmaf(-lr, m.y, p.y); p.z = fmaf(-lr, m.z, p.z); p.w = fmaf(-lr, m.w, p.w);
+    reinterpret_cast<float4*>(c.momentum)[i] = m;
+    reinterpret_cast<float4*>(c.param)[i] = p;
+    if (sh != nullptr) {
+      const __nv_bfloat162 a = __floats2bfloat162_rn(p.x, p.y), b = __floats2bfloat162_rn(p.z, p.w);
+      reinterpret_cast<uint2*>(sh)[i] = make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
+    }
+  }
+  for (int64_t i = n4 * 4 + threadIdx.x; i < c.n; i += blockDim.x) {
+    float p = c.param[i];
+    const float m = fmaf(momentum, c.momentum[i], fmaf(wd, p, c.grad[i]));
+    p = fmaf(-lr, m, p);
+    c.momentum[i] = m;
+    c.param[i] = p;
+    if (sh != nullptr) sh[i] = __float2bfloat16_rn(p);
+  }
+}
+
+}  // namespace
+
+int sgd_momentum_step(const cswin_sgd_chunk_t* chunks, int n_chunks, const float* lr, float momentum, float wd, cudaStream_t s) {
+  CSWIN_REQUIRE(chunks && lr && n_chunks >= 0, CSWIN_ERR_INVALID, "sgd_momentum_step: bad arguments");
+  if (n_chunks == 0) return CSWIN_OK;
+  sgd_momentum_kernel<<<(unsigned)n_chunks, 256, 0, s>>>(chunks, lr, momentum, wd);
+  CSWIN_LAUNCH_CHECK();
+  return CSWIN_OK;
+}
+
+namespace {
 }  // namespace
 
 int act_fwd(const void* z, int64_t ldz, void* out, int64_t ldo, int64_t M, int N, int act, int dtype, cudaStream_t s) {

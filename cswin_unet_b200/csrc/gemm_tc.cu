@@ -363,7 +363,7 @@ int linear_fwd_tc(const cswin_linear_args_t* a, cudaStream_t stream, bool* handl
   if (a->ln_gamma != nullptr) return CSWIN_OK;                               // LayerNorm prologue: SIMT kernel (host calls LN first on the bf16 path)
   const int K = a->K1 + a->K2;
   if (!aligned16(a->a) || !aligned16(a->w) || (a->lda * 2) % 16 || (a->ldw * 2) % 16) return CSWIN_OK;
-  if (a->K1 % 8 || K % 8) return CSWIN_OK;
+  // K itself may be ragged (TMA zero-fills past the tensor extent); only the row pitches above must be 16-byte multiples
   if (a->a2 && (!aligned16(a->a2) || (a->lda2 * 2) % 16 || a->K1 % BK || a->K2 % 8)) return CSWIN_OK;
   if (a->M > 0x7fffffff) return CSWIN_OK;
   if (tc::encode_tiled_fn() == nullptr) return CSWIN_OK;

@@ -226,6 +226,30 @@ def mlp_fused(x: Tensor, w1f: Tensor, cs1: Tensor, b1f: Tensor, w2: Tensor, b2: 
     return out, st
 
 
+SGD_CHUNK = 65536
+
+
+def sgd_chunk_table(params, grads, momenta, shadows) -> Tensor:
+    """Host-side int64 (n_chunks, 5) table == cswin_sgd_chunk_t[]: one row per <= SGD_CHUNK-element piece of a parameter."""
+    rows = []
+    for p, g, m, sh in zip(params, grads, momenta, shadows):
+        assert p.dtype == g.dtype == m.dtype == torch.float32 and p.is_contiguous() and g.is_contiguous() and m.is_contiguous()
+        assert g.numel() == p.numel() == m.numel() and (sh is None or (sh.dtype == torch.bfloat16 and sh.is_contiguous()))
+        n = p.numel()
+        for off in range(0, n, SGD_CHUNK):
+            rows.append((p.data_ptr() + 4 * off, g.data_ptr() + 4 * off, m.data_ptr() + 4 * off,
+                         0 if sh is None else sh.data_ptr() + 2 * off, min(SGD_CHUNK, n - off)))
+    return torch.tensor(rows, dtype=torch.int64).view(-1, 5)
+
+
+def sgd_momentum_step(table_dev: Tensor, lr_dev: Tensor, momentum: float, weight_decay: float) -> None:
+    """One launch: m = momentum m + (g + wd p); p -= lr m; shadow = bf16(p) for every chunk of table_dev (device int64 (n,5))."""
+    _need_cuda(table_dev, lr_dev)
+    assert table_dev.dtype == torch.int64 and table_dev.is_contiguous() and lr_dev.dtype == torch.float32
+    check(lib().cswin_sgd_momentum_step(table_dev.data_ptr(), table_dev.shape[0], lr_dev.data_ptr(), momentum, weight_decay,
+                                        _stream()), "cswin_sgd_momentum_step")
+
+
 def row_stats(x: Tensor) -> Tensor:
     """(M, 1, 2) fp32 per-row (sum, sum^2) of a (..., C) activation — seeds the folded-LayerNorm chain."""
     _need_cuda(x)
@@ -357,14 +381,17 @@ def linear_wgrad(dz: Tensor, a: Tensor, dw: Tensor, db: Optional[Tensor]) -> Non
                                    dz.shape[-1], a.shape[-1], _dtype_code(dz), _stream()), "cswin_linear_wgrad")
 
 
-def layernorm_bwd(x: Tensor, dy: Tensor, gamma: Tensor, mean: Tensor, rstd: Tensor):
+def layernorm_bwd(x: Tensor, dy: Tensor, gamma: Tensor, mean: Tensor, rstd: Tensor, dg: Optional[Tensor] = None,
+                  db: Optional[Tensor] = None):
     _need_cuda(x, dy, gamma, mean, rstd)
     x2, M, ldx = _rows(x)
     d2, _, ldy = _rows(dy)
     Cn = x.shape[-1]
     dx = torch.empty(x.shape, dtype=x.dtype, device=x.device)
-    dg = torch.zeros(Cn, dtype=torch.float32, device=x.device)
-    db = torch.zeros(Cn, dtype=torch.float32, device=x.device)
+    if dg is None:                                        # accumulated into: the caller may pass pre-zeroed slices
+        dg = torch.zeros(Cn, dtype=torch.float32, device=x.device)
+    if db is None:
+        db = torch.zeros(Cn, dtype=torch.float32, device=x.device)
     check(lib().cswin_layernorm_bwd(x2.data_ptr(), ldx, d2.data_ptr(), ldy, gamma.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
                                     dx.data_ptr(), Cn, dg.data_ptr(), db.data_ptr(), M, Cn, _dtype_code(x), _stream()),
           "cswin_layernorm_bwd")
@@ -390,7 +417,8 @@ def carafe_reassemble_bwd(enc: Tensor, z: Tensor, dy: Tensor, B: int, H: int, W:
         sb, sy, sx, sc = Cn * Ho * Wo, Wo, 1, Ho * Wo
     else:
         sb, sy, sx, sc = Ho * Wo * Cn, Wo * Cn, Cn, 1
-    denc = torch.empty_like(enc)
+    ne = enc.shape[-1]                                    # row pitch padded to 16 bytes: the encoder Linear's dgrad / wgrad stay on tcgen05
+    denc = torch.empty(enc.shape[:-1] + ((ne + 7) // 8 * 8,), dtype=enc.dtype, device=enc.device)[..., :ne]
     dz = torch.empty_like(z)
     dbias = torch.zeros(Cn, dtype=torch.float32, device=z.device)
     kws = torch.empty(B * H * W * up * up * 9, dtype=torch.float32, device=z.device)

@@ -13,10 +13,13 @@ from __future__ import annotations
 
 from typing import Optional
 
+import os
+
 import torch
 import torch.nn.functional as F
 
 from . import autograd as ag
+from . import ops
 from . import parallel
 
 Tensor = torch.Tensor
@@ -48,14 +51,27 @@ class TrainStep:
         self.model.compute_dtype = compute_dtype
         self.n_classes = model.num_classes
         self.group = group
+        self.momentum, self.weight_decay = momentum, weight_decay
+        # torch.optim.SGD is kept for zero_grad() / the non-fp32-parameter fallback; the step itself is ONE native launch over
+        # every parameter (cswin_sgd_momentum_step: weight decay + momentum + update + bf16 shadow refresh)
         self.opt = torch.optim.SGD(model.parameters(), lr=lr, momentum=momentum, weight_decay=weight_decay)
+        self._params = [p for p in model.parameters() if p.requires_grad]
+        self._native_sgd = os.environ.get("CSWIN_TORCH_SGD") != "1" and all(
+            p.dtype == torch.float32 and p.is_cuda and p.is_contiguous() for p in self._params)
+        dev = self._params[0].device
+        self.lr_dev = torch.tensor([lr], dtype=torch.float32, device=dev)
+        self.momentum_buffers = [torch.zeros_like(p) for p in self._params] if self._native_sgd else []
+        n_chunks = sum((p.numel() + ops.SGD_CHUNK - 1) // ops.SGD_CHUNK for p in self._params)
+        self._tbl_host = torch.empty((n_chunks, 5), dtype=torch.int64).pin_memory() if self._native_sgd else None
+        self._tbl_dev = torch.empty((n_chunks, 5), dtype=torch.int64, device=dev) if self._native_sgd else None
+        self._tbl_key, self._tbl_n = None, 0
+        self._versions = None
         self.use_graph = graph
         self.warmup = warmup
         self._graphs = None
         self._static = None
         self._seen = 0
         self._make_shadow(compute_dtype)
-        import os
         self._pool = None if os.environ.get("CSWIN_NO_POOL") == "1" else ag.ZeroPool(
             sum(p.numel() + 4 for p in model.parameters()), next(model.parameters()).device)
         self._distributed = torch.distributed.is_available() and torch.distributed.is_initialized() and \
@@ -70,11 +86,43 @@ class TrainStep:
         for p in ps:
             self._shadow_views.append(flat[off:off + p.numel()].view(p.shape))
             off += (p.numel() + 7) // 8 * 8
+        self._shadow_of = {id(p): v for p, v in zip(ps, self._shadow_views)}
+
+    @property
+    def lr(self) -> float:
+        return self.opt.param_groups[0]["lr"]
+
+    @lr.setter
+    def lr(self, value: float) -> None:
+        """Learning-rate schedule hook (trainer.py:63-66): takes effect at the next step, also under CUDA-graph replay."""
+        for g in self.opt.param_groups:
+            g["lr"] = float(value)
+        self.lr_dev.fill_(float(value))
+
+    def _refresh_shadow(self) -> None:
+        if self._shadow_src:
+            torch._foreach_copy_(self._shadow_views, [p.detach() for p in self._shadow_src])
+
+    def _optimizer_step(self) -> None:
+        if not self._native_sgd:
+            self.opt.step()
+            return
+        ps = [(p, m) for p, m in zip(self._params, self.momentum_buffers) if p.grad is not None]
+        key = tuple(p.grad.data_ptr() for p, _ in ps)
+        if key != self._tbl_key:                               # gradient buffers moved (always static under graph replay)
+            tbl = ops.sgd_chunk_table([p.detach() for p, _ in ps], [p.grad.contiguous() for p, _ in ps], [m for _, m in ps],
+                                      [self._shadow_of.get(id(p)) for p, _ in ps])
+            self._tbl_n = tbl.shape[0]
+            self._tbl_host[:self._tbl_n].copy_(tbl)
+            self._tbl_key = key
+        self._tbl_dev.copy_(self._tbl_host, non_blocking=True)
+        ops.sgd_momentum_step(self._tbl_dev[:self._tbl_n], self.lr_dev, self.momentum, self.weight_decay)
 
     def _fwd_bwd(self, images: Tensor, labels: Tensor) -> Tensor:
-        if self._shadow_src:                                     # one multi-tensor fp32 -> compute-dtype copy per step
-            torch._foreach_copy_(self._shadow_views, [p.detach() for p in self._shadow_src])
-            ag.SHADOW = {id(p): v for p, v in zip(self._shadow_src, self._shadow_views)}
+        if self._shadow_src:
+            if not self._native_sgd:                             # one multi-tensor fp32 -> compute-dtype copy per step
+                self._refresh_shadow()                           # (the native SGD kernel refreshes the shadows itself)
+            ag.SHADOW = self._shadow_of
         if self._pool is not None:
             self._pool.reset()
             ag.POOL = self._pool
@@ -91,7 +139,7 @@ class TrainStep:
         self.opt.zero_grad(set_to_none=True)
         loss = self._fwd_bwd(images, labels)
         parallel.allreduce_gradients(self.model.parameters(), self.group)
-        self.opt.step()
+        self._optimizer_step()
         return loss
 
     def _capture(self, images: Tensor, labels: Tensor) -> None:
@@ -102,15 +150,26 @@ class TrainStep:
         with torch.cuda.graph(g1):                         # forward + backward (+ optimizer when single-rank)
             self._loss = self._fwd_bwd(sx, sy)
             if not self._distributed:
-                self.opt.step()
+                self._optimizer_step()
         g2 = None
         if self._distributed:                              # all-reduce eagerly between the two graphs
             g2 = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g2, pool=g1.pool()):
-                self.opt.step()
+                self._optimizer_step()
         self._graphs = (g1, g2)
 
+    def _check_external_writes(self) -> None:
+        """The native step writes parameters through raw pointers (no version bump): a changed `_version` means someone else
+        (load_state_dict, TPGM projection, ...) wrote them since the last step, so the bf16 shadows are refreshed first."""
+        if not (self._native_sgd and self._shadow_src):
+            return
+        vers = [p._version for p in self._shadow_src]
+        if vers != self._versions:
+            self._refresh_shadow()
+            self._versions = vers
+
     def __call__(self, images: Tensor, labels: Tensor) -> Tensor:
+        self._check_external_writes()
         if not self.use_graph:
             return self._eager(images, labels)
         if self._graphs is None:

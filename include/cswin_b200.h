@@ -165,6 +165,21 @@ typedef struct {
 int cswin_mlp_fwd(const cswin_mlp_args_t* args, int32_t dtype, cswin_stream_t stream);
 int32_t cswin_mlp_stats_parts(int32_t C, int32_t hidden);   /* 0 if the shape is unsupported */
 
+/* ---- optimizer step of the data-parallel training path: torch.optim.SGD(momentum, weight_decay).step() -------------------
+ * replaces `optimizer.step()` of trainer.py:42/:61 (SGD lr 0.05 poly-decayed, momentum 0.9, weight decay 1e-4) for ALL
+ * parameters in one launch, and refreshes the bf16 copy of each weight that the next forward's tcgen05 kernels stream:
+ *     g' = grad + weight_decay * p ;  m = momentum * m + g' ;  p -= lr * m ;  shadow = bf16(p)
+ * (dampening 0, no Nesterov; a zero-initialised m reproduces torch's first step m = g').  `chunks` is a DEVICE array: one
+ * entry per <= 65536-element piece of a parameter, pointers pre-offset; lr is read from DEVICE memory so a CUDA graph of
+ * the step follows the caller's learning-rate schedule (trainer.py:63-66) without re-capture. */
+typedef struct {
+  float* param; const float* grad; float* momentum;
+  void* shadow;                                    /* bf16 copy of param (NULL: none) */
+  int64_t n;
+} cswin_sgd_chunk_t;
+int cswin_sgd_momentum_step(const cswin_sgd_chunk_t* chunks, int32_t n_chunks, const float* lr, float momentum,
+                            float weight_decay, cswin_stream_t stream);
+
 /* per-row (sum x, sum x^2) of a (M, C) activation as one part: stats (M, 1, 2) fp32 — for inputs no Linear produced */
 int cswin_row_stats(const void* x, int64_t ldx, int64_t M, int32_t C, float* stats, int32_t dtype, cswin_stream_t stream);
 

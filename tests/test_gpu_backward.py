@@ -213,3 +213,64 @@ def test_lepe_attention_backward_bf16_tensor_core_vs_fp64(cfgs, B):
         sl = (Ellipsis, slice(off, off + cb))
         assert rel(gb[sl], ref[0][sl]) <= 2e-2, (key, "dqkv", rel(gb[sl], ref[0][sl]))
         assert rel(gw, ref[1]) <= 2e-2 and rel(gbias, ref[2]) <= 2e-2, (key, rel(gw, ref[1]), rel(gbias, ref[2]))
+
+
+def test_native_sgd_matches_torch_optim_sgd():
+    """cswin_sgd_momentum_step == torch.optim.SGD(lr, momentum .9, weight_decay 1e-4).step() (trainer.py:42, :61) over ragged,
+    unaligned tensors for 4 steps with a changing learning rate, and leaves bf16(param) in the shadow copies."""
+    from cswin_unet_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    shapes = [(7,), (64, 3, 7, 7), (131072 + 5,), (192, 64), (9, 64, 1, 1), (1,)]
+    ps = [torch.randn(s, generator=g).to(DEV) for s in shapes]
+    ref = [p.clone().requires_grad_(True) for p in ps]
+    opt = torch.optim.SGD(ref, lr=0.05, momentum=0.9, weight_decay=1e-4)
+    mom = [torch.zeros_like(p) for p in ps]
+    flat = torch.zeros(sum((p.numel() + 7) // 8 * 8 for p in ps), dtype=torch.bfloat16, device=DEV)
+    sh, off = [], 0
+    for p in ps:
+        sh.append(flat[off:off + p.numel()].view(p.shape))
+        off += (p.numel() + 7) // 8 * 8
+    lr_dev = torch.tensor([0.05], device=DEV)
+    for step in range(4):
+        grads = [torch.randn(s, generator=g).to(DEV) for s in shapes]
+        lr = 0.05 * (1 - step / 4) ** 0.9
+        for gp in opt.param_groups:
+            gp["lr"] = lr
+        lr_dev.fill_(lr)
+        for r, gr in zip(ref, grads):
+            r.grad = gr.clone()
+        opt.step()
+        tbl = ops.sgd_chunk_table(ps, grads, mom, sh).to(DEV)
+        assert tbl.shape[0] == sum((p.numel() + ops.SGD_CHUNK - 1) // ops.SGD_CHUNK for p in ps)
+        ops.sgd_momentum_step(tbl, lr_dev, 0.9, 1e-4)
+        for p, r, s_ in zip(ps, ref, sh):
+            assert (p - r.detach()).abs().max().item() <= 1e-6 * max(1.0, r.abs().max().item()), step
+            assert torch.equal(s_, p.bfloat16())
+
+
+def test_train_step_native_sgd_follows_torch_sgd_trajectory(monkeypatch):
+    """TrainStep (CUDA-graph replay, native fused SGD, lr schedule through device memory) against the same TrainStep driven by
+    torch.optim.SGD: identical loss trajectory over 5 steps within bf16 noise, and parameters that moved the same way."""
+    x = torch.from_numpy(synth.synth_image_batch(2, 3, 224, seed=0, kind="ct")).to(DEV)
+    y = torch.from_numpy(synth.synth_labels(2, 224, 9, seed=0)).to(DEV)
+    out = {}
+    for mode in ("native", "torch"):
+        if mode == "torch":
+            monkeypatch.setenv("CSWIN_TORCH_SGD", "1")
+        torch.manual_seed(0)
+        m = cw.cswin_tiny_224(num_classes=9, drop_path_rate=0.0)
+        shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+        m.load_state_dict({k: torch.from_numpy(v) for k, v in synth.synth_state_dict(shapes, seed=1234).items()}, strict=True)
+        m = m.to(DEV)
+        step = cw.TrainStep(m, lr=0.05, warmup=1)
+        assert step._native_sgd == (mode == "native")
+        losses = []
+        for i in range(5):
+            step.lr = 0.05 * (1 - i / 5) ** 0.9
+            losses.append(float(step(x, y)))
+        out[mode] = (losses, torch.cat([p.detach().flatten() for p in m.parameters()]).clone())
+    ln, lt = out["native"][0], out["torch"][0]
+    print(f"[native sgd] losses {ln} vs torch {lt}")
+    assert ln[-1] < ln[0]
+    assert max(abs(a - b) for a, b in zip(ln, lt)) <= 3e-2
+    assert cos(out["native"][1], out["torch"][1]) >= 0.9999

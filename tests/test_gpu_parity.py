@@ -524,3 +524,25 @@ def test_fused_mlp_rejects_unsupported():
         ops.mlp_fused(x, torch.zeros(2048, 512, device=DEV, dtype=torch.bfloat16), torch.zeros(2048, device=DEV),
                       torch.zeros(2048, device=DEV), torch.zeros(512, 2048, device=DEV, dtype=torch.bfloat16),
                       torch.zeros(512, device=DEV), ops.row_stats(x), 1e-5, want_stats=False)
+
+
+@pytest.mark.parametrize("M,N,K", [(1176, 576, 36), (75264, 64, 9), (300, 40, 20)])
+def test_linear_bf16_ragged_k_on_tensor_cores(M, N, K):
+    """Contraction lengths that are not multiples of 8 (the CARAFE encoder's 36 / the head's 9 output channels seen from their
+    data gradients) stay on the tcgen05 kernel as long as the row pitches are 16-byte multiples: TMA zero-fills the tail."""
+    g = torch.Generator().manual_seed(M + N + K)
+    ld = (K + 7) // 8 * 8
+    a = torch.zeros(M, ld, dtype=torch.bfloat16); a[:, :K] = torch.randn(M, K, generator=g).bfloat16()
+    a[:, K:] = 7.0                                            # poison the padding: it must never be read as data
+    w = torch.zeros(N, ld, dtype=torch.bfloat16); w[:, :K] = (torch.randn(N, K, generator=g) / K ** 0.5).bfloat16()
+    w[:, K:] = -3.0
+    wkn = (torch.randn(K, N, generator=g) / K ** 0.5).bfloat16()
+    ad, wd = a.to(DEV)[:, :K], w.to(DEV)[:, :K]
+    n0 = cw.tc_launch_count()
+    y1 = ops.linear(ad, wd, None)
+    y2 = ops.linear(ad, wkn.to(DEV), None, w_kn=True)
+    assert cw.tc_launch_count() - n0 == 2
+    r1 = a[:, :K].double() @ w[:, :K].double().T
+    r2 = a[:, :K].double() @ wkn.double()
+    assert (y1.float().cpu().double() - r1).abs().max().item() <= 3e-2
+    assert (y2.float().cpu().double() - r2).abs().max().item() <= 3e-2
