@@ -190,6 +190,95 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const T* __restrict_
   }
 }
 
+// bf16 rows of C = LPR * NV * 8 channels: LPR lanes per row, NV 16-byte vectors per lane, 32 / LPR rows per warp in flight.
+// dgamma / dbeta are carried in registers across the rows of a warp, reduced through shared memory, one atomic per channel
+// per CTA.
+template <int LPR, int NV>
+__global__ void __launch_bounds__(256) layernorm_bwd_bf16_vec_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx,
+                                                                      const __nv_bfloat16* __restrict__ dy, int64_t ldy,
+                                                                      const __nv_bfloat16* __restrict__ gamma,
+                                                                      const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                                      __nv_bfloat16* __restrict__ dx, int64_t ldo,
+                                                                      float* __restrict__ dgamma, float* __restrict__ dbeta, int64_t M) {
+  constexpr int C = LPR * NV * 8, RPW = 32 / LPR;
+  __shared__ float red[8][C * 2];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, sub = lane / LPR, l = lane % LPR;
+  float gm[NV][8], dg[NV][8], dbt[NV][8];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const uint4 u = *reinterpret_cast<const uint4*>(gamma + (v * LPR + l) * 8);
+    const uint32_t uw[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      gm[v][e] = __uint_as_float((e & 1) ? (uw[e >> 1] & 0xffff0000u) : (uw[e >> 1] << 16));
+      dg[v][e] = 0.f; dbt[v][e] = 0.f;
+    }
+  }
+  const float invC = 1.0f / (float)C;
+  for (int64_t base = ((int64_t)blockIdx.x * 8 + w) * RPW; base < M; base += (int64_t)gridDim.x * 8 * RPW) {
+    const int64_t row = base + sub;
+    const bool valid = row < M;
+    const float mu = valid ? mean[row] : 0.f, rs = valid ? rstd[row] : 0.f;
+    float xh[NV][8], g[NV][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      uint4 ux = make_uint4(0, 0, 0, 0), ud = make_uint4(0, 0, 0, 0);
+      if (valid) {
+        ux = *reinterpret_cast<const uint4*>(x + row * ldx + (v * LPR + l) * 8);
+        ud = *reinterpret_cast<const uint4*>(dy + row * ldy + (v * LPR + l) * 8);
+      }
+      const uint32_t xw[4] = {ux.x, ux.y, ux.z, ux.w}, dw[4] = {ud.x, ud.y, ud.z, ud.w};
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float xv = __uint_as_float((e & 1) ? (xw[e >> 1] & 0xffff0000u) : (xw[e >> 1] << 16));
+        const float d = __uint_as_float((e & 1) ? (dw[e >> 1] & 0xffff0000u) : (dw[e >> 1] << 16));
+        xh[v][e] = (xv - mu) * rs;
+        g[v][e] = d * gm[v][e];
+        dg[v][e] = fmaf(d, xh[v][e], dg[v][e]);
+        dbt[v][e] += d;
+        s1 += g[v][e];
+        s2 = fmaf(g[v][e], xh[v][e], s2);
+      }
+    }
+#pragma unroll
+    for (int o = 1; o < LPR; o <<= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+    s1 *= invC; s2 *= invC;
+    if (valid) {
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        uint32_t o[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const __nv_bfloat162 h2 = __floats2bfloat162_rn(rs * (g[v][2 * e] - s1 - xh[v][2 * e] * s2),
+                                                          rs * (g[v][2 * e + 1] - s1 - xh[v][2 * e + 1] * s2));
+          o[e] = *reinterpret_cast<const uint32_t*>(&h2);
+        }
+        *reinterpret_cast<uint4*>(dx + row * ldo + (v * LPR + l) * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+      }
+    }
+  }
+#pragma unroll
+  for (int v = 0; v < NV; ++v)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+#pragma unroll
+      for (int o = LPR; o < 32; o <<= 1) {
+        dg[v][e] += __shfl_xor_sync(0xffffffffu, dg[v][e], o);
+        dbt[v][e] += __shfl_xor_sync(0xffffffffu, dbt[v][e], o);
+      }
+      if (sub == 0) { red[w][((v * LPR + l) * 8 + e) * 2] = dg[v][e]; red[w][((v * LPR + l) * 8 + e) * 2 + 1] = dbt[v][e]; }
+    }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int ww = 0; ww < 8; ++ww) { a += red[ww][c * 2]; b += red[ww][c * 2 + 1]; }
+    atomicAdd(dgamma + c, a);
+    atomicAdd(dbeta + c, b);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // dx[b, iy, ix, c] = sum over taps (ky,kx) with (iy + pad - ky) % stride == 0 ... of dcol[(b,oy,ox), (ky*KW+kx)*C + c]
 template <typename T>
@@ -435,6 +524,18 @@ int layernorm_bwd(const void* x, int64_t ldx, const void* dy, int64_t ldy, const
   CSWIN_REQUIRE(C > 0 && C <= 512, CSWIN_ERR_UNSUPPORTED, "layernorm_bwd: C=%d outside (0, 512]", C);
   if (M == 0) return CSWIN_OK;
   const unsigned grid = (unsigned)std::min<int64_t>(ceil_div64(M, 8), (int64_t)sm_count() * 4);
+  const bool vec = dtype == CSWIN_BF16 && (ldx % 8 == 0) && (ldy % 8 == 0) && (ldo % 8 == 0) &&
+                   ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx) |
+                     reinterpret_cast<uintptr_t>(gamma)) & 15) == 0;
+  if (vec && (C == 64 || C == 128 || C == 256 || C == 512)) {
+    const int rpw = C == 64 ? 4 : C == 128 ? 2 : 1;
+    const unsigned gv = (unsigned)std::min<int64_t>(ceil_div64(M, 8 * rpw), (int64_t)sm_count() * 2);
+#define LNV(L, V) layernorm_bwd_bf16_vec_kernel<L, V><<<gv, 256, 0, s>>>((const __nv_bfloat16*)x, ldx, (const __nv_bfloat16*)dy, ldy, (const __nv_bfloat16*)gamma, mean, rstd, (__nv_bfloat16*)dx, ldo, dgamma, dbeta, M)
+    if (C == 64) LNV(8, 1); else if (C == 128) LNV(16, 1); else if (C == 256) LNV(32, 1); else LNV(32, 2);
+#undef LNV
+    CSWIN_LAUNCH_CHECK();
+    return CSWIN_OK;
+  }
 #define LNB(T, V) layernorm_bwd_kernel<T, V><<<grid, 256, 0, s>>>((const T*)x, ldx, (const T*)dy, ldy, (const T*)gamma, mean, rstd, (T*)dx, ldo, dgamma, dbeta, M, C)
   if (dtype == CSWIN_F32) { if (C <= 128) LNB(float, 4); else LNB(float, 16); }
   else { if (C <= 128) LNB(__nv_bfloat16, 4); else LNB(__nv_bfloat16, 16); }

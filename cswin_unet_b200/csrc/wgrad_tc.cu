@@ -25,6 +25,7 @@ constexpr int kWThreads = 192;    // warp 0 TMA, warp 1 MMA + TMEM, warps 2..5 e
 struct alignas(64) WgradParams {
   CUtensorMap map_z, map_a;
   float* dw; int64_t ldw;
+  float* db;                      // bias gradient (column sums of dZ), accumulated by the k-tile-0 CTAs; may be NULL
   int N, K, BN, nblk, tmem_cols, vec4;
   int64_t M, mchunk;
 };
@@ -46,12 +47,15 @@ __global__ void __launch_bounds__(kWThreads) linear_wgrad_tc_kernel(const __grid
   const int64_t mend = mbeg + P.mchunk < P.M ? mbeg + P.mchunk : P.M;
   const int nmb = (int)((mend - mbeg + MB - 1) / MB);
 
+  // bias gradient: the epilogue warps of the first k-tile's CTAs are idle during the main loop, so they sum the columns of
+  // every dZ block as it lands in shared memory (each block is released by the MMA commit AND these four warps)
+  const bool do_colsum = P.db != nullptr && blockIdx.y == 0;
   auto full = [&](int s) { return smem_u32(&bars[s]); };
   auto empty = [&](int s) { return smem_u32(&bars[kWStages + s]); };
   const uint32_t bar_acc = smem_u32(&bars[2 * kWStages]);
 
   if (warp == 0 && lane == 0) {
-    for (int s = 0; s < kWStages; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
+    for (int s = 0; s < kWStages; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), do_colsum ? 5u : 1u); }
     mbar_init(bar_acc, 1);
     fence_barrier_init();
     tma_prefetch_desc(&P.map_z); tma_prefetch_desc(&P.map_a);
@@ -96,6 +100,27 @@ __global__ void __launch_bounds__(kWThreads) linear_wgrad_tc_kernel(const __grid
     }
   } else {
     const int q = warp & 3;
+    if (do_colsum) {
+      // thread <-> column c = (warp - 2) * 32 + lane of the 128-column dZ tile: box j = c / 64, 16-byte chunk (cc / 8) ^ (m % 8)
+      const int c = (warp - 2) * 32 + lane, cc = c & 63;
+      const uint32_t cbase = (uint32_t)(c >> 6) * 8192 + (uint32_t)(cc & 7) * 2;
+      float acc = 0.f;
+      int s = 0; uint32_t ph = 0;
+      for (int mb = 0; mb < nmb; ++mb) {
+        mbar_wait(full(s), ph);
+        const uint32_t zb = smem_u32(Zs + (size_t)s * z_bytes) + cbase;
+#pragma unroll 16
+        for (int m = 0; m < MB; ++m) {
+          uint16_t h;
+          asm volatile("ld.shared.u16 %0, [%1];" : "=h"(h) : "r"(zb + m * 128 + ((((cc >> 3) ^ (m & 7))) << 4)));
+          acc += __uint_as_float((uint32_t)h << 16);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty(s));
+        if (++s == kWStages) { s = 0; ph ^= 1; }
+      }
+      if (n0 + c < P.N && nmb > 0) atomicAdd(P.db + n0 + c, acc);
+    }
     mbar_wait(bar_acc, 0);
     tc_fence_after();
     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
@@ -124,25 +149,6 @@ __global__ void __launch_bounds__(kWThreads) linear_wgrad_tc_kernel(const __grid
   if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)P.tmem_cols);
 }
 
-// db[n] += sum_m dZ[m, n]  (one warp per 32 columns, rows strided over the grid)
-__global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ dz, int64_t ldz, float* __restrict__ db,
-                                                          int64_t M, int N) {
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int n = blockIdx.x * 32 + lane;
-  float acc = 0.f;
-  if (n < N)
-    for (int64_t m = (int64_t)blockIdx.y * 8 + w; m < M; m += (int64_t)gridDim.y * 8) acc += __bfloat162float(dz[m * ldz + n]);
-  __shared__ float red[8][32];
-  red[w][lane] = acc;
-  __syncthreads();
-  if (w == 0 && n < N) {
-    float s = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) s += red[i][lane];
-    atomicAdd(db + n, s);
-  }
-}
-
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 }  // namespace
@@ -153,7 +159,7 @@ int linear_wgrad_tc(const void* dz, int64_t ldz, const void* a, int64_t lda, flo
   if (!aligned16(dz) || !aligned16(a) || (ldz * 2) % 16 || (lda * 2) % 16 || M > 0x7fffffff) return CSWIN_OK;
   if (tc::encode_tiled_fn() == nullptr) return CSWIN_OK;
   WgradParams P;
-  P.dw = dw; P.ldw = ldw; P.N = N; P.K = K; P.M = M;
+  P.dw = dw; P.ldw = ldw; P.db = db; P.N = N; P.K = K; P.M = M;
   P.vec4 = aligned16(dw) && (ldw * 4) % 16 == 0;
   P.nblk = K >= 256 ? 4 : (K + 63) / 64;
   P.BN = P.nblk * 64;
@@ -189,11 +195,6 @@ int linear_wgrad_tc(const void* dz, int64_t ldz, const void* a, int64_t lda, flo
   linear_wgrad_tc_kernel<<<grid, kWThreads, smem, stream>>>(P);
   CSWIN_LAUNCH_CHECK();
   g_tc_launches.fetch_add(1, std::memory_order_relaxed);
-  if (db != nullptr) {
-    dim3 g2((unsigned)((N + 31) / 32), (unsigned)std::min<int64_t>(ceil_div64(M, 64), 64));
-    colsum_bf16_kernel<<<g2, 256, 0, stream>>>((const __nv_bfloat16*)dz, ldz, db, M, N);
-    CSWIN_LAUNCH_CHECK();
-  }
   *handled = true;
   return CSWIN_OK;
 }
