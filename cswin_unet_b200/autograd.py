@@ -265,5 +265,26 @@ class CarafeReassembleFn(Function):
         return denc, dz, dbias.to(ctx.bd), None, None, None, None
 
 
+class CarafeHeadFn(Function):
+    """Folded segmentation head on the tape: enc (M, 144), z (M, zcols >= classes), folded bias (classes) -> fp32 NCHW logits
+    (cswin_unet.py:536-544 with CARAFE4.out and `output` folded into z's producer)."""
+
+    @staticmethod
+    def forward(ctx, enc, z, bias, B, H, W, up, n_classes):
+        logits, _ = ops.carafe_head(enc, z, bias.to(z.dtype), B, H, W, up, want_logits=True, logits_dtype=torch.float32,
+                                    n_classes=n_classes)
+        ctx.save_for_backward(enc, z)
+        ctx.geom, ctx.bd = (B, H, W, up, n_classes), bias.dtype
+        return logits
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dlogits):
+        enc, z = ctx.saved_tensors
+        B, H, W, up, nc = ctx.geom
+        denc, dz, dbias = ops.carafe_head_bwd(enc, z, dlogits, B, H, W, up, nc)
+        return denc, dz, dbias.to(ctx.bd), None, None, None, None, None
+
+
 def linear(a, w, bias=None, a2=None, residual=None, sample_scale=None, rps=0):
     return LinearFn.apply(a, w, bias, a2, residual, sample_scale, rps)

@@ -201,6 +201,14 @@ int cswin_carafe_reassemble_bwd(const void* enc, int64_t ldenc, const void* z, i
                                kappa_ws, B, H, W, C, up, dtype, (cudaStream_t)stream);
 }
 
+int cswin_carafe_head_bwd(const void* enc, int64_t ldenc, const void* z, int64_t ldz, const float* dlogits, void* denc,
+                          int64_t lddenc, void* dz, int64_t lddz, int32_t zcols, float* dbias, float* kws, int32_t B, int32_t H,
+                          int32_t W, int32_t C, int32_t up, int32_t dtype, cswin_stream_t stream) {
+  CSWIN_REQUIRE(valid_dtype(dtype) && B >= 0 && H > 0 && W > 0, CSWIN_ERR_INVALID, "carafe_head_bwd: bad arguments");
+  return carafe_head_bwd(enc, ldenc, z, ldz, dlogits, denc, lddenc, dz, lddz, zcols, dbias, kws, B, H, W, C, up, dtype,
+                         (cudaStream_t)stream);
+}
+
 int cswin_sgd_momentum_step(const cswin_sgd_chunk_t* chunks, int32_t n_chunks, const float* lr, float momentum,
                             float weight_decay, cswin_stream_t stream) {
   return sgd_momentum_step(chunks, n_chunks, lr, momentum, weight_decay, (cudaStream_t)stream);

@@ -415,6 +415,155 @@ __global__ void __launch_bounds__(256) carafe_bwd_b_kernel(const TG* __restrict_
   for (int j = 0; j < V; ++j) stf(dz + pix * lddz + lane * V + j, acc[j]);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Folded segmentation head backward (up = 4, NC classes, fp32 NCHW d logits).  Same work split as the forward head kernel:
+// Kernel A: one warp per (batch, low-res row, 8 low-res pixels), lane = (pixel, output sub-row) owning 4 output pixels:
+//           kappa recomputed from enc, d kappa = <d logits, z^>, softmax backward -> d enc; kappa parked tap-major for
+//           kernel B; d bias reduced warp -> CTA -> one atomic per class per CTA.
+// Kernel B: one warp per low-res pixel p', lane = (sub-pixel ae, class half): d z[p'] = sum_t sum_ae kappa[p'-off(t)][t][ae]
+//           * d logits[p'-off(t), ae]  (gather; no atomics), zero in the padded columns.
+template <typename T> __device__ __forceinline__ void ld4(const T* p, float (&o)[4]);
+template <> __device__ __forceinline__ void ld4<float>(const float* p, float (&o)[4]) {
+  const float4 v = *reinterpret_cast<const float4*>(p); o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+}
+template <> __device__ __forceinline__ void ld4<__nv_bfloat16>(const __nv_bfloat16* p, float (&o)[4]) {
+  const uint2 u = *reinterpret_cast<const uint2*>(p);
+  o[0] = __uint_as_float(u.x << 16); o[1] = __uint_as_float(u.x & 0xffff0000u);
+  o[2] = __uint_as_float(u.y << 16); o[3] = __uint_as_float(u.y & 0xffff0000u);
+}
+template <typename T> __device__ __forceinline__ void st4(T* p, const float (&v)[4]);
+template <> __device__ __forceinline__ void st4<float>(float* p, const float (&v)[4]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+template <> __device__ __forceinline__ void st4<__nv_bfloat16>(__nv_bfloat16* p, const float (&v)[4]) {
+  const __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+  *reinterpret_cast<uint2*>(p) = make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
+}
+
+template <typename T, int NC>
+__global__ void __launch_bounds__(256) carafe_head_bwd_a_kernel(const T* __restrict__ enc, int64_t ldenc, const T* __restrict__ z,
+                                                                 int64_t ldz, const float* __restrict__ dl, T* __restrict__ denc,
+                                                                 int64_t lddenc, float* __restrict__ kws, float* __restrict__ dbias,
+                                                                 int B, int H, int W) {
+  __shared__ float sdb[NC];
+  if (threadIdx.x < NC) sdb[threadIdx.x] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int xgroups = (W + 7) >> 3;
+  const int64_t wid = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const bool wvalid = wid < (int64_t)B * H * xgroups;
+  const int xg = (int)(wid % xgroups);
+  const int y0 = (int)((wid / xgroups) % H);
+  const int b = (int)(wid / ((int64_t)xgroups * H));
+  const int x0 = xg * 8 + (lane >> 2), ay = lane & 3;
+  const bool valid = wvalid && x0 < W;
+  const int Ho = H * 4, Wo = W * 4, oy = y0 * 4 + ay;
+  float dbl[NC];
+#pragma unroll
+  for (int c = 0; c < NC; ++c) dbl[c] = 0.f;
+  if (valid) {
+    const int64_t pix = ((int64_t)b * H + y0) * W + x0;
+    float k[9][4];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) ld4(enc + pix * ldenc + t * 16 + ay * 4, k[t]);
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      float mx = k[0][a];
+#pragma unroll
+      for (int t = 1; t < 9; ++t) mx = fmaxf(mx, k[t][a]);
+      float sum = 0.f;
+#pragma unroll
+      for (int t = 0; t < 9; ++t) { k[t][a] = expf(k[t][a] - mx); sum += k[t][a]; }
+      const float inv = 1.0f / sum;
+#pragma unroll
+      for (int t = 0; t < 9; ++t) k[t][a] *= inv;
+    }
+    float g[NC][4];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      ld4(dl + (((int64_t)b * NC + c) * Ho + oy) * Wo + x0 * 4, g[c]);
+      dbl[c] = (g[c][0] + g[c][1]) + (g[c][2] + g[c][3]);
+    }
+    float dk[9][4];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+#pragma unroll
+      for (int a = 0; a < 4; ++a) dk[t][a] = 0.f;
+      const int yy = y0 + t / 3 - 1, xx = x0 + t % 3 - 1;
+      if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+        const T* zr = z + (((int64_t)b * H + yy) * W + xx) * ldz;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          const float zc = ldf(zr + c);
+#pragma unroll
+          for (int a = 0; a < 4; ++a) dk[t][a] = fmaf(g[c][a], zc, dk[t][a]);
+        }
+      }
+    }
+    float dot[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+      for (int a = 0; a < 4; ++a) dot[a] = fmaf(k[t][a], dk[t][a], dot[a]);
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      float de[4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) de[a] = k[t][a] * (dk[t][a] - dot[a]);
+      st4(denc + pix * lddenc + t * 16 + ay * 4, de);
+      *reinterpret_cast<float4*>(kws + (pix * 9 + t) * 16 + ay * 4) = make_float4(k[t][0], k[t][1], k[t][2], k[t][3]);
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    const float sdbl = warp_sum(dbl[c]);
+    if (lane == 0 && sdbl != 0.f) atomicAdd(&sdb[c], sdbl);
+  }
+  __syncthreads();
+  if (threadIdx.x < NC && sdb[threadIdx.x] != 0.f) atomicAdd(dbias + threadIdx.x, sdb[threadIdx.x]);
+}
+
+template <typename T, int NC>
+__global__ void __launch_bounds__(256) carafe_head_bwd_b_kernel(const float* __restrict__ dl, const float* __restrict__ kws,
+                                                                 T* __restrict__ dz, int64_t lddz, int zcols, int64_t npix, int H, int W) {
+  constexpr int HC = (NC + 1) / 2;                                  // classes per lane half
+  const int lane = threadIdx.x & 31, ae = lane & 15, h = lane >> 4;
+  const int64_t pix = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (pix >= npix) return;
+  const int x0 = (int)(pix % W), y0 = (int)((pix / W) % H);
+  const int64_t b = pix / ((int64_t)W * H);
+  const int Ho = H * 4, Wo = W * 4;
+  float acc[HC];
+#pragma unroll
+  for (int j = 0; j < HC; ++j) acc[j] = 0.f;
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const int py = y0 - (t / 3 - 1), px = x0 - (t % 3 - 1);          // the pixel whose tap t reads (y0, x0)
+    if (py < 0 || py >= H || px < 0 || px >= W) continue;
+    const int64_t pp = (b * H + py) * W + px;
+    const float kv = kws[(pp * 9 + t) * 16 + ae];
+    const float* src = dl + ((b * NC) * Ho + py * 4 + (ae >> 2)) * (int64_t)Wo + px * 4 + (ae & 3);
+#pragma unroll
+    for (int j = 0; j < HC; ++j) {
+      const int c = h * HC + j;
+      if (c < NC) acc[j] = fmaf(kv, src[(int64_t)c * Ho * Wo], acc[j]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < HC; ++j) {
+#pragma unroll
+    for (int o = 1; o < 16; o <<= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
+  }
+  if (ae == 0) {
+#pragma unroll
+    for (int j = 0; j < HC; ++j) {
+      const int c = h * HC + j;
+      if (c < NC) stf(dz + pix * lddz + c, acc[j]);
+    }
+  }
+  if (lane >= NC && lane < zcols) stf(dz + pix * lddz + lane, 0.f);    // padded columns
+}
+
 unsigned grid_for(int64_t total, int per_cta) {
   return (unsigned)std::min<int64_t>(ceil_div64(total, per_cta), (int64_t)sm_count() * 32);
 }
@@ -597,6 +746,32 @@ int carafe_reassemble_bwd(const void* enc, int64_t ldenc, const void* z, int64_t
   if (dy_is_f32)
     return carafe_bwd_launch<__nv_bfloat16, float>(enc, ldenc, z, ldz, dy, sb, sy, sx, sc, denc, lddenc, dz, lddz, dbias, kws, npix, H, W, C, up, s);
   return carafe_bwd_launch<__nv_bfloat16, __nv_bfloat16>(enc, ldenc, z, ldz, dy, sb, sy, sx, sc, denc, lddenc, dz, lddz, dbias, kws, npix, H, W, C, up, s);
+}
+
+int carafe_head_bwd(const void* enc, int64_t ldenc, const void* z, int64_t ldz, const float* dlogits, void* denc, int64_t lddenc,
+                    void* dz, int64_t lddz, int zcols, float* dbias, float* kws, int B, int H, int W, int C, int up, int dtype,
+                    cudaStream_t s) {
+  CSWIN_REQUIRE(enc && z && dlogits && denc && dz && dbias && kws, CSWIN_ERR_INVALID, "carafe_head_bwd: null pointer");
+  CSWIN_REQUIRE(up == 4 && (C == 2 || C == 3 || C == 4 || C == 9), CSWIN_ERR_UNSUPPORTED,
+                "carafe_head_bwd: supported: up = 4 and 2, 3, 4 or 9 classes (got up=%d, %d classes)", up, C);
+  CSWIN_REQUIRE(ldenc >= 144 && lddenc >= 144 && ldz >= C && lddz >= zcols && zcols >= C && zcols <= 32, CSWIN_ERR_INVALID,
+                "carafe_head_bwd: bad leading dimensions");
+  const int es = dtype == CSWIN_F32 ? 4 : 2;
+  CSWIN_REQUIRE((ldenc * es) % (4 * es) == 0 && (lddenc * es) % (4 * es) == 0 && reinterpret_cast<uintptr_t>(enc) % (4 * es) == 0 &&
+                reinterpret_cast<uintptr_t>(denc) % (4 * es) == 0 && reinterpret_cast<uintptr_t>(dlogits) % 16 == 0 &&
+                reinterpret_cast<uintptr_t>(kws) % 16 == 0, CSWIN_ERR_UNSUPPORTED, "carafe_head_bwd: operands must be vector-aligned");
+  const int64_t npix = (int64_t)B * H * W;
+  if (npix == 0) return CSWIN_OK;
+  const unsigned ga = (unsigned)ceil_div64((int64_t)B * H * ((W + 7) / 8), 8), gb = (unsigned)ceil_div64(npix, 8);
+#define HB(T, NC_) do { \
+    carafe_head_bwd_a_kernel<T, NC_><<<ga, 256, 0, s>>>((const T*)enc, ldenc, (const T*)z, ldz, dlogits, (T*)denc, lddenc, kws, dbias, B, H, W); \
+    carafe_head_bwd_b_kernel<T, NC_><<<gb, 256, 0, s>>>(dlogits, kws, (T*)dz, lddz, zcols, npix, H, W); } while (0)
+#define HBT(NC_) do { if (dtype == CSWIN_F32) HB(float, NC_); else HB(__nv_bfloat16, NC_); } while (0)
+  if (C == 9) HBT(9); else if (C == 4) HBT(4); else if (C == 3) HBT(3); else HBT(2);
+#undef HBT
+#undef HB
+  CSWIN_LAUNCH_CHECK();
+  return CSWIN_OK;
 }
 
 }  // namespace cswin

@@ -17,6 +17,8 @@ from __future__ import annotations
 from typing import List, Optional, Sequence
 
 import numpy as np
+import os
+
 import torch
 import torch.nn as nn
 
@@ -25,6 +27,10 @@ from . import ops
 from .modules import CARAFE, CARAFE4, CSWinBlock, Merge_Block, _Native, _no_autograd
 
 Tensor = torch.Tensor
+
+
+# training head folded like the inference head (CSWIN_UNFOLDED_TRAIN_HEAD=1 restores the reference's unfolded structure)
+FOLD_TRAIN_HEAD = os.environ.get("CSWIN_UNFOLDED_TRAIN_HEAD") != "1"
 
 
 class CSWinTransformer(_Native):
@@ -160,8 +166,21 @@ class CSWinTransformer(_Native):
         B, L, Cn = x.shape
         H = W = int(round(L ** 0.5))
         up = self.upsample1
+        if (ag.needs_grad(x, self.output.weight, *up.parameters()) and FOLD_TRAIN_HEAD
+                and ops.carafe_head_bwd_supported(self.num_classes, up.up_factor)):
+            # training, folded like inference: W_f = W_output W_out and b_f = W_output b_out are formed ON THE TAPE (two tiny
+            # fp32 matmuls), so autograd turns the head kernel's d z / d bias into the gradients of both 1x1 convs; the
+            # (B, 16 L, 64) activation of the unfolded structure and its backward never exist
+            nc = self.num_classes
+            enc = up._kernel_logits_tape(x, H, W)
+            wo2 = self.output.weight.reshape(nc, -1).float()
+            wf = torch.nn.functional.pad(wo2 @ up.out.weight.reshape(up.out.weight.shape[0], -1).float(), (0, 0, 0, 16 - nc))
+            bf = wo2 @ up.out.bias.float()
+            z = ag.linear(x, wf, None)                                          # (B, L, 16); columns >= classes are 0
+            lg = ag.CarafeHeadFn.apply(enc, z.view(B * L, -1), bf, B, H, W, up.up_factor, nc)   # fp32 NCHW
+            return lg.to(logits_dtype) if logits_dtype is not None else lg
         if ag.needs_grad(x, self.output.weight, *up.parameters()):
-            # training: the reference's unfolded structure (CARAFE4 with its own `out` conv, then the `output` conv) so that
+            # training, CSWIN_UNFOLDED_TRAIN_HEAD=1 or an unsupported class count: the reference's unfolded structure (CARAFE4 with its own `out` conv, then the `output` conv) so that
             # every parameter receives its gradient from a native kernel; logits come back token-major and are viewed NCHW
             y = up(x)                                                           # (B, 16 L, 64)
             lg = ag.linear(y, self.output.weight.reshape(self.output.weight.shape[0], -1), None)

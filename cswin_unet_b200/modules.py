@@ -426,14 +426,18 @@ class CARAFE(_Native):
                                        lambda t: t.permute(0, 2, 3, 1).reshape(t.shape[0], -1)),
                           self._w("enc.b", self.encoder.bias, dt))                      # (B*L, 9 s^2)
 
+    def _kernel_logits_tape(self, x: Tensor, H: int, W: int) -> Tensor:
+        """_kernel_logits on the autograd tape (training)."""
+        d = ag.linear(x, self.down.weight.reshape(self.down.weight.shape[0], -1), self.down.bias)
+        col = ag.Im2colTokensFn.apply(d, H, W, 3, 3, 1, 1)
+        return ag.linear(col, self.encoder.weight.permute(0, 2, 3, 1).reshape(self.encoder.weight.shape[0], -1), self.encoder.bias)
+
     def forward(self, x: Tensor) -> Tensor:
         B, L, Cn = x.shape
         H = W = _side(L)
         if ag.needs_grad(x, *self.parameters()):
             rs = lambda t: t.reshape(t.shape[0], -1)
-            d = ag.linear(x, rs(self.down.weight), self.down.bias)
-            col = ag.Im2colTokensFn.apply(d, H, W, 3, 3, 1, 1)
-            enc = ag.linear(col, self.encoder.weight.permute(0, 2, 3, 1).reshape(self.encoder.weight.shape[0], -1), self.encoder.bias)
+            enc = self._kernel_logits_tape(x, H, W)
             z = ag.linear(x, rs(self.out.weight), None)
             return ag.CarafeReassembleFn.apply(enc, z.view(B * L, -1), self.out.bias, B, H, W, self.up_factor)
         dt = x.dtype

@@ -324,6 +324,26 @@ def carafe_head(enc: Tensor, z: Tensor, bias: Tensor, B: int, H: int, W: int, up
 # ----------------------------------------------------------------------------------------------
 # backward ops (training step)
 # ----------------------------------------------------------------------------------------------
+def carafe_head_bwd_supported(n_classes: int, up: int) -> bool:
+    return up == 4 and n_classes in (2, 3, 4, 9)
+
+
+def carafe_head_bwd(enc: Tensor, z: Tensor, dlogits: Tensor, B: int, H: int, W: int, up: int, n_classes: int):
+    """Backward of carafe_head: dlogits fp32 NCHW -> (d enc (M, 144) [row pitch padded to 16 B], d z like z, d bias fp32 (C))."""
+    _need_cuda(enc, z, dlogits)
+    dlogits = dlogits.float().contiguous()
+    M = B * H * W
+    assert dlogits.shape == (B, n_classes, H * up, W * up) and enc.shape[0] == M and z.shape[0] == M and enc.stride(1) == 1
+    ne = enc.shape[-1]
+    denc = torch.empty((M, (ne + 7) // 8 * 8), dtype=enc.dtype, device=enc.device)[:, :ne]
+    dz = torch.empty((M, z.shape[-1]), dtype=z.dtype, device=z.device)
+    dbias = torch.zeros(n_classes, dtype=torch.float32, device=z.device)
+    kws = torch.empty(M * ne, dtype=torch.float32, device=z.device)
+    check(lib().cswin_carafe_head_bwd(enc.data_ptr(), enc.stride(0), z.data_ptr(), z.stride(0), dlogits.data_ptr(),
+                                      denc.data_ptr(), denc.stride(0), dz.data_ptr(), dz.stride(0), z.shape[-1],
+                                      dbias.data_ptr(), kws.data_ptr(), B, H, W, n_classes, up, _dtype_code(z), _stream()),
+          "cswin_carafe_head_bwd")
+    return denc, dz, dbias
 def lepe_attention_bwd(branches: Sequence[dict], B: int, reso: int, scale: float, dtype: torch.dtype) -> None:
     """branches: forward description + dout, dq, dk, dv (views with unit channel stride), dconv_w (C_b,9) / dconv_b (C_b) fp32."""
     arr = (LepeBranchGrad * len(branches))()

@@ -165,6 +165,15 @@ typedef struct {
 int cswin_mlp_fwd(const cswin_mlp_args_t* args, int32_t dtype, cswin_stream_t stream);
 int32_t cswin_mlp_stats_parts(int32_t C, int32_t hidden);   /* 0 if the shape is unsupported */
 
+/* ---- backward of cswin_carafe_head_fwd (the folded CARAFE4 + out + output head, up = 4; 2, 3, 4 or 9 classes) ---------------
+ * dlogits: fp32 NCHW (B, C, 4H, 4W) contiguous.  Writes d enc (B*H*W, 144) and d z (B*H*W, zcols; columns >= C are zeroed),
+ * accumulates d bias (C, fp32, pre-zeroed by the caller).  kws: workspace of B*H*W*144 floats (the softmaxed kernels,
+ * tap-major).  The gradients of CARAFE4.out and of the `output` conv follow from d z / d bias by the chain rule of the fold
+ * W_f = W_output W_out, b_f = W_output b_out (host side, two 9x64 matmuls). */
+int cswin_carafe_head_bwd(const void* enc, int64_t ldenc, const void* z, int64_t ldz, const float* dlogits, void* denc,
+                          int64_t lddenc, void* dz, int64_t lddz, int32_t zcols, float* dbias, float* kws, int32_t B, int32_t H,
+                          int32_t W, int32_t C, int32_t up, int32_t dtype, cswin_stream_t stream);
+
 /* ---- optimizer step of the data-parallel training path: torch.optim.SGD(momentum, weight_decay).step() -------------------
  * replaces `optimizer.step()` of trainer.py:42/:61 (SGD lr 0.05 poly-decayed, momentum 0.9, weight decay 1e-4) for ALL
  * parameters in one launch, and refreshes the bf16 copy of each weight that the next forward's tcgen05 kernels stream:
