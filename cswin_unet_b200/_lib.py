@@ -85,6 +85,9 @@ SIGNATURES = {
     "cswin_linear_fwd": (c_int32, [C.POINTER(LinearArgs), c_int32, c_void_p]),
     "cswin_carafe_head_bwd": (c_int32, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int64,
                                         c_int32, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]),
+    "cswin_seg_loss_fwd": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_int64, c_int32, c_int64, c_void_p]),
+    "cswin_seg_loss_bwd": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_float, c_float, c_int64, c_int32,
+                                     c_int64, c_void_p]),
     "cswin_sgd_momentum_step": (c_int32, [c_void_p, c_int32, c_void_p, c_float, c_float, c_void_p]),
     "cswin_mlp_fwd": (c_int32, [C.POINTER(MlpArgs), c_int32, c_void_p]),
     "cswin_mlp_stats_parts": (c_int32, [c_int32, c_int32]),

@@ -286,5 +286,26 @@ class CarafeHeadFn(Function):
         return denc, dz, dbias.to(ctx.bd), None, None, None, None, None
 
 
+class SegLossFn(Function):
+    """w_ce * CE + w_dice * Dice(softmax) on fp32 NCHW logits (trainer.py:55-57, utils.py:9-45): one native pass each way."""
+
+    @staticmethod
+    def forward(ctx, logits, labels, w_ce, w_dice):
+        sums = ops.seg_loss_fwd(logits, labels)
+        nc = logits.shape[1]
+        npix = labels.numel()
+        inter, z, y = sums[1:1 + nc], sums[1 + nc:1 + 2 * nc], sums[1 + 2 * nc:1 + 3 * nc]
+        loss = w_ce * sums[0] / npix + w_dice * (1.0 - (2 * inter + 1e-5) / (z + y + 1e-5)).mean()
+        ctx.save_for_backward(logits, labels, sums)
+        ctx.w = (w_ce, w_dice)
+        return loss
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gout):
+        logits, labels, sums = ctx.saved_tensors
+        return ops.seg_loss_bwd(logits, labels, sums, gout, *ctx.w), None, None, None
+
+
 def linear(a, w, bias=None, a2=None, residual=None, sample_scale=None, rps=0):
     return LinearFn.apply(a, w, bias, a2, residual, sample_scale, rps)

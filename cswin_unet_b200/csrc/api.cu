@@ -209,6 +209,16 @@ int cswin_carafe_head_bwd(const void* enc, int64_t ldenc, const void* z, int64_t
                          (cudaStream_t)stream);
 }
 
+int cswin_seg_loss_fwd(const float* logits, const void* labels, int32_t label_bytes, float* sums, int64_t B, int32_t C, int64_t HW,
+                       cswin_stream_t stream) {
+  return seg_loss_fwd(logits, labels, label_bytes, sums, B, C, HW, (cudaStream_t)stream);
+}
+
+int cswin_seg_loss_bwd(const float* logits, const void* labels, int32_t label_bytes, const float* sums, const float* grad_out,
+                       float* dlogits, float w_ce, float w_dice, int64_t B, int32_t C, int64_t HW, cswin_stream_t stream) {
+  return seg_loss_bwd(logits, labels, label_bytes, sums, grad_out, dlogits, w_ce, w_dice, B, C, HW, (cudaStream_t)stream);
+}
+
 int cswin_sgd_momentum_step(const cswin_sgd_chunk_t* chunks, int32_t n_chunks, const float* lr, float momentum,
                             float weight_decay, cswin_stream_t stream) {
   return sgd_momentum_step(chunks, n_chunks, lr, momentum, weight_decay, (cudaStream_t)stream);

@@ -564,6 +564,98 @@ __global__ void __launch_bounds__(256) carafe_head_bwd_b_kernel(const float* __r
   if (lane >= NC && lane < zcols) stf(dz + pix * lddz + lane, 0.f);    // padded columns
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Segmentation loss of the baseline trainer: w_ce * CrossEntropy + w_dice * DiceLoss(softmax=True)  (trainer.py:55-57,
+// utils.py:9-45) on fp32 NCHW logits, two passes over the logits in total:
+//   forward : per pixel softmax; sums[0] += -log p[y]; per class c: sums[1+c] += p_c [y==c] (I), sums[1+NC+c] += p_c^2 (Z),
+//             sums[1+2NC+c] += [y==c] (Y)   -> loss = w_ce sums[0]/P + w_dice mean_c (1 - (2I+s)/(Z+Y+s)), s = 1e-5
+//   backward: d logit_c = gout * ( w_ce/P (p_c - [y==c]) + p_c (q_c - sum_k p_k q_k) ),
+//             q_c = -w_dice/NC * (2 [y==c] D_c - 2 p_c N_c) / D_c^2,  N_c = 2I_c + s, D_c = Z_c + Y_c + s.
+template <int NC> __device__ __forceinline__ int load_label(const void* lab, int lbytes, int64_t i) {
+  return lbytes == 8 ? (int)reinterpret_cast<const long long*>(lab)[i] : lbytes == 4 ? reinterpret_cast<const int*>(lab)[i]
+                                                                                      : (int)reinterpret_cast<const uint8_t*>(lab)[i];
+}
+
+template <int NC>
+__global__ void __launch_bounds__(256) seg_loss_fwd_kernel(const float* __restrict__ logits, const void* __restrict__ labels,
+                                                            int lbytes, float* __restrict__ sums, int64_t B, int64_t HW) {
+  float acc[1 + 3 * NC];
+#pragma unroll
+  for (int j = 0; j < 1 + 3 * NC; ++j) acc[j] = 0.f;
+  const int64_t total = B * HW;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = i / HW, px = i - b * HW;
+    const float* lp = logits + b * NC * HW + px;
+    float l[NC], mx = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) { l[c] = lp[(int64_t)c * HW]; mx = fmaxf(mx, l[c]); }
+    float sum = 0.f;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) { l[c] = __expf(l[c] - mx); sum += l[c]; }
+    const float inv = 1.0f / sum;
+    const int y = load_label<NC>(labels, lbytes, i);
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const float p = l[c] * inv;
+      if (c == y) { acc[0] -= __logf(fmaxf(p, 1e-38f)); acc[1 + c] += p; acc[1 + 2 * NC + c] += 1.f; }
+      acc[1 + NC + c] = fmaf(p, p, acc[1 + NC + c]);
+    }
+  }
+  __shared__ float red[8][1 + 3 * NC];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int j = 0; j < 1 + 3 * NC; ++j) {
+    const float v = warp_sum(acc[j]);
+    if (lane == 0) red[w][j] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 1 + 3 * NC) {
+    float v = 0.f;
+#pragma unroll
+    for (int ww = 0; ww < 8; ++ww) v += red[ww][threadIdx.x];
+    atomicAdd(sums + threadIdx.x, v);
+  }
+}
+
+template <int NC>
+__global__ void __launch_bounds__(256) seg_loss_bwd_kernel(const float* __restrict__ logits, const void* __restrict__ labels,
+                                                            int lbytes, const float* __restrict__ sums, const float* __restrict__ gout,
+                                                            float* __restrict__ dlogits, float w_ce, float w_dice, int64_t B, int64_t HW) {
+  const int64_t total = B * HW;
+  const float go = *gout;
+  const float ce_scale = go * w_ce / (float)total;
+  float a_y[NC], a_p[NC];                         // q_c = a_y[c] [y==c] + a_p[c] p_c
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    const float N = 2.f * sums[1 + c] + 1e-5f, D = sums[1 + NC + c] + sums[1 + 2 * NC + c] + 1e-5f;
+    const float k = -go * w_dice / ((float)NC * D * D);
+    a_y[c] = k * 2.f * D;
+    a_p[c] = -k * 2.f * N;
+  }
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = i / HW, px = i - b * HW;
+    const float* lp = logits + b * NC * HW + px;
+    float p[NC], mx = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) { p[c] = lp[(int64_t)c * HW]; mx = fmaxf(mx, p[c]); }
+    float sum = 0.f;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) { p[c] = __expf(p[c] - mx); sum += p[c]; }
+    const float inv = 1.0f / sum;
+    const int y = load_label<NC>(labels, lbytes, i);
+    float q[NC], dot = 0.f;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      p[c] *= inv;
+      q[c] = fmaf(a_p[c], p[c], c == y ? a_y[c] : 0.f);
+      dot = fmaf(p[c], q[c], dot);
+    }
+    float* dp = dlogits + b * NC * HW + px;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) dp[(int64_t)c * HW] = fmaf(ce_scale, p[c] - (c == y ? 1.f : 0.f), p[c] * (q[c] - dot));
+  }
+}
+
 unsigned grid_for(int64_t total, int per_cta) {
   return (unsigned)std::min<int64_t>(ceil_div64(total, per_cta), (int64_t)sm_count() * 32);
 }
@@ -770,6 +862,33 @@ int carafe_head_bwd(const void* enc, int64_t ldenc, const void* z, int64_t ldz, 
   if (C == 9) HBT(9); else if (C == 4) HBT(4); else if (C == 3) HBT(3); else HBT(2);
 #undef HBT
 #undef HB
+  CSWIN_LAUNCH_CHECK();
+  return CSWIN_OK;
+}
+
+int seg_loss_fwd(const float* logits, const void* labels, int label_bytes, float* sums, int64_t B, int C, int64_t HW, cudaStream_t s) {
+  CSWIN_REQUIRE(logits && labels && sums && B >= 0 && HW > 0, CSWIN_ERR_INVALID, "seg_loss_fwd: bad arguments");
+  CSWIN_REQUIRE(label_bytes == 1 || label_bytes == 4 || label_bytes == 8, CSWIN_ERR_INVALID, "seg_loss: labels must be uint8, int32 or int64");
+  CSWIN_REQUIRE(C == 2 || C == 3 || C == 4 || C == 9, CSWIN_ERR_UNSUPPORTED, "seg_loss: supported class counts: 2, 3, 4, 9 (got %d)", C);
+  if (B == 0) return CSWIN_OK;
+  const unsigned grid = (unsigned)std::min<int64_t>(ceil_div64(B * HW, 256), (int64_t)sm_count() * 8);
+#define SL(NC_) seg_loss_fwd_kernel<NC_><<<grid, 256, 0, s>>>(logits, labels, label_bytes, sums, B, HW)
+  if (C == 9) SL(9); else if (C == 4) SL(4); else if (C == 3) SL(3); else SL(2);
+#undef SL
+  CSWIN_LAUNCH_CHECK();
+  return CSWIN_OK;
+}
+
+int seg_loss_bwd(const float* logits, const void* labels, int label_bytes, const float* sums, const float* gout, float* dlogits,
+                 float w_ce, float w_dice, int64_t B, int C, int64_t HW, cudaStream_t s) {
+  CSWIN_REQUIRE(logits && labels && sums && gout && dlogits && B >= 0 && HW > 0, CSWIN_ERR_INVALID, "seg_loss_bwd: bad arguments");
+  CSWIN_REQUIRE(label_bytes == 1 || label_bytes == 4 || label_bytes == 8, CSWIN_ERR_INVALID, "seg_loss: labels must be uint8, int32 or int64");
+  CSWIN_REQUIRE(C == 2 || C == 3 || C == 4 || C == 9, CSWIN_ERR_UNSUPPORTED, "seg_loss: supported class counts: 2, 3, 4, 9 (got %d)", C);
+  if (B == 0) return CSWIN_OK;
+  const unsigned grid = (unsigned)std::min<int64_t>(ceil_div64(B * HW, 256), (int64_t)sm_count() * 16);
+#define SL(NC_) seg_loss_bwd_kernel<NC_><<<grid, 256, 0, s>>>(logits, labels, label_bytes, sums, gout, dlogits, w_ce, w_dice, B, HW)
+  if (C == 9) SL(9); else if (C == 4) SL(4); else if (C == 3) SL(3); else SL(2);
+#undef SL
   CSWIN_LAUNCH_CHECK();
   return CSWIN_OK;
 }

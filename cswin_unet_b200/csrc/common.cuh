@@ -102,6 +102,9 @@ int row_stats(const void* x, int64_t ldx, int64_t M, int C, float* stats, int dt
 int carafe_head_bwd(const void* enc, int64_t ldenc, const void* z, int64_t ldz, const float* dlogits, void* denc, int64_t lddenc,
                     void* dz, int64_t lddz, int zcols, float* dbias, float* kws, int B, int H, int W, int C, int up, int dtype,
                     cudaStream_t s);
+int seg_loss_fwd(const float* logits, const void* labels, int label_bytes, float* sums, int64_t B, int C, int64_t HW, cudaStream_t s);
+int seg_loss_bwd(const float* logits, const void* labels, int label_bytes, const float* sums, const float* gout, float* dlogits,
+                 float w_ce, float w_dice, int64_t B, int C, int64_t HW, cudaStream_t s);
 int sgd_momentum_step(const cswin_sgd_chunk_t* chunks, int n_chunks, const float* lr, float momentum, float wd, cudaStream_t s);
 int mlp_fwd_tc(const cswin_mlp_args_t* a, cudaStream_t stream);
 int mlp_tc_stats_parts(int C, int hidden);

@@ -324,6 +324,38 @@ def carafe_head(enc: Tensor, z: Tensor, bias: Tensor, B: int, H: int, W: int, up
 # ----------------------------------------------------------------------------------------------
 # backward ops (training step)
 # ----------------------------------------------------------------------------------------------
+def seg_loss_supported(n_classes: int) -> bool:
+    return n_classes in (2, 3, 4, 9)
+
+
+def _label_bytes(labels: Tensor) -> int:
+    return {torch.uint8: 1, torch.int32: 4, torch.int64: 8}[labels.dtype]
+
+
+def seg_loss_fwd(logits: Tensor, labels: Tensor) -> Tensor:
+    """logits fp32 NCHW contiguous, labels (B, H, W) uint8/int32/int64 -> sums (1 + 3C) fp32 (see cswin_seg_loss_fwd)."""
+    _need_cuda(logits, labels)
+    assert logits.dtype == torch.float32 and logits.is_contiguous() and labels.is_contiguous()
+    B, Cn = logits.shape[:2]
+    HW = logits[0, 0].numel()
+    assert labels.numel() == B * HW
+    sums = torch.zeros(1 + 3 * Cn, dtype=torch.float32, device=logits.device)
+    check(lib().cswin_seg_loss_fwd(logits.data_ptr(), labels.data_ptr(), _label_bytes(labels), sums.data_ptr(), B, Cn, HW, _stream()),
+          "cswin_seg_loss_fwd")
+    return sums
+
+
+def seg_loss_bwd(logits: Tensor, labels: Tensor, sums: Tensor, grad_out: Tensor, w_ce: float, w_dice: float) -> Tensor:
+    _need_cuda(logits, labels, sums, grad_out)
+    B, Cn = logits.shape[:2]
+    HW = logits[0, 0].numel()
+    go = grad_out.reshape(1).float().contiguous()
+    dl = torch.empty_like(logits)
+    check(lib().cswin_seg_loss_bwd(logits.data_ptr(), labels.data_ptr(), _label_bytes(labels), sums.data_ptr(), go.data_ptr(),
+                                   dl.data_ptr(), w_ce, w_dice, B, Cn, HW, _stream()), "cswin_seg_loss_bwd")
+    return dl
+
+
 def carafe_head_bwd_supported(n_classes: int, up: int) -> bool:
     return up == 4 and n_classes in (2, 3, 4, 9)
 

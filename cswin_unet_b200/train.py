@@ -23,11 +23,15 @@ from . import ops
 from . import parallel
 
 Tensor = torch.Tensor
+NATIVE_LOSS = os.environ.get("CSWIN_TORCH_LOSS") != "1"
 
 
 def seg_loss(logits: Tensor, target: Tensor, n_classes: int) -> Tensor:
     """0.4 * CrossEntropy + 0.6 * DiceLoss(softmax=True)   (trainer.py:55-57, utils.py:9-45)."""
     logits = logits.float()
+    if (logits.is_cuda and NATIVE_LOSS and ops.seg_loss_supported(n_classes) and logits.shape[1] == n_classes
+            and target.dtype in (torch.uint8, torch.int32, torch.int64)):
+        return ag.SegLossFn.apply(logits.contiguous(), target.contiguous(), 0.4, 0.6)   # native: one pass each way
     ce = F.cross_entropy(logits, target.long())
     prob = torch.softmax(logits, dim=1)
     # (F.one_hot validates its input with a host sync, which would break CUDA-graph capture of the step)

@@ -174,6 +174,18 @@ int cswin_carafe_head_bwd(const void* enc, int64_t ldenc, const void* z, int64_t
                           int64_t lddenc, void* dz, int64_t lddz, int32_t zcols, float* dbias, float* kws, int32_t B, int32_t H,
                           int32_t W, int32_t C, int32_t up, int32_t dtype, cswin_stream_t stream);
 
+/* ---- training loss of the baseline trainer: w_ce * CrossEntropy + w_dice * DiceLoss(softmax=True) --------------------------
+ * replaces trainer.py:55-57 (`loss_ce`, `loss_dice`, 0.4 / 0.6 mix) with utils.py:9-45 (DiceLoss: per-class ratio of sums over the
+ * whole LOCAL batch, smooth 1e-5) — two passes over the fp32 NCHW logits (B, C, HW) instead of ~25 element-wise kernels.
+ * labels: (B, HW) uint8 / int32 / int64 (label_bytes = 1 / 4 / 8).  sums: 1 + 3C floats, ZEROED by the caller; after fwd:
+ * sums[0] = sum of -log p[y], sums[1..C] = I_c, sums[1+C..2C] = Z_c, sums[1+2C..3C] = Y_c; the scalar loss is
+ * w_ce * sums[0] / (B HW) + w_dice * mean_c (1 - (2 I_c + 1e-5) / (Z_c + Y_c + 1e-5)) (formed by the caller).
+ * bwd: dlogits = *grad_out * d loss / d logits, grad_out a DEVICE scalar.  Supported C: 2, 3, 4, 9. */
+int cswin_seg_loss_fwd(const float* logits, const void* labels, int32_t label_bytes, float* sums, int64_t B, int32_t C, int64_t HW,
+                       cswin_stream_t stream);
+int cswin_seg_loss_bwd(const float* logits, const void* labels, int32_t label_bytes, const float* sums, const float* grad_out,
+                       float* dlogits, float w_ce, float w_dice, int64_t B, int32_t C, int64_t HW, cswin_stream_t stream);
+
 /* ---- optimizer step of the data-parallel training path: torch.optim.SGD(momentum, weight_decay).step() -------------------
  * replaces `optimizer.step()` of trainer.py:42/:61 (SGD lr 0.05 poly-decayed, momentum 0.9, weight decay 1e-4) for ALL
  * parameters in one launch, and refreshes the bf16 copy of each weight that the next forward's tcgen05 kernels stream:

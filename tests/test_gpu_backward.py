@@ -274,3 +274,21 @@ def test_train_step_native_sgd_follows_torch_sgd_trajectory(monkeypatch):
     assert ln[-1] < ln[0]
     assert max(abs(a - b) for a, b in zip(ln, lt)) <= 3e-2
     assert cos(out["native"][1], out["torch"][1]) >= 0.9999
+
+
+@pytest.mark.parametrize("nc,ldt", [(9, torch.int64), (9, torch.uint8), (4, torch.int32), (3, torch.int64), (2, torch.uint8)])
+def test_native_seg_loss_matches_oracle(nc, ldt):
+    """cswin_seg_loss_fwd/bwd == 0.4 CE + 0.6 DiceLoss(softmax=True) of trainer.py:55-57 / utils.py:9-45 (oracle, fp64 autograd),
+    including classes that never occur in the labels and an upstream gradient != 1."""
+    from cswin_unet_b200 import train as T_
+    g = torch.Generator().manual_seed(nc)
+    logits = (torch.randn(3, nc, 40, 56, generator=g) * 2.0)
+    labels = torch.randint(0, max(nc - 1, 1), (3, 40, 56), generator=g)          # the last class never occurs (for nc > 1)
+    lo = logits.double().requires_grad_(True)
+    ref = O.seg_loss(lo, labels, nc)
+    (ref * 1.7).backward()
+    ln = logits.to(DEV).requires_grad_(True)
+    got = T_.seg_loss(ln, labels.to(ldt).to(DEV), nc)
+    (got * 1.7).backward()
+    assert abs(float(got) - float(ref)) <= 2e-6 * max(1.0, abs(float(ref)))
+    assert rel(ln.grad, lo.grad) <= 2e-5
