@@ -39,13 +39,13 @@ constexpr int kMaxStages = 8;
 constexpr int kThreads = 320;                          // warp 0 TMA, warp 1 MMA + TMEM, warps 2..9 epilogue
 
 struct alignas(64) GemmTcParams {
-  CUtensorMap map_a, map_a2, map_w;
+  CUtensorMap map_a, map_a2, map_w, map_out;
   const __nv_bfloat16* bias;
   const __nv_bfloat16* res; int64_t ldr;
   const float* sscale; int rps;
   __nv_bfloat16* out; int64_t ldo;
   int64_t M; int N; int K1; int K2;
-  int BN, stages, nkb, nkb1, act, tmem_cols, vec_ok, bias_vec, w_kn;
+  int BN, stages, nkb, nkb1, act, tmem_cols, vec_ok, bias_vec, w_kn, tma_out;
   const float* ln_stats; int ln_parts; float ln_invC, ln_eps;
   const float* ln_cs; const float* bias_f32; float* stats_out;
   unsigned long long* trace;
@@ -186,6 +186,81 @@ __global__ void __launch_bounds__(kThreads, 2) linear_tc_kernel(const __grid_con
     if (warp == 2 && lane == 0) trace_stamp(P.trace, 5);  // accumulator ready
     tc_fence_after();
     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+    if (P.tma_out) {
+      // ---- fast path (16-byte aligned rows, N % 8 == 0): everything happens in the accumulator layout (thread = row): bias /
+      //      GELU / scale -> bf16 -> residual add (packed bf16x2) -> row statistics -> 64B-swizzled staging box -> one TMA
+      //      store per 32 x 32 unit.  No shared-memory read-back, no per-thread global stores, ragged edges clipped by TMA.
+      for (int u = ch; u < nunits; u += 2) {
+        uint32_t v[32];
+        tmem_ld32(trow + u * 32, v);
+        uint4 rv[4];
+        const int ncol = n0 + u * 32;
+        const bool has_res = P.res != nullptr && mrow < P.M;
+        if (has_res) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            rv[c] = (ncol + c * 8 < P.N) ? *reinterpret_cast<const uint4*>(P.res + mrow * P.ldr + ncol + c * 8) : make_uint4(0, 0, 0, 0);
+        }
+        tmem_wait_ld();
+        const float4* b4 = reinterpret_cast<const float4*>(sBias + u * 32);
+        const float4* c4 = reinterpret_cast<const float4*>(sCs + u * 32);
+        if (u != ch) {                                    // the previous unit's TMA store must have finished reading the staging box
+          if (lane == 0) tma_store_wait_read();
+          __syncwarp();
+        }
+        float st1 = 0.f, st2 = 0.f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          float f[8];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const float4 bb = b4[c * 2 + h];
+            if (kFold) {
+              const float4 cc = c4[c * 2 + h];
+              f[h * 4 + 0] = fmaf(ln_rstd, fmaf(-ln_mean, cc.x, __uint_as_float(v[c * 8 + h * 4 + 0])), bb.x);
+              f[h * 4 + 1] = fmaf(ln_rstd, fmaf(-ln_mean, cc.y, __uint_as_float(v[c * 8 + h * 4 + 1])), bb.y);
+              f[h * 4 + 2] = fmaf(ln_rstd, fmaf(-ln_mean, cc.z, __uint_as_float(v[c * 8 + h * 4 + 2])), bb.z);
+              f[h * 4 + 3] = fmaf(ln_rstd, fmaf(-ln_mean, cc.w, __uint_as_float(v[c * 8 + h * 4 + 3])), bb.w);
+            } else {
+              f[h * 4 + 0] = __uint_as_float(v[c * 8 + h * 4 + 0]) + bb.x;
+              f[h * 4 + 1] = __uint_as_float(v[c * 8 + h * 4 + 1]) + bb.y;
+              f[h * 4 + 2] = __uint_as_float(v[c * 8 + h * 4 + 2]) + bb.z;
+              f[h * 4 + 3] = __uint_as_float(v[c * 8 + h * 4 + 3]) + bb.w;
+            }
+          }
+          if (P.act == 1) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = gelu_fast(f[e]);
+          }
+          if (P.sscale != nullptr) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] *= sc;
+          }
+          uint4 x = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+          if (has_res) {
+            x.x = add_bf16x2(x.x, rv[c].x); x.y = add_bf16x2(x.y, rv[c].y);
+            x.z = add_bf16x2(x.z, rv[c].z); x.w = add_bf16x2(x.w, rv[c].w);
+          }
+          if (kStats && ncol + c * 8 < P.N) {             // (sum, sum^2) of the bf16 values this row contributes
+            const float e0 = bf16_lo(x.x), e1 = bf16_hi(x.x), e2 = bf16_lo(x.y), e3 = bf16_hi(x.y);
+            const float e4 = bf16_lo(x.z), e5 = bf16_hi(x.z), e6 = bf16_lo(x.w), e7 = bf16_hi(x.w);
+            st1 += ((e0 + e1) + (e2 + e3)) + ((e4 + e5) + (e6 + e7));
+            st2 = fmaf(e0, e0, fmaf(e1, e1, fmaf(e2, e2, fmaf(e3, e3, fmaf(e4, e4, fmaf(e5, e5, fmaf(e6, e6, fmaf(e7, e7, st2))))))));
+          }
+          const uint32_t addr = stg_u32 + lane * 64 + (((c ^ (lane >> 1)) & 3) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(x.x), "r"(x.y), "r"(x.z), "r"(x.w) : "memory");
+        }
+        if (kStats) { atomicAdd(&sStat[(q * 32 + lane) * 2], st1); atomicAdd(&sStat[(q * 32 + lane) * 2 + 1], st2); }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&P.map_out, stg_u32, ncol, (int)(m0 + q * 32));
+          tma_store_commit();
+        }
+      }
+      if (lane == 0) tma_store_wait_read();               // shared memory may be released / re-used after this
+      __syncwarp();
+    } else
     for (int u = ch; u < nunits; u += 2) {
       uint32_t v[32];
       PSTAMP(8);
@@ -308,6 +383,7 @@ __global__ void __launch_bounds__(kThreads, 2) linear_tc_kernel(const __grid_con
 }
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+bool no_tma_out() { static const bool v = [] { const char* e = getenv("CSWIN_GEMM_TMA_OUT"); return e && e[0] == '0'; }(); return v; }  // A/B switch
 
 size_t smem_bytes(int bn, int stages) {
   const size_t ring = (size_t)stages * (BM * BK * 2 + (size_t)bn * BK * 2);     // >= 18 KB > the aliased 16 KB staging
@@ -387,6 +463,12 @@ int linear_fwd_tc(const cswin_linear_args_t* a, cudaStream_t stream, bool* handl
   P.trace = g_trace.load(std::memory_order_relaxed);
   P.vec_ok = aligned16(a->out) && (a->ldo * 2) % 16 == 0 &&
              (a->residual == nullptr || (aligned16(a->residual) && (a->ldr * 2) % 16 == 0));
+  P.tma_out = P.vec_ok && a->N % 8 == 0 && !no_tma_out();
+  if (P.tma_out) {
+    const uint64_t dims[2] = {(uint64_t)a->N, (uint64_t)a->M}, str[1] = {(uint64_t)a->ldo * 2};
+    const uint32_t box[2] = {32, 32};
+    if (!tc::make_tensor_map_bf16(&P.map_out, a->out, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B)) return CSWIN_ERR_CUDA;
+  }
   if (a->stats_out != nullptr && !P.vec_ok) { set_error("linear_fwd: stats_out needs 16-byte aligned output rows"); return CSWIN_ERR_UNSUPPORTED; }
 
   {

@@ -5,8 +5,8 @@
 
 One process per GPU; with torch.distributed initialised the only exchange is the bucketed NCCL all-reduce of the
 23.57 M gradients (`parallel.allreduce_gradients`) — the reference uses single-process nn.DataParallel
-(trainer.py:37-38).  Loss and optimizer are harness-level torch code (not yet fused); the Dice term is
-formed per rank (a ratio of sums over the LOCAL batch), as SURVEY 8e notes.
+(trainer.py:37-38).  Loss (cswin_seg_loss_fwd/bwd) and optimizer (cswin_sgd_momentum_step) are native too (SURVEY 8f
+rank 3); the Dice term is formed per rank (a ratio of sums over the LOCAL batch), as SURVEY 8e notes.
 The reference's logging `.item()` calls (>= 11 host syncs per step) are not reproduced: the step returns a device tensor.
 """
 from __future__ import annotations
@@ -73,6 +73,7 @@ class TrainStep:
         self.use_graph = graph
         self.warmup = warmup
         self._graphs = None
+        self.native_launches_per_step = 0
         self._static = None
         self._seen = 0
         self._make_shadow(compute_dtype)
@@ -150,6 +151,8 @@ class TrainStep:
         self._static = (images.clone(), labels.clone())
         sx, sy = self._static
         self.opt.zero_grad(set_to_none=True)
+        from ._lib import launch_count
+        n0 = launch_count()
         g1 = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g1):                         # forward + backward (+ optimizer when single-rank)
             self._loss = self._fwd_bwd(sx, sy)
@@ -161,6 +164,7 @@ class TrainStep:
             with torch.cuda.graph(g2, pool=g1.pool()):
                 self._optimizer_step()
         self._graphs = (g1, g2)
+        self.native_launches_per_step = launch_count() - n0        # launches of this library recorded into the graph(s)
 
     def _check_external_writes(self) -> None:
         """The native step writes parameters through raw pointers (no version bump): a changed `_version` means someone else
