@@ -92,6 +92,8 @@ SIGNATURES = {
     "cswin_mlp_fwd": (c_int32, [C.POINTER(MlpArgs), c_int32, c_void_p]),
     "cswin_mlp_stats_parts": (c_int32, [c_int32, c_int32]),
     "cswin_linear_stats_parts": (c_int32, [c_int64, c_int32, c_int32, c_int32]),
+    "cswin_layernorm_stats_fwd": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int32, c_float,
+                                            c_void_p, c_int32, c_void_p]),
     "cswin_row_stats": (c_int32, [c_void_p, c_int64, c_int64, c_int32, c_void_p, c_int32, c_void_p]),
     "cswin_im2col_tokens": (c_int32, [c_void_p, c_int64, c_int64, c_void_p, c_int64] + [c_int32] * 9 + [c_void_p]),
     "cswin_im2col_nchw": (c_int32, [c_void_p, c_int32, c_void_p, c_int64] + [c_int32] * 9 + [c_void_p]),

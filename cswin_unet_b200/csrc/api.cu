@@ -90,7 +90,13 @@ int cswin_layernorm_fwd(const void* x, int64_t ldx, const void* gamma, const voi
                         cswin_stream_t stream) {
   CSWIN_REQUIRE(valid_dtype(dtype), CSWIN_ERR_INVALID, "layernorm_fwd: bad dtype %d", dtype);
   CSWIN_REQUIRE(M >= 0, CSWIN_ERR_INVALID, "layernorm_fwd: negative M");
-  return layernorm_fwd(x, ldx, gamma, beta, y, ldy, M, C, eps, mean_out, rstd_out, dtype, (cudaStream_t)stream);
+  return layernorm_fwd(x, ldx, gamma, beta, y, ldy, M, C, eps, mean_out, rstd_out, nullptr, dtype, (cudaStream_t)stream);
+}
+
+int cswin_layernorm_stats_fwd(const void* x, int64_t ldx, const void* gamma, const void* beta, void* y, int64_t ldy,
+                              int64_t M, int32_t C, float eps, float* row_stats_out, int32_t dtype, cswin_stream_t stream) {
+  CSWIN_REQUIRE(valid_dtype(dtype) && M >= 0 && row_stats_out, CSWIN_ERR_INVALID, "layernorm_stats_fwd: bad arguments");
+  return layernorm_fwd(x, ldx, gamma, beta, y, ldy, M, C, eps, nullptr, nullptr, row_stats_out, dtype, (cudaStream_t)stream);
 }
 
 int cswin_linear_fwd(const cswin_linear_args_t* a, int32_t dtype, cswin_stream_t stream) {

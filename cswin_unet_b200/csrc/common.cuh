@@ -97,7 +97,7 @@ int lepe_attention_fwd_tc(const cswin_lepe_branch_t* br, int nb, int B, int reso
 int lepe_attention_bwd_tc(const cswin_lepe_branch_grad_t* br, int nb, int B, int reso, float scale, cudaStream_t s, bool* handled);
 int lepe_attention_bwd_simt(const cswin_lepe_branch_grad_t* br, int nb, int B, int reso, float scale, int dtype, cudaStream_t s);
 int layernorm_fwd(const void* x, int64_t ldx, const void* g, const void* b, void* y, int64_t ldy, int64_t M, int C,
-                  float eps, float* mean, float* rstd, int dtype, cudaStream_t s);
+                  float eps, float* mean, float* rstd, float* ystats, int dtype, cudaStream_t s);
 int row_stats(const void* x, int64_t ldx, int64_t M, int C, float* stats, int dtype, cudaStream_t s);
 int carafe_head_bwd(const void* enc, int64_t ldenc, const void* z, int64_t ldz, const float* dlogits, void* denc, int64_t lddenc,
                     void* dz, int64_t lddz, int zcols, float* dbias, float* kws, int B, int H, int W, int C, int up, int dtype,

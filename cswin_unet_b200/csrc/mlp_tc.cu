@@ -40,7 +40,7 @@ using namespace tc;
 
 constexpr int BM = 128, HC = 64;
 constexpr int kThreads = 320;
-constexpr int kMaxSlots = 4;
+constexpr int kMaxSlots = 8;
 constexpr int kMaxHidPerCta = 512;
 
 struct alignas(64) MlpTcParams {
@@ -331,8 +331,8 @@ size_t mlp_smem_bytes(int C, int slots) {
 struct MlpCfg { int spl, slots, tmem_cols; };
 bool mlp_cfg(int C, int hidden, MlpCfg* c) {
   if (hidden != 4 * C) return false;
-  if (C == 64) *c = MlpCfg{1, 4, 256};
-  else if (C == 128) *c = MlpCfg{1, 3, 256};
+  if (C == 64) *c = MlpCfg{1, 6, 256};          // ring depth: the weight stream must cover ~1 us of TMA latency
+  else if (C == 128) *c = MlpCfg{1, 8, 256};
   else if (C == 256) *c = MlpCfg{2, 3, 512};
   else return false;
   return true;

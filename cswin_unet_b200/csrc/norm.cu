@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(256) layernorm_bf16_vec_kernel(const __nv_bflo
                                                                   const __nv_bfloat16* __restrict__ b,
                                                                   __nv_bfloat16* __restrict__ y, int64_t ldy, int64_t M,
                                                                   float eps, float* __restrict__ mean_out,
-                                                                  float* __restrict__ rstd_out) {
+                                                                  float* __restrict__ rstd_out, float* __restrict__ ystats) {
   constexpr int C = LPR * NV * 8;
   constexpr int RPW = 32 / LPR;
   pdl_trigger();
@@ -88,6 +88,7 @@ __global__ void __launch_bounds__(256) layernorm_bf16_vec_kernel(const __nv_bflo
 #pragma unroll
   for (int o = LPR / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
   const float rstd = rsqrtf(q * (1.0f / C) + eps);
+  float y1 = 0.f, y2 = 0.f;                             // (sum, sum^2) of the bf16 outputs, for a following folded LayerNorm
   if (ok) {
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
@@ -102,6 +103,9 @@ __global__ void __launch_bounds__(256) layernorm_bf16_vec_kernel(const __nv_bflo
         const float hi = (v[i * 8 + 2 * e + 1] - mean) * rstd * __uint_as_float(gw[e] & 0xffff0000u) + __uint_as_float(bw[e] & 0xffff0000u);
         const __nv_bfloat162 pk = __floats2bfloat162_rn(lo, hi);
         o[e] = *reinterpret_cast<const uint32_t*>(&pk);
+        const float ylo = __uint_as_float(o[e] << 16), yhi = __uint_as_float(o[e] & 0xffff0000u);
+        y1 += ylo + yhi;
+        y2 = fmaf(ylo, ylo, fmaf(yhi, yhi, y2));
       }
       *reinterpret_cast<uint4*>(y + row * ldy + c0) = make_uint4(o[0], o[1], o[2], o[3]);
     }
@@ -110,16 +114,21 @@ __global__ void __launch_bounds__(256) layernorm_bf16_vec_kernel(const __nv_bflo
       if (rstd_out) rstd_out[row] = rstd;
     }
   }
+  if (ystats != nullptr) {                              // uniform branch: every lane takes part in the shuffles
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) { y1 += __shfl_xor_sync(0xffffffffu, y1, o); y2 += __shfl_xor_sync(0xffffffffu, y2, o); }
+    if (ok && sub == 0) { ystats[row * 2] = y1; ystats[row * 2 + 1] = y2; }
+  }
 }
 
 template <int LPR, int NV>
 int launch_vec(const void* x, int64_t ldx, const void* g, const void* b, void* y, int64_t ldy, int64_t M, float eps,
-               float* mean, float* rstd, cudaStream_t s) {
+               float* mean, float* rstd, float* ystats, cudaStream_t s) {
   constexpr int RPW = 32 / LPR;
   const int64_t rows_per_cta = 8 * RPW;
   CSWIN_CUDA_OK(launch_pdl(layernorm_bf16_vec_kernel<LPR, NV>, dim3((unsigned)ceil_div64(M, rows_per_cta)), dim3(256), 0, s,
                            (const __nv_bfloat16*)x, ldx, (const __nv_bfloat16*)g, (const __nv_bfloat16*)b, (__nv_bfloat16*)y,
-                           ldy, M, eps, mean, rstd));
+                           ldy, M, eps, mean, rstd, ystats));
   CSWIN_LAUNCH_CHECK();
   return CSWIN_OK;
 }
@@ -168,18 +177,22 @@ int row_stats(const void* x, int64_t ldx, int64_t M, int C, float* stats, int dt
 }
 
 int layernorm_fwd(const void* x, int64_t ldx, const void* g, const void* b, void* y, int64_t ldy, int64_t M, int C,
-                  float eps, float* mean, float* rstd, int dtype, cudaStream_t s) {
+                  float eps, float* mean, float* rstd, float* ystats, int dtype, cudaStream_t s) {
   CSWIN_REQUIRE(x && g && b && y, CSWIN_ERR_INVALID, "layernorm: null pointer");
   CSWIN_REQUIRE(C > 0 && C <= 2048, CSWIN_ERR_UNSUPPORTED, "layernorm: C=%d outside (0, 2048]", C);
   CSWIN_REQUIRE(ldx >= C && ldy >= C, CSWIN_ERR_INVALID, "layernorm: leading dimension smaller than C");
   if (M == 0) return CSWIN_OK;
-  if (dtype == CSWIN_F32) return launch<float>(x, ldx, g, b, y, ldy, M, C, eps, mean, rstd, s);
+  if (dtype == CSWIN_F32) {
+    CSWIN_REQUIRE(!ystats, CSWIN_ERR_UNSUPPORTED, "layernorm: output row statistics exist on the vectorised bf16 path only");
+    return launch<float>(x, ldx, g, b, y, ldy, M, C, eps, mean, rstd, s);
+  }
   const bool vec = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(g) |
                      reinterpret_cast<uintptr_t>(b)) % 16 == 0) && (ldx * 2) % 16 == 0 && (ldy * 2) % 16 == 0;
-  if (vec && C == 64) return launch_vec<8, 1>(x, ldx, g, b, y, ldy, M, eps, mean, rstd, s);
-  if (vec && C == 128) return launch_vec<16, 1>(x, ldx, g, b, y, ldy, M, eps, mean, rstd, s);
-  if (vec && C == 256) return launch_vec<32, 1>(x, ldx, g, b, y, ldy, M, eps, mean, rstd, s);
-  if (vec && C == 512) return launch_vec<32, 2>(x, ldx, g, b, y, ldy, M, eps, mean, rstd, s);
+  if (vec && C == 64) return launch_vec<8, 1>(x, ldx, g, b, y, ldy, M, eps, mean, rstd, ystats, s);
+  if (vec && C == 128) return launch_vec<16, 1>(x, ldx, g, b, y, ldy, M, eps, mean, rstd, ystats, s);
+  if (vec && C == 256) return launch_vec<32, 1>(x, ldx, g, b, y, ldy, M, eps, mean, rstd, ystats, s);
+  if (vec && C == 512) return launch_vec<32, 2>(x, ldx, g, b, y, ldy, M, eps, mean, rstd, ystats, s);
+  CSWIN_REQUIRE(!ystats, CSWIN_ERR_UNSUPPORTED, "layernorm: output row statistics need C in {64,128,256,512} and 16-byte aligned rows");
   return launch<__nv_bfloat16>(x, ldx, g, b, y, ldy, M, C, eps, mean, rstd, s);
 }
 

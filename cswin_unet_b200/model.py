@@ -33,6 +33,14 @@ Tensor = torch.Tensor
 FOLD_TRAIN_HEAD = os.environ.get("CSWIN_UNFOLDED_TRAIN_HEAD") != "1"
 
 
+def _view_keep_stats(y: Tensor, shape) -> Tensor:
+    v = y.view(shape)
+    st = getattr(y, "_cswin_stats", None)
+    if st is not None:
+        v._cswin_stats = st
+    return v
+
+
 class CSWinTransformer(_Native):
     def __init__(self, img_size=224, patch_size=16, in_chans=3, num_classes=8, embed_dim=64, depth=[1, 2, 9, 1],
                  split_size=[1, 2, 7, 7], num_heads=12, mlp_ratio=4., qkv_bias=True, qk_scale=None, drop_rate=0.,
@@ -109,20 +117,24 @@ class CSWinTransformer(_Native):
             return y.view(B, -1, y.shape[-1])
         wk = self._w("stem.w", conv.weight, dt, lambda t: torch.nn.functional.pad(t.reshape(t.shape[0], -1), (0, Kp - K)))
         y = ops.linear(col, wk, self._w("stem.b", conv.bias, dt))
-        y = ops.layernorm(y, self._w("stem.n.w", ln.weight, dt), self._w("stem.n.b", ln.bias, dt), ln.eps)
-        return y.view(B, -1, y.shape[-1])
+        y = ops.layernorm_with_row_stats(y, self._w("stem.n.w", ln.weight, dt), self._w("stem.n.b", ln.bias, dt), ln.eps)
+        return _view_keep_stats(y, (B, -1, y.shape[-1]))
 
     def _skip_linear(self, lin: nn.Linear, skip: Tensor, x: Tensor, key: str) -> Tensor:
         if ag.needs_grad(skip, x, lin.weight):
             return ag.linear(skip, lin.weight, lin.bias, a2=x)
         dt = x.dtype
+        if dt == torch.bfloat16:                             # the epilogue also emits the row statistics the next block folds
+            y, st = ops.linear(skip, self._w(key + ".w", lin.weight, dt), self._w(key + ".b", lin.bias, dt), a2=x, want_stats=True)
+            y._cswin_stats = st
+            return y
         return ops.linear(skip, self._w(key + ".w", lin.weight, dt), self._w(key + ".b", lin.bias, dt), a2=x)
 
     def _ln(self, ln: nn.LayerNorm, x: Tensor, key: str) -> Tensor:
         if ag.needs_grad(x, ln.weight):
             return ag.LayerNormFn.apply(x, ln.weight, ln.bias, ln.eps)
         dt = x.dtype
-        return ops.layernorm(x, self._w(key + ".w", ln.weight, dt), self._w(key + ".b", ln.bias, dt), ln.eps)
+        return ops.layernorm_with_row_stats(x, self._w(key + ".w", ln.weight, dt), self._w(key + ".b", ln.bias, dt), ln.eps)
 
     def forward_features(self, x: Tensor) -> Tensor:
         dt = self.compute_dtype or x.dtype

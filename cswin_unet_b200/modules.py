@@ -395,9 +395,12 @@ class Merge_Block(_Native):
         wk = self._w("conv.w", self.conv.weight, dt, lambda t: t.permute(0, 2, 3, 1).reshape(t.shape[0], -1))
         col = ops.im2col_tokens(x, H, W, 3, 3, 2, 1)
         y = ops.linear(col, wk, self._w("conv.b", self.conv.bias, dt))
-        y = ops.layernorm(y, self._w("n.w", self.norm.weight, dt), self._w("n.b", self.norm.bias, dt), self.norm.eps)
+        y = ops.layernorm_with_row_stats(y, self._w("n.w", self.norm.weight, dt), self._w("n.b", self.norm.bias, dt), self.norm.eps)
         Ho = (H + 2 - 3) // 2 + 1
-        return y.view(B, Ho * Ho, -1)
+        v = y.view(B, Ho * Ho, -1)
+        if hasattr(y, "_cswin_stats"):
+            v._cswin_stats = y._cswin_stats                  # rides along to the first block of the next stage
+        return v
 
 
 class CARAFE(_Native):

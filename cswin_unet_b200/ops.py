@@ -127,6 +127,23 @@ def layernorm(x: Tensor, gamma: Tensor, beta: Tensor, eps: float = 1e-5, out: Op
     return (y, mean, rstd) if stats else y
 
 
+def layernorm_with_row_stats(x: Tensor, gamma: Tensor, beta: Tensor, eps: float = 1e-5) -> Tensor:
+    """bf16 LayerNorm whose output carries `_cswin_stats` = (M, 1, 2) row (sum, sum^2), for the next block's folded LayerNorm.
+    Falls back to the plain kernel (the block then runs one row_stats pass) when the shape is outside the fast path."""
+    Cn = x.shape[-1]
+    x2, M, ldx = _rows(x)
+    if (x.dtype != torch.bfloat16 or Cn not in (64, 128, 256, 512) or ldx % 8 or x2.data_ptr() % 16
+            or gamma.data_ptr() % 16 or beta.data_ptr() % 16):
+        return layernorm(x, gamma, beta, eps)
+    _need_cuda(x, gamma, beta)
+    y = torch.empty(x.shape, dtype=x.dtype, device=x.device)
+    st = torch.empty((M, 1, 2), dtype=torch.float32, device=x.device)
+    check(lib().cswin_layernorm_stats_fwd(x2.data_ptr(), ldx, gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), Cn, M, Cn,
+                                          C.c_float(eps), st.data_ptr(), _dtype_code(x), _stream()), "cswin_layernorm_stats_fwd")
+    y._cswin_stats = st
+    return y
+
+
 def linear(a: Tensor, w: Tensor, bias: Optional[Tensor] = None, *, a2: Optional[Tensor] = None,
            ln: Optional[Tuple[Tensor, Tensor, float]] = None, act: int = 0, residual: Optional[Tensor] = None,
            sample_scale: Optional[Tensor] = None, rows_per_sample: int = 0, out: Optional[Tensor] = None,

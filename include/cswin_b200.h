@@ -201,6 +201,11 @@ typedef struct {
 int cswin_sgd_momentum_step(const cswin_sgd_chunk_t* chunks, int32_t n_chunks, const float* lr, float momentum,
                             float weight_decay, cswin_stream_t stream);
 
+/* LayerNorm that also emits the (sum, sum^2) row statistics of its bf16 OUTPUT, (M, 1, 2) fp32, seeding the folded-LayerNorm
+ * chain of the next CSWinBlock without a separate pass (bf16, C in {64,128,256,512}, 16-byte aligned rows; else UNSUPPORTED) */
+int cswin_layernorm_stats_fwd(const void* x, int64_t ldx, const void* gamma, const void* beta, void* y, int64_t ldy,
+                              int64_t M, int32_t C, float eps, float* row_stats_out, int32_t dtype, cswin_stream_t stream);
+
 /* per-row (sum x, sum x^2) of a (M, C) activation as one part: stats (M, 1, 2) fp32 — for inputs no Linear produced */
 int cswin_row_stats(const void* x, int64_t ldx, int64_t M, int32_t C, float* stats, int32_t dtype, cswin_stream_t stream);
 

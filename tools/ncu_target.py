@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Tiny driver for `ncu --set full`: runs a few launches of one op at one shape.
-usage: ncu_target.py attn <stage 1-4> <B> | linear <M> <N> <K> [act] [res]"""
+usage: ncu_target.py attn <stage 1-4> <B> | block_infer <stage> <B> | block_train <stage> <B> | linear <M> <N> <K> [act] [res]"""
 import os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -23,6 +23,14 @@ if kind == "attn":
     else:
         descs = [blk.attns[0].branch_desc(q, k, v, out)]
     fn = lambda: ops.lepe_attention_fwd(descs, B, reso, float(blk.attns[0].scale), torch.bfloat16)
+elif kind == "block_infer":          # inference forward of one CSWinBlock (bf16): folded-LN Linears, attention, (fused) MLP
+    stage, B = int(sys.argv[2]), int(sys.argv[3])
+    C, reso, heads, split, last = [(64, 56, 2, 1, False), (128, 28, 4, 2, False), (256, 14, 8, 7, False), (512, 7, 16, 7, True)][stage - 1]
+    blk = cw.CSWinBlock(dim=C, reso=reso, num_heads=heads, split_size=split, qkv_bias=True, last_stage=last).to(DEV).eval()
+    x = torch.randn(B, reso * reso, C, device=DEV, dtype=torch.bfloat16)
+    def fn():
+        with torch.no_grad():
+            blk(blk(x))
 elif kind == "block_train":          # forward + backward of one CSWinBlock (bf16): attention fwd/bwd, Linear fwd/dgrad/wgrad ...
     stage, B = int(sys.argv[2]), int(sys.argv[3])
     C, reso, heads, split, last = [(64, 56, 2, 1, False), (128, 28, 4, 2, False), (256, 14, 8, 7, False), (512, 7, 16, 7, True)][stage - 1]
