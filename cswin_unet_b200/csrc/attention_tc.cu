@@ -63,7 +63,8 @@ __device__ __forceinline__ float ex2_approx(float x) {
 
 __global__ void __launch_bounds__(kThreads, 3) lepe_attn_fwd_tc_kernel(const __grid_constant__ TcParams P) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment by pointer arithmetic on the shared array: keeps the shared address space (LDS / STS, not generic LD / ST)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* Qs = smem;
   uint8_t* Ks = smem + kOperandBytes;
   uint8_t* Vs = smem + 2 * kOperandBytes;
@@ -205,18 +206,16 @@ __global__ void __launch_bounds__(kThreads, 3) lepe_attn_fwd_tc_kernel(const __g
         for (int j = 0; j < 32; j += 2) {
           const float e0 = ex2_approx(fmaf(__uint_as_float(v[j]), P.scale_log2e, -mxs));
           const float e1 = ex2_approx(fmaf(__uint_as_float(v[j + 1]), P.scale_log2e, -mxs));
-          const uint32_t pr = pack_bf16x2(e0, e1);
-          sum += bf16_lo(pr) + bf16_hi(pr);                  // sum what the MMA will see (bf16-rounded P)
-          pk[c][j >> 1] = pr;
+          sum += e0 + e1;                                    // fp32 denominator (the reference normalises before rounding P)
+          pk[c][j >> 1] = pack_bf16x2(e0, e1);
         }
       } else {
 #pragma unroll
         for (int j = 0; j < 32; j += 2) {
           const float e0 = (j < lim) ? ex2_approx(fmaf(__uint_as_float(v[j]), P.scale_log2e, -mxs)) : 0.f;
           const float e1 = (j + 1 < lim) ? ex2_approx(fmaf(__uint_as_float(v[j + 1]), P.scale_log2e, -mxs)) : 0.f;
-          const uint32_t pr = pack_bf16x2(e0, e1);
-          sum += bf16_lo(pr) + bf16_hi(pr);
-          pk[c][j >> 1] = pr;
+          sum += e0 + e1;
+          pk[c][j >> 1] = pack_bf16x2(e0, e1);
         }
       }
     }
