@@ -193,6 +193,8 @@ __global__ void __launch_bounds__(kThreads, 3) lepe_attn_fwd_tc_kernel(const __g
   mx = fmaxf(mx, Xmax[(half ^ 1) * 128 + row]);
   const float mxs = mx * P.scale_log2e;
   float sum = 0.f;
+  float2 sum2 = make_float2(0.f, 0.f);
+  const float2 sl2 = make_float2(P.scale_log2e, P.scale_log2e), nmxs2 = make_float2(-mxs, -mxs);
   uint32_t pk[2][16];                                        // bf16 P of my columns, held until every S read is done
 #pragma unroll
   for (int c = 0; c < 2; ++c) {
@@ -203,11 +205,11 @@ __global__ void __launch_bounds__(kThreads, 3) lepe_attn_fwd_tc_kernel(const __g
       const int lim = N - (kbeg + 32 * c);
       if (lim >= 32) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          const float e0 = ex2_approx(fmaf(__uint_as_float(v[j]), P.scale_log2e, -mxs));
-          const float e1 = ex2_approx(fmaf(__uint_as_float(v[j + 1]), P.scale_log2e, -mxs));
-          sum += e0 + e1;                                    // fp32 denominator (the reference normalises before rounding P)
-          pk[c][j >> 1] = pack_bf16x2(e0, e1);
+        for (int j = 0; j < 32; j += 2) {                    // packed pairs: one FFMA2 + one FADD2 per two scores
+          const float2 t = ffma2(make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), sl2, nmxs2);
+          const float2 e = make_float2(ex2_approx(t.x), ex2_approx(t.y));
+          sum2 = fadd2(sum2, e);                             // fp32 denominator (the reference normalises before rounding P)
+          pk[c][j >> 1] = pack_bf16x2(e.x, e.y);
         }
       } else {
 #pragma unroll
@@ -232,6 +234,7 @@ __global__ void __launch_bounds__(kThreads, 3) lepe_attn_fwd_tc_kernel(const __g
     for (int j = 0; j < 16; ++j) z[j] = 0u;
     tmem_st16(trow + ((1 - slot) * 32) + half * 16, z);
   }
+  sum += sum2.x + sum2.y;
   Xsum[half * 128 + row] = sum;
   tmem_wait_st();
   tc_fence_before();
@@ -252,11 +255,11 @@ __global__ void __launch_bounds__(kThreads, 3) lepe_attn_fwd_tc_kernel(const __g
   mbar_wait(bar_tma, 0);                                     // (already complete) acquire the TMA-written V tile
   const bool valid = slot < np && n < N;
   const int r = n / ws, c = n - r * ws;
-  float lp[16];
+  float2 lp[8];                                              // 16 channels as packed fp32 pairs (FFMA2)
   {
-    const float* bc = Bc + min(slot, np - 1) * 32 + half * 16;
+    const float2* bc = reinterpret_cast<const float2*>(Bc + min(slot, np - 1) * 32 + half * 16);
 #pragma unroll
-    for (int j = 0; j < 16; ++j) lp[j] = bc[j];
+    for (int j = 0; j < 8; ++j) lp[j] = bc[j];
   }
   if (valid) {
     const uint32_t vbase = smem_u32(Vs);
@@ -273,14 +276,10 @@ __global__ void __launch_bounds__(kThreads, 3) lepe_attn_fwd_tc_kernel(const __g
                        : "r"(v_chunk_addr(vbase, vr, half * 2 + ch)));
           const float4 w0 = *reinterpret_cast<const float4*>(wt + t * 32 + ch * 8);
           const float4 w1 = *reinterpret_cast<const float4*>(wt + t * 32 + ch * 8 + 4);
-          lp[ch * 8 + 0] = fmaf(w0.x, bf16_lo(vv.x), lp[ch * 8 + 0]);
-          lp[ch * 8 + 1] = fmaf(w0.y, bf16_hi(vv.x), lp[ch * 8 + 1]);
-          lp[ch * 8 + 2] = fmaf(w0.z, bf16_lo(vv.y), lp[ch * 8 + 2]);
-          lp[ch * 8 + 3] = fmaf(w0.w, bf16_hi(vv.y), lp[ch * 8 + 3]);
-          lp[ch * 8 + 4] = fmaf(w1.x, bf16_lo(vv.z), lp[ch * 8 + 4]);
-          lp[ch * 8 + 5] = fmaf(w1.y, bf16_hi(vv.z), lp[ch * 8 + 5]);
-          lp[ch * 8 + 6] = fmaf(w1.z, bf16_lo(vv.w), lp[ch * 8 + 6]);
-          lp[ch * 8 + 7] = fmaf(w1.w, bf16_hi(vv.w), lp[ch * 8 + 7]);
+          lp[ch * 4 + 0] = ffma2(make_float2(w0.x, w0.y), make_float2(bf16_lo(vv.x), bf16_hi(vv.x)), lp[ch * 4 + 0]);
+          lp[ch * 4 + 1] = ffma2(make_float2(w0.z, w0.w), make_float2(bf16_lo(vv.y), bf16_hi(vv.y)), lp[ch * 4 + 1]);
+          lp[ch * 4 + 2] = ffma2(make_float2(w1.x, w1.y), make_float2(bf16_lo(vv.z), bf16_hi(vv.z)), lp[ch * 4 + 2]);
+          lp[ch * 4 + 3] = ffma2(make_float2(w1.z, w1.w), make_float2(bf16_lo(vv.w), bf16_hi(vv.w)), lp[ch * 4 + 3]);
         }
       }
     }
@@ -304,8 +303,10 @@ __global__ void __launch_bounds__(kThreads, 3) lepe_attn_fwd_tc_kernel(const __g
       __nv_bfloat16* dst = br.out + (int64_t)mb * br.o_bs + tok * br.o_ts + mhead * 32 + half * 16;
       uint32_t w[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        w[j] = pack_bf16x2(fmaf(__uint_as_float(o[2 * j]), inv, lp[2 * j]), fmaf(__uint_as_float(o[2 * j + 1]), inv, lp[2 * j + 1]));
+      for (int j = 0; j < 8; ++j) {
+        const float2 y = ffma2(make_float2(__uint_as_float(o[2 * j]), __uint_as_float(o[2 * j + 1])), make_float2(inv, inv), lp[j]);
+        w[j] = pack_bf16x2(y.x, y.y);
+      }
       *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
       *reinterpret_cast<uint4*>(dst + 8) = make_uint4(w[4], w[5], w[6], w[7]);
       if (br.lse != nullptr && half == 0)

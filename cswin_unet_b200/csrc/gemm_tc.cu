@@ -209,34 +209,33 @@ __global__ void __launch_bounds__(kThreads, 2) linear_tc_kernel(const __grid_con
           __syncwarp();
         }
         float st1 = 0.f, st2 = 0.f;
+        const float2 nmean2 = make_float2(-ln_mean, -ln_mean), rstd2 = make_float2(ln_rstd, ln_rstd), sc2 = make_float2(sc, sc);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          float f[8];
+          float2 f[4];                                    // 8 columns as 4 packed fp32 pairs (FFMA2 / FADD2)
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             const float4 bb = b4[c * 2 + h];
-            if (kFold) {
+            const float2 a0 = make_float2(__uint_as_float(v[c * 8 + h * 4 + 0]), __uint_as_float(v[c * 8 + h * 4 + 1]));
+            const float2 a1 = make_float2(__uint_as_float(v[c * 8 + h * 4 + 2]), __uint_as_float(v[c * 8 + h * 4 + 3]));
+            if (kFold) {                                  // rstd * (acc - mean * colsum) + bias'
               const float4 cc = c4[c * 2 + h];
-              f[h * 4 + 0] = fmaf(ln_rstd, fmaf(-ln_mean, cc.x, __uint_as_float(v[c * 8 + h * 4 + 0])), bb.x);
-              f[h * 4 + 1] = fmaf(ln_rstd, fmaf(-ln_mean, cc.y, __uint_as_float(v[c * 8 + h * 4 + 1])), bb.y);
-              f[h * 4 + 2] = fmaf(ln_rstd, fmaf(-ln_mean, cc.z, __uint_as_float(v[c * 8 + h * 4 + 2])), bb.z);
-              f[h * 4 + 3] = fmaf(ln_rstd, fmaf(-ln_mean, cc.w, __uint_as_float(v[c * 8 + h * 4 + 3])), bb.w);
+              f[h * 2 + 0] = ffma2(rstd2, ffma2(nmean2, make_float2(cc.x, cc.y), a0), make_float2(bb.x, bb.y));
+              f[h * 2 + 1] = ffma2(rstd2, ffma2(nmean2, make_float2(cc.z, cc.w), a1), make_float2(bb.z, bb.w));
             } else {
-              f[h * 4 + 0] = __uint_as_float(v[c * 8 + h * 4 + 0]) + bb.x;
-              f[h * 4 + 1] = __uint_as_float(v[c * 8 + h * 4 + 1]) + bb.y;
-              f[h * 4 + 2] = __uint_as_float(v[c * 8 + h * 4 + 2]) + bb.z;
-              f[h * 4 + 3] = __uint_as_float(v[c * 8 + h * 4 + 3]) + bb.w;
+              f[h * 2 + 0] = fadd2(a0, make_float2(bb.x, bb.y));
+              f[h * 2 + 1] = fadd2(a1, make_float2(bb.z, bb.w));
             }
           }
           if (P.act == 1) {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) f[e] = gelu_fast(f[e]);
+            for (int e = 0; e < 4; ++e) f[e] = gelu_fast2(f[e]);
           }
           if (P.sscale != nullptr) {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) f[e] *= sc;
+            for (int e = 0; e < 4; ++e) f[e] = fmul2(f[e], sc2);
           }
-          uint4 x = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+          uint4 x = make_uint4(pack_bf16x2(f[0].x, f[0].y), pack_bf16x2(f[1].x, f[1].y), pack_bf16x2(f[2].x, f[2].y), pack_bf16x2(f[3].x, f[3].y));
           if (has_res) {
             x.x = add_bf16x2(x.x, rv[c].x); x.y = add_bf16x2(x.y, rv[c].y);
             x.z = add_bf16x2(x.z, rv[c].z); x.w = add_bf16x2(x.w, rv[c].w);

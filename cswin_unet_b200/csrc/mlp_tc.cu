@@ -220,15 +220,16 @@ __global__ void __launch_bounds__(kThreads, 2) mlp_tc_kernel(const __grid_consta
       const float4* b4 = reinterpret_cast<const float4*>(sB1 + j * HC + half * 32);
       const float4* c4 = reinterpret_cast<const float4*>(sCs + j * HC + half * 32);
       uint32_t pk[16];
+      const float2 nmean2 = make_float2(nmean, nmean), rstd2 = make_float2(rstd, rstd);
 #pragma unroll
-      for (int g = 0; g < 8; ++g) {
+      for (int g = 0; g < 8; ++g) {                          // packed fp32 pairs: FFMA2 fold + 7-op GELU per two elements
         const float4 bb = b4[g], cc = c4[g];
-        const float f0 = gelu_fast(fmaf(rstd, fmaf(nmean, cc.x, __uint_as_float(v[g * 4 + 0])), bb.x));
-        const float f1 = gelu_fast(fmaf(rstd, fmaf(nmean, cc.y, __uint_as_float(v[g * 4 + 1])), bb.y));
-        const float f2 = gelu_fast(fmaf(rstd, fmaf(nmean, cc.z, __uint_as_float(v[g * 4 + 2])), bb.z));
-        const float f3 = gelu_fast(fmaf(rstd, fmaf(nmean, cc.w, __uint_as_float(v[g * 4 + 3])), bb.w));
-        pk[g * 2] = pack_bf16x2(f0, f1);
-        pk[g * 2 + 1] = pack_bf16x2(f2, f3);
+        const float2 a0 = make_float2(__uint_as_float(v[g * 4 + 0]), __uint_as_float(v[g * 4 + 1]));
+        const float2 a1 = make_float2(__uint_as_float(v[g * 4 + 2]), __uint_as_float(v[g * 4 + 3]));
+        const float2 f0 = gelu_fast2(ffma2(rstd2, ffma2(nmean2, make_float2(cc.x, cc.y), a0), make_float2(bb.x, bb.y)));
+        const float2 f1 = gelu_fast2(ffma2(rstd2, ffma2(nmean2, make_float2(cc.z, cc.w), a1), make_float2(bb.z, bb.w)));
+        pk[g * 2] = pack_bf16x2(f0.x, f0.y);
+        pk[g * 2 + 1] = pack_bf16x2(f1.x, f1.y);
       }
       if (j >= 2) PWAIT(e_hfree, mbar_wait(bar(kHFree + b), ((j >> 1) - 1) & 1));   // MMA2(j - 2) has finished reading H[b]
       const uint32_t hrow = smem_u32(Hs + b * 16384) + row * 128;

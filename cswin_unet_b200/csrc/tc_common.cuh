@@ -215,6 +215,39 @@ __device__ __forceinline__ float gelu_fast(float x) {
   return fmaf(h, t, h);
 }
 
+// ---- packed fp32 pairs (Blackwell FFMA2 / FADD2 / FMUL2: two fp32 operations per issue slot) ----
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(reinterpret_cast<uint64_t&>(d))
+      : "l"(reinterpret_cast<const uint64_t&>(a)), "l"(reinterpret_cast<const uint64_t&>(b)), "l"(reinterpret_cast<const uint64_t&>(c)));
+  return d;
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+  float2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(reinterpret_cast<uint64_t&>(d))
+      : "l"(reinterpret_cast<const uint64_t&>(a)), "l"(reinterpret_cast<const uint64_t&>(b)));
+  return d;
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+  float2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(reinterpret_cast<uint64_t&>(d))
+      : "l"(reinterpret_cast<const uint64_t&>(a)), "l"(reinterpret_cast<const uint64_t&>(b)));
+  return d;
+}
+// gelu_fast on a pair: 7 packed FP instructions + 2 MUFU for two elements
+__device__ __forceinline__ float2 gelu_fast2(float2 x) {
+  const float2 x2 = fmul2(x, x);
+  float2 p = ffma2(x2, make_float2(-1.36882761e-05f, -1.36882761e-05f), make_float2(-1.94451094e-04f, -1.94451094e-04f));
+  p = ffma2(p, x2, make_float2(3.65466544e-02f, 3.65466544e-02f));
+  p = ffma2(p, x2, make_float2(7.97820264e-01f, 7.97820264e-01f));
+  const float2 u = fmul2(p, x);
+  float2 t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t.x) : "f"(u.x));
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t.y) : "f"(u.y));
+  const float2 h = fmul2(x, make_float2(0.5f, 0.5f));
+  return ffma2(h, t, h);
+}
+
 // ---- thread-block clusters / distributed shared memory ----
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ void cluster_sync_all() {   // every thread of every CTA of the cluster
