@@ -373,8 +373,9 @@ def run_native(args):
         line["train_step"] = {"value": world * tk * B / (ms_tr * 1e-3), "unit": UNIT, "ms_per_step": ms_tr / tk, "steps": tk,
                               "warmup": tw, "batch_per_gpu": B, "dtype": "bf16 compute, fp32 master weights + gradients",
                               "gpu_launches": int(step_fn.native_launches_per_step * tk + (cw.launch_count() - n_tr0)),
-                              "what": "forward + native backward + native loss (0.4 CE + 0.6 Dice) + bucketed NCCL gradient all-reduce "
-                                      "(N>1) + native fused SGD(momentum .9, wd 1e-4); whole step replayed as a CUDA graph",
+                              "what": "forward + native backward + native loss (0.4 CE + 0.6 Dice) + NCCL gradient all-reduce overlapped with the "
+                                      "backward on the pooled gradient buffer (N>1) + native fused SGD(momentum .9, wd 1e-4); whole step "
+                                      "(collectives included) replayed as one CUDA graph",
                               "roofline_frac_tensor": world and (tk * B / (ms_tr * 1e-3)) * 33.231 / 1e3 / (pk["bf16_tflops_sustained"] or pk["bf16_tflops"])}
         del tmodel, step_fn
 

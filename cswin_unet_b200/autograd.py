@@ -40,9 +40,15 @@ class ZeroPool:
         self.buf = torch.zeros(numel, dtype=torch.float32, device=device)
         self.off = 0
 
+        self.on_commit = None           # callable(offset): everything below `offset` has had its producing kernels launched
+
     def reset(self):
         self.buf.zero_()
         self.off = 0
+
+    def commit(self):
+        if self.on_commit is not None:
+            self.on_commit(self.off)
 
     def take(self, shape) -> Optional[Tensor]:
         n = 1
@@ -57,6 +63,12 @@ class ZeroPool:
 
 
 POOL: Optional[ZeroPool] = None
+
+
+def _commit() -> None:
+    """Called at the end of every backward that filled pooled gradient slices (see parallel.PoolGradReducer)."""
+    if POOL is not None:
+        POOL.commit()
 
 
 def _zeros(shape, device) -> Tensor:
@@ -114,6 +126,7 @@ class LayerNormFn(Function):
         x, g, mean, rstd = ctx.saved_tensors
         Cn = x.shape[-1]
         dx, dg, db = ops.layernorm_bwd(x, dy.contiguous(), g, mean, rstd, _zeros((Cn,), x.device), _zeros((Cn,), x.device))
+        _commit()
         return dx, dg.to(ctx.pd), db.to(ctx.pd), None
 
 
@@ -156,6 +169,7 @@ class LinearFn(Function):
                 ops.linear_wgrad(dz, a2, dwf[:, K1:], None)
             dw = dwf.to(ctx.wd)
             db = dbf.to(ctx.bd) if ctx.has_bias else None
+            _commit()
         return da, dw, db, da2, (dout if ctx.has_res else None), None, None
 
 
@@ -227,6 +241,7 @@ class LepeAttentionFn(Function):
                         lse=lses[i])
         descs = LepeAttentionFn._descs(qkv, dout, ws, meta, Cn, extra)
         ops.lepe_attention_bwd(descs, B, meta["reso"], meta["scale"], qkv.dtype)
+        _commit()
         g0 = (gw[0].view(h, 1, 3, 3).to(ctx.pd), gb[0].to(ctx.pd))
         g1 = (gw[1].view(h, 1, 3, 3).to(ctx.pd), gb[1].to(ctx.pd)) if len(ws) == 2 else (None, None)
         return dqkv, g0[0], g0[1], g1[0], g1[1], None

@@ -36,6 +36,9 @@ using namespace tc;
 
 constexpr int BM = 128, BK = 64;
 constexpr int kMaxStages = 8;
+#ifndef CSWIN_GEMM_MINB
+#define CSWIN_GEMM_MINB 2                 // CTAs per SM the register budget is sized for (3 -> 64 registers, minor spills)
+#endif
 constexpr int kThreads = 320;                          // warp 0 TMA, warp 1 MMA + TMEM, warps 2..9 epilogue
 
 struct alignas(64) GemmTcParams {
@@ -52,7 +55,7 @@ struct alignas(64) GemmTcParams {
 };
 
 template <bool kFold, bool kStats>
-__global__ void __launch_bounds__(kThreads, 2) linear_tc_kernel(const __grid_constant__ GemmTcParams P) {
+__global__ void __launch_bounds__(kThreads, CSWIN_GEMM_MINB) linear_tc_kernel(const __grid_constant__ GemmTcParams P) {
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for the 128-byte swizzle; plain pointer arithmetic keeps the shared address space (LDS/STS)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -399,6 +402,8 @@ struct TileCfg { int bn, stages; };
 // CSWIN_GEMM_BN=<n> forces BN for experiments.
 TileCfg pick_tile(int64_t M, int N, int nkb, int act, int sms, bool w_kn) {
   static const int forced = [] { const char* e = getenv("CSWIN_GEMM_BN"); return e ? atoi(e) : 0; }();
+  // CSWIN_GEMM_SMEM_CAP_KB: per-CTA shared-memory ceiling, so that a CTA of the NEXT kernel (PDL) fits next to the resident ones
+  static const size_t smem_cap = [] { const char* e = getenv("CSWIN_GEMM_SMEM_CAP_KB"); return e ? (size_t)atoi(e) * 1024 : (size_t)0; }();
   const int n16 = w_kn ? ((N + 63) & ~63) : ((N + 15) & ~15);      // (K,N) weights are fetched in 64-column boxes
   const int64_t mt = (M + BM - 1) / BM;
   const int cands[] = {64, 96, 128, 192, 256};
@@ -411,13 +416,14 @@ TileCfg pick_tile(int64_t M, int N, int nkb, int act, int sms, bool w_kn) {
     if (N % bn != 0 && bn > 64 && bn != n16) continue;
     const int64_t tiles = mt * ((N + bn - 1) / bn);
     int resident = 512 / tmem_cols_for(bn);
-    if (resident > 2) resident = 2;                              // 320 threads x ~80 registers: two CTAs per SM
+    if (resident > CSWIN_GEMM_MINB) resident = CSWIN_GEMM_MINB;   // register budget: CSWIN_GEMM_MINB CTAs of 320 threads per SM
     while (resident > 1 && smem_bytes(bn, 2) * resident > 220 * 1024) --resident;
     const int64_t waves = (tiles + (int64_t)sms * resident - 1) / ((int64_t)sms * resident);
     int64_t share = (tiles + sms - 1) / sms;                    // CTAs that will actually share an SM
     if (share > resident) share = resident;
     int st = 1;
-    while (st < kMaxStages && st < nkb && smem_bytes(bn, st + 1) * share <= 220 * 1024) ++st;
+    while (st < kMaxStages && st < nkb && smem_bytes(bn, st + 1) * share <= 220 * 1024 &&
+           (smem_cap == 0 || smem_bytes(bn, st + 1) <= smem_cap)) ++st;
     const double t_tile = 2.0 + nkb * (0.10 + 0.7 / st) + (bn / 64.0) * (act ? 3.5 : 1.6);
     const double t = waves * t_tile;
     if (t < best_t - 1e-9) { best_t = t; best = TileCfg{bn, st}; }

@@ -57,3 +57,53 @@ def allreduce_gradients(params: Iterable[Tensor], group=None, bucket_bytes: int 
         torch._foreach_copy_(bucket, views)
         n_coll += 1
     return n_coll
+
+
+class PoolGradReducer:
+    """Gradient all-reduce overlapped with the backward, without packing: the weight-gradient kernels accumulate into slices of
+    ONE flat fp32 buffer (autograd.ZeroPool) handed out in the order the backward reaches them, so a finished prefix of that
+    buffer IS a gradient bucket.  Whenever ~bucket_bytes more have been committed (ZeroPool.commit, called after the producing
+    kernels are enqueued) the range is all-reduced in place on a side stream (NCCL over NVLink / NVSwitch) while the backward
+    keeps running on the main stream; `finish()` reduces the tail and joins the streams.  Capturable into the step's CUDA graph.
+    Gradients that do not live in the pool (a few produced by torch ops on the tape) are handled by `allreduce_gradients`."""
+
+    def __init__(self, pool, group=None, bucket_bytes: int = 16 << 20):
+        self.pool, self.group, self.bucket = pool, group, bucket_bytes // 4
+        self.world = dist.get_world_size(group)
+        self.comm = torch.cuda.Stream() if pool.buf.is_cuda else None     # (CPU / gloo: same logic, no streams — used by the tests)
+        self.start = 0
+        self.n_coll = 0
+
+    def begin(self) -> None:
+        self.start = 0
+        self.n_coll = 0
+        self.pool.on_commit = self._on_commit
+
+    def _on_commit(self, off: int) -> None:
+        if off - self.start >= self.bucket:
+            self._launch(self.start, off)
+            self.start = off
+
+    def _launch(self, a: int, b: int) -> None:
+        seg = self.pool.buf[a:b]
+        if self.comm is None:
+            dist.all_reduce(seg, op=dist.ReduceOp.SUM, group=self.group)
+            seg.div_(self.world)
+        else:
+            self.comm.wait_stream(torch.cuda.current_stream())     # the kernels that filled [a, b) are already enqueued there
+            with torch.cuda.stream(self.comm):
+                dist.all_reduce(seg, op=dist.ReduceOp.SUM, group=self.group)
+                seg.div_(self.world)
+        self.n_coll += 1
+
+    def finish(self) -> None:
+        self.pool.on_commit = None
+        if self.pool.off > self.start:
+            self._launch(self.start, self.pool.off)
+            self.start = self.pool.off
+        if self.comm is not None:
+            torch.cuda.current_stream().wait_stream(self.comm)
+
+    def in_pool(self, t: Tensor) -> bool:
+        lo = self.pool.buf.data_ptr()
+        return lo <= t.data_ptr() < lo + self.pool.buf.numel() * 4

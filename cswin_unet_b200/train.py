@@ -81,6 +81,10 @@ class TrainStep:
             sum(p.numel() + 4 for p in model.parameters()), next(model.parameters()).device)
         self._distributed = torch.distributed.is_available() and torch.distributed.is_initialized() and \
             torch.distributed.get_world_size(group) > 1
+        # all-reduce overlapped with the backward on the pooled gradient buffer (CSWIN_DDP_OVERLAP=0: bucketed all-reduce
+        # after the backward, between two CUDA graphs)
+        self._reducer = parallel.PoolGradReducer(self._pool, group) if (
+            self._distributed and self._pool is not None and os.environ.get("CSWIN_DDP_OVERLAP", "1") != "0") else None
 
     def _make_shadow(self, dtype: torch.dtype) -> None:
         ps = [p for p in self.model.parameters() if p.dtype != dtype]
@@ -131,19 +135,28 @@ class TrainStep:
         if self._pool is not None:
             self._pool.reset()
             ag.POOL = self._pool
+        if self._reducer is not None:
+            self._reducer.begin()
         try:
             logits = self.model(images)
             loss = seg_loss(logits, labels, self.n_classes)
             loss.backward()
+            if self._reducer is not None:                       # tail bucket + gradients that live outside the pool
+                self._reducer.finish()
+                rest = [p for p in self.model.parameters() if p.grad is not None and not self._reducer.in_pool(p.grad)]
+                parallel.allreduce_gradients(rest, self.group)
         finally:
             ag.SHADOW = {}
             ag.POOL = None
+            if self._pool is not None:
+                self._pool.on_commit = None
         return loss.detach()
 
     def _eager(self, images: Tensor, labels: Tensor) -> Tensor:
         self.opt.zero_grad(set_to_none=True)
         loss = self._fwd_bwd(images, labels)
-        parallel.allreduce_gradients(self.model.parameters(), self.group)
+        if self._reducer is None:
+            parallel.allreduce_gradients(self.model.parameters(), self.group)
         self._optimizer_step()
         return loss
 
@@ -156,10 +169,10 @@ class TrainStep:
         g1 = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g1):                         # forward + backward (+ optimizer when single-rank)
             self._loss = self._fwd_bwd(sx, sy)
-            if not self._distributed:
-                self._optimizer_step()
+            if not self._distributed or self._reducer is not None:
+                self._optimizer_step()                     # (overlapped DDP: the NCCL all-reduces are part of this graph)
         g2 = None
-        if self._distributed:                              # all-reduce eagerly between the two graphs
+        if self._distributed and self._reducer is None:    # all-reduce eagerly between the two graphs
             g2 = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g2, pool=g1.pool()):
                 self._optimizer_step()

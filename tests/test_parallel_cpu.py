@@ -47,6 +47,25 @@ def _worker(rank, world, port, n_total, out_dir):
         for i, p in enumerate(params):
             want = (i + 1) * sum(range(1, world + 1)) / world
             assert torch.allclose(p.grad, torch.full_like(p, want))
+        # 3. overlapped pooled reducer: slices of ONE flat buffer handed out in backward order, reduced in place in buckets
+        from cswin_unet_b200 import autograd as ag
+        pool = ag.ZeroPool(4096, "cpu")
+        red = parallel.PoolGradReducer(pool, bucket_bytes=4 * 300)
+        for step in range(2):                                   # two steps: the pool and the reducer are re-armed every step
+            pool.reset()
+            red.begin()
+            slices = []
+            for i, shape in enumerate(((10, 10), (7,), (333,), (64, 3), (5,))):
+                v = pool.take(shape)
+                v += float(rank + 1) * (i + 1 + step)           # "wgrad kernel" accumulates into the zeroed slice
+                slices.append(v)
+                pool.commit()
+            red.finish()
+            assert red.n_coll >= 2 and pool.on_commit is None
+            for i, v in enumerate(slices):
+                want = (i + 1 + step) * sum(range(1, world + 1)) / world
+                assert red.in_pool(v) and torch.allclose(v, torch.full_like(v, want)), (step, i)
+            assert not red.in_pool(torch.zeros(3))
         np.save(os.path.join(out_dir, f"ok{rank}.npy"), np.array([1]))
     finally:
         dist.destroy_process_group()
