@@ -87,6 +87,7 @@ __global__ void __launch_bounds__(kThr, 2) lepe_attn_bwd_tc_kernel(const __grid_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
 
   const int tid = threadIdx.x, warp = tid >> 5;
+  pdl_trigger();
   if (tid == 0) trace_stamp(P.trace, 0);
   const int row = tid & 127, half = tid >> 7;
   const int bi = (P.nb > 1 && (int)blockIdx.x >= P.br[1].tile_begin) ? 1 : 0;
@@ -141,6 +142,7 @@ __global__ void __launch_bounds__(kThr, 2) lepe_attn_bwd_tc_kernel(const __grid_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (tid == 0) trace_stamp(P.trace, 1);
+  pdl_wait();                                            // d out (previous kernel's output) and the gradient buffers are safe from here
 
   if (warp == 0 && elect_one()) {     // one elected lane, warp-uniform datapath for the TMA / tcgen05 issue
     mbar_expect_tx(bar_tma, (uint32_t)(np * 4 * N * kRowB));
@@ -395,7 +397,7 @@ int lepe_attention_bwd_tc(const cswin_lepe_branch_grad_t* gs, int nb, int B, int
   static std::atomic<bool> configured{false};
   if (!configured.exchange(true))
     CSWIN_CUDA_OK(cudaFuncSetAttribute(lepe_attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
-  lepe_attn_bwd_tc_kernel<<<tiles, kThr, kSmem, stream>>>(P);
+  CSWIN_CUDA_OK(launch_pdl(lepe_attn_bwd_tc_kernel, dim3(tiles), dim3(kThr), (size_t)kSmem, stream, P));
   CSWIN_LAUNCH_CHECK();
   g_tc_launches.fetch_add(1, std::memory_order_relaxed);
   *handled = true;

@@ -54,6 +54,8 @@ __device__ __forceinline__ float gelu_grad(float x) {
 __global__ void __launch_bounds__(256) act_bwd_bf16_vec_kernel(const uint4* __restrict__ dout, const uint4* __restrict__ z,
                                                                 const float* __restrict__ sscale, int64_t elems_per_sample,
                                                                 uint4* __restrict__ dz, int64_t nvec, int act) {
+  pdl_trigger();
+  pdl_wait();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
     const uint4 d = dout[i];
     const float sc = sscale != nullptr ? sscale[(i * 8) / elems_per_sample] : 1.0f;
@@ -70,6 +72,8 @@ __global__ void __launch_bounds__(256) act_bwd_bf16_vec_kernel(const uint4* __re
   }
 }
 __global__ void __launch_bounds__(256) act_fwd_bf16_vec_kernel(const uint4* __restrict__ z, uint4* __restrict__ out, int64_t nvec) {
+  pdl_trigger();
+  pdl_wait();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
     const uint4 zz = z[i];
     const uint32_t zw[4] = {zz.x, zz.y, zz.z, zz.w};
@@ -200,6 +204,8 @@ __global__ void __launch_bounds__(256) layernorm_bwd_bf16_vec_kernel(const __nv_
                                                                       const float* __restrict__ mean, const float* __restrict__ rstd,
                                                                       __nv_bfloat16* __restrict__ dx, int64_t ldo,
                                                                       float* __restrict__ dgamma, float* __restrict__ dbeta, int64_t M) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int C = LPR * NV * 8, RPW = 32 / LPR;
   __shared__ float red[8][C * 2];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, sub = lane / LPR, l = lane % LPR;
@@ -285,6 +291,8 @@ template <typename T>
 __global__ void __launch_bounds__(256) col2im_tokens_kernel(const T* __restrict__ dcol, int64_t ldcol, T* __restrict__ dx,
                                                              int64_t x_bs, int64_t x_ts, int B, int H, int W, int C, int KH,
                                                              int KW, int stride, int pad, int Ho, int Wo) {
+  pdl_trigger();
+  pdl_wait();
   const int64_t total = (int64_t)B * H * W * C;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % C);
@@ -711,7 +719,7 @@ int act_fwd(const void* z, int64_t ldz, void* out, int64_t ldo, int64_t M, int N
   if (M * N == 0) return CSWIN_OK;
   if (dtype == CSWIN_BF16 && act == 1 && ldz == N && ldo == N && N % 8 == 0 && (reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(out)) % 16 == 0) {
     const int64_t nvec = M * N / 8;
-    act_fwd_bf16_vec_kernel<<<grid_for(nvec, 256), 256, 0, s>>>((const uint4*)z, (uint4*)out, nvec);
+    CSWIN_CUDA_OK(launch_pdl(act_fwd_bf16_vec_kernel, dim3(grid_for(nvec, 256)), dim3(256), (size_t)0, s, (const uint4*)z, (uint4*)out, nvec));
     CSWIN_LAUNCH_CHECK();
     return CSWIN_OK;
   }
@@ -730,7 +738,7 @@ int act_bwd(const void* dout, int64_t ldd, const void* z, int64_t ldz, const flo
   if (dtype == CSWIN_BF16 && ldd == N && ldo == N && (act == 0 || ldz == N) && N % 8 == 0 && (!sscale || ((int64_t)rps * N) % 8 == 0) &&
       (reinterpret_cast<uintptr_t>(dout) | reinterpret_cast<uintptr_t>(dz) | (act ? reinterpret_cast<uintptr_t>(z) : 0)) % 16 == 0) {
     const int64_t nvec = M * N / 8;
-    act_bwd_bf16_vec_kernel<<<grid_for(nvec, 256), 256, 0, s>>>((const uint4*)dout, (const uint4*)z, sscale, (int64_t)rps * N, (uint4*)dz, nvec, act);
+    CSWIN_CUDA_OK(launch_pdl(act_bwd_bf16_vec_kernel, dim3(grid_for(nvec, 256)), dim3(256), (size_t)0, s, (const uint4*)dout, (const uint4*)z, sscale, (int64_t)rps * N, (uint4*)dz, nvec, act));
     CSWIN_LAUNCH_CHECK();
     return CSWIN_OK;
   }
@@ -771,7 +779,7 @@ int layernorm_bwd(const void* x, int64_t ldx, const void* dy, int64_t ldy, const
   if (vec && (C == 64 || C == 128 || C == 256 || C == 512)) {
     const int rpw = C == 64 ? 4 : C == 128 ? 2 : 1;
     const unsigned gv = (unsigned)std::min<int64_t>(ceil_div64(M, 8 * rpw), (int64_t)sm_count() * 2);
-#define LNV(L, V) layernorm_bwd_bf16_vec_kernel<L, V><<<gv, 256, 0, s>>>((const __nv_bfloat16*)x, ldx, (const __nv_bfloat16*)dy, ldy, (const __nv_bfloat16*)gamma, mean, rstd, (__nv_bfloat16*)dx, ldo, dgamma, dbeta, M)
+#define LNV(L, V) CSWIN_CUDA_OK(launch_pdl(layernorm_bwd_bf16_vec_kernel<L, V>, dim3(gv), dim3(256), (size_t)0, s, (const __nv_bfloat16*)x, ldx, (const __nv_bfloat16*)dy, ldy, (const __nv_bfloat16*)gamma, mean, rstd, (__nv_bfloat16*)dx, ldo, dgamma, dbeta, M))
     if (C == 64) LNV(8, 1); else if (C == 128) LNV(16, 1); else if (C == 256) LNV(32, 1); else LNV(32, 2);
 #undef LNV
     CSWIN_LAUNCH_CHECK();
@@ -792,8 +800,8 @@ int col2im_tokens(const void* dcol, int64_t ldcol, void* dx, int64_t x_bs, int64
   const int64_t total = (int64_t)B * H * W * C;
   if (total == 0) return CSWIN_OK;
   const unsigned grid = grid_for(total, 256);
-  if (dtype == CSWIN_F32) col2im_tokens_kernel<float><<<grid, 256, 0, s>>>((const float*)dcol, ldcol, (float*)dx, x_bs, x_ts, B, H, W, C, KH, KW, stride, pad, Ho, Wo);
-  else col2im_tokens_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)dcol, ldcol, (__nv_bfloat16*)dx, x_bs, x_ts, B, H, W, C, KH, KW, stride, pad, Ho, Wo);
+  if (dtype == CSWIN_F32) CSWIN_CUDA_OK(launch_pdl(col2im_tokens_kernel<float>, dim3(grid), dim3(256), (size_t)0, s, (const float*)dcol, ldcol, (float*)dx, x_bs, x_ts, B, H, W, C, KH, KW, stride, pad, Ho, Wo));
+  else CSWIN_CUDA_OK(launch_pdl(col2im_tokens_kernel<__nv_bfloat16>, dim3(grid), dim3(256), (size_t)0, s, (const __nv_bfloat16*)dcol, ldcol, (__nv_bfloat16*)dx, x_bs, x_ts, B, H, W, C, KH, KW, stride, pad, Ho, Wo));
   CSWIN_LAUNCH_CHECK();
   return CSWIN_OK;
 }

@@ -42,6 +42,7 @@ __global__ void __launch_bounds__(kWThreads) linear_wgrad_tc_kernel(const __grid
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kWStages + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  pdl_trigger();
   const int n0 = blockIdx.x * TN, k0 = blockIdx.y * BN;
   const int64_t mbeg = (int64_t)blockIdx.z * P.mchunk;
   const int64_t mend = mbeg + P.mchunk < P.M ? mbeg + P.mchunk : P.M;
@@ -65,6 +66,7 @@ __global__ void __launch_bounds__(kWThreads) linear_wgrad_tc_kernel(const __grid
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                                           // dZ, A and the gradient buffer are safe from here
 
   if (warp == 0) {
     if (elect_one()) {
@@ -192,7 +194,7 @@ int linear_wgrad_tc(const void* dz, int64_t ldz, const void* a, int64_t lda, flo
     configured.store(true, std::memory_order_relaxed);
   }
   dim3 grid((unsigned)((N + TN - 1) / TN), (unsigned)((K + P.BN - 1) / P.BN), (unsigned)split);
-  linear_wgrad_tc_kernel<<<grid, kWThreads, smem, stream>>>(P);
+  CSWIN_CUDA_OK(launch_pdl(linear_wgrad_tc_kernel, grid, dim3(kWThreads), smem, stream, P));
   CSWIN_LAUNCH_CHECK();
   g_tc_launches.fetch_add(1, std::memory_order_relaxed);
   *handled = true;
