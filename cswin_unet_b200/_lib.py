@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(_HERE, "libcswin_b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "cswin_b200.h")
 
 F32, BF16 = 0, 1
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 c_void_p, c_int32, c_int64, c_float = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 
@@ -80,6 +80,7 @@ SIGNATURES = {
     "cswin_debug_set_trace": (None, [c_void_p]),
     "cswin_lepe_attention_fwd": (c_int32, [C.POINTER(LepeBranch), c_int32, c_int32, c_int32, c_float, c_int32, c_void_p]),
     "cswin_lepe_attention_bwd": (c_int32, [C.POINTER(LepeBranchGrad), c_int32, c_int32, c_int32, c_float, c_int32, c_void_p]),
+    "cswin_lepe_param_grad": (c_int32, [C.POINTER(LepeBranchGrad), c_int32, c_int32, c_int32, c_int32, c_void_p, C.POINTER(c_int32)]),
     "cswin_layernorm_fwd": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int32,
                                       c_float, c_void_p, c_void_p, c_int32, c_void_p]),
     "cswin_linear_fwd": (c_int32, [C.POINTER(LinearArgs), c_int32, c_void_p]),
@@ -103,7 +104,7 @@ SIGNATURES = {
     "cswin_linear_wgrad": (c_int32, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int32,
                                      c_int32, c_int32, c_void_p]),
     "cswin_layernorm_bwd": (c_int32, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
-                                      c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p]),
+                                      c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p]),
     "cswin_col2im_tokens": (c_int32, [c_void_p, c_int64, c_void_p, c_int64, c_int64] + [c_int32] * 9 + [c_void_p]),
     "cswin_carafe_reassemble_bwd": (c_int32, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int32, c_int64, c_int64,
                                               c_int64, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p]

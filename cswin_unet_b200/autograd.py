@@ -110,6 +110,18 @@ def _c(p: Optional[Tensor], dt: torch.dtype) -> Optional[Tensor]:
     return p if (p.dtype == dt and p.is_contiguous()) else p.to(dt).contiguous()
 
 
+PARAM_GRAD_SIDE_STREAM = _os.environ.get("CSWIN_PARAM_GRAD_SIDE_STREAM", "1") != "0"
+_SIDE_STREAMS: dict = {}
+
+
+def _side_stream(device) -> "torch.cuda.Stream":
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+    s = _SIDE_STREAMS.get(key)
+    if s is None:
+        s = _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+    return s
+
+
 class LayerNormFn(Function):
     @staticmethod
     def forward(ctx, x, gamma, beta, eps):
@@ -126,6 +138,33 @@ class LayerNormFn(Function):
         x, g, mean, rstd = ctx.saved_tensors
         Cn = x.shape[-1]
         dx, dg, db = ops.layernorm_bwd(x, dy.contiguous(), g, mean, rstd, _zeros((Cn,), x.device), _zeros((Cn,), x.device))
+        _commit()
+        return dx, dg.to(ctx.pd), db.to(ctx.pd), None
+
+
+class LayerNormForkFn(Function):
+    """x -> (LayerNorm(x), x): the pre-norm residual pattern `x + f(LN(x))` (cswin_unet.py:178-179).  Handing out the residual
+    operand here makes this node the only consumer of x, so the two gradients of x (through the LayerNorm and around it)
+    meet inside the LayerNorm backward kernel's store instead of in a separate accumulation kernel of the autograd engine."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps):
+        dt = x.dtype
+        g, b = _c(gamma, dt), _c(beta, dt)
+        y, mean, rstd = ops.layernorm(x, g, b, eps, stats=True)
+        ctx.save_for_backward(x, g, mean, rstd)
+        ctx.pd = gamma.dtype
+        return y, x.view_as(x)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy, dres):
+        x, g, mean, rstd = ctx.saved_tensors
+        Cn = x.shape[-1]
+        if dy is None:                                      # only the residual path was used
+            return dres, None, None, None
+        dx, dg, db = ops.layernorm_bwd(x, dy.contiguous(), g, mean, rstd, _zeros((Cn,), x.device), _zeros((Cn,), x.device),
+                                       dx_add=None if dres is None else dres.contiguous())
         _commit()
         return dx, dg.to(ctx.pd), db.to(ctx.pd), None
 
@@ -240,7 +279,19 @@ class LepeAttentionFn(Function):
             return dict(dout=dout[..., sl], dq=dq[..., sl], dk=dk[..., sl], dv=dv[..., sl], dconv_w=gw[i], dconv_b=gb[i],
                         lse=lses[i])
         descs = LepeAttentionFn._descs(qkv, dout, ws, meta, Cn, extra)
-        ops.lepe_attention_bwd(descs, B, meta["reso"], meta["scale"], qkv.dtype)
+        # d get_v.{weight,bias} need only dout and v: they run as their own streaming kernel on a second stream, next to the
+        # attention backward kernel (which is latency-bound and leaves most issue slots idle)
+        side = None
+        if PARAM_GRAD_SIDE_STREAM and qkv.dtype == torch.bfloat16:
+            cur = torch.cuda.current_stream()
+            side = _side_stream(qkv.device)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                if not ops.lepe_param_grad(descs, B, meta["reso"], qkv.dtype):
+                    side = None
+        ops.lepe_attention_bwd(descs, B, meta["reso"], meta["scale"], qkv.dtype, param_grads=side is None)
+        if side is not None:
+            cur.wait_stream(side)
         _commit()
         g0 = (gw[0].view(h, 1, 3, 3).to(ctx.pd), gb[0].to(ctx.pd))
         g1 = (gw[1].view(h, 1, 3, 3).to(ctx.pd), gb[1].to(ctx.pd)) if len(ws) == 2 else (None, None)

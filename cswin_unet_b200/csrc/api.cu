@@ -85,6 +85,19 @@ int cswin_lepe_attention_bwd(const cswin_lepe_branch_grad_t* branches, int32_t n
   return lepe_attention_bwd_simt(branches, n_branches, B, reso, scale, dtype, (cudaStream_t)stream);
 }
 
+int cswin_lepe_param_grad(const cswin_lepe_branch_grad_t* branches, int32_t n_branches, int32_t B, int32_t reso,
+                          int32_t dtype, cswin_stream_t stream, int32_t* handled) {
+  CSWIN_REQUIRE(valid_dtype(dtype) && handled, CSWIN_ERR_INVALID, "lepe_param_grad: bad dtype %d / null handled", dtype);
+  CSWIN_REQUIRE(branches && (n_branches == 1 || n_branches == 2), CSWIN_ERR_INVALID, "lepe_param_grad: n_branches must be 1 or 2");
+  CSWIN_REQUIRE(B >= 0 && reso > 0, CSWIN_ERR_INVALID, "lepe_param_grad: bad B=%d reso=%d", B, reso);
+  *handled = 0;
+  if (B == 0 || dtype != CSWIN_BF16) return CSWIN_OK;
+  bool h = false;
+  const int rc = lepe_param_grad_tc(branches, n_branches, B, reso, (cudaStream_t)stream, &h);
+  *handled = h ? 1 : 0;
+  return rc;
+}
+
 int cswin_layernorm_fwd(const void* x, int64_t ldx, const void* gamma, const void* beta, void* y, int64_t ldy,
                         int64_t M, int32_t C, float eps, float* mean_out, float* rstd_out, int32_t dtype,
                         cswin_stream_t stream) {
@@ -185,10 +198,12 @@ int cswin_linear_wgrad(const void* dz, int64_t ldz, const void* a, int64_t lda, 
 }
 
 int cswin_layernorm_bwd(const void* x, int64_t ldx, const void* dy, int64_t ldy, const void* gamma, const float* mean,
-                        const float* rstd, void* dx, int64_t ldo, float* dgamma, float* dbeta, int64_t M, int32_t C,
-                        int32_t dtype, cswin_stream_t stream) {
+                        const float* rstd, void* dx, int64_t ldo, const void* dx_add, int64_t ld_add, float* dgamma,
+                        float* dbeta, int64_t M, int32_t C, int32_t dtype, cswin_stream_t stream) {
   CSWIN_REQUIRE(valid_dtype(dtype) && M >= 0, CSWIN_ERR_INVALID, "layernorm_bwd: bad arguments");
-  return layernorm_bwd(x, ldx, dy, ldy, gamma, mean, rstd, dx, ldo, dgamma, dbeta, M, C, dtype, (cudaStream_t)stream);
+  CSWIN_REQUIRE(dx_add == nullptr || ld_add >= C, CSWIN_ERR_INVALID, "layernorm_bwd: ld_add too small");
+  return layernorm_bwd(x, ldx, dy, ldy, gamma, mean, rstd, dx, ldo, dx_add, dx_add ? ld_add : 0, dgamma, dbeta, M, C, dtype,
+                       (cudaStream_t)stream);
 }
 
 int cswin_col2im_tokens(const void* dcol, int64_t ldcol, void* dx, int64_t x_bs, int64_t x_ts, int32_t B, int32_t H, int32_t W,

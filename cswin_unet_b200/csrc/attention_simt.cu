@@ -322,7 +322,8 @@ __global__ void __launch_bounds__(kBwdWarps * 32) lepe_attn_bwd_simt_kernel(cons
     }
     __syncwarp();
   }
-  // ---- LePE parameter gradients ----
+  // ---- LePE parameter gradients (skipped when the caller computes them with cswin_lepe_param_grad) ----
+  if (bg.dcw == nullptr) return;                         // CTA-uniform
   for (int jj = 0; jj < d; jj += 32) {
     const int j = jj + lane;
     float acc[10];
@@ -368,7 +369,7 @@ int launch_bwd(const cswin_lepe_branch_grad_t* gs, int nb, int B, int reso, floa
   P.nb = nb; P.B = B; P.reso = reso; P.scale = scale;
   for (int i = 0; i < nb; ++i) {
     const cswin_lepe_branch_grad_t& s = gs[i];
-    CSWIN_REQUIRE(s.dout && s.dq && s.dk && s.dv && s.dconv_w && s.dconv_b, CSWIN_ERR_INVALID, "lepe_attention_bwd: null pointer in branch %d", i);
+    CSWIN_REQUIRE(s.dout && s.dq && s.dk && s.dv && ((s.dconv_w != nullptr) == (s.dconv_b != nullptr)), CSWIN_ERR_INVALID, "lepe_attention_bwd: null pointer in branch %d", i);
     BranchGradDev<T>& d = P.br[i];
     d.f = F.br[i];
     d.g = (const T*)s.dout; d.g_bs = s.do_bs; d.g_ts = s.do_ts;

@@ -158,7 +158,8 @@ template <typename T, int VPL>
 __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ dy,
                                                              int64_t ldy, const T* __restrict__ gamma,
                                                              const float* __restrict__ mean, const float* __restrict__ rstd,
-                                                             T* __restrict__ dx, int64_t ldo, float* __restrict__ dgamma,
+                                                             T* __restrict__ dx, int64_t ldo, const T* __restrict__ dx_add,
+                                                             int64_t lda, float* __restrict__ dgamma,
                                                              float* __restrict__ dbeta, int64_t M, int C) {
   __shared__ float red[8][32 * VPL * 2];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -188,7 +189,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const T* __restrict_
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
       const int c = lane + 32 * i;
-      if (c < C) stf(dx + row * ldo + c, rs * (g[i] - s1 - xh[i] * s2));
+      if (c < C) stf(dx + row * ldo + c, rs * (g[i] - s1 - xh[i] * s2) + (dx_add != nullptr ? ldf(dx_add + row * lda + c) : 0.f));
     }
   }
 #pragma unroll
@@ -212,6 +213,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_bf16_vec_kernel(const __nv_
                                                                       const __nv_bfloat16* __restrict__ gamma,
                                                                       const float* __restrict__ mean, const float* __restrict__ rstd,
                                                                       __nv_bfloat16* __restrict__ dx, int64_t ldo,
+                                                                      const __nv_bfloat16* __restrict__ dx_add, int64_t lda,
                                                                       float* __restrict__ dgamma, float* __restrict__ dbeta, int64_t M) {
   pdl_trigger();
   pdl_wait();
@@ -263,10 +265,13 @@ __global__ void __launch_bounds__(256) layernorm_bwd_bf16_vec_kernel(const __nv_
 #pragma unroll
       for (int v = 0; v < NV; ++v) {
         uint32_t o[4];
+        uint4 ua = make_uint4(0, 0, 0, 0);                 // gradient that by-passed the LayerNorm through the residual add
+        if (dx_add != nullptr) ua = *reinterpret_cast<const uint4*>(dx_add + row * lda + (v * LPR + l) * 8);
+        const uint32_t aw[4] = {ua.x, ua.y, ua.z, ua.w};
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const __nv_bfloat162 h2 = __floats2bfloat162_rn(rs * (g[v][2 * e] - s1 - xh[v][2 * e] * s2),
-                                                          rs * (g[v][2 * e + 1] - s1 - xh[v][2 * e + 1] * s2));
+          const __nv_bfloat162 h2 = __floats2bfloat162_rn(rs * (g[v][2 * e] - s1 - xh[v][2 * e] * s2) + __uint_as_float(aw[e] << 16),
+                                                          rs * (g[v][2 * e + 1] - s1 - xh[v][2 * e + 1] * s2) + __uint_as_float(aw[e] & 0xffff0000u));
           o[e] = *reinterpret_cast<const uint32_t*>(&h2);
         }
         *reinterpret_cast<uint4*>(dx + row * ldo + (v * LPR + l) * 8) = make_uint4(o[0], o[1], o[2], o[3]);
@@ -820,25 +825,25 @@ int linear_wgrad(const void* dz, int64_t ldz, const void* a, int64_t lda, float*
 }
 
 int layernorm_bwd(const void* x, int64_t ldx, const void* dy, int64_t ldy, const void* gamma, const float* mean,
-                  const float* rstd, void* dx, int64_t ldo, float* dgamma, float* dbeta, int64_t M, int C, int dtype,
-                  cudaStream_t s) {
+                  const float* rstd, void* dx, int64_t ldo, const void* dx_add, int64_t lda, float* dgamma, float* dbeta,
+                  int64_t M, int C, int dtype, cudaStream_t s) {
   CSWIN_REQUIRE(x && dy && gamma && mean && rstd && dx && dgamma && dbeta, CSWIN_ERR_INVALID, "layernorm_bwd: null pointer");
   CSWIN_REQUIRE(C > 0 && C <= 512, CSWIN_ERR_UNSUPPORTED, "layernorm_bwd: C=%d outside (0, 512]", C);
   if (M == 0) return CSWIN_OK;
   const unsigned grid = (unsigned)std::min<int64_t>(ceil_div64(M, 8), (int64_t)sm_count() * 4);
-  const bool vec = dtype == CSWIN_BF16 && (ldx % 8 == 0) && (ldy % 8 == 0) && (ldo % 8 == 0) &&
+  const bool vec = dtype == CSWIN_BF16 && (ldx % 8 == 0) && (ldy % 8 == 0) && (ldo % 8 == 0) && (lda % 8 == 0) &&
                    ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx) |
-                     reinterpret_cast<uintptr_t>(gamma)) & 15) == 0;
+                     reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(dx_add)) & 15) == 0;
   if (vec && (C == 64 || C == 128 || C == 256 || C == 512)) {
     const int rpw = C == 64 ? 4 : C == 128 ? 2 : 1;
     const unsigned gv = (unsigned)std::min<int64_t>(ceil_div64(M, 8 * rpw), (int64_t)sm_count() * 2);
-#define LNV(L, V) CSWIN_CUDA_OK(launch_pdl(layernorm_bwd_bf16_vec_kernel<L, V>, dim3(gv), dim3(256), (size_t)0, s, (const __nv_bfloat16*)x, ldx, (const __nv_bfloat16*)dy, ldy, (const __nv_bfloat16*)gamma, mean, rstd, (__nv_bfloat16*)dx, ldo, dgamma, dbeta, M))
+#define LNV(L, V) CSWIN_CUDA_OK(launch_pdl(layernorm_bwd_bf16_vec_kernel<L, V>, dim3(gv), dim3(256), (size_t)0, s, (const __nv_bfloat16*)x, ldx, (const __nv_bfloat16*)dy, ldy, (const __nv_bfloat16*)gamma, mean, rstd, (__nv_bfloat16*)dx, ldo, (const __nv_bfloat16*)dx_add, lda, dgamma, dbeta, M))
     if (C == 64) LNV(8, 1); else if (C == 128) LNV(16, 1); else if (C == 256) LNV(32, 1); else LNV(32, 2);
 #undef LNV
     CSWIN_LAUNCH_CHECK();
     return CSWIN_OK;
   }
-#define LNB(T, V) layernorm_bwd_kernel<T, V><<<grid, 256, 0, s>>>((const T*)x, ldx, (const T*)dy, ldy, (const T*)gamma, mean, rstd, (T*)dx, ldo, dgamma, dbeta, M, C)
+#define LNB(T, V) layernorm_bwd_kernel<T, V><<<grid, 256, 0, s>>>((const T*)x, ldx, (const T*)dy, ldy, (const T*)gamma, mean, rstd, (T*)dx, ldo, (const T*)dx_add, lda, dgamma, dbeta, M, C)
   if (dtype == CSWIN_F32) { if (C <= 128) LNB(float, 4); else LNB(float, 16); }
   else { if (C <= 128) LNB(__nv_bfloat16, 4); else LNB(__nv_bfloat16, 16); }
 #undef LNB

@@ -96,6 +96,7 @@ int lepe_attention_fwd_simt(const cswin_lepe_branch_t* br, int nb, int B, int re
 int lepe_attention_fwd_tc(const cswin_lepe_branch_t* br, int nb, int B, int reso, float scale, cudaStream_t s, bool* handled);
 int lepe_attention_bwd_tc(const cswin_lepe_branch_grad_t* br, int nb, int B, int reso, float scale, cudaStream_t s, bool* handled);
 int lepe_attention_bwd_simt(const cswin_lepe_branch_grad_t* br, int nb, int B, int reso, float scale, int dtype, cudaStream_t s);
+int lepe_param_grad_tc(const cswin_lepe_branch_grad_t* br, int nb, int B, int reso, cudaStream_t s, bool* handled);
 int layernorm_fwd(const void* x, int64_t ldx, const void* g, const void* b, void* y, int64_t ldy, int64_t M, int C,
                   float eps, float* mean, float* rstd, float* ystats, int dtype, cudaStream_t s);
 int row_stats(const void* x, int64_t ldx, int64_t M, int C, float* stats, int dtype, cudaStream_t s);
@@ -127,8 +128,8 @@ int linear_wgrad(const void* dz, int64_t ldz, const void* a, int64_t lda, float*
 int linear_wgrad_tc(const void* dz, int64_t ldz, const void* a, int64_t lda, float* dw, int64_t ldw, float* db, int64_t M,
                     int N, int K, cudaStream_t s, bool* handled);
 int layernorm_bwd(const void* x, int64_t ldx, const void* dy, int64_t ldy, const void* gamma, const float* mean,
-                  const float* rstd, void* dx, int64_t ldo, float* dgamma, float* dbeta, int64_t M, int C, int dtype,
-                  cudaStream_t s);
+                  const float* rstd, void* dx, int64_t ldo, const void* dx_add, int64_t lda, float* dgamma, float* dbeta,
+                  int64_t M, int C, int dtype, cudaStream_t s);
 int col2im_tokens(const void* dcol, int64_t ldcol, void* dx, int64_t x_bs, int64_t x_ts, int B, int H, int W, int C, int KH,
                   int KW, int stride, int pad, int dtype, cudaStream_t s);
 int carafe_reassemble_bwd(const void* enc, int64_t ldenc, const void* z, int64_t ldz, const void* dy, int dy_is_f32,

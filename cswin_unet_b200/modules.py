@@ -16,7 +16,7 @@ from __future__ import annotations
 
 import math
 import os
-from typing import Callable, Dict, Optional, Tuple
+from typing import Callable, Dict, List, Optional, Tuple
 
 import torch
 import torch.nn as nn
@@ -30,6 +30,50 @@ Tensor = torch.Tensor
 # ------------------------------------------------------------------------------------------
 # helpers
 # ------------------------------------------------------------------------------------------
+class DropPathPlan:
+    """All stochastic-depth masks of one training step from TWO launches instead of three per DropPath call (152 -> 2 at
+    cswin_tiny: bernoulli_, div_, cast per call are ~2 us each and sit on the step's critical path).  The first step under
+    a plan records the keep probabilities in call order (every module still draws for itself); later steps draw one
+    (calls, B) Bernoulli matrix up front and hand out its rows.  Statistically identical to timm's DropPath; the RNG
+    stream is consumed in one draw per step instead of one per call, so masks differ from a per-call run with the same
+    seed (plain module use, without a plan, keeps timm's per-call consumption)."""
+
+    def __init__(self):
+        self.keeps: List[Tuple[float, bool]] = []
+        self.recording = True
+        self.rows: Optional[Tensor] = None
+        self._probs = self._inv = None
+        self.i = 0
+
+    def begin(self, batch: int, device) -> None:
+        self.i = 0
+        self.rows = None
+        if self.recording or not self.keeps:
+            return
+        if self._probs is None or self._probs.device != torch.device(device):
+            self._probs = torch.tensor([k for k, _ in self.keeps], dtype=torch.float32, device=device).view(-1, 1)
+            self._inv = torch.tensor([(1.0 / k if (k > 0.0 and sc) else 1.0) for k, sc in self.keeps], dtype=torch.float32,
+                                     device=device).view(-1, 1)
+        self.rows = torch.bernoulli(self._probs.expand(-1, batch)) * self._inv
+
+    def take(self, keep: float, scale_by_keep: bool, batch: int) -> Optional[Tensor]:
+        if self.recording:
+            self.keeps.append((keep, scale_by_keep))
+            return None
+        if self.rows is None or self.i >= len(self.keeps) or self.keeps[self.i] != (keep, scale_by_keep) or self.rows.shape[1] != batch:
+            self.i += 1
+            return None                                     # call sequence changed: this call draws for itself
+        row = self.rows[self.i]
+        self.i += 1
+        return row
+
+    def end(self) -> None:
+        self.recording = False
+
+
+DROP_PATH_PLAN: Optional[DropPathPlan] = None            # set by train.TrainStep around the forward
+
+
 class DropPath(nn.Module):
     """Stochastic depth with timm's semantics and RNG consumption (one bernoulli_ of shape (B,1,..,1) in x.dtype)."""
 
@@ -43,6 +87,10 @@ class DropPath(nn.Module):
         if self.drop_prob == 0. or not self.training:
             return None
         keep = 1.0 - self.drop_prob
+        if DROP_PATH_PLAN is not None:
+            row = DROP_PATH_PLAN.take(keep, self.scale_by_keep, x.shape[0])
+            if row is not None:
+                return row
         m = x.new_empty((x.shape[0],) + (1,) * (x.ndim - 1)).bernoulli_(keep)
         if keep > 0.0 and self.scale_by_keep:
             m.div_(keep)
@@ -349,7 +397,7 @@ class CSWinBlock(_Native):
         B, L, Cn = x.shape
         for a in self.attns:
             a._check(L)
-        u = ag.LayerNormFn.apply(x, self.norm1.weight, self.norm1.bias, self.norm1.eps)
+        u, xr = ag.LayerNormForkFn.apply(x, self.norm1.weight, self.norm1.bias, self.norm1.eps)
         qkv = ag.linear(u, self.qkv.weight, self.qkv.bias)
         meta = dict(reso=H, scale=float(self.attns[0].scale), heads=[a.num_heads for a in self.attns],
                     win=[(a.H_sp, a.W_sp) for a in self.attns])
@@ -357,10 +405,10 @@ class CSWinBlock(_Native):
         a1 = self.attns[1] if self.branch_num == 2 else None
         att = ag.LepeAttentionFn.apply(qkv, a0.get_v.weight, a0.get_v.bias, a1.get_v.weight if a1 else None,
                                        a1.get_v.bias if a1 else None, meta)
-        x1 = ag.linear(att, self.proj.weight, self.proj.bias, residual=x, sample_scale=self._sample_scale(x), rps=L)
-        u2 = ag.LayerNormFn.apply(x1, self.norm2.weight, self.norm2.bias, self.norm2.eps)
+        x1 = ag.linear(att, self.proj.weight, self.proj.bias, residual=xr, sample_scale=self._sample_scale(x), rps=L)
+        u2, x1r = ag.LayerNormForkFn.apply(x1, self.norm2.weight, self.norm2.bias, self.norm2.eps)
         hid = ag.GeluFn.apply(ag.linear(u2, self.mlp.fc1.weight, self.mlp.fc1.bias))
-        return ag.linear(hid, self.mlp.fc2.weight, self.mlp.fc2.bias, residual=x1, sample_scale=self._sample_scale(x), rps=L)
+        return ag.linear(hid, self.mlp.fc2.weight, self.mlp.fc2.bias, residual=x1r, sample_scale=self._sample_scale(x), rps=L)
 
 
 # ------------------------------------------------------------------------------------------

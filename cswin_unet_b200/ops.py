@@ -393,8 +393,7 @@ def carafe_head_bwd(enc: Tensor, z: Tensor, dlogits: Tensor, B: int, H: int, W: 
                                       dbias.data_ptr(), kws.data_ptr(), B, H, W, n_classes, up, _dtype_code(z), _stream()),
           "cswin_carafe_head_bwd")
     return denc, dz, dbias
-def lepe_attention_bwd(branches: Sequence[dict], B: int, reso: int, scale: float, dtype: torch.dtype) -> None:
-    """branches: forward description + dout, dq, dk, dv (views with unit channel stride), dconv_w (C_b,9) / dconv_b (C_b) fp32."""
+def _lepe_grad_array(branches: Sequence[dict], param_grads: bool):
     arr = (LepeBranchGrad * len(branches))()
     keep = []
     for i, b in enumerate(branches):
@@ -411,11 +410,33 @@ def lepe_attention_bwd(branches: Sequence[dict], B: int, reso: int, scale: float
             assert t.stride(-1) == 1
             setattr(g, n, t.data_ptr()); setattr(g, n + "_bs", t.stride(0)); setattr(g, n + "_ts", t.stride(1))
         assert b["dconv_w"].dtype == torch.float32 and b["dconv_b"].dtype == torch.float32
-        g.dconv_w, g.dconv_b = b["dconv_w"].data_ptr(), b["dconv_b"].data_ptr()
+        if param_grads:
+            g.dconv_w, g.dconv_b = b["dconv_w"].data_ptr(), b["dconv_b"].data_ptr()
+        else:
+            g.dconv_w, g.dconv_b = None, None
         arr[i] = g
+    return arr, keep
+
+
+def lepe_attention_bwd(branches: Sequence[dict], B: int, reso: int, scale: float, dtype: torch.dtype,
+                       param_grads: bool = True) -> None:
+    """branches: forward description + dout, dq, dk, dv (views with unit channel stride), dconv_w (C_b,9) / dconv_b (C_b) fp32.
+    param_grads=False: dconv_w / dconv_b are left alone (the caller ran `lepe_param_grad`)."""
+    arr, keep = _lepe_grad_array(branches, param_grads)
     code = F32 if dtype == torch.float32 else BF16
     check(lib().cswin_lepe_attention_bwd(arr, len(branches), B, reso, C.c_float(scale), code, _stream()),
           "cswin_lepe_attention_bwd")
+
+
+def lepe_param_grad(branches: Sequence[dict], B: int, reso: int, dtype: torch.dtype) -> bool:
+    """dconv_w / dconv_b += gradients of get_v from dout and v alone, on the current stream.  False = configuration outside the
+    kernel's envelope, nothing launched (then call lepe_attention_bwd with param_grads=True)."""
+    if dtype != torch.bfloat16:
+        return False
+    arr, keep = _lepe_grad_array(branches, True)
+    handled = C.c_int32(0)
+    check(lib().cswin_lepe_param_grad(arr, len(branches), B, reso, BF16, _stream(), C.byref(handled)), "cswin_lepe_param_grad")
+    return bool(handled.value)
 
 
 def act_fwd(z: Tensor, act: int = 1) -> Tensor:
@@ -451,10 +472,15 @@ def linear_wgrad(dz: Tensor, a: Tensor, dw: Tensor, db: Optional[Tensor]) -> Non
 
 
 def layernorm_bwd(x: Tensor, dy: Tensor, gamma: Tensor, mean: Tensor, rstd: Tensor, dg: Optional[Tensor] = None,
-                  db: Optional[Tensor] = None):
-    _need_cuda(x, dy, gamma, mean, rstd)
+                  db: Optional[Tensor] = None, dx_add: Optional[Tensor] = None):
+    """dx = LayerNorm'(dy) (+ dx_add: the gradient that reached x through the residual connection around the LayerNorm)."""
+    _need_cuda(x, dy, gamma, mean, rstd, dx_add)
     x2, M, ldx = _rows(x)
     d2, _, ldy = _rows(dy)
+    add2, lda = None, 0
+    if dx_add is not None:
+        assert dx_add.shape == x.shape and dx_add.dtype == x.dtype
+        add2, _, lda = _rows(dx_add)
     Cn = x.shape[-1]
     dx = torch.empty(x.shape, dtype=x.dtype, device=x.device)
     if dg is None:                                        # accumulated into: the caller may pass pre-zeroed slices
@@ -462,7 +488,8 @@ def layernorm_bwd(x: Tensor, dy: Tensor, gamma: Tensor, mean: Tensor, rstd: Tens
     if db is None:
         db = torch.zeros(Cn, dtype=torch.float32, device=x.device)
     check(lib().cswin_layernorm_bwd(x2.data_ptr(), ldx, d2.data_ptr(), ldy, gamma.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
-                                    dx.data_ptr(), Cn, dg.data_ptr(), db.data_ptr(), M, Cn, _dtype_code(x), _stream()),
+                                    dx.data_ptr(), Cn, _ptr(add2), lda, dg.data_ptr(), db.data_ptr(), M, Cn, _dtype_code(x),
+                                    _stream()),
           "cswin_layernorm_bwd")
     return dx, dg, db
 

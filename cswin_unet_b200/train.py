@@ -19,6 +19,7 @@ import torch
 import torch.nn.functional as F
 
 from . import autograd as ag
+from . import modules
 from . import ops
 from . import parallel
 
@@ -50,7 +51,8 @@ class TrainStep:
     replayed; the NCCL all-reduce stays outside the graph (eager, bucketed) when more than one rank trains."""
 
     def __init__(self, model, lr: float = 0.05, momentum: float = 0.9, weight_decay: float = 1e-4,
-                 compute_dtype: torch.dtype = torch.bfloat16, group=None, graph: bool = True, warmup: int = 3):
+                 compute_dtype: torch.dtype = torch.bfloat16, group=None, graph: bool = True, warmup: int = 3,
+                 batched_drop_path: bool = True):
         self.model = model.train()
         self.model.compute_dtype = compute_dtype
         self.n_classes = model.num_classes
@@ -77,6 +79,8 @@ class TrainStep:
         self._static = None
         self._seen = 0
         self._make_shadow(compute_dtype)
+        # every DropPath mask of a step from one Bernoulli draw (modules.DropPathPlan); False = timm's per-call RNG consumption
+        self._drop_plan = modules.DropPathPlan() if (batched_drop_path and os.environ.get("CSWIN_DROPPATH_PER_CALL") != "1") else None
         self._pool = None if os.environ.get("CSWIN_NO_POOL") == "1" else ag.ZeroPool(
             sum(p.numel() + 4 for p in model.parameters()), next(model.parameters()).device)
         self._distributed = torch.distributed.is_available() and torch.distributed.is_initialized() and \
@@ -137,8 +141,14 @@ class TrainStep:
             ag.POOL = self._pool
         if self._reducer is not None:
             self._reducer.begin()
+        if self._drop_plan is not None:
+            self._drop_plan.begin(images.shape[0], images.device)
+            modules.DROP_PATH_PLAN = self._drop_plan
         try:
             logits = self.model(images)
+            if self._drop_plan is not None:
+                self._drop_plan.end()
+            modules.DROP_PATH_PLAN = None
             loss = seg_loss(logits, labels, self.n_classes)
             loss.backward()
             if self._reducer is not None:                       # tail bucket + gradients that live outside the pool
@@ -146,6 +156,7 @@ class TrainStep:
                 rest = [p for p in self.model.parameters() if p.grad is not None and not self._reducer.in_pool(p.grad)]
                 parallel.allreduce_gradients(rest, self.group)
         finally:
+            modules.DROP_PATH_PLAN = None
             ag.SHADOW = {}
             ag.POOL = None
             if self._pool is not None:

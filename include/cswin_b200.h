@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define CSWIN_ABI_VERSION 3
+#define CSWIN_ABI_VERSION 4
 
 typedef struct CUstream_st* cswin_stream_t; /* == cudaStream_t */
 
@@ -93,6 +93,14 @@ typedef struct {
 
 int cswin_lepe_attention_bwd(const cswin_lepe_branch_grad_t* branches, int32_t n_branches, int32_t B, int32_t reso,
                              float scale, int32_t dtype, cswin_stream_t stream);
+
+/* The parameter-gradient half of the above on its own: dconv_w / dconv_b += autograd of get_v (cswin_unet.py:55, :76)
+ * from `dout` and `fwd.v` only (q, k, lse, dq, dk, dv are not touched), so a caller can run it on a second stream next
+ * to cswin_lepe_attention_bwd called with dconv_w = dconv_b = NULL (which then skips them).  *handled = 1 if the
+ * kernel was launched, 0 if the configuration is outside its envelope (bf16, C_b % 32 == 0, 8-byte aligned rows) —
+ * nothing was launched and the caller passes dconv_w / dconv_b to cswin_lepe_attention_bwd instead. */
+int cswin_lepe_param_grad(const cswin_lepe_branch_grad_t* branches, int32_t n_branches, int32_t B, int32_t reso,
+                          int32_t dtype, cswin_stream_t stream, int32_t* handled);
 
 /* ------------------------------------------------------------------------------------------------
  * LayerNorm over the last dimension.  Replaces nn.LayerNorm calls: norm1/norm2 (cswin_unet.py:168,179),
@@ -265,9 +273,12 @@ int cswin_act_bwd(const void* dout, int64_t ldd, const void* z, int64_t ldz, con
                   cswin_stream_t stream);
 int cswin_linear_wgrad(const void* dz, int64_t ldz, const void* a, int64_t lda, float* dw, int64_t ldw, float* db, int64_t M,
                        int32_t N, int32_t K, int32_t dtype, cswin_stream_t stream);
+/* dx = LayerNorm'(dy) [+ dx_add]; dx_add (optional, layout of dx with row pitch ld_add) is the gradient that by-passes the
+ * LayerNorm through the residual connection (x + f(LN(x)), cswin_unet.py:178-179): autograd's separate accumulation add
+ * becomes part of this kernel's store.  dgamma / dbeta (C) fp32 are accumulated into. */
 int cswin_layernorm_bwd(const void* x, int64_t ldx, const void* dy, int64_t ldy, const void* gamma, const float* mean,
-                        const float* rstd, void* dx, int64_t ldo, float* dgamma, float* dbeta, int64_t M, int32_t C,
-                        int32_t dtype, cswin_stream_t stream);
+                        const float* rstd, void* dx, int64_t ldo, const void* dx_add, int64_t ld_add, float* dgamma,
+                        float* dbeta, int64_t M, int32_t C, int32_t dtype, cswin_stream_t stream);
 /* adjoint of cswin_im2col_tokens: dx (B, H*W, C) from dcol (B*Ho*Wo, KH*KW*C) */
 int cswin_col2im_tokens(const void* dcol, int64_t ldcol, void* dx, int64_t x_bs, int64_t x_ts, int32_t B, int32_t H, int32_t W,
                         int32_t C, int32_t KH, int32_t KW, int32_t stride, int32_t pad, int32_t dtype, cswin_stream_t stream);

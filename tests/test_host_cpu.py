@@ -93,3 +93,38 @@ def test_synth_is_deterministic_and_name_keyed():
     c = synth.synth_tensor("stage1.0.proj.weight", (192, 64), 7)
     assert np.array_equal(a, b) and not np.array_equal(a, c)
     assert abs(float(a.std()) - 1 / 8) < 0.01
+
+
+def test_drop_path_plan_batches_the_draws_of_a_step():
+    """modules.DropPathPlan: the first step records the call sequence (modules draw for themselves), later steps hand out rows of
+    one (calls, B) Bernoulli draw with timm's scaling (mask / keep_prob); a changed call sequence falls back to per-call draws."""
+    import torch
+    from cswin_unet_b200 import modules
+    plan = modules.DropPathPlan()
+    dps = [modules.DropPath(p).train() for p in (0.1, 0.5, 0.0, 0.3)]
+    x = torch.zeros(4096, 3, 2)
+    try:
+        for step in range(3):
+            plan.begin(x.shape[0], "cpu")
+            modules.DROP_PATH_PLAN = plan
+            outs = [d.sample_scale(x) for d in dps]
+            plan.end()
+            modules.DROP_PATH_PLAN = None
+            assert outs[2] is None                                            # p == 0: inactive, not part of the plan
+            for d, o in zip(dps, outs):
+                if o is None:
+                    continue
+                keep = 1.0 - d.drop_prob
+                assert o.shape == (4096,) and o.dtype == torch.float32
+                vals = set(round(v, 5) for v in o.unique().tolist())
+                assert vals <= {0.0, round(1.0 / keep, 5)}
+                assert abs((o > 0).float().mean().item() - keep) < 0.04       # Bernoulli(keep)
+            if step > 0:
+                assert plan.rows is not None and plan.rows.shape == (3, 4096) and plan.i == 3
+        # a different call sequence: the plan declines, the module draws for itself
+        plan.begin(x.shape[0], "cpu")
+        modules.DROP_PATH_PLAN = plan
+        o = modules.DropPath(0.25).train().sample_scale(x)
+        assert o is not None and abs((o > 0).float().mean().item() - 0.75) < 0.04
+    finally:
+        modules.DROP_PATH_PLAN = None

@@ -27,3 +27,13 @@ tot = sum(v[1] for v in agg.values()); cnt = sum(v[0] for v in agg.values())
 print(f"batch {B}: {cnt} kernels, {tot/1e3:.2f} ms device time")
 for n, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:32]:
     print(f"{t:9.1f} us {c:5d} x {t/c:8.2f}  {n}")
+
+if len(sys.argv) > 2 and sys.argv[2] == "ops":
+    # which torch-level (non-native) ops still launch kernels: aten op x input shapes, by device time
+    with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], record_shapes=True) as prof2:
+        step(x, y); torch.cuda.synchronize()
+    rows = [e for e in prof2.key_averages(group_by_input_shape=True) if e.key.startswith("aten::") and e.self_device_time_total > 0]
+    rows.sort(key=lambda e: -e.self_device_time_total)
+    print("torch-level ops with device time:")
+    for e in rows[:40]:
+        print(f"{e.self_device_time_total:9.1f} us {e.count:5d} x  {e.key:28s} {str(e.input_shapes)[:110]}")
