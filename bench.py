@@ -96,6 +96,26 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
+def shutdown_dist(timeout_s: float = 20.0) -> None:
+    """destroy_process_group() with a watchdog: NCCL teardown after CUDA-graph-captured collectives has been seen to block;
+    the result line is already printed and flushed, so a stuck teardown ends the process instead of hanging the launcher."""
+    import gc
+    gc.collect()
+    torch.cuda.synchronize()
+    done = threading.Event()
+
+    def watch():
+        if not done.wait(timeout_s):
+            sys.stdout.flush(); sys.stderr.flush()
+            os._exit(0)
+    threading.Thread(target=watch, daemon=True).start()
+    try:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+    finally:
+        done.set()
+
+
 def dist_env():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -157,7 +177,7 @@ def run_reference(args):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"{args.steps} steps x {sample} slices, torch CPU fp32, {cores} threads"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -182,7 +202,6 @@ def run_native(args):
     dev = torch.device("cuda", local)
     if world > 1:
         import torch.distributed as dist
-        os.environ["NCCL_DEBUG"] = "WARN"                           # keep NCCL's version banner off stdout (one JSON line)
         dist.init_process_group("nccl", device_id=dev)
     cw.lib()                                                       # fail loudly if the extension is missing
 
@@ -377,6 +396,7 @@ def run_native(args):
                                       "backward on the pooled gradient buffer (N>1) + native fused SGD(momentum .9, wd 1e-4); whole step "
                                       "(collectives included) replayed as one CUDA graph",
                               "roofline_frac_tensor": world and (tk * B / (ms_tr * 1e-3)) * 33.231 / 1e3 / (pk["bf16_tflops_sustained"] or pk["bf16_tflops"])}
+        step_fn.close()
         del tmodel, step_fn
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -384,13 +404,40 @@ def run_native(args):
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": f"{n} forwards of batch {BATCH} in {dt:.1f} s, oracle (torch CPU fp32), {cores} threads"}
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
-        torch.distributed.destroy_process_group()
+        shutdown_dist()
     return 0
 
 
+class StdoutGuard:
+    """Everything that libraries write to fd 1 while the benchmark runs (NCCL's version banner, ...) goes to stderr; only the
+    result line reaches the real stdout."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self.real = os.dup(1)
+        os.dup2(2, 1)
+
+    def emit(self, text: str) -> None:
+        sys.stdout.flush()
+        os.write(self.real, (text + "\n").encode())
+
+
+GUARD = None
+
+
+def emit(line: dict) -> None:
+    text = json.dumps(line)
+    if GUARD is not None:
+        GUARD.emit(text)
+    else:
+        print(text, flush=True)
+
+
 def main():
+    global GUARD
+    GUARD = StdoutGuard()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)

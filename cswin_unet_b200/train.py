@@ -200,6 +200,18 @@ class TrainStep:
             self._refresh_shadow()
             self._versions = vers
 
+    def close(self) -> None:
+        """Drop the captured CUDA graphs (and with them the captured NCCL all-reduces).  Call before
+        torch.distributed.destroy_process_group(): tearing a communicator down while graphs that contain its collectives
+        are alive can block forever."""
+        self._graphs = None
+        self._static = None
+        self._loss = None
+        if self._reducer is not None:
+            self._pool.on_commit = None
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
+
     def __call__(self, images: Tensor, labels: Tensor) -> Tensor:
         self._check_external_writes()
         if not self.use_graph:
