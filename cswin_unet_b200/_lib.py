@@ -58,6 +58,7 @@ class LinearArgs(C.Structure):
         ("act", c_int32), ("w_layout", c_int32),
         ("ln_stats", c_void_p), ("ln_stats_parts", c_int32), ("ln_C", c_int32),
         ("ln_colsum", c_void_p), ("bias_f32", c_void_p), ("stats_out", c_void_p),
+        ("aux_out", c_void_p), ("ld_aux", c_int64),
     ]
 
 

@@ -212,6 +212,51 @@ class LinearFn(Function):
         return da, dw, db, da2, (dout if ctx.has_res else None), None, None
 
 
+class MlpFn(Function):
+    """out = residual + sample_scale * fc2(GELU(fc1(u)))  (Mlp, cswin_unet.py:12-28 + the residual / DropPath of :179) with the
+    activation work inside the GEMM epilogues: fc1 writes z and GELU(z) from one accumulator read (aux_out), and the backward's
+    dZ = dH o GELU'(z) is the epilogue of the fc2 data-gradient GEMM (act 2) — no separate activation passes either way."""
+
+    @staticmethod
+    def forward(ctx, u, w1, b1, w2, b2, residual, sample_scale, rps):
+        dt = u.dtype
+        w1c, b1c, w2c, b2c = _c(w1, dt), _c(b1, dt), _c(w2, dt), _c(b2, dt)
+        z = torch.empty(u.shape[:-1] + (w1c.shape[0],), dtype=dt, device=u.device)
+        h = ops.linear(u, w1c, b1c, act=1, aux_out=z)
+        out = ops.linear(h, w2c, b2c, residual=residual, sample_scale=sample_scale, rows_per_sample=rps)
+        ctx.save_for_backward(u, z, h, w1c, w2c, sample_scale)
+        ctx.rps, ctx.has_res = rps, residual is not None
+        ctx.dts = (w1.dtype, b1.dtype, w2.dtype, b2.dtype)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout):
+        u, z, h, w1c, w2c, ss = ctx.saved_tensors
+        dout = _tma_rows(dout)
+        dz2 = dout if ss is None else ops.act_bwd(dout, None, ss, ctx.rps, act=0)
+        dw2f, db2f = _zeros(tuple(w2c.shape), dout.device), _zeros((w2c.shape[0],), dout.device)
+        ops.linear_wgrad(dz2, h, dw2f, db2f)
+        dz = ops.linear(dz2, w2c, w_kn=True, act=2, residual=z)          # dH o GELU'(z)
+        dw1f, db1f = _zeros(tuple(w1c.shape), dout.device), _zeros((w1c.shape[0],), dout.device)
+        ops.linear_wgrad(dz, u, dw1f, db1f)
+        du = ops.linear(dz, w1c, w_kn=True) if ctx.needs_input_grad[0] else None
+        _commit()
+        d = ctx.dts
+        return du, dw1f.to(d[0]), db1f.to(d[1]), dw2f.to(d[2]), db2f.to(d[3]), (dout if ctx.has_res else None), None, None
+
+
+def mlp(u, w1, b1, w2, b2, residual=None, sample_scale=None, rps=0):
+    """MlpFn when the tcgen05 training epilogues apply (bf16, aligned rows), else the composed Linear / GELU / Linear nodes."""
+    if b1 is not None and b2 is not None and ops.train_epilogues_supported(u, w1.shape[0]) and w2.shape[0] % 8 == 0 and FUSE_TRAIN_GELU:
+        return MlpFn.apply(u, w1, b1, w2, b2, residual, sample_scale, rps)
+    hid = GeluFn.apply(linear(u, w1, b1))
+    return linear(hid, w2, b2, residual=residual, sample_scale=sample_scale, rps=rps)
+
+
+FUSE_TRAIN_GELU = _os.environ.get("CSWIN_FUSE_TRAIN_GELU", "1") != "0"
+
+
 class GeluFn(Function):
     @staticmethod
     def forward(ctx, z):

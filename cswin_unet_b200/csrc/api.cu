@@ -124,7 +124,9 @@ int cswin_linear_fwd(const cswin_linear_args_t* a, int32_t dtype, cswin_stream_t
   CSWIN_REQUIRE((a->ln_gamma != nullptr) == (a->ln_beta != nullptr), CSWIN_ERR_INVALID, "linear_fwd: ln_gamma and ln_beta must be given together");
   CSWIN_REQUIRE(!a->ln_gamma || !a->a2, CSWIN_ERR_INVALID, "linear_fwd: LayerNorm prologue needs a single A source");
   CSWIN_REQUIRE(!a->sample_scale || a->rows_per_sample > 0, CSWIN_ERR_INVALID, "linear_fwd: rows_per_sample must be > 0");
-  CSWIN_REQUIRE(a->act == 0 || a->act == 1, CSWIN_ERR_INVALID, "linear_fwd: act must be 0 (none) or 1 (GELU)");
+  CSWIN_REQUIRE(a->act == 0 || a->act == 1 || a->act == 2, CSWIN_ERR_INVALID, "linear_fwd: act must be 0 (none), 1 (GELU) or 2 (x GELU'(residual))");
+  CSWIN_REQUIRE(a->act != 2 || a->residual, CSWIN_ERR_INVALID, "linear_fwd: act 2 needs the pre-activation in `residual`");
+  CSWIN_REQUIRE(!a->aux_out || (a->act == 1 && a->ld_aux >= a->N), CSWIN_ERR_INVALID, "linear_fwd: aux_out needs act 1 and ld_aux >= N");
   if (a->M == 0) return CSWIN_OK;
   const bool folded = a->ln_colsum || a->ln_stats || a->stats_out || a->bias_f32;
   CSWIN_REQUIRE(!folded || dtype == CSWIN_BF16, CSWIN_ERR_UNSUPPORTED, "linear_fwd: LayerNorm folding / stats_out / bias_f32 exist on the bf16 path only");
@@ -135,6 +137,7 @@ int cswin_linear_fwd(const cswin_linear_args_t* a, int32_t dtype, cswin_stream_t
     int rc = linear_fwd_tc(a, (cudaStream_t)stream, &handled);
     if (rc != CSWIN_OK || handled) return rc;
   }
+  CSWIN_REQUIRE(!a->aux_out && a->act != 2, CSWIN_ERR_UNSUPPORTED, "linear_fwd: the training epilogues (aux_out, act 2) exist on the bf16 tcgen05 path with 16-byte aligned rows only");
   CSWIN_REQUIRE(!folded, CSWIN_ERR_UNSUPPORTED, "linear_fwd: operands are not TMA-compatible (16-byte aligned pointers / row pitches), which the folded-LayerNorm form requires");
   return linear_fwd_simt(a, dtype, (cudaStream_t)stream);
 }

@@ -42,7 +42,7 @@ constexpr int kMaxStages = 8;
 constexpr int kThreads = 320;                          // warp 0 TMA, warp 1 MMA + TMEM, warps 2..9 epilogue
 
 struct alignas(64) GemmTcParams {
-  CUtensorMap map_a, map_a2, map_w, map_out;
+  CUtensorMap map_a, map_a2, map_w, map_out, map_aux;
   const __nv_bfloat16* bias;
   const __nv_bfloat16* res; int64_t ldr;
   const float* sscale; int rps;
@@ -51,10 +51,29 @@ struct alignas(64) GemmTcParams {
   int BN, stages, nkb, nkb1, act, tmem_cols, vec_ok, bias_vec, w_kn, tma_out;
   const float* ln_stats; int ln_parts; float ln_invC, ln_eps;
   const float* ln_cs; const float* bias_f32; float* stats_out;
+  int aux, aux_off;                      // training epilogue: also store the pre-activation (map_aux); staging offset in smem
   unsigned long long* trace;
 };
 
-template <bool kFold, bool kStats>
+// GELU'(x) for a packed pair, same fit as the streaming activation kernels (backward.cu gelu_grad_fast)
+__device__ __forceinline__ float gelu_grad_fast1(float x) {
+  const float x2 = x * x;
+  float p = fmaf(x2, -1.36882761e-05f, -1.94451094e-04f);
+  p = fmaf(p, x2, 3.65466544e-02f);
+  p = fmaf(p, x2, 7.97820264e-01f);
+  float t, e;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(p * x));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x2 * -0.72134752044448170368f));
+  return fmaf(x * 0.39894228040143267794f, e, fmaf(0.5f, t, 0.5f));
+}
+__device__ __forceinline__ float2 gelu_grad_pair(uint32_t zz) {
+  return make_float2(gelu_grad_fast1(bf16_lo(zz)), gelu_grad_fast1(bf16_hi(zz)));
+}
+
+// kTrain adds the two training-only epilogues (TMA-store fast path only):
+//   aux : out = GELU(z) AND z itself goes to a second tensor (fc1 of the MLP: the backward needs the pre-activation);
+//   act 2: out = acc * GELU'(residual) — the data gradient of fc2 multiplied by GELU'(z) in place of a separate pass.
+template <bool kFold, bool kStats, bool kTrain = false>
 __global__ void __launch_bounds__(kThreads, CSWIN_GEMM_MINB) linear_tc_kernel(const __grid_constant__ GemmTcParams P) {
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for the 128-byte swizzle; plain pointer arithmetic keeps the shared address space (LDS/STS)
@@ -199,6 +218,7 @@ __global__ void __launch_bounds__(kThreads, CSWIN_GEMM_MINB) linear_tc_kernel(co
         uint4 rv[4];
         const int ncol = n0 + u * 32;
         const bool has_res = P.res != nullptr && mrow < P.M;
+        if (kTrain && !has_res) { rv[0] = rv[1] = rv[2] = rv[3] = make_uint4(0, 0, 0, 0); }
         if (has_res) {
 #pragma unroll
           for (int c = 0; c < 4; ++c)
@@ -230,16 +250,25 @@ __global__ void __launch_bounds__(kThreads, CSWIN_GEMM_MINB) linear_tc_kernel(co
               f[h * 2 + 1] = fadd2(a1, make_float2(bb.z, bb.w));
             }
           }
+          if (kTrain && P.aux) {                            // pre-activation z (bf16) into the second staging box
+            const uint32_t aaddr = stg_u32 + (uint32_t)P.aux_off + lane * 64 + (((c ^ (lane >> 1)) & 3) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(aaddr), "r"(pack_bf16x2(f[0].x, f[0].y)), "r"(pack_bf16x2(f[1].x, f[1].y)),
+                         "r"(pack_bf16x2(f[2].x, f[2].y)), "r"(pack_bf16x2(f[3].x, f[3].y)) : "memory");
+          }
           if (P.act == 1) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) f[e] = gelu_fast2(f[e]);
+          }
+          if (kTrain && P.act == 2) {                       // dZ = dH o GELU'(z), z = `residual` operand
+            f[0] = fmul2(f[0], gelu_grad_pair(rv[c].x)); f[1] = fmul2(f[1], gelu_grad_pair(rv[c].y));
+            f[2] = fmul2(f[2], gelu_grad_pair(rv[c].z)); f[3] = fmul2(f[3], gelu_grad_pair(rv[c].w));
           }
           if (P.sscale != nullptr) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) f[e] = fmul2(f[e], sc2);
           }
           uint4 x = make_uint4(pack_bf16x2(f[0].x, f[0].y), pack_bf16x2(f[1].x, f[1].y), pack_bf16x2(f[2].x, f[2].y), pack_bf16x2(f[3].x, f[3].y));
-          if (has_res) {
+          if (has_res && !(kTrain && P.act == 2)) {
             x.x = add_bf16x2(x.x, rv[c].x); x.y = add_bf16x2(x.y, rv[c].y);
             x.z = add_bf16x2(x.z, rv[c].z); x.w = add_bf16x2(x.w, rv[c].w);
           }
@@ -257,6 +286,7 @@ __global__ void __launch_bounds__(kThreads, CSWIN_GEMM_MINB) linear_tc_kernel(co
         __syncwarp();
         if (lane == 0) {
           tma_store_2d(&P.map_out, stg_u32, ncol, (int)(m0 + q * 32));
+          if (kTrain && P.aux) tma_store_2d(&P.map_aux, stg_u32 + (uint32_t)P.aux_off, ncol, (int)(m0 + q * 32));
           tma_store_commit();
         }
       }
@@ -498,17 +528,33 @@ int linear_fwd_tc(const cswin_linear_args_t* a, cudaStream_t stream, bool* handl
                                   CU_TENSOR_MAP_SWIZZLE_128B)) return CSWIN_ERR_CUDA;
   }
 
-  const size_t smem = smem_bytes(P.BN, P.stages);
+  // training epilogues (aux pre-activation output, act 2 = multiply by GELU'(residual)): TMA-store fast path, plain (unfolded) form
+  const bool train = a->aux_out != nullptr || a->act == 2;
+  P.aux = 0; P.aux_off = 0;
+  size_t smem = smem_bytes(P.BN, P.stages);
+  if (train) {
+    if (!P.tma_out || a->ln_stats != nullptr || a->stats_out != nullptr) return CSWIN_OK;       // caller reports "unsupported"
+    if (a->act == 2 && a->residual == nullptr) return CSWIN_OK;
+    if (a->aux_out != nullptr) {
+      if (!aligned16(a->aux_out) || (a->ld_aux * 2) % 16) return CSWIN_OK;
+      const uint64_t dims[2] = {(uint64_t)a->N, (uint64_t)a->M}, str[1] = {(uint64_t)a->ld_aux * 2};
+      const uint32_t box[2] = {32, 32};
+      if (!tc::make_tensor_map_bf16(&P.map_aux, a->aux_out, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B)) return CSWIN_ERR_CUDA;
+      P.aux = 1;
+      P.aux_off = (int)((smem - 1024 + 1023) / 1024 * 1024);   // second 16 KB staging area behind everything else (the main one
+      smem = 1024 + (size_t)P.aux_off + 8 * 2048;               // aliases the ring); 1 KB aligned: the swizzle is address-based
+    }
+  }
   using Kern = void (*)(const GemmTcParams);
-  static const Kern kerns[4] = {linear_tc_kernel<false, false>, linear_tc_kernel<true, false>, linear_tc_kernel<false, true>,
-                                linear_tc_kernel<true, true>};
+  static const Kern kerns[5] = {linear_tc_kernel<false, false>, linear_tc_kernel<true, false>, linear_tc_kernel<false, true>,
+                                linear_tc_kernel<true, true>, linear_tc_kernel<false, false, true>};
   static std::atomic<int> configured{0};
   if (!configured.load(std::memory_order_acquire)) {
     for (Kern k : kerns) CSWIN_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured.store(1, std::memory_order_release);
   }
   dim3 grid((unsigned)((a->M + BM - 1) / BM), (unsigned)((a->N + P.BN - 1) / P.BN));
-  const Kern kern = kerns[(a->ln_stats != nullptr ? 1 : 0) | (a->stats_out != nullptr ? 2 : 0)];
+  const Kern kern = train ? kerns[4] : kerns[(a->ln_stats != nullptr ? 1 : 0) | (a->stats_out != nullptr ? 2 : 0)];
   CSWIN_CUDA_OK(launch_pdl(kern, grid, dim3(kThreads), smem, stream, P));
   CSWIN_LAUNCH_CHECK();
   g_tc_launches.fetch_add(1, std::memory_order_relaxed);

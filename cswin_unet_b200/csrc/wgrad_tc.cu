@@ -9,6 +9,8 @@
 //   tile: UMMA M = 128 output rows (n), UMMA N = BN output columns (k, 64..256), contraction in 64-row blocks of m;
 //   the M range is split over gridDim.z CTAs (the output is tiny, the contraction long), each CTA accumulates its
 //   slice in TMEM and adds it to the fp32 gradient with red.global.add.f32.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -167,9 +169,13 @@ int linear_wgrad_tc(const void* dz, int64_t ldz, const void* a, int64_t lda, flo
   P.BN = P.nblk * 64;
   P.tmem_cols = P.BN <= 64 ? 64 : P.BN <= 128 ? 128 : 256;
   const int tiles = ((N + TN - 1) / TN) * ((K + P.BN - 1) / P.BN);
-  // split the contraction so that ~2 CTAs per SM exist, but keep the number of fp32 atomics per launch bounded
-  int64_t split = std::max<int64_t>(1, (2 * (int64_t)sm_count()) / tiles);
-  const int64_t max_by_atomics = std::max<int64_t>(1, (int64_t)(4 << 20) / ((int64_t)N * K));
+  // split the contraction so that ~1 CTA per SM exists (measured: profiles/r01_wgrad_split_sweep.log; 2 per SM costs 5 % more over
+  // the 16 block shapes because of the extra fp32 atomics), but keep the number of fp32 atomics per launch bounded
+  // CSWIN_WGRAD_CTAS_PER_SM / CSWIN_WGRAD_ATOMIC_CAP (elements of dW x split allowed per launch): tuning knobs
+  static const int ctas_per_sm = [] { const char* e = getenv("CSWIN_WGRAD_CTAS_PER_SM"); return e ? std::max(1, atoi(e)) : 1; }();
+  static const int64_t atomic_cap = [] { const char* e = getenv("CSWIN_WGRAD_ATOMIC_CAP"); return e ? std::max<int64_t>(1, atoll(e)) : (int64_t)(4 << 20); }();
+  int64_t split = std::max<int64_t>(1, ((int64_t)ctas_per_sm * sm_count()) / tiles);
+  const int64_t max_by_atomics = std::max<int64_t>(1, atomic_cap / ((int64_t)N * K));
   split = std::min(split, std::max<int64_t>(max_by_atomics, 1));
   split = std::min(split, ceil_div64(M, 2 * MB));
   if (split < 1) split = 1;

@@ -407,8 +407,8 @@ class CSWinBlock(_Native):
                                        a1.get_v.bias if a1 else None, meta)
         x1 = ag.linear(att, self.proj.weight, self.proj.bias, residual=xr, sample_scale=self._sample_scale(x), rps=L)
         u2, x1r = ag.LayerNormForkFn.apply(x1, self.norm2.weight, self.norm2.bias, self.norm2.eps)
-        hid = ag.GeluFn.apply(ag.linear(u2, self.mlp.fc1.weight, self.mlp.fc1.bias))
-        return ag.linear(hid, self.mlp.fc2.weight, self.mlp.fc2.bias, residual=x1r, sample_scale=self._sample_scale(x), rps=L)
+        return ag.mlp(u2, self.mlp.fc1.weight, self.mlp.fc1.bias, self.mlp.fc2.weight, self.mlp.fc2.bias, residual=x1r,
+                      sample_scale=self._sample_scale(x), rps=L)
 
 
 # ------------------------------------------------------------------------------------------

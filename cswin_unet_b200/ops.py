@@ -148,7 +148,7 @@ def linear(a: Tensor, w: Tensor, bias: Optional[Tensor] = None, *, a2: Optional[
            ln: Optional[Tuple[Tensor, Tensor, float]] = None, act: int = 0, residual: Optional[Tensor] = None,
            sample_scale: Optional[Tensor] = None, rows_per_sample: int = 0, out: Optional[Tensor] = None,
            n_out: Optional[int] = None, w_kn: bool = False, ln_fold=None, bias_f32: Optional[Tensor] = None,
-           want_stats: bool = False):
+           want_stats: bool = False, aux_out: Optional[Tensor] = None):
     """out = residual + sample_scale[row // rows_per_sample] * act(LN?([a | a2]) @ w[:n_out].T + bias).
 
     bf16 only: `ln_fold = (stats (M, parts, 2) fp32, colsum (N) fp32, eps)` applies LayerNorm algebraically in the
@@ -205,6 +205,10 @@ def linear(a: Tensor, w: Tensor, bias: Optional[Tensor] = None, *, a2: Optional[
         assert cs.dtype == torch.float32 and cs.numel() >= N and a2 is None
         args.ln_stats, args.ln_stats_parts, args.ln_C = st.data_ptr(), st.shape[1], K1
         args.ln_colsum, args.ln_eps = cs.data_ptr(), eps
+    if aux_out is not None:                               # training: act = 1 and the pre-activation goes here as well
+        x_, Mx, ldx = _rows(aux_out)
+        assert x_.data_ptr() == aux_out.data_ptr() and Mx == M and aux_out.shape[-1] == N and aux_out.dtype == a.dtype
+        args.aux_out, args.ld_aux = aux_out.data_ptr(), ldx
     stats = None
     if want_stats:
         parts = lib().cswin_linear_stats_parts(M, N, K1 + K2, act)
@@ -212,6 +216,12 @@ def linear(a: Tensor, w: Tensor, bias: Optional[Tensor] = None, *, a2: Optional[
         args.stats_out = stats.data_ptr()
     check(lib().cswin_linear_fwd(C.byref(args), _dtype_code(a), _stream()), "cswin_linear_fwd")
     return (out, stats) if want_stats else out
+
+
+def train_epilogues_supported(a: Tensor, n_out: int) -> bool:
+    """The training epilogues of cswin_linear_fwd (aux_out, act 2) need the tcgen05 fast path: bf16, 16-byte aligned rows."""
+    return (a.dtype == torch.bfloat16 and a.is_cuda and a.shape[-1] % 8 == 0 and n_out % 8 == 0 and a.stride(-1) == 1
+            and a.data_ptr() % 16 == 0)
 
 
 def mlp_supported(C_: int, hidden: int) -> bool:

@@ -132,7 +132,7 @@ typedef struct {
   const float* sample_scale; int32_t rows_per_sample;  /* DropPath m_b/(1-p), fp32 (M/rows_per_sample) or NULL */
   void* out; int64_t ldo;
   int64_t M; int32_t N;
-  int32_t act;
+  int32_t act;                                     /* 0 none, 1 GELU(erf), 2 see "training epilogues" below */
   int32_t w_layout;                                /* 0: w is (N, K) row-major (nn.Linear.weight);  1: w is (K, N) row-major, i.e.
                                                       out = a w — the data gradient dA = dZ W reads W in place, no transpose */
   /* --- LayerNorm folded into the Linear (bf16 / tcgen05 path only; all NULL / 0 by default) ---------------------------
@@ -146,6 +146,12 @@ typedef struct {
   const float* ln_colsum;
   const float* bias_f32;                           /* fp32 bias (used instead of `bias` when non-NULL) */
   float* stats_out;
+  /* --- training epilogues (bf16 / tcgen05 path with 16-byte aligned rows and N % 8 == 0; otherwise CSWIN_ERR_UNSUPPORTED) --
+   * aux_out: with act = 1 the pre-activation z = [a|a2] w^T + bias is ALSO written here ((M,N), row pitch ld_aux): fc1 of
+   *          the Mlp keeps z for the backward and hands GELU(z) to fc2 without a separate activation pass (Mlp :22-23).
+   * act = 2: out = (a w) * GELU'(residual): the data gradient of fc2 multiplied by GELU'(z) in the epilogue
+   *          (`residual` carries z; it is not added). */
+  void* aux_out; int64_t ld_aux;
 } cswin_linear_args_t;
 
 int cswin_linear_fwd(const cswin_linear_args_t* args, int32_t dtype, cswin_stream_t stream);

@@ -292,3 +292,37 @@ def test_native_seg_loss_matches_oracle(nc, ldt):
     (got * 1.7).backward()
     assert abs(float(got) - float(ref)) <= 2e-6 * max(1.0, abs(float(ref)))
     assert rel(ln.grad, lo.grad) <= 2e-5
+
+
+@pytest.mark.parametrize("M,K,N", [(4704, 256, 1024), (1176, 512, 2048), (300, 64, 256), (18816, 128, 512)])
+def test_linear_training_epilogues_match_the_composed_kernels(M, K, N):
+    """cswin_linear_fwd training epilogues (tcgen05 path): aux_out = pre-activation next to GELU(z) (Mlp fc1, cswin_unet.py:22-23),
+    act 2 = data gradient x GELU'(z).  Checked against the separate kernels they replace and against fp64 math."""
+    from cswin_unet_b200 import ops
+    g = torch.Generator().manual_seed(M + N)
+    u = torch.randn(M, K, generator=g).bfloat16().to(DEV)
+    w1 = (torch.randn(N, K, generator=g) * K ** -0.5).bfloat16().to(DEV)
+    b1 = (torch.randn(N, generator=g) * 0.1).bfloat16().to(DEV)
+    z_ref = ops.linear(u, w1, b1)
+    h_ref = ops.act_fwd(z_ref, act=1)
+    z = torch.empty_like(z_ref)
+    t0 = cw.tc_launch_count()
+    h = ops.linear(u, w1, b1, act=1, aux_out=z)
+    assert cw.tc_launch_count() == t0 + 1
+    assert torch.equal(z, z_ref), "aux_out must be bit-identical to the plain Linear"
+    z64 = u.double() @ w1.double().T + b1.double()
+    h64 = torch.nn.functional.gelu(z64)
+    assert (h.double() - h64).abs().max().item() <= 2e-2 and rel(h, h64) <= 6e-3
+    assert rel(h, h_ref.double()) <= 6e-3
+    # backward epilogue: dz = (dh_src @ w2) * GELU'(z)
+    C2 = K
+    dz2 = torch.randn(M, C2, generator=g).bfloat16().to(DEV)
+    w2 = (torch.randn(C2, N, generator=g) * N ** -0.5).bfloat16().to(DEV)          # fc2.weight (C, hidden), read in place as (K', N')
+    dh = ops.linear(dz2, w2, w_kn=True)
+    dz_ref = ops.act_bwd(dh, z, None, 0, act=1)
+    dz = ops.linear(dz2, w2, w_kn=True, act=2, residual=z)
+    x = z.double()
+    gp = 0.5 * (1 + torch.erf(x / 2 ** 0.5)) + x * torch.exp(-0.5 * x * x) / (2 * np.pi) ** 0.5
+    dz64 = (dz2.double() @ w2.double()) * gp
+    assert rel(dz, dz64) <= 6e-3, rel(dz, dz64)
+    assert rel(dz, dz_ref.double()) <= 8e-3, rel(dz, dz_ref.double())
