@@ -23,6 +23,11 @@
 //      same V tile in smem (zero padding at the WINDOW border), then adds it to O / rowsum and stores 32 B
 //      straight into the (B, L, C) concat layout (windows2img + cat are address arithmetic).
 // HBM traffic = q, k, v read once + out written once; the N x N scores never leave TMEM.
+//
+// Wide variant (kWide, windows of 128 < N <= 256 tokens — the 512^2 configuration's 32x8 / 8x32 / 16x16 stripes): a
+// (window, head) problem is two tiles of 128 query rows, each against all N keys: K / V tiles of 256 rows, S = 128 x 256
+// fp32 in TMEM columns [0,256), P (bf16) back into columns [0,128), O into columns [128,160) (S is dead by then); each of
+// the two threads of a row owns 128 key columns.  Needs 128 % W_sp == 0 so that a query tile is a rectangular TMA box.
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -51,6 +56,7 @@ constexpr int kOperandBytes = kTileRows * kRowBytes;  // 8 KB
 constexpr uint32_t kTmemCols = 128;
 //                         Q,K,V               Wt[2][9][32]     Bc[2][32]    xchg[2][128]   barriers   align slack
 constexpr int kSmemBytes = 3 * kOperandBytes + 2 * 9 * 32 * 4 + 2 * 32 * 4 + 2 * 128 * 4 + 64 + 1024;
+constexpr int kSmemBytesWide = 5 * kOperandBytes + 2 * 9 * 32 * 4 + 2 * 32 * 4 + 2 * 128 * 4 + 64 + 1024;   // K, V: 256 rows
 
 __device__ __forceinline__ uint32_t v_chunk_addr(uint32_t vbase, int row, int chunk) {
   return vbase + row * kRowBytes + (((chunk ^ (row >> 1)) & 3) << 4);          // Swizzle<2,4,3> (64-byte swizzle)
@@ -61,14 +67,19 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
-__global__ void __launch_bounds__(kThreads, 3) lepe_attn_fwd_tc_kernel(const __grid_constant__ TcParams P) {
+template <bool kWide>
+__global__ void __launch_bounds__(kThreads, kWide ? 2 : 3) lepe_attn_fwd_tc_kernel(const __grid_constant__ TcParams P) {
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment by pointer arithmetic on the shared array: keeps the shared address space (LDS / STS, not generic LD / ST)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  constexpr int kKvBytes = kWide ? 2 * kOperandBytes : kOperandBytes;   // K / V tile: 256 or 128 rows
+  constexpr int kKvRows = kWide ? 256 : 128;
+  constexpr int kCh = kWide ? 4 : 2;                                    // 32-column chunks of S per thread
+  constexpr uint32_t kOCol = kWide ? 128 : 64;                          // TMEM column of the O accumulator
   uint8_t* Qs = smem;
   uint8_t* Ks = smem + kOperandBytes;
-  uint8_t* Vs = smem + 2 * kOperandBytes;
-  float* Wt = reinterpret_cast<float*>(smem + 3 * kOperandBytes);     // [2][9][32]
+  uint8_t* Vs = Ks + kKvBytes;
+  float* Wt = reinterpret_cast<float*>(Vs + kKvBytes);                 // [2][9][32]
   float* Bc = Wt + 2 * 9 * 32;                                        // [2][32]
   float* Xmax = Bc + 2 * 32;                                          // [2 halves][128 rows]
   float* Xsum = Xmax;                                                 // reused after the max exchange
@@ -84,14 +95,15 @@ __global__ void __launch_bounds__(kThreads, 3) lepe_attn_fwd_tc_kernel(const __g
   const TcBranch& br = P.br[bi];
   const int tile = blockIdx.x - br.tile_begin;
   const int N = br.N, hs = br.hs, ws = br.ws;
-  const int slots = (N <= 64) ? 2 : 1;
+  const int slots = (!kWide && N <= 64) ? 2 : 1;
   const int slot_rows = kTileRows / slots;
-  const int p0 = tile * slots;
+  const int qt = kWide ? (tile & 1) : 0;                             // wide: which 128-row query tile of the problem
+  const int p0 = kWide ? (tile >> 1) : tile * slots;
   const int np = min(slots, br.nprob - p0);
   const int kext = (slots == 2) ? 128 : ((N + 15) & ~15);            // kv extent fed to the P.V MMA
 
   const int slot = row / slot_rows;            // warp-uniform
-  const int n = row - slot * slot_rows;        // token index inside the window
+  const int n = row - slot * slot_rows + qt * kTileRows;             // token index inside the window
 
   // (batch, window, head) of my slot, and of both slots for the TMA-issuing thread
   int mb, mih, miw, mhead;
@@ -104,13 +116,13 @@ __global__ void __launch_bounds__(kThreads, 3) lepe_attn_fwd_tc_kernel(const __g
   }
 
   const uint32_t bar_tma = smem_u32(&bars[0]), bar_s = smem_u32(&bars[1]), bar_o = smem_u32(&bars[2]);
-  if (warp == 0) { tmem_alloc(smem_u32(tmem_slot), kTmemCols); tmem_relinquish(); }
+  if (warp == 0) { tmem_alloc(smem_u32(tmem_slot), kWide ? 256u : kTmemCols); tmem_relinquish(); }
   if (tid == 32) { mbar_init(bar_tma, 1); mbar_init(bar_s, 1); mbar_init(bar_o, 1); fence_barrier_init(); }
 
   // zero the V rows the P.V MMA reads but TMA does not write (0 * stale-NaN would poison O)
-  for (int i = tid; i < kTileRows * 4; i += kThreads) {
+  for (int i = tid; i < kKvRows * 4; i += kThreads) {
     const int r = i >> 2;
-    const int s = r / slot_rows, rn = r - s * slot_rows;
+    const int s = kWide ? 0 : r / slot_rows, rn = r - s * slot_rows;
     if (r < kext && (s >= np || rn >= N)) *reinterpret_cast<uint4*>(Vs + i * 16) = make_uint4(0, 0, 0, 0);
   }
   // stage the LePE weights of the head(s) of this tile: 288 contiguous bf16 per head -> Wt[slot][tap][ch] fp32
@@ -140,8 +152,18 @@ __global__ void __launch_bounds__(kThreads, 3) lepe_attn_fwd_tc_kernel(const __g
   pdl_wait();                                                // q, k, v (previous kernel's output) and `out` are safe from here
 
   if (warp == 0 && elect_one()) {     // one elected lane, warp-uniform datapath for the TMA / tcgen05 issue
-    mbar_expect_tx(bar_tma, (uint32_t)(np * 3 * N * kRowBytes));
-    for (int s = 0; s < np; ++s) {
+    mbar_expect_tx(bar_tma, kWide ? (uint32_t)((2 * N + kTileRows) * kRowBytes) : (uint32_t)(np * 3 * N * kRowBytes));
+    if (kWide) {                      // q: rows [128 qt, +128) of the window (a box of 128 / W_sp window rows); k, v: the window
+      int local = p0;
+      const int hd = local % br.heads; local /= br.heads;
+      const int win = local % br.nwin;
+      const int b = local / br.nwin;
+      const int ih = win / br.nww, iw = win - ih * br.nww;
+      tma_load_4d(smem_u32(Qs), &P.map[bi][0], bar_tma, hd * 32, iw * ws, ih * hs + qt * (kTileRows / ws), b);
+      tma_load_4d(smem_u32(Ks), &P.map[bi][1], bar_tma, hd * 32, iw * ws, ih * hs, b);
+      tma_load_4d(smem_u32(Vs), &P.map[bi][2], bar_tma, hd * 32, iw * ws, ih * hs, b);
+    }
+    for (int s = 0; s < (kWide ? 0 : np); ++s) {
       int local = p0 + s;
       const int hd = local % br.heads; local /= br.heads;
       const int win = local % br.nwin;
@@ -169,10 +191,10 @@ __global__ void __launch_bounds__(kThreads, 3) lepe_attn_fwd_tc_kernel(const __g
 
   // ---- softmax: this thread owns columns [cbeg, cbeg + hcols) of S row `row` (slot-local key index kbeg..) ----
   const uint32_t trow = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-  const int hcols = slot_rows >> 1;                          // 32 (two problems) or 64 (one problem)
+  const int hcols = kWide ? 128 : (slot_rows >> 1);          // 32 (two problems), 64 (one problem) or 128 (wide)
   const int kbeg = half * hcols;                             // first slot-local key of my half
   const int cbeg = slot * slot_rows + kbeg;                  // first S column of my half
-  const int nch = hcols >> 5;                                // chunks of 32 columns: 1 or 2
+  const int nch = hcols >> 5;                                // chunks of 32 columns: 1, 2 or 4
   float mx = -INFINITY;
   for (int c = 0; c < nch; ++c) {
     if (kbeg + 32 * c >= kext) break;                        // (one-problem mode) chunk entirely beyond the keys
@@ -195,9 +217,9 @@ __global__ void __launch_bounds__(kThreads, 3) lepe_attn_fwd_tc_kernel(const __g
   float sum = 0.f;
   float2 sum2 = make_float2(0.f, 0.f);
   const float2 sl2 = make_float2(P.scale_log2e, P.scale_log2e), nmxs2 = make_float2(-mxs, -mxs);
-  uint32_t pk[2][16];                                        // bf16 P of my columns, held until every S read is done
+  uint32_t pk[kCh][16];                                      // bf16 P of my columns, held until every S read is done
 #pragma unroll
-  for (int c = 0; c < 2; ++c) {
+  for (int c = 0; c < kCh; ++c) {
     if (c < nch && kbeg + 32 * c < kext) {
       uint32_t v[32];
       tmem_ld32(trow + cbeg + 32 * c, v);
@@ -226,7 +248,7 @@ __global__ void __launch_bounds__(kThreads, 3) lepe_attn_fwd_tc_kernel(const __g
   // publish only after every thread has its S values in registers.
   __syncthreads();
 #pragma unroll
-  for (int c = 0; c < 2; ++c)
+  for (int c = 0; c < kCh; ++c)
     if (c < nch && kbeg + 32 * c < kext) tmem_st16(trow + ((cbeg + 32 * c) >> 1), pk[c]);
   if (slots == 2) {                                          // keys of the other problem: P = 0 (16 of its 32 cols each)
     uint32_t z[16];
@@ -246,7 +268,7 @@ __global__ void __launch_bounds__(kThreads, 3) lepe_attn_fwd_tc_kernel(const __g
     const uint64_t vd = make_smem_desc(smem_u32(Vs), 8 * kRowBytes, 8 * kRowBytes, kLayoutSw64);
     const uint32_t idesc = make_idesc_bf16(128, 32, 0, 1);   // B = V is MN-major
     for (int k = 0; k < kext / 16; ++k)
-      mma_ts(tmem_base + 64, tmem_base + 8 * k, vd + (uint64_t)k * ((16 * kRowBytes) >> 4), idesc, k > 0);
+      mma_ts(tmem_base + kOCol, tmem_base + 8 * k, vd + (uint64_t)k * ((16 * kRowBytes) >> 4), idesc, k > 0);
     tc_commit(bar_o);
   }
   sum += Xsum[(half ^ 1) * 128 + row];
@@ -295,7 +317,7 @@ __global__ void __launch_bounds__(kThreads, 3) lepe_attn_fwd_tc_kernel(const __g
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
         : "=r"(o[0]), "=r"(o[1]), "=r"(o[2]), "=r"(o[3]), "=r"(o[4]), "=r"(o[5]), "=r"(o[6]), "=r"(o[7]), "=r"(o[8]),
           "=r"(o[9]), "=r"(o[10]), "=r"(o[11]), "=r"(o[12]), "=r"(o[13]), "=r"(o[14]), "=r"(o[15])
-        : "r"(trow + 64 + half * 16) : "memory");
+        : "r"(trow + kOCol + half * 16) : "memory");
     tmem_wait_ld();
     if (valid) {
       const float inv = 1.0f / sum;
@@ -316,7 +338,7 @@ __global__ void __launch_bounds__(kThreads, 3) lepe_attn_fwd_tc_kernel(const __g
   tc_fence_before();
   __syncthreads();
   if (tid == 0) trace_stamp(P.trace, 7);                     // exit
-  if (warp == 0) tmem_dealloc(tmem_base, kTmemCols);
+  if (warp == 0) tmem_dealloc(tmem_base, kWide ? 256u : kTmemCols);
 }
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
@@ -326,18 +348,23 @@ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 
 int lepe_attention_fwd_tc(const cswin_lepe_branch_t* brs, int nb, int B, int reso, float scale, cudaStream_t stream,
                           bool* handled) {
   *handled = false;
-  // eligibility: head_dim 32, window <= 128 tokens, TMA-compatible strides / alignment; otherwise the SIMT kernel runs
+  // eligibility: head_dim 32, window <= 128 tokens (or <= 256 with 128 % W_sp == 0: wide variant), TMA-compatible strides /
+  // alignment; otherwise the SIMT kernel runs
+  int n_wide = 0;
   for (int i = 0; i < nb; ++i) {
     const cswin_lepe_branch_t& s = brs[i];
     if (!s.q || !s.k || !s.v || !s.out || !s.conv_w || !s.conv_b) return CSWIN_OK;     // SIMT path reports the error
     if (s.heads <= 0 || s.C_b != s.heads * 32) return CSWIN_OK;
     if (s.H_sp <= 0 || s.W_sp <= 0 || reso % s.H_sp || reso % s.W_sp) return CSWIN_OK;
-    if (s.H_sp * s.W_sp > 128 || s.H_sp > 256 || s.W_sp > 256) return CSWIN_OK;
+    if (s.H_sp * s.W_sp > 256 || s.H_sp > 256 || s.W_sp > 256) return CSWIN_OK;
+    if (s.H_sp * s.W_sp > 128) { if (128 % s.W_sp) return CSWIN_OK; ++n_wide; }
     const int64_t strides[] = {s.q_bs, s.q_ts, s.k_bs, s.k_ts, s.v_bs, s.v_ts, s.o_bs, s.o_ts};
     for (int64_t st : strides) if (st <= 0 || (st * 2) % 16 != 0) return CSWIN_OK;
     if (!aligned16(s.q) || !aligned16(s.k) || !aligned16(s.v) || !aligned16(s.out) || !aligned16(s.conv_w)) return CSWIN_OK;
   }
   if (tc::encode_tiled_fn() == nullptr) return CSWIN_OK;
+  if (n_wide != 0 && n_wide != nb) return CSWIN_OK;                  // one launch = one kernel variant
+  const bool wide = n_wide != 0;
 
   TcParams P;
   P.nb = nb; P.reso = reso; P.scale = scale; P.scale_log2e = scale * 1.4426950408889634f;
@@ -353,19 +380,20 @@ int lepe_attention_fwd_tc(const cswin_lepe_branch_t* brs, int nb, int B, int res
     d.nprob = B * d.nwin * d.heads;
     d.tile_begin = tiles;
     const int slots = d.N <= 64 ? 2 : 1;
-    tiles += (d.nprob + slots - 1) / slots;
+    tiles += wide ? 2 * d.nprob : (d.nprob + slots - 1) / slots;
     const void* ptr[3] = {s.q, s.k, s.v};
     const int64_t bs[3] = {s.q_bs, s.k_bs, s.v_bs}, ts[3] = {s.q_ts, s.k_ts, s.v_ts};
     for (int j = 0; j < 3; ++j) {
       const uint64_t dims[4] = {(uint64_t)s.C_b, (uint64_t)reso, (uint64_t)reso, (uint64_t)B};
       const uint64_t str[3] = {(uint64_t)ts[j] * 2, (uint64_t)ts[j] * 2 * reso, (uint64_t)bs[j] * 2};
-      const uint32_t box[4] = {32, (uint32_t)s.W_sp, (uint32_t)s.H_sp, 1};
+      const uint32_t box[4] = {32, (uint32_t)s.W_sp, (uint32_t)((wide && j == 0) ? 128 / s.W_sp : s.H_sp), 1};   // wide q: one 128-row tile
       if (!tc::make_tensor_map_bf16(&P.map[i][j], ptr[j], 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B)) return CSWIN_ERR_CUDA;
     }
   }
   if (nb == 1) P.br[1] = P.br[0];
-  static_assert(kSmemBytes <= 48 * 1024, "dynamic smem must stay under the no-opt-in limit");
-  CSWIN_CUDA_OK(launch_pdl(lepe_attn_fwd_tc_kernel, dim3(tiles), dim3(kThreads), (size_t)kSmemBytes, stream, P));
+  static_assert(kSmemBytes <= 48 * 1024 && kSmemBytesWide <= 48 * 1024, "dynamic smem must stay under the no-opt-in limit");
+  if (wide) CSWIN_CUDA_OK(launch_pdl(lepe_attn_fwd_tc_kernel<true>, dim3(tiles), dim3(kThreads), (size_t)kSmemBytesWide, stream, P));
+  else CSWIN_CUDA_OK(launch_pdl(lepe_attn_fwd_tc_kernel<false>, dim3(tiles), dim3(kThreads), (size_t)kSmemBytes, stream, P));
   CSWIN_LAUNCH_CHECK();
   g_tc_launches.fetch_add(1, std::memory_order_relaxed);
   *handled = true;

@@ -77,6 +77,29 @@ def test_lepe_attention_bf16_vs_oracle(tag, cfgs, B):
         assert err <= 3e-2, f"{(cb, reso, idx, split, heads)}: bf16 max-abs {err:.3e}"
 
 
+LEPE_WIDE = ((128, 32, 0, 8, 4), (128, 32, 1, 8, 4), (512, 16, -1, 8, 16), (64, 24, 0, 8, 2), (32, 16, 0, 16, 1), (32, 48, 0, 4, 1))
+
+
+@pytest.mark.parametrize("B", [1, 3])
+def test_lepe_attention_bf16_wide_windows_on_tcgen05(B):
+    """BASELINE configs[4] (512^2, split [1,2,8,8]): stripe windows of 256 tokens (32x8, 8x32, 16x16) — and ragged ones of 192
+    (24x8, 48x4: the second query tile is half empty) — run on the wide variant of the tcgen05 kernel (two 128-row query
+    tiles per (window, head), S = 128 x 256 in TMEM).  Checked against the fp64 oracle on the bf16-rounded inputs."""
+    for (cb, reso, idx, split, heads) in LEPE_WIDE:
+        m, qkv = lepe_case(cb, reso, idx, split, heads, B, torch.bfloat16)
+        assert 128 < m.H_sp * m.W_sp <= 256 and 128 % m.W_sp == 0
+        t0 = cw.tc_launch_count()
+        with torch.no_grad():
+            y = m(qkv).float().cpu()
+        assert cw.tc_launch_count() == t0 + 1, f"{(cb, reso, idx, split, heads)}: wide windows must run on the tcgen05 kernel"
+        q, k, v = (qkv[i].float().cpu().double() for i in range(3))
+        w = m.get_v.weight.detach().bfloat16().double().cpu()
+        b = m.get_v.bias.detach().bfloat16().double().cpu()
+        ref = O.lepe_attention(q, k, v, w, b, reso, idx, split, heads)
+        err = (y.double() - ref).abs().max().item()
+        assert err <= 3e-2, f"{(cb, reso, idx, split, heads)} B={B}: bf16 max-abs {err:.3e}"
+
+
 def test_lepe_attention_batch24_matches_oracle_fp32():
     """BASELINE config 2 at the bench batch size: both branches of a stage-2 block in ONE launch."""
     B, reso, C, heads, split = 24, 28, 128, 4, 2
@@ -399,8 +422,8 @@ def test_linear_kn_weight_layout(dtype, tol, M, N, K):
 
 
 def test_512px_config_blocks_fp32_and_bf16_vs_oracle():
-    """BASELINE configs[4]: 512^2 input with split [1,2,8,8] -> stripe windows of 128 / 128 / 256 / 256 tokens.  Windows of
-    256 tokens are outside the tcgen05 attention envelope (N <= 128) and must still be exact on the general SIMT kernel."""
+    """BASELINE configs[4]: 512^2 input with split [1,2,8,8] -> stripe windows of 128 / 128 / 256 / 256 tokens.  fp32 runs on
+    the general SIMT kernel (exact); bf16 runs on the tcgen05 kernel (its wide variant for the 256-token windows)."""
     for (dim, reso, heads, split, last) in ((64, 128, 2, 1, False), (256, 32, 8, 8, False), (512, 16, 16, 8, True)):
         m = cw.CSWinBlock(dim=dim, reso=reso, num_heads=heads, split_size=split, qkv_bias=True, last_stage=last).to(DEV).eval()
         load_named(m, f"block512/{dim}/", 3)
