@@ -62,7 +62,8 @@ int cswin_lepe_attention_fwd(const cswin_lepe_branch_t* branches, int32_t n_bran
   CSWIN_REQUIRE(branches && (n_branches == 1 || n_branches == 2), CSWIN_ERR_INVALID, "lepe_attention_fwd: n_branches must be 1 or 2");
   CSWIN_REQUIRE(B >= 0 && reso > 0, CSWIN_ERR_INVALID, "lepe_attention_fwd: bad B=%d reso=%d", B, reso);
   if (B == 0) return CSWIN_OK;
-  if (dtype == CSWIN_BF16) {
+  static const bool fwd_simt = [] { const char* e = getenv("CSWIN_ATTN_FWD_SIMT"); return e && e[0] == '1'; }();   // A/B debugging aid
+  if (dtype == CSWIN_BF16 && !fwd_simt) {
     bool handled = false;
     int rc = lepe_attention_fwd_tc(branches, n_branches, B, reso, scale, (cudaStream_t)stream, &handled);
     if (rc != CSWIN_OK || handled) return rc;

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Tiny driver for `ncu --set full`: runs a few launches of one op at one shape.
-usage: ncu_target.py attn <stage 1-4> <B> | block_infer <stage> <B> | block_train <stage> <B> | linear <M> <N> <K> [act] [res]"""
+usage: ncu_target.py attn <stage 1-4> <B> | attn512 <stage 1-4> <B> | block_infer <stage> <B> | block_train <stage> <B> | linear <M> <N> <K> [act] [res]"""
 import os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -9,9 +9,11 @@ from cswin_unet_b200 import ops
 
 DEV = "cuda"
 kind = sys.argv[1]
-if kind == "attn":
+if kind in ("attn", "attn512"):
     stage, B = int(sys.argv[2]), int(sys.argv[3])
-    C, reso, heads, split, last = [(64, 56, 2, 1, False), (128, 28, 4, 2, False), (256, 14, 8, 7, False), (512, 7, 16, 7, True)][stage - 1]
+    T224 = [(64, 56, 2, 1, False), (128, 28, 4, 2, False), (256, 14, 8, 7, False), (512, 7, 16, 7, True)]
+    T512 = [(64, 128, 2, 1, False), (128, 64, 4, 2, False), (256, 32, 8, 8, False), (512, 16, 16, 8, True)]      # split [1,2,8,8]
+    C, reso, heads, split, last = (T224 if kind == "attn" else T512)[stage - 1]
     blk = cw.CSWinBlock(dim=C, reso=reso, num_heads=heads, split_size=split, qkv_bias=True, last_stage=last).to(DEV).eval()
     L = reso * reso
     qkv = torch.randn(B, L, 3 * C, device=DEV, dtype=torch.bfloat16)
