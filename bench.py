@@ -369,35 +369,54 @@ def run_native(args):
     # ---- train step (BASELINE configs[2]): forward + native backward + gradient all-reduce (NCCL, N > 1) + SGD, bf16
     #      compute with fp32 master weights, batch 24 per GPU, drop_path 0.2 active.  Reported next to the headline. ----
     if not args.no_train:
-        import copy
-        tmodel = copy.deepcopy(model).train()
-        step_fn = cw.TrainStep(tmodel, lr=0.05, compute_dtype=torch.bfloat16)
-        timg = pool[0]
-        tlab = torch.from_numpy(synth.synth_labels(B, 224, 9, seed=rank)).to(dev)
-        tw, tk = 5, max(5, min(args.steps, 20))                     # warm-up: 3 eager steps + graph capture + 1 replay
-        for _ in range(tw):
-            step_fn(timg, tlab)
-        barrier()
-        n_tr0 = cw.launch_count()
-        e0.record()
-        for i in range(tk):
-            step_fn(pool[i % n_rot], tlab)
-        e1.record()
-        barrier()
-        ms_tr = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms_tr], device=dev)
-            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-            ms_tr = float(t.item())
-        line["train_step"] = {"value": world * tk * B / (ms_tr * 1e-3), "unit": UNIT, "ms_per_step": ms_tr / tk, "steps": tk,
-                              "warmup": tw, "batch_per_gpu": B, "dtype": "bf16 compute, fp32 master weights + gradients",
-                              "gpu_launches": int(step_fn.native_launches_per_step * tk + (cw.launch_count() - n_tr0)),
-                              "what": "forward + native backward + native loss (0.4 CE + 0.6 Dice) + NCCL gradient all-reduce overlapped with the "
-                                      "backward on the pooled gradient buffer (N>1) + native fused SGD(momentum .9, wd 1e-4); whole step "
-                                      "(collectives included) replayed as one CUDA graph",
-                              "roofline_frac_tensor": world and (tk * B / (ms_tr * 1e-3)) * 33.231 / 1e3 / (pk["bf16_tflops_sustained"] or pk["bf16_tflops"])}
-        step_fn.close()
-        del tmodel, step_fn
+        # The train leg must never cost the headline: a failure is reported inside `train_step`, and a stall (e.g. a wedged
+        # collective on one rank) is cut by a watchdog that still prints the line — every rank arms its own.
+        fired = threading.Event()
+
+        def train_watchdog():
+            if not fired.wait(args.train_timeout):
+                line["train_step"] = {"error": f"train leg exceeded {args.train_timeout:.0f} s and was abandoned"}
+                if rank == 0:
+                    emit(line)
+                sys.stderr.flush()
+                os._exit(0)
+        threading.Thread(target=train_watchdog, daemon=True).start()
+        try:
+            import copy
+            tmodel = copy.deepcopy(model).train()
+            step_fn = cw.TrainStep(tmodel, lr=0.05, compute_dtype=torch.bfloat16)
+            timg = pool[0]
+            tlab = torch.from_numpy(synth.synth_labels(B, 224, 9, seed=rank)).to(dev)
+            tw, tk = 5, max(5, min(args.steps, 20))                     # warm-up: 3 eager steps + graph capture + 1 replay
+            for _ in range(tw):
+                step_fn(timg, tlab)
+            barrier()
+            n_tr0 = cw.launch_count()
+            e0.record()
+            for i in range(tk):
+                step_fn(pool[i % n_rot], tlab)
+            e1.record()
+            barrier()
+            ms_tr = e0.elapsed_time(e1)
+            if world > 1:
+                t = torch.tensor([ms_tr], device=dev)
+                torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+                ms_tr = float(t.item())
+            line["train_step"] = {"value": world * tk * B / (ms_tr * 1e-3), "unit": UNIT, "ms_per_step": ms_tr / tk, "steps": tk,
+                                  "warmup": tw, "batch_per_gpu": B, "dtype": "bf16 compute, fp32 master weights + gradients",
+                                  "gpu_launches": int(step_fn.native_launches_per_step * tk + (cw.launch_count() - n_tr0)),
+                                  "what": "forward + native backward + native loss (0.4 CE + 0.6 Dice) + NCCL gradient all-reduce overlapped with the "
+                                          "backward on the pooled gradient buffer (N>1) + native fused SGD(momentum .9, wd 1e-4); whole step "
+                                          "(collectives included) replayed as one CUDA graph",
+                                  "roofline_frac_tensor": world and (tk * B / (ms_tr * 1e-3)) * 33.231 / 1e3 / (pk["bf16_tflops_sustained"] or pk["bf16_tflops"])}
+            step_fn.close()
+            del tmodel, step_fn
+        except Exception as e:                                  # noqa: BLE001 — reported, not swallowed
+            import traceback
+            traceback.print_exc()
+            line["train_step"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+        finally:
+            fired.set()
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, cores, n, dt = cpu_forward_rate(args.cpu_budget, BATCH)
@@ -447,6 +466,7 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU-oracle work for cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the train-step leg")
+    ap.add_argument("--train-timeout", type=float, default=240.0, help="seconds before a stalled train-step leg is abandoned")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
     if args.impl == "reference":

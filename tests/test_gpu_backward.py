@@ -326,3 +326,36 @@ def test_linear_training_epilogues_match_the_composed_kernels(M, K, N):
     dz64 = (dz2.double() @ w2.double()) * gp
     assert rel(dz, dz64) <= 6e-3, rel(dz, dz64)
     assert rel(dz, dz_ref.double()) <= 8e-3, rel(dz, dz_ref.double())
+
+
+LEPE_WIDE_BWD = ((128, 32, 0, 8, 4), (128, 32, 1, 8, 4), (512, 16, -1, 8, 16), (64, 24, 0, 8, 2))
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-5), (torch.bfloat16, 2e-2)])
+def test_lepe_attention_backward_wide_windows_vs_fp64(dtype, tol):
+    """BASELINE configs[4] (512^2): 256- and 192-token stripe windows.  Forward on the wide tcgen05 kernel (bf16), backward of
+    q / k / v on the general kernel with the get_v parameter gradients from cswin_lepe_param_grad on the second stream
+    (dconv_w = NULL in the backward call) — compared with autograd through the fp64 oracle."""
+    B = 2
+    for (cb, reso, idx, split, heads) in LEPE_WIDE_BWD:
+        full_c = cb if idx == -1 else 2 * cb
+        base64 = torch.from_numpy(synth.synth_qkv(B, reso, full_c, seed=0)).to(dtype).double()
+        off = cb if idx == 1 else 0
+        w64 = torch.from_numpy(synth.synth_tensor(f"lepe/{cb}/{reso}/{idx}/get_v.weight", (cb, 1, 3, 3), 1)).to(dtype).double()
+        b64 = torch.from_numpy(synth.synth_tensor(f"lepe/{cb}/{reso}/{idx}/get_v.bias", (cb,), 1)).to(dtype).double()
+        key = f"c{cb}_r{reso}_i{idx}_s{split}_h{heads}"
+        gup64 = torch.from_numpy(synth.synth_tensor(f"lepe_grad/{key}", (B, reso * reso, cb), 2)).to(dtype).double()
+        leaves = [t.clone().requires_grad_(True) for t in (base64, w64, b64)]
+        v = leaves[0].permute(2, 0, 1, 3)[..., off:off + cb]
+        yo = O.lepe_attention(v[0], v[1], v[2], leaves[1], leaves[2], reso, idx, split, heads)
+        ref = torch.autograd.grad(yo, leaves, gup64)
+        base = base64.to(DEV).to(dtype).requires_grad_(True)
+        m = cw.LePEAttention(cb, resolution=reso, idx=idx, split_size=split, num_heads=heads).to(DEV)
+        with torch.no_grad():
+            m.get_v.weight.copy_(w64.float()); m.get_v.bias.copy_(b64.float())
+        y = m(base.permute(2, 0, 1, 3)[..., off:off + cb])
+        assert rel(y, yo) <= tol, (key, "forward", rel(y, yo))
+        gb, gw, gbias = torch.autograd.grad(y, [base, m.get_v.weight, m.get_v.bias], gup64.to(DEV).to(dtype))
+        sl = (Ellipsis, slice(off, off + cb))
+        assert rel(gb[sl], ref[0][sl]) <= tol, (key, "dqkv", rel(gb[sl], ref[0][sl]))
+        assert rel(gw, ref[1]) <= tol and rel(gbias, ref[2]) <= tol, (key, rel(gw, ref[1]), rel(gbias, ref[2]))
