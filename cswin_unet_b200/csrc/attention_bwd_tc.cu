@@ -333,6 +333,270 @@ __global__ void __launch_bounds__(kThr, 2) lepe_attn_bwd_tc_kernel(const __grid_
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// Wide variant: windows of 128 < N <= 256 tokens (the 512^2 configuration's 32x8 / 8x32 / 16x16 stripes, 14x14 windows ...).
+// One CTA per (window, head) problem (persistent over problems), 1 CTA per SM: Q, K, V, G of the whole window in shared memory
+// (4 x 16 KB, one TMA box each), processed as 2 query tiles x 2 key halves of 128 x 128:
+//   pass A (per query tile): S = Q K^T and dP = G V^T per key half into TMEM columns [0,128) / [128,256), the row's
+//           delta = sum_j P_ij dP_ij accumulated over both halves (the row's lse comes from the forward);
+//   pass B: S, dP again per key half, P / dS (bf16, 128-byte swizzle) into shared memory, then
+//           dV[half] += P^T G_tile, dK[half] += dS^T Q_tile (accumulated over the two query tiles in TMEM columns
+//           [352,416) / [288,352)), dQ_tile += dS K_half (columns [256,288), stored after the second half).
+// S and dP are recomputed instead of kept: at 128 x 256 fp32 each they would fill all 512 TMEM columns on their own.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kWOpB = 256 * kRowB;                  // 16 KB per [256][32] bf16 operand
+constexpr int kSmemWideBwd = 4 * kWOpB + 2 * kPB + 9 * 32 * 4 + 2 * 128 * 4 + 64 + 1024;
+constexpr uint32_t kColDQ = 256, kColDK = 288, kColDV = 352;
+
+__global__ void __launch_bounds__(kThr, 1) lepe_attn_bwd_wide_tc_kernel(const __grid_constant__ BwdParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* Qs = smem;
+  uint8_t* Ks = Qs + kWOpB;
+  uint8_t* Vs = Ks + kWOpB;
+  uint8_t* Gs = Vs + kWOpB;
+  uint8_t* Ps = Gs + kWOpB;                 // [2 column blocks][128 rows][128 B]
+  uint8_t* Ds = Ps + kPB;
+  float* Wt = reinterpret_cast<float*>(Ds + kPB);       // [9][32]
+  float* Xd = Wt + 9 * 32;                              // [2][128]      delta exchange
+  uint64_t* bars = reinterpret_cast<uint64_t*>(Xd + 2 * 128);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int row = tid & 127, half = tid >> 7;
+  const uint32_t bar_tma = smem_u32(&bars[0]), bar_s = smem_u32(&bars[1]), bar_o = smem_u32(&bars[2]);
+  if (warp == 0) { tmem_alloc(smem_u32(tmem_slot), 512u); tmem_relinquish(); }
+  if (tid == 32) { mbar_init(bar_tma, 1); mbar_init(bar_s, 1); mbar_init(bar_o, 1); fence_barrier_init(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  pdl_trigger();                                         // only now: this CTA owns all 512 TMEM columns of its SM, a dependent CTA
+                                                         // that got them first would wait for this grid while this CTA waits for TMEM
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t trow = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+  const uint32_t qsb = smem_u32(Qs), ksb = smem_u32(Ks), vsb = smem_u32(Vs), gsb = smem_u32(Gs), ps = smem_u32(Ps), dsb = smem_u32(Ds);
+
+  uint32_t ph_tma = 0, ph_s = 0, ph_o = 0;               // mbarrier phase parities
+  int w_bi = -1, w_hd = -1;                              // (branch, head) whose LePE weights are staged
+  for (int gt = blockIdx.x; gt < P.total_tiles; gt += gridDim.x) {
+    const int bi = (P.nb > 1 && gt >= P.br[1].tile_begin) ? 1 : 0;
+    const BwdBranch& br = P.br[bi];
+    const int N = br.N, hs = br.hs, ws = br.ws;
+    const int kext = (N + 15) & ~15;
+    int local = gt - br.tile_begin;
+    const int mhead = local % br.heads; local /= br.heads;
+    const int win = local % br.nwin;
+    const int mb = local / br.nwin;
+    const int mih = win / br.nww, miw = win - mih * br.nww;
+
+    if (bi != w_bi || mhead != w_hd) {                   // LePE weights of this head: Wt[tap][ch]   (CTA-uniform branch)
+      if (tid < 36) {
+        const uint4 raw = *reinterpret_cast<const uint4*>(br.cw + (size_t)mhead * 288 + tid * 8);
+        const uint32_t w4[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int idx = tid * 8 + e, ch = idx / 9, t = idx - ch * 9;
+          Wt[t * 32 + ch] = (e & 1) ? bf16_hi(w4[e >> 1]) : bf16_lo(w4[e >> 1]);
+        }
+      }
+      w_bi = bi; w_hd = mhead;
+    }
+    // rows [N, 256) of Q, K, V, G are contraction / output rows of the MMAs but not written by TMA: zero them
+    for (int i = tid; i < 4 * 256 * 4; i += kThr) {
+      const int r = (i >> 2) & 255;
+      if (r >= N) *reinterpret_cast<uint4*>(smem + i * 16) = make_uint4(0, 0, 0, 0);
+    }
+    fence_proxy_async();
+    __syncthreads();
+    pdl_wait();
+    if (warp == 0 && elect_one()) {      // one elected lane, warp-uniform datapath for the TMA / tcgen05 issue
+      mbar_expect_tx(bar_tma, (uint32_t)(4 * N * kRowB));
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        tma_load_4d(smem_u32(smem + j * kWOpB), &P.map[bi][j], bar_tma, mhead * 32, miw * ws, mih * hs, mb);
+    }
+    mbar_wait(bar_tma, ph_tma); ph_tma ^= 1;
+    tc_fence_after();
+
+    bool pending_o = false;                              // a dV / dK / dQ commit whose completion nobody has waited for yet
+#pragma unroll 1
+    for (int qt = 0; qt < 2; ++qt) {
+      const int qn = qt * 128 + row;                     // window-local token of my query row
+      const bool qvalid = qn < N;
+      const int qr = qn / ws, qc = qn - qr * ws;
+      const int64_t qtok = (int64_t)(mih * hs + qr) * P.reso + (miw * ws + qc);
+      const float lse2 = (qvalid ? br.lse[((int64_t)mb * P.reso * P.reso + qtok) * br.heads + mhead] : 0.f) * 1.4426950408889634f;
+      float delta = 0.f;
+#pragma unroll 1
+      for (int pass = 0; pass < 2; ++pass) {             // 0: delta, 1: P / dS and the three gradient contractions
+#pragma unroll 1
+        for (int kh = 0; kh < 2; ++kh) {
+          const int kx = min(128, kext - 128 * kh);      // key columns of this half fed to the MMAs (multiple of 16, >= 16)
+          if (warp == 0 && elect_one()) {      // one elected lane, warp-uniform datapath for the TMA / tcgen05 issue
+            tc_fence_after();
+            const uint32_t idesc = make_idesc_bf16(128, kx, 0, 0);
+            const uint64_t qd = make_smem_desc(qsb + qt * 8192, 16, 512, kLayoutSw64), kd = make_smem_desc(ksb + kh * 8192, 16, 512, kLayoutSw64);
+            const uint64_t gd = make_smem_desc(gsb + qt * 8192, 16, 512, kLayoutSw64), vd = make_smem_desc(vsb + kh * 8192, 16, 512, kLayoutSw64);
+            mma_ss(tmem_base, qd, kd, idesc, false);
+            mma_ss(tmem_base, qd + 2, kd + 2, idesc, true);
+            mma_ss(tmem_base + 128, gd, vd, idesc, false);
+            mma_ss(tmem_base + 128, gd + 2, vd + 2, idesc, true);
+            tc_commit(bar_s);
+          }
+          mbar_wait(bar_s, ph_s); ph_s ^= 1;
+          tc_fence_after();
+          // my 64 key columns of this half: [half * 64, +64), two chunks of 32
+          if (pass == 0) {
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+              const int k0 = half * 64 + 32 * c;
+              if (k0 < kx) {
+                uint32_t s[32], d[32];
+                tmem_ld32(trow + k0, s);
+                tmem_ld32(trow + 128 + k0, d);
+                tmem_wait_ld();
+                const int lim = qvalid ? N - (kh * 128 + k0) : 0;
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (j < lim) delta = fmaf(ex2a(fmaf(__uint_as_float(s[j]), P.scale_log2e, -lse2)), __uint_as_float(d[j]), delta);
+              }
+            }
+            tc_fence_before();
+            __syncthreads();                             // S / dP consumed: the next MMA pair may overwrite them
+          } else {
+            if (pending_o) { mbar_wait(bar_o, ph_o); ph_o ^= 1; pending_o = false; }   // P / dS of the previous half have been read
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+              const int k0 = half * 64 + 32 * c;         // column inside the 128-column tile (multiple of 32)
+              uint32_t pp[16], dd[16];
+              if (k0 < kx) {
+                uint32_t s[32], d[32];
+                tmem_ld32(trow + k0, s);
+                tmem_ld32(trow + 128 + k0, d);
+                tmem_wait_ld();
+                const int lim = qvalid ? N - (kh * 128 + k0) : 0;
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) {
+                  float p0_ = 0.f, p1_ = 0.f, d0 = 0.f, d1 = 0.f;
+                  if (j < lim) { p0_ = ex2a(fmaf(__uint_as_float(s[j]), P.scale_log2e, -lse2)); d0 = p0_ * (__uint_as_float(d[j]) - delta); }
+                  if (j + 1 < lim) { p1_ = ex2a(fmaf(__uint_as_float(s[j + 1]), P.scale_log2e, -lse2)); d1 = p1_ * (__uint_as_float(d[j + 1]) - delta); }
+                  pp[j >> 1] = pack_bf16x2(p0_, p1_);
+                  dd[j >> 1] = pack_bf16x2(d0, d1);
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) { pp[j] = 0u; dd[j] = 0u; }
+              }
+              const int blk = k0 >> 6, ch0 = (k0 & 63) >> 3;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                sts128(sw128(ps + blk * 16384, row, ch0 + k), pp[4 * k], pp[4 * k + 1], pp[4 * k + 2], pp[4 * k + 3]);
+                sts128(sw128(dsb + blk * 16384, row, ch0 + k), dd[4 * k], dd[4 * k + 1], dd[4 * k + 2], dd[4 * k + 3]);
+              }
+            }
+            fence_proxy_async();
+            tc_fence_before();
+            __syncthreads();                             // S / dP consumed; P / dS visible to the tensor core
+            if (warp == 0 && elect_one()) {      // one elected lane, warp-uniform datapath for the TMA / tcgen05 issue
+              tc_fence_after();
+              const uint32_t id_mn = make_idesc_bf16(128, 32, 1, 1);      // A = P / dS read MN-major (kv rows out), B MN-major
+              const uint32_t id_k = make_idesc_bf16(128, 32, 0, 1);       // A = dS K-major (q rows out), B = K MN-major
+              const uint64_t pd = make_smem_desc(ps, 16384, 1024, kLayoutSw128), dd = make_smem_desc(dsb, 16384, 1024, kLayoutSw128);
+              const uint64_t gd = make_smem_desc(gsb + qt * 8192, 512, 512, kLayoutSw64), qd = make_smem_desc(qsb + qt * 8192, 512, 512, kLayoutSw64);
+              const uint64_t kd = make_smem_desc(ksb + kh * 8192, 512, 512, kLayoutSw64);
+              for (int k = 0; k < 8; ++k) {                               // contraction over the 128 query rows of this tile
+                mma_ss(tmem_base + kColDV + 32 * kh, pd + (uint64_t)k * (2048 >> 4), gd + (uint64_t)k * (1024 >> 4), id_mn, (qt | k) != 0);
+                mma_ss(tmem_base + kColDK + 32 * kh, dd + (uint64_t)k * (2048 >> 4), qd + (uint64_t)k * (1024 >> 4), id_mn, (qt | k) != 0);
+              }
+              const uint64_t dk_ = make_smem_desc(dsb, 16, 1024, kLayoutSw128);         // dS as K-major A
+              for (int k = 0; k < kx / 16; ++k) {                         // contraction over the keys of this half
+                const uint64_t a = dk_ + (uint64_t)((k >> 2) * (16384 >> 4) + (k & 3) * 2);
+                mma_ss(tmem_base + kColDQ, a, kd + (uint64_t)k * (1024 >> 4), id_k, (kh | k) != 0);
+              }
+              tc_commit(bar_o);
+            }
+            pending_o = true;
+          }
+        }
+        if (pass == 0) {                                 // the two threads of a row meet
+          Xd[half * 128 + row] = delta;
+          __syncthreads();
+          delta += Xd[(half ^ 1) * 128 + row];
+          __syncthreads();                               // Xd free for the next query tile
+        }
+      }
+      // dQ of this query tile (both key halves accumulated)
+      mbar_wait(bar_o, ph_o); ph_o ^= 1; pending_o = false;
+      tc_fence_after();
+      {
+        uint32_t q16[16];
+        tmem_ld16(trow + kColDQ + half * 16, q16);
+        tmem_wait_ld();
+        if (qvalid) {
+          __nv_bfloat16* pq = br.dq + (int64_t)mb * br.dq_bs + qtok * br.dq_ts + mhead * 32 + half * 16;
+          uint32_t a[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) a[j] = pack_bf16x2(__uint_as_float(q16[2 * j]) * P.scale, __uint_as_float(q16[2 * j + 1]) * P.scale);
+          *reinterpret_cast<uint4*>(pq) = make_uint4(a[0], a[1], a[2], a[3]); *reinterpret_cast<uint4*>(pq + 8) = make_uint4(a[4], a[5], a[6], a[7]);
+        }
+      }
+      tc_fence_before();
+      __syncthreads();                                   // dQ columns free for the next query tile
+    }
+    // dK, dV of both key halves (+ the LePE conv-transpose of G into dV)
+#pragma unroll 1
+    for (int kh = 0; kh < 2; ++kh) {
+      const int n = kh * 128 + row;
+      const bool valid = n < N;
+      const int r_ = n / ws, c_ = n - r_ * ws;
+      float lv[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) lv[j] = 0.f;
+      if (valid) {
+        const float* wt = Wt + half * 16;
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+          const int rr = r_ - (t / 3 - 1), cc = c_ - (t % 3 - 1);       // the output position that read me through tap t
+          if (rr >= 0 && rr < hs && cc >= 0 && cc < ws) {
+            const int gr = rr * ws + cc;
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch) {
+              const uint4 g4 = lds128(sw64(gsb, gr, half * 2 + ch));
+              const float4 w0 = *reinterpret_cast<const float4*>(wt + t * 32 + ch * 8);
+              const float4 w1 = *reinterpret_cast<const float4*>(wt + t * 32 + ch * 8 + 4);
+              lv[ch * 8 + 0] = fmaf(w0.x, bf16_lo(g4.x), lv[ch * 8 + 0]); lv[ch * 8 + 1] = fmaf(w0.y, bf16_hi(g4.x), lv[ch * 8 + 1]);
+              lv[ch * 8 + 2] = fmaf(w0.z, bf16_lo(g4.y), lv[ch * 8 + 2]); lv[ch * 8 + 3] = fmaf(w0.w, bf16_hi(g4.y), lv[ch * 8 + 3]);
+              lv[ch * 8 + 4] = fmaf(w1.x, bf16_lo(g4.z), lv[ch * 8 + 4]); lv[ch * 8 + 5] = fmaf(w1.y, bf16_hi(g4.z), lv[ch * 8 + 5]);
+              lv[ch * 8 + 6] = fmaf(w1.z, bf16_lo(g4.w), lv[ch * 8 + 6]); lv[ch * 8 + 7] = fmaf(w1.w, bf16_hi(g4.w), lv[ch * 8 + 7]);
+            }
+          }
+        }
+      }
+      uint32_t k16[16], v16[16];
+      tmem_ld16(trow + kColDK + 32 * kh + half * 16, k16);
+      tmem_ld16(trow + kColDV + 32 * kh + half * 16, v16);
+      tmem_wait_ld();
+      if (valid) {
+        const int64_t tok = (int64_t)(mih * hs + r_) * P.reso + (miw * ws + c_);
+        const int64_t cho = mhead * 32 + half * 16;
+        __nv_bfloat16* pk = br.dk + (int64_t)mb * br.dk_bs + tok * br.dk_ts + cho;
+        __nv_bfloat16* pv = br.dv + (int64_t)mb * br.dv_bs + tok * br.dv_ts + cho;
+        uint32_t b[8], c[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          b[j] = pack_bf16x2(__uint_as_float(k16[2 * j]) * P.scale, __uint_as_float(k16[2 * j + 1]) * P.scale);
+          c[j] = pack_bf16x2(__uint_as_float(v16[2 * j]) + lv[2 * j], __uint_as_float(v16[2 * j + 1]) + lv[2 * j + 1]);
+        }
+        *reinterpret_cast<uint4*>(pk) = make_uint4(b[0], b[1], b[2], b[3]); *reinterpret_cast<uint4*>(pk + 8) = make_uint4(b[4], b[5], b[6], b[7]);
+        *reinterpret_cast<uint4*>(pv) = make_uint4(c[0], c[1], c[2], c[3]); *reinterpret_cast<uint4*>(pv + 8) = make_uint4(c[4], c[5], c[6], c[7]);
+      }
+    }
+    tc_fence_before();
+    __syncthreads();                                     // closes the problem: shared-memory operands and TMEM are free again
+  }
+  if (warp == 0) tmem_dealloc(tmem_base, 512u);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // d get_v.weight[c, tap] = sum over (b, token) of G[b, tok, c] * V[b, tok + tap, c]  (neighbour inside the same window),
 // d get_v.bias[c] = sum G[b, tok, c]   — autograd of the depthwise conv in LePEAttention.get_lepe (cswin_unet.py:67-80).
 // ------------------------------------------------------------------------------------------------------------------
@@ -525,17 +789,27 @@ int lepe_param_grad_tc(const cswin_lepe_branch_grad_t* gs, int nb, int B, int re
 int lepe_attention_bwd_tc(const cswin_lepe_branch_grad_t* gs, int nb, int B, int reso, float scale, cudaStream_t stream,
                           bool* handled) {
   *handled = false;
+  int n_wide = 0;                                        // branches with 128 < N <= 256: wide kernel (all or none)
   for (int i = 0; i < nb; ++i) {
     const cswin_lepe_branch_grad_t& g = gs[i];
     const cswin_lepe_branch_t& s = g.fwd;
     if (!s.q || !s.k || !s.v || !s.conv_w || !s.lse || !g.dout || !g.dq || !g.dk || !g.dv || ((g.dconv_w != nullptr) != (g.dconv_b != nullptr))) return CSWIN_OK;
     if (s.heads <= 0 || s.C_b != s.heads * 32) return CSWIN_OK;
-    if (s.H_sp <= 0 || s.W_sp <= 0 || reso % s.H_sp || reso % s.W_sp || s.H_sp * s.W_sp > 128 || s.H_sp > 256 || s.W_sp > 256) return CSWIN_OK;
+    if (s.H_sp <= 0 || s.W_sp <= 0 || reso % s.H_sp || reso % s.W_sp || s.H_sp * s.W_sp > 256 || s.H_sp > 256 || s.W_sp > 256) return CSWIN_OK;
+    if (s.H_sp * s.W_sp > 128) ++n_wide;
     const int64_t st[] = {s.q_bs, s.q_ts, s.k_bs, s.k_ts, s.v_bs, s.v_ts, g.do_bs, g.do_ts, g.dq_bs, g.dq_ts, g.dk_bs, g.dk_ts, g.dv_bs, g.dv_ts};
     for (int64_t v : st) if (v <= 0 || (v * 2) % 16 != 0) return CSWIN_OK;
     if (!al16(s.q) || !al16(s.k) || !al16(s.v) || !al16(g.dout) || !al16(g.dq) || !al16(g.dk) || !al16(g.dv) || !al16(s.conv_w)) return CSWIN_OK;
   }
   if (tc::encode_tiled_fn() == nullptr) return CSWIN_OK;
+  if (n_wide != 0 && n_wide != nb) return CSWIN_OK;
+  const bool wide = n_wide != 0;
+  if (gs[0].dconv_w != nullptr) {                        // parameter gradients first: if their kernel declines, so does this path
+    bool pg = false;
+    const int rc = lepe_param_grad_tc(gs, nb, B, reso, stream, &pg);
+    if (rc != CSWIN_OK) return rc;
+    if (!pg) return CSWIN_OK;
+  }
   BwdParams P;
   P.nb = nb; P.reso = reso; P.scale = scale; P.scale_log2e = scale * 1.4426950408889634f;
   P.trace = g_trace.load(std::memory_order_relaxed);
@@ -551,7 +825,7 @@ int lepe_attention_bwd_tc(const cswin_lepe_branch_grad_t* gs, int nb, int B, int
     d.nwin = (reso / s.H_sp) * (reso / s.W_sp); d.N = s.H_sp * s.W_sp; d.nprob = B * d.nwin * d.heads;
     d.tile_begin = tiles;
     const int slots = d.N <= 64 ? 2 : 1;
-    tiles += (d.nprob + slots - 1) / slots;
+    tiles += wide ? d.nprob : (d.nprob + slots - 1) / slots;
     const void* ptr[4] = {s.q, s.k, s.v, g.dout};
     const int64_t bs[4] = {s.q_bs, s.k_bs, s.v_bs, g.do_bs}, ts[4] = {s.q_ts, s.k_ts, s.v_ts, g.do_ts};
     for (int j = 0; j < 4; ++j) {
@@ -576,15 +850,13 @@ int lepe_attention_bwd_tc(const cswin_lepe_branch_grad_t* gs, int nb, int B, int
     }
     grid = (period <= cap) ? cap / period * period : cap;
   }
-  if (gs[0].dconv_w != nullptr) {
-    bool pg = false;
-    const int rc = lepe_param_grad_tc(gs, nb, B, reso, stream, &pg);
-    if (rc != CSWIN_OK) return rc;
-  }
   static std::atomic<bool> configured{false};
-  if (!configured.exchange(true))
+  if (!configured.exchange(true)) {
     CSWIN_CUDA_OK(cudaFuncSetAttribute(lepe_attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
-  CSWIN_CUDA_OK(launch_pdl(lepe_attn_bwd_tc_kernel, dim3(grid), dim3(kThr), (size_t)kSmem, stream, P));
+    CSWIN_CUDA_OK(cudaFuncSetAttribute(lepe_attn_bwd_wide_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemWideBwd));
+  }
+  if (wide) CSWIN_CUDA_OK(launch_pdl(lepe_attn_bwd_wide_tc_kernel, dim3(std::min(tiles, sm_count())), dim3(kThr), (size_t)kSmemWideBwd, stream, P));
+  else CSWIN_CUDA_OK(launch_pdl(lepe_attn_bwd_tc_kernel, dim3(grid), dim3(kThr), (size_t)kSmem, stream, P));
   CSWIN_LAUNCH_CHECK();
   g_tc_launches.fetch_add(1, std::memory_order_relaxed);
   *handled = true;

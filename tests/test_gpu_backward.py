@@ -328,14 +328,14 @@ def test_linear_training_epilogues_match_the_composed_kernels(M, K, N):
     assert rel(dz, dz_ref.double()) <= 8e-3, rel(dz, dz_ref.double())
 
 
-LEPE_WIDE_BWD = ((128, 32, 0, 8, 4), (128, 32, 1, 8, 4), (512, 16, -1, 8, 16), (64, 24, 0, 8, 2))
+LEPE_WIDE_BWD = ((128, 32, 0, 8, 4), (128, 32, 1, 8, 4), (512, 16, -1, 8, 16), (64, 24, 0, 8, 2), (64, 14, -1, 14, 2))
 
 
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-5), (torch.bfloat16, 2e-2)])
 def test_lepe_attention_backward_wide_windows_vs_fp64(dtype, tol):
-    """BASELINE configs[4] (512^2): 256- and 192-token stripe windows.  Forward on the wide tcgen05 kernel (bf16), backward of
-    q / k / v on the general kernel with the get_v parameter gradients from cswin_lepe_param_grad on the second stream
-    (dconv_w = NULL in the backward call) — compared with autograd through the fp64 oracle."""
+    """BASELINE configs[4] (512^2): 256-, 192- and 196-token windows.  bf16: forward and backward on the wide tcgen05 kernels
+    (two query tiles x two key halves per (window, head)); fp32: the general kernels.  Both with the get_v parameter
+    gradients from cswin_lepe_param_grad on the second stream where it applies — compared with autograd through the fp64 oracle."""
     B = 2
     for (cb, reso, idx, split, heads) in LEPE_WIDE_BWD:
         full_c = cb if idx == -1 else 2 * cb
@@ -353,9 +353,12 @@ def test_lepe_attention_backward_wide_windows_vs_fp64(dtype, tol):
         m = cw.LePEAttention(cb, resolution=reso, idx=idx, split_size=split, num_heads=heads).to(DEV)
         with torch.no_grad():
             m.get_v.weight.copy_(w64.float()); m.get_v.bias.copy_(b64.float())
+        t0 = cw.tc_launch_count()
         y = m(base.permute(2, 0, 1, 3)[..., off:off + cb])
         assert rel(y, yo) <= tol, (key, "forward", rel(y, yo))
         gb, gw, gbias = torch.autograd.grad(y, [base, m.get_v.weight, m.get_v.bias], gup64.to(DEV).to(dtype))
+        if dtype == torch.bfloat16:           # forward: wide tcgen05 kernel when 128 % W_sp == 0; backward: wide tcgen05 kernel always
+            assert cw.tc_launch_count() == t0 + (2 if 128 % m.W_sp == 0 else 1), (key, cw.tc_launch_count() - t0)
         sl = (Ellipsis, slice(off, off + cb))
         assert rel(gb[sl], ref[0][sl]) <= tol, (key, "dqkv", rel(gb[sl], ref[0][sl]))
         assert rel(gw, ref[1]) <= tol and rel(gbias, ref[2]) <= tol, (key, rel(gw, ref[1]), rel(gbias, ref[2]))

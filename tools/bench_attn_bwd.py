@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Per-stage device time of the fused LePE attention forward / backward kernels (torch.profiler / CUPTI), plus the
-in-kernel %globaltimer phase trace of the backward kernel.  Usage: python tools/bench_attn_bwd.py [B]"""
+in-kernel %globaltimer phase trace of the backward kernel.  Usage: python tools/bench_attn_bwd.py [B] [512]"""
 import collections
 import os
 import sys
@@ -15,6 +15,8 @@ from cswin_unet_b200 import _lib, autograd as ag  # noqa: E402
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 24
 STAGES = [(64, 56, 2, 1, False), (128, 28, 4, 2, False), (256, 14, 8, 7, False), (512, 7, 16, 7, True)]
+if len(sys.argv) > 2 and sys.argv[2] == "512":          # 512^2 configuration, split [1,2,8,8]
+    STAGES = [(64, 128, 2, 1, False), (128, 64, 4, 2, False), (256, 32, 8, 8, False), (512, 16, 16, 8, True)]
 NAMES = ["entry", "prologue", "S/dP ready", "P,dS published", "lepe dv done", "dw/db done", "dQ/dK/dV ready", "exit"]
 
 for si, (C, reso, heads, split, last) in enumerate(STAGES):
