@@ -82,6 +82,9 @@ SIGNATURES = {
     "cswin_lepe_attention_fwd": (c_int32, [C.POINTER(LepeBranch), c_int32, c_int32, c_int32, c_float, c_int32, c_void_p]),
     "cswin_lepe_attention_bwd": (c_int32, [C.POINTER(LepeBranchGrad), c_int32, c_int32, c_int32, c_float, c_int32, c_void_p]),
     "cswin_lepe_param_grad": (c_int32, [C.POINTER(LepeBranchGrad), c_int32, c_int32, c_int32, c_int32, c_void_p, C.POINTER(c_int32)]),
+    "cswin_zoom_cubic_fwd": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_int64, c_int64, c_int32, c_int32,
+                                       c_int32, c_void_p]),
+    "cswin_zoom_nearest_u8": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_int32, c_int32, c_void_p]),
     "cswin_layernorm_fwd": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int32,
                                       c_float, c_void_p, c_void_p, c_int32, c_void_p]),
     "cswin_linear_fwd": (c_int32, [C.POINTER(LinearArgs), c_int32, c_void_p]),

@@ -99,6 +99,16 @@ int cswin_lepe_param_grad(const cswin_lepe_branch_grad_t* branches, int32_t n_br
   return rc;
 }
 
+int cswin_zoom_cubic_fwd(const float* in, int32_t n, int32_t H, int32_t W, double* work, float* out, int64_t out_slice_stride,
+                         int64_t out_channel_stride, int32_t channel_copies, int32_t OH, int32_t OW, cswin_stream_t stream) {
+  return zoom_cubic(in, n, H, W, work, out, out_slice_stride, out_channel_stride, channel_copies, OH, OW, (cudaStream_t)stream);
+}
+
+int cswin_zoom_nearest_u8(const uint8_t* in, int32_t n, int32_t H, int32_t W, uint8_t* out, int32_t OH, int32_t OW,
+                          cswin_stream_t stream) {
+  return zoom_nearest_u8(in, n, H, W, out, OH, OW, (cudaStream_t)stream);
+}
+
 int cswin_layernorm_fwd(const void* x, int64_t ldx, const void* gamma, const void* beta, void* y, int64_t ldy,
                         int64_t M, int32_t C, float eps, float* mean_out, float* rstd_out, int32_t dtype,
                         cswin_stream_t stream) {

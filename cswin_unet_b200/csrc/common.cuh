@@ -96,6 +96,9 @@ int lepe_attention_fwd_simt(const cswin_lepe_branch_t* br, int nb, int B, int re
 int lepe_attention_fwd_tc(const cswin_lepe_branch_t* br, int nb, int B, int reso, float scale, cudaStream_t s, bool* handled);
 int lepe_attention_bwd_tc(const cswin_lepe_branch_grad_t* br, int nb, int B, int reso, float scale, cudaStream_t s, bool* handled);
 int lepe_attention_bwd_simt(const cswin_lepe_branch_grad_t* br, int nb, int B, int reso, float scale, int dtype, cudaStream_t s);
+int zoom_cubic(const float* in, int n, int H, int W, double* work, float* out, int64_t out_ns, int64_t out_cs, int reps, int OH,
+               int OW, cudaStream_t s);
+int zoom_nearest_u8(const uint8_t* in, int n, int H, int W, uint8_t* out, int OH, int OW, cudaStream_t s);
 int lepe_param_grad_tc(const cswin_lepe_branch_grad_t* br, int nb, int B, int reso, cudaStream_t s, bool* handled);
 int layernorm_fwd(const void* x, int64_t ldx, const void* g, const void* b, void* y, int64_t ldy, int64_t M, int C,
                   float eps, float* mean, float* rstd, float* ystats, int dtype, cudaStream_t s);

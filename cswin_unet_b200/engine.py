@@ -110,17 +110,65 @@ class SliceEngine:
         return self.batch * self.in_chans * self.size * self.size * 4, self.batch * self.size * self.size
 
 
-def predict_volume(engine: "SliceEngine", image, order_in: int = 3, shard: Optional[Tuple[int, int]] = None):
+def _predict_volume_gpu(engine: "SliceEngine", image, rng: range):
+    """predict_volume with both resampling steps on the GPU (cswin_zoom_cubic_fwd / cswin_zoom_nearest_u8): per batch the raw
+    slices go host -> device, are zoomed straight into the engine's input buffer (all three channel planes), the captured
+    forward graph runs, and the label map is zoomed back before it leaves the device.  Same arithmetic as scipy (float64
+    spline prefilter and interpolation, scipy's edge rule), so the label maps equal the host-resampled ones."""
+    import numpy as np
+    from . import ops
+    D, H, W = image.shape
+    P, Bt = engine.size, engine.batch
+    dev = engine.device
+    key = (H, W)
+    buf = engine.__dict__.setdefault("_resample_bufs", {}).get(key)
+    if buf is None:
+        with torch.cuda.device(dev):
+            buf = {"raw": [torch.empty((Bt, H, W), dtype=torch.float32, device=dev) for _ in range(2)],
+                   "work": torch.empty(Bt * H * W, dtype=torch.float64, device=dev),
+                   "lab": [torch.empty((Bt, H, W), dtype=torch.uint8, device=dev) for _ in range(2)],
+                   "host_in": [torch.empty((Bt, H, W), dtype=torch.float32).pin_memory() for _ in range(2)],
+                   "ev": [torch.cuda.Event() for _ in range(2)]}
+        engine._resample_bufs[key] = buf
+    out = torch.empty((len(rng), H, W), dtype=torch.uint8).pin_memory()
+    cs = engine.streams["compute"]
+    cs.wait_stream(torch.cuda.current_stream(dev))
+    idx = list(rng)
+    with torch.cuda.stream(cs), torch.no_grad():
+        for bi, i0 in enumerate(range(0, len(idx), Bt)):
+            sl = idx[i0:i0 + Bt]
+            n = len(sl)
+            k = bi % 2
+            slot = engine.slots[k]
+            buf["ev"][k].synchronize()                               # the pinned staging buffer of this parity is free again
+            buf["host_in"][k][:n].copy_(torch.from_numpy(image[sl[0]:sl[-1] + 1]))
+            buf["raw"][k][:n].copy_(buf["host_in"][k][:n], non_blocking=True)
+            buf["ev"][k].record(cs)
+            ops.zoom_cubic(buf["raw"][k][:n], (P, P), out=slot["x"], work=buf["work"])
+            slot["graph"].replay()
+            ops.zoom_nearest_u8(slot["y"][:n].contiguous(), (H, W), out=buf["lab"][k])
+            out[i0:i0 + n].copy_(buf["lab"][k][:n], non_blocking=True)
+    cs.synchronize()
+    return out.numpy().copy()
+
+
+def predict_volume(engine: "SliceEngine", image, order_in: int = 3, shard: Optional[Tuple[int, int]] = None,
+                   resample: str = "scipy"):
     """The slice loop of `test_single_volume` (utils.py:61-80) on the engine: every slice of the (D, H, W) float volume is
     resized to the network resolution with scipy `zoom(order=3)` on the host (as the reference does), segmented in
     batches, and the label map is resized back with `zoom(order=0)`.  `shard=(rank, world)` restricts the work to this
-    rank's contiguous slice range; returns (labels uint8 (n_local, H, W), range)."""
+    rank's contiguous slice range; returns (labels uint8 (n_local, H, W), range).
+    `resample="gpu"` does both zooms on the device instead (same arithmetic, ~15 ms of host time per 512^2 slice saved)."""
     import numpy as np
-    from scipy.ndimage import zoom
-    image = np.asarray(image, dtype=np.float32)
+    image = np.ascontiguousarray(np.asarray(image, dtype=np.float32))
     D, H, W = image.shape
     rng = shard_slices(D, shard[1], shard[0]) if shard else range(D)
     P = engine.size
+    if resample == "gpu" and order_in == 3 and len(rng) > 0 and (H, W) != (P, P):      # (same size: the reference does not zoom)
+        return _predict_volume_gpu(engine, image, rng), rng
+    if resample not in ("scipy", "gpu"):
+        raise ValueError(f"resample must be 'scipy' or 'gpu', got {resample!r}")
+    from scipy.ndimage import zoom
     resized = np.empty((len(rng), 1, P, P), np.float32)
     for j, d in enumerate(rng):
         sl = image[d]

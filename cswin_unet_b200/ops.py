@@ -533,3 +533,36 @@ def carafe_reassemble_bwd(enc: Tensor, z: Tensor, dy: Tensor, B: int, H: int, W:
                                             dz.data_ptr(), dz.stride(0), dbias.data_ptr(), kws.data_ptr(), B, H, W, Cn, up,
                                             _dtype_code(z), _stream()), "cswin_carafe_reassemble_bwd")
     return denc, dz, dbias
+
+
+def zoom_cubic(x: Tensor, out_hw: Tuple[int, int], out: Optional[Tensor] = None, work: Optional[Tensor] = None) -> Tensor:
+    """scipy.ndimage.zoom(slice, (oh / H, ow / W), order=3) for every slice of x (n, H, W) float32 (utils.py:69).
+    `out`: (n, C, oh, ow) float32 contiguous per channel plane — every channel receives the same plane (the model's 1 -> 3
+    channel repeat) — default (n, 1, oh, ow).  `work`: n*H*W float64 scratch."""
+    _need_cuda(x, out, work)
+    assert x.dtype == torch.float32 and x.dim() == 3 and x.is_contiguous()
+    n, H, W = x.shape
+    oh, ow = out_hw
+    if out is None:
+        out = torch.empty((n, 1, oh, ow), dtype=torch.float32, device=x.device)
+    assert out.dtype == torch.float32 and out.dim() == 4 and out.shape[0] >= n and tuple(out.shape[2:]) == (oh, ow)
+    assert out.stride(3) == 1 and out.stride(2) == ow
+    if work is None:
+        work = torch.empty(n * H * W, dtype=torch.float64, device=x.device)
+    assert work.dtype == torch.float64 and work.numel() >= n * H * W and work.is_contiguous()
+    check(lib().cswin_zoom_cubic_fwd(x.data_ptr(), n, H, W, work.data_ptr(), out.data_ptr(), out.stride(0), out.stride(1),
+                                     out.shape[1], oh, ow, _stream()), "cswin_zoom_cubic_fwd")
+    return out
+
+
+def zoom_nearest_u8(lab: Tensor, out_hw: Tuple[int, int], out: Optional[Tensor] = None) -> Tensor:
+    """scipy.ndimage.zoom(label_map, (oh / H, ow / W), order=0) for every (H, W) uint8 map of lab (n, H, W) (utils.py:77)."""
+    _need_cuda(lab, out)
+    assert lab.dtype == torch.uint8 and lab.dim() == 3 and lab.is_contiguous()
+    n, H, W = lab.shape
+    oh, ow = out_hw
+    if out is None:
+        out = torch.empty((n, oh, ow), dtype=torch.uint8, device=lab.device)
+    assert out.dtype == torch.uint8 and out.is_contiguous() and out.shape[0] >= n and tuple(out.shape[1:]) == (oh, ow)
+    check(lib().cswin_zoom_nearest_u8(lab.data_ptr(), n, H, W, out.data_ptr(), oh, ow, _stream()), "cswin_zoom_nearest_u8")
+    return out

@@ -103,6 +103,21 @@ int cswin_lepe_param_grad(const cswin_lepe_branch_grad_t* branches, int32_t n_br
                           int32_t dtype, cswin_stream_t stream, int32_t* handled);
 
 /* ------------------------------------------------------------------------------------------------
+ * Slice resampling of the evaluation loop (test_single_volume, utils.py:61-90) — scipy.ndimage.zoom with scipy's defaults
+ * (mode='constant', cval=0, prefilter=True, grid_mode=False), reproduced in float64 including its edge behaviour (a
+ * coordinate that rounds above in-1, e.g. 223 * (511/223), yields cval: the last row / column of a 512 -> 224 zoom is 0).
+ *   cswin_zoom_cubic_fwd  : utils.py:69  zoom(slice, (P/x, P/y), order=3).  in (n, H, W) float32 contiguous; work = n*H*W
+ *                           doubles of caller-owned scratch (the spline coefficients); out element (s, c, oy, ox) at
+ *                           s*out_slice_stride + c*out_channel_stride + oy*OW + ox for c < channel_copies (the 1 -> 3
+ *                           channel repeat of vision_transformer.py:40-41 costs nothing here).
+ *   cswin_zoom_nearest_u8 : utils.py:77  zoom(out, (x/P, y/P), order=0) on the uint8 label map, (n, H, W) -> (n, OH, OW).
+ * ------------------------------------------------------------------------------------------------ */
+int cswin_zoom_cubic_fwd(const float* in, int32_t n, int32_t H, int32_t W, double* work, float* out, int64_t out_slice_stride,
+                         int64_t out_channel_stride, int32_t channel_copies, int32_t OH, int32_t OW, cswin_stream_t stream);
+int cswin_zoom_nearest_u8(const uint8_t* in, int32_t n, int32_t H, int32_t W, uint8_t* out, int32_t OH, int32_t OW,
+                          cswin_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * LayerNorm over the last dimension.  Replaces nn.LayerNorm calls: norm1/norm2 (cswin_unet.py:168,179),
  * Merge_Block.norm :218, stem LN :341, norm :497, norm_up :533.   y = (x-mean)/sqrt(var+eps)*gamma+beta
  * mean_out / rstd_out: optional fp32 (M) saved statistics for the backward.

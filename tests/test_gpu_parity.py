@@ -569,3 +569,49 @@ def test_linear_bf16_ragged_k_on_tensor_cores(M, N, K):
     r2 = a[:, :K].double() @ wkn.double()
     assert (y1.float().cpu().double() - r1).abs().max().item() <= 3e-2
     assert (y2.float().cpu().double() - r2).abs().max().item() <= 3e-2
+
+
+# ---------------------------------------------------------------------------------------------------
+# slice resampling (scipy.ndimage.zoom of utils.py:69 / :77) on the GPU
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,H,W,P", [(3, 512, 512, 224), (2, 40, 36, 17), (1, 64, 64, 28), (2, 300, 200, 224), (1, 160, 144, 224)])
+def test_zoom_cubic_matches_scipy(n, H, W, P):
+    from scipy.ndimage import zoom
+    rng = np.random.default_rng(n + H + P)
+    x = rng.random((n, H, W)).astype(np.float32)
+    ref = np.stack([zoom(s, (P / H, P / W), order=3) for s in x])
+    out = ops.zoom_cubic(torch.from_numpy(x).to(DEV), (P, P), out=torch.zeros((n, 3, P, P), device=DEV))
+    y = out.cpu().numpy()
+    assert np.array_equal(y[:, 0], y[:, 1]) and np.array_equal(y[:, 0], y[:, 2])          # the 1 -> 3 channel repeat
+    err = np.abs(y[:, 0] - ref).max()
+    exact = (y[:, 0] == ref).mean()
+    print(f"[zoom cubic {H}x{W}->{P}] max-abs {err:.2e}, bit-identical {exact:.6f}")
+    assert err <= 1e-6 and exact >= 0.999
+    if (H, W, P) == (512, 512, 224):                     # scipy's edge rule: 223 * (511 / 223) > 511 -> cval
+        assert (ref[:, -1] == 0).all() and (y[:, 0, -1] == 0).all() and (y[:, 0, :, -1] == 0).all()
+
+
+@pytest.mark.parametrize("n,P,H,W", [(3, 224, 512, 512), (2, 28, 64, 64), (2, 224, 300, 200), (1, 17, 40, 36)])
+def test_zoom_nearest_matches_scipy(n, P, H, W):
+    from scipy.ndimage import zoom
+    rng = np.random.default_rng(n + H + P)
+    lab = (rng.random((n, P, P)) * 9).astype(np.uint8)
+    ref = np.stack([zoom(l, (H / P, W / P), order=0) for l in lab])
+    y = ops.zoom_nearest_u8(torch.from_numpy(lab).to(DEV), (H, W)).cpu().numpy()
+    assert y.shape == ref.shape and np.array_equal(y, ref)
+
+
+def test_predict_volume_gpu_resampling_equals_host_resampling():
+    """predict_volume(resample='gpu') (cswin_zoom_cubic_fwd -> forward -> cswin_zoom_nearest_u8, nothing but raw slices in and
+    label maps out) gives the label maps of the reference's host-side scipy loop (utils.py:61-80)."""
+    vol = _synthetic_volume(D=7, S=160, seed=5)
+    m = build_model("alive")
+    eng = cw.SliceEngine(m, batch=3, compute_dtype=torch.bfloat16)
+    host, _ = cw.predict_volume(eng, vol)
+    gpu, rng = cw.predict_volume(eng, vol, resample="gpu")
+    assert gpu.shape == host.shape and gpu.dtype == np.uint8 and list(rng) == list(range(7))
+    agree = (gpu == host).mean()
+    print(f"[volume gpu-resample] label agreement with the scipy path {agree:.6f}")
+    assert agree >= 0.9999
+    part = cw.predict_volume(eng, vol, shard=(1, 2), resample="gpu")
+    assert np.array_equal(part[0], gpu[list(part[1])])

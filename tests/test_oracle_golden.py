@@ -132,3 +132,23 @@ def test_metrics_fallback_rules():
     b[1, 3:6, 2:5] = True
     d, h = O.dice_hd95_percase(a, b)
     assert abs(d - 2 * 6 / 18) < 1e-12 and h == 1.0
+
+
+def test_zoom_oracle_is_scipy_bit_for_bit():
+    """oracle/zoom_oracle.py restates scipy.ndimage.zoom as the reference calls it (utils.py:69 order 3, :77 order 0); scipy is
+    the dependency that owns this arithmetic, so the oracle is pinned against scipy itself, including the zero last row /
+    column of the 512 -> 224 zoom."""
+    import numpy as np
+    from scipy.ndimage import zoom
+    from oracle import zoom_oracle as Z
+    rng = np.random.default_rng(1)
+    for (H, W, P) in ((512, 512, 224), (40, 36, 17), (64, 64, 28), (300, 200, 224)):
+        x = rng.random((H, W)).astype(np.float32)
+        ref = zoom(x, (P / H, P / W), order=3)
+        mine = Z.zoom_cubic(x, (Z.out_len(H, P / H), Z.out_len(W, P / W)))
+        assert mine.shape == ref.shape and np.array_equal(mine, ref), (H, W, P, np.abs(mine - ref).max())
+    assert (zoom(rng.random((512, 512)).astype(np.float32), (224 / 512, 224 / 512), order=3)[-1] == 0).all()
+    for (P, H, W) in ((224, 512, 512), (28, 64, 64), (224, 300, 200), (17, 40, 36)):
+        lab = (rng.random((P, P)) * 9).astype(np.uint8)
+        ref = zoom(lab, (H / P, W / P), order=0)
+        assert np.array_equal(Z.zoom_nearest(lab, (Z.out_len(P, H / P), Z.out_len(P, W / P))), ref)
