@@ -13,6 +13,8 @@ process / GPU over a shard of the slices (`shard_slices`); there is no collectiv
 """
 from __future__ import annotations
 
+import os
+
 from typing import Iterable, Iterator, List, Optional, Sequence, Tuple
 
 import torch
@@ -110,6 +112,9 @@ class SliceEngine:
         return self.batch * self.in_chans * self.size * self.size * 4, self.batch * self.size * self.size
 
 
+REGISTER_VOLUME = os.environ.get("CSWIN_VOLUME_REGISTER", "0") == "1"     # measured: page-locking a 150 MB volume costs as much as the staging memcpy it saves
+
+
 def _predict_volume_gpu(engine: "SliceEngine", image, rng: range):
     """predict_volume with both resampling steps on the GPU (cswin_zoom_cubic_fwd / cswin_zoom_nearest_u8): per batch the raw
     slices go host -> device, are zoomed straight into the engine's input buffer (all three channel planes), the captured
@@ -134,22 +139,35 @@ def _predict_volume_gpu(engine: "SliceEngine", image, rng: range):
     cs = engine.streams["compute"]
     cs.wait_stream(torch.cuda.current_stream(dev))
     idx = list(rng)
-    with torch.cuda.stream(cs), torch.no_grad():
-        for bi, i0 in enumerate(range(0, len(idx), Bt)):
-            sl = idx[i0:i0 + Bt]
-            n = len(sl)
-            k = bi % 2
-            slot = engine.slots[k]
-            buf["ev"][k].synchronize()                               # the pinned staging buffer of this parity is free again
-            buf["host_in"][k][:n].copy_(torch.from_numpy(image[sl[0]:sl[-1] + 1]))
-            buf["raw"][k][:n].copy_(buf["host_in"][k][:n], non_blocking=True)
-            buf["ev"][k].record(cs)
-            ops.zoom_cubic(buf["raw"][k][:n], (P, P), out=slot["x"], work=buf["work"])
-            slot["graph"].replay()
-            ops.zoom_nearest_u8(slot["y"][:n].contiguous(), (H, W), out=buf["lab"][k])
-            out[i0:i0 + n].copy_(buf["lab"][k][:n], non_blocking=True)
-    cs.synchronize()
-    return out.numpy().copy()
+    # page-lock the caller's volume for the duration of the call: the slices then go host -> device straight from it (no
+    # staging memcpy); if registration is refused the pinned staging buffers are used
+    vol_t = torch.from_numpy(image)
+    rt = torch.cuda.cudart()
+    registered = REGISTER_VOLUME and int(rt.cudaHostRegister(vol_t.data_ptr(), vol_t.numel() * 4, 0)) == 0
+    try:
+        with torch.cuda.stream(cs), torch.no_grad():
+            for bi, i0 in enumerate(range(0, len(idx), Bt)):
+                sl = idx[i0:i0 + Bt]
+                n = len(sl)
+                k = bi % 2
+                slot = engine.slots[k]
+                src = vol_t[sl[0]:sl[-1] + 1]
+                if not registered:
+                    buf["ev"][k].synchronize()                       # the pinned staging buffer of this parity is free again
+                    buf["host_in"][k][:n].copy_(src)
+                    src = buf["host_in"][k][:n]
+                buf["raw"][k][:n].copy_(src, non_blocking=True)
+                buf["ev"][k].record(cs)
+                ops.zoom_cubic(buf["raw"][k][:n], (P, P), out=slot["x"], work=buf["work"])
+                slot["graph"].replay()
+                ops.zoom_nearest_u8(slot["y"][:n].contiguous(), (H, W), out=buf["lab"][k])
+                out[i0:i0 + n].copy_(buf["lab"][k][:n], non_blocking=True)
+        cs.synchronize()
+    finally:
+        if registered:
+            cs.synchronize()
+            rt.cudaHostUnregister(vol_t.data_ptr())
+    return out.numpy()                                               # (a view of the pinned result buffer: no extra copy)
 
 
 def predict_volume(engine: "SliceEngine", image, order_in: int = 3, shard: Optional[Tuple[int, int]] = None,
