@@ -122,6 +122,41 @@ def _side_stream(device) -> "torch.cuda.Stream":
     return s
 
 
+# Off by default: measured 6.03 vs 6.05 ms per train step — the wgrad CTA (4-stage ring, up to 193 KB of shared memory) and the
+# dgrad Linear's CTAs do not fit on one SM together, so the two kernels take turns instead of overlapping, and the fork / join
+# breaks the programmatic-dependent-launch chain of the main stream.  Needs a 2-stage wgrad ring to pay off.
+WGRAD_SIDE_STREAM = _os.environ.get("CSWIN_WGRAD_SIDE_STREAM", "0") == "1"
+
+
+class _Fork:
+    """Runs the weight-gradient kernel(s) of a Linear on the second stream while the data-gradient GEMM runs on the main one: both
+    need only dZ, neither fills the GPU for long (<= 1 wave each), and the optimizer / all-reduce are the only consumers of dW.
+    `with _Fork(t) as f:` enqueues on the side stream after everything already enqueued on the main stream; `f.join()` makes the
+    main stream wait for it (before ZeroPool.commit: an all-reduce may start right after)."""
+
+    def __init__(self, like: Tensor, enabled: bool = True):
+        self.on = enabled and WGRAD_SIDE_STREAM and like.is_cuda and like.dtype == torch.bfloat16
+        self.side = self.cur = None
+
+    def __enter__(self):
+        if self.on:
+            self.cur = torch.cuda.current_stream()
+            self.side = _side_stream(self.cur.device)
+            self.side.wait_stream(self.cur)
+            self._ctx = torch.cuda.stream(self.side)
+            self._ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self.on:
+            self._ctx.__exit__(*exc)
+        return False
+
+    def join(self) -> None:
+        if self.on:
+            self.cur.wait_stream(self.side)
+
+
 class LayerNormFn(Function):
     @staticmethod
     def forward(ctx, x, gamma, beta, eps):
@@ -191,7 +226,17 @@ class LinearFn(Function):
         dz = dout if ss is None else ops.act_bwd(dout, None, ss, ctx.rps, act=0)
         K1 = a.shape[-1]
         N, K = wc.shape
-        need = ctx.needs_input_grad                                # dA = dZ @ W: a forward Linear that reads W (N, K) as (K', N')
+        need = ctx.needs_input_grad
+        dw = db = dwf = dbf = None
+        fk = None
+        if need[1] or need[2]:                                     # dW on the second stream, next to dA below
+            dwf = _zeros((N, K), dz.device)
+            dbf = _zeros((N,), dz.device) if ctx.has_bias else None
+            with _Fork(dz) as fk:
+                ops.linear_wgrad(dz, a, dwf[:, :K1], dbf)
+                if a2 is not None:
+                    ops.linear_wgrad(dz, a2, dwf[:, K1:], None)
+        # dA = dZ @ W: a forward Linear that reads W (N, K) in place as (K', N')
         if _DGRAD_TRANSPOSE:                                       # A/B switch: materialise W^T instead
             wt = wc.t().contiguous()
             da = ops.linear(dz, wt[:K1]) if need[0] else None
@@ -199,13 +244,8 @@ class LinearFn(Function):
         else:
             da = ops.linear(dz, wc[:, :K1], w_kn=True) if need[0] else None
             da2 = ops.linear(dz, wc[:, K1:], w_kn=True) if (a2 is not None and need[3]) else None
-        dw = db = None
-        if need[1] or need[2]:
-            dwf = _zeros((N, K), dz.device)
-            dbf = _zeros((N,), dz.device) if ctx.has_bias else None
-            ops.linear_wgrad(dz, a, dwf[:, :K1], dbf)
-            if a2 is not None:
-                ops.linear_wgrad(dz, a2, dwf[:, K1:], None)
+        if fk is not None:
+            fk.join()
             dw = dwf.to(ctx.wd)
             db = dbf.to(ctx.bd) if ctx.has_bias else None
             _commit()
@@ -236,11 +276,14 @@ class MlpFn(Function):
         dout = _tma_rows(dout)
         dz2 = dout if ss is None else ops.act_bwd(dout, None, ss, ctx.rps, act=0)
         dw2f, db2f = _zeros(tuple(w2c.shape), dout.device), _zeros((w2c.shape[0],), dout.device)
-        ops.linear_wgrad(dz2, h, dw2f, db2f)
+        with _Fork(dz2) as f2:                                           # the weight gradients run on the second stream,
+            ops.linear_wgrad(dz2, h, dw2f, db2f)                         # next to the data-gradient GEMMs
         dz = ops.linear(dz2, w2c, w_kn=True, act=2, residual=z)          # dH o GELU'(z)
         dw1f, db1f = _zeros(tuple(w1c.shape), dout.device), _zeros((w1c.shape[0],), dout.device)
-        ops.linear_wgrad(dz, u, dw1f, db1f)
+        with _Fork(dz) as f1:
+            ops.linear_wgrad(dz, u, dw1f, db1f)
         du = ops.linear(dz, w1c, w_kn=True) if ctx.needs_input_grad[0] else None
+        f2.join(); f1.join()
         _commit()
         d = ctx.dts
         return du, dw1f.to(d[0]), db1f.to(d[1]), dw2f.to(d[2]), db2f.to(d[3]), (dout if ctx.has_res else None), None, None
