@@ -124,7 +124,8 @@ def _side_stream(device) -> "torch.cuda.Stream":
 
 # Off by default: measured 6.03 vs 6.05 ms per train step — the wgrad CTA (4-stage ring, up to 193 KB of shared memory) and the
 # dgrad Linear's CTAs do not fit on one SM together, so the two kernels take turns instead of overlapping, and the fork / join
-# breaks the programmatic-dependent-launch chain of the main stream.  Needs a 2-stage wgrad ring to pay off.
+# breaks the programmatic-dependent-launch chain of the main stream.  A 2-stage wgrad ring (97 KB, -DCSWIN_WGRAD_STAGES=2) does
+# overlap, but is itself 0.33 ms per step slower: 6.07 ms with the fork vs 6.37 ms without, i.e. no net gain either.
 WGRAD_SIDE_STREAM = _os.environ.get("CSWIN_WGRAD_SIDE_STREAM", "0") == "1"
 
 

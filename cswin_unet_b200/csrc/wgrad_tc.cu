@@ -21,7 +21,10 @@ using namespace tc;
 
 constexpr int TN = 128;           // n rows per tile (UMMA M)
 constexpr int MB = 64;            // m rows per pipeline block
-constexpr int kWStages = 4;
+#ifndef CSWIN_WGRAD_STAGES
+#define CSWIN_WGRAD_STAGES 4             // TMA ring depth (2 leaves room for a second kernel's CTA on the SM: see autograd._Fork)
+#endif
+constexpr int kWStages = CSWIN_WGRAD_STAGES;
 constexpr int kWThreads = 192;    // warp 0 TMA, warp 1 MMA + TMEM, warps 2..5 epilogue
 
 struct alignas(64) WgradParams {
