@@ -838,7 +838,7 @@ int lepe_attention_bwd_tc(const cswin_lepe_branch_grad_t* gs, int nb, int B, int
   if (nb == 1) P.br[1] = P.br[0];
   P.total_tiles = tiles;
   // persistent grid: 2 CTAs per SM; rounded down to a multiple of the tile period of the heads, so that the tiles a CTA
-  // walks (stride = grid) keep their heads and the d w / d b partial sums leave the CTA once
+  // walks (stride = grid) keep their heads and the LePE weights are staged once per CTA
   int grid = tiles;
   const int cap = 2 * sm_count();
   if (tiles > cap) {

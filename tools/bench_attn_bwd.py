@@ -17,7 +17,7 @@ B = int(sys.argv[1]) if len(sys.argv) > 1 else 24
 STAGES = [(64, 56, 2, 1, False), (128, 28, 4, 2, False), (256, 14, 8, 7, False), (512, 7, 16, 7, True)]
 if len(sys.argv) > 2 and sys.argv[2] == "512":          # 512^2 configuration, split [1,2,8,8]
     STAGES = [(64, 128, 2, 1, False), (128, 64, 4, 2, False), (256, 32, 8, 8, False), (512, 16, 16, 8, True)]
-NAMES = ["entry", "prologue", "S/dP ready", "P,dS published", "lepe dv done", "dw/db done", "dQ/dK/dV ready", "exit"]
+NAMES = ["entry", "prologue", "S/dP ready", "P,dS published", "lepe dv done", "(unused)", "dQ/dK/dV ready", "exit"]
 
 for si, (C, reso, heads, split, last) in enumerate(STAGES):
     blk = cw.CSWinBlock(dim=C, reso=reso, num_heads=heads, split_size=split, qkv_bias=True, last_stage=last).cuda().train()
