@@ -466,7 +466,7 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU-oracle work for cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the train-step leg")
-    ap.add_argument("--train-timeout", type=float, default=240.0, help="seconds before a stalled train-step leg is abandoned")
+    ap.add_argument("--train-timeout", type=float, default=150.0, help="seconds before a stalled train-step leg is abandoned")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
     if args.impl == "reference":
