@@ -61,6 +61,10 @@ void cswin_debug_set_trace(void* device_buffer);
  *
  * For every batch b, window (ih,iw), head g:   out = softmax(scale * q k^T) v + dwconv3x3_windowpad(v) + bias
  * q/k/v point at element (b=0, token=0, first channel of the branch); token t = y*reso + x.
+ *
+ * Kernel envelope (bf16): head_dim 32, 16-byte aligned rows and windows of N = H_sp*W_sp <= 128 tokens run on the tcgen05
+ * kernels; 128 < N <= 256 on their wide variants (forward additionally needs 128 % W_sp == 0); anything else — and every fp32
+ * call — on the general SIMT kernels (same results, slower).  Nothing is refused for its shape.
  * ------------------------------------------------------------------------------------------------ */
 typedef struct {
   const void* q; const void* k; const void* v;
