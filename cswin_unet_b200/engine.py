@@ -64,6 +64,7 @@ class SliceEngine:
                 pool = g.pool()
                 slot["graph"] = g
         self._n = 0
+        self._resample_bufs = {}                                 # (H, W) -> device / pinned buffers of predict_volume(resample='gpu')
 
     # ---- one batch ------------------------------------------------------------------------------------
     def _submit(self, host_x: Tensor) -> dict:
@@ -126,7 +127,7 @@ def _predict_volume_gpu(engine: "SliceEngine", image, rng: range):
     P, Bt = engine.size, engine.batch
     dev = engine.device
     key = (H, W)
-    buf = engine.__dict__.setdefault("_resample_bufs", {}).get(key)
+    buf = engine._resample_bufs.get(key)
     if buf is None:
         with torch.cuda.device(dev):
             buf = {"raw": [torch.empty((Bt, H, W), dtype=torch.float32, device=dev) for _ in range(2)],
