@@ -48,8 +48,8 @@ int main(void) {
   printf("%zu %zu %zu %zu %zu %zu\n", sizeof(cswin_lepe_branch_t), offsetof(cswin_lepe_branch_t, lse),
          offsetof(cswin_lepe_branch_t, W_sp), sizeof(cswin_lepe_branch_grad_t), offsetof(cswin_lepe_branch_grad_t, dconv_b),
          sizeof(cswin_linear_args_t));
-  printf("%zu %zu %zu\n", offsetof(cswin_linear_args_t, ln_eps), offsetof(cswin_linear_args_t, rows_per_sample),
-         offsetof(cswin_linear_args_t, stats_out));
+  printf("%zu %zu %zu %zu %zu\n", offsetof(cswin_linear_args_t, ln_eps), offsetof(cswin_linear_args_t, rows_per_sample),
+         offsetof(cswin_linear_args_t, stats_out), offsetof(cswin_linear_args_t, aux_out), offsetof(cswin_linear_args_t, ld_aux));
   return 0;
 }'''
     with tempfile.TemporaryDirectory() as d:
@@ -60,7 +60,7 @@ int main(void) {
     got = [int(v) for v in out]
     B, G, L = _lib.LepeBranch, _lib.LepeBranchGrad, _lib.LinearArgs
     want = [ctypes.sizeof(B), B.lse.offset, B.W_sp.offset, ctypes.sizeof(G), G.dconv_b.offset, ctypes.sizeof(L),
-            L.ln_eps.offset, L.rows_per_sample.offset, L.stats_out.offset]
+            L.ln_eps.offset, L.rows_per_sample.offset, L.stats_out.offset, L.aux_out.offset, L.ld_aux.offset]
     assert got == want
 
 

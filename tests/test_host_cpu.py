@@ -128,3 +128,38 @@ def test_drop_path_plan_batches_the_draws_of_a_step():
         assert o is not None and abs((o > 0).float().mean().item() - 0.75) < 0.04
     finally:
         modules.DROP_PATH_PLAN = None
+
+
+def test_bench_reference_arm_prints_one_contract_line():
+    """`bench.py --impl reference` (the CPU port of the reference path, rank 0 only) prints exactly one JSON line with the keys
+    of the bench contract; library chatter on stdout is diverted to stderr."""
+    import json, os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, out.stdout
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["unit"] == "slices/s" and d["value"] > 0 and d["vs_baseline"] is None
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and "workload" in d["config"]
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    # other ranks of a torchrun launch exit 0 without work and without output
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    o2 = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2"], capture_output=True,
+                        text=True, timeout=600, cwd=root, env=env)
+    assert o2.returncode == 0 and o2.stdout.strip() == ""
+
+
+def test_bench_native_arm_refuses_to_run_without_a_gpu():
+    """No CPU fallback: the native arm must fail loudly where there is no CUDA device (this container)."""
+    import os, subprocess, sys
+    import torch
+    if torch.cuda.is_available():
+        return
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "1"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode != 0 and "CUDA" in (out.stderr + out.stdout)
