@@ -90,12 +90,16 @@ def load_synth(module: torch.nn.Module, prefix: str, seed: int):
 
 # extra LePE configs beyond T224: small / 512^2-like / odd head dims
 LEPE_EXTRA = ((32, 16, 0, 2, 1), (64, 16, 1, 2, 2), (64, 8, -1, 8, 2), (128, 16, 0, 8, 4), (48, 12, 1, 3, 3))
+# BASELINE configs[4] (512^2, split [1,2,8,8]): stripe windows of 256 tokens (32x8, 8x32, 16x16), ragged 192 (24x8) and 196 (14x14)
+LEPE_WIDE = ((128, 32, 0, 8, 4), (128, 32, 1, 8, 4), (512, 16, -1, 8, 16), (64, 24, 0, 8, 2), (64, 14, -1, 14, 2))
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--ref", default="/root/reference")
+    ap.add_argument("--only", default="", help="comma-separated groups to (re)write: lepe_t224, lepe_extra, lepe_wide, rest; default all")
     args = ap.parse_args()
+    only = set(filter(None, args.only.split(",")))
     install_shims()
     sys.path.insert(0, args.ref)
     torch.set_grad_enabled(True)
@@ -103,7 +107,9 @@ def main():
     import networks.cswin_unet as ref          # the unmodified reference
 
     # ---------------- LePEAttention forward + backward ----------------
-    for tag, cfgs, B in (("t224", synth.LEPE_CONFIGS_T224, 1), ("extra", LEPE_EXTRA, 2)):
+    for tag, cfgs, B in (("t224", synth.LEPE_CONFIGS_T224, 1), ("extra", LEPE_EXTRA, 2), ("wide", LEPE_WIDE, 1)):
+        if only and f"lepe_{tag}" not in only:
+            continue
         out = {}
         for (cb, reso, idx, split, heads) in cfgs:
             m = ref.LePEAttention(cb, resolution=reso, idx=idx, split_size=split, num_heads=heads).double()
@@ -123,6 +129,8 @@ def main():
             out[key + "_db"] = pack(gbias.reshape(1, cb))
         save(f"lepe_{tag}", **out)
 
+    if only and "rest" not in only:
+        return
     # ---------------- CSWinBlock forward (one per stage) ----------------
     out = {}
     for (dim, reso, heads, split, last) in ((64, 56, 2, 1, False), (128, 28, 4, 2, False), (256, 14, 8, 7, False), (512, 7, 16, 7, True)):

@@ -14,6 +14,8 @@ from tests import golden_util as G
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
 LEPE_EXTRA = ((32, 16, 0, 2, 1), (64, 16, 1, 2, 2), (64, 8, -1, 8, 2), (128, 16, 0, 8, 4), (48, 12, 1, 3, 3))
+# BASELINE configs[4] (512^2) windows with golden vectors from the unmodified reference (tests/golden/lepe_wide.npz)
+LEPE_WIDE_GOLD = ((128, 32, 0, 8, 4), (128, 32, 1, 8, 4), (512, 16, -1, 8, 16), (64, 24, 0, 8, 2), (64, 14, -1, 14, 2))
 
 
 def T(a, dtype=torch.float32, device=DEV):
@@ -30,7 +32,7 @@ def cos(a, b):
     return float((a @ b) / (a.norm() * b.norm()).clamp_min(1e-30))
 
 
-@pytest.mark.parametrize("tag,cfgs,B", [("t224", synth.LEPE_CONFIGS_T224, 1), ("extra", LEPE_EXTRA, 2)])
+@pytest.mark.parametrize("tag,cfgs,B", [("t224", synth.LEPE_CONFIGS_T224, 1), ("extra", LEPE_EXTRA, 2), ("wide", LEPE_WIDE_GOLD, 1)])
 def test_lepe_attention_backward_fp32_vs_reference_autograd(tag, cfgs, B):
     z = G.load(f"lepe_{tag}")
     for (cb, reso, idx, split, heads) in cfgs:

@@ -23,9 +23,11 @@ def lepe_inputs(cb, reso, idx, B, dtype=torch.float64):
 
 
 LEPE_EXTRA = ((32, 16, 0, 2, 1), (64, 16, 1, 2, 2), (64, 8, -1, 8, 2), (128, 16, 0, 8, 4), (48, 12, 1, 3, 3))
+# BASELINE configs[4] (512^2): 256-token stripe windows, ragged 192- and 196-token ones (tests/golden/lepe_wide.npz)
+LEPE_WIDE = ((128, 32, 0, 8, 4), (128, 32, 1, 8, 4), (512, 16, -1, 8, 16), (64, 24, 0, 8, 2), (64, 14, -1, 14, 2))
 
 
-@pytest.mark.parametrize("tag,cfgs,B", [("t224", synth.LEPE_CONFIGS_T224, 1), ("extra", LEPE_EXTRA, 2)])
+@pytest.mark.parametrize("tag,cfgs,B", [("t224", synth.LEPE_CONFIGS_T224, 1), ("extra", LEPE_EXTRA, 2), ("wide", LEPE_WIDE, 1)])
 def test_lepe_attention_vectorised_matches_reference(tag, cfgs, B):
     z = G.load(f"lepe_{tag}")
     for (cb, reso, idx, split, heads) in cfgs:
@@ -43,11 +45,12 @@ def test_lepe_attention_loops_matches_reference():
         G.compare(z, f"c{cb}_r{reso}_i{idx}_s{split}_h{heads}", y, atol=2e-6)
 
 
-def test_lepe_attention_backward_via_autograd_matches_reference():
+@pytest.mark.parametrize("tag,cfgs,B", [("extra", LEPE_EXTRA, 2), ("wide", LEPE_WIDE, 1)])
+def test_lepe_attention_backward_via_autograd_matches_reference(tag, cfgs, B):
     """The oracle's autograd is the truth for the CUDA backward; pin it to the reference's autograd."""
-    z = G.load("lepe_extra")
-    for (cb, reso, idx, split, heads) in LEPE_EXTRA:
-        qkv, w, b = lepe_inputs(cb, reso, idx, 2)
+    z = G.load(f"lepe_{tag}")
+    for (cb, reso, idx, split, heads) in cfgs:
+        qkv, w, b = lepe_inputs(cb, reso, idx, B)
         q, k, v = (t.clone().requires_grad_(True) for t in qkv)
         w = w.requires_grad_(True); b = b.requires_grad_(True)
         y = O.lepe_attention(q, k, v, w, b, reso, idx, split, heads)
