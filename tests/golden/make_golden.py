@@ -129,6 +129,20 @@ def main():
             out[key + "_db"] = pack(gbias.reshape(1, cb))
         save(f"lepe_{tag}", **out)
 
+    if not only or "model_512" in only:
+        # ---------------- whole model, BASELINE configs[4]: 512^2 input, 3 classes, split [1,2,8,8] ----------------
+        m512 = ref.CSWinTransformer(img_size=512, patch_size=4, in_chans=3, num_classes=3, embed_dim=64,
+                                    depth=[1, 2, 9, 1], split_size=[1, 2, 8, 8], num_heads=[2, 4, 8, 16],
+                                    mlp_ratio=4., qkv_bias=True, qk_scale=None, drop_rate=0., drop_path_rate=0.2).eval()
+        shapes512 = {k: tuple(v.shape) for k, v in m512.state_dict().items()}
+        m512.load_state_dict({k: T(v) for k, v in synth.synth_state_dict(shapes512, seed=1234).items()}, strict=True)
+        x = T(synth.synth_image_batch(1, 3, 512, seed=0, kind="ct"))
+        with torch.no_grad():
+            logits64 = m512.double()(x.double())
+        out = {"logits_ct": pack(logits64.permute(0, 2, 3, 1), stride_if_big=37),       # rows = pixels, 3 classes
+               "argmax_ct": logits64.argmax(1).to(torch.uint8).numpy(),
+               "key_shapes": np.array([k + ":" + ",".join(map(str, v)) for k, v in shapes512.items()])}
+        save("model_512", **out)
     if only and "rest" not in only:
         return
     # ---------------- CSWinBlock forward (one per stage) ----------------

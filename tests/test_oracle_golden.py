@@ -155,3 +155,19 @@ def test_zoom_oracle_is_scipy_bit_for_bit():
         lab = (rng.random((P, P)) * 9).astype(np.uint8)
         ref = zoom(lab, (H / P, W / P), order=0)
         assert np.array_equal(Z.zoom_nearest(lab, (Z.out_len(P, H / P), Z.out_len(P, W / P))), ref)
+
+
+def test_full_model_512px_config_matches_reference():
+    """BASELINE configs[4]: the oracle's model forward at 512^2 (3 classes, split [1,2,8,8]: 128- and 256-token stripe windows)
+    against the unmodified reference (tests/golden/model_512.npz), fp64."""
+    z = G.load("model_512")
+    cfg = O.OracleConfig(img_size=512, num_classes=3, split_size=(1, 2, 8, 8))
+    shapes = O.state_dict_shapes(cfg)
+    ref_shapes = dict(s.split(":") for s in z["key_shapes"])
+    assert list(shapes) == list(ref_shapes) and all(",".join(map(str, v)) == ref_shapes[k] for k, v in shapes.items())
+    sd = {k: T(v).double() for k, v in synth.synth_state_dict(shapes, seed=1234).items()}
+    x = T(synth.synth_image_batch(1, 3, 512, seed=0, kind="ct")).double()
+    with torch.no_grad():
+        logits = O.cswin_unet_forward(sd, x, cfg)
+    G.compare(z, "logits_ct", logits.permute(0, 2, 3, 1).numpy(), atol=1e-6, rtol=1e-6)
+    assert (logits.argmax(1).numpy() == z["argmax_ct"]).mean() > 0.99999
