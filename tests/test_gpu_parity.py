@@ -617,3 +617,33 @@ def test_predict_volume_gpu_resampling_equals_host_resampling():
     assert agree >= 0.9999
     part = cw.predict_volume(eng, vol, shard=(1, 2), resample="gpu")
     assert np.array_equal(part[0], gpu[list(part[1])])
+
+
+def test_full_model_512px_config_logits_vs_golden():
+    """BASELINE configs[4]: the native model at 512^2 (3 classes, split [1,2,8,8]) against the unmodified reference's logits
+    (tests/golden/model_512.npz): fp32 <= 1e-4 and argmax agreement; the bf16 forward (wide tcgen05 attention kernels) is run
+    and reported against the same vectors."""
+    z = G.load("model_512")
+    m = cw.cswin_tiny_224(num_classes=3, img_size=512, split_size=[1, 2, 8, 8]).eval()
+    shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in synth.synth_state_dict(shapes, seed=1234).items()}, strict=True)
+    m = m.to(DEV)
+    x = T(synth.synth_image_batch(1, 3, 512, seed=0, kind="ct"))
+    with torch.no_grad():
+        logits = m(x)
+        m.compute_dtype = torch.bfloat16
+        t0 = cw.tc_launch_count()
+        l16 = m(x).float()
+        n_tc = cw.tc_launch_count() - t0
+    assert logits.shape == (1, 3, 512, 512) and logits.dtype == torch.float32
+    err = G.compare(z, "logits_ct", logits.permute(0, 2, 3, 1).cpu().numpy(), atol=1e-4)
+    agree = (logits.argmax(1).cpu().numpy() == z["argmax_ct"]).mean()
+    a16 = (l16.argmax(1).cpu().numpy() == z["argmax_ct"]).mean()
+    e16 = (l16 - logits).abs().max().item()
+    print(f"[512px fp32] max-abs {err:.2e} argmax agreement {agree:.6f}; [bf16] max-abs vs fp32 {e16:.2e}, argmax agreement {a16:.6f}, "
+          f"{n_tc} tcgen05 launches")
+    assert agree >= 0.999
+    # bf16 numbers are reported only: with these "alive" synthetic weights and 3 classes the argmax of a smooth input sits on
+    # near-ties (the bf16 criteria of the north star are asserted on the reference-init T224 model above, and the 512^2 bf16
+    # kernels block by block in test_512px_config_blocks_* / test_lepe_attention_bf16_wide_windows_on_tcgen05)
+    assert torch.isfinite(l16).all()
