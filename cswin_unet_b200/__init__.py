@@ -11,8 +11,8 @@ from .install import install, uninstall  # noqa: F401
 from .model import CSWinTransformer, CSwinUnet, cswin_tiny_224  # noqa: F401
 from .train import TrainStep, seg_loss  # noqa: F401
 from .modules import (CARAFE, CARAFE4, CSWinBlock, DropPath, LePEAttention, Merge_Block, Mlp,  # noqa: F401
-                      img2windows, windows2img)
+                      bump_param_epoch as invalidate_weight_caches, img2windows, windows2img)
 
 __all__ = ["LePEAttention", "CSWinBlock", "Mlp", "Merge_Block", "CARAFE", "CARAFE4", "DropPath", "img2windows",
            "windows2img", "CSWinTransformer", "CSwinUnet", "cswin_tiny_224", "SliceEngine", "shard_slices", "predict_volume", "TrainStep", "seg_loss", "install", "uninstall", "build", "lib",
-           "launch_count", "tc_launch_count", "CswinError", "synth"]
+           "launch_count", "tc_launch_count", "CswinError", "synth", "invalidate_weight_caches"]

@@ -442,24 +442,36 @@ class CarafeHeadFn(Function):
 
 
 class SegLossFn(Function):
-    """w_ce * CE + w_dice * Dice(softmax) on fp32 NCHW logits (trainer.py:55-57, utils.py:9-45): one native pass each way."""
+    """w_ce * CE + w_dice * Dice(softmax) on fp32 NCHW logits (trainer.py:55-57, utils.py:9-45): one native pass each way.
+
+    `group` (a torch.distributed group, or True for the default group) selects the reference's GLOBAL-batch Dice: the
+    reference's nn.DataParallel gathers the logits and forms Dice — a ratio of sums — over the whole batch (trainer.py:37-38,
+    :55-57), so the 3 x classes Dice sums are all-reduced between the two passes (one tiny collective, capturable) and the
+    Dice part of the local gradient is scaled by the world size (the gradient all-reduce AVERAGES over ranks, while the global
+    Dice gradient is the SUM of the per-rank contributions).  CE is a mean over local pixels, which averages correctly."""
 
     @staticmethod
-    def forward(ctx, logits, labels, w_ce, w_dice):
+    def forward(ctx, logits, labels, w_ce, w_dice, group=None):
         sums = ops.seg_loss_fwd(logits, labels)
         nc = logits.shape[1]
         npix = labels.numel()
+        world = 1
+        if group is not None and torch.distributed.is_initialized():
+            g = None if group is True else group
+            world = torch.distributed.get_world_size(g)
+            if world > 1:
+                torch.distributed.all_reduce(sums[1:], op=torch.distributed.ReduceOp.SUM, group=g)
         inter, z, y = sums[1:1 + nc], sums[1 + nc:1 + 2 * nc], sums[1 + 2 * nc:1 + 3 * nc]
         loss = w_ce * sums[0] / npix + w_dice * (1.0 - (2 * inter + 1e-5) / (z + y + 1e-5)).mean()
         ctx.save_for_backward(logits, labels, sums)
-        ctx.w = (w_ce, w_dice)
+        ctx.w = (w_ce, w_dice * world)
         return loss
 
     @staticmethod
     @once_differentiable
     def backward(ctx, gout):
         logits, labels, sums = ctx.saved_tensors
-        return ops.seg_loss_bwd(logits, labels, sums, gout, *ctx.w), None, None, None
+        return ops.seg_loss_bwd(logits, labels, sums, gout, *ctx.w), None, None, None, None
 
 
 def linear(a, w, bias=None, a2=None, residual=None, sample_scale=None, rps=0):

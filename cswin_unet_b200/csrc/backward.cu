@@ -48,18 +48,8 @@ __global__ void __launch_bounds__(256) act_fwd_kernel(const T* __restrict__ z, i
 }
 
 // bf16, contiguous rows (ld == N), N % 8 == 0: 16-byte vectors, 8 elements per thread
-// bf16 path: Phi(x) from the same tanh-form fit as tc::gelu_fast (|dPhi| <= 6.6e-6), phi(x) through ex2.approx — two MUFU and
-// ~9 FMA-pipe instructions instead of erff's ~40; the error is far below the bf16 resolution of the product it scales
-__device__ __forceinline__ float gelu_grad_fast(float x) {
-  const float x2 = x * x;
-  float p = fmaf(x2, -1.36882761e-05f, -1.94451094e-04f);
-  p = fmaf(p, x2, 3.65466544e-02f);
-  p = fmaf(p, x2, 7.97820264e-01f);
-  float t, e;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(p * x));
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x2 * -0.72134752044448170368f));
-  return fmaf(x * 0.39894228040143267794f, e, fmaf(0.5f, t, 0.5f));
-}
+// bf16 path: GELU'(x) = tc::gelu_grad_fast (clamped tanh-form fit of Phi + ex2.approx for phi; tc_common.cuh)
+using tc::gelu_grad_fast;
 __global__ void __launch_bounds__(256) act_bwd_bf16_vec_kernel(const uint4* __restrict__ dout, const uint4* __restrict__ z,
                                                                 const float* __restrict__ sscale, int64_t elems_per_sample,
                                                                 uint4* __restrict__ dz, int64_t nvec, int act) {

@@ -55,19 +55,9 @@ struct alignas(64) GemmTcParams {
   unsigned long long* trace;
 };
 
-// GELU'(x) for a packed pair, same fit as the streaming activation kernels (backward.cu gelu_grad_fast)
-__device__ __forceinline__ float gelu_grad_fast1(float x) {
-  const float x2 = x * x;
-  float p = fmaf(x2, -1.36882761e-05f, -1.94451094e-04f);
-  p = fmaf(p, x2, 3.65466544e-02f);
-  p = fmaf(p, x2, 7.97820264e-01f);
-  float t, e;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(p * x));
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x2 * -0.72134752044448170368f));
-  return fmaf(x * 0.39894228040143267794f, e, fmaf(0.5f, t, 0.5f));
-}
+// GELU'(x) for a packed pair: tc::gelu_grad_fast (clamped fit, shared with the streaming activation kernels in backward.cu)
 __device__ __forceinline__ float2 gelu_grad_pair(uint32_t zz) {
-  return make_float2(gelu_grad_fast1(bf16_lo(zz)), gelu_grad_fast1(bf16_hi(zz)));
+  return make_float2(gelu_grad_fast(bf16_lo(zz)), gelu_grad_fast(bf16_hi(zz)));
 }
 
 // kTrain adds the two training-only epilogues (TMA-store fast path only):

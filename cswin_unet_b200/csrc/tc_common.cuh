@@ -200,19 +200,33 @@ __device__ __forceinline__ uint32_t add_bf16x2(uint32_t a, uint32_t b) {
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
 
-// GELU(erf) for the bf16 epilogue: x * Phi(x) with Phi(x) = 0.5 (1 + tanh(x (c0 + c1 x^2 + c2 x^4 + c3 x^6))), the odd
-// degree-7 minimax fit of atanh(erf(x / sqrt 2)) (max |dPhi| = 6.6e-6, max |dGELU| = 2.4e-5 over all x) evaluated with one
-// MUFU op (tanh.approx, relative error 2^-11): total error <= 2.5e-4 |x|, i.e. >= 16x below bf16 resolution, for
-// 7 FMA-pipe instructions + 1 MUFU instead of erff's ~40.  The fp32 SIMT path keeps erff.
+// GELU(erf) for the bf16 epilogue: x * Phi(x) with Phi(x) = 0.5 (1 + tanh(u (c0 + c1 u^2 + c2 u^4 + c3 u^6))), u = clamp(x, +-5.5):
+// the odd degree-7 minimax fit of atanh(erf(x / sqrt 2)) (max |dPhi| = 6.6e-6, max |dGELU| = 2.4e-5 for ALL x once the argument
+// is clamped — the raw polynomial turns over near |x| = 7.3, so it must never see larger arguments) evaluated with one MUFU
+// op (tanh.approx, error 2^-11): total error <= 2.5e-4 |x| for x >= -5.5, i.e. >= 16x below bf16 resolution; below -5.5 the
+// result is exactly 0 (true value > -1.1e-7) so the tanh error is not multiplied by a large |x|.  The fp32 SIMT path keeps erff.
+constexpr float kGeluClamp = 5.5f;
+__device__ __forceinline__ float gelu_tanh_arg(float x) {          // argument of the tanh in Phi(x); shared with GELU'
+  const float u = fminf(fmaxf(x, -kGeluClamp), kGeluClamp);
+  const float u2 = u * u;
+  float p = fmaf(u2, -1.36882761e-05f, -1.94451094e-04f);
+  p = fmaf(p, u2, 3.65466544e-02f);
+  p = fmaf(p, u2, 7.97820264e-01f);
+  return p * u;
+}
 __device__ __forceinline__ float gelu_fast(float x) {
-  const float x2 = x * x;
-  float p = fmaf(x2, -1.36882761e-05f, -1.94451094e-04f);
-  p = fmaf(p, x2, 3.65466544e-02f);
-  p = fmaf(p, x2, 7.97820264e-01f);
   float t;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(p * x));
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(gelu_tanh_arg(x)));
   const float h = 0.5f * x;
-  return fmaf(h, t, h);
+  return x < -kGeluClamp ? 0.f : fmaf(h, t, h);
+}
+// GELU'(x) = Phi(x) + x phi(x): Phi from the same fit, phi through ex2.approx (two MUFU + ~11 FMA-pipe instructions)
+__device__ __forceinline__ float gelu_grad_fast(float x) {
+  float t, e;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(gelu_tanh_arg(x)));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * x * -0.72134752044448170368f));
+  const float Phi = x < -kGeluClamp ? 0.f : fmaf(0.5f, t, 0.5f);
+  return fmaf(x * 0.39894228040143267794f, e, Phi);
 }
 
 // ---- packed fp32 pairs (Blackwell FFMA2 / FADD2 / FMUL2: two fp32 operations per issue slot) ----
@@ -234,18 +248,22 @@ __device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
       : "l"(reinterpret_cast<const uint64_t&>(a)), "l"(reinterpret_cast<const uint64_t&>(b)));
   return d;
 }
-// gelu_fast on a pair: 7 packed FP instructions + 2 MUFU for two elements
+// gelu_fast on a pair: packed FP instructions + 2 MUFU for two elements (same clamp / saturation as gelu_fast)
 __device__ __forceinline__ float2 gelu_fast2(float2 x) {
-  const float2 x2 = fmul2(x, x);
-  float2 p = ffma2(x2, make_float2(-1.36882761e-05f, -1.36882761e-05f), make_float2(-1.94451094e-04f, -1.94451094e-04f));
-  p = ffma2(p, x2, make_float2(3.65466544e-02f, 3.65466544e-02f));
-  p = ffma2(p, x2, make_float2(7.97820264e-01f, 7.97820264e-01f));
-  const float2 u = fmul2(p, x);
+  const float2 u = make_float2(fminf(fmaxf(x.x, -kGeluClamp), kGeluClamp), fminf(fmaxf(x.y, -kGeluClamp), kGeluClamp));
+  const float2 u2 = fmul2(u, u);
+  float2 p = ffma2(u2, make_float2(-1.36882761e-05f, -1.36882761e-05f), make_float2(-1.94451094e-04f, -1.94451094e-04f));
+  p = ffma2(p, u2, make_float2(3.65466544e-02f, 3.65466544e-02f));
+  p = ffma2(p, u2, make_float2(7.97820264e-01f, 7.97820264e-01f));
+  const float2 a = fmul2(p, u);
   float2 t;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(t.x) : "f"(u.x));
-  asm("tanh.approx.f32 %0, %1;" : "=f"(t.y) : "f"(u.y));
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t.x) : "f"(a.x));
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t.y) : "f"(a.y));
   const float2 h = fmul2(x, make_float2(0.5f, 0.5f));
-  return ffma2(h, t, h);
+  float2 r = ffma2(h, t, h);
+  r.x = x.x < -kGeluClamp ? 0.f : r.x;
+  r.y = x.y < -kGeluClamp ? 0.f : r.y;
+  return r;
 }
 
 // ---- thread-block clusters / distributed shared memory ----

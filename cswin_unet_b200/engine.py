@@ -50,6 +50,21 @@ class SliceEngine:
                         "ev_in": torch.cuda.Event(), "ev_done": torch.cuda.Event(), "ev_out": torch.cuda.Event(),
                         "ev_free": torch.cuda.Event()}
                 self.slots.append(slot)
+        self._n = 0
+        self._resample_bufs = {}                                 # (H, W) -> device / pinned buffers of predict_volume(resample='gpu')
+        self._capture()
+
+    def _weights_signature(self):
+        """(parameter epoch, sum of torch versions): changes whenever the model's weights were written — by the native SGD
+        (raw pointers, modules.bump_param_epoch) or by torch (load_state_dict, optimizers, TPGM's .data.copy_ ...)."""
+        from .modules import param_epoch
+        return param_epoch(), sum(p._version for p in self.model.parameters())
+
+    def _capture(self) -> None:
+        """(Re-)capture the forward graphs.  The graphs bake pointers to weight tensors DERIVED from the parameters (bf16 casts,
+        folded LayerNorm / head matrices): they must be rebuilt when the parameters change, which `refresh_if_stale` does."""
+        torch.cuda.synchronize(self.device)
+        with torch.cuda.device(self.device), torch.no_grad():
             cs = self.streams["compute"]
             cs.wait_stream(torch.cuda.current_stream(self.device))
             with torch.cuda.stream(cs):
@@ -63,11 +78,20 @@ class SliceEngine:
                     slot["y"] = self.model.predict_labels(slot["x"])
                 pool = g.pool()
                 slot["graph"] = g
-        self._n = 0
-        self._resample_bufs = {}                                 # (H, W) -> device / pinned buffers of predict_volume(resample='gpu')
+        self._sig = self._weights_signature()
+
+    def refresh_if_stale(self) -> bool:
+        """Re-capture when the model's weights changed since the graphs were built (train -> validate loops of the reference:
+        universal_train.py:644/868).  Called by every entry point; costs one integer comparison when nothing changed."""
+        if self._weights_signature() == self._sig:
+            return False
+        self.model.eval()
+        self._capture()
+        return True
 
     # ---- one batch ------------------------------------------------------------------------------------
     def _submit(self, host_x: Tensor) -> dict:
+        self.refresh_if_stale()
         slot = self.slots[self._n % 2]
         self._n += 1
         n = host_x.shape[0]
@@ -137,6 +161,7 @@ def _predict_volume_gpu(engine: "SliceEngine", image, rng: range):
                    "ev": [torch.cuda.Event() for _ in range(2)]}
         engine._resample_bufs[key] = buf
     out = torch.empty((len(rng), H, W), dtype=torch.uint8).pin_memory()
+    engine.refresh_if_stale()
     cs = engine.streams["compute"]
     cs.wait_stream(torch.cuda.current_stream(dev))
     idx = list(rng)

@@ -111,6 +111,21 @@ FUSE_MLP_MAX_DIM = int(os.environ.get("CSWIN_FUSE_MLP_MAX_DIM", "64"))
 FOLD_LN = os.environ.get("CSWIN_FOLD_LN", "1") != "0"     # LayerNorm folded into the tcgen05 Linear epilogue (bf16 inference)
 
 
+# Parameters can be written behind torch's back: the native fused SGD (train.TrainStep -> cswin_sgd_momentum_step) updates them
+# through raw pointers and never bumps `param._version`.  Every such writer calls `bump_param_epoch()`; the epoch is part of the
+# cache signature below (and of SliceEngine's captured-graph signature), so derived tensors are re-derived after training.
+_PARAM_EPOCH = [0]
+
+
+def bump_param_epoch() -> int:
+    _PARAM_EPOCH[0] += 1
+    return _PARAM_EPOCH[0]
+
+
+def param_epoch() -> int:
+    return _PARAM_EPOCH[0]
+
+
 class _Derived:
     """Cache of tensors derived from parameters (dtype casts, re-packed conv weights)."""
 
@@ -122,7 +137,7 @@ class _Derived:
             params = (params,)
         if fn is None and params[0].dtype == dtype and params[0].is_contiguous():
             return params[0].detach()                    # read the parameter in place: can never go stale
-        sig = tuple((p._version, p.data_ptr(), p.device) for p in params) + (dtype,)
+        sig = tuple((p._version, p.data_ptr(), p.device) for p in params) + (dtype, _PARAM_EPOCH[0])
         hit = self._d.get(key)
         if not fresh and hit is not None and hit[0] == sig:
             return hit[1]
@@ -146,6 +161,14 @@ class _Native(nn.Module):
 
     def _w(self, key: str, params, dtype, fn=None) -> Tensor:
         return self._derived.get(key, params, dtype, fn, fresh=self.training)
+
+    def train(self, mode: bool = True):
+        # `.data` writes (TPGM: universal_train.py:380-388, 451-453) and raw-pointer optimizers do not bump `_version`; they
+        # happen in training mode, so a train <-> eval switch drops the derived tensors and invalidates captured engines
+        if mode != self.training:
+            self._derived.clear()
+            bump_param_epoch()
+        return super().train(mode)
 
     def __getstate__(self):
         st = self.__dict__.copy()

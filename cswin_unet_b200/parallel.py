@@ -51,9 +51,12 @@ def allreduce_gradients(params: Iterable[Tensor], group=None, bucket_bytes: int 
         for g in bucket:
             views.append(flat[off: off + g.numel()].view(g.shape)); off += g.numel()
         torch._foreach_copy_(views, bucket)
-        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
-        if average:
-            flat.div_(world)
+        if average and flat.is_cuda and dist.get_backend(group) == "nccl":
+            dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=group)       # averaged inside the collective: no div_ launch
+        else:
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+            if average:
+                flat.div_(world)
         torch._foreach_copy_(bucket, views)
         n_coll += 1
     return n_coll
@@ -71,18 +74,30 @@ class PoolGradReducer:
         self.pool, self.group, self.bucket = pool, group, bucket_bytes // 4
         self.world = dist.get_world_size(group)
         self.comm = torch.cuda.Stream() if pool.buf.is_cuda else None     # (CPU / gloo: same logic, no streams — used by the tests)
+        # NCCL averages inside the collective (no per-bucket div_ launch); gloo has no AVG
+        self.avg = pool.buf.is_cuda and dist.get_backend(group) == "nccl"
         self.start = 0
+        self.prev = 0
         self.n_coll = 0
+        self.launched = []                 # [(a, b)] ranges reduced this step (tests / timelines)
 
     def begin(self) -> None:
         self.start = 0
+        self.prev = 0
         self.n_coll = 0
+        self.launched = []
         self.pool.on_commit = self._on_commit
 
     def _on_commit(self, off: int) -> None:
-        if off - self.start >= self.bucket:
-            self._launch(self.start, off)
-            self.start = off
+        # A bucket never includes the range of the node that is committing right now: that node has not returned yet, so
+        # autograd may still read its pool slices on the main stream (AccumulateGrad clones a gradient that reaches its
+        # parameter through a permute / reshape of the weight — Merge_Block, CARAFE.encoder, stem — and `.to(param dtype)`
+        # runs after the commit).  Everything below the PREVIOUS commit's offset has had all of its consumers enqueued: the
+        # engine runs the view-backward and AccumulateGrad nodes of a finished node before the next kernel-bearing node.
+        if self.prev - self.start >= self.bucket:
+            self._launch(self.start, self.prev)
+            self.start = self.prev
+        self.prev = off
 
     def _launch(self, a: int, b: int) -> None:
         seg = self.pool.buf[a:b]
@@ -90,17 +105,22 @@ class PoolGradReducer:
             dist.all_reduce(seg, op=dist.ReduceOp.SUM, group=self.group)
             seg.div_(self.world)
         else:
-            self.comm.wait_stream(torch.cuda.current_stream())     # the kernels that filled [a, b) are already enqueued there
+            self.comm.wait_stream(torch.cuda.current_stream())     # the kernels that filled / read [a, b) are already enqueued there
             with torch.cuda.stream(self.comm):
-                dist.all_reduce(seg, op=dist.ReduceOp.SUM, group=self.group)
-                seg.div_(self.world)
+                if self.avg:
+                    dist.all_reduce(seg, op=dist.ReduceOp.AVG, group=self.group)
+                else:
+                    dist.all_reduce(seg, op=dist.ReduceOp.SUM, group=self.group)
+                    seg.div_(self.world)
         self.n_coll += 1
+        self.launched.append((a, b))
 
     def finish(self) -> None:
+        """After backward() has returned: every consumer of every pool slice is enqueued, reduce the tail and join."""
         self.pool.on_commit = None
         if self.pool.off > self.start:
             self._launch(self.start, self.pool.off)
-            self.start = self.pool.off
+            self.start = self.prev = self.pool.off
         if self.comm is not None:
             torch.cuda.current_stream().wait_stream(self.comm)
 

@@ -27,12 +27,15 @@ Tensor = torch.Tensor
 NATIVE_LOSS = os.environ.get("CSWIN_TORCH_LOSS") != "1"
 
 
-def seg_loss(logits: Tensor, target: Tensor, n_classes: int) -> Tensor:
-    """0.4 * CrossEntropy + 0.6 * DiceLoss(softmax=True)   (trainer.py:55-57, utils.py:9-45)."""
+def seg_loss(logits: Tensor, target: Tensor, n_classes: int, global_dice_group=None) -> Tensor:
+    """0.4 * CrossEntropy + 0.6 * DiceLoss(softmax=True)   (trainer.py:55-57, utils.py:9-45).
+
+    `global_dice_group` (a process group, or True for the default one): form Dice over the GLOBAL batch like the reference's
+    nn.DataParallel does (the Dice sums are all-reduced; see autograd.SegLossFn).  Default None = per-rank Dice."""
     logits = logits.float()
     if (logits.is_cuda and NATIVE_LOSS and ops.seg_loss_supported(n_classes) and logits.shape[1] == n_classes
             and target.dtype in (torch.uint8, torch.int32, torch.int64)):
-        return ag.SegLossFn.apply(logits.contiguous(), target.contiguous(), 0.4, 0.6)   # native: one pass each way
+        return ag.SegLossFn.apply(logits.contiguous(), target.contiguous(), 0.4, 0.6, global_dice_group)   # native: one pass each way
     ce = F.cross_entropy(logits, target.long())
     prob = torch.softmax(logits, dim=1)
     # (F.one_hot validates its input with a host sync, which would break CUDA-graph capture of the step)
@@ -41,7 +44,19 @@ def seg_loss(logits: Tensor, target: Tensor, n_classes: int) -> Tensor:
     inter = (prob * onehot).sum(dims)
     zsum = (prob * prob).sum(dims)
     ysum = onehot.sum(dims)
+    world = 1
+    if global_dice_group is not None and torch.distributed.is_initialized():
+        g = None if global_dice_group is True else global_dice_group
+        world = torch.distributed.get_world_size(g)
+        if world > 1:                                         # other ranks' sums enter as constants (their gradient lives there)
+            packed = torch.stack([inter, zsum, ysum]).detach().clone()
+            torch.distributed.all_reduce(packed, group=g)
+            inter = inter + (packed[0] - inter.detach())
+            zsum = zsum + (packed[1] - zsum.detach())
+            ysum = ysum + (packed[2] - ysum.detach())
     dice = (1.0 - (2 * inter + 1e-5) / (zsum + ysum + 1e-5)).mean()
+    if world > 1:                                             # value unchanged, gradient x world (the all-reduce averages)
+        dice = dice.detach() + world * (dice - dice.detach())
     return 0.4 * ce + 0.6 * dice
 
 
@@ -52,7 +67,10 @@ class TrainStep:
 
     def __init__(self, model, lr: float = 0.05, momentum: float = 0.9, weight_decay: float = 1e-4,
                  compute_dtype: torch.dtype = torch.bfloat16, group=None, graph: bool = True, warmup: int = 3,
-                 batched_drop_path: bool = True):
+                 batched_drop_path: bool = True, global_dice: bool = False, distributed: Optional[bool] = None):
+        """global_dice: Dice over the global batch as the reference's nn.DataParallel computes it (all-reduce of the Dice sums);
+        default = per-rank Dice.  distributed: None = follow torch.distributed; False = never all-reduce (used by the
+        N-rank gradient-parity check to compute per-rank gradients inside an initialised process group)."""
         self.model = model.train()
         self.model.compute_dtype = compute_dtype
         self.n_classes = model.num_classes
@@ -85,6 +103,9 @@ class TrainStep:
             sum(p.numel() + 4 for p in model.parameters()), next(model.parameters()).device)
         self._distributed = torch.distributed.is_available() and torch.distributed.is_initialized() and \
             torch.distributed.get_world_size(group) > 1
+        if distributed is not None:
+            self._distributed = self._distributed and distributed
+        self._dice_group = (group if group is not None else True) if (global_dice and self._distributed) else None
         # all-reduce overlapped with the backward on the pooled gradient buffer (CSWIN_DDP_OVERLAP=0: bucketed all-reduce
         # after the backward, between two CUDA graphs)
         self._reducer = parallel.PoolGradReducer(self._pool, group) if (
@@ -130,6 +151,7 @@ class TrainStep:
             self._tbl_key = key
         self._tbl_dev.copy_(self._tbl_host, non_blocking=True)
         ops.sgd_momentum_step(self._tbl_dev[:self._tbl_n], self.lr_dev, self.momentum, self.weight_decay)
+        modules.bump_param_epoch()                             # raw-pointer write: invalidate every derived-weight cache
 
     def _fwd_bwd(self, images: Tensor, labels: Tensor) -> Tensor:
         if self._shadow_src:
@@ -149,7 +171,7 @@ class TrainStep:
             if self._drop_plan is not None:
                 self._drop_plan.end()
             modules.DROP_PATH_PLAN = None
-            loss = seg_loss(logits, labels, self.n_classes)
+            loss = seg_loss(logits, labels, self.n_classes, self._dice_group)
             loss.backward()
             if self._reducer is not None:                       # tail bucket + gradients that live outside the pool
                 self._reducer.finish()
@@ -163,10 +185,20 @@ class TrainStep:
                 self._pool.on_commit = None
         return loss.detach()
 
+    def gradients(self, images: Tensor, labels: Tensor) -> Tensor:
+        """Forward + backward (+ the gradient all-reduce when distributed) WITHOUT the optimizer step: returns the loss and
+        leaves the (averaged) gradients in `p.grad`.  Eager; used by the N-rank gradient-parity check."""
+        self._check_external_writes()
+        self.opt.zero_grad(set_to_none=True)
+        loss = self._fwd_bwd(images, labels)
+        if self._reducer is None and self._distributed:
+            parallel.allreduce_gradients(self.model.parameters(), self.group)
+        return loss
+
     def _eager(self, images: Tensor, labels: Tensor) -> Tensor:
         self.opt.zero_grad(set_to_none=True)
         loss = self._fwd_bwd(images, labels)
-        if self._reducer is None:
+        if self._reducer is None and self._distributed:
             parallel.allreduce_gradients(self.model.parameters(), self.group)
         self._optimizer_step()
         return loss
@@ -234,4 +266,5 @@ class TrainStep:
         if g2 is not None:
             parallel.allreduce_gradients(self.model.parameters(), self.group)
             g2.replay()
+        modules.bump_param_epoch()                         # the replayed optimizer kernel wrote the parameters (no Python ran)
         return self._loss

@@ -364,3 +364,37 @@ def test_lepe_attention_backward_wide_windows_vs_fp64(dtype, tol):
         sl = (Ellipsis, slice(off, off + cb))
         assert rel(gb[sl], ref[0][sl]) <= tol, (key, "dqkv", rel(gb[sl], ref[0][sl]))
         assert rel(gw, ref[1]) <= tol and rel(gbias, ref[2]) <= tol, (key, rel(gw, ref[1]), rel(gbias, ref[2]))
+
+
+def test_eval_after_native_training_sees_the_trained_weights():
+    """the fused SGD writes parameters through raw pointers (no `_version` bump); eval-mode forwards and a
+    SliceEngine captured BEFORE training must run with the trained weights afterwards (interleaved validation is a reference
+    workflow: universal_train.py:644/868)."""
+    torch.manual_seed(0)
+    m = cw.cswin_tiny_224(num_classes=4, drop_path_rate=0.0).to(DEV)
+    x = T(synth.synth_image_batch(2, 3, 224, seed=3, kind="ct"))
+    y = torch.randint(0, 4, (2, 224, 224), device=DEV)
+    m.eval()
+    m.compute_dtype = torch.bfloat16
+    with torch.no_grad():
+        before = m(x).float()
+    eng = cw.SliceEngine(m, batch=2)
+    lab_before = eng.predict(x.cpu())
+    step = cw.TrainStep(m, lr=0.5, graph=True, warmup=1)
+    for _ in range(4):
+        step(x, y)
+    torch.cuda.synchronize()
+    m.eval()
+    with torch.no_grad():
+        after = m(x).float()
+    fresh = cw.cswin_tiny_224(num_classes=4, drop_path_rate=0.0).to(DEV).eval()
+    fresh.load_state_dict(m.state_dict(), strict=True)
+    fresh.compute_dtype = torch.bfloat16
+    with torch.no_grad():
+        want = fresh(x).float()
+    assert (after - before).abs().max().item() > 1e-2, "training did not change the logits: test is vacuous"
+    assert torch.equal(after, want), f"stale derived weights after training: {(after - want).abs().max().item():.3e}"
+    lab_after = eng.predict(x.cpu())                       # engine captured before training: must have re-captured itself
+    lab_want = cw.SliceEngine(fresh, batch=2).predict(x.cpu())
+    assert torch.equal(lab_after, lab_want)
+    step.close()

@@ -647,3 +647,65 @@ def test_full_model_512px_config_logits_vs_golden():
     # near-ties (the bf16 criteria of the north star are asserted on the reference-init T224 model above, and the 512^2 bf16
     # kernels block by block in test_512px_config_blocks_* / test_lepe_attention_bf16_wide_windows_on_tcgen05)
     assert torch.isfinite(l16).all()
+
+
+# ---------------------------------------------------------------------------------------------------
+# GELU over the range trained checkpoints produce (the degree-7 tanh-argument fit turns over near |x| = 7.3)
+# ---------------------------------------------------------------------------------------------------
+def _wide_preacts(M, N, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    z = (torch.rand(M, N, generator=g) * 40.0 - 20.0)
+    z[0, :8] = torch.tensor([-20.0, -8.0, -7.4, -5.5, 5.5, 7.4, 8.0, 20.0])
+    return z.bfloat16()
+
+
+def test_gelu_epilogue_wide_range_bf16():
+    """Linear + GELU epilogue (tcgen05 fast path and predicated path), fused MLP and the activation kernel with pre-activations
+    in [-20, 20]: bf16 result within one bf16 ulp of exact GELU(erf) of the same pre-activation (Mlp, cswin_unet.py:22-26)."""
+    M, K = 256, 64
+    z = _wide_preacts(M, K)
+    eye = torch.eye(K).bfloat16()
+    ref = torch.nn.functional.gelu(z.double()).float()
+    tol = lambda r: 2.0 ** -8 * r.abs() + 2e-3                        # one bf16 ulp relative + the documented tanh.approx floor
+    # (a) GEMM with identity weights: accumulator == z exactly, epilogue = GELU
+    for n_out in (K, K - 4):                                          # N % 8 == 0 -> TMA-store path; ragged N -> predicated path
+        y = ops.linear(z.to(DEV), eye[:n_out].contiguous().to(DEV), None, act=1).float().cpu()
+        assert ((y - ref[:, :n_out]).abs() <= tol(ref[:, :n_out])).all(), (y - ref[:, :n_out]).abs().max()
+        assert y[0, 0] == 0.0 and y[0, 1] == 0.0 and abs(y[0, 6].item() - 8.0) < 0.04 and abs(y[0, 7].item() - 20.0) < 0.1
+    # (b) streaming activation kernel
+    y = ops.act_fwd(z.to(DEV), act=1).float().cpu()
+    assert ((y - ref).abs() <= tol(ref)).all()
+    # (c) fused MLP: LayerNorm with a huge gamma pushes fc1 pre-activations far outside +-7
+    C, hid = 64, 256
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(300, C, generator=g).bfloat16()
+    gam = torch.full((C,), 12.0)
+    W1 = (torch.randn(hid, C, generator=g) / C ** 0.5)
+    w1f = (W1 * gam[None, :]).bfloat16()
+    W2 = (torch.randn(C, hid, generator=g) / hid ** 0.5).bfloat16()
+    xd = x.to(DEV)
+    yf, _ = ops.mlp_fused(xd, w1f.to(DEV), w1f.float().sum(1).to(DEV), torch.zeros(hid, device=DEV), W2.to(DEV),
+                          torch.zeros(C, device=DEV), ops.row_stats(xd), 1e-5)
+    xs = x.double()
+    u = (xs - xs.mean(1, keepdim=True)) / (xs.var(1, unbiased=False, keepdim=True) + 1e-5).sqrt()
+    pre = u @ w1f.double().T
+    assert pre.abs().max() > 20.0
+    refm = xs + torch.nn.functional.gelu(pre) @ W2.double().T
+    err = (yf.float().cpu().double() - refm).abs().max().item()
+    assert err <= 2e-2 * refm.abs().max().item(), (err, refm.abs().max().item())
+
+
+def test_gelu_grad_wide_range_bf16():
+    """GELU' in the streaming kernel (cswin_act_bwd) and in the fc2 data-gradient epilogue (act = 2) for |z| up to 20."""
+    M, N = 256, 64
+    z = _wide_preacts(M, N, seed=1)
+    dh = torch.ones(M, N).bfloat16()
+    zd = z.double()
+    ref = (0.5 * (1 + torch.erf(zd / 2 ** 0.5)) + zd * torch.exp(-zd * zd / 2) / (2 * torch.pi) ** 0.5).float()
+    dz = ops.act_bwd(dh.to(DEV), z.to(DEV), None, 0, act=1).float().cpu()
+    assert ((dz - ref).abs() <= 2.0 ** -8 * ref.abs() + 1e-3).all(), (dz - ref).abs().max()
+    assert dz[0, 0] == 0.0 and dz[0, 1] == 0.0 and abs(dz[0, 6].item() - 1.0) < 5e-3 and abs(dz[0, 7].item() - 1.0) < 5e-3
+    # act = 2 epilogue: dZ = (dH2 @ W) o GELU'(z) with W = I (w_kn layout) -> GELU'(z) itself
+    eye = torch.eye(N).bfloat16()
+    dz2 = ops.linear(dh.to(DEV), eye.to(DEV), w_kn=True, act=2, residual=z.to(DEV)).float().cpu()
+    assert ((dz2 - ref).abs() <= 2.0 ** -8 * ref.abs() + 1e-3).all(), (dz2 - ref).abs().max()

@@ -56,16 +56,38 @@ def _worker(rank, world, port, n_total, out_dir):
             red.begin()
             slices = []
             for i, shape in enumerate(((10, 10), (7,), (333,), (64, 3), (5,))):
+                before = pool.off
                 v = pool.take(shape)
                 v += float(rank + 1) * (i + 1 + step)           # "wgrad kernel" accumulates into the zeroed slice
                 slices.append(v)
                 pool.commit()
+                # a bucket launched at this commit must not contain the committing node's own range —
+                # autograd may still read it (AccumulateGrad clone of a permuted view, dtype cast) after the commit
+                assert all(b <= before for (_, b) in red.launched), (red.launched, before)
             red.finish()
             assert red.n_coll >= 2 and pool.on_commit is None
             for i, v in enumerate(slices):
                 want = (i + 1 + step) * sum(range(1, world + 1)) / world
                 assert red.in_pool(v) and torch.allclose(v, torch.full_like(v, want)), (step, i)
             assert not red.in_pool(torch.zeros(3))
+        # 4. global-batch Dice (reference nn.DataParallel semantics, trainer.py:55-57): the per-rank gradient of
+        #    seg_loss(..., global_dice_group=True) w.r.t. the local logits == world x the gradient of the single-process loss on
+        #    the concatenated batch (the gradient all-reduce AVERAGES over ranks)
+        from cswin_unet_b200.train import seg_loss
+        g = torch.Generator().manual_seed(7)
+        full_logits = torch.randn(2 * world, 4, 6, 5, generator=g, dtype=torch.float64)
+        full_labels = torch.randint(0, 4, (2 * world, 6, 5), generator=g)
+        fl = full_logits.clone().requires_grad_(True)
+        want_loss = seg_loss(fl.float(), full_labels, 4)
+        (g_full,) = torch.autograd.grad(want_loss, fl)
+        mine = full_logits[2 * rank:2 * rank + 2].clone().requires_grad_(True)
+        loss = seg_loss(mine.float(), full_labels[2 * rank:2 * rank + 2], 4, global_dice_group=True)
+        (g_mine,) = torch.autograd.grad(loss, mine)
+        assert torch.allclose(g_mine, world * g_full[2 * rank:2 * rank + 2], rtol=1e-4, atol=1e-7), (g_mine - world * g_full[2 * rank:2 * rank + 2]).abs().max()
+        # loss value: CE is the local mean, Dice the global one; averaged over ranks it is the single-process loss
+        lv = loss.detach().double().clone()
+        dist.all_reduce(lv)
+        assert abs(float(lv) / world - float(want_loss)) < 1e-5
         np.save(os.path.join(out_dir, f"ok{rank}.npy"), np.array([1]))
     finally:
         dist.destroy_process_group()
