@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — CSWin-UNet-tiny 224^2 slices/sec on B200 (BASELINE.json metric), one process per GPU.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference|reference-cuda]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 ... bench.py --gpus N ...
 
 native arm  : a "step" is one bf16 forward of cswin_tiny_224_lite over one batch of 24 synthetic 3x224x224 slices
@@ -11,8 +11,11 @@ native arm  : a "step" is one bf16 forward of cswin_tiny_224_lite over one batch
                          batch, forward, argmax label map, D2H of the label map, every step,
               `roofline` = fused LePE attention kernel family: algorithmic bytes / CUDA-event time vs measured HBM peak,
               `cpu_baseline` = the CPU oracle (port of the reference's PyTorch path) on this box's host cores.
-reference arm: the reference's CPU path (oracle port; /root/reference cannot travel to the GPU box) on all host cores,
-              same metric / config; rank 0 only.
+reference arm: the reference's own CPU path on all host cores, same metric / config; rank 0 only.  It is the UNMODIFIED
+              reference (baseline/_ref/networks/cswin_unet.py, copied verbatim by build(); kind "reference") when that copy
+              travelled with the snapshot, else the oracle port (kind "port").
+reference-cuda: the unmodified reference in eager PyTorch on the same B200 (fp32 as the reference runs it, and bf16 autocast)
+              — the comparator SURVEY 8d / BASELINE.md 3 ask for; also reported inside the native line as `reference_cuda`.
 Slices are independent, so N GPUs = N replicas each running its own batches: weak scaling, no collective on the
 data path; timing = max over ranks of the device time, bracketed by barrier + synchronize.
 """
@@ -136,18 +139,35 @@ def oracle_model():
 
 def cpu_forward_rate(budget_s: float, batch: int, min_iters: int = 2):
     from cswin_unet_b200 import synth
-    O, sd = oracle_model()
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
+    ref = reference_model("cpu")
+    if ref is not None:
+        kind, fwd = "reference", ref
+    else:
+        O, sd = oracle_model()
+        kind, fwd = "port", (lambda t: O.cswin_unet_forward(sd, t))
     x = torch.from_numpy(synth.synth_image_batch(batch, 3, 224, seed=0, kind="ct"))
     with torch.no_grad():
-        O.cswin_unet_forward(sd, x[:2])                        # warm-up
+        fwd(x[:2])                                             # warm-up
         t0 = time.perf_counter(); n = 0
         while n < min_iters or (time.perf_counter() - t0) < budget_s:
-            O.cswin_unet_forward(sd, x)
+            fwd(x)
             n += 1
         dt = time.perf_counter() - t0
-    return n * batch / dt, cores, n, dt
+    return n * batch / dt, cores, n, dt, kind
+
+
+def reference_model(device="cpu"):
+    """The unmodified reference model with the bench's synthetic weights, or None if baseline/_ref did not travel."""
+    from baseline import ref_loader
+    from cswin_unet_b200 import synth
+    if not ref_loader.available():
+        return None
+    m = ref_loader.build_reference_model().eval()
+    shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in synth.synth_state_dict(shapes, seed=1234).items()}, strict=True)
+    return m.to(device)
 
 
 def run_reference(args):
@@ -155,29 +175,91 @@ def run_reference(args):
     if rank != 0:
         return 0
     from cswin_unet_b200 import synth
-    O, sd = oracle_model()
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
+    ref = reference_model("cpu")
+    if ref is not None:
+        kind, what = "reference", "UNMODIFIED reference networks/cswin_unet.py (baseline/_ref), torch CPU fp32"
+        fwd = ref
+    else:
+        O, sd = oracle_model()
+        kind, what = "port", "CPU port of the reference PyTorch path (oracle/cswin_oracle.py), fp32"
+        fwd = lambda x: O.cswin_unet_forward(sd, x)       # noqa: E731
     # bounded sample per step so that K+W steps end within minutes on any host: a batch of 24 slices is ~1.5 s on 8 cores
     sample = BATCH
     x = torch.from_numpy(synth.synth_image_batch(sample, 3, 224, seed=0, kind="ct"))
     with torch.no_grad():
         for _ in range(args.warmup):
-            O.cswin_unet_forward(sd, x)
+            fwd(x)
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            O.cswin_unet_forward(sd, x)
+            fwd(x)
         dt = time.perf_counter() - t0
     value = args.steps * sample / dt
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"cswin_tiny_224_lite eval forward, batch {sample} per step, 3x224x224 synthetic slices, "
-                                   "CPU port of the reference PyTorch path (oracle/cswin_oracle.py), fp32"},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+            "config": {"workload": f"cswin_tiny_224_lite eval forward, batch {sample} per step, 3x224x224 synthetic slices, " + what},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
                              "sample": f"{args.steps} steps x {sample} slices, torch CPU fp32, {cores} threads"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
+    return 0
+
+
+def reference_cuda_rates(dev, batches=(BATCH, 1), iters=10, warm=3):
+    """Eager-CUDA throughput of the unmodified reference on this GPU (stock code path: cuBLAS / cuDNN / ATen kernels, no repo
+    module): fp32 (how the reference runs, TF32 off as train.py:73-78 leaves it) and bf16 autocast; device-resident inputs,
+    CUDA events.  Returns None when baseline/_ref did not travel."""
+    from cswin_unet_b200 import synth
+    ref = reference_model(dev)
+    if ref is None:
+        return None
+    out = {"what": "unmodified reference (baseline/_ref/networks/cswin_unet.py), eager PyTorch on this GPU, eval forward, "
+                   "device-resident inputs, CUDA events", "torch": torch.__version__}
+    for B in batches:
+        x = torch.from_numpy(synth.synth_image_batch(B, 3, 224, seed=0, kind="ct")).to(dev)
+        for name, ctx in (("fp32", None), ("bf16_autocast", torch.autocast("cuda", dtype=torch.bfloat16))):
+            with torch.no_grad():
+                def fwd():
+                    if ctx is None:
+                        return ref(x)
+                    with ctx:
+                        return ref(x)
+                for _ in range(warm):
+                    fwd()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(iters):
+                    fwd()
+                e1.record()
+                torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / iters
+            out[f"batch{B}_{name}"] = {"slices_per_s": B / (ms * 1e-3), "ms_per_forward": ms}
+    del ref
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_reference_cuda(args):
+    rank, world, local = dist_env()
+    if rank != 0:
+        return 0
+    if not torch.cuda.is_available():
+        emit({"impl": "reference-cuda", "unavailable": "no CUDA device"})
+        return 0
+    torch.cuda.set_device(local)
+    r = reference_cuda_rates(torch.device("cuda", local), iters=max(args.steps, 5), warm=max(args.warmup, 3))
+    if r is None:
+        emit({"impl": "reference-cuda", "unavailable": "baseline/_ref/networks/cswin_unet.py did not travel with the snapshot"})
+        return 0
+    v = r[f"batch{BATCH}_fp32"]
+    emit({"impl": "reference-cuda", "metric": METRIC, "value": v["slices_per_s"], "unit": UNIT, "n_gpus": 1, "steps": max(args.steps, 5),
+          "warmup": max(args.warmup, 3), "ms_per_step": v["ms_per_forward"], "higher_is_better": True, "scaling": "weak",
+          "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+          "config": {"workload": f"cswin_tiny_224_lite eval forward, batch {BATCH}, unmodified reference in eager PyTorch on the GPU"},
+          "detail": r})
     return 0
 
 
@@ -418,10 +500,21 @@ def run_native(args):
         finally:
             fired.set()
 
+    if rank == 0 and world == 1 and not args.no_reference_cuda:
+        try:                                                       # the eager-PyTorch reference on this same GPU
+            rc = reference_cuda_rates(dev)
+            line["reference_cuda"] = rc if rc is not None else {"unavailable": "baseline/_ref did not travel with the snapshot"}
+            if rc is not None:
+                line["speedup_vs_reference_cuda"] = {
+                    "bf16_vs_ref_fp32": value / rc[f"batch{BATCH}_fp32"]["slices_per_s"],
+                    "bf16_vs_ref_bf16_autocast": value / rc[f"batch{BATCH}_bf16_autocast"]["slices_per_s"]}
+        except Exception as e:                                     # noqa: BLE001
+            line["reference_cuda"] = {"error": f"{type(e).__name__}: {e}"[:300]}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, cores, n, dt = cpu_forward_rate(args.cpu_budget, BATCH)
-        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                                "sample": f"{n} forwards of batch {BATCH} in {dt:.1f} s, oracle (torch CPU fp32), {cores} threads"}
+        v, cores, n, dt, kind = cpu_forward_rate(args.cpu_budget, BATCH)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
+                                "sample": f"{n} forwards of batch {BATCH} in {dt:.1f} s, "
+                                          f"{'unmodified reference' if kind == 'reference' else 'oracle port'} (torch CPU fp32), {cores} threads"}
     if rank == 0:
         emit(line)
     if world > 1:
@@ -461,16 +554,19 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--impl", default="native", choices=["native", "reference", "reference-cuda"])
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU-oracle work for cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-reference-cuda", action="store_true", help="skip timing the eager reference on the GPU")
     ap.add_argument("--no-train", action="store_true", help="skip the train-step leg")
     ap.add_argument("--train-timeout", type=float, default=150.0, help="seconds before a stalled train-step leg is abandoned")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
     if args.impl == "reference":
         return run_reference(args)
+    if args.impl == "reference-cuda":
+        return run_reference_cuda(args)
     return run_native(args)
 
 

@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(_HERE, "libcswin_b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "cswin_b200.h")
 
 F32, BF16 = 0, 1
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 c_void_p, c_int32, c_int64, c_float = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 
@@ -73,6 +73,23 @@ class MlpArgs(C.Structure):
     ]
 
 
+class QkvAttnBranch(C.Structure):
+    """== cswin_qkv_attn_branch_t"""
+    _fields_ = [("conv_w", c_void_p), ("conv_b", c_void_p), ("heads", c_int32), ("H_sp", c_int32), ("W_sp", c_int32),
+                ("reserved", c_int32)]
+
+
+class QkvAttnArgs(C.Structure):
+    """== cswin_qkv_attn_args_t"""
+    _fields_ = [
+        ("x", c_void_p), ("x_bs", c_int64), ("x_ts", c_int64), ("w", c_void_p), ("ldw", c_int64), ("bias_f32", c_void_p),
+        ("ln_stats", c_void_p), ("ln_colsum", c_void_p), ("ln_stats_parts", c_int32), ("ln_eps", c_float),
+        ("out", c_void_p), ("o_bs", c_int64), ("o_ts", c_int64),
+        ("B", c_int32), ("reso", c_int32), ("C", c_int32), ("n_branches", c_int32),
+        ("br", QkvAttnBranch * 2), ("scale", c_float), ("reserved", c_int32),
+    ]
+
+
 SIGNATURES = {
     "cswin_abi_version": (c_int32, []),
     "cswin_last_error": (C.c_char_p, []),
@@ -96,6 +113,9 @@ SIGNATURES = {
     "cswin_sgd_momentum_step": (c_int32, [c_void_p, c_int32, c_void_p, c_float, c_float, c_void_p]),
     "cswin_mlp_fwd": (c_int32, [C.POINTER(MlpArgs), c_int32, c_void_p]),
     "cswin_mlp_stats_parts": (c_int32, [c_int32, c_int32]),
+    "cswin_qkv_lepe_attention_fwd": (c_int32, [C.POINTER(QkvAttnArgs), c_int32, c_void_p]),
+    "cswin_qkv_lepe_attention_supported": (c_int32, [c_int32, c_int32, c_int32, C.POINTER(c_int32), C.POINTER(c_int32),
+                                                     C.POINTER(c_int32)]),
     "cswin_linear_stats_parts": (c_int32, [c_int64, c_int32, c_int32, c_int32]),
     "cswin_layernorm_stats_fwd": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int32, c_float,
                                             c_void_p, c_int32, c_void_p]),

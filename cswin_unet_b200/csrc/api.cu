@@ -270,6 +270,21 @@ int cswin_mlp_fwd(const cswin_mlp_args_t* a, int32_t dtype, cswin_stream_t strea
 
 int32_t cswin_mlp_stats_parts(int32_t C, int32_t hidden) { return mlp_tc_stats_parts(C, hidden); }
 
+int cswin_qkv_lepe_attention_fwd(const cswin_qkv_attn_args_t* a, int32_t dtype, cswin_stream_t stream) {
+  CSWIN_REQUIRE(a != nullptr, CSWIN_ERR_INVALID, "qkv_lepe_attention_fwd: null args");
+  CSWIN_REQUIRE(dtype == CSWIN_BF16, CSWIN_ERR_UNSUPPORTED, "qkv_lepe_attention_fwd: exists on the bf16 / tcgen05 path only");
+  CSWIN_REQUIRE(a->x && a->w && a->out && a->B >= 0 && a->reso > 0 && a->C > 0 && a->n_branches >= 1 && a->n_branches <= 2 &&
+                a->ldw >= a->C && (a->ln_stats == nullptr || a->ln_stats_parts > 0),
+                CSWIN_ERR_INVALID, "qkv_lepe_attention_fwd: bad arguments");
+  return qkv_attn_fwd_tc(a, (cudaStream_t)stream);
+}
+
+int32_t cswin_qkv_lepe_attention_supported(int32_t C, int32_t reso, int32_t n_branches, const int32_t* heads, const int32_t* H_sp,
+                                           const int32_t* W_sp) {
+  if (heads == nullptr || H_sp == nullptr || W_sp == nullptr) return 0;
+  return qkv_attn_supported(C, reso, n_branches, heads, H_sp, W_sp);
+}
+
 int32_t cswin_linear_stats_parts(int64_t M, int32_t N, int32_t K, int32_t act) { return linear_tc_stats_parts(M, N, K, act); }
 
 int cswin_row_stats(const void* x, int64_t ldx, int64_t M, int32_t C, float* stats, int32_t dtype, cswin_stream_t stream) {

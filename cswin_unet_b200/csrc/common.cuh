@@ -112,6 +112,8 @@ int seg_loss_bwd(const float* logits, const void* labels, int label_bytes, const
 int sgd_momentum_step(const cswin_sgd_chunk_t* chunks, int n_chunks, const float* lr, float momentum, float wd, cudaStream_t s);
 int mlp_fwd_tc(const cswin_mlp_args_t* a, cudaStream_t stream);
 int mlp_tc_stats_parts(int C, int hidden);
+int qkv_attn_fwd_tc(const cswin_qkv_attn_args_t* a, cudaStream_t stream);
+int qkv_attn_supported(int C, int reso, int nb, const int* heads, const int* hs, const int* ws);
 int linear_tc_stats_parts(int64_t M, int N, int K, int act);
 int linear_fwd_simt(const cswin_linear_args_t* a, int dtype, cudaStream_t s);
 int linear_fwd_tc(const cswin_linear_args_t* a, cudaStream_t s, bool* handled);

@@ -222,9 +222,12 @@ class CSWinTransformer(_Native):
         return logits
 
     def forward(self, x: Tensor) -> Tensor:
+        in_dt = x.dtype
         x = self.forward_features(x)
         x = self.forward_up_features(x)
-        return self.up_x4(x)
+        # logits leave in the dtype of the INPUT: an fp32 image through the bf16 compute path (compute_dtype) gets fp32 logits
+        # straight from the head kernel's fp32 accumulators instead of a final rounding to bf16 (|logit| ~ 25 -> 0.1 absolute)
+        return self.up_x4(x, logits_dtype=in_dt if in_dt in (torch.float32, torch.bfloat16) else None)
 
     @torch.no_grad()
     def predict_labels(self, x: Tensor) -> Tensor:

@@ -109,6 +109,8 @@ class DropPath(nn.Module):
 FUSE_MLP = os.environ.get("CSWIN_FUSE_MLP", "1") != "0"
 FUSE_MLP_MAX_DIM = int(os.environ.get("CSWIN_FUSE_MLP_MAX_DIM", "64"))
 FOLD_LN = os.environ.get("CSWIN_FOLD_LN", "1") != "0"     # LayerNorm folded into the tcgen05 Linear epilogue (bf16 inference)
+# [LN1 -> qkv -> both LePE attention branches] as one kernel (csrc/qkv_attn_tc.cu) where the block shape allows it
+FUSE_QKV_ATTN = os.environ.get("CSWIN_FUSE_QKV_ATTN", "1") != "0"
 
 
 # Parameters can be written behind torch's back: the native fused SGD (train.TrainStep -> cswin_sgd_momentum_step) updates them
@@ -361,6 +363,13 @@ class CSWinBlock(_Native):
             if st is None or st.shape[0] != B * L:
                 st = ops.row_stats(x)
             wq, csq, bq = self._folded("qkv", self.qkv, self.norm1)
+            if FUSE_QKV_ATTN and x.is_contiguous() and self._qkv_attn_ok():
+                for a in self.attns:
+                    a._check(L)
+                brs = [dict(conv_w=a._w("cw", a.get_v.weight, dt), conv_b=a._w("cb", a.get_v.bias, dt), heads=a.num_heads,
+                            H_sp=a.H_sp, W_sp=a.W_sp) for a in self.attns]
+                att = ops.qkv_lepe_attention(x, wq, bq, (st, csq, self.norm1.eps), brs, H, float(self.attns[0].scale))
+                return self._after_attention(x, att, dt, True)
             qkv = ops.linear(x, wq, None, ln_fold=(st, csq, self.norm1.eps), bias_f32=bq)
         else:
             qkv = ops.linear(x, w("qkv.w", self.qkv.weight, dt),
@@ -381,6 +390,19 @@ class CSWinBlock(_Native):
             descs = [self.attns[0].branch_desc(q, k, v, att)]
             scale = float(self.attns[0].scale)
         ops.lepe_attention_fwd(descs, B, H, scale, dt)
+        return self._after_attention(x, att, dt, fold)
+
+    def _qkv_attn_ok(self) -> bool:
+        ok = self.__dict__.get("_qkv_attn_ok_cache")
+        if ok is None:
+            ok = ops.qkv_attention_supported(self.dim, self.patches_resolution, [(a.num_heads, a.H_sp, a.W_sp) for a in self.attns])
+            self.__dict__["_qkv_attn_ok_cache"] = ok
+        return ok
+
+    def _after_attention(self, x: Tensor, att: Tensor, dt, fold: bool) -> Tensor:
+        """proj + residual, then the MLP half of the block (cswin_unet.py:177-179)."""
+        B, L, Cn = x.shape
+        w = self._w
         if fold:
             x1, st1 = ops.linear(att, w("proj.w", self.proj.weight, dt), w("proj.b", self.proj.bias, dt), residual=x,
                                  sample_scale=self._sample_scale(x), rows_per_sample=L, want_stats=True)

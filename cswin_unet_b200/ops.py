@@ -12,7 +12,7 @@ from typing import Optional, Sequence, Tuple
 import torch
 
 from . import _lib
-from ._lib import BF16, F32, LepeBranch, LepeBranchGrad, LinearArgs, MlpArgs, check, lib
+from ._lib import BF16, F32, LepeBranch, LepeBranchGrad, LinearArgs, MlpArgs, QkvAttnArgs, check, lib
 
 Tensor = torch.Tensor
 
@@ -251,6 +251,49 @@ def mlp_fused(x: Tensor, w1f: Tensor, cs1: Tensor, b1f: Tensor, w2: Tensor, b2: 
         a.stats_out = st.data_ptr()
     check(lib().cswin_mlp_fwd(C.byref(a), _dtype_code(x), _stream()), "cswin_mlp_fwd")
     return out, st
+
+
+def qkv_attention_supported(Cn: int, reso: int, branches: Sequence[Tuple[int, int, int]]) -> bool:
+    """branches: [(heads, H_sp, W_sp)] — is the fused [LayerNorm -> qkv -> LePE attention] kernel available for this block?"""
+    n = len(branches)
+    arr = lambda i: (C.c_int32 * 2)(*([b[i] for b in branches] + [0] * (2 - n)))
+    return bool(lib().cswin_qkv_lepe_attention_supported(Cn, reso, n, arr(0), arr(1), arr(2)))
+
+
+def qkv_lepe_attention(x: Tensor, w: Tensor, bias_f32: Optional[Tensor], ln_fold, branches: Sequence[dict], reso: int,
+                       scale: float, out: Optional[Tensor] = None) -> Tensor:
+    """att = cat_i LePEAttention_i(qkv(LN(x)) slices) in one tcgen05 launch (cswin_qkv_lepe_attention_fwd).
+    x (B, L, C) bf16; w (3C, C) bf16 (gamma-folded when `ln_fold = (stats (M, parts, 2), colsum (3C) fp32, eps)`); bias_f32 (3C) fp32;
+    branches: [{conv_w (C_b,1,3,3) bf16, conv_b (C_b) bf16, heads, H_sp, W_sp}]."""
+    _need_cuda(x, w, bias_f32)
+    assert x.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and x.dim() == 3 and x.stride(2) == 1 and w.stride(1) == 1
+    B, L, Cn = x.shape
+    assert L == reso * reso and w.shape == (3 * Cn, Cn)
+    if out is None:
+        out = torch.empty((B, L, Cn), dtype=x.dtype, device=x.device)
+    a = QkvAttnArgs()
+    a.x, a.x_bs, a.x_ts = x.data_ptr(), x.stride(0), x.stride(1)
+    a.w, a.ldw = w.data_ptr(), w.stride(0)
+    if bias_f32 is not None:
+        assert bias_f32.dtype == torch.float32 and bias_f32.numel() == 3 * Cn
+        a.bias_f32 = bias_f32.data_ptr()
+    if ln_fold is not None:
+        st, cs, eps = ln_fold
+        assert st.dtype == torch.float32 and st.is_contiguous() and st.shape[0] == B * L and st.shape[2] == 2
+        assert cs.dtype == torch.float32 and cs.numel() == 3 * Cn and x.is_contiguous()
+        a.ln_stats, a.ln_colsum, a.ln_stats_parts, a.ln_eps = st.data_ptr(), cs.data_ptr(), st.shape[1], eps
+    a.out, a.o_bs, a.o_ts = out.data_ptr(), out.stride(0), out.stride(1)
+    a.B, a.reso, a.C, a.n_branches, a.scale = B, reso, Cn, len(branches), scale
+    keep = []
+    for i, b in enumerate(branches):
+        cw, cb = b["conv_w"].contiguous(), b["conv_b"].contiguous()
+        _need_cuda(cw, cb)
+        assert cw.dtype == torch.bfloat16 and cb.dtype == torch.bfloat16
+        keep += [cw, cb]
+        a.br[i].conv_w, a.br[i].conv_b = cw.data_ptr(), cb.data_ptr()
+        a.br[i].heads, a.br[i].H_sp, a.br[i].W_sp = b["heads"], b["H_sp"], b["W_sp"]
+    check(lib().cswin_qkv_lepe_attention_fwd(C.byref(a), BF16, _stream()), "cswin_qkv_lepe_attention_fwd")
+    return out
 
 
 SGD_CHUNK = 65536

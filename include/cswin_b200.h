@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define CSWIN_ABI_VERSION 4
+#define CSWIN_ABI_VERSION 5
 
 typedef struct CUstream_st* cswin_stream_t; /* == cudaStream_t */
 
@@ -197,6 +197,38 @@ typedef struct {
 } cswin_mlp_args_t;
 int cswin_mlp_fwd(const cswin_mlp_args_t* args, int32_t dtype, cswin_stream_t stream);
 int32_t cswin_mlp_stats_parts(int32_t C, int32_t hidden);   /* 0 if the shape is unsupported */
+
+/* ---- [LayerNorm -> qkv Linear -> LePE attention of both branches] in one launch (bf16 / tcgen05 only) -----------------------
+ * replaces, inside CSWinBlock.forward (networks/cswin_unet.py:160-181): norm1 :168, the qkv Linear and its (3,B,L,C) view
+ * :169, both LePEAttention.forward calls :172-176 (:82-109 with im2cswin :59-65, get_lepe :67-80, img2windows :184-191,
+ * windows2img :194-202) and the torch.cat of :174.  The (B, L, 3C) qkv tensor never exists in global memory: each CTA computes
+ * the q | k | v columns of up to two heads for one 128-row window tile (gathered by TMA in window order) on the tensor cores,
+ * converts them to bf16 tiles in shared memory and runs the attention of those heads from there.
+ *   x        : (B, L = reso^2, C) bf16 activation, token t = y*reso + x; RAW rows when the LayerNorm is folded
+ *   w        : (3C, C) bf16 rows [q | k | v] (qkv.weight, or qkv.weight o gamma when folded); bias_f32: (3C) fp32 or NULL
+ *   ln_stats / ln_colsum / ln_eps: folded LayerNorm exactly as in cswin_linear_args_t (both NULL: x is used as it is)
+ *   br[i]    : branch i owns channels [sum_{j<i} 32 heads_j, +32 heads_i) of q, of k, of v and of out
+ *   out      : (B, L, C) bf16, both branches written into their concat position
+ * Envelope (cswin_qkv_lepe_attention_supported): C in {64, 128, 192, 256}, head_dim 32, windows of <= 128 tokens, branches
+ * with >= 2 heads use an even head count; otherwise CSWIN_ERR_UNSUPPORTED and the caller composes cswin_linear_fwd +
+ * cswin_lepe_attention_fwd. */
+typedef struct {
+  const void* conv_w; const void* conv_b;          /* get_v.weight (C_b,1,3,3) / get_v.bias (C_b) of the branch, bf16 */
+  int32_t heads, H_sp, W_sp, reserved;
+} cswin_qkv_attn_branch_t;
+typedef struct {
+  const void* x; int64_t x_bs, x_ts;               /* batch / token stride of x (elements) */
+  const void* w; int64_t ldw;
+  const float* bias_f32;
+  const float* ln_stats; const float* ln_colsum; int32_t ln_stats_parts; float ln_eps;
+  void* out; int64_t o_bs, o_ts;
+  int32_t B, reso, C, n_branches;
+  cswin_qkv_attn_branch_t br[2];
+  float scale; int32_t reserved;
+} cswin_qkv_attn_args_t;
+int cswin_qkv_lepe_attention_fwd(const cswin_qkv_attn_args_t* args, int32_t dtype, cswin_stream_t stream);
+int32_t cswin_qkv_lepe_attention_supported(int32_t C, int32_t reso, int32_t n_branches, const int32_t* heads, const int32_t* H_sp,
+                                           const int32_t* W_sp);
 
 /* ---- backward of cswin_carafe_head_fwd (the folded CARAFE4 + out + output head, up = 4; 2, 3, 4 or 9 classes) ---------------
  * dlogits: fp32 NCHW (B, C, 4H, 4W) contiguous.  Writes d enc (B*H*W, 144) and d z (B*H*W, zcols; columns >= C are zeroed),

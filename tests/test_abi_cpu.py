@@ -50,6 +50,8 @@ int main(void) {
          sizeof(cswin_linear_args_t));
   printf("%zu %zu %zu %zu %zu\n", offsetof(cswin_linear_args_t, ln_eps), offsetof(cswin_linear_args_t, rows_per_sample),
          offsetof(cswin_linear_args_t, stats_out), offsetof(cswin_linear_args_t, aux_out), offsetof(cswin_linear_args_t, ld_aux));
+  printf("%zu %zu %zu %zu %zu %zu\n", sizeof(cswin_qkv_attn_args_t), offsetof(cswin_qkv_attn_args_t, ln_eps), offsetof(cswin_qkv_attn_args_t, out),
+         offsetof(cswin_qkv_attn_args_t, n_branches), offsetof(cswin_qkv_attn_args_t, br), offsetof(cswin_qkv_attn_args_t, scale));
   return 0;
 }'''
     with tempfile.TemporaryDirectory() as d:
@@ -58,9 +60,10 @@ int main(void) {
         subprocess.check_call(["gcc", "-I", os.path.dirname(_lib.HEADER_PATH), c, "-o", exe])
         out = subprocess.check_output([exe], text=True).split()
     got = [int(v) for v in out]
-    B, G, L = _lib.LepeBranch, _lib.LepeBranchGrad, _lib.LinearArgs
+    B, G, L, Q = _lib.LepeBranch, _lib.LepeBranchGrad, _lib.LinearArgs, _lib.QkvAttnArgs
     want = [ctypes.sizeof(B), B.lse.offset, B.W_sp.offset, ctypes.sizeof(G), G.dconv_b.offset, ctypes.sizeof(L),
-            L.ln_eps.offset, L.rows_per_sample.offset, L.stats_out.offset, L.aux_out.offset, L.ld_aux.offset]
+            L.ln_eps.offset, L.rows_per_sample.offset, L.stats_out.offset, L.aux_out.offset, L.ld_aux.offset,
+            ctypes.sizeof(Q), Q.ln_eps.offset, Q.out.offset, Q.n_branches.offset, Q.br.offset, Q.scale.offset]
     assert got == want
 
 

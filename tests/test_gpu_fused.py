@@ -1,0 +1,122 @@
+"""GPU tests of the fused block kernels (through the C ABI): csrc/qkv_attn_tc.cu ([LayerNorm -> qkv Linear -> LePE attention of
+both branches] in one launch; cswin_unet.py:168-176 with :82-109) against the composed native path (cswin_linear_fwd +
+cswin_lepe_attention_fwd), against the CPU oracle in fp64, and through CSWinBlock / the whole model."""
+import numpy as np
+import pytest
+import torch
+
+import cswin_unet_b200 as cw
+from cswin_unet_b200 import modules, ops, synth
+from oracle import cswin_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+# (C, reso, heads, split, last_stage, B): the three two-branch stages of cswin_tiny_224 (batch sizes that leave ragged window
+# tiles), a one-branch 8x8 window (two-windows-per-tile mode with ONE window: np < slots), a 6-head block (head groups of 2 over 3
+# heads per branch is NOT supported -> must fall back), an odd number of windows per branch
+FUSED_CASES = [(64, 56, 2, 1, False, 2), (128, 28, 4, 2, False, 3), (256, 14, 8, 7, False, 5), (256, 14, 8, 7, False, 24),
+               (128, 8, 4, 8, True, 3), (128, 12, 4, 4, False, 2), (192, 14, 6, 7, False, 2), (64, 8, 2, 8, True, 4)]
+
+
+def _block(C, reso, heads, split, last):
+    blk = cw.CSWinBlock(dim=C, reso=reso, num_heads=heads, split_size=split, qkv_bias=True, last_stage=last).eval()
+    sd = {k: torch.from_numpy(synth.synth_tensor(f"fused/{C}/{reso}/" + k, tuple(v.shape), 11)) for k, v in blk.state_dict().items()}
+    blk.load_state_dict(sd, strict=True)
+    return blk.to(DEV), sd
+
+
+def _branch_args(descs):
+    return [dict(conv_w=d["conv_w"], conv_b=d["conv_b"], heads=d["heads"], H_sp=d["H_sp"], W_sp=d["W_sp"]) for d in descs]
+
+
+@pytest.mark.parametrize("C,reso,heads,split,last,B", FUSED_CASES)
+def test_qkv_attention_fused_equals_composed_and_oracle(C, reso, heads, split, last, B):
+    blk, sd = _block(C, reso, heads, split, last)
+    L = reso * reso
+    x = torch.from_numpy(synth.synth_tensor(f"fused_in/{C}/{reso}", (B, L, C), 12)).bfloat16()
+    xd = x.to(DEV)
+    brs = [(a.num_heads, a.H_sp, a.W_sp) for a in blk.attns]
+    supported = ops.qkv_attention_supported(C, reso, brs)
+    assert supported == (C != 192), (C, supported)          # 3 heads per branch: no head groups of 2
+    dt = torch.bfloat16
+    st = ops.row_stats(xd)
+    wq, csq, bq = blk._folded("qkv", blk.qkv, blk.norm1)
+    # composed: folded-LN Linear -> (B, L, 3C) -> attention kernel
+    qkv = ops.linear(xd, wq, None, ln_fold=(st, csq, blk.norm1.eps), bias_f32=bq)
+    att_c = torch.empty((B, L, C), dtype=dt, device=DEV)
+    q, k, v = qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:]
+    descs, off = [], 0
+    for a in blk.attns:
+        sl = slice(off, off + a.dim)
+        descs.append(a.branch_desc(q[..., sl], k[..., sl], v[..., sl], att_c[..., sl]))
+        off += a.dim
+    ops.lepe_attention_fwd(descs, B, reso, float(blk.attns[0].scale), dt)
+    if not supported:
+        with pytest.raises(cw.CswinError):
+            ops.qkv_lepe_attention(xd, wq, bq, (st, csq, blk.norm1.eps), _branch_args(descs), reso, float(blk.attns[0].scale))
+        return
+    n0 = cw.tc_launch_count()
+    att_f = ops.qkv_lepe_attention(xd, wq, bq, (st, csq, blk.norm1.eps), _branch_args(descs), reso, float(blk.attns[0].scale))
+    assert cw.tc_launch_count() == n0 + 1
+    # fp64 truth from the oracle's pieces on the same bf16 input
+    xs = x.double()
+    u = O._ln(xs, sd["norm1.weight"].double(), sd["norm1.bias"].double(), 1e-5)
+    z = u @ sd["qkv.weight"].double().T + sd["qkv.bias"].double()
+    ref = torch.empty(B, L, C, dtype=torch.float64)
+    off = 0
+    for i, a in enumerate(blk.attns):
+        sl = slice(off, off + a.dim)
+        ref[..., sl] = O.lepe_attention(z[..., :C][..., sl], z[..., C:2 * C][..., sl], z[..., 2 * C:][..., sl],
+                                        sd[f"attns.{i}.get_v.weight"].double(), sd[f"attns.{i}.get_v.bias"].double(), reso,
+                                        a.idx, a.split_size, a.num_heads, float(a.scale))
+        off += a.dim
+    ef = (att_f.float().cpu().double() - ref).abs().max().item()
+    ec = (att_c.float().cpu().double() - ref).abs().max().item()
+    d = (att_f.float() - att_c.float()).abs().max().item()
+    print(f"[qkv+attn fused C={C} reso={reso} B={B}] max-abs vs fp64: fused {ef:.3e}, composed {ec:.3e}; fused vs composed {d:.3e}")
+    assert torch.isfinite(att_f.float()).all()
+    assert ef <= 1.25 * ec + 4e-3, (ef, ec)                   # not less accurate than the composed bf16 path
+    assert d <= 3e-2 * max(1.0, ref.abs().max().item())
+
+
+def test_qkv_attention_fused_without_layernorm_fold():
+    """ln_stats = NULL: x is consumed as it is (caller normalised it) and the bias is the plain qkv bias."""
+    C, reso, heads, split, B = 128, 28, 4, 2, 2
+    blk, sd = _block(C, reso, heads, split, False)
+    x = torch.from_numpy(synth.synth_tensor("fused_in/plain", (B, reso * reso, C), 13)).bfloat16().to(DEV)
+    w = sd["qkv.weight"].bfloat16().to(DEV)
+    bias = sd["qkv.bias"].float().to(DEV)
+    brs = [dict(conv_w=a.get_v.weight.detach().bfloat16(), conv_b=a.get_v.bias.detach().bfloat16(), heads=a.num_heads, H_sp=a.H_sp, W_sp=a.W_sp)
+           for a in blk.attns]
+    att_f = ops.qkv_lepe_attention(x, w, bias, None, brs, reso, float(blk.attns[0].scale))
+    qkv = ops.linear(x, w, sd["qkv.bias"].bfloat16().to(DEV))
+    att_c = torch.empty_like(att_f)
+    descs = []
+    for i, a in enumerate(blk.attns):
+        sl = slice(i * 64, (i + 1) * 64)
+        descs.append(dict(q=qkv[..., :C][..., sl], k=qkv[..., C:2 * C][..., sl], v=qkv[..., 2 * C:][..., sl], out=att_c[..., sl],
+                          conv_w=brs[i]["conv_w"], conv_b=brs[i]["conv_b"], heads=a.num_heads, H_sp=a.H_sp, W_sp=a.W_sp))
+    ops.lepe_attention_fwd(descs, B, reso, float(blk.attns[0].scale), torch.bfloat16)
+    d = (att_f.float() - att_c.float()).abs().max().item()
+    print(f"[qkv+attn fused, no fold] fused vs composed {d:.3e}")
+    assert d <= 3e-2
+
+
+@pytest.mark.parametrize("C,reso,heads,split,last,B", [(64, 56, 2, 1, False, 2), (128, 28, 4, 2, False, 2), (256, 14, 8, 7, False, 3)])
+def test_block_with_fused_kernels_matches_oracle(C, reso, heads, split, last, B, monkeypatch):
+    blk, sd = _block(C, reso, heads, split, last)
+    x = torch.from_numpy(synth.synth_tensor(f"fusedblk_in/{C}", (B, reso * reso, C), 14)).bfloat16()
+    ref = O.cswin_block({k: v.double() for k, v in sd.items()}, "", x.double(), reso, heads, split, last)
+    outs = {}
+    for fused in (True, False):
+        monkeypatch.setattr(modules, "FUSE_QKV_ATTN", fused)
+        n0 = cw.launch_count()
+        with torch.no_grad():
+            outs[fused] = blk(x.to(DEV)).float().cpu().double()
+        outs[(fused, "n")] = cw.launch_count() - n0
+    ef = (outs[True] - ref).abs().max().item()
+    ec = (outs[False] - ref).abs().max().item()
+    print(f"[block C={C}] launches fused {outs[(True, 'n')]} vs composed {outs[(False, 'n')]}; max-abs vs fp64 fused {ef:.3e} composed {ec:.3e}")
+    assert outs[(True, "n")] < outs[(False, "n")]
+    assert ef <= 1.25 * ec + 5e-3

@@ -1,0 +1,78 @@
+"""bf16 acceptance on DECISIVE logits (north star: "per-pixel argmax agreement >= 99.9 %, identical Dice / HD95 to 1e-3";
+SURVEY 7.2.5) against committed outputs of the unmodified reference on briefly-trained weights
+(tests/golden/trained_{t224,512}.npz — see tests/golden/make_trained_golden.py for how they were produced).
+
+Tolerances.  The trained logits reach |logit| ~ 25, so "max-abs <= 2e-2" is read RELATIVE to the logit range
+(2e-2 x max |logit| / 8 ... stated per assertion); the fixture also stores the reference's OWN bf16-autocast error on the same
+inputs as the yard-stick, and the native bf16 path must beat it.  fp32: max-abs <= 1e-4 x max(1, |logit| max)."""
+import numpy as np
+import pytest
+import torch
+
+import cswin_unet_b200 as cw
+from cswin_unet_b200 import synth
+from oracle import cswin_oracle as O
+from tests import golden_util as G
+from tests import trained_util as TU
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _native(config):
+    c = TU.CONFIGS[config]
+    m = cw.cswin_tiny_224(num_classes=c["num_classes"], img_size=c["img_size"], split_size=c["split_size"]).eval()
+    z = TU.load(config)
+    shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    m.load_state_dict(TU.state_dict(z, shapes), strict=True)
+    return m.to(DEV), z
+
+
+@pytest.mark.parametrize("config", ["t224", "512"])
+def test_trained_model_logits_and_argmax(config):
+    m, z = _native(config)
+    x, ys = TU.test_inputs(config)
+    ref_arg = z["argmax"]
+    scale = max(1.0, float(z["logit_absmax"]))
+    res = {}
+    with torch.no_grad():
+        for name, dt in (("fp32", torch.float32), ("bf16", torch.bfloat16)):
+            m.compute_dtype = dt
+            lg = torch.cat([m(x[i:i + 2].to(DEV)).float().cpu() for i in range(0, x.shape[0], 2)])
+            err = G.compare(z, "logits", TU.logits_rows(lg), atol=(1e-4 if name == "fp32" else 2e-2) * scale)
+            agree = float((lg.argmax(1).numpy() == ref_arg).mean())
+            res[name] = (err, agree)
+        m.compute_dtype = torch.bfloat16
+        lab = torch.cat([m.predict_labels(x[i:i + 2].to(DEV)).cpu() for i in range(0, x.shape[0], 2)]).numpy()
+    agree_lab = float((lab == ref_arg).mean())
+    ref16_err, ref16_agree = float(z["ref_bf16_autocast_maxabs"]), float(z["ref_bf16_autocast_agree"])
+    print(f"[trained {config}] |logit| max {scale:.2f}; fp32: max-abs {res['fp32'][0]:.2e}, argmax {res['fp32'][1]:.6f}; bf16: max-abs "
+          f"{res['bf16'][0]:.2e}, argmax {res['bf16'][1]:.6f}, in-kernel argmax labels {agree_lab:.6f}; reference's own bf16 autocast: "
+          f"max-abs {ref16_err:.2e}, argmax {ref16_agree:.6f}")
+    assert res["fp32"][1] >= 0.9999
+    assert res["bf16"][0] <= ref16_err, "native bf16 must be at least as accurate as the reference's own bf16 autocast"
+    assert res["bf16"][1] >= 0.999 and agree_lab >= 0.999, (res, agree_lab)
+
+
+@pytest.mark.parametrize("config", ["t224", "512"])
+def test_trained_model_volume_dice_hd95(config):
+    """The test_single_volume loop (utils.py:61-90) on the bf16 engine vs the reference's stored label volume: per-class Dice and
+    HD95 against the task's ground truth identical to 1e-3, no class skipped."""
+    m, z = _native(config)
+    _, _, S, NC, D, VS = [int(v) for v in z["meta"]]
+    vol, gt = synth.synth_seg_volume(D, VS, NC, seed=77)
+    ref_pred = z["vol_pred"]
+    eng = cw.SliceEngine(m, batch=min(4, D), compute_dtype=torch.bfloat16)
+    for resample in ("scipy", "gpu"):
+        pred, _ = cw.predict_volume(eng, vol, resample=resample)
+        agree = float((pred == ref_pred).mean())
+        worst_d = worst_h = 0.0
+        for c in range(1, NC):
+            d_ref, h_ref = z["vol_metrics"][c - 1]
+            d_chk, h_chk = O.dice_hd95_percase(ref_pred == c, gt == c)
+            assert abs(d_chk - d_ref) < 1e-9 and abs(h_chk - h_ref) < 1e-9          # the fixture is self-consistent
+            d_new, h_new = O.dice_hd95_percase(pred == c, gt == c)
+            worst_d, worst_h = max(worst_d, abs(d_new - d_ref)), max(worst_h, abs(h_new - h_ref))
+        print(f"[trained {config} volume, resample={resample}] label agreement {agree:.6f}, worst per-class |dDice| {worst_d:.2e}, |dHD95| {worst_h:.2e}")
+        assert agree >= 0.999
+        assert worst_d <= 1e-3 and worst_h <= 1e-3, (worst_d, worst_h)

