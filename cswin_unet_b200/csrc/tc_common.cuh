@@ -207,33 +207,36 @@ __device__ __forceinline__ uint32_t add_bf16x2(uint32_t a, uint32_t b) {
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
 
-// GELU(erf) for the bf16 epilogue: x * Phi(x) with Phi(x) = 0.5 (1 + tanh(u (c0 + c1 u^2 + c2 u^4 + c3 u^6))), u = clamp(x, +-5.5):
-// the odd degree-7 minimax fit of atanh(erf(x / sqrt 2)) (max |dPhi| = 6.6e-6, max |dGELU| = 2.4e-5 for ALL x once the argument
-// is clamped — the raw polynomial turns over near |x| = 7.3, so it must never see larger arguments) evaluated with one MUFU
-// op (tanh.approx, error 2^-11): total error <= 2.5e-4 |x| for x >= -5.5, i.e. >= 16x below bf16 resolution; below -5.5 the
-// result is exactly 0 (true value > -1.1e-7) so the tanh error is not multiplied by a large |x|.  The fp32 SIMT path keeps erff.
+// GELU(erf) for the bf16 epilogue: x * Phi(x) with Phi(x) = 0.5 (1 + tanh(x (c0 + c1 x^2 + c2 x^4 + c3 x^6))), the odd degree-7
+// minimax fit of atanh(erf(x / sqrt 2)) (max |dPhi| = 6.6e-6, max |dGELU| = 2.4e-5) evaluated with one MUFU op (tanh.approx).
+// The raw polynomial turns over near |x| = 7.3 (the tanh argument would change sign: GELU(8) = 0, GELU(-8) = -8), so it is
+// evaluated at min(x^2, 5.5^2) — it is positive there, so the argument keeps the sign of x and |argument| >= 7.4 beyond |x| = 5.5
+// (tanh = +-1) — and x itself is clamped from below at -5.5 so that the 2^-11 error of tanh.approx is never multiplied by a
+// large |x| (GELU(-5.5) = -1e-7; the result below -5.5 is within 1.4e-3 of 0).  Total error <= 2.5e-4 |x| + 2.4e-5 for x >= -5.5,
+// i.e. >= 16x below bf16 resolution, for 2 FMNMX + 7 FMA-pipe + 1 MUFU instead of erff's ~40.  The fp32 SIMT path keeps erff.
 constexpr float kGeluClamp = 5.5f;
-__device__ __forceinline__ float gelu_tanh_arg(float x) {          // argument of the tanh in Phi(x); shared with GELU'
-  const float u = fminf(fmaxf(x, -kGeluClamp), kGeluClamp);
-  const float u2 = u * u;
-  float p = fmaf(u2, -1.36882761e-05f, -1.94451094e-04f);
-  p = fmaf(p, u2, 3.65466544e-02f);
-  p = fmaf(p, u2, 7.97820264e-01f);
-  return p * u;
-}
 __device__ __forceinline__ float gelu_fast(float x) {
+  const float xc = fmaxf(x, -kGeluClamp);
+  const float x2 = fminf(xc * xc, kGeluClamp * kGeluClamp);
+  float p = fmaf(x2, -1.36882761e-05f, -1.94451094e-04f);
+  p = fmaf(p, x2, 3.65466544e-02f);
+  p = fmaf(p, x2, 7.97820264e-01f);
   float t;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(gelu_tanh_arg(x)));
-  const float h = 0.5f * x;
-  return x < -kGeluClamp ? 0.f : fmaf(h, t, h);
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(p * xc));
+  const float h = 0.5f * xc;
+  return fmaf(h, t, h);
 }
-// GELU'(x) = Phi(x) + x phi(x): Phi from the same fit, phi through ex2.approx (two MUFU + ~11 FMA-pipe instructions)
+// GELU'(x) = Phi(x) + x phi(x): Phi from the same fit (same clamps), phi through ex2.approx (two MUFU + ~11 FMA-pipe instructions)
 __device__ __forceinline__ float gelu_grad_fast(float x) {
+  const float xc = fmaxf(x, -kGeluClamp);
+  const float x2 = fminf(xc * xc, kGeluClamp * kGeluClamp);
+  float p = fmaf(x2, -1.36882761e-05f, -1.94451094e-04f);
+  p = fmaf(p, x2, 3.65466544e-02f);
+  p = fmaf(p, x2, 7.97820264e-01f);
   float t, e;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(gelu_tanh_arg(x)));
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(p * xc));
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * x * -0.72134752044448170368f));
-  const float Phi = x < -kGeluClamp ? 0.f : fmaf(0.5f, t, 0.5f);
-  return fmaf(x * 0.39894228040143267794f, e, Phi);
+  return fmaf(x * 0.39894228040143267794f, e, fmaf(0.5f, t, 0.5f));
 }
 
 // ---- packed fp32 pairs (Blackwell FFMA2 / FADD2 / FMUL2: two fp32 operations per issue slot) ----
@@ -255,22 +258,20 @@ __device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
       : "l"(reinterpret_cast<const uint64_t&>(a)), "l"(reinterpret_cast<const uint64_t&>(b)));
   return d;
 }
-// gelu_fast on a pair: packed FP instructions + 2 MUFU for two elements (same clamp / saturation as gelu_fast)
+// gelu_fast on a pair: 4 FMNMX + 8 packed FP instructions + 2 MUFU for two elements
 __device__ __forceinline__ float2 gelu_fast2(float2 x) {
-  const float2 u = make_float2(fminf(fmaxf(x.x, -kGeluClamp), kGeluClamp), fminf(fmaxf(x.y, -kGeluClamp), kGeluClamp));
-  const float2 u2 = fmul2(u, u);
-  float2 p = ffma2(u2, make_float2(-1.36882761e-05f, -1.36882761e-05f), make_float2(-1.94451094e-04f, -1.94451094e-04f));
-  p = ffma2(p, u2, make_float2(3.65466544e-02f, 3.65466544e-02f));
-  p = ffma2(p, u2, make_float2(7.97820264e-01f, 7.97820264e-01f));
-  const float2 a = fmul2(p, u);
+  const float2 xc = make_float2(fmaxf(x.x, -kGeluClamp), fmaxf(x.y, -kGeluClamp));
+  float2 x2 = fmul2(xc, xc);
+  x2 = make_float2(fminf(x2.x, kGeluClamp * kGeluClamp), fminf(x2.y, kGeluClamp * kGeluClamp));
+  float2 p = ffma2(x2, make_float2(-1.36882761e-05f, -1.36882761e-05f), make_float2(-1.94451094e-04f, -1.94451094e-04f));
+  p = ffma2(p, x2, make_float2(3.65466544e-02f, 3.65466544e-02f));
+  p = ffma2(p, x2, make_float2(7.97820264e-01f, 7.97820264e-01f));
+  const float2 a = fmul2(p, xc);
   float2 t;
   asm("tanh.approx.f32 %0, %1;" : "=f"(t.x) : "f"(a.x));
   asm("tanh.approx.f32 %0, %1;" : "=f"(t.y) : "f"(a.y));
-  const float2 h = fmul2(x, make_float2(0.5f, 0.5f));
-  float2 r = ffma2(h, t, h);
-  r.x = x.x < -kGeluClamp ? 0.f : r.x;
-  r.y = x.y < -kGeluClamp ? 0.f : r.y;
-  return r;
+  const float2 h = fmul2(xc, make_float2(0.5f, 0.5f));
+  return ffma2(h, t, h);
 }
 
 // ---- thread-block clusters / distributed shared memory ----

@@ -29,6 +29,16 @@ from .modules import CARAFE, CARAFE4, CSWinBlock, Merge_Block, _Native, _no_auto
 Tensor = torch.Tensor
 
 
+# Inference forwards of a batch are split into CSWIN_STREAMS sub-batches that run on their own CUDA streams (fork / join, also
+# inside CUDA-graph capture).  At cswin_tiny sizes every kernel is at most one or two waves and latency-bound — barrier / TMEM
+# set-up, the first TMA round trip and the epilogue drain of one launch leave the tensor cores idle — so two independent launch
+# chains on the same SMs could hide each other's fill and drain.  Samples are independent (no batch statistics anywhere), results
+# are bit-identical to the unsplit forward.  MEASURED on B200 at batch 24 (profiles/r02_sweep_streams.log): 18,984 slices/s with one
+# chain, 18,018 / 16,703 / 16,348 with 2 / 3 / 4 — each launch is bound by its own latency chain (first TMA round trip, K loop at
+# the L2 -> SM ingest limit, epilogue), which does not get shorter with half the rows, and two chains contend for the same SMs.
+# Default 1 (off); kept as an A/B switch.
+N_STREAMS = max(1, int(os.environ.get("CSWIN_STREAMS", "1")))
+
 # training head folded like the inference head (CSWIN_UNFOLDED_TRAIN_HEAD=1 restores the reference's unfolded structure)
 FOLD_TRAIN_HEAD = os.environ.get("CSWIN_UNFOLDED_TRAIN_HEAD") != "1"
 
@@ -172,7 +182,7 @@ class CSWinTransformer(_Native):
         return self._ln(self.norm_up, x, "norm_up")
 
     def up_x4(self, x: Tensor, logits_dtype: Optional[torch.dtype] = None, want_logits: bool = True,
-              want_labels: bool = False):
+              want_labels: bool = False, out_logits: Optional[Tensor] = None, out_labels: Optional[Tensor] = None):
         """CARAFE4 + output conv with the two 1x1 maps folded (cswin_unet.py:536-544).  Returns NCHW logits
         (B, classes, 4H, 4W); with want_labels also / only the uint8 arg-max label map (utils.py:73-75)."""
         B, L, Cn = x.shape
@@ -212,29 +222,72 @@ class CSWinTransformer(_Native):
         if self.num_classes <= 16:
             logits, labels = ops.carafe_head(enc, z.view(B * L, -1), bf, B, H, W, up.up_factor, want_logits=want_logits,
                                              want_labels=want_labels, logits_dtype=logits_dtype or dt,
-                                             n_classes=self.num_classes)
+                                             n_classes=self.num_classes, out_logits=out_logits, out_labels=out_labels)
         else:                                                                   # generic re-assembly, labels via torch
             logits = ops.carafe_reassemble(enc, z.view(B * L, -1), bf, B, H, W, up.up_factor, nchw_out=True,
                                            out_dtype=logits_dtype or dt)
             labels = logits.argmax(1).to(torch.uint8) if want_labels else None
+            if out_logits is not None and want_logits:
+                out_logits.copy_(logits); logits = out_logits
+            if out_labels is not None and want_labels:
+                out_labels.copy_(labels); labels = out_labels
+        if want_labels:
+            return (logits, labels) if want_logits else labels
+        return logits
+
+    def _run(self, x: Tensor, logits_dtype, want_logits: bool, want_labels: bool, out_logits=None, out_labels=None):
+        x = self.forward_features(x)
+        x = self.forward_up_features(x)
+        return self.up_x4(x, logits_dtype=logits_dtype, want_logits=want_logits, want_labels=want_labels,
+                          out_logits=out_logits, out_labels=out_labels)
+
+    def _side_streams(self, device, n: int):
+        key = "_streams_%s" % (device,)
+        st = self.__dict__.get(key)
+        if st is None or len(st) < n:
+            st = [torch.cuda.Stream(device) for _ in range(n)]
+            self.__dict__[key] = st
+        return st[:n]
+
+    def _run_split(self, x: Tensor, logits_dtype, want_logits: bool, want_labels: bool):
+        """`_run` over N_STREAMS sub-batches on concurrent streams (inference only; see N_STREAMS)."""
+        B = x.shape[0]
+        n = min(N_STREAMS, B)
+        if (n <= 1 or not x.is_cuda or self.num_classes > 16
+                or ag.needs_grad(x, *self.parameters())):
+            return self._run(x, logits_dtype, want_logits, want_labels)
+        S = self.img_size
+        dt = logits_dtype or self.compute_dtype or x.dtype
+        logits = torch.empty((B, self.num_classes, S, S), dtype=dt, device=x.device) if want_logits else None
+        labels = torch.empty((B, S, S), dtype=torch.uint8, device=x.device) if want_labels else None
+        cur = torch.cuda.current_stream(x.device)
+        side = self._side_streams(x.device, n - 1)
+        fork = torch.cuda.Event()
+        fork.record(cur)
+        for i in range(n):
+            lo, hi = B * i // n, B * (i + 1) // n
+            s = cur if i == 0 else side[i - 1]
+            if i:
+                s.wait_event(fork)
+            with torch.cuda.stream(s):
+                self._run(x[lo:hi], dt, want_logits, want_labels, None if logits is None else logits[lo:hi],
+                          None if labels is None else labels[lo:hi])
+        for s in side:
+            cur.wait_stream(s)
         if want_labels:
             return (logits, labels) if want_logits else labels
         return logits
 
     def forward(self, x: Tensor) -> Tensor:
-        in_dt = x.dtype
-        x = self.forward_features(x)
-        x = self.forward_up_features(x)
         # logits leave in the dtype of the INPUT: an fp32 image through the bf16 compute path (compute_dtype) gets fp32 logits
         # straight from the head kernel's fp32 accumulators instead of a final rounding to bf16 (|logit| ~ 25 -> 0.1 absolute)
-        return self.up_x4(x, logits_dtype=in_dt if in_dt in (torch.float32, torch.bfloat16) else None)
+        in_dt = x.dtype
+        return self._run_split(x, in_dt if in_dt in (torch.float32, torch.bfloat16) else None, True, False)
 
     @torch.no_grad()
     def predict_labels(self, x: Tensor) -> Tensor:
         """argmax(softmax(forward(x)), 1) as uint8 (B, H, W), computed inside the head kernel (no logits written)."""
-        x = self.forward_features(x)
-        x = self.forward_up_features(x)
-        return self.up_x4(x, want_logits=False, want_labels=True)
+        return self._run_split(x, None, False, True)
 
 
 class CSwinUnet(nn.Module):

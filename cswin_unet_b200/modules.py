@@ -109,8 +109,13 @@ class DropPath(nn.Module):
 FUSE_MLP = os.environ.get("CSWIN_FUSE_MLP", "1") != "0"
 FUSE_MLP_MAX_DIM = int(os.environ.get("CSWIN_FUSE_MLP_MAX_DIM", "64"))
 FOLD_LN = os.environ.get("CSWIN_FOLD_LN", "1") != "0"     # LayerNorm folded into the tcgen05 Linear epilogue (bf16 inference)
-# [LN1 -> qkv -> both LePE attention branches] as one kernel (csrc/qkv_attn_tc.cu) where the block shape allows it
-FUSE_QKV_ATTN = os.environ.get("CSWIN_FUSE_QKV_ATTN", "1") != "0"
+# [LN1 -> qkv -> both LePE attention branches] as one kernel (csrc/qkv_attn_tc.cu) where the block shape allows it.  Bit-identical
+# to the composed path, one launch and the (B, L, 3C) qkv round trip fewer per block — and still SLOWER in the forward on B200
+# (17,433 vs 18,984 slices/s, profiles/r02_sweep_streams.log): with 24 images there are only 192 (image, branch, head pair, window)
+# work units at stage 3, each CTA runs GEMM -> epilogue -> two heads of attention back to back (14.3 us per CTA, in-kernel trace
+# profiles/r02_trace_qa_s3.log) where the two separate launches spread the same work over 444 + 384 shorter CTAs (5.7 + 8.5 us).
+# Default off; CSWIN_FUSE_QKV_ATTN=1 enables it.
+FUSE_QKV_ATTN = os.environ.get("CSWIN_FUSE_QKV_ATTN", "0") == "1"
 
 
 # Parameters can be written behind torch's back: the native fused SGD (train.TrainStep -> cswin_sgd_momentum_step) updates them

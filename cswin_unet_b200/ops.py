@@ -377,14 +377,21 @@ def carafe_reassemble(enc: Tensor, z: Tensor, bias: Tensor, B: int, H: int, W: i
 
 
 def carafe_head(enc: Tensor, z: Tensor, bias: Tensor, B: int, H: int, W: int, up: int, *, want_logits: bool = True,
-                want_labels: bool = False, logits_dtype: Optional[torch.dtype] = None, n_classes: Optional[int] = None):
+                want_labels: bool = False, logits_dtype: Optional[torch.dtype] = None, n_classes: Optional[int] = None,
+                out_logits: Optional[Tensor] = None, out_labels: Optional[Tensor] = None):
     """Folded segmentation head: returns (logits (B,C,up H,up W) or None, labels uint8 (B,up H,up W) or None).
-    z may be padded beyond n_classes columns (rows of 16 bf16 let the kernel use 16-byte loads)."""
-    _need_cuda(enc, z, bias)
+    z may be padded beyond n_classes columns (rows of 16 bf16 let the kernel use 16-byte loads).  `out_logits` / `out_labels`:
+    contiguous destination tensors of those shapes (e.g. a batch slice of a larger buffer) instead of fresh allocations."""
+    _need_cuda(enc, z, bias, out_logits, out_labels)
     Cn = n_classes or z.shape[-1]
     ld = logits_dtype or z.dtype
-    logits = torch.empty((B, Cn, H * up, W * up), dtype=ld, device=z.device) if want_logits else None
-    labels = torch.empty((B, H * up, W * up), dtype=torch.uint8, device=z.device) if want_labels else None
+    logits = labels = None
+    if want_logits:
+        logits = out_logits if out_logits is not None else torch.empty((B, Cn, H * up, W * up), dtype=ld, device=z.device)
+        assert logits.shape == (B, Cn, H * up, W * up) and logits.dtype == ld and logits.is_contiguous()
+    if want_labels:
+        labels = out_labels if out_labels is not None else torch.empty((B, H * up, W * up), dtype=torch.uint8, device=z.device)
+        assert labels.shape == (B, H * up, W * up) and labels.dtype == torch.uint8 and labels.is_contiguous()
     check(lib().cswin_carafe_head_fwd(enc.data_ptr(), enc.stride(0), z.data_ptr(), z.stride(0), bias.data_ptr(),
                                       _ptr(logits), int(ld == torch.float32), _ptr(labels), B, H, W, Cn, up,
                                       _dtype_code(z), _stream()), "cswin_carafe_head_fwd")

@@ -189,6 +189,20 @@ def main():
     out["vol_pred"] = pred
     mets = np.array([O.dice_hd95_percase(pred == c, gt == c) for c in range(1, NC)], np.float64)
     out["vol_metrics"] = mets
+    # yard-stick: the reference's OWN bf16 autocast through the same loop, and how far its metrics move
+    pred16 = np.zeros((D, VS, VS), np.uint8)
+    with torch.no_grad(), torch.autocast("cpu", dtype=torch.bfloat16):
+        for d in range(D):
+            sl = vol[d] if VS == S else zoom(vol[d], (S / VS, S / VS), order=3)
+            inp = torch.from_numpy(np.ascontiguousarray(sl))[None, None].float().repeat(1, 3, 1, 1)
+            o = torch.argmax(torch.softmax(m(inp).float(), dim=1), dim=1)[0].numpy()
+            pred16[d] = o if VS == S else zoom(o, (VS / S, VS / S), order=0)
+    mets16 = np.array([O.dice_hd95_percase(pred16 == c, gt == c) for c in range(1, NC)], np.float64)
+    out["ref_bf16_vol_agree"] = np.float64((pred16 == pred).mean())
+    out["ref_bf16_vol_ddice"] = np.float64(np.abs(mets16[:, 0] - mets[:, 0]).max())
+    out["ref_bf16_vol_dhd95"] = np.float64(np.abs(mets16[:, 1] - mets[:, 1]).max())
+    print(f"[{args.config}] reference bf16 autocast through the same loop: label agreement {out['ref_bf16_vol_agree']:.6f}, worst |dDice| "
+          f"{out['ref_bf16_vol_ddice']:.2e}, worst |dHD95| {out['ref_bf16_vol_dhd95']:.2e}")
     print(f"[{args.config}] volume {D}x{VS}^2: per-class (Dice, HD95) of the reference vs ground truth:\n{np.round(mets, 4)}")
     out["meta"] = np.array([args.steps, B, S, NC, D, VS], np.int64)
     path = os.path.join(HERE, f"trained_{args.config}.npz")

@@ -671,7 +671,7 @@ def test_gelu_epilogue_wide_range_bf16():
     for n_out in (K, K - 4):                                          # N % 8 == 0 -> TMA-store path; ragged N -> predicated path
         y = ops.linear(z.to(DEV), eye[:n_out].contiguous().to(DEV), None, act=1).float().cpu()
         assert ((y - ref[:, :n_out]).abs() <= tol(ref[:, :n_out])).all(), (y - ref[:, :n_out]).abs().max()
-        assert y[0, 0] == 0.0 and y[0, 1] == 0.0 and abs(y[0, 6].item() - 8.0) < 0.04 and abs(y[0, 7].item() - 20.0) < 0.1
+        assert abs(y[0, 0].item()) <= 2e-3 and abs(y[0, 1].item()) <= 2e-3 and abs(y[0, 6].item() - 8.0) < 0.04 and abs(y[0, 7].item() - 20.0) < 0.1
     # (b) streaming activation kernel
     y = ops.act_fwd(z.to(DEV), act=1).float().cpu()
     assert ((y - ref).abs() <= tol(ref)).all()
@@ -704,7 +704,7 @@ def test_gelu_grad_wide_range_bf16():
     ref = (0.5 * (1 + torch.erf(zd / 2 ** 0.5)) + zd * torch.exp(-zd * zd / 2) / (2 * torch.pi) ** 0.5).float()
     dz = ops.act_bwd(dh.to(DEV), z.to(DEV), None, 0, act=1).float().cpu()
     assert ((dz - ref).abs() <= 2.0 ** -8 * ref.abs() + 1e-3).all(), (dz - ref).abs().max()
-    assert dz[0, 0] == 0.0 and dz[0, 1] == 0.0 and abs(dz[0, 6].item() - 1.0) < 5e-3 and abs(dz[0, 7].item() - 1.0) < 5e-3
+    assert abs(dz[0, 0].item()) < 1e-6 and abs(dz[0, 1].item()) < 1e-6 and abs(dz[0, 6].item() - 1.0) < 5e-3 and abs(dz[0, 7].item() - 1.0) < 5e-3
     # act = 2 epilogue: dZ = (dH2 @ W) o GELU'(z) with W = I (w_kn layout) -> GELU'(z) itself
     eye = torch.eye(N).bfloat16()
     dz2 = ops.linear(dh.to(DEV), eye.to(DEV), w_kn=True, act=2, residual=z.to(DEV)).float().cpu()

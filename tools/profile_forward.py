@@ -14,7 +14,7 @@ shapes = {k: tuple(v.shape) for k, v in model.state_dict().items()}
 model.load_state_dict({k: torch.from_numpy(v) for k, v in synth.synth_state_dict(shapes, seed=1234).items()}, strict=True)
 model = model.to(dev); model.compute_dtype = torch.bfloat16
 x = torch.from_numpy(synth.synth_image_batch(B, 3, 224, seed=0, kind="ct")).to(dev)
-names = ["lepe_attention_fwd", "linear", "layernorm", "im2col_tokens", "im2col_nchw", "carafe_reassemble", "carafe_head"]
+names = ["qkv_lepe_attention", "mlp_fused", "row_stats", "layernorm_with_row_stats", "lepe_attention_fwd", "linear", "layernorm", "im2col_tokens", "im2col_nchw", "carafe_reassemble", "carafe_head"]
 calls = []
 origs = {n: getattr(ops, n) for n in names}
 def mk(n):
@@ -35,6 +35,12 @@ def desc(n, a, k):
         return f"M={m} N={k.get('n_out') or a[1].shape[0]} K={a[1].shape[1]} act={k.get('act',0)} res={int(k.get('residual') is not None)} ln={int(k.get('ln') is not None)} a2={int(k.get('a2') is not None)}"
     if n == "lepe_attention_fwd":
         d = a[0][0]; return f"B={a[1]} reso={a[2]} C_b={d['q'].shape[-1]} N={d['H_sp']*d['W_sp']} branches={len(a[0])}"
+    if n == "qkv_lepe_attention":
+        return f"B={a[0].shape[0]} reso={a[5]} C={a[0].shape[-1]} N={a[4][0]['H_sp']*a[4][0]['W_sp']} branches={len(a[4])}"
+    if n == "mlp_fused":
+        return f"M={a[0].numel()//a[0].shape[-1]} C={a[0].shape[-1]}"
+    if n in ("row_stats", "layernorm_with_row_stats"):
+        return f"M={a[0].numel()//a[0].shape[-1]} C={a[0].shape[-1]}"
     if n == "layernorm":
         return f"M={a[0].numel()//a[0].shape[-1]} C={a[0].shape[-1]}"
     return " ".join(str(tuple(t.shape)) for t in a if torch.is_tensor(t))

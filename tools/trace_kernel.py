@@ -20,6 +20,17 @@ if kind == "attn":
              if blk.branch_num == 2 else [blk.attns[0].branch_desc(q, k, v, out)])
     fn = lambda: ops.lepe_attention_fwd(descs, B, reso, float(blk.attns[0].scale), torch.bfloat16)
     names = ["entry", "prologue", "qkv_landed", "S_ready", "P_published", "lepe_done", "O_ready", "exit"]
+elif kind == "qa":
+    stage, B = int(sys.argv[2]), int(sys.argv[3])
+    C, reso, heads, split, last = [(64, 56, 2, 1, False), (128, 28, 4, 2, False), (256, 14, 8, 7, False)][stage - 1]
+    blk = cw.CSWinBlock(dim=C, reso=reso, num_heads=heads, split_size=split, qkv_bias=True, last_stage=last).to(DEV).eval()
+    x = torch.randn(B, reso * reso, C, device=DEV, dtype=torch.bfloat16)
+    st = ops.row_stats(x)
+    wq, csq, bq = blk._folded("qkv", blk.qkv, blk.norm1)
+    brs = [dict(conv_w=a.get_v.weight.detach().bfloat16(), conv_b=a.get_v.bias.detach().bfloat16(), heads=a.num_heads, H_sp=a.H_sp, W_sp=a.W_sp) for a in blk.attns]
+    out = torch.empty_like(x)
+    fn = lambda: ops.qkv_lepe_attention(x, wq, bq, (st, csq, 1e-5), brs, reso, float(blk.attns[0].scale), out=out)
+    names = ["entry", "prologue", "acc_ready", "tiles_published", "pv_issued", "-", "-", "exit"]
 elif kind == "mlp":
     M, C = int(sys.argv[2]), int(sys.argv[3])
     x = torch.randn(M, C, device=DEV, dtype=torch.bfloat16)
