@@ -5,7 +5,7 @@ torch.distributed); all arithmetic runs in hand-written CUDA through the C ABI i
 include/cswin_b200.h.  There is no CPU path and no library fallback.
 """
 from . import synth  # noqa: F401  (pure numpy; safe without the extension)
-from ._lib import CswinError, build, launch_count, lib, tc_launch_count  # noqa: F401
+from ._lib import CswinError, build, launch_count, lib, simt_fallback_count, tc_launch_count  # noqa: F401
 from .engine import SliceEngine, predict_volume, shard_slices  # noqa: F401
 from .install import install, uninstall  # noqa: F401
 from .model import CSWinTransformer, CSwinUnet, cswin_tiny_224  # noqa: F401
@@ -15,4 +15,4 @@ from .modules import (CARAFE, CARAFE4, CSWinBlock, DropPath, LePEAttention, Merg
 
 __all__ = ["LePEAttention", "CSWinBlock", "Mlp", "Merge_Block", "CARAFE", "CARAFE4", "DropPath", "img2windows",
            "windows2img", "CSWinTransformer", "CSwinUnet", "cswin_tiny_224", "SliceEngine", "shard_slices", "predict_volume", "TrainStep", "seg_loss", "install", "uninstall", "build", "lib",
-           "launch_count", "tc_launch_count", "CswinError", "synth", "invalidate_weight_caches"]
+           "launch_count", "tc_launch_count", "simt_fallback_count", "CswinError", "synth", "invalidate_weight_caches"]

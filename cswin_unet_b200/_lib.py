@@ -95,6 +95,7 @@ SIGNATURES = {
     "cswin_last_error": (C.c_char_p, []),
     "cswin_launch_count": (C.c_uint64, []),
     "cswin_tc_launch_count": (C.c_uint64, []),
+    "cswin_simt_fallback_count": (C.c_uint64, []),
     "cswin_debug_set_trace": (None, [c_void_p]),
     "cswin_lepe_attention_fwd": (c_int32, [C.POINTER(LepeBranch), c_int32, c_int32, c_int32, c_float, c_int32, c_void_p]),
     "cswin_lepe_attention_bwd": (c_int32, [C.POINTER(LepeBranchGrad), c_int32, c_int32, c_int32, c_float, c_int32, c_void_p]),
@@ -188,6 +189,11 @@ def check(rc: int, what: str) -> None:
 
 def launch_count() -> int:
     return int(lib().cswin_launch_count())
+
+
+def simt_fallback_count() -> int:
+    """bf16 calls that fell outside a tcgen05 kernel's envelope and ran on the general SIMT kernels (loud: warned once per op)."""
+    return int(lib().cswin_simt_fallback_count())
 
 
 def tc_launch_count() -> int:

@@ -44,6 +44,19 @@ int sm_count() {
 
 static bool valid_dtype(int dtype) { return dtype == CSWIN_F32 || dtype == CSWIN_BF16; }
 
+// bf16 calls that fall outside a tcgen05 kernel's envelope (window > 256 tokens, head_dim != 32, unaligned rows) run on the
+// general SIMT kernels: same results, up to ~45x slower.  That must not happen silently: every such launch is counted
+// (cswin_simt_fallback_count) and the FIRST one of each op prints one line to stderr (CSWIN_QUIET_FALLBACK=1 silences it).
+std::atomic<uint64_t> g_simt_fallbacks{0};
+static void note_simt_fallback(int op, const char* what) {
+  static std::atomic<int> warned[4] = {{0}, {0}, {0}, {0}};
+  g_simt_fallbacks.fetch_add(1, std::memory_order_relaxed);
+  static const bool quiet = [] { const char* e = getenv("CSWIN_QUIET_FALLBACK"); return e && e[0] == '1'; }();
+  if (!quiet && warned[op & 3].exchange(1) == 0)
+    fprintf(stderr, "[cswin_b200] warning: bf16 %s is outside the tcgen05 kernel's envelope (see include/cswin_b200.h) and runs on the "
+                    "general SIMT kernel — correct but much slower; further occurrences are only counted (cswin_simt_fallback_count).\n", what);
+}
+
 }  // namespace cswin
 
 using namespace cswin;
@@ -55,6 +68,7 @@ const char* cswin_last_error(void) { return t_err; }
 uint64_t cswin_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 void cswin_debug_set_trace(void* device_buffer) { g_trace.store((unsigned long long*)device_buffer); }
 uint64_t cswin_tc_launch_count(void) { return g_tc_launches.load(std::memory_order_relaxed); }
+uint64_t cswin_simt_fallback_count(void) { return g_simt_fallbacks.load(std::memory_order_relaxed); }
 
 int cswin_lepe_attention_fwd(const cswin_lepe_branch_t* branches, int32_t n_branches, int32_t B, int32_t reso,
                              float scale, int32_t dtype, cswin_stream_t stream) {
@@ -67,6 +81,7 @@ int cswin_lepe_attention_fwd(const cswin_lepe_branch_t* branches, int32_t n_bran
     bool handled = false;
     int rc = lepe_attention_fwd_tc(branches, n_branches, B, reso, scale, (cudaStream_t)stream, &handled);
     if (rc != CSWIN_OK || handled) return rc;
+    note_simt_fallback(0, "cswin_lepe_attention_fwd");
   }
   return lepe_attention_fwd_simt(branches, n_branches, B, reso, scale, dtype, (cudaStream_t)stream);
 }
@@ -82,6 +97,7 @@ int cswin_lepe_attention_bwd(const cswin_lepe_branch_grad_t* branches, int32_t n
     bool handled = false;
     int rc = lepe_attention_bwd_tc(branches, n_branches, B, reso, scale, (cudaStream_t)stream, &handled);
     if (rc != CSWIN_OK || handled) return rc;
+    note_simt_fallback(1, "cswin_lepe_attention_bwd");
   }
   return lepe_attention_bwd_simt(branches, n_branches, B, reso, scale, dtype, (cudaStream_t)stream);
 }
@@ -147,6 +163,7 @@ int cswin_linear_fwd(const cswin_linear_args_t* a, int32_t dtype, cswin_stream_t
     bool handled = false;
     int rc = linear_fwd_tc(a, (cudaStream_t)stream, &handled);
     if (rc != CSWIN_OK || handled) return rc;
+    if (!a->ln_gamma) note_simt_fallback(2, "cswin_linear_fwd");       // (a LayerNorm PROLOGUE is the SIMT kernel's documented job)
   }
   CSWIN_REQUIRE(!a->aux_out && a->act != 2, CSWIN_ERR_UNSUPPORTED, "linear_fwd: the training epilogues (aux_out, act 2) exist on the bf16 tcgen05 path with 16-byte aligned rows only");
   CSWIN_REQUIRE(!folded, CSWIN_ERR_UNSUPPORTED, "linear_fwd: operands are not TMA-compatible (16-byte aligned pointers / row pitches), which the folded-LayerNorm form requires");
@@ -207,6 +224,7 @@ int cswin_linear_wgrad(const void* dz, int64_t ldz, const void* a, int64_t lda, 
     bool handled = false;
     int rc = linear_wgrad_tc(dz, ldz, a, lda, dw, ldw, db, M, N, K, (cudaStream_t)stream, &handled);
     if (rc != CSWIN_OK || handled) return rc;
+    note_simt_fallback(3, "cswin_linear_wgrad");
   }
   return linear_wgrad(dz, ldz, a, lda, dw, ldw, db, M, N, K, dtype, (cudaStream_t)stream);
 }

@@ -49,6 +49,9 @@ const char* cswin_last_error(void);
 uint64_t cswin_launch_count(void);
 /* ... of which tcgen05 / TMEM / TMA kernels (attention_tc.cu, gemm_tc.cu); lets tests assert the tensor-core path ran */
 uint64_t cswin_tc_launch_count(void);
+/* bf16 calls that fell outside a tcgen05 kernel's envelope and ran on the general SIMT kernels instead (same results, much slower):
+ * counted here; the first occurrence per op also prints one warning line to stderr (CSWIN_QUIET_FALLBACK=1 silences it). */
+uint64_t cswin_simt_fallback_count(void);
 /* debug / profiling aid: when non-NULL, the tcgen05 kernels write %globaltimer stamps of their phases for the first 1024
  * CTAs of every launch into this device buffer (1024 x 16 uint64); NULL (default) disables it. Not part of the data path. */
 void cswin_debug_set_trace(void* device_buffer);

@@ -709,3 +709,21 @@ def test_gelu_grad_wide_range_bf16():
     eye = torch.eye(N).bfloat16()
     dz2 = ops.linear(dh.to(DEV), eye.to(DEV), w_kn=True, act=2, residual=z.to(DEV)).float().cpu()
     assert ((dz2 - ref).abs() <= 2.0 ** -8 * ref.abs() + 1e-3).all(), (dz2 - ref).abs().max()
+
+
+def test_bf16_simt_fallback_is_counted_and_the_model_never_takes_it():
+    """a bf16 call outside the tcgen05 envelope (here a 20x20 = 400-token window) runs on the general SIMT
+    kernel, which is reported (counter + one warning line), and the cswin_tiny forward never falls back."""
+    m, qkv = lepe_case(64, 20, -1, 20, 2, 1, torch.bfloat16)                 # one 20x20 = 400-token window: > 256, SIMT kernel
+    n0 = cw.simt_fallback_count()
+    with torch.no_grad():
+        y = m(qkv)
+    assert cw.simt_fallback_count() == n0 + 1 and torch.isfinite(y.float()).all()
+    model = build_model("alive")
+    model.compute_dtype = torch.bfloat16
+    x = T(synth.synth_image_batch(2, 3, 224, seed=0, kind="ct"))
+    n1 = cw.simt_fallback_count()
+    with torch.no_grad():
+        model(x)
+        model.predict_labels(x)
+    assert cw.simt_fallback_count() == n1, "the cswin_tiny_224 bf16 forward took a SIMT fallback"
