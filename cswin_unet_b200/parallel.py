@@ -70,12 +70,15 @@ class PoolGradReducer:
     keeps running on the main stream; `finish()` reduces the tail and joins the streams.  Capturable into the step's CUDA graph.
     Gradients that do not live in the pool (a few produced by torch ops on the tape) are handled by `allreduce_gradients`."""
 
-    def __init__(self, pool, group=None, bucket_bytes: int = 16 << 20):
+    def __init__(self, pool, group=None, bucket_bytes: int = 16 << 20, world: Optional[int] = None):
         self.pool, self.group, self.bucket = pool, group, bucket_bytes // 4
-        self.world = dist.get_world_size(group)
+        # world = 1 (no process group needed): no collective at all, but `after` still fires per bucket on the side stream — the
+        # single-GPU train step uses it to overlap the optimizer update of finished buckets with the rest of the backward
+        self.world = world if world is not None else dist.get_world_size(group)
         self.comm = torch.cuda.Stream() if pool.buf.is_cuda else None     # (CPU / gloo: same logic, no streams — used by the tests)
         # NCCL averages inside the collective (no per-bucket div_ launch); gloo has no AVG
-        self.avg = pool.buf.is_cuda and dist.get_backend(group) == "nccl"
+        self.avg = self.world > 1 and pool.buf.is_cuda and dist.get_backend(group) == "nccl"
+        self.after = None                  # callable(a, b): runs on the comm stream right after the range [a, b) has been reduced
         self.start = 0
         self.prev = 0
         self.n_coll = 0
@@ -102,18 +105,47 @@ class PoolGradReducer:
     def _launch(self, a: int, b: int) -> None:
         seg = self.pool.buf[a:b]
         if self.comm is None:
-            dist.all_reduce(seg, op=dist.ReduceOp.SUM, group=self.group)
-            seg.div_(self.world)
+            if self.world > 1:
+                dist.all_reduce(seg, op=dist.ReduceOp.SUM, group=self.group)
+                seg.div_(self.world)
+            if self.after is not None:
+                self.after(a, b)
         else:
             self.comm.wait_stream(torch.cuda.current_stream())     # the kernels that filled / read [a, b) are already enqueued there
             with torch.cuda.stream(self.comm):
-                if self.avg:
-                    dist.all_reduce(seg, op=dist.ReduceOp.AVG, group=self.group)
-                else:
-                    dist.all_reduce(seg, op=dist.ReduceOp.SUM, group=self.group)
-                    seg.div_(self.world)
-        self.n_coll += 1
+                if self.world > 1:
+                    if self.avg:
+                        dist.all_reduce(seg, op=dist.ReduceOp.AVG, group=self.group)
+                    else:
+                        dist.all_reduce(seg, op=dist.ReduceOp.SUM, group=self.group)
+                        seg.div_(self.world)
+                if self.after is not None:
+                    self.after(a, b)
+        if self.world > 1:
+            self.n_coll += 1
         self.launched.append((a, b))
+
+    def reduce_outside_pool(self, grads) -> None:
+        """Gradients that autograd materialised OUTSIDE the pool (a permuted clone of a re-packed conv weight's gradient): one
+        grouped all-reduce on the comm stream, in place, no packing copies; `finish()` joins."""
+        grads = [g for g in grads if g is not None]
+        if self.world <= 1 or not grads:
+            return
+        if self.comm is None:
+            for g in grads:
+                dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.group)
+                g.div_(self.world)
+            self.n_coll += 1
+            return
+        self.comm.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self.comm):
+            op = dist.ReduceOp.AVG if self.avg else dist.ReduceOp.SUM
+            with dist._coalescing_manager(group=self.group, device=grads[0].device, async_ops=False):
+                for g in grads:
+                    dist.all_reduce(g, op=op, group=self.group)
+            if not self.avg:
+                torch._foreach_div_(grads, float(self.world))
+        self.n_coll += 1
 
     def finish(self) -> None:
         """After backward() has returned: every consumer of every pool slice is enqueued, reduce the tail and join."""

@@ -108,8 +108,20 @@ class TrainStep:
         self._dice_group = (group if group is not None else True) if (global_dice and self._distributed) else None
         # all-reduce overlapped with the backward on the pooled gradient buffer (CSWIN_DDP_OVERLAP=0: bucketed all-reduce
         # after the backward, between two CUDA graphs)
-        self._reducer = parallel.PoolGradReducer(self._pool, group) if (
+        self._reducer = parallel.PoolGradReducer(self._pool, group, bucket_bytes=int(float(os.environ.get("CSWIN_DDP_BUCKET_MB", "16")) * (1 << 20))) if (
             self._distributed and self._pool is not None and os.environ.get("CSWIN_DDP_OVERLAP", "1") != "0") else None
+        # Optional (CSWIN_BUCKET_SGD=1): optimizer update per gradient bucket, on the reducer's side stream right after the bucket's
+        # all-reduce, so that neither the ~95 us fused SGD pass nor (N > 1) the wait for the last all-reduce sits at the end of the
+        # step.  Safe: a bucket holds gradients whose layers' backward kernels are already enqueued (PoolGradReducer), and nothing
+        # later in the backward reads those layers' parameters.  MEASURED slower on B200 — 1 GPU 6.12 vs 6.04 ms, 2 GPUs 6.34 vs
+        # 6.25 ms (profiles/r02_ddp_suite_2gpu.log): the update kernels then share HBM / SMs with the latency-bound backward
+        # kernels on the critical path instead of running alone at 5.5 TB/s — so the default stays ONE launch after the backward.
+        env = os.environ.get("CSWIN_BUCKET_SGD", "0")
+        self._bucket_sgd = (self._native_sgd and self._pool is not None and next(model.parameters()).is_cuda and env == "1"
+                            and (self._reducer is not None or not self._distributed))
+        if self._bucket_sgd and self._reducer is None:
+            self._reducer = parallel.PoolGradReducer(self._pool, None, world=1)
+        self._bk = None                      # bucket-SGD tables, built from the first backward's gradient layout
 
     def _make_shadow(self, dtype: torch.dtype) -> None:
         ps = [p for p in self.model.parameters() if p.dtype != dtype]
@@ -138,6 +150,8 @@ class TrainStep:
             torch._foreach_copy_(self._shadow_views, [p.detach() for p in self._shadow_src])
 
     def _optimizer_step(self) -> None:
+        if getattr(self, "_sgd_in_backward", False):           # already done, bucket by bucket, inside the backward
+            return
         if not self._native_sgd:
             self.opt.step()
             return
@@ -153,6 +167,60 @@ class TrainStep:
         ops.sgd_momentum_step(self._tbl_dev[:self._tbl_n], self.lr_dev, self.momentum, self.weight_decay)
         modules.bump_param_epoch()                             # raw-pointer write: invalidate every derived-weight cache
 
+    # ---- optimizer update per reduced bucket (see __init__) ------------------------------------------------------------------
+    def _build_bucket_tables(self) -> None:
+        """After a backward: split the parameters into those whose gradient lives in the pool (sorted by pool offset; their chunk
+        rows go to one device table that `_sgd_range` slices) and the rest (one small table)."""
+        import numpy as np
+        base = self._pool.buf.data_ptr()
+        inp, rest = [], []
+        for p, m in zip(self._params, self.momentum_buffers):
+            if p.grad is None:
+                continue
+            g = p.grad
+            (inp if (self._reducer.in_pool(g) and g.is_contiguous()) else rest).append((g.data_ptr(), p, g, m))
+        inp.sort(key=lambda t: t[0])
+
+        def table(rows):
+            if not rows:
+                return None, None
+            t = ops.sgd_chunk_table([r[1].detach() for r in rows], [r[2] for r in rows], [r[3] for r in rows],
+                                    [self._shadow_of.get(id(r[1])) for r in rows])
+            return t.to(self._pool.buf.device), (t[:, 1].numpy() - base) // 4
+        tp, offs = table(inp)
+        n_rest = sum((r[1].numel() + ops.SGD_CHUNK - 1) // ops.SGD_CHUNK for r in rest)
+        self._bk = {"pool": tp, "offs": np.asarray(offs) if offs is not None else None,
+                    "rest_params": [(r[1], r[3]) for r in rest],
+                    "rest_host": torch.empty((max(n_rest, 1), 5), dtype=torch.int64).pin_memory(),
+                    "rest_dev": torch.empty((max(n_rest, 1), 5), dtype=torch.int64, device=self._pool.buf.device), "n_rest": n_rest,
+                    # pooled gradients keep their addresses from step to step (same backward order); the few gradients autograd
+                    # clones outside the pool are fresh allocations every step and get their (tiny) table rebuilt below
+                    "key": tuple(t[0] for t in inp)}
+
+    def _sgd_rest(self) -> None:
+        """Update of the parameters whose gradient lives outside the pool (rebuilt table: their gradient tensors move)."""
+        bk = self._bk
+        if not bk["rest_params"]:
+            return
+        ps = [(p, m) for p, m in bk["rest_params"] if p.grad is not None]
+        t = ops.sgd_chunk_table([p.detach() for p, _ in ps], [p.grad.contiguous() for p, _ in ps], [m for _, m in ps],
+                                [self._shadow_of.get(id(p)) for p, _ in ps])
+        n = t.shape[0]
+        assert n <= bk["rest_host"].shape[0]
+        bk["rest_host"][:n].copy_(t)
+        bk["rest_dev"].copy_(bk["rest_host"], non_blocking=True)
+        ops.sgd_momentum_step(bk["rest_dev"][:n], self.lr_dev, self.momentum, self.weight_decay)
+
+    def _sgd_range(self, a: int, b: int) -> None:
+        """SGD update of every parameter whose (pooled) gradient lies in pool range [a, b): runs on the reducer's side stream."""
+        import numpy as np
+        bk = self._bk
+        if bk["pool"] is None:
+            return
+        lo, hi = int(np.searchsorted(bk["offs"], a, "left")), int(np.searchsorted(bk["offs"], b, "left"))
+        if hi > lo:
+            ops.sgd_momentum_step(bk["pool"][lo:hi], self.lr_dev, self.momentum, self.weight_decay)
+
     def _fwd_bwd(self, images: Tensor, labels: Tensor) -> Tensor:
         if self._shadow_src:
             if not self._native_sgd:                             # one multi-tensor fp32 -> compute-dtype copy per step
@@ -161,8 +229,13 @@ class TrainStep:
         if self._pool is not None:
             self._pool.reset()
             ag.POOL = self._pool
+        self._sgd_in_backward = False
         if self._reducer is not None:
             self._reducer.begin()
+            self._reducer.after = None
+            if self._bucket_sgd and self._bk is not None and not getattr(self, "_grads_only", False):
+                self._reducer.after = self._sgd_range
+                self._sgd_in_backward = True
         if self._drop_plan is not None:
             self._drop_plan.begin(images.shape[0], images.device)
             modules.DROP_PATH_PLAN = self._drop_plan
@@ -173,10 +246,24 @@ class TrainStep:
             modules.DROP_PATH_PLAN = None
             loss = seg_loss(logits, labels, self.n_classes, self._dice_group)
             loss.backward()
-            if self._reducer is not None:                       # tail bucket + gradients that live outside the pool
-                self._reducer.finish()
+            if self._reducer is not None:                       # gradients outside the pool, then the tail bucket, then join
                 rest = [p for p in self.model.parameters() if p.grad is not None and not self._reducer.in_pool(p.grad)]
-                parallel.allreduce_gradients(rest, self.group)
+                self._reducer.reduce_outside_pool([p.grad for p in rest])
+                if self._sgd_in_backward:
+                    key = tuple(sorted(p.grad.data_ptr() for p in self._params if p.grad is not None and self._reducer.in_pool(p.grad)
+                                       and p.grad.is_contiguous()))
+                    if key != self._bk["key"]:
+                        raise RuntimeError("TrainStep: the pooled gradient layout changed between steps while the optimizer update runs "
+                                           "per bucket inside the backward (set CSWIN_BUCKET_SGD=0 for models whose backward order varies)")
+                    cs = self._reducer.comm                      # on the side stream, after the grouped all-reduce of `rest`
+                    cs.wait_stream(torch.cuda.current_stream())
+                    with torch.cuda.stream(cs):
+                        self._sgd_rest()
+                self._reducer.finish()
+                if self._sgd_in_backward:
+                    modules.bump_param_epoch()
+                elif self._bucket_sgd and self._bk is None:
+                    self._build_bucket_tables()                 # layout known now: later steps update per bucket
         finally:
             modules.DROP_PATH_PLAN = None
             ag.SHADOW = {}
@@ -190,7 +277,11 @@ class TrainStep:
         leaves the (averaged) gradients in `p.grad`.  Eager; used by the N-rank gradient-parity check."""
         self._check_external_writes()
         self.opt.zero_grad(set_to_none=True)
-        loss = self._fwd_bwd(images, labels)
+        self._grads_only = True
+        try:
+            loss = self._fwd_bwd(images, labels)
+        finally:
+            self._grads_only = False
         if self._reducer is None and self._distributed:
             parallel.allreduce_gradients(self.model.parameters(), self.group)
         return loss
