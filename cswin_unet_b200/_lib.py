@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(_HERE, "libcswin_b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "cswin_b200.h")
 
 F32, BF16 = 0, 1
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 c_void_p, c_int32, c_int64, c_float = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 
@@ -90,6 +90,32 @@ class QkvAttnArgs(C.Structure):
     ]
 
 
+class StageBlock(C.Structure):
+    """== cswin_stage_block_t"""
+    _fields_ = [
+        ("w_qkv", c_void_p), ("cs_qkv", c_void_p), ("b_qkv", c_void_p), ("w_proj", c_void_p), ("b_proj", c_void_p),
+        ("w_fc1", c_void_p), ("cs_fc1", c_void_p), ("b_fc1", c_void_p), ("w_fc2", c_void_p), ("b_fc2", c_void_p),
+        ("lepe_w", c_void_p * 2), ("lepe_b", c_void_p * 2), ("eps1", c_float), ("eps2", c_float),
+    ]
+
+
+class StageArgs(C.Structure):
+    """== cswin_stage_args_t"""
+    _fields_ = [
+        ("x", c_void_p), ("stats_in", c_void_p), ("stats_in_parts", c_int32), ("n_blocks", c_int32),
+        ("qkv", c_void_p), ("att", c_void_p), ("x1", c_void_p), ("hid", c_void_p),
+        ("stats_x", c_void_p), ("stats_x1", c_void_p), ("ctrl", c_void_p), ("ctrl_ints", c_int64),
+        ("blocks", C.POINTER(StageBlock)),
+        ("B", c_int32), ("reso", c_int32), ("C", c_int32), ("hidden", c_int32), ("n_branches", c_int32), ("reserved", c_int32),
+        ("heads", c_int32 * 2), ("H_sp", c_int32 * 2), ("W_sp", c_int32 * 2), ("scale", c_float), ("reserved2", c_int32),
+    ]
+
+
+class StagePlan(C.Structure):
+    """== cswin_stage_plan_t"""
+    _fields_ = [("parts_x", c_int32), ("parts_x1", c_int32), ("max_blocks", c_int32), ("reserved", c_int32), ("ctrl_ints", c_int64)]
+
+
 SIGNATURES = {
     "cswin_abi_version": (c_int32, []),
     "cswin_last_error": (C.c_char_p, []),
@@ -118,6 +144,9 @@ SIGNATURES = {
     "cswin_qkv_lepe_attention_supported": (c_int32, [c_int32, c_int32, c_int32, C.POINTER(c_int32), C.POINTER(c_int32),
                                                      C.POINTER(c_int32)]),
     "cswin_linear_stats_parts": (c_int32, [c_int64, c_int32, c_int32, c_int32]),
+    "cswin_stage_plan": (c_int32, [c_int32, c_int32, c_int32, c_int32, c_int32, C.POINTER(c_int32), C.POINTER(c_int32),
+                                   C.POINTER(c_int32), C.POINTER(StagePlan)]),
+    "cswin_stage_fwd": (c_int32, [C.POINTER(StageArgs), c_int32, c_void_p]),
     "cswin_layernorm_stats_fwd": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int32, c_float,
                                             c_void_p, c_int32, c_void_p]),
     "cswin_row_stats": (c_int32, [c_void_p, c_int64, c_int64, c_int32, c_void_p, c_int32, c_void_p]),

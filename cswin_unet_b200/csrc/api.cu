@@ -303,6 +303,23 @@ int32_t cswin_qkv_lepe_attention_supported(int32_t C, int32_t reso, int32_t n_br
   return qkv_attn_supported(C, reso, n_branches, heads, H_sp, W_sp);
 }
 
+int cswin_stage_plan(int32_t B, int32_t reso, int32_t C, int32_t hidden, int32_t n_branches, const int32_t* heads,
+                     const int32_t* H_sp, const int32_t* W_sp, cswin_stage_plan_t* plan) {
+  CSWIN_REQUIRE(heads && H_sp && W_sp && plan, CSWIN_ERR_INVALID, "stage_plan: null pointer");
+  const int rc = stage_plan(B, reso, C, hidden, n_branches, heads, H_sp, W_sp, plan);
+  if (rc != CSWIN_OK) set_error("stage_plan: shape outside the persistent stage kernel's envelope");
+  return rc;
+}
+
+int cswin_stage_fwd(const cswin_stage_args_t* a, int32_t dtype, cswin_stream_t stream) {
+  CSWIN_REQUIRE(a != nullptr, CSWIN_ERR_INVALID, "stage_fwd: null args");
+  CSWIN_REQUIRE(dtype == CSWIN_BF16, CSWIN_ERR_UNSUPPORTED, "stage_fwd: exists on the bf16 / tcgen05 path only");
+  CSWIN_REQUIRE(a->x && a->qkv && a->att && a->x1 && a->hid && a->blocks && a->n_blocks >= 1 && a->B >= 0 && a->reso > 0 &&
+                a->n_branches >= 1 && a->n_branches <= 2, CSWIN_ERR_INVALID, "stage_fwd: bad arguments");
+  if (a->B == 0) return CSWIN_OK;
+  return stage_fwd_tc(a, (cudaStream_t)stream);
+}
+
 int32_t cswin_linear_stats_parts(int64_t M, int32_t N, int32_t K, int32_t act) { return linear_tc_stats_parts(M, N, K, act); }
 
 int cswin_row_stats(const void* x, int64_t ldx, int64_t M, int32_t C, float* stats, int32_t dtype, cswin_stream_t stream) {

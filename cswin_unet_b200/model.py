@@ -24,7 +24,7 @@ import torch.nn as nn
 
 from . import autograd as ag
 from . import ops
-from .modules import CARAFE, CARAFE4, CSWinBlock, Merge_Block, _Native, _no_autograd
+from .modules import CARAFE, CARAFE4, CSWinBlock, Merge_Block, _Native, _no_autograd, run_stage
 
 Tensor = torch.Tensor
 
@@ -151,34 +151,26 @@ class CSWinTransformer(_Native):
         if dt not in (torch.float32, torch.bfloat16):
             raise TypeError(f"compute dtype must be float32 or bfloat16, got {dt}")
         x = self._stem(x, dt)
-        for blk in self.stage1:
-            x = blk(x)
+        x = run_stage(self.stage1, x)
         self.x1 = x
         x = self.merge1(x)
-        for blk in self.stage2:
-            x = blk(x)
+        x = run_stage(self.stage2, x)
         self.x2 = x
         x = self.merge2(x)
-        for blk in self.stage3:
-            x = blk(x)
+        x = run_stage(self.stage3, x)
         self.x3 = x
         x = self.merge3(x)
-        for blk in self.stage4:
-            x = blk(x)
+        x = run_stage(self.stage4, x)
         return self._ln(self.norm, x, "norm")
 
     def forward_up_features(self, x: Tensor) -> Tensor:
-        for blk in self.stage_up4:
-            x = blk(x)
+        x = run_stage(self.stage_up4, x)
         x = self._skip_linear(self.concat_linear4, self.x3, self.upsample4(x), "cl4")
-        for blk in self.stage_up3:
-            x = blk(x)
+        x = run_stage(self.stage_up3, x)
         x = self._skip_linear(self.concat_linear3, self.x2, self.upsample3(x), "cl3")
-        for blk in self.stage_up2:
-            x = blk(x)
+        x = run_stage(self.stage_up2, x)
         x = self._skip_linear(self.concat_linear2, self.x1, self.upsample2(x), "cl2")
-        for blk in self.stage_up1:
-            x = blk(x)
+        x = run_stage(self.stage_up1, x)
         return self._ln(self.norm_up, x, "norm_up")
 
     def up_x4(self, x: Tensor, logits_dtype: Optional[torch.dtype] = None, want_logits: bool = True,

@@ -461,6 +461,63 @@ class CSWinBlock(_Native):
                       sample_scale=self._sample_scale(x), rps=L)
 
 
+# All blocks of a stage as ONE persistent dataflow launch (csrc/stage_tc.cu) instead of 5 launches per block: same tiles, same
+# arithmetic as the composed path, ordered by per-row-tile completion counters instead of kernel boundaries.  CSWIN_STAGE_EXEC
+# lists the block dims that use it ("0" = never, default see below); anything outside the kernel's envelope, training, fp32 and
+# DropPath-active calls run the composed path.
+STAGE_EXEC_DIMS = tuple(int(t) for t in os.environ.get("CSWIN_STAGE_EXEC", "256").split(",") if t.strip() not in ("", "0"))
+
+
+def _stage_block_desc(blk: "CSWinBlock") -> dict:
+    dt = torch.bfloat16
+    w = blk._w
+    wq, csq, bq = blk._folded("qkv", blk.qkv, blk.norm1)
+    w1, cs1, b1 = blk._folded("fc1", blk.mlp.fc1, blk.norm2)
+    b32 = lambda t: t.to(dt).float()                          # the composed path adds the bf16-rounded bias in fp32
+    return dict(w_qkv=wq, cs_qkv=csq, b_qkv=bq, w_proj=w("proj.w", blk.proj.weight, dt),
+                b_proj=w("proj.b32", blk.proj.bias, torch.float32, b32), w_fc1=w1, cs_fc1=cs1, b_fc1=b1,
+                w_fc2=w("fc2.w", blk.mlp.fc2.weight, dt), b_fc2=w("fc2.b32r", blk.mlp.fc2.bias, torch.float32, b32),
+                lepe_w=[a._w("cw", a.get_v.weight, dt).contiguous() for a in blk.attns],
+                lepe_b=[a._w("cb", a.get_v.bias, dt).contiguous() for a in blk.attns],
+                eps1=float(blk.norm1.eps), eps2=float(blk.norm2.eps))
+
+
+def run_stage(blocks, x: Tensor) -> Tensor:
+    """`for blk in blocks: x = blk(x)` (cswin_unet.py:462-478, :505-533).  bf16 inference on an eligible stage runs all blocks
+    in one persistent launch and OVERWRITES x (always a fresh activation: stem / Merge_Block / skip-Linear output)."""
+    blocks = list(blocks)
+    b0 = blocks[0] if blocks else None
+    ok = (b0 is not None and x.is_cuda and x.dtype == torch.bfloat16 and FOLD_LN and b0.dim in STAGE_EXEC_DIMS
+          and not ag.needs_grad(x, *(p for b in blocks for p in b.parameters()))
+          and all((not b.training or not isinstance(b.drop_path, DropPath) or b.drop_path.drop_prob == 0.) for b in blocks)
+          and all(b.dim == b0.dim and b.patches_resolution == b0.patches_resolution and b.branch_num == b0.branch_num
+                  and b.mlp.fc1.out_features == b0.mlp.fc1.out_features and b.qkv.weight.shape[0] == 3 * b0.dim
+                  and [(a.num_heads, a.H_sp, a.W_sp) for a in b.attns] == [(a.num_heads, a.H_sp, a.W_sp) for a in b0.attns]
+                  and float(b.attns[0].scale) == float(b0.attns[0].scale) for b in blocks))
+    plan = None
+    if ok:
+        B, L, Cn = x.shape
+        branches = [(a.num_heads, a.H_sp, a.W_sp) for a in b0.attns]
+        key = ("_stage_plan", B)
+        plan = b0.__dict__.get(key, False)
+        if plan is False:
+            plan = ops.stage_plan(B, b0.patches_resolution, Cn, b0.mlp.fc1.out_features, branches) if L == b0.patches_resolution ** 2 else None
+            b0.__dict__[key] = plan
+    if plan is None:
+        for blk in blocks:
+            x = blk(x)
+        return x
+    for a in b0.attns:
+        a._check(L)
+    st = getattr(x, "_cswin_stats", None)
+    if st is None or st.shape[0] != B * L:
+        st = ops.row_stats(x)
+    if not x.is_contiguous():
+        x = x.contiguous()
+    return ops.stage_forward(x, st, [_stage_block_desc(b) for b in blocks], b0.patches_resolution, b0.mlp.fc1.out_features,
+                             branches, float(b0.attns[0].scale), plan)
+
+
 # ------------------------------------------------------------------------------------------
 # Merge_Block / CARAFE / CARAFE4
 # ------------------------------------------------------------------------------------------

@@ -12,7 +12,8 @@ from typing import Optional, Sequence, Tuple
 import torch
 
 from . import _lib
-from ._lib import BF16, F32, LepeBranch, LepeBranchGrad, LinearArgs, MlpArgs, QkvAttnArgs, check, lib
+from ._lib import (BF16, F32, LepeBranch, LepeBranchGrad, LinearArgs, MlpArgs, QkvAttnArgs, StageArgs, StageBlock, StagePlan,
+                   check, lib)
 
 Tensor = torch.Tensor
 
@@ -294,6 +295,81 @@ def qkv_lepe_attention(x: Tensor, w: Tensor, bias_f32: Optional[Tensor], ln_fold
         a.br[i].heads, a.br[i].H_sp, a.br[i].W_sp = b["heads"], b["H_sp"], b["W_sp"]
     check(lib().cswin_qkv_lepe_attention_fwd(C.byref(a), BF16, _stream()), "cswin_qkv_lepe_attention_fwd")
     return out
+
+
+def stage_plan(B: int, reso: int, Cn: int, hidden: int, branches: Sequence[Tuple[int, int, int]]):
+    """branches: [(heads, H_sp, W_sp)].  Returns the StagePlan of the persistent stage kernel, or None outside its envelope."""
+    n = len(branches)
+    arr = lambda i: (C.c_int32 * 2)(*([b[i] for b in branches] + [0] * (2 - n)))
+    plan = StagePlan()
+    rc = lib().cswin_stage_plan(B, reso, Cn, hidden, n, arr(0), arr(1), arr(2), C.byref(plan))
+    return plan if rc == 0 else None
+
+
+_STAGE_WS = {}
+
+
+def _stage_workspace(x: Tensor, hidden: int, plan) -> dict:
+    """qkv / att / x1 / hid / statistics / ctrl buffers of the stage kernel, cached per (device, stream, shape): the launches of
+    one stream are ordered, so consecutive stages of the same shape share them; ctrl is zeroed once here and left zeroed by the
+    kernel."""
+    B, L, Cn = x.shape
+    key = (x.device, torch.cuda.current_stream().cuda_stream, B, L, Cn, hidden)
+    ws = _STAGE_WS.get(key)
+    if ws is None:
+        M = B * L
+        e = lambda *shape, dt=torch.bfloat16: torch.empty(shape, dtype=dt, device=x.device)
+        ws = dict(qkv=e(M, 3 * Cn), att=e(M, Cn), x1=e(M, Cn), hid=e(M, hidden),
+                  stats_x=e(M, plan.parts_x, 2, dt=torch.float32), stats_x1=e(M, plan.parts_x1, 2, dt=torch.float32),
+                  ctrl=torch.zeros(plan.ctrl_ints, dtype=torch.int32, device=x.device))
+        _STAGE_WS[key] = ws
+    return ws
+
+
+def stage_forward(x: Tensor, stats_in: Tensor, blocks: Sequence[dict], reso: int, hidden: int,
+                  branches: Sequence[Tuple[int, int, int]], scale: float, plan=None) -> Tensor:
+    """All CSWinBlocks of one stage in one persistent launch per <= plan.max_blocks blocks (cswin_stage_fwd).  x (B, L, C) bf16
+    contiguous is OVERWRITTEN with the stage's output and returned.  blocks: [{w_qkv, cs_qkv, b_qkv, w_proj, b_proj, w_fc1, cs_fc1,
+    b_fc1, w_fc2, b_fc2, lepe_w: [..], lepe_b: [..], eps1, eps2}] (see include/cswin_b200.h); stats_in (M, parts, 2) fp32."""
+    _need_cuda(x, stats_in)
+    assert x.dtype == torch.bfloat16 and x.dim() == 3 and x.is_contiguous()
+    B, L, Cn = x.shape
+    assert L == reso * reso and stats_in.dtype == torch.float32 and stats_in.is_contiguous() and stats_in.shape[0] == B * L
+    plan = plan or stage_plan(B, reso, Cn, hidden, branches)
+    if plan is None:
+        raise _lib.CswinError("stage_forward: shape outside the persistent stage kernel's envelope")
+    ws = _stage_workspace(x, hidden, plan)
+    n = len(branches)
+    st, parts = stats_in, stats_in.shape[1]
+    for lo in range(0, len(blocks), plan.max_blocks):
+        chunk = blocks[lo:lo + plan.max_blocks]
+        arr = (StageBlock * len(chunk))()
+        for i, b in enumerate(chunk):
+            for k in ("w_qkv", "w_proj", "w_fc1", "w_fc2"):
+                assert b[k].dtype == torch.bfloat16 and b[k].is_contiguous() and b[k].is_cuda
+            for k in ("cs_qkv", "b_qkv", "b_proj", "cs_fc1", "b_fc1", "b_fc2"):
+                assert b[k].dtype == torch.float32 and b[k].is_contiguous() and b[k].is_cuda
+            assert b["w_qkv"].shape == (3 * Cn, Cn) and b["w_proj"].shape == (Cn, Cn) and b["w_fc1"].shape == (hidden, Cn)
+            assert b["w_fc2"].shape == (Cn, hidden)
+            d = arr[i]
+            for k in ("w_qkv", "cs_qkv", "b_qkv", "w_proj", "b_proj", "w_fc1", "cs_fc1", "b_fc1", "w_fc2", "b_fc2"):
+                setattr(d, k, b[k].data_ptr())
+            for j in range(n):
+                cw, cb = b["lepe_w"][j], b["lepe_b"][j]
+                assert cw.dtype == torch.bfloat16 and cb.dtype == torch.bfloat16 and cw.is_contiguous() and cb.is_contiguous()
+                d.lepe_w[j], d.lepe_b[j] = cw.data_ptr(), cb.data_ptr()
+            d.eps1, d.eps2 = b["eps1"], b["eps2"]
+        a = StageArgs()
+        a.x, a.stats_in, a.stats_in_parts, a.n_blocks = x.data_ptr(), st.data_ptr(), parts, len(chunk)
+        a.qkv, a.att, a.x1, a.hid = (ws[k].data_ptr() for k in ("qkv", "att", "x1", "hid"))
+        a.stats_x, a.stats_x1, a.ctrl, a.ctrl_ints = ws["stats_x"].data_ptr(), ws["stats_x1"].data_ptr(), ws["ctrl"].data_ptr(), ws["ctrl"].numel()
+        a.blocks = arr
+        a.B, a.reso, a.C, a.hidden, a.n_branches, a.scale = B, reso, Cn, hidden, n, scale
+        for j, (h, hs, wsp) in enumerate(branches):
+            a.heads[j], a.H_sp[j], a.W_sp[j] = h, hs, wsp
+        check(lib().cswin_stage_fwd(C.byref(a), BF16, _stream()), "cswin_stage_fwd")
+        st, parts = ws["stats_x"], plan.parts_x                 # the next chunk continues from this one's row statistics
+    return x
 
 
 SGD_CHUNK = 65536

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define CSWIN_ABI_VERSION 5
+#define CSWIN_ABI_VERSION 6
 
 typedef struct CUstream_st* cswin_stream_t; /* == cudaStream_t */
 
@@ -232,6 +232,47 @@ typedef struct {
 int cswin_qkv_lepe_attention_fwd(const cswin_qkv_attn_args_t* args, int32_t dtype, cswin_stream_t stream);
 int32_t cswin_qkv_lepe_attention_supported(int32_t C, int32_t reso, int32_t n_branches, const int32_t* heads, const int32_t* H_sp,
                                            const int32_t* W_sp);
+
+/* ---- all CSWinBlocks of one stage in ONE persistent dataflow launch (bf16 / tcgen05 only, inference) ------------------------
+ * replaces the stage loops `for blk in self.stageN: x = blk(x)` (networks/cswin_unet.py:462-478, :505-533) over
+ * CSWinBlock.forward (:160-181): per block norm1 + qkv :168-169, both LePEAttention.forward calls + cat :172-176 (:82-109),
+ * proj + residual :177-178, norm2 + Mlp + residual :179 (Mlp :22-26) — DropPath is the identity in eval mode.
+ * The 128 x BN Linear tiles and 128-row attention tiles of cswin_linear_fwd / cswin_lepe_attention_fwd (same arithmetic) are
+ * pulled from one in-order tile counter by resident CTAs and ordered by per-row-tile / per-image completion counters, so that
+ * row tile m of an op starts when row tile m of its producer is complete: no launch gaps, no grid-wide barriers between the
+ * 5 x n_blocks ops.  LayerNorms are folded exactly as in cswin_linear_args_t.
+ *   x         : (B, L = reso^2, C) bf16 contiguous, IN: input of the first block, OUT: output of the last block
+ *   stats_in  : (M = B L, stats_in_parts, 2) fp32 per-row partial (sum, sum^2) of x, written by the producer of x
+ *   qkv, att, x1, hid : workspaces (M, 3C), (M, C), (M, C), (M, hidden) bf16 contiguous, 16-byte aligned
+ *   stats_x, stats_x1 : (M, plan.parts_x, 2), (M, plan.parts_x1, 2) fp32; after the call stats_x holds the row statistics of x
+ *   ctrl      : plan.ctrl_ints int32, ZEROED ONCE by the caller when it is allocated; the kernel leaves it zeroed.  One ctrl
+ *               buffer must not be used by two launches that may run concurrently (different streams).
+ *   blocks    : HOST array of n_blocks <= plan.max_blocks descriptors (device pointers inside)
+ *   heads / H_sp / W_sp : the block's attention branches (branch i owns channels [32 sum_{j<i} heads_j, +32 heads_i))
+ * Envelope (cswin_stage_plan returns CSWIN_ERR_UNSUPPORTED outside it): C and hidden multiples of 64, head_dim 32, stripe
+ * windows of <= 128 tokens. */
+typedef struct {
+  const void* w_qkv; const float* cs_qkv; const float* b_qkv;     /* (3C, C) bf16 W o gamma1; (3C) fp32 column sums; (3C) fp32 b + W beta1 */
+  const void* w_proj; const float* b_proj;                         /* (C, C) bf16; (C) fp32 */
+  const void* w_fc1; const float* cs_fc1; const float* b_fc1;     /* (hidden, C) bf16 W o gamma2; (hidden) fp32; (hidden) fp32 */
+  const void* w_fc2; const float* b_fc2;                           /* (C, hidden) bf16; (C) fp32 */
+  const void* lepe_w[2]; const void* lepe_b[2];                    /* get_v.weight (C_b,1,3,3) / get_v.bias (C_b) per branch, bf16 */
+  float eps1, eps2;                                                /* norm1.eps, norm2.eps */
+} cswin_stage_block_t;
+typedef struct {
+  void* x; const float* stats_in; int32_t stats_in_parts; int32_t n_blocks;
+  void* qkv; void* att; void* x1; void* hid;
+  float* stats_x; float* stats_x1;
+  int32_t* ctrl; int64_t ctrl_ints;
+  const cswin_stage_block_t* blocks;
+  int32_t B, reso, C, hidden, n_branches, reserved;
+  int32_t heads[2], H_sp[2], W_sp[2];
+  float scale; int32_t reserved2;
+} cswin_stage_args_t;
+typedef struct { int32_t parts_x, parts_x1, max_blocks, reserved; int64_t ctrl_ints; } cswin_stage_plan_t;
+int cswin_stage_plan(int32_t B, int32_t reso, int32_t C, int32_t hidden, int32_t n_branches, const int32_t* heads,
+                     const int32_t* H_sp, const int32_t* W_sp, cswin_stage_plan_t* plan);
+int cswin_stage_fwd(const cswin_stage_args_t* args, int32_t dtype, cswin_stream_t stream);
 
 /* ---- backward of cswin_carafe_head_fwd (the folded CARAFE4 + out + output head, up = 4; 2, 3, 4 or 9 classes) ---------------
  * dlogits: fp32 NCHW (B, C, 4H, 4W) contiguous.  Writes d enc (B*H*W, 144) and d z (B*H*W, zcols; columns >= C are zeroed),
