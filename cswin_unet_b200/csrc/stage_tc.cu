@@ -49,6 +49,24 @@ constexpr int kAttScratch = 3 * kAttOperand;  // Wt [2][9][32] f32, Bc [2][32] f
 constexpr int kAttStageBytes = kAttScratch + 2 * 9 * 32 * 4 + 2 * 32 * 4 + 2 * 128 * 4;
 constexpr int kCtrlFlags = 64;                // ctrl[0] tile counter, ctrl[32] finished-CTA counter, flags from ctrl[64]
 
+// -DCSWIN_STAGE_PROFILE: per-CTA cycle accounting of every wait (written to the debug trace buffer, tools/trace_stage.py)
+#ifdef CSWIN_STAGE_PROFILE
+#define PROF_DECL(...) uint32_t __VA_ARGS__
+#define PROF_T0(t) const long long t = clock64()
+#define PROF_ACC(t, acc) acc += (uint32_t)(clock64() - t)
+#define PROF_OUT(slot, v) do { if (P.trace != nullptr && !P.tile_trace && blockIdx.x < 1024) P.trace[(size_t)blockIdx.x * 16 + (slot)] = (v); } while (0)
+// CSWIN_STAGE_TILE_TRACE=1: the trace buffer is (total tiles, 10) uint64 and receives %globaltimer stamps per TILE instead
+#define TSTAMP(t, slot) do { if (P.tile_trace) { unsigned long long gt_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_)); P.trace[(size_t)(t) * 10 + (slot)] = gt_; } } while (0)
+#define TVAL(t, slot, v) do { if (P.tile_trace) P.trace[(size_t)(t) * 10 + (slot)] = (v); } while (0)
+#else
+#define TSTAMP(t, slot)
+#define TVAL(t, slot, v)
+#define PROF_DECL(...)
+#define PROF_T0(t)
+#define PROF_ACC(t, acc)
+#define PROF_OUT(slot, v)
+#endif
+
 enum { OP_QKV = 0, OP_ATT = 1, OP_PROJ = 2, OP_FC1 = 3, OP_FC2 = 4, N_OPS = 5 };
 
 struct GemmOp { int N, nkb, BN, nch, act, fold, has_res, pad; };
@@ -76,6 +94,7 @@ struct alignas(64) StageParams {
   int mt, U, tpb, total, att_tiles_img, S, stage_bytes, pad;
   int t0[N_OPS + 1];                                  // first tile of each op inside a block (block order), t0[5] = tiles per block
   float scale, scale_log2e, invC, pad2;
+  unsigned long long* trace; int tile_trace, pad3;
 };
 
 __device__ __forceinline__ int ld_acquire(const int* p) {
@@ -107,7 +126,6 @@ __device__ __forceinline__ void wait_flag(const int* p, int need) {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
   uint32_t spins = 0;
   while (ld_acquire(p) < need) {
-    __nanosleep(32);
     if ((++spins & 0xff) == 0) {
       uint64_t t1;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
@@ -198,26 +216,36 @@ __global__ void __launch_bounds__(kThreads, 2) stage_tc_kernel(const __grid_cons
     if (elect_one()) {
       uint32_t rc = 0;                          // ring stages produced so far
       int qi = 0; uint32_t qph = 1;
+      PROF_DECL(p_dep = 0, p_empty = 0, p_tq = 0, p_tiles = 0);
+      PROF_T0(p_start);
       int next = atomicAdd(P.ctrl, 1);
       for (;;) {
+        PROF_T0(tq0);
         const int t = next;
         if (t < P.total) next = atomicAdd(P.ctrl, 1);      // in flight while this tile's loads are issued
         mbar_wait(tq_empty(qi), qph);
+        PROF_ACC(tq0, p_tq);
         tq[qi] = t < P.total ? t : -1;
         mbar_arrive(tq_full(qi));
         if (++qi == kQ) { qi = 0; qph ^= 1; }
         if (t >= P.total) break;
         const Tile T = decode(P, t);
         const Dep d = deps_of(P, T);
+        TSTAMP(t, 0); TVAL(t, 8, (unsigned long long)blockIdx.x); TVAL(t, 9, (unsigned long long)(T.j | (T.op << 8) | (T.m << 12) | ((unsigned long long)T.n << 32)));
         if (T.op == OP_ATT) {
           const AttBranch& br = P.br[(P.nb > 1 && T.n >= P.br[0].tiles_img) ? 1 : 0];
           const int bi = (P.nb > 1 && T.n >= P.br[0].tiles_img) ? 1 : 0;
           const int p0 = (T.n - (bi ? P.br[0].tiles_img : 0)) * br.slots;
           const int np = min(br.slots, br.nprob_img - p0);
           const int s = rc % S; const uint32_t ph = (rc / S) & 1;
+          PROF_T0(e0);
           mbar_wait(empty(s), ph ^ 1);
+          PROF_ACC(e0, p_empty);
+          PROF_T0(d0);
           wait_deps(d);
           fence_proxy_async_all();
+          PROF_ACC(d0, p_dep);
+          TSTAMP(t, 1);
           mbar_expect_tx(full(s), (uint32_t)(np * 3 * br.N * 64));
           const uint32_t base = smem_u32(ring + (size_t)s * P.stage_bytes);
           const int slot_rows = BM / br.slots;
@@ -238,23 +266,36 @@ __global__ void __launch_bounds__(kThreads, 2) stage_tc_kernel(const __grid_cons
           bool waited = d.f == nullptr;
           for (int kb = 0; kb < op.nkb; ++kb, ++rc) {
             const int s = rc % S; const uint32_t ph = (rc / S) & 1;
+            PROF_T0(e0);
             mbar_wait(empty(s), ph ^ 1);
+            PROF_ACC(e0, p_empty);
             const uint32_t base = smem_u32(ring + (size_t)s * P.stage_bytes);
             mbar_expect_tx(full(s), kABytes + w_bytes);
             tma_load_2d(base + kABytes, &P.blk[T.j].w[g], full(s), kb * BK, T.n * op.BN);     // weights never wait
-            if (!waited) { wait_deps(d); fence_proxy_async_all(); waited = true; }
+            if (!waited) { PROF_T0(d0); wait_deps(d); fence_proxy_async_all(); waited = true; PROF_ACC(d0, p_dep); TSTAMP(t, 1); }
             tma_load_2d(base, &P.a_map[g], full(s), kb * BK, T.m * BM);
           }
         }
+        TSTAMP(t, 2);
+#ifdef CSWIN_STAGE_PROFILE
+        ++p_tiles;
+#endif
       }
+#ifdef CSWIN_STAGE_PROFILE
+      PROF_OUT(0, (unsigned long long)(clock64() - p_start)); PROF_OUT(1, p_dep); PROF_OUT(2, p_empty); PROF_OUT(3, p_tq); PROF_OUT(15, p_tiles);
+#endif
     }
   } else if (warp == 1) {
     // =============================== tcgen05.mma issuer ===============================
     if (elect_one()) {
       uint32_t rc = 0, seq = 0, att_par = 0;    // att_par: bit a = parity of p_ready / o_full of accumulator slot a
       int qi = 0; uint32_t qph = 0;
+      PROF_DECL(m_full = 0, m_acc = 0, m_p = 0, m_tq = 0);
+      PROF_T0(m_start);
       for (;;) {
+        PROF_T0(q0);
         mbar_wait(tq_full(qi), qph);
+        PROF_ACC(q0, m_tq);
         const int t = tq[qi];
         mbar_arrive(tq_empty(qi));
         if (++qi == kQ) { qi = 0; qph ^= 1; }
@@ -263,7 +304,9 @@ __global__ void __launch_bounds__(kThreads, 2) stage_tc_kernel(const __grid_cons
         const int a = seq & 1; const uint32_t aph = (seq >> 1) & 1;
         ++seq;
         const uint32_t acc = tmem_base + a * kAccCols;
+        PROF_T0(a0);
         mbar_wait(acc_empty(a), aph ^ 1);
+        PROF_ACC(a0, m_acc);
         tc_fence_after();
         if (T.op == OP_ATT) {
           const int bi = (P.nb > 1 && T.n >= P.br[0].tiles_img) ? 1 : 0;
@@ -272,7 +315,10 @@ __global__ void __launch_bounds__(kThreads, 2) stage_tc_kernel(const __grid_cons
           const int s = rc % S; const uint32_t ph = (rc / S) & 1;
           ++rc;
           const uint32_t base = smem_u32(ring + (size_t)s * P.stage_bytes);
+          PROF_T0(f0);
           mbar_wait(full(s), ph);
+          PROF_ACC(f0, m_full);
+          TSTAMP(t, 3);
           tc_fence_after();
           const uint64_t qd = make_smem_desc(base, 16, 8 * 64, kLayoutSw64);
           const uint64_t kd = make_smem_desc(base + kAttOperand, 16, 8 * 64, kLayoutSw64);
@@ -280,20 +326,26 @@ __global__ void __launch_bounds__(kThreads, 2) stage_tc_kernel(const __grid_cons
           mma_ss(acc, qd, kd, idesc, false);
           mma_ss(acc, qd + 2, kd + 2, idesc, true);
           tc_commit(acc_full(a));                                  // S ready
+          PROF_T0(p0t);
           mbar_wait(p_ready(a), (att_par >> a) & 1);                   // P (bf16) is in TMEM, padded V rows are zero
+          PROF_ACC(p0t, m_p);
           tc_fence_after();
           const uint64_t vd = make_smem_desc(base + 2 * kAttOperand, 8 * 64, 8 * 64, kLayoutSw64);
           const uint32_t idesc2 = make_idesc_bf16(128, 32, 0, 1);  // B = V is MN-major
           for (int k = 0; k < kext / 16; ++k)
             mma_ts(acc + 64, acc + 8 * k, vd + (uint64_t)k * ((16 * 64) >> 4), idesc2, k > 0);
           tc_commit(o_full(a));
+          TSTAMP(t, 4);
           att_par ^= 1u << a;
         } else {
           const GemmOp& op = P.op[gemm_index(T.op)];
           const uint32_t idesc = make_idesc_bf16(BM, op.BN, 0, 0);
           for (int kb = 0; kb < op.nkb; ++kb, ++rc) {
             const int s = rc % S; const uint32_t ph = (rc / S) & 1;
+            PROF_T0(f0);
             mbar_wait(full(s), ph);
+            PROF_ACC(f0, m_full);
+            if (kb == 0) TSTAMP(t, 3);
             tc_fence_after();
             const uint32_t base = smem_u32(ring + (size_t)s * P.stage_bytes);
             const uint64_t ad = make_smem_desc(base, 16, 1024, kLayoutSw128);
@@ -303,8 +355,12 @@ __global__ void __launch_bounds__(kThreads, 2) stage_tc_kernel(const __grid_cons
             tc_commit(empty(s));
           }
           tc_commit(acc_full(a));
+          TSTAMP(t, 4);
         }
       }
+#ifdef CSWIN_STAGE_PROFILE
+      PROF_OUT(4, (unsigned long long)(clock64() - m_start)); PROF_OUT(5, m_full); PROF_OUT(6, m_acc); PROF_OUT(7, m_p); PROF_OUT(14, m_tq);
+#endif
     }
   } else {
     // =============================== epilogue / softmax / LePE: warps 2..9 ===============================
@@ -315,8 +371,13 @@ __global__ void __launch_bounds__(kThreads, 2) stage_tc_kernel(const __grid_cons
     int qi = 0; uint32_t qph = 0;
     uint8_t* stg = Stg + (warp - 2) * 2048;
     const uint32_t stg_u32 = smem_u32(stg);
+    PROF_DECL(e_tq = 0, e_acc = 0, e_dep = 0, e_store = 0, e_rel = 0, e_att = 0, e_gemm = 0);
+    PROF_T0(e_start);
     for (;;) {
+      PROF_T0(q0);
       mbar_wait(tq_full(qi), qph);
+      PROF_ACC(q0, e_tq);
+      PROF_T0(tile0);
       const int t = tq[qi];
       __syncwarp();
       if (lane == 0) mbar_arrive(tq_empty(qi));
@@ -380,7 +441,10 @@ __global__ void __launch_bounds__(kThreads, 2) stage_tc_kernel(const __grid_cons
           Bc[sl * 32 + ch] = __bfloat162float(P.blk[T.j].cb[bi][hd * 32 + ch]);
         }
         fence_proxy_async();
+        PROF_T0(w0);
         mbar_wait(acc_full(a), aph);                                // S ready
+        PROF_ACC(w0, e_acc);
+        if (ctid == 0) TSTAMP(t, 5);
         tc_fence_after();
 
         const int hcols = slot_rows >> 1;                           // 32 (two problems) or 64 (one problem)
@@ -512,9 +576,13 @@ __global__ void __launch_bounds__(kThreads, 2) stage_tc_kernel(const __grid_cons
         if (ctid == 0) {
           mbar_arrive(empty(s));
           mbar_arrive(acc_empty(a));
-          __threadfence();
-          red_release_add(my_flag, 1);
+          TSTAMP(t, 6);
+          PROF_T0(r0);
+          red_release_add(my_flag, 1);           // release: orders the tile's global stores (all warps, via the barrier above) before the count
+          PROF_ACC(r0, e_rel);
+          TSTAMP(t, 7);
         }
+        PROF_ACC(tile0, e_att);
       } else {
         // ---------------- epilogue of one 128 x BN Linear tile (the TMA-store fast path of gemm_tc.cu) ----------------
         const int g = gemm_index(T.op);
@@ -527,7 +595,9 @@ __global__ void __launch_bounds__(kThreads, 2) stage_tc_kernel(const __grid_cons
         // my own acquire of what this tile reads with plain loads (row statistics, residual rows)
         {
           const Dep d = deps_of(P, T);
+          PROF_T0(d0);
           if (d.f != nullptr) { if (lane == 0) wait_deps(d); __syncwarp(); }
+          PROF_ACC(d0, e_dep);
         }
         bar_epi();                               // the previous tile's epilogue no longer reads sBias / sCs / sStat
         if (ctid < BN) {
@@ -550,7 +620,10 @@ __global__ void __launch_bounds__(kThreads, 2) stage_tc_kernel(const __grid_cons
         const bool has_res = res != nullptr && mrow < P.M;
         const bool stats = op.has_res != 0;      // proj and fc2 emit the row statistics of their output for the next folded Linear
         bar_epi();
+        PROF_T0(w0);
         mbar_wait(acc_full(a), aph);
+        PROF_ACC(w0, e_acc);
+        if (ctid == 0) TSTAMP(t, 5);
         tc_fence_after();
         for (int u = half; u < nunits; u += 2) {
           uint32_t v[32];
@@ -614,9 +687,11 @@ __global__ void __launch_bounds__(kThreads, 2) stage_tc_kernel(const __grid_cons
           }
         }
         tc_fence_before();
+        PROF_T0(s0);
         if (lane == 0) tma_store_wait_all();     // this warp's output boxes are written (not merely read out of shared memory)
         __syncwarp();
         bar_epi();                               // every warp: accumulator read, statistics accumulated, stores complete
+        PROF_ACC(s0, e_store);
         if (stats && ctid < BM && m0 + ctid < P.M) {
           float* dst = (g == 1 ? P.stats_x1 : P.stats_x) + ((m0 + ctid) * op.nch + T.n) * 2;
           dst[0] = sStat[ctid * 2]; dst[1] = sStat[ctid * 2 + 1];
@@ -624,12 +699,22 @@ __global__ void __launch_bounds__(kThreads, 2) stage_tc_kernel(const __grid_cons
         if (ctid == 0) mbar_arrive(acc_empty(a));
         if (stats) bar_epi();
         if (ctid == 0) {
-          fence_proxy_async_all();
-          __threadfence();
-          red_release_add(my_flag, 1);
+          TSTAMP(t, 6);
+          PROF_T0(r0);
+          red_release_add(my_flag, 1);           // the bulk stores of every warp have completed (wait_group 0 + barrier): publish
+          PROF_ACC(r0, e_rel);
+          TSTAMP(t, 7);
         }
+        PROF_ACC(tile0, e_gemm);
       }
     }
+#ifdef CSWIN_STAGE_PROFILE
+    if (ctid == 0) {
+      PROF_OUT(8, (unsigned long long)(clock64() - e_start)); PROF_OUT(9, e_tq); PROF_OUT(10, e_acc); PROF_OUT(11, e_dep); PROF_OUT(12, e_store);
+      PROF_OUT(13, e_rel | ((unsigned long long)e_att << 32));
+    }
+    (void)e_gemm;
+#endif
   }
   tc_fence_before();
   __syncthreads();
@@ -800,6 +885,8 @@ int stage_fwd_tc(const cswin_stage_args_t* a, cudaStream_t stream) {
   P.mt = pl.mt; P.U = pl.U; P.tpb = pl.tpb; P.total = pl.tpb * a->n_blocks; P.att_tiles_img = pl.att_tiles_img;
   P.S = pl.S; P.stage_bytes = pl.stage_bytes;
   for (int i = 0; i <= N_OPS; ++i) P.t0[i] = pl.t0[i];
+  P.trace = g_trace.load(std::memory_order_relaxed);
+  P.tile_trace = P.trace != nullptr && env_int("CSWIN_STAGE_TILE_TRACE", 0) ? 1 : 0;
   P.scale = a->scale; P.scale_log2e = a->scale * 1.4426950408889634f; P.invC = 1.0f / (float)C;
   if (!a->stats_in || a->stats_in_parts <= 0 || !a->stats_x || !a->stats_x1 || !a->ctrl) { set_error("stage_fwd: null statistics / ctrl pointer"); return CSWIN_ERR_INVALID; }
 
@@ -809,6 +896,7 @@ int stage_fwd_tc(const cswin_stage_args_t* a, cudaStream_t stream) {
     configured.store(1, std::memory_order_release);
   }
   int grid = env_int("CSWIN_STAGE_CTAS_PER_SM", 2) * sm_count();
+  if (env_int("CSWIN_STAGE_CTAS", 0) > 0) grid = env_int("CSWIN_STAGE_CTAS", 0);
   if (grid > P.total) grid = P.total;
   CSWIN_CUDA_OK(launch_pdl(stage_tc_kernel, dim3(grid), dim3(kThreads), pl.smem, stream, P));
   CSWIN_LAUNCH_CHECK();
