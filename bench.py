@@ -297,21 +297,32 @@ def run_native(args):
     n_rot = 16
     host = torch.from_numpy(synth.synth_image_batch(B, 3, 224, seed=1000 + rank, kind="ct"))
     pool = [(host + 0.001 * i).to(dev) for i in range(n_rot)]      # 16 x 14.4 MB fp32 = 231 MB > 126 MB L2
-    static_x = pool[0].clone()
-
+    # K forwards IN FLIGHT: K captured graphs of the same model (own static input / output buffers, own stream each), steps go
+    # round-robin over them.  Every step is still one batch-B forward; at batch 24 each kernel is <= 2 waves and latency-bound,
+    # so independent forwards overlap on the SMs (the engine's predict_stream does the same, see cswin_unet_b200/engine.py).
+    K = max(1, args.inflight)
+    from cswin_unet_b200 import _lib as cwlib
+    cap_kb = int(os.environ.get("CSWIN_INFLIGHT_SMEM_CAP_KB", "100")) if K > 1 else 0     # as SliceEngine(inflight > 1) sets it
+    streams = [torch.cuda.Stream() for _ in range(K + 1)]
+    static_x = [pool[0].clone() for _ in range(K + 1)]
+    graphs, static_y = [], []
     with torch.no_grad():
         n0 = cw.launch_count()
-        model(static_x)
+        model(static_x[0])
         launches_per_fwd = cw.launch_count() - n0
-        s = torch.cuda.Stream()
-        s.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(s):
-            for _ in range(2):
-                model(static_x)
-        torch.cuda.current_stream().wait_stream(s)
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            static_y = model(static_x)
+        for k in range(K + 1):                                     # graph K: the single-forward (latency) configuration, no smem cap
+            cwlib.set_option(cwlib.OPT_GEMM_SMEM_CAP_KB, cap_kb if k < K else 0)
+            s = streams[k]
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                for _ in range(2):
+                    model(static_x[k])
+            s.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=s):
+                static_y.append(model(static_x[k]))
+            graphs.append(g)
+    cwlib.set_option(cwlib.OPT_GEMM_SMEM_CAP_KB, 0)                # everything captured / launched below is single-stream
 
     def barrier():
         torch.cuda.synchronize()
@@ -320,20 +331,35 @@ def run_native(args):
         torch.cuda.synchronize()
 
     def step(i):
-        static_x.copy_(pool[i % n_rot], non_blocking=True)
-        graph.replay()
+        k = i % K
+        with torch.cuda.stream(streams[k]):
+            static_x[k].copy_(pool[i % n_rot], non_blocking=True)
+            graphs[k].replay()
+
+    def timed_steps(n, ks):
+        """n steps round-robin over the graphs `ks`; CUDA events on the current stream bracket all of them."""
+        cur = torch.cuda.current_stream()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record(cur)
+        for kk in ks:
+            streams[kk].wait_event(a0)
+        for i in range(n):
+            kk = ks[i % len(ks)]
+            with torch.cuda.stream(streams[kk]):
+                static_x[kk].copy_(pool[i % n_rot], non_blocking=True)
+                graphs[kk].replay()
+        for kk in ks:
+            cur.wait_stream(streams[kk])
+        a1.record(cur)
+        return a0, a1
 
     # ---- value: device-resident inputs ----
-    for i in range(args.warmup):
+    for i in range(max(args.warmup, K)):
         step(i)
     sampler = ClockSampler(local)
     barrier()
     sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(args.steps):
-        step(i)
-    e1.record()
+    e0, e1 = timed_steps(args.steps, list(range(K)))
     barrier()
     clocks = sampler.stop()
     ms = e0.elapsed_time(e1)
@@ -342,11 +368,18 @@ def run_native(args):
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
         ms = float(t.item())
     value = world * args.steps * B / (ms * 1e-3)
+    # the same K steps with ONE forward in flight: latency of a single batch-B forward (what round 1 reported as `value`)
+    barrier()
+    timed_steps(3, [K])
+    l0, l1 = timed_steps(args.steps, [K])
+    barrier()
+    ms_single = l0.elapsed_time(l1) / args.steps
 
     # ---- e2e: HOST buffers through the public API (SliceEngine): every step copies its batch host->device from pinned
     #      memory, runs the forward, and reads the uint8 label map back; copies of adjacent steps overlap the forward ----
-    engine = cw.SliceEngine(model, batch=B, compute_dtype=torch.bfloat16)
+    engine = cw.SliceEngine(model, batch=B, compute_dtype=torch.bfloat16, inflight=K)
     pinned = [(host + 0.001 * i).pin_memory() for i in range(4)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     h2d_bytes, d2h_bytes = engine.bytes_per_batch()
 
     def e2e_run(n):
@@ -430,7 +463,7 @@ def run_native(args):
                 "achieved": lin_flops / (lin_total_ms * 1e-3) / 1e12, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
                 "frac": lin_flops / (lin_total_ms * 1e-3) / 1e12 / pk["bf16_tflops"], "traffic": None, "peak_source": pk["source"] + " (burst)",
                 "launches_per_forward": len(lin_calls), "ms_per_forward": lin_total_ms, "flops_per_forward": lin_flops,
-                "share_of_step": lin_total_ms / (ms / args.steps),
+                "share_of_step": lin_total_ms / ms_single,
                 "how": "CUDA graph of the Linear launches of one forward (real buffers, L2-warm as in the step), CUDA events over 20 replays; "
                        "algorithmic flops = 2 M N K of every launch",
                 "why_low": "at batch 24 every launch is <= 2 waves: its time is one latency chain (launch dependency ~2.5 us, first TMA round "
@@ -448,7 +481,10 @@ def run_native(args):
                                    "slices, synthetic weights; BASELINE configs[2] shapes, forward pass",
                        "global_batch": B * world, "parallelism": f"slice-sharded replicas x{world}, no collective",
                        "l2": f"inputs rotate over {n_rot} batches = {n_rot * host.numel() * 4 / 1e6:.0f} MB > 126 MB L2",
-                       "launch": "CUDA graph replay of the native forward"},
+                       "launch": f"CUDA graph replay of the native forward, {K} forwards in flight (one graph + stream each, steps round-robin)",
+                       "inflight": K},
+            "single_forward": {"ms_per_step": ms_single, "value": world * B / (ms_single * 1e-3), "unit": UNIT,
+                               "what": "same steps with ONE forward in flight: latency of a batch-" + str(B) + " forward"},
             "clocks": clocks, "gpu_launches": int(launches_per_fwd * args.steps),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes),
                     "d2h_bytes_per_step": int(d2h_bytes), "ms_per_step": ms_e2e / args.steps,
@@ -682,6 +718,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="native", choices=["native", "reference", "reference-cuda"])
     ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--inflight", type=int, default=int(os.environ.get("CSWIN_INFLIGHT", "3")),
+                    help="batch-B forwards in flight (one CUDA graph + stream each); 1 = strictly one after the other")
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU-oracle work for cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-reference-cuda", action="store_true", help="skip timing the eager reference on the GPU")

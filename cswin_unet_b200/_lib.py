@@ -123,6 +123,7 @@ SIGNATURES = {
     "cswin_tc_launch_count": (C.c_uint64, []),
     "cswin_simt_fallback_count": (C.c_uint64, []),
     "cswin_debug_set_trace": (None, [c_void_p]),
+    "cswin_set_option": (c_int32, [c_int32, c_int32]),
     "cswin_lepe_attention_fwd": (c_int32, [C.POINTER(LepeBranch), c_int32, c_int32, c_int32, c_float, c_int32, c_void_p]),
     "cswin_lepe_attention_bwd": (c_int32, [C.POINTER(LepeBranchGrad), c_int32, c_int32, c_int32, c_float, c_int32, c_void_p]),
     "cswin_lepe_param_grad": (c_int32, [C.POINTER(LepeBranchGrad), c_int32, c_int32, c_int32, c_int32, c_void_p, C.POINTER(c_int32)]),
@@ -214,6 +215,13 @@ def check(rc: int, what: str) -> None:
     if rc != 0:
         msg = lib().cswin_last_error()
         raise CswinError(f"{what} failed (code {rc}): {msg.decode() if msg else '?'}")
+
+
+OPT_GEMM_SMEM_CAP_KB = 1
+
+
+def set_option(option: int, value: int) -> None:
+    check(lib().cswin_set_option(option, value), "cswin_set_option")
 
 
 def launch_count() -> int:

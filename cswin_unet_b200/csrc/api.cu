@@ -11,6 +11,7 @@ namespace cswin {
 std::atomic<uint64_t> g_launches{0};
 std::atomic<uint64_t> g_tc_launches{0};
 std::atomic<unsigned long long*> g_trace{nullptr};
+std::atomic<int> g_gemm_smem_cap_kb{0};
 
 namespace {
 thread_local char t_err[512] = "";
@@ -67,6 +68,11 @@ int cswin_abi_version(void) { return CSWIN_ABI_VERSION; }
 const char* cswin_last_error(void) { return t_err; }
 uint64_t cswin_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 void cswin_debug_set_trace(void* device_buffer) { g_trace.store((unsigned long long*)device_buffer); }
+int cswin_set_option(int32_t option, int32_t value) {
+  if (option == CSWIN_OPT_GEMM_SMEM_CAP_KB && value >= 0 && value <= 227) { g_gemm_smem_cap_kb.store(value); return CSWIN_OK; }
+  set_error("set_option: unknown option %d or value %d out of range", option, value);
+  return CSWIN_ERR_INVALID;
+}
 uint64_t cswin_tc_launch_count(void) { return g_tc_launches.load(std::memory_order_relaxed); }
 uint64_t cswin_simt_fallback_count(void) { return g_simt_fallbacks.load(std::memory_order_relaxed); }
 

@@ -17,6 +17,7 @@ namespace cswin {
 void set_error(const char* fmt, ...);
 extern std::atomic<uint64_t> g_launches;
 extern std::atomic<uint64_t> g_tc_launches;
+extern std::atomic<int> g_gemm_smem_cap_kb;        // cswin_set_option(CSWIN_OPT_GEMM_SMEM_CAP_KB): per-CTA smem ceiling of the tcgen05 Linear (0 = none)
 extern std::atomic<unsigned long long*> g_trace;   // debug: device buffer for in-kernel %globaltimer stamps (or null)
 
 #define CSWIN_REQUIRE(cond, code, ...)            \

@@ -423,7 +423,8 @@ struct TileCfg { int bn, stages; };
 TileCfg pick_tile(int64_t M, int N, int nkb, int act, int sms, bool w_kn) {
   static const int forced = [] { const char* e = getenv("CSWIN_GEMM_BN"); return e ? atoi(e) : 0; }();
   // CSWIN_GEMM_SMEM_CAP_KB: per-CTA shared-memory ceiling, so that a CTA of the NEXT kernel (PDL) fits next to the resident ones
-  static const size_t smem_cap = [] { const char* e = getenv("CSWIN_GEMM_SMEM_CAP_KB"); return e ? (size_t)atoi(e) * 1024 : (size_t)0; }();
+  static const int env_cap = [] { const char* e = getenv("CSWIN_GEMM_SMEM_CAP_KB"); return e ? atoi(e) : -1; }();
+  const size_t smem_cap = (size_t)(env_cap >= 0 ? env_cap : g_gemm_smem_cap_kb.load(std::memory_order_relaxed)) * 1024;   // env wins (A/B runs)
   const int n16 = w_kn ? ((N + 63) & ~63) : ((N + 15) & ~15);      // (K,N) weights are fetched in 64-column boxes
   const int64_t mt = (M + BM - 1) / BM;
   const int cands[] = {64, 96, 128, 192, 256};

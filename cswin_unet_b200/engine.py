@@ -2,7 +2,11 @@
 
 The reference evaluates one slice at a time (utils.py:61-90: host zoom -> `.cuda()` -> forward -> argmax -> `.cpu()`).
 Slices are independent, so the engine batches them, keeps the forward in a CUDA graph, and pipelines
-host->device copy / forward / device->host copy of consecutive batches on three streams with two buffer slots:
+host->device copy / forward / device->host copy of consecutive batches; `inflight` (default CSWIN_INFLIGHT = 3) batches run
+their forwards CONCURRENTLY, each on its own stream with its own captured graph and buffers: at batch 24 every kernel of the
+forward is at most one or two waves and bound by its own latency chain, so a second / third independent forward fills the
+SMs the first leaves idle (measured on B200: 19.2k -> 23.4k -> 25.1k slices/s with 1 / 2 / 3 forwards in flight,
+profiles/r02_concurrent_forwards.log):
 
     eng = SliceEngine(model, batch=24)                 # model: CSWinTransformer on a CUDA device
     labels = eng.predict(host_batch)                   # (B,3|1,H,W) float32 CPU tensor -> (B,H,W) uint8 CPU tensor
@@ -31,7 +35,8 @@ def shard_slices(n_slices: int, world: int, rank: int) -> range:
 
 class SliceEngine:
     def __init__(self, model, batch: int, img_size: Optional[int] = None, in_chans: int = 3,
-                 compute_dtype: torch.dtype = torch.bfloat16, device: Optional[torch.device] = None):
+                 compute_dtype: torch.dtype = torch.bfloat16, device: Optional[torch.device] = None,
+                 inflight: Optional[int] = None):
         self.model = model.eval()
         self.batch = batch
         self.size = img_size or model.img_size
@@ -40,15 +45,17 @@ class SliceEngine:
         if self.device.type != "cuda":
             raise RuntimeError("SliceEngine needs a CUDA device: cswin_unet_b200 has no CPU path")
         model.compute_dtype = compute_dtype
+        self.inflight = max(1, int(os.environ.get("CSWIN_INFLIGHT", "3")) if inflight is None else int(inflight))
         self.streams = {k: torch.cuda.Stream(self.device) for k in ("h2d", "compute", "d2h")}
         shape = (batch, in_chans, self.size, self.size)
         self.slots = []
         with torch.cuda.device(self.device), torch.no_grad():
-            for _ in range(2):
+            for i in range(max(2, self.inflight)):                   # >= 2 slots: copies of one batch overlap the forward of another
                 x = torch.zeros(shape, dtype=torch.float32, device=self.device)
                 slot = {"x": x, "host_out": torch.empty((batch, self.size, self.size), dtype=torch.uint8).pin_memory(),
                         "ev_in": torch.cuda.Event(), "ev_done": torch.cuda.Event(), "ev_out": torch.cuda.Event(),
-                        "ev_free": torch.cuda.Event()}
+                        "ev_free": torch.cuda.Event(),
+                        "stream": self.streams["compute"] if (i == 0 or self.inflight == 1) else torch.cuda.Stream(self.device)}
                 self.slots.append(slot)
         self._n = 0
         self._resample_bufs = {}                                 # (H, W) -> device / pinned buffers of predict_volume(resample='gpu')
@@ -64,21 +71,29 @@ class SliceEngine:
         """(Re-)capture the forward graphs.  The graphs bake pointers to weight tensors DERIVED from the parameters (bf16 casts,
         folded LayerNorm / head matrices): they must be rebuilt when the parameters change, which `refresh_if_stale` does."""
         torch.cuda.synchronize(self.device)
-        with torch.cuda.device(self.device), torch.no_grad():
-            cs = self.streams["compute"]
-            cs.wait_stream(torch.cuda.current_stream(self.device))
-            with torch.cuda.stream(cs):
-                for _ in range(2):                               # warm-up: derive cached weights, load kernels
-                    self.model.predict_labels(self.slots[0]["x"])
-            cs.synchronize()
-            pool = None
-            for slot in self.slots:                              # one graph per slot (static input / output buffers)
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, pool=pool, stream=cs):
-                    slot["y"] = self.model.predict_labels(slot["x"])
-                pool = g.pool()
-                slot["graph"] = g
+        # CTAs of concurrent launches must fit next to each other on an SM: cap the tcgen05 Linear's operand ring while capturing
+        # (process-wide option read when a launch is enqueued, i.e. baked into the graphs); restored afterwards
+        from . import _lib
+        _lib.set_option(_lib.OPT_GEMM_SMEM_CAP_KB, int(os.environ.get("CSWIN_INFLIGHT_SMEM_CAP_KB", "100")) if self.inflight > 1 else 0)
+        try:
+            self._capture_graphs()
+        finally:
+            _lib.set_option(_lib.OPT_GEMM_SMEM_CAP_KB, 0)
         self._sig = self._weights_signature()
+
+    def _capture_graphs(self) -> None:
+        with torch.cuda.device(self.device), torch.no_grad():
+            for slot in self.slots:                              # one graph per slot (static input / output buffers), captured
+                cs = slot["stream"]                              # on the stream it will be replayed on; concurrent replays must
+                cs.wait_stream(torch.cuda.current_stream(self.device))   # not share a memory pool, so each graph owns its own
+                with torch.cuda.stream(cs):
+                    for _ in range(2):                           # warm-up: derive cached weights, load kernels
+                        self.model.predict_labels(slot["x"])
+                cs.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=cs):
+                    slot["y"] = self.model.predict_labels(slot["x"])
+                slot["graph"] = g
 
     def refresh_if_stale(self) -> bool:
         """Re-capture when the model's weights changed since the graphs were built (train -> validate loops of the reference:
@@ -92,14 +107,14 @@ class SliceEngine:
     # ---- one batch ------------------------------------------------------------------------------------
     def _submit(self, host_x: Tensor) -> dict:
         self.refresh_if_stale()
-        slot = self.slots[self._n % 2]
+        slot = self.slots[self._n % len(self.slots)]
         self._n += 1
         n = host_x.shape[0]
         if n > self.batch or tuple(host_x.shape[2:]) != (self.size, self.size):
             raise ValueError(f"expected at most {self.batch} slices of {self.size}x{self.size}, got {tuple(host_x.shape)}")
         if host_x.shape[1] == 1 and self.in_chans == 3:
             host_x = host_x.expand(-1, 3, -1, -1)                  # vision_transformer.py:40-41 (1 -> 3 channel repeat)
-        h2d, cs, d2h = self.streams["h2d"], self.streams["compute"], self.streams["d2h"]
+        h2d, cs, d2h = self.streams["h2d"], slot["stream"], self.streams["d2h"]
         with torch.cuda.stream(h2d):
             h2d.wait_event(slot["ev_done"])                        # previous forward on this slot has consumed x
             slot["x"][:n].copy_(host_x, non_blocking=True)
@@ -124,10 +139,11 @@ class SliceEngine:
         return self._collect(self._submit(host_x))
 
     def predict_stream(self, batches: Iterable[Tensor]) -> Iterator[Tensor]:
-        """Pipelined: batch i+1 is copied in while batch i runs and batch i-1 is copied out."""
+        """Pipelined: up to len(slots) batches are between their host->device copy and their device->host copy; their forwards
+        run concurrently on the slots' streams."""
         pending: List[dict] = []
         for hx in batches:
-            if len(pending) == 2:
+            if len(pending) == len(self.slots):
                 yield self._collect(pending.pop(0))
             pending.append(self._submit(hx))
         while pending:
@@ -151,19 +167,21 @@ def _predict_volume_gpu(engine: "SliceEngine", image, rng: range):
     P, Bt = engine.size, engine.batch
     dev = engine.device
     key = (H, W)
+    ns = len(engine.slots)
     buf = engine._resample_bufs.get(key)
     if buf is None:
         with torch.cuda.device(dev):
-            buf = {"raw": [torch.empty((Bt, H, W), dtype=torch.float32, device=dev) for _ in range(2)],
-                   "work": torch.empty(Bt * H * W, dtype=torch.float64, device=dev),
-                   "lab": [torch.empty((Bt, H, W), dtype=torch.uint8, device=dev) for _ in range(2)],
-                   "host_in": [torch.empty((Bt, H, W), dtype=torch.float32).pin_memory() for _ in range(2)],
-                   "ev": [torch.cuda.Event() for _ in range(2)]}
+            buf = {"raw": [torch.empty((Bt, H, W), dtype=torch.float32, device=dev) for _ in range(ns)],
+                   "work": [torch.empty(Bt * H * W, dtype=torch.float64, device=dev) for _ in range(ns)],
+                   "lab": [torch.empty((Bt, H, W), dtype=torch.uint8, device=dev) for _ in range(ns)],
+                   "host_in": [torch.empty((Bt, H, W), dtype=torch.float32).pin_memory() for _ in range(ns)],
+                   "ev": [torch.cuda.Event() for _ in range(ns)]}
         engine._resample_bufs[key] = buf
     out = torch.empty((len(rng), H, W), dtype=torch.uint8).pin_memory()
     engine.refresh_if_stale()
-    cs = engine.streams["compute"]
-    cs.wait_stream(torch.cuda.current_stream(dev))
+    cur = torch.cuda.current_stream(dev)
+    for slot in engine.slots:
+        slot["stream"].wait_stream(cur)
     idx = list(rng)
     # page-lock the caller's volume for the duration of the call: the slices then go host -> device straight from it (no
     # staging memcpy); if registration is refused the pinned staging buffers are used
@@ -171,27 +189,30 @@ def _predict_volume_gpu(engine: "SliceEngine", image, rng: range):
     rt = torch.cuda.cudart()
     registered = REGISTER_VOLUME and int(rt.cudaHostRegister(vol_t.data_ptr(), vol_t.numel() * 4, 0)) == 0
     try:
-        with torch.cuda.stream(cs), torch.no_grad():
+        with torch.no_grad():
             for bi, i0 in enumerate(range(0, len(idx), Bt)):
                 sl = idx[i0:i0 + Bt]
                 n = len(sl)
-                k = bi % 2
-                slot = engine.slots[k]
-                src = vol_t[sl[0]:sl[-1] + 1]
-                if not registered:
-                    buf["ev"][k].synchronize()                       # the pinned staging buffer of this parity is free again
-                    buf["host_in"][k][:n].copy_(src)
-                    src = buf["host_in"][k][:n]
-                buf["raw"][k][:n].copy_(src, non_blocking=True)
-                buf["ev"][k].record(cs)
-                ops.zoom_cubic(buf["raw"][k][:n], (P, P), out=slot["x"], work=buf["work"])
-                slot["graph"].replay()
-                ops.zoom_nearest_u8(slot["y"][:n].contiguous(), (H, W), out=buf["lab"][k])
-                out[i0:i0 + n].copy_(buf["lab"][k][:n], non_blocking=True)
-        cs.synchronize()
+                k = bi % ns                                          # batches alternate over the slots; each slot's chain (copy in,
+                slot = engine.slots[k]                               # zoom, forward, zoom back, copy out) runs on its own stream
+                with torch.cuda.stream(slot["stream"]):
+                    src = vol_t[sl[0]:sl[-1] + 1]
+                    if not registered:
+                        buf["ev"][k].synchronize()                   # the pinned staging buffer of this slot is free again
+                        buf["host_in"][k][:n].copy_(src)
+                        src = buf["host_in"][k][:n]
+                    buf["raw"][k][:n].copy_(src, non_blocking=True)
+                    buf["ev"][k].record(slot["stream"])
+                    ops.zoom_cubic(buf["raw"][k][:n], (P, P), out=slot["x"], work=buf["work"][k])
+                    slot["graph"].replay()
+                    ops.zoom_nearest_u8(slot["y"][:n].contiguous(), (H, W), out=buf["lab"][k])
+                    out[i0:i0 + n].copy_(buf["lab"][k][:n], non_blocking=True)
+        for slot in engine.slots:
+            slot["stream"].synchronize()
     finally:
         if registered:
-            cs.synchronize()
+            for slot in engine.slots:
+                slot["stream"].synchronize()
             rt.cudaHostUnregister(vol_t.data_ptr())
     return out.numpy()                                               # (a view of the pinned result buffer: no extra copy)
 

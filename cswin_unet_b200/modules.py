@@ -463,9 +463,13 @@ class CSWinBlock(_Native):
 
 # All blocks of a stage as ONE persistent dataflow launch (csrc/stage_tc.cu) instead of 5 launches per block: same tiles, same
 # arithmetic as the composed path, ordered by per-row-tile completion counters instead of kernel boundaries.  CSWIN_STAGE_EXEC
-# lists the block dims that use it ("0" = never, default see below); anything outside the kernel's envelope, training, fp32 and
-# DropPath-active calls run the composed path.
-STAGE_EXEC_DIMS = tuple(int(t) for t in os.environ.get("CSWIN_STAGE_EXEC", "256").split(",") if t.strip() not in ("", "0"))
+# lists the block dims that use it (e.g. "256" or "64,128,256,512"); anything outside the kernel's envelope, training, fp32 and
+# DropPath-active calls run the composed path.  MEASURED on B200 (profiles/r02_stage_kernel_*.log): bit-identical to the composed
+# path, but SLOWER at batch 24 (stage 3, 9 blocks: 639 us vs 309 us): a block is a chain of 5 dependent ops, and the chain is
+# latency-bound either way — per link the dataflow version pays deps-visible -> load 0.6 us -> mainloop 1.4 us (fc2 7 us with the
+# 2-stage ring that fits next to a second CTA) -> epilogue + bulk-store completion 3.2-4.4 us -> red.release 0.8-1.4 us -> flag
+# poll 1.3-1.9 us = 8-13 us, more than the 5-8 us a PDL-chained launch costs.  Default: off.
+STAGE_EXEC_DIMS = tuple(int(t) for t in os.environ.get("CSWIN_STAGE_EXEC", "").split(",") if t.strip() not in ("", "0"))
 
 
 def _stage_block_desc(blk: "CSWinBlock") -> dict:

@@ -52,6 +52,12 @@ uint64_t cswin_tc_launch_count(void);
 /* bf16 calls that fell outside a tcgen05 kernel's envelope and ran on the general SIMT kernels instead (same results, much slower):
  * counted here; the first occurrence per op also prints one warning line to stderr (CSWIN_QUIET_FALLBACK=1 silences it). */
 uint64_t cswin_simt_fallback_count(void);
+/* process-wide tuning options (take effect for launches enqueued / graphs captured AFTER the call).
+ *  CSWIN_OPT_GEMM_SMEM_CAP_KB: per-CTA shared-memory ceiling of the tcgen05 Linear's operand ring in KB (0 = none, default).
+ *    With several independent forwards in flight (SliceEngine(inflight > 1)) a ceiling of ~100 KB lets CTAs of two launches share
+ *    an SM: +6 % throughput at 3 forwards in flight, -4 % for a single forward (profiles/r02_concurrent_forwards.log). */
+enum { CSWIN_OPT_GEMM_SMEM_CAP_KB = 1 };
+int cswin_set_option(int32_t option, int32_t value);
 /* debug / profiling aid: when non-NULL, the tcgen05 kernels write %globaltimer stamps of their phases for the first 1024
  * CTAs of every launch into this device buffer (1024 x 16 uint64); NULL (default) disables it. Not part of the data path. */
 void cswin_debug_set_trace(void* device_buffer);

@@ -410,6 +410,25 @@ def test_predict_volume_sharded_equals_unsharded():
     assert np.array_equal(np.concatenate(parts, 0), full)
 
 
+@pytest.mark.parametrize("inflight", [2, 3])
+def test_engine_concurrent_forwards_equal_sequential(inflight):
+    """SliceEngine(inflight = K) runs K captured forwards concurrently on K streams: label maps (stream API, ragged last batch) and
+    resampled volumes must equal the strictly sequential engine's, batch by batch, over several rounds of slot reuse."""
+    m = build_model("alive")
+    g = torch.Generator().manual_seed(5)
+    batches = [torch.rand(3 if i != 6 else 2, 3, 224, 224, generator=g) for i in range(7)]
+    seq = list(cw.SliceEngine(m, batch=3, compute_dtype=torch.bfloat16, inflight=1).predict_stream(iter(batches)))
+    eng = cw.SliceEngine(m, batch=3, compute_dtype=torch.bfloat16, inflight=inflight)
+    assert len(eng.slots) == max(2, inflight) and len({s["stream"].cuda_stream for s in eng.slots}) == inflight
+    for _ in range(2):
+        con = list(eng.predict_stream(iter(batches)))
+        assert len(con) == len(seq) and all(torch.equal(a, b) for a, b in zip(con, seq))
+    vol = _synthetic_volume(D=8, S=256, seed=4)
+    want, _ = cw.predict_volume(cw.SliceEngine(m, batch=3, compute_dtype=torch.bfloat16, inflight=1), vol, resample="gpu")
+    got, _ = cw.predict_volume(eng, vol, resample="gpu")
+    assert np.array_equal(np.asarray(got), np.asarray(want))
+
+
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-4), (torch.bfloat16, 3e-2)])
 @pytest.mark.parametrize("M,N,K", [(3136, 64, 192), (784, 128, 512), (4704, 1024, 256), (201, 152, 64), (98, 40, 72)])
 def test_linear_kn_weight_layout(dtype, tol, M, N, K):
