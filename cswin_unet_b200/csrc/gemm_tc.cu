@@ -204,6 +204,7 @@ __global__ void __launch_bounds__(kThreads, CSWIN_GEMM_MINB) linear_tc_kernel(co
       //      store per 32 x 32 unit.  No shared-memory read-back, no per-thread global stores, ragged edges clipped by TMA.
       for (int u = ch; u < nunits; u += 2) {
         uint32_t v[32];
+        PSTAMP(8);
         tmem_ld32(trow + u * 32, v);
         uint4 rv[4];
         const int ncol = n0 + u * 32;
@@ -215,12 +216,14 @@ __global__ void __launch_bounds__(kThreads, CSWIN_GEMM_MINB) linear_tc_kernel(co
             rv[c] = (ncol + c * 8 < P.N) ? *reinterpret_cast<const uint4*>(P.res + mrow * P.ldr + ncol + c * 8) : make_uint4(0, 0, 0, 0);
         }
         tmem_wait_ld();
+        PSTAMP(9);
         const float4* b4 = reinterpret_cast<const float4*>(sBias + u * 32);
         const float4* c4 = reinterpret_cast<const float4*>(sCs + u * 32);
         if (u != ch) {                                    // the previous unit's TMA store must have finished reading the staging box
           if (lane == 0) tma_store_wait_read();
           __syncwarp();
         }
+        PSTAMP(10);
         float st1 = 0.f, st2 = 0.f;
         const float2 nmean2 = make_float2(-ln_mean, -ln_mean), rstd2 = make_float2(ln_rstd, ln_rstd), sc2 = make_float2(sc, sc);
 #pragma unroll
@@ -272,13 +275,16 @@ __global__ void __launch_bounds__(kThreads, CSWIN_GEMM_MINB) linear_tc_kernel(co
           asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(x.x), "r"(x.y), "r"(x.z), "r"(x.w) : "memory");
         }
         if (kStats) { atomicAdd(&sStat[(q * 32 + lane) * 2], st1); atomicAdd(&sStat[(q * 32 + lane) * 2 + 1], st2); }
+        PSTAMP(11);
         fence_proxy_async();
         __syncwarp();
+        PSTAMP(12);
         if (lane == 0) {
           tma_store_2d(&P.map_out, stg_u32, ncol, (int)(m0 + q * 32));
           if (kTrain && P.aux) tma_store_2d(&P.map_aux, stg_u32 + (uint32_t)P.aux_off, ncol, (int)(m0 + q * 32));
           tma_store_commit();
         }
+        PSTAMP(13);
       }
       if (lane == 0) tma_store_wait_read();               // shared memory may be released / re-used after this
       __syncwarp();

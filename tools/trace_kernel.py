@@ -78,6 +78,8 @@ for i, n in enumerate(names):
 if os.environ.get("GEMM_PROFILE"):
     tt = buf.cpu().numpy().reshape(1024, 16)[live].astype(np.float64)
     lab = ["tmem_ld issue", "tmem_ld done", "math+st.shared+syncwarp", "lds+residual issued", "residual arrived", "stores done"]
+    if os.environ.get("GEMM_PROFILE") == "tma":          # TMA-store fast path stamps
+        lab = ["unit start", "tmem_ld + residual loads done", "staging box free (wait_read)", "math + st.shared", "fence.proxy.async + syncwarp", "TMA store issued"]
     for i in range(9, 14):
         print(f"  cyc {lab[i-8]:28s} +{np.median(tt[:, i] - tt[:, i-1]):7.0f}")
 print(f"per-CTA lifetime median {np.median(t[:,7]-t[:,0])/1e3:.2f} us, max {np.max(t[:,7]-t[:,0])/1e3:.2f}; entry spread {np.ptp(t[:,0])/1e3:.2f} us")
