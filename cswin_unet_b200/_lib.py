@@ -13,7 +13,7 @@ import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC_DIR = os.path.join(_HERE, "csrc")
-LIB_PATH = os.path.join(_HERE, "libcswin_b200.so")
+LIB_PATH = os.environ.get("CSWIN_LIB_PATH") or os.path.join(_HERE, "libcswin_b200.so")   # override: A/B builds of the same ABI
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "cswin_b200.h")
 
 F32, BF16 = 0, 1

@@ -7,8 +7,8 @@
 //   512 -> 224 the last one is 511.00000000000006) gives cval = 0: scipy's last row / column are zero and so are ours;
 //   order 3: recursive prefilter (pole sqrt(3) - 2, gain 6, mirror initialisation) along H, then along W, 4 x 4 taps with
 //   mirrored edge indices; order 0: index floor(cc + 0.5).
-// Both are bandwidth kernels: the prefilter is one thread per line (the recursion is sequential), the interpolation one thread
-// per output pixel.  On the CPU the two calls cost ~15 ms per 512^2 slice, i.e. 300 x the network's share of a slice.
+// Both are bandwidth kernels: the prefilter is one thread per line (the recursion is sequential; loads are batched / staged through
+// shared memory so that they stay off the dependent chain), the interpolation one thread per output pixel.  On the CPU the two calls cost ~15 ms per 512^2 slice, i.e. 300 x the network's share of a slice.
 #include <algorithm>
 
 #include "common.cuh"
@@ -16,42 +16,157 @@
 namespace cswin {
 namespace {
 
-// One thread per line: c = prefilter(src line) in float64.  src may be the float32 image (first axis) or the float64 work
-// buffer itself (second axis, in place).  Element i of line l lives at base(l) + i * estride.
+// c = prefilter(src line) in float64, one thread per line; the recursion along a line is sequential and its operation order is
+// scipy's (bit-compatible results), so the parallelism is across lines and the job of the kernels is to keep the loads off the
+// dependent chain: the first version issued one (uncoalesced, for rows) load per recursion step and was latency-bound at ~0.6 us
+// per step (322 + 259 us for 8 slices of 512^2, profiles/r02_ncu_rest_kernels_summary.txt).
+constexpr int kPfChunk = 8;
+
+struct PfConst { double z, gain, z_n_1, anti; };
+__device__ __forceinline__ PfConst pf_const(int n) {
+  PfConst k;
+  k.z = sqrt(3.0) - 2.0;                                   // the cubic B-spline pole, formed as scipy forms it
+  k.gain = __dmul_rn(1.0 - k.z, 1.0 - 1.0 / k.z);          // (1 - z)(1 - 1/z) = 6 up to rounding, as scipy forms it
+  k.z_n_1 = pow(k.z, (double)(n - 1));
+  k.anti = __ddiv_rn(k.z, __dsub_rn(__dmul_rn(k.z, k.z), 1.0));
+  return k;
+}
+
+// Lines whose neighbours are adjacent in memory (lane l <-> line l, element i at base + i * estride): along H of a slice.  Every
+// access of a warp is one contiguous segment; elements are fetched kPfChunk at a time before the dependent steps that use them.
 template <typename TIn>
-__global__ void __launch_bounds__(128) spline_prefilter_kernel(const TIn* src, double* dst, int64_t n_lines,   // (src may alias dst)
-                                                               int lines_per_img, int64_t img_stride, int64_t lstride, int64_t estride,
-                                                               int n) {
+__global__ void __launch_bounds__(32) spline_prefilter_cols_kernel(const TIn* src, double* dst, int64_t n_lines, int lines_per_img,
+                                                                   int64_t img_stride, int64_t estride, int n) {
   const int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (l >= n_lines) return;
-  const int64_t base = (l / lines_per_img) * img_stride + (l % lines_per_img) * lstride;
+  const int64_t base = (l / lines_per_img) * img_stride + (l % lines_per_img);
   const TIn* s = src + base;
   double* c = dst + base;
   if (n < 2) { if (n == 1) c[0] = (double)s[0]; return; }
-  const double z = sqrt(3.0) - 2.0;                       // the cubic B-spline pole, formed as scipy forms it
-  const double gain = __dmul_rn(1.0 - z, 1.0 - 1.0 / z);  // (1 - z)(1 - 1/z) = 6 up to rounding, as scipy forms it
-  const double z_n_1 = pow(z, (double)(n - 1));
+  const PfConst k = pf_const(n);
   // causal initialisation with mirror boundaries (scipy _init_causal_mirror)
-  double c0 = __dadd_rn(__dmul_rn((double)s[0], gain), __dmul_rn(z_n_1, __dmul_rn((double)s[(int64_t)(n - 1) * estride], gain)));
-  double z_i = z;
-  for (int i = 1; i < n - 1; ++i) {
-    const double a = __dmul_rn((double)s[(int64_t)i * estride], gain), b = __dmul_rn((double)s[(int64_t)(n - 1 - i) * estride], gain);
-    c0 = __dadd_rn(c0, __dmul_rn(z_i, __dadd_rn(a, __dmul_rn(z_n_1, b))));
-    z_i = __dmul_rn(z_i, z);
+  double c0 = __dadd_rn(__dmul_rn((double)s[0], k.gain), __dmul_rn(k.z_n_1, __dmul_rn((double)s[(int64_t)(n - 1) * estride], k.gain)));
+  double z_i = k.z;
+  for (int i0 = 1; i0 < n - 1; i0 += kPfChunk) {
+    double a[kPfChunk], b[kPfChunk];
+#pragma unroll
+    for (int j = 0; j < kPfChunk; ++j) {
+      const int i = i0 + j;
+      a[j] = i < n - 1 ? (double)s[(int64_t)i * estride] : 0.0;
+      b[j] = i < n - 1 ? (double)s[(int64_t)(n - 1 - i) * estride] : 0.0;
+    }
+#pragma unroll
+    for (int j = 0; j < kPfChunk; ++j) {
+      if (i0 + j < n - 1) {
+        c0 = __dadd_rn(c0, __dmul_rn(z_i, __dadd_rn(__dmul_rn(a[j], k.gain), __dmul_rn(k.z_n_1, __dmul_rn(b[j], k.gain)))));
+        z_i = __dmul_rn(z_i, k.z);
+      }
+    }
   }
-  double prev = __ddiv_rn(c0, __dsub_rn(1.0, __dmul_rn(z_n_1, z_n_1)));
+  double prev = __ddiv_rn(c0, __dsub_rn(1.0, __dmul_rn(k.z_n_1, k.z_n_1)));
   c[0] = prev;
-  for (int i = 1; i < n; ++i) {                           // causal pass
-    prev = __dadd_rn(__dmul_rn((double)s[(int64_t)i * estride], gain), __dmul_rn(z, prev));
-    c[(int64_t)i * estride] = prev;
+  for (int i0 = 1; i0 < n; i0 += kPfChunk) {              // causal pass
+    double a[kPfChunk];
+#pragma unroll
+    for (int j = 0; j < kPfChunk; ++j) a[j] = i0 + j < n ? (double)s[(int64_t)(i0 + j) * estride] : 0.0;
+#pragma unroll
+    for (int j = 0; j < kPfChunk; ++j) {
+      if (i0 + j < n) {
+        prev = __dadd_rn(__dmul_rn(a[j], k.gain), __dmul_rn(k.z, prev));
+        c[(int64_t)(i0 + j) * estride] = prev;
+      }
+    }
   }
-  // anticausal initialisation (scipy _init_anticausal_mirror) and pass
-  double nxt = __dmul_rn(__dadd_rn(__dmul_rn(z, c[(int64_t)(n - 2) * estride]), c[(int64_t)(n - 1) * estride]),
-                         __ddiv_rn(z, __dsub_rn(__dmul_rn(z, z), 1.0)));
+  // anticausal initialisation (scipy _init_anticausal_mirror) and pass; c[n-1] == prev
+  double nxt = __dmul_rn(__dadd_rn(__dmul_rn(k.z, c[(int64_t)(n - 2) * estride]), prev), k.anti);
   c[(int64_t)(n - 1) * estride] = nxt;
-  for (int i = n - 2; i >= 0; --i) {
-    nxt = __dmul_rn(z, __dsub_rn(nxt, c[(int64_t)i * estride]));
-    c[(int64_t)i * estride] = nxt;
+  for (int i0 = n - 2; i0 >= 0; i0 -= kPfChunk) {
+    double a[kPfChunk];
+#pragma unroll
+    for (int j = 0; j < kPfChunk; ++j) a[j] = i0 - j >= 0 ? c[(int64_t)(i0 - j) * estride] : 0.0;
+#pragma unroll
+    for (int j = 0; j < kPfChunk; ++j) {
+      if (i0 - j >= 0) {
+        nxt = __dmul_rn(k.z, __dsub_rn(nxt, a[j]));
+        c[(int64_t)(i0 - j) * estride] = nxt;
+      }
+    }
+  }
+}
+
+// Lines that are contiguous in memory (a row of a slice), in place on the float64 coefficients: one warp owns 32 consecutive rows and
+// moves them through shared memory in 32-column tiles (coalesced 256-byte row segments in, the same out), lane l runs the recursion
+// of row l on its tile row.  Tile rows are padded to 33 doubles: the 16 lanes of a half-warp hit 16 different bank pairs.
+constexpr int kPfT = 32;
+__global__ void __launch_bounds__(32) spline_prefilter_rows_kernel(double* c, int64_t n_lines, int64_t lstride, int n) {
+  __shared__ double ta[kPfT][kPfT + 1], tb[kPfT][kPfT + 1];
+  const int lane = threadIdx.x;
+  const int64_t l0 = (int64_t)blockIdx.x * kPfT;           // first line of this warp (lines of consecutive slices are contiguous)
+  const int rows = (int)min((int64_t)kPfT, n_lines - l0);
+  double* base = c + l0 * lstride;
+  if (n < 2) return;                                        // (a single element is its own coefficient: nothing to do in place)
+  const PfConst k = pf_const(n);
+  const bool live = lane < rows;
+  auto load_tile = [&](double (*t)[kPfT + 1], int col0) {   // tile[r][j] = line r, element col0 + j
+    for (int r = 0; r < rows; ++r) { const int col = col0 + lane; t[r][lane] = col < n && col >= 0 ? base[(int64_t)r * lstride + col] : 0.0; }
+    __syncwarp();
+  };
+  auto store_tile = [&](double (*t)[kPfT + 1], int col0) {
+    __syncwarp();
+    for (int r = 0; r < rows; ++r) { const int col = col0 + lane; if (col < n && col >= 0) base[(int64_t)r * lstride + col] = t[r][lane]; }
+    __syncwarp();
+  };
+  // ---- causal initialisation: c0 = s[0] g + z^(n-1) s[n-1] g + sum_{i=1}^{n-2} z^i (s[i] g + z^(n-1) s[n-1-i] g), i ascending ----
+  double c0 = 0.0, z_i = k.z;
+  for (int col0 = 0; col0 < n; col0 += kPfT) {
+    // element i = col0 + j pairs with element n-1-i = (n-1-col0) - j: the mirror tile starts at n-1-col0-(kPfT-1) and is read backwards
+    load_tile(ta, col0);
+    load_tile(tb, n - 1 - col0 - (kPfT - 1));
+    if (live) {
+      for (int j = 0; j < kPfT; ++j) {
+        const int i = col0 + j;
+        if (i >= n - 1) break;
+        const double a = ta[lane][j], b = tb[lane][kPfT - 1 - j];
+        if (i == 0) c0 = __dadd_rn(__dmul_rn(a, k.gain), __dmul_rn(k.z_n_1, __dmul_rn(b, k.gain)));
+        else {
+          c0 = __dadd_rn(c0, __dmul_rn(z_i, __dadd_rn(__dmul_rn(a, k.gain), __dmul_rn(k.z_n_1, __dmul_rn(b, k.gain)))));
+          z_i = __dmul_rn(z_i, k.z);
+        }
+      }
+    }
+    __syncwarp();
+  }
+  double prev = __ddiv_rn(c0, __dsub_rn(1.0, __dmul_rn(k.z_n_1, k.z_n_1)));
+  // ---- causal pass ----
+  for (int col0 = 0; col0 < n; col0 += kPfT) {
+    load_tile(ta, col0);
+    if (live) {
+      for (int j = 0; j < kPfT && col0 + j < n; ++j) {
+        if (col0 + j > 0) prev = __dadd_rn(__dmul_rn(ta[lane][j], k.gain), __dmul_rn(k.z, prev));
+        ta[lane][j] = prev;
+      }
+    }
+    store_tile(ta, col0);
+  }
+  // ---- anticausal initialisation and pass (tiles from the last one backwards; the last tile may be ragged) ----
+  double nxt = 0.0;
+  const int last0 = ((n - 1) / kPfT) * kPfT;
+  for (int col0 = last0; col0 >= 0; col0 -= kPfT) {
+    load_tile(ta, col0);
+    if (col0 == last0 && (n - 1) - last0 == 0) load_tile(tb, col0 - kPfT);     // c[n-2] lives in the previous tile
+    if (live) {
+      for (int j = min(kPfT - 1, n - 1 - col0); j >= 0; --j) {
+        const int i = col0 + j;
+        if (i == n - 1) {
+          const double cm2 = j > 0 ? ta[lane][j - 1] : tb[lane][kPfT - 1];
+          nxt = __dmul_rn(__dadd_rn(__dmul_rn(k.z, cm2), ta[lane][j]), k.anti);
+        } else {
+          nxt = __dmul_rn(k.z, __dsub_rn(nxt, ta[lane][j]));
+        }
+        ta[lane][j] = nxt;
+      }
+    }
+    store_tile(ta, col0);
   }
 }
 
@@ -132,12 +247,12 @@ int zoom_cubic(const float* in, int n, int H, int W, double* work, float* out, i
   const int64_t img = (int64_t)H * W;
   {   // along H (axis 0 of a slice): one line per (slice, column); neighbouring threads = neighbouring columns (coalesced)
     const int64_t lines = (int64_t)n * W;
-    spline_prefilter_kernel<float><<<(unsigned)((lines + 127) / 128), 128, 0, s>>>(in, work, lines, W, img, 1, W, H);
+    spline_prefilter_cols_kernel<float><<<(unsigned)((lines + 31) / 32), 32, 0, s>>>(in, work, lines, W, img, W, H);
     CSWIN_LAUNCH_CHECK();
   }
   {   // along W, in place on the float64 coefficients
     const int64_t lines = (int64_t)n * H;
-    spline_prefilter_kernel<double><<<(unsigned)((lines + 127) / 128), 128, 0, s>>>(work, work, lines, H, img, W, 1, W);
+    spline_prefilter_rows_kernel<<<(unsigned)((lines + 31) / 32), 32, 0, s>>>(work, lines, W, W);   // rows of consecutive slices are contiguous
     CSWIN_LAUNCH_CHECK();
   }
   const int64_t total = (int64_t)n * OH * OW;
