@@ -378,9 +378,12 @@ def run_native(args):
     # ---- e2e: HOST buffers through the public API (SliceEngine): every step copies its batch host->device from pinned
     #      memory, runs the forward, and reads the uint8 label map back; copies of adjacent steps overlap the forward ----
     engine = cw.SliceEngine(model, batch=B, compute_dtype=torch.bfloat16, inflight=K)
-    pinned = [(host + 0.001 * i).pin_memory() for i in range(4)]
+    # the host batch is what the reference's evaluation loop hands to the model: single-channel slices (utils.py:69-71), which
+    # CSwinUnet.forward repeats to 3 channels (vision_transformer.py:40-41) — here on the device, after ONE channel crossed PCIe.
+    # (`host` has three identical channels: synth 'ct' slices are that repeat.)
+    pinned = [(host[:, :1] + 0.001 * i).contiguous().pin_memory() for i in range(4)]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    h2d_bytes, d2h_bytes = engine.bytes_per_batch()
+    h2d_bytes, d2h_bytes = engine.bytes_per_batch(host_chans=1)
 
     def e2e_run(n):
         done = 0
@@ -488,8 +491,8 @@ def run_native(args):
             "clocks": clocks, "gpu_launches": int(launches_per_fwd * args.steps),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes),
                     "d2h_bytes_per_step": int(d2h_bytes), "ms_per_step": ms_e2e / args.steps,
-                    "path": "SliceEngine.predict_stream: pinned host fp32 batch -> H2D -> graph-replayed forward with in-kernel "
-                            "argmax -> D2H uint8 label map; 2 buffer slots, copies overlap the neighbouring steps' forward"},
+                    "path": "SliceEngine.predict_stream: pinned host fp32 batch of single-channel slices (as test_single_volume feeds them) -> H2D -> 1->3 channel repeat on the device -> graph-replayed forward with in-kernel "
+                            f"argmax -> D2H uint8 label map; {K} forwards in flight (own slot, graph and stream each), copies overlap the forwards"},
             "roofline": roofline, "roofline_attention": roofline_attention, "roofline_model": roofline_model}
 
     # ---- train step (BASELINE configs[2]): forward + native backward + gradient all-reduce (NCCL, N > 1) + SGD, bf16

@@ -112,12 +112,18 @@ class SliceEngine:
         n = host_x.shape[0]
         if n > self.batch or tuple(host_x.shape[2:]) != (self.size, self.size):
             raise ValueError(f"expected at most {self.batch} slices of {self.size}x{self.size}, got {tuple(host_x.shape)}")
-        if host_x.shape[1] == 1 and self.in_chans == 3:
-            host_x = host_x.expand(-1, 3, -1, -1)                  # vision_transformer.py:40-41 (1 -> 3 channel repeat)
         h2d, cs, d2h = self.streams["h2d"], slot["stream"], self.streams["d2h"]
         with torch.cuda.stream(h2d):
             h2d.wait_event(slot["ev_done"])                        # previous forward on this slot has consumed x
-            slot["x"][:n].copy_(host_x, non_blocking=True)
+            if host_x.shape[1] == 1 and self.in_chans == 3:
+                # 1 -> 3 channel repeat (vision_transformer.py:40-41; test_single_volume feeds single-channel slices, utils.py:69-71):
+                # ONE channel crosses PCIe, the repeat is a device-side broadcast copy (a third of the host->device bytes)
+                if "x1" not in slot:
+                    slot["x1"] = torch.empty((self.batch, 1, self.size, self.size), dtype=torch.float32, device=self.device)
+                slot["x1"][:n].copy_(host_x, non_blocking=True)
+                slot["x"][:n].copy_(slot["x1"][:n].expand(-1, 3, -1, -1))
+            else:
+                slot["x"][:n].copy_(host_x, non_blocking=True)
             slot["ev_in"].record(h2d)
         with torch.cuda.stream(cs):
             cs.wait_event(slot["ev_in"])
@@ -149,8 +155,9 @@ class SliceEngine:
         while pending:
             yield self._collect(pending.pop(0))
 
-    def bytes_per_batch(self) -> Tuple[int, int]:
-        return self.batch * self.in_chans * self.size * self.size * 4, self.batch * self.size * self.size
+    def bytes_per_batch(self, host_chans: Optional[int] = None) -> Tuple[int, int]:
+        """(host->device, device->host) bytes of one full batch; host_chans = channels of the host tensor (1: repeated on the device)."""
+        return self.batch * (host_chans or self.in_chans) * self.size * self.size * 4, self.batch * self.size * self.size
 
 
 STAGING_THREADS = max(1, int(os.environ.get("CSWIN_STAGING_THREADS", "4")))   # host threads copying a batch into its pinned staging buffer

@@ -423,6 +423,11 @@ def test_engine_concurrent_forwards_equal_sequential(inflight):
     for _ in range(2):
         con = list(eng.predict_stream(iter(batches)))
         assert len(con) == len(seq) and all(torch.equal(a, b) for a, b in zip(con, seq))
+    # single-channel host batches: one channel crosses PCIe, the 1 -> 3 repeat (vision_transformer.py:40-41) happens on the device
+    one = [b[:, :1].contiguous() for b in batches]
+    want1 = list(eng.predict_stream(iter([b.expand(-1, 3, -1, -1).contiguous() for b in one])))
+    got1 = list(eng.predict_stream(iter(one)))
+    assert all(torch.equal(a, b) for a, b in zip(got1, want1))
     vol = _synthetic_volume(D=8, S=256, seed=4)
     want, _ = cw.predict_volume(cw.SliceEngine(m, batch=3, compute_dtype=torch.bfloat16, inflight=1), vol, resample="gpu")
     got, _ = cw.predict_volume(eng, vol, resample="gpu")
