@@ -158,6 +158,36 @@ def cpu_forward_rate(budget_s: float, batch: int, min_iters: int = 2):
     return n * batch / dt, cores, n, dt, kind
 
 
+def cpu_extra_rates(budget_s: float = 8.0):
+    """BASELINE.md 3 plan, items 2: the reference on the host cores at batch 1 (eval forward) and one train step at batch 24
+    (trainer.py:42-63 loop).  Bounded: a few forwards, one warm-up + >= 1 timed train step.  None if baseline/_ref is absent."""
+    from cswin_unet_b200 import synth
+    ref = reference_model("cpu")
+    if ref is None:
+        return None
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    out = {"cores": cores}
+    x1 = torch.from_numpy(synth.synth_image_batch(1, 3, 224, seed=0, kind="ct"))
+    with torch.no_grad():
+        ref(x1)
+        t0 = time.perf_counter(); n = 0
+        while n < 3 or (time.perf_counter() - t0) < 1.0:
+            ref(x1); n += 1
+        out["forward_batch1"] = {"slices_per_s": n / (time.perf_counter() - t0), "ms_per_forward": 1e3 * (time.perf_counter() - t0) / n}
+    ref.train()
+    x = torch.from_numpy(synth.synth_image_batch(BATCH, 3, 224, seed=0, kind="ct"))
+    y = torch.from_numpy(synth.synth_labels(BATCH, 224, 9, seed=0)).long()
+    step = _reference_train_step_fn(ref, x, y, 9, None)
+    step()
+    t0 = time.perf_counter(); n = 0
+    while n < 1 or (time.perf_counter() - t0) < budget_s - 3.0:
+        step(); n += 1
+    dt = time.perf_counter() - t0
+    out[f"train_step_batch{BATCH}"] = {"slices_per_s": n * BATCH / dt, "ms_per_step": 1e3 * dt / n, "steps": n}
+    return out
+
+
 def reference_model(device="cpu"):
     """The unmodified reference model with the bench's synthetic weights, or None if baseline/_ref did not travel."""
     from baseline import ref_loader
@@ -207,7 +237,28 @@ def run_reference(args):
     return 0
 
 
-def reference_cuda_rates(dev, batches=(BATCH, 1), iters=10, warm=3):
+def _reference_train_step_fn(ref, x, y, n_classes=9, autocast=None):
+    """One step of the reference's own training loop (trainer.py:42-63: SGD momentum .9 / wd 1e-4, 0.4 CE + 0.6 Dice (utils.py:9-45,
+    restated by the oracle and pinned against the reference's DiceLoss), zero_grad / backward / step) on a reference model."""
+    from oracle import cswin_oracle as O          # the loss restatement only (baseline arm, not the product path)
+    opt = torch.optim.SGD(ref.parameters(), lr=0.05, momentum=0.9, weight_decay=1e-4)
+
+    def step():
+        if autocast is None:
+            out = ref(x)
+        else:
+            with autocast:
+                out = ref(x)
+        out = out.float()
+        loss = 0.4 * torch.nn.functional.cross_entropy(out, y) + 0.6 * O.dice_loss(out, y, n_classes)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        return loss
+    return step
+
+
+def reference_cuda_rates(dev, batches=(BATCH, 1, 192), iters=10, warm=3):
     """Eager-CUDA throughput of the unmodified reference on this GPU (stock code path: cuBLAS / cuDNN / ATen kernels, no repo
     module): fp32 (how the reference runs, TF32 off as train.py:73-78 leaves it) and bf16 autocast; device-resident inputs,
     CUDA events.  Returns None when baseline/_ref did not travel."""
@@ -226,17 +277,38 @@ def reference_cuda_rates(dev, batches=(BATCH, 1), iters=10, warm=3):
                         return ref(x)
                     with ctx:
                         return ref(x)
-                for _ in range(warm):
+                it_b = iters if B <= BATCH else 3                # batch 192 is ~150 ms per eager forward
+                for _ in range(warm if B <= BATCH else 1):
                     fwd()
                 torch.cuda.synchronize()
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-                for _ in range(iters):
+                for _ in range(it_b):
                     fwd()
                 e1.record()
                 torch.cuda.synchronize()
-            ms = e0.elapsed_time(e1) / iters
+            ms = e0.elapsed_time(e1) / it_b
             out[f"batch{B}_{name}"] = {"slices_per_s": B / (ms * 1e-3), "ms_per_forward": ms}
+    # the reference's train step (trainer.py:42-63) in eager PyTorch on this GPU, batch 24: the baseline of `train_step`
+    try:
+        ref.train()
+        x = torch.from_numpy(synth.synth_image_batch(BATCH, 3, 224, seed=0, kind="ct")).to(dev)
+        y = torch.from_numpy(synth.synth_labels(BATCH, 224, 9, seed=0)).to(dev).long()
+        for name, ctx in (("fp32", None), ("bf16_autocast", torch.autocast("cuda", dtype=torch.bfloat16))):
+            step = _reference_train_step_fn(ref, x, y, 9, ctx)
+            for _ in range(3):
+                step()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(5):
+                step()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 5
+            out[f"train_step_batch{BATCH}_{name}"] = {"slices_per_s": BATCH / (ms * 1e-3), "ms_per_step": ms}
+    except Exception as e:                                         # noqa: BLE001 — reported, the forward numbers stand
+        out["train_step_error"] = f"{type(e).__name__}: {e}"[:200]
     del ref
     torch.cuda.empty_cache()
     return out
@@ -574,6 +646,10 @@ def run_native(args):
                 line["speedup_vs_reference_cuda"] = {
                     "bf16_vs_ref_fp32": value / rc[f"batch{BATCH}_fp32"]["slices_per_s"],
                     "bf16_vs_ref_bf16_autocast": value / rc[f"batch{BATCH}_bf16_autocast"]["slices_per_s"]}
+                ts, rt = line.get("train_step", {}), rc.get(f"train_step_batch{BATCH}_bf16_autocast")
+                if ts.get("value") and rt:
+                    line["speedup_vs_reference_cuda"]["train_step_vs_ref_bf16_autocast"] = ts["value"] / rt["slices_per_s"]
+                    line["speedup_vs_reference_cuda"]["train_step_vs_ref_fp32"] = ts["value"] / rc[f"train_step_batch{BATCH}_fp32"]["slices_per_s"]
         except Exception as e:                                     # noqa: BLE001
             line["reference_cuda"] = {"error": f"{type(e).__name__}: {e}"[:300]}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -581,6 +657,12 @@ def run_native(args):
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
                                 "sample": f"{n} forwards of batch {BATCH} in {dt:.1f} s, "
                                           f"{'unmodified reference' if kind == 'reference' else 'oracle port'} (torch CPU fp32), {cores} threads"}
+        try:                                                       # batch-1 forward and one train step on the host cores
+            ex = cpu_extra_rates()
+            if ex is not None:
+                line["cpu_baseline"]["more"] = ex
+        except Exception as e:                                     # noqa: BLE001
+            line["cpu_baseline"]["more"] = {"error": f"{type(e).__name__}: {e}"[:200]}
     if rank == 0:
         emit(line)
     if world > 1:
