@@ -201,7 +201,6 @@ class CSWinTransformer(_Native):
             lg = lg.view(B, H * up.up_factor, W * up.up_factor, -1).permute(0, 3, 1, 2)
             return lg.to(logits_dtype) if logits_dtype is not None else lg
         dt = x.dtype
-        enc = up._kernel_logits(x, H, W)
         wo = self.output.weight
         npad = 16 if self.num_classes <= 16 else self.num_classes             # 16-column rows: vector loads in the head kernel
 
@@ -210,13 +209,13 @@ class CSWinTransformer(_Native):
             return torch.nn.functional.pad(w, (0, 0, 0, npad - w.shape[0]))
         wf = self._w("head.w", (wo, up.out.weight), dt, fold_w)
         bf = self._w("head.b", (wo, up.out.bias), dt, lambda o, b: o.reshape(o.shape[0], -1).float() @ b.float())
-        z = ops.linear(x, wf)                                                   # (B, L, npad); columns >= classes are 0
+        enc, z = up._kernel_logits(x, H, W, wf, z_key="head")                   # z (B, L, npad) = folded head map of x; columns >= classes are 0
         if self.num_classes <= 16:
-            logits, labels = ops.carafe_head(enc, z.view(B * L, -1), bf, B, H, W, up.up_factor, want_logits=want_logits,
+            logits, labels = ops.carafe_head(enc, z.flatten(0, 1), bf, B, H, W, up.up_factor, want_logits=want_logits,
                                              want_labels=want_labels, logits_dtype=logits_dtype or dt,
                                              n_classes=self.num_classes, out_logits=out_logits, out_labels=out_labels)
         else:                                                                   # generic re-assembly, labels via torch
-            logits = ops.carafe_reassemble(enc, z.view(B * L, -1), bf, B, H, W, up.up_factor, nchw_out=True,
+            logits = ops.carafe_reassemble(enc, z.flatten(0, 1), bf, B, H, W, up.up_factor, nchw_out=True,
                                            out_dtype=logits_dtype or dt)
             labels = logits.argmax(1).to(torch.uint8) if want_labels else None
             if out_logits is not None and want_logits:

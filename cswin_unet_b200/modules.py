@@ -578,15 +578,29 @@ class CARAFE(_Native):
                                  self.kernel_size // 2)
         self.out = nn.Conv2d(dim, dim_out, 1)
 
-    def _kernel_logits(self, x: Tensor, H: int, W: int) -> Tensor:
+    def _kernel_logits(self, x: Tensor, H: int, W: int, z_weight: Optional[Tensor] = None, z_key: str = "out"):
+        """Kernel logits of the re-assembly (down -> 3x3 encoder).  With `z_weight` ((Nz, C): the 1x1 map that is applied at low
+        resolution, `out.weight` or the folded head) ONE Linear computes [down | z] from x — both read the same rows — and the
+        method returns (logits, z) with z a column view of that Linear's output."""
         dt = x.dtype
-        B = x.shape[0]
-        d = ops.linear(x, self._w("down.w", self.down.weight, dt, lambda t: t.reshape(t.shape[0], -1)),
-                       self._w("down.b", self.down.bias, dt))                           # (B, L, C/4)
+        wd = self._w("down.w", self.down.weight, dt, lambda t: t.reshape(t.shape[0], -1))
+        bd = self._w("down.b", self.down.bias, dt)
+        z = None
+        if z_weight is None:
+            d = ops.linear(x, wd, bd)                                                   # (B, L, C/4)
+        else:
+            nd, nz = wd.shape[0], z_weight.shape[0]
+            wcat = self._w("downz.w." + z_key, (self.down.weight, z_weight), dt,
+                           lambda a, b: torch.cat([a.reshape(a.shape[0], -1).to(dt), b.reshape(b.shape[0], -1).to(dt)], 0))
+            bcat = self._w("downz.b." + z_key, (self.down.bias, z_weight), dt,
+                           lambda a, b: torch.cat([a.to(dt), torch.zeros(b.shape[0], dtype=dt, device=a.device)]))
+            y = ops.linear(x, wcat, bcat)                                               # (B, L, C/4 + Nz): [down(x) | z(x)], no bias on z yet
+            d, z = y[..., :nd], y[..., nd:]
         col = ops.im2col_tokens(d, H, W, 3, 3, 1, 1)
-        return ops.linear(col, self._w("enc.w", self.encoder.weight, dt,
-                                       lambda t: t.permute(0, 2, 3, 1).reshape(t.shape[0], -1)),
-                          self._w("enc.b", self.encoder.bias, dt))                      # (B*L, 9 s^2)
+        enc = ops.linear(col, self._w("enc.w", self.encoder.weight, dt,
+                                      lambda t: t.permute(0, 2, 3, 1).reshape(t.shape[0], -1)),
+                         self._w("enc.b", self.encoder.bias, dt))                       # (B*L, 9 s^2)
+        return enc if z_weight is None else (enc, z)
 
     def _kernel_logits_tape(self, x: Tensor, H: int, W: int) -> Tensor:
         """_kernel_logits on the autograd tape (training)."""
@@ -603,10 +617,9 @@ class CARAFE(_Native):
             z = ag.linear(x, rs(self.out.weight), None)
             return ag.CarafeReassembleFn.apply(enc, z.view(B * L, -1), self.out.bias, B, H, W, self.up_factor)
         dt = x.dtype
-        enc = self._kernel_logits(x, H, W)
-        z = ops.linear(x, self._w("out.w", self.out.weight, dt, lambda t: t.reshape(t.shape[0], -1)))   # no bias yet
-        return ops.carafe_reassemble(enc, z.view(B * L, -1), self._w("out.b", self.out.bias, dt), B, H, W,
-                                     self.up_factor)
+        enc, z = self._kernel_logits(x, H, W, self.out.weight)                          # z = out(x) without its bias, at LOW resolution
+        return ops.carafe_reassemble(enc, z.reshape(B * L, -1) if z.is_contiguous() else z.flatten(0, 1), self._w("out.b", self.out.bias, dt),
+                                     B, H, W, self.up_factor)
 
 
 class CARAFE4(CARAFE):
