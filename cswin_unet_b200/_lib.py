@@ -17,7 +17,7 @@ LIB_PATH = os.environ.get("CSWIN_LIB_PATH") or os.path.join(_HERE, "libcswin_b20
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "cswin_b200.h")
 
 F32, BF16 = 0, 1
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 c_void_p, c_int32, c_int64, c_float = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 
@@ -148,6 +148,8 @@ SIGNATURES = {
     "cswin_stage_plan": (c_int32, [c_int32, c_int32, c_int32, c_int32, c_int32, C.POINTER(c_int32), C.POINTER(c_int32),
                                    C.POINTER(c_int32), C.POINTER(StagePlan)]),
     "cswin_stage_fwd": (c_int32, [C.POINTER(StageArgs), c_int32, c_void_p]),
+    "cswin_stem_fwd": (c_int32, [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_int32, c_int32,
+                                 c_int32, c_int32, c_void_p, C.POINTER(c_int32)]),
     "cswin_layernorm_stats_fwd": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int32, c_float,
                                             c_void_p, c_int32, c_void_p]),
     "cswin_row_stats": (c_int32, [c_void_p, c_int64, c_int64, c_int32, c_void_p, c_int32, c_void_p]),

@@ -309,6 +309,20 @@ int32_t cswin_qkv_lepe_attention_supported(int32_t C, int32_t reso, int32_t n_br
   return qkv_attn_supported(C, reso, n_branches, heads, H_sp, W_sp);
 }
 
+int cswin_stem_fwd(const void* x, int32_t x_is_f32, const void* w_packed, const float* bias, const float* gamma, const float* beta,
+                   float eps, void* out, float* stats, int32_t B, int32_t H, int32_t W, int32_t dtype, cswin_stream_t stream,
+                   int32_t* handled) {
+  CSWIN_REQUIRE(handled != nullptr, CSWIN_ERR_INVALID, "stem_fwd: null handled");
+  *handled = 0;
+  CSWIN_REQUIRE(dtype == CSWIN_BF16, CSWIN_ERR_UNSUPPORTED, "stem_fwd: exists on the bf16 / tcgen05 path only");
+  CSWIN_REQUIRE(x && w_packed && bias && gamma && beta && out && stats && B >= 0 && H > 0 && W > 0, CSWIN_ERR_INVALID, "stem_fwd: bad arguments");
+  if (B == 0) { *handled = 1; return CSWIN_OK; }
+  bool h = false;
+  const int rc = stem_fwd_tc(x, x_is_f32, w_packed, bias, gamma, beta, eps, out, stats, B, H, W, (cudaStream_t)stream, &h);
+  *handled = h ? 1 : 0;
+  return rc;
+}
+
 int cswin_stage_plan(int32_t B, int32_t reso, int32_t C, int32_t hidden, int32_t n_branches, const int32_t* heads,
                      const int32_t* H_sp, const int32_t* W_sp, cswin_stage_plan_t* plan) {
   CSWIN_REQUIRE(heads && H_sp && W_sp && plan, CSWIN_ERR_INVALID, "stage_plan: null pointer");

@@ -118,6 +118,8 @@ int qkv_attn_supported(int C, int reso, int nb, const int* heads, const int* hs,
 int linear_tc_stats_parts(int64_t M, int N, int K, int act);
 int stage_plan(int B, int reso, int C, int hidden, int nb, const int* heads, const int* hs, const int* ws, cswin_stage_plan_t* out);
 int stage_fwd_tc(const cswin_stage_args_t* a, cudaStream_t stream);
+int stem_fwd_tc(const void* x, int x_is_f32, const void* w_packed, const float* bias, const float* gamma, const float* beta, float eps,
+                void* out, float* stats, int B, int H, int W, cudaStream_t stream, bool* handled);
 int linear_fwd_simt(const cswin_linear_args_t* a, int dtype, cudaStream_t s);
 int linear_fwd_tc(const cswin_linear_args_t* a, cudaStream_t s, bool* handled);
 int im2col_tokens(const void* x, int64_t x_bs, int64_t x_ts, void* col, int64_t ldcol, int B, int H, int W, int C, int KH,

@@ -39,6 +39,9 @@ Tensor = torch.Tensor
 # Default 1 (off); kept as an A/B switch.
 N_STREAMS = max(1, int(os.environ.get("CSWIN_STREAMS", "1")))
 
+# stem conv + LayerNorm as one implicit-GEMM launch (csrc/stem_tc.cu) instead of im2col + Linear + LayerNorm (bf16 inference)
+FUSE_STEM = os.environ.get("CSWIN_FUSE_STEM", "1") != "0"
+
 # training head folded like the inference head (CSWIN_UNFOLDED_TRAIN_HEAD=1 restores the reference's unfolded structure)
 FOLD_TRAIN_HEAD = os.environ.get("CSWIN_UNFOLDED_TRAIN_HEAD") != "1"
 
@@ -120,11 +123,20 @@ class CSWinTransformer(_Native):
         B = x.shape[0]
         K = conv.weight[0].numel()
         Kp = (K + 7) // 8 * 8                               # row pitch multiple of 16 B for the bf16 TMA path
-        col = ops.im2col_nchw(x, 7, 7, 4, 2, Kp, dt)                      # the network input needs no gradient
         if ag.needs_grad(*self.stage1_conv_embed.parameters()):
+            col = ops.im2col_nchw(x, 7, 7, 4, 2, Kp, dt)                  # the network input needs no gradient
             wk = torch.nn.functional.pad(conv.weight.reshape(conv.weight.shape[0], -1), (0, Kp - K))
             y = ag.LayerNormFn.apply(ag.linear(col, wk, conv.bias), ln.weight, ln.bias, ln.eps)
             return y.view(B, -1, y.shape[-1])
+        if (FUSE_STEM and dt == torch.bfloat16 and x.is_cuda and tuple(conv.weight.shape) == (64, 3, 7, 7) and conv.stride == (4, 4)
+                and conv.padding == (2, 2) and conv.bias is not None):
+            # conv + token layout + LayerNorm + row statistics in one tcgen05 launch (csrc/stem_tc.cu)
+            f32 = torch.float32
+            y = ops.stem_fused(x, self._w("stem.w192", conv.weight, dt, lambda t: torch.nn.functional.pad(t.reshape(t.shape[0], -1), (0, 192 - K))),
+                               self._w("stem.b32", conv.bias, f32), self._w("stem.n.w32", ln.weight, f32), self._w("stem.n.b32", ln.bias, f32), ln.eps)
+            if y is not None:
+                return y
+        col = ops.im2col_nchw(x, 7, 7, 4, 2, Kp, dt)
         wk = self._w("stem.w", conv.weight, dt, lambda t: torch.nn.functional.pad(t.reshape(t.shape[0], -1), (0, Kp - K)))
         y = ops.linear(col, wk, self._w("stem.b", conv.bias, dt))
         y = ops.layernorm_with_row_stats(y, self._w("stem.n.w", ln.weight, dt), self._w("stem.n.b", ln.bias, dt), ln.eps)

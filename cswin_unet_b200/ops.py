@@ -372,6 +372,29 @@ def stage_forward(x: Tensor, stats_in: Tensor, blocks: Sequence[dict], reso: int
     return x
 
 
+def stem_fused(x: Tensor, w_packed: Tensor, bias: Tensor, gamma: Tensor, beta: Tensor, eps: float) -> Optional[Tensor]:
+    """Conv2d(3, 64, 7, 4, 2) + token layout + LayerNorm(64) in one tcgen05 launch (cswin_stem_fwd).  x (B, 3, H, W) fp32 / bf16,
+    w_packed (64, 192) bf16, bias / gamma / beta (64) fp32.  Returns (B, Ho Wo, 64) bf16 carrying `_cswin_stats`, or None when the
+    shape is outside the kernel's envelope (the caller composes im2col + Linear + LayerNorm)."""
+    _need_cuda(x, w_packed, bias, gamma, beta)
+    assert x.dim() == 4 and x.shape[1] == 3 and x.dtype in (torch.float32, torch.bfloat16)
+    assert w_packed.dtype == torch.bfloat16 and tuple(w_packed.shape) == (64, 192) and w_packed.is_contiguous()
+    assert bias.dtype == gamma.dtype == beta.dtype == torch.float32 and bias.numel() == gamma.numel() == beta.numel() == 64
+    x = x.contiguous()
+    B, _, H, W = x.shape
+    Ho, Wo = (H + 4 - 7) // 4 + 1, (W + 4 - 7) // 4 + 1
+    out = torch.empty((B, Ho * Wo, 64), dtype=torch.bfloat16, device=x.device)
+    st = torch.empty((B * Ho * Wo, 1, 2), dtype=torch.float32, device=x.device)
+    handled = C.c_int32(0)
+    check(lib().cswin_stem_fwd(x.data_ptr(), int(x.dtype == torch.float32), w_packed.data_ptr(), bias.data_ptr(), gamma.data_ptr(),
+                               beta.data_ptr(), C.c_float(eps), out.data_ptr(), st.data_ptr(), B, H, W, BF16, _stream(),
+                               C.byref(handled)), "cswin_stem_fwd")
+    if not handled.value:
+        return None
+    out._cswin_stats = st
+    return out
+
+
 SGD_CHUNK = 65536
 
 

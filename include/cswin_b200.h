@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define CSWIN_ABI_VERSION 6
+#define CSWIN_ABI_VERSION 7
 
 typedef struct CUstream_st* cswin_stream_t; /* == cudaStream_t */
 
@@ -238,6 +238,19 @@ typedef struct {
 int cswin_qkv_lepe_attention_fwd(const cswin_qkv_attn_args_t* args, int32_t dtype, cswin_stream_t stream);
 int32_t cswin_qkv_lepe_attention_supported(int32_t C, int32_t reso, int32_t n_branches, const int32_t* heads, const int32_t* H_sp,
                                            const int32_t* W_sp);
+
+/* ---- the stem in one launch (bf16 / tcgen05 only): Conv2d(3, 64, 7, stride 4, padding 2) -> tokens -> LayerNorm(64) -------------
+ * replaces `stage1_conv_embed` (networks/cswin_unet.py:338-342: conv :339, Rearrange :340, LayerNorm :341) — an implicit GEMM whose
+ * A tile is gathered from the NCHW image inside the CTA (no column matrix), bias + LayerNorm + row statistics in the epilogue.
+ *   x        : (B, 3, H, W) fp32 (x_is_f32 = 1) or bf16, contiguous
+ *   w_packed : (64, 192) bf16 = conv.weight.reshape(64, 147) zero-padded to 192 columns (column (c*7 + ky)*7 + kx), 16-byte aligned
+ *   bias, gamma, beta : (64) fp32 (conv.bias, LayerNorm weight / bias)
+ *   out      : (B * Ho * Wo, 64) bf16 token-major, Ho = (H + 4 - 7) / 4 + 1;  stats: (B Ho Wo, 1, 2) fp32 (sum, sum^2) of the bf16 rows
+ * *handled = 0 (nothing launched) when the staged input rows of a tile do not fit in shared memory (very narrow / very wide images): the caller composes
+ * cswin_im2col_nchw + cswin_linear_fwd + cswin_layernorm_stats_fwd instead. */
+int cswin_stem_fwd(const void* x, int32_t x_is_f32, const void* w_packed, const float* bias, const float* gamma, const float* beta,
+                   float eps, void* out, float* stats, int32_t B, int32_t H, int32_t W, int32_t dtype, cswin_stream_t stream,
+                   int32_t* handled);
 
 /* ---- all CSWinBlocks of one stage in ONE persistent dataflow launch (bf16 / tcgen05 only, inference) ------------------------
  * replaces the stage loops `for blk in self.stageN: x = blk(x)` (networks/cswin_unet.py:462-478, :505-533) over

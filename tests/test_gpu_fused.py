@@ -120,3 +120,41 @@ def test_block_with_fused_kernels_matches_oracle(C, reso, heads, split, last, B,
     print(f"[block C={C}] launches fused {outs[(True, 'n')]} vs composed {outs[(False, 'n')]}; max-abs vs fp64 fused {ef:.3e} composed {ec:.3e}")
     assert outs[(True, "n")] < outs[(False, "n")]
     assert ef <= 1.25 * ec + 5e-3
+
+
+@pytest.mark.parametrize("B,S,in_dtype", [(2, 224, torch.float32), (3, 224, torch.bfloat16), (1, 512, torch.float32), (5, 172, torch.float32), (2, 96, torch.float32)])
+def test_stem_fused_equals_composed_and_oracle(B, S, in_dtype, monkeypatch):
+    """csrc/stem_tc.cu: Conv2d(3, 64, 7, 4, 2) + token layout + LayerNorm(64) (cswin_unet.py:338-342) as one implicit-GEMM launch,
+    against the composed path (im2col + Linear + LayerNorm) and against torch in fp64; ragged last tile (B = 3, 5), tiles that
+    span two images, a 512^2 input (128 pixels per output row) and small images (43 and 24 pixels per output row)."""
+    from cswin_unet_b200 import model as model_mod
+    m = cw.cswin_tiny_224(num_classes=9).eval()                           # (the stem does not depend on img_size)
+    shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    sd = {k: torch.from_numpy(v) for k, v in synth.synth_state_dict(shapes, seed=5).items()}
+    sd["stage1_conv_embed.2.weight"] = 1.0 + 0.3 * torch.from_numpy(synth.synth_tensor("stem/g", (64,), 5))
+    sd["stage1_conv_embed.2.bias"] = 0.2 * torch.from_numpy(synth.synth_tensor("stem/b", (64,), 6))
+    sd["stage1_conv_embed.0.bias"] = 0.1 * torch.from_numpy(synth.synth_tensor("stem/cb", (64,), 7))
+    m.load_state_dict(sd, strict=True)
+    m = m.to(DEV)
+    x = torch.from_numpy(synth.synth_image_batch(B, 3, S, seed=3, kind="randn")).to(in_dtype).to(DEV)
+    outs = {}
+    for fused in (True, False):
+        monkeypatch.setattr(model_mod, "FUSE_STEM", fused)
+        n0 = cw.launch_count()
+        with torch.no_grad():
+            y = m._stem(x, torch.bfloat16)
+        outs[fused] = (y.float().cpu(), y._cswin_stats.cpu(), cw.launch_count() - n0)
+    assert outs[True][2] == 1 and outs[False][2] == 3, (outs[True][2], outs[False][2])
+    xr = x.float().cpu().double()
+    ref = torch.nn.functional.conv2d(xr, sd["stage1_conv_embed.0.weight"].bfloat16().double(), sd["stage1_conv_embed.0.bias"].double(), stride=4, padding=2)
+    ref = ref.flatten(2).transpose(1, 2)
+    ref = torch.nn.functional.layer_norm(ref, (64,), sd["stage1_conv_embed.2.weight"].double(), sd["stage1_conv_embed.2.bias"].double(), 1e-5)
+    ef, ec = (outs[True][0].double() - ref).abs().max().item(), (outs[False][0].double() - ref).abs().max().item()
+    d = (outs[True][0] - outs[False][0]).abs().max().item()
+    # the statistics side channel must describe the bf16 rows that were written
+    yb = outs[True][0].double()
+    st = outs[True][1].double().view(-1, 2)
+    es = max((st[:, 0] - yb.sum(-1).flatten()).abs().max().item(), (st[:, 1] - (yb * yb).sum(-1).flatten()).abs().max().item())
+    print(f"[stem fused B={B} S={S} {in_dtype}] max-abs vs fp64: fused {ef:.3e}, composed {ec:.3e}; fused vs composed {d:.3e}; stats error {es:.2e}")
+    assert outs[True][0].shape == ref.shape and torch.isfinite(outs[True][0]).all()
+    assert ef <= 1.25 * ec + 2e-3 and d <= 6e-2 and es <= 2e-3
