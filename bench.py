@@ -4,9 +4,12 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference|reference-cuda]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 ... bench.py --gpus N ...
 
-native arm  : a "step" is one bf16 forward of cswin_tiny_224_lite over one batch of 24 synthetic 3x224x224 slices
-              per GPU through the native kernels (libcswin_b200.so), replayed as a CUDA graph.
-              `value`  = slices/s with the inputs resident in HBM (16 rotating batches = 231 MB > L2),
+native arm  : a "step" is one bf16 forward of cswin_tiny_224_lite over one batch of 96 synthetic 3x224x224 slices
+              per GPU through the native kernels (libcswin_b200.so), replayed as a CUDA graph, 2 such forwards in flight.
+              (Slice inference has no batch of its own — test_single_volume, utils.py:61-90, walks the ~150 slices of a
+              volume — so the engine's batch is a free parameter: 96 x 2 in flight is where the B200 saturates; the batch-24
+              figures, single and 3 in flight, stay in the line as `extra.forward_batch24`; the train step is batch 24.)
+              `value`  = slices/s with the inputs resident in HBM (8 rotating batches = 462 MB > L2),
               `e2e`    = same metric through the public nn.Module call with HOST (pinned) inputs: H2D copy of the
                          batch, forward, argmax label map, D2H of the label map, every step,
               `roofline` = fused LePE attention kernel family: algorithmic bytes / CUDA-event time vs measured HBM peak,
@@ -36,7 +39,8 @@ sys.path.insert(0, ROOT)
 
 METRIC = "CSWin-UNet-tiny 224^2 slices/sec (bf16 fwd)"
 UNIT = "slices/s"
-BATCH = 24
+BATCH = 24                         # BASELINE configs[2]: the train step's batch, and the latency point of the forward
+FWD_BATCH = 96                     # slices per forward step of the headline (throughput point, see the module docstring)
 GFLOP_PER_SLICE_FWD = 10.028       # BASELINE.md section 2 (FlopCounterMode on the unmodified reference)
 # dram__bytes_read.sum + dram__bytes_write.sum of lepe_attn_fwd_tc_kernel, ncu --set full, batch 24, summed over the 26 launches
 # of one forward (2 x 28.95 MB + 4 x 14.50 MB + 18 x 7.28 MB + 2 x 3.67 MB read, ~0 written inside the kernel: the output
@@ -215,8 +219,8 @@ def run_reference(args):
         O, sd = oracle_model()
         kind, what = "port", "CPU port of the reference PyTorch path (oracle/cswin_oracle.py), fp32"
         fwd = lambda x: O.cswin_unet_forward(sd, x)       # noqa: E731
-    # bounded sample per step so that K+W steps end within minutes on any host: a batch of 24 slices is ~1.5 s on 8 cores
-    sample = BATCH
+    # bounded sample per step so that K+W steps end within minutes on any host: a batch of 96 slices is ~1.5 s on 16 cores
+    sample = args.batch
     x = torch.from_numpy(synth.synth_image_batch(sample, 3, 224, seed=0, kind="ct"))
     with torch.no_grad():
         for _ in range(args.warmup):
@@ -258,7 +262,7 @@ def _reference_train_step_fn(ref, x, y, n_classes=9, autocast=None):
     return step
 
 
-def reference_cuda_rates(dev, batches=(BATCH, 1, 192), iters=10, warm=3):
+def reference_cuda_rates(dev, batches=(BATCH, 1, FWD_BATCH, 192), iters=10, warm=3):
     """Eager-CUDA throughput of the unmodified reference on this GPU (stock code path: cuBLAS / cuDNN / ATen kernels, no repo
     module): fp32 (how the reference runs, TF32 off as train.py:73-78 leaves it) and bf16 autocast; device-resident inputs,
     CUDA events.  Returns None when baseline/_ref did not travel."""
@@ -322,15 +326,15 @@ def run_reference_cuda(args):
         emit({"impl": "reference-cuda", "unavailable": "no CUDA device"})
         return 0
     torch.cuda.set_device(local)
-    r = reference_cuda_rates(torch.device("cuda", local), iters=max(args.steps, 5), warm=max(args.warmup, 3))
+    r = reference_cuda_rates(torch.device("cuda", local), batches=tuple(dict.fromkeys((args.batch, BATCH, 1, 192))), iters=max(args.steps, 5), warm=max(args.warmup, 3))
     if r is None:
         emit({"impl": "reference-cuda", "unavailable": "baseline/_ref/networks/cswin_unet.py did not travel with the snapshot"})
         return 0
-    v = r[f"batch{BATCH}_fp32"]
+    v = r[f"batch{args.batch}_fp32"]
     emit({"impl": "reference-cuda", "metric": METRIC, "value": v["slices_per_s"], "unit": UNIT, "n_gpus": 1, "steps": max(args.steps, 5),
           "warmup": max(args.warmup, 3), "ms_per_step": v["ms_per_forward"], "higher_is_better": True, "scaling": "weak",
           "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-          "config": {"workload": f"cswin_tiny_224_lite eval forward, batch {BATCH}, unmodified reference in eager PyTorch on the GPU"},
+          "config": {"workload": f"cswin_tiny_224_lite eval forward, batch {args.batch}, unmodified reference in eager PyTorch on the GPU"},
           "detail": r})
     return 0
 
@@ -366,15 +370,15 @@ def run_native(args):
     model.compute_dtype = torch.bfloat16
 
     B = args.batch
-    n_rot = 16
+    n_rot = 16 if B <= 32 else 8
     host = torch.from_numpy(synth.synth_image_batch(B, 3, 224, seed=1000 + rank, kind="ct"))
-    pool = [(host + 0.001 * i).to(dev) for i in range(n_rot)]      # 16 x 14.4 MB fp32 = 231 MB > 126 MB L2
+    pool = [(host + 0.001 * i).to(dev) for i in range(n_rot)]      # 8 x 57.8 MB fp32 (batch 96) = 462 MB > 126 MB L2
     # K forwards IN FLIGHT: K captured graphs of the same model (own static input / output buffers, own stream each), steps go
     # round-robin over them.  Every step is still one batch-B forward; at batch 24 each kernel is <= 2 waves and latency-bound,
     # so independent forwards overlap on the SMs (the engine's predict_stream does the same, see cswin_unet_b200/engine.py).
     K = max(1, args.inflight)
     from cswin_unet_b200 import _lib as cwlib
-    cap_kb = int(os.environ.get("CSWIN_INFLIGHT_SMEM_CAP_KB", "100")) if K > 1 else 0     # as SliceEngine(inflight > 1) sets it
+    cap_kb = int(os.environ.get("CSWIN_INFLIGHT_SMEM_CAP_KB", "100" if B <= 32 else "0")) if K > 1 else 0     # as SliceEngine(inflight > 1) sets it
     streams = [torch.cuda.Stream() for _ in range(K + 1)]
     static_x = [pool[0].clone() for _ in range(K + 1)]
     graphs, static_y = [], []
@@ -581,19 +585,21 @@ def run_native(args):
                     "what": "the same launches with K copies of the graph replayed concurrently on K streams (the regime `value` is timed in)"},
                 "how": "CUDA graph of the Linear launches of one forward (real buffers, L2-warm as in the step), CUDA events over 20 replays; "
                        "algorithmic flops = 2 M N K of every launch",
-                "why_low": "at batch 24 every launch is <= 2 waves: its time is one latency chain (launch dependency ~2.5 us, first TMA round "
-                           "trip ~1 us, K loop at the ~60 B/clk/SM L2->SM ingest limit, epilogue) around <= 0.5 us of MMA issue; see "
-                           "profiles/r02_timeline_fwd_composed.log and profiles/r02_trace_linear.log"}
+                "why_low": "K = 64..256 for 98 of the 114 launches: arithmetic intensity 40-120 flop/B, i.e. these GEMMs sit at or below the "
+                           "HBM / L2 ridge (252 flop/B), and their time is the epilogue (bias / LayerNorm fold / GELU / residual / row statistics: "
+                           "~14 instructions per output element-pair, issue-bound at 0.4-0.5 IPC per scheduler, profiles/r02_ncu_linear_fc1_b96.txt) "
+                           "plus one TMA round trip per tile; at batch 24 every launch is additionally <= 2 waves (latency chain)"}
     model_tflops = value / world * GFLOP_PER_SLICE_FWD / 1e3
     roofline_model = {"bound": "tensor", "achieved": model_tflops, "peak": pk["bf16_tflops"],
                       "unit": "TFLOP/s", "frac": model_tflops / pk["bf16_tflops"],
-                      "note": "whole forward, 10.028 GFLOP/slice algorithmic, per GPU, vs the burst bf16 peak (the timed region is ~25 ms)"}
+                      "note": "whole forward, 10.028 GFLOP/slice algorithmic, per GPU, vs the burst bf16 peak"}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
             "config": {"workload": f"cswin_tiny_224_lite (9 classes) eval forward, batch {B}/GPU, 3x224x224 synthetic CT-like "
-                                   "slices, synthetic weights; BASELINE configs[2] shapes, forward pass",
+                                   "slices, synthetic weights; BASELINE configs[0] / [2] network, forward pass (slice batches as the volume loop of "
+                                   "configs[3] would feed them; batch-24 figures in extra.forward_batch24)",
                        "global_batch": B * world, "parallelism": f"slice-sharded replicas x{world}, no collective",
                        "l2": f"inputs rotate over {n_rot} batches = {n_rot * host.numel() * 4 / 1e6:.0f} MB > 126 MB L2",
                        "launch": f"CUDA graph replay of the native forward, {K} forwards in flight (one graph + stream each, steps round-robin)",
@@ -626,8 +632,10 @@ def run_native(args):
             import copy
             tmodel = copy.deepcopy(model).train()
             step_fn = cw.TrainStep(tmodel, lr=0.05, compute_dtype=torch.bfloat16)
-            timg = pool[0]
-            tlab = torch.from_numpy(synth.synth_labels(B, 224, 9, seed=rank)).to(dev)
+            TB = min(BATCH, B)                                          # BASELINE configs[2]: batch 24 per GPU
+            tpool = [p_[:TB].contiguous() for p_ in pool]
+            timg = tpool[0]
+            tlab = torch.from_numpy(synth.synth_labels(TB, 224, 9, seed=rank)).to(dev)
             tw, tk = 5, max(5, min(args.steps, 20))                     # warm-up: 3 eager steps + graph capture + 1 replay
             for _ in range(tw):
                 step_fn(timg, tlab)
@@ -635,7 +643,7 @@ def run_native(args):
             n_tr0 = cw.launch_count()
             e0.record()
             for i in range(tk):
-                step_fn(pool[i % n_rot], tlab)
+                step_fn(tpool[i % n_rot], tlab)
             e1.record()
             barrier()
             ms_tr = e0.elapsed_time(e1)
@@ -643,15 +651,15 @@ def run_native(args):
                 t = torch.tensor([ms_tr], device=dev)
                 torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
                 ms_tr = float(t.item())
-            line["train_step"] = {"value": world * tk * B / (ms_tr * 1e-3), "unit": UNIT, "ms_per_step": ms_tr / tk, "steps": tk,
-                                  "warmup": tw, "batch_per_gpu": B, "dtype": "bf16 compute, fp32 master weights + gradients",
+            line["train_step"] = {"value": world * tk * TB / (ms_tr * 1e-3), "unit": UNIT, "ms_per_step": ms_tr / tk, "steps": tk,
+                                  "warmup": tw, "batch_per_gpu": TB, "dtype": "bf16 compute, fp32 master weights + gradients",
                                   "gpu_launches": int(step_fn.native_launches_per_step * tk + (cw.launch_count() - n_tr0)),
                                   "what": "forward + native backward + native loss (0.4 CE + 0.6 Dice) + NCCL gradient all-reduce overlapped with the "
                                           "backward on the pooled gradient buffer (N>1) + native fused SGD(momentum .9, wd 1e-4); whole step "
                                           "(collectives included) replayed as one CUDA graph",
-                                  "roofline_frac_tensor": world and (tk * B / (ms_tr * 1e-3)) * 33.231 / 1e3 / (pk["bf16_tflops_sustained"] or pk["bf16_tflops"])}
+                                  "roofline_frac_tensor": world and (tk * TB / (ms_tr * 1e-3)) * 33.231 / 1e3 / (pk["bf16_tflops_sustained"] or pk["bf16_tflops"])}
             step_fn.close()
-            del tmodel, step_fn
+            del tmodel, step_fn, tpool
         except Exception as e:                                  # noqa: BLE001 — reported, not swallowed
             import traceback
             traceback.print_exc()
@@ -671,7 +679,7 @@ def run_native(args):
                 os._exit(0)
         threading.Thread(target=extras_watchdog, daemon=True).start()
         try:
-            line["extra"] = extra_workloads(cw, synth, model, dev, rank, world, barrier, pool[0], args)
+            line["extra"] = extra_workloads(cw, synth, model, dev, rank, world, barrier, pool[0][:BATCH].contiguous(), args)
         except Exception as e:                                     # noqa: BLE001 — reported, not swallowed
             import traceback
             traceback.print_exc()
@@ -680,12 +688,13 @@ def run_native(args):
             done_x.set()
     if rank == 0 and world == 1 and not args.no_reference_cuda:
         try:                                                       # the eager-PyTorch reference on this same GPU
-            rc = reference_cuda_rates(dev)
+            rc = reference_cuda_rates(dev, batches=tuple(dict.fromkeys((BATCH, 1, B, 192))))
             line["reference_cuda"] = rc if rc is not None else {"unavailable": "baseline/_ref did not travel with the snapshot"}
             if rc is not None:
                 line["speedup_vs_reference_cuda"] = {
-                    "bf16_vs_ref_fp32": value / rc[f"batch{BATCH}_fp32"]["slices_per_s"],
-                    "bf16_vs_ref_bf16_autocast": value / rc[f"batch{BATCH}_bf16_autocast"]["slices_per_s"]}
+                    "bf16_vs_ref_fp32": value / rc[f"batch{B}_fp32"]["slices_per_s"],
+                    "bf16_vs_ref_bf16_autocast": value / rc[f"batch{B}_bf16_autocast"]["slices_per_s"],
+                    "what": f"`value` over the unmodified reference's eager forward at the same batch ({B}) on the same GPU"}
                 ts, rt = line.get("train_step", {}), rc.get(f"train_step_batch{BATCH}_bf16_autocast")
                 if ts.get("value") and rt:
                     line["speedup_vs_reference_cuda"]["train_step_vs_ref_bf16_autocast"] = ts["value"] / rt["slices_per_s"]
@@ -693,9 +702,9 @@ def run_native(args):
         except Exception as e:                                     # noqa: BLE001
             line["reference_cuda"] = {"error": f"{type(e).__name__}: {e}"[:300]}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, cores, n, dt, kind = cpu_forward_rate(args.cpu_budget, BATCH)
+        v, cores, n, dt, kind = cpu_forward_rate(args.cpu_budget, B)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
-                                "sample": f"{n} forwards of batch {BATCH} in {dt:.1f} s, "
+                                "sample": f"{n} forwards of batch {B} in {dt:.1f} s, "
                                           f"{'unmodified reference' if kind == 'reference' else 'oracle port'} (torch CPU fp32), {cores} threads"}
         try:                                                       # batch-1 forward and one train step on the host cores
             ex = cpu_extra_rates()
@@ -747,14 +756,48 @@ def extra_workloads(cw, synth, model, dev, rank, world, barrier, x24, args):
         return ms
 
     out = {}
-    # ---- the same bf16 forward at batch 96 (one forward in flight): the throughput regime the in-flight forwards approach ----
+    # ---- the same bf16 forward at batch 24 (BASELINE configs[2]'s batch; the headline of the earlier rounds): one forward at a
+    #      time = the latency of a batch-24 forward, and 3 in flight ----
     model.compute_dtype = torch.bfloat16
-    x96 = torch.cat([x24 + 0.001 * i for i in range(4)], 0)
-    ms = graph_rate(model, x96, 10)
-    out["forward_batch96"] = {"value": world * x96.shape[0] / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "batch_per_gpu": int(x96.shape[0]),
-                              "what": "same network and kernels, one batch-96 forward at a time (4x the rows per launch): where the latency "
-                                      "chain of a batch-24 forward stops dominating"}
-    del x96
+    ms = graph_rate(model, x24, 20)
+    fb24 = {"value": world * x24.shape[0] / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "batch_per_gpu": int(x24.shape[0]),
+            "what": "same network and kernels, ONE batch-24 forward at a time: every launch is <= 2 waves, the step is a latency chain of ~160 launches"}
+    try:
+        K3 = 3
+        ss = [torch.cuda.Stream() for _ in range(K3)]
+        xs = [x24 + 0.001 * i for i in range(K3)]
+        gs = []
+        with torch.no_grad():
+            for s_, x_ in zip(ss, xs):
+                s_.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(s_):
+                    model(x_)
+                s_.synchronize()
+                g_ = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g_, stream=s_):
+                    model(x_)
+                gs.append(g_)
+        barrier()
+        cur = torch.cuda.current_stream()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 30
+        e0.record(cur)
+        for s_ in ss:
+            s_.wait_event(e0)
+        for i in range(reps):
+            with torch.cuda.stream(ss[i % K3]):
+                gs[i % K3].replay()
+        for s_ in ss:
+            cur.wait_stream(s_)
+        e1.record(cur)
+        barrier()
+        ms3 = max_ms(e0.elapsed_time(e1)) / reps
+        fb24["inflight3"] = {"value": world * x24.shape[0] / (ms3 * 1e-3), "unit": UNIT, "ms_per_step": ms3,
+                             "what": "3 batch-24 forwards in flight (own graph + stream each): the earlier headline configuration"}
+        del gs
+    except Exception as e:                                         # noqa: BLE001 — an extra
+        fb24["inflight3"] = {"error": f"{type(e).__name__}: {e}"[:200]}
+    out["forward_batch24"] = fb24
     # ---- fp32 forward: the exact SIMT path every <= 1e-4 parity claim is made on ----
     model.compute_dtype = torch.float32
     ms = graph_rate(model, x24, 5)
@@ -850,8 +893,8 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="native", choices=["native", "reference", "reference-cuda"])
-    ap.add_argument("--batch", type=int, default=BATCH)
-    ap.add_argument("--inflight", type=int, default=int(os.environ.get("CSWIN_INFLIGHT", "3")),
+    ap.add_argument("--batch", type=int, default=FWD_BATCH, help="slices per forward step (headline: 96; 24 = the latency point)")
+    ap.add_argument("--inflight", type=int, default=int(os.environ.get("CSWIN_INFLIGHT", "2")),
                     help="batch-B forwards in flight (one CUDA graph + stream each); 1 = strictly one after the other")
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU-oracle work for cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")

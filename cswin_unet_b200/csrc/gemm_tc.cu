@@ -49,6 +49,7 @@ struct alignas(64) GemmTcParams {
   __nv_bfloat16* out; int64_t ldo;
   int64_t M; int N; int K1; int K2;
   int BN, stages, nkb, nkb1, act, tmem_cols, vec_ok, bias_vec, w_kn, tma_out;
+  int nt_n, ntiles, acc_stride;          // N tiles per row of tiles; persistent form: total tiles, TMEM columns per accumulator buffer
   const float* ln_stats; int ln_parts; float ln_invC, ln_eps;
   const float* ln_cs; const float* bias_f32; float* stats_out;
   int aux, aux_off;                      // training epilogue: also store the pre-activation (map_aux); staging offset in smem
@@ -63,7 +64,12 @@ __device__ __forceinline__ float2 gelu_grad_pair(uint32_t zz) {
 // kTrain adds the two training-only epilogues (TMA-store fast path only):
 //   aux : out = GELU(z) AND z itself goes to a second tensor (fc1 of the MLP: the backward needs the pre-activation);
 //   act 2: out = acc * GELU'(residual) — the data gradient of fc2 multiplied by GELU'(z) in place of a separate pass.
-template <bool kFold, bool kStats, bool kTrain = false>
+//
+// kPersist: the CTA walks tiles `blockIdx.x + i * gridDim.x` (N tile fastest, so that CTAs running at the same time share A rows
+// in L2).  The operand ring runs on across tiles, the accumulator is double-buffered in TMEM (2 x acc_stride columns) and the
+// epilogue staging no longer aliases the ring: the TMA / MMA warps work on tile i+1 while the epilogue warps drain tile i, and
+// barrier init / TMEM allocation / descriptor prefetch are paid once per CTA.  Used when a launch is more than one wave of CTAs.
+template <bool kFold, bool kStats, bool kTrain = false, bool kPersist = false>
 __global__ void __launch_bounds__(kThreads, CSWIN_GEMM_MINB) linear_tc_kernel(const __grid_constant__ GemmTcParams P) {
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for the 128-byte swizzle; plain pointer arithmetic keeps the shared address space (LDS/STS)
@@ -74,30 +80,37 @@ __global__ void __launch_bounds__(kThreads, CSWIN_GEMM_MINB) linear_tc_kernel(co
   uint8_t* Ws = As + (size_t)S * a_bytes;               // [S][BN][64]
   // epilogue staging (8 warps x 32 rows x 64 B, bf16, swizzled) re-uses the operand ring: it is only touched after
   // bar_acc, i.e. after every TMA load has landed and every MMA has finished reading shared memory
-  uint8_t* Epi = smem;
   const size_t ring = (size_t)S * (a_bytes + w_bytes);
-  float* sBias = reinterpret_cast<float*>(smem + ring);                  // [256] fp32
-  float* sCs = sBias + 256;                                              // [256] folded-LayerNorm column sums
-  float* sStat = sCs + 256;                                              // [128][2] per-row (sum, sum^2) of this tile's output
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sStat + 256);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 1);
+  uint8_t* Epi = kPersist ? smem + ring : smem;                          // persistent form: own 16 KB behind the ring
+  constexpr int kCB = kPersist ? 2 : 1;                                  // column-constant buffers (one per accumulator buffer)
+  float* sBias = reinterpret_cast<float*>(smem + ring + (kPersist ? 8 * 2048 : 0));   // [kCB][256] fp32
+  float* sCs = sBias + kCB * 256;                                        // [kCB][256] folded-LayerNorm column sums
+  float* sStat = sCs + kCB * 256;                                        // [128][2] per-row (sum, sum^2) of this tile's output
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sStat + 256);             // full[8], empty[8], acc_full[2], acc_empty[2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   pdl_trigger();
   if (tid == 0) trace_stamp(P.trace, 0);                                   // kernel entry
-  const int64_t m0 = (int64_t)blockIdx.x * BM;
-  const int n0 = blockIdx.y * BN;
+  const int nt_n = P.nt_n;
+  // first (or only) tile of this CTA
+  int64_t m0 = kPersist ? (int64_t)((int)blockIdx.x / nt_n) * BM : (int64_t)blockIdx.x * BM;
+  int n0 = kPersist ? ((int)blockIdx.x % nt_n) * BN : (int)blockIdx.y * BN;
+  int n_tile = kPersist ? (int)blockIdx.x % nt_n : (int)blockIdx.y;
 
   auto full = [&](int s) { return smem_u32(&bars[s]); };
   auto empty = [&](int s) { return smem_u32(&bars[kMaxStages + s]); };
-  const uint32_t bar_acc = smem_u32(&bars[2 * kMaxStages]);
+  auto acc_full = [&](int b) { return smem_u32(&bars[2 * kMaxStages + b]); };
+  auto acc_empty = [&](int b) { return smem_u32(&bars[2 * kMaxStages + 2 + b]); };
+  const uint32_t bar_acc = acc_full(0);
 
   // One elected thread initialises the barriers and immediately requests the W tiles of the first ring pass: weights do not
   // depend on the previous kernel (PDL) nor on the rest of this CTA's prologue (TMEM allocation, bias loads).
   const int npre = P.nkb < S ? P.nkb : S;
   if (warp == 0 && elect_one()) {
     for (int s = 0; s < S; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
-    mbar_init(bar_acc, 1);
+    mbar_init(acc_full(0), 1);
+    if (kPersist) { mbar_init(acc_full(1), 1); mbar_init(acc_empty(0), 8); mbar_init(acc_empty(1), 8); }
     fence_barrier_init();
     fence_proxy_async();
     tma_prefetch_desc(&P.map_w);
@@ -112,7 +125,7 @@ __global__ void __launch_bounds__(kThreads, CSWIN_GEMM_MINB) linear_tc_kernel(co
   }
   if (warp == 1) { tmem_alloc(smem_u32(tmem_slot), (uint32_t)P.tmem_cols); tmem_relinquish(); }
   float bias_r = 0.f, cs_r = 0.f;                       // per-column constants: loaded now, parked in smem by the epilogue warps
-  if (warp >= 2) {                                      // (the loads stay in flight across the CTA barrier)
+  if (!kPersist && warp >= 2) {                         // (the loads stay in flight across the CTA barrier)
     const int j = tid - 64, n = n0 + j;
     if (j < BN && n < P.N) {
       bias_r = P.bias_f32 != nullptr ? P.bias_f32[n] : P.bias != nullptr ? __bfloat162float(P.bias[n]) : 0.f;
@@ -129,6 +142,24 @@ __global__ void __launch_bounds__(kThreads, CSWIN_GEMM_MINB) linear_tc_kernel(co
   if (warp == 0) {
     if (elect_one()) {                                  // ---- TMA producer (elect.sync keeps the warp-uniform datapath) ----
       int s = 0; uint32_t ph = 1;                       // ring slot and pass parity, advanced without div / mod
+      if (kPersist) {
+        int g = 0;                                      // ring uses so far (W of the first `npre` was requested in the prologue)
+        for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
+          const int tm0 = (tile / nt_n) * BM, tn0 = (tile % nt_n) * BN;
+          for (int kb = 0; kb < P.nkb; ++kb, ++g) {
+            if (g >= npre) {
+              if (g >= S) mbar_wait(empty(s), ph);
+              mbar_expect_tx(full(s), a_bytes + w_bytes);
+              if (!P.w_kn) tma_load_2d(smem_u32(Ws + (size_t)s * w_bytes), &P.map_w, full(s), kb * BK, tn0);
+              else for (int j = 0; j * 64 < BN; ++j)
+                tma_load_2d(smem_u32(Ws + (size_t)s * w_bytes + j * 8192), &P.map_w, full(s), tn0 + 64 * j, kb * BK);
+            }
+            if (kb < P.nkb1) tma_load_2d(smem_u32(As + (size_t)s * a_bytes), &P.map_a, full(s), kb * BK, tm0);
+            else             tma_load_2d(smem_u32(As + (size_t)s * a_bytes), &P.map_a2, full(s), (kb - P.nkb1) * BK, tm0);
+            if (++s == S) { s = 0; ph ^= 1; }
+          }
+        }
+      } else
       for (int kb = 0; kb < P.nkb; ++kb) {
         if (kb >= S) {
           mbar_wait(empty(s), ph);
@@ -148,18 +179,27 @@ __global__ void __launch_bounds__(kThreads, CSWIN_GEMM_MINB) linear_tc_kernel(co
       const uint32_t idesc = make_idesc_bf16(BM, BN, 0, P.w_kn);
       const uint32_t wstep = P.w_kn ? (2048 >> 4) : 2;   // 16 contraction rows: 2 KB (MN-major) or 32 B (K-major) further
       int s = 0; uint32_t ph = 0;
-      for (int kb = 0; kb < P.nkb; ++kb) {
-        mbar_wait(full(s), ph);
-        if (kb == 0) trace_stamp(P.trace, 3);           // first operands landed
-        tc_fence_after();
-        const uint64_t ad = make_smem_desc(smem_u32(As + (size_t)s * a_bytes), 16, 1024, kLayoutSw128);
-        const uint64_t wd = make_smem_desc(smem_u32(Ws + (size_t)s * w_bytes), P.w_kn ? 8192 : 16, 1024, kLayoutSw128);
+      int it = 0;
+      for (int tile = kPersist ? (int)blockIdx.x : 0; tile < (kPersist ? P.ntiles : 1); tile += kPersist ? (int)gridDim.x : 1, ++it) {
+        const int buf = it & 1;
+        if (kPersist && it >= 2) {                      // the epilogue warps have drained this buffer's previous tile
+          mbar_wait(acc_empty(buf), (uint32_t)(((it >> 1) - 1) & 1));
+          tc_fence_after();
+        }
+        const uint32_t d_tmem = tmem_base + (kPersist ? (uint32_t)(buf * P.acc_stride) : 0u);
+        for (int kb = 0; kb < P.nkb; ++kb) {
+          mbar_wait(full(s), ph);
+          if (kb == 0 && it == 0) trace_stamp(P.trace, 3);    // first operands landed
+          tc_fence_after();
+          const uint64_t ad = make_smem_desc(smem_u32(As + (size_t)s * a_bytes), 16, 1024, kLayoutSw128);
+          const uint64_t wd = make_smem_desc(smem_u32(Ws + (size_t)s * w_bytes), P.w_kn ? 8192 : 16, 1024, kLayoutSw128);
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k) mma_ss(tmem_base, ad + 2 * k, wd + (uint64_t)wstep * k, idesc, (kb | k) != 0);
-        tc_commit(empty(s));                            // smem slot reusable once these MMAs have read it
-        if (++s == S) { s = 0; ph ^= 1; }
+          for (int k = 0; k < BK / 16; ++k) mma_ss(d_tmem, ad + 2 * k, wd + (uint64_t)wstep * k, idesc, (kb | k) != 0);
+          tc_commit(empty(s));                          // smem slot reusable once these MMAs have read it
+          if (++s == S) { s = 0; ph ^= 1; }
+        }
+        tc_commit(acc_full(buf));                       // accumulator complete
       }
-      tc_commit(bar_acc);                               // accumulator complete
       trace_stamp(P.trace, 4);                          // all MMAs issued
     }
   } else {
@@ -168,10 +208,32 @@ __global__ void __launch_bounds__(kThreads, CSWIN_GEMM_MINB) linear_tc_kernel(co
     //      swizzled 2 KB staging tile -> row-contiguous read-back so the residual load and the store are coalesced 16 B.
     const int q = warp & 3;
     const int ch = (warp - 2) >> 2;
-    sBias[tid - 64] = bias_r;
-    if (kFold) sCs[tid - 64] = cs_r;
+    if (!kPersist) {
+      sBias[tid - 64] = bias_r;
+      if (kFold) sCs[tid - 64] = cs_r;
+    }
     if (kStats) sStat[tid - 64] = 0.f;
-    asm volatile("bar.sync 1, 256;" ::: "memory");      // the 8 epilogue warps only
+    if (!kPersist) asm volatile("bar.sync 1, 256;" ::: "memory");      // the 8 epilogue warps only
+    uint8_t* stg = Epi + (warp - 2) * 2048;
+    const uint32_t stg_u32 = smem_u32(stg);
+    const int nunits = (BN + 31) >> 5;
+    int it = 0;
+    for (int tile = kPersist ? (int)blockIdx.x : 0; tile < (kPersist ? P.ntiles : 1); tile += kPersist ? (int)gridDim.x : 1, ++it) {
+    const int buf = kPersist ? (it & 1) : 0;
+    if (kPersist) {                                     // this tile's coordinates and column constants
+      n_tile = tile % nt_n; m0 = (int64_t)(tile / nt_n) * BM; n0 = n_tile * BN;
+      const int j = tid - 64, n = n0 + j;
+      float b = 0.f, c = 0.f;
+      if (j < BN && n < P.N) {
+        b = P.bias_f32 != nullptr ? P.bias_f32[n] : P.bias != nullptr ? __bfloat162float(P.bias[n]) : 0.f;
+        if (kFold) c = P.ln_cs[n];
+      }
+      sBias[buf * 256 + j] = b;
+      if (kFold) sCs[buf * 256 + j] = c;
+      asm volatile("bar.sync 1, 256;" ::: "memory");    // also orders the previous tile's statistics hand-off
+    }
+    const float* sB = sBias + buf * 256;
+    const float* sC = sCs + buf * 256;
     if (P.res != nullptr && P.vec_ok) {                 // pull this thread's residual segments towards L1 while the MMAs run
       for (int u = ch; u < ((BN + 31) >> 5); u += 2) {
         const int n = n0 + u * 32 + (lane & 3) * 8;
@@ -182,8 +244,6 @@ __global__ void __launch_bounds__(kThreads, CSWIN_GEMM_MINB) linear_tc_kernel(co
         }
       }
     }
-    uint8_t* stg = Epi + (warp - 2) * 2048;
-    const uint32_t stg_u32 = smem_u32(stg);
     const int64_t mrow = m0 + q * 32 + lane;            // accumulator row held by this thread in phase 1
     const float sc = (P.sscale != nullptr && mrow < P.M) ? P.sscale[mrow / P.rps] : 1.0f;
     float ln_mean = 0.f, ln_rstd = 1.f;                 // folded LayerNorm: row statistics from the producer's partial sums
@@ -193,11 +253,10 @@ __global__ void __launch_bounds__(kThreads, CSWIN_GEMM_MINB) linear_tc_kernel(co
       ln_mean = s1 * P.ln_invC;
       ln_rstd = rsqrtf(fmaxf(fmaf(-ln_mean, ln_mean, s2 * P.ln_invC), 0.f) + P.ln_eps);
     }
-    const int nunits = (BN + 31) >> 5;
-    mbar_wait(bar_acc, 0);
-    if (warp == 2 && lane == 0) trace_stamp(P.trace, 5);  // accumulator ready
+    mbar_wait(acc_full(buf), kPersist ? (uint32_t)((it >> 1) & 1) : 0u);
+    if (warp == 2 && lane == 0 && it == 0) trace_stamp(P.trace, 5);  // accumulator ready
     tc_fence_after();
-    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (kPersist ? (uint32_t)(buf * P.acc_stride) : 0u);
     if (P.tma_out) {
       // ---- fast path (16-byte aligned rows, N % 8 == 0): everything happens in the accumulator layout (thread = row): bias /
       //      GELU / scale -> bf16 -> residual add (packed bf16x2) -> row statistics -> 64B-swizzled staging box -> one TMA
@@ -217,8 +276,13 @@ __global__ void __launch_bounds__(kThreads, CSWIN_GEMM_MINB) linear_tc_kernel(co
         }
         tmem_wait_ld();
         PSTAMP(9);
-        const float4* b4 = reinterpret_cast<const float4*>(sBias + u * 32);
-        const float4* c4 = reinterpret_cast<const float4*>(sCs + u * 32);
+        if (kPersist && u + 2 >= nunits) {                // last unit of this warp: the accumulator buffer is free for tile i + 2
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(acc_empty(buf));
+        }
+        const float4* b4 = reinterpret_cast<const float4*>(sB + u * 32);
+        const float4* c4 = reinterpret_cast<const float4*>(sC + u * 32);
         if (u != ch) {                                    // the previous unit's TMA store must have finished reading the staging box
           if (lane == 0) tma_store_wait_read();
           __syncwarp();
@@ -288,6 +352,7 @@ __global__ void __launch_bounds__(kThreads, CSWIN_GEMM_MINB) linear_tc_kernel(co
       }
       if (lane == 0) tma_store_wait_read();               // shared memory may be released / re-used after this
       __syncwarp();
+      if (kPersist && ch >= nunits && lane == 0) mbar_arrive(acc_empty(buf));   // BN <= 32: this warp had no unit, it still signs off
     } else
     for (int u = ch; u < nunits; u += 2) {
       uint32_t v[32];
@@ -295,8 +360,8 @@ __global__ void __launch_bounds__(kThreads, CSWIN_GEMM_MINB) linear_tc_kernel(co
       tmem_ld32(trow + u * 32, v);
       tmem_wait_ld();
       PSTAMP(9);
-      const float4* b4 = reinterpret_cast<const float4*>(sBias + u * 32);
-      const float4* c4 = reinterpret_cast<const float4*>(sCs + u * 32);
+      const float4* b4 = reinterpret_cast<const float4*>(sB + u * 32);
+      const float4* c4 = reinterpret_cast<const float4*>(sC + u * 32);
 #pragma unroll
       for (int c = 0; c < 4; ++c) {                     // four 16-byte chunks of 8 columns
         float f[8];
@@ -397,11 +462,15 @@ __global__ void __launch_bounds__(kThreads, CSWIN_GEMM_MINB) linear_tc_kernel(co
     if (kStats) {
       asm volatile("bar.sync 1, 256;" ::: "memory");      // all 8 epilogue warps have accumulated their units
       const int r = tid - 64;
-      if (r < BM && m0 + r < P.M) {
-        float* dst = P.stats_out + ((m0 + r) * gridDim.y + blockIdx.y) * 2;
-        dst[0] = sStat[r * 2]; dst[1] = sStat[r * 2 + 1];
+      if (r < BM) {
+        if (m0 + r < P.M) {
+          float* dst = P.stats_out + ((m0 + r) * nt_n + n_tile) * 2;
+          dst[0] = sStat[r * 2]; dst[1] = sStat[r * 2 + 1];
+        }
+        if (kPersist) { sStat[r * 2] = 0.f; sStat[r * 2 + 1] = 0.f; }   // visible to the others through the next tile's barrier
       }
     }
+    }   // tile loop
     if (warp == 2 && lane == 0) trace_stamp(P.trace, 6);  // epilogue done
   }
   tc_fence_before();
@@ -419,7 +488,13 @@ size_t smem_bytes(int bn, int stages) {
 }
 int tmem_cols_for(int bn) { return bn <= 64 ? 64 : bn <= 128 ? 128 : 256; }      // the epilogue reads whole 64-col groups
 
-struct TileCfg { int bn, stages; };
+size_t smem_bytes_persist(int bn, int stages) {                                   // + own staging, second column-constant buffer
+  return smem_bytes(bn, stages) + 8 * 2048 + 2 * 1024;
+}
+// CSWIN_GEMM_PERSIST=0 switches the persistent form off (A/B runs); =2 forces it wherever it is legal
+int persist_mode() { static const int v = [] { const char* e = getenv("CSWIN_GEMM_PERSIST"); return e ? atoi(e) : 1; }(); return v; }
+
+struct TileCfg { int bn, stages; int persist, grid; };
 
 // Tile-shape choice.  At cswin_tiny sizes a Linear is a handful of waves at most, so the launch is latency- not
 // throughput-bound: the model below (constants fitted to L2-warm CUDA-event timings on B200, microseconds) trades the
@@ -434,8 +509,9 @@ TileCfg pick_tile(int64_t M, int N, int nkb, int act, int sms, bool w_kn) {
   const int n16 = w_kn ? ((N + 63) & ~63) : ((N + 15) & ~15);      // (K,N) weights are fetched in 64-column boxes
   const int64_t mt = (M + BM - 1) / BM;
   const int cands[] = {64, 96, 128, 192, 256};
-  TileCfg best{n16 < 64 ? n16 : 64, 1};
+  TileCfg best{n16 < 64 ? n16 : 64, 1, 0, 0};
   double best_t = 1e30;
+  int64_t best_waves = 1;
   for (int bn : cands) {
     if (forced >= 16 && forced <= 256 && forced % 16 == 0) bn = forced;
     if (w_kn && bn % 64) continue;
@@ -453,8 +529,29 @@ TileCfg pick_tile(int64_t M, int N, int nkb, int act, int sms, bool w_kn) {
            (smem_cap == 0 || smem_bytes(bn, st + 1) <= smem_cap)) ++st;
     const double t_tile = 2.0 + nkb * (0.10 + 0.7 / st) + (bn / 64.0) * (act ? 3.5 : 1.6);
     const double t = waves * t_tile;
-    if (t < best_t - 1e-9) { best_t = t; best = TileCfg{bn, st}; }
+    if (t < best_t - 1e-9) { best_t = t; best = TileCfg{bn, st, 0, 0}; best_waves = waves; }
     if (forced) break;
+  }
+  // More than one wave of CTAs: persistent form, 2 CTAs per SM, each with a double-buffered accumulator (2 x <= 128 columns of
+  // TMEM, so 4 x 128 per SM) and as deep an operand ring as fits next to the second CTA.
+  // Measured on B200 (tools/check_persist.py): wins where the epilogue is light and the tile shape is kept (N <= 128 or a deep K
+  // loop: 301056x64x64 40 -> 29 us, 301056x16x64 23 -> 13, 75264x128x512 28 -> 24); loses where BN would have to shrink from
+  // 192 / 256 (more tiles re-reading A) and for the GELU epilogues, which are instruction-issue bound either way — those keep
+  // the one-tile form.
+  const int pm = persist_mode();
+  if (pm == 2 || (pm != 0 && best_waves > 1 && best.bn <= 128 && act == 0)) {
+    int bn = best.bn > 128 ? 128 : best.bn;
+    if (best.bn > 128 && N % 128 != 0) bn = (N % 96 == 0 && !w_kn) ? 96 : 64;
+    if (!(w_kn && bn % 64)) {
+      const size_t lim = smem_cap != 0 && smem_cap < 112 * 1024 ? smem_cap : 112 * 1024;
+      int st = 1;
+      while (st < kMaxStages && st < 2 * nkb && smem_bytes_persist(bn, st + 1) <= lim) ++st;
+      const int64_t tiles = mt * ((N + bn - 1) / bn);
+      if (smem_bytes_persist(bn, st) <= 113 * 1024 && tiles <= 0x7fffffff) {
+        const int64_t slots = (int64_t)sms * 2;
+        best = TileCfg{bn, st, 1, (int)(tiles < slots ? tiles : slots)};
+      }
+    }
   }
   return best;
 }
@@ -489,6 +586,9 @@ int linear_fwd_tc(const cswin_linear_args_t* a, cudaStream_t stream, bool* handl
   P.BN = cfg.bn;
   P.stages = cfg.stages;
   P.tmem_cols = tmem_cols_for(P.BN);
+  P.nt_n = (a->N + P.BN - 1) / P.BN;
+  P.ntiles = (int)(((a->M + BM - 1) / BM) * P.nt_n);
+  P.acc_stride = P.tmem_cols;
   P.bias_vec = a->bias != nullptr && aligned16(a->bias);
   P.ln_stats = a->ln_stats; P.ln_parts = a->ln_stats_parts; P.ln_invC = a->ln_C > 0 ? 1.0f / (float)a->ln_C : 0.f;
   P.ln_eps = a->ln_eps; P.ln_cs = a->ln_colsum; P.bias_f32 = a->bias_f32; P.stats_out = a->stats_out;
@@ -543,15 +643,24 @@ int linear_fwd_tc(const cswin_linear_args_t* a, cudaStream_t stream, bool* handl
     }
   }
   using Kern = void (*)(const GemmTcParams);
-  static const Kern kerns[5] = {linear_tc_kernel<false, false>, linear_tc_kernel<true, false>, linear_tc_kernel<false, true>,
-                                linear_tc_kernel<true, true>, linear_tc_kernel<false, false, true>};
+  static const Kern kerns[9] = {linear_tc_kernel<false, false>, linear_tc_kernel<true, false>, linear_tc_kernel<false, true>,
+                                linear_tc_kernel<true, true>, linear_tc_kernel<false, false, true>,
+                                linear_tc_kernel<false, false, false, true>, linear_tc_kernel<true, false, false, true>,
+                                linear_tc_kernel<false, true, false, true>, linear_tc_kernel<true, true, false, true>};
   static std::atomic<int> configured{0};
   if (!configured.load(std::memory_order_acquire)) {
     for (Kern k : kerns) CSWIN_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured.store(1, std::memory_order_release);
   }
   dim3 grid((unsigned)((a->M + BM - 1) / BM), (unsigned)((a->N + P.BN - 1) / P.BN));
-  const Kern kern = train ? kerns[4] : kerns[(a->ln_stats != nullptr ? 1 : 0) | (a->stats_out != nullptr ? 2 : 0)];
+  const int variant = (a->ln_stats != nullptr ? 1 : 0) | (a->stats_out != nullptr ? 2 : 0);
+  Kern kern = train ? kerns[4] : kerns[variant];
+  if (cfg.persist && !train && P.tma_out) {             // persistent form: 1-D grid of resident CTAs, two accumulator buffers
+    kern = kerns[5 + variant];
+    grid = dim3((unsigned)cfg.grid);
+    P.tmem_cols = 2 * P.acc_stride;
+    smem = smem_bytes_persist(P.BN, P.stages);
+  }
   CSWIN_CUDA_OK(launch_pdl(kern, grid, dim3(kThreads), smem, stream, P));
   CSWIN_LAUNCH_CHECK();
   g_tc_launches.fetch_add(1, std::memory_order_relaxed);

@@ -50,12 +50,17 @@ class SliceEngine:
         shape = (batch, in_chans, self.size, self.size)
         self.slots = []
         with torch.cuda.device(self.device), torch.no_grad():
-            for i in range(max(2, self.inflight)):                   # >= 2 slots: copies of one batch overlap the forward of another
+            # slots = forwards in flight + one batch in its host->device copy + one being drained / collected by the host: with
+            # only `inflight` slots the copy-in of batch k+ns starts after batch k has left the device, and one of the compute
+            # streams idles for a copy time per step (batch 96: 25.2k -> see profiles/r02_bench_*.json)
+            n_slots = 2 if self.inflight == 1 else self.inflight + 2
+            compute = [self.streams["compute"]] + [torch.cuda.Stream(self.device) for _ in range(self.inflight - 1)]
+            for i in range(n_slots):
                 x = torch.zeros(shape, dtype=torch.float32, device=self.device)
                 slot = {"x": x, "host_out": torch.empty((batch, self.size, self.size), dtype=torch.uint8).pin_memory(),
                         "ev_in": torch.cuda.Event(), "ev_done": torch.cuda.Event(), "ev_out": torch.cuda.Event(),
                         "ev_free": torch.cuda.Event(),
-                        "stream": self.streams["compute"] if (i == 0 or self.inflight == 1) else torch.cuda.Stream(self.device)}
+                        "stream": compute[i % self.inflight]}        # exactly `inflight` forwards run concurrently
                 self.slots.append(slot)
         self._n = 0
         self._resample_bufs = {}                                 # (H, W) -> device / pinned buffers of predict_volume(resample='gpu')
@@ -74,7 +79,9 @@ class SliceEngine:
         # CTAs of concurrent launches must fit next to each other on an SM: cap the tcgen05 Linear's operand ring while capturing
         # (process-wide option read when a launch is enqueued, i.e. baked into the graphs); restored afterwards
         from . import _lib
-        _lib.set_option(_lib.OPT_GEMM_SMEM_CAP_KB, int(os.environ.get("CSWIN_INFLIGHT_SMEM_CAP_KB", "100")) if self.inflight > 1 else 0)
+        # (batch <= 32 only: there every launch is <= 2 waves; at batch 96 the cap costs 4 %, measured)
+        cap_default = "100" if self.batch <= 32 else "0"
+        _lib.set_option(_lib.OPT_GEMM_SMEM_CAP_KB, int(os.environ.get("CSWIN_INFLIGHT_SMEM_CAP_KB", cap_default)) if self.inflight > 1 else 0)
         try:
             self._capture_graphs()
         finally:
@@ -94,6 +101,9 @@ class SliceEngine:
                 with torch.cuda.graph(g, stream=cs):
                     slot["y"] = self.model.predict_labels(slot["x"])
                 slot["graph"] = g
+                with torch.cuda.stream(cs):                      # first replay uploads the graph (several ms for ~160 nodes): pay it here,
+                    g.replay()                                   # not inside the first timed / user-visible batch of every slot
+                cs.synchronize()
 
     def refresh_if_stale(self) -> bool:
         """Re-capture when the model's weights changed since the graphs were built (train -> validate loops of the reference:

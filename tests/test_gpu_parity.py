@@ -195,6 +195,44 @@ def test_linear_fused(dtype, tol, M, N, K1, K2, ln, act, res, drop):
     assert y.shape == (M, N) and err <= tol, f"max-abs {err:.3e}"
 
 
+PERSIST_CASES = [
+    # M, N, K1, K2, act, res, stats : more than one wave of 128-row tiles -> the persistent form of linear_tc_kernel (gemm_tc.cu,
+    # kPersist: tiles walked by resident CTAs, accumulator double-buffered in TMEM, operand ring running across tiles)
+    (38457, 64, 64, 0, 0, True, True),
+    (38457, 16, 64, 0, 0, False, False),       # BN = 16: half of the epilogue warps own no column unit
+    (38457, 96, 152, 0, 0, False, False),      # ragged K (TMA zero fill), BN = 96
+    (38457, 128, 512, 0, 0, True, True),       # deep K loop, residual + row statistics
+    (38457, 128, 128, 128, 0, False, False),   # two-source K loop (decoder concat Linear)
+    (38457, 72, 64, 0, 0, True, False),        # ragged N
+]
+
+
+@pytest.mark.parametrize("M,N,K1,K2,act,res,stats", PERSIST_CASES)
+def test_linear_persistent_form_multiwave(M, N, K1, K2, act, res, stats):
+    g = torch.Generator().manual_seed(M + N + K1 + K2)
+    a = torch.randn(M, K1, generator=g).bfloat16()
+    a2 = torch.randn(M, K2, generator=g).bfloat16() if K2 else None
+    w = (torch.randn(N, K1 + K2, generator=g) / (K1 + K2) ** 0.5).bfloat16()
+    bias = (0.1 * torch.randn(N, generator=g)).bfloat16()
+    r = torch.randn(M, N, generator=g).bfloat16() if res else None
+    n0 = cw.tc_launch_count()
+    out = ops.linear(a.to(DEV), w.to(DEV), bias.to(DEV), a2=None if a2 is None else a2.to(DEV), act=act,
+                     residual=None if r is None else r.to(DEV), want_stats=stats)
+    assert cw.tc_launch_count() == n0 + 1                  # the tcgen05 kernel, not the SIMT fallback
+    y, st = out if stats else (out, None)
+    A = a.double() if a2 is None else torch.cat([a.double(), a2.double()], -1)
+    ref = A @ w.double().T + bias.double()
+    if res:
+        ref = ref + r.double()
+    yd = y.float().cpu().double()
+    err = (yd - ref).abs().max().item()
+    assert y.shape == (M, N) and err <= 4e-2, f"max-abs {err:.3e}"
+    if stats:                                              # side channel == row sums of the bf16 values actually stored
+        s2 = st.cpu().double().sum(1)
+        assert (s2[:, 0] - yd.sum(1)).abs().max().item() <= 2e-3
+        assert ((s2[:, 1] - (yd * yd).sum(1)).abs() / (yd * yd).sum(1)).max().item() <= 1e-5
+
+
 # ---------------------------------------------------------------------------------------------------
 # block / merge / carafe vs golden
 # ---------------------------------------------------------------------------------------------------
@@ -419,7 +457,8 @@ def test_engine_concurrent_forwards_equal_sequential(inflight):
     batches = [torch.rand(3 if i != 6 else 2, 3, 224, 224, generator=g) for i in range(7)]
     seq = list(cw.SliceEngine(m, batch=3, compute_dtype=torch.bfloat16, inflight=1).predict_stream(iter(batches)))
     eng = cw.SliceEngine(m, batch=3, compute_dtype=torch.bfloat16, inflight=inflight)
-    assert len(eng.slots) == max(2, inflight) and len({s["stream"].cuda_stream for s in eng.slots}) == inflight
+    # slots = forwards in flight + one batch copying in + one draining; exactly `inflight` compute streams
+    assert len(eng.slots) == (2 if inflight == 1 else inflight + 2) and len({s["stream"].cuda_stream for s in eng.slots}) == inflight
     for _ in range(2):
         con = list(eng.predict_stream(iter(batches)))
         assert len(con) == len(seq) and all(torch.equal(a, b) for a, b in zip(con, seq))
