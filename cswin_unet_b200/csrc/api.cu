@@ -184,6 +184,21 @@ int cswin_im2col_tokens(const void* x, int64_t x_bs, int64_t x_ts, void* col, in
   return im2col_tokens(x, x_bs, x_ts, col, ldcol, B, H, W, C, KH, KW, stride, pad, dtype, (cudaStream_t)stream);
 }
 
+int cswin_conv_tokens_fwd(const void* x, int64_t x_bs, int64_t x_ts, const void* w, int64_t ldw, const void* bias, void* out,
+                          int64_t ldo, int32_t B, int32_t H, int32_t W, int32_t C, int32_t N, int32_t KH, int32_t KW, int32_t stride,
+                          int32_t pad, int32_t dtype, cswin_stream_t stream, int32_t* handled) {
+  CSWIN_REQUIRE(handled != nullptr, CSWIN_ERR_INVALID, "conv_tokens_fwd: null handled");
+  *handled = 0;
+  CSWIN_REQUIRE(dtype == CSWIN_BF16, CSWIN_ERR_UNSUPPORTED, "conv_tokens_fwd: exists on the bf16 / tcgen05 path only");
+  CSWIN_REQUIRE(x && w && out && B >= 0 && H > 0 && W > 0 && C > 0 && N > 0 && KH > 0 && KW > 0 && stride > 0 && pad >= 0 &&
+                ldw >= (int64_t)KH * KW * C && ldo >= N, CSWIN_ERR_INVALID, "conv_tokens_fwd: bad arguments");
+  if (B == 0) { *handled = 1; return CSWIN_OK; }
+  bool h = false;
+  const int rc = conv_tokens_fwd_tc(x, x_bs, x_ts, w, ldw, bias, out, ldo, B, H, W, C, N, KH, KW, stride, pad, (cudaStream_t)stream, &h);
+  *handled = h ? 1 : 0;
+  return rc;
+}
+
 int cswin_im2col_nchw(const void* x, int32_t x_is_f32, void* col, int64_t ldcol, int32_t B, int32_t C, int32_t H,
                       int32_t W, int32_t KH, int32_t KW, int32_t stride, int32_t pad, int32_t dtype,
                       cswin_stream_t stream) {

@@ -122,6 +122,8 @@ int stem_fwd_tc(const void* x, int x_is_f32, const void* w_packed, const float* 
                 void* out, float* stats, int B, int H, int W, cudaStream_t stream, bool* handled);
 int linear_fwd_simt(const cswin_linear_args_t* a, int dtype, cudaStream_t s);
 int linear_fwd_tc(const cswin_linear_args_t* a, cudaStream_t s, bool* handled);
+int conv_tokens_fwd_tc(const void* x, int64_t x_bs, int64_t x_ts, const void* w, int64_t ldw, const void* bias, void* out, int64_t ldo,
+                       int B, int H, int W, int C, int N, int KH, int KW, int stride, int pad, cudaStream_t stream, bool* handled);
 int im2col_tokens(const void* x, int64_t x_bs, int64_t x_ts, void* col, int64_t ldcol, int B, int H, int W, int C, int KH,
                   int KW, int stride, int pad, int dtype, cudaStream_t s);
 int im2col_nchw(const void* x, int x_is_f32, void* col, int64_t ldcol, int B, int C, int H, int W, int KH, int KW,

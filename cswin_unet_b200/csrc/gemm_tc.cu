@@ -50,6 +50,10 @@ struct alignas(64) GemmTcParams {
   int64_t M; int N; int K1; int K2;
   int BN, stages, nkb, nkb1, act, tmem_cols, vec_ok, bias_vec, w_kn, tma_out;
   int nt_n, ntiles, acc_stride;          // N tiles per row of tiles; persistent form: total tiles, TMEM columns per accumulator buffer
+  // implicit-GEMM convolution over a (B, H, W, C) token image (cswin_conv_tokens_fwd): map_a is the 4-D image map with element
+  // strides (1, stride, stride, 1); an M tile = cv_rows output pixels = cv_bh full output rows of one image (cv_nb = 1) or cv_nb
+  // whole images; K block kb = 64 channels of tap kb / cv_cblk
+  int conv, cv_rows, cv_tpi, cv_nb, cv_bh, cv_stride, cv_pad, cv_KW, cv_cblk;
   const float* ln_stats; int ln_parts; float ln_invC, ln_eps;
   const float* ln_cs; const float* bias_f32; float* stats_out;
   int aux, aux_off;                      // training epilogue: also store the pre-activation (map_aux); staging offset in smem
@@ -94,7 +98,8 @@ __global__ void __launch_bounds__(kThreads, CSWIN_GEMM_MINB) linear_tc_kernel(co
   if (tid == 0) trace_stamp(P.trace, 0);                                   // kernel entry
   const int nt_n = P.nt_n;
   // first (or only) tile of this CTA
-  int64_t m0 = kPersist ? (int64_t)((int)blockIdx.x / nt_n) * BM : (int64_t)blockIdx.x * BM;
+  int64_t m0 = kPersist ? (int64_t)((int)blockIdx.x / nt_n) * BM : (int64_t)blockIdx.x * (P.conv ? P.cv_rows : BM);
+  const uint32_t a_tx = P.conv ? (uint32_t)P.cv_rows * 128u : a_bytes;      // bytes one A box delivers
   int n0 = kPersist ? ((int)blockIdx.x % nt_n) * BN : (int)blockIdx.y * BN;
   int n_tile = kPersist ? (int)blockIdx.x % nt_n : (int)blockIdx.y;
 
@@ -115,7 +120,7 @@ __global__ void __launch_bounds__(kThreads, CSWIN_GEMM_MINB) linear_tc_kernel(co
     fence_proxy_async();
     tma_prefetch_desc(&P.map_w);
     for (int kb = 0; kb < npre; ++kb) {
-      mbar_expect_tx(full(kb), a_bytes + w_bytes);
+      mbar_expect_tx(full(kb), a_tx + w_bytes);
       if (!P.w_kn) tma_load_2d(smem_u32(Ws + (size_t)kb * w_bytes), &P.map_w, full(kb), kb * BK, n0);
       else for (int j = 0; j * 64 < BN; ++j)             // (K, N) weight: [64 k][64 n] boxes = MN-major B blocks
         tma_load_2d(smem_u32(Ws + (size_t)kb * w_bytes + j * 8192), &P.map_w, full(kb), n0 + 64 * j, kb * BK);
@@ -160,17 +165,27 @@ __global__ void __launch_bounds__(kThreads, CSWIN_GEMM_MINB) linear_tc_kernel(co
           }
         }
       } else
+      {
+      // implicit conv: image / first output row of this tile
+      const int cb0 = !P.conv ? 0 : P.cv_nb > 1 ? (int)blockIdx.x * P.cv_nb : (int)blockIdx.x / P.cv_tpi;
+      const int cy0 = !P.conv || P.cv_nb > 1 ? 0 : ((int)blockIdx.x % P.cv_tpi) * P.cv_bh * P.cv_stride - P.cv_pad;
       for (int kb = 0; kb < P.nkb; ++kb) {
         if (kb >= S) {
           mbar_wait(empty(s), ph);
-          mbar_expect_tx(full(s), a_bytes + w_bytes);
+          mbar_expect_tx(full(s), a_tx + w_bytes);
           if (!P.w_kn) tma_load_2d(smem_u32(Ws + (size_t)s * w_bytes), &P.map_w, full(s), kb * BK, n0);
           else for (int j = 0; j * 64 < BN; ++j)
             tma_load_2d(smem_u32(Ws + (size_t)s * w_bytes + j * 8192), &P.map_w, full(s), n0 + 64 * j, kb * BK);
         }
-        if (kb < P.nkb1) tma_load_2d(smem_u32(As + (size_t)s * a_bytes), &P.map_a, full(s), kb * BK, (int)m0);
-        else             tma_load_2d(smem_u32(As + (size_t)s * a_bytes), &P.map_a2, full(s), (kb - P.nkb1) * BK, (int)m0);
+        if (P.conv) {                                    // tap (ky, kx), 64 channels: a strided box of the token image, zero padding = TMA OOB fill
+          const int tap = kb / P.cv_cblk, c0 = (kb - tap * P.cv_cblk) * BK;
+          const int ky = tap / P.cv_KW, kx = tap - ky * P.cv_KW;
+          tma_load_4d(smem_u32(As + (size_t)s * a_bytes), &P.map_a, full(s), c0, kx - P.cv_pad, cy0 + (P.cv_nb > 1 ? ky - P.cv_pad : ky), cb0);
+        }
+        else if (kb < P.nkb1) tma_load_2d(smem_u32(As + (size_t)s * a_bytes), &P.map_a, full(s), kb * BK, (int)m0);
+        else                  tma_load_2d(smem_u32(As + (size_t)s * a_bytes), &P.map_a2, full(s), (kb - P.nkb1) * BK, (int)m0);
         if (++s == S) { s = 0; ph ^= 1; }
+      }
       }
       trace_stamp(P.trace, 2);                          // all TMA issued
     }
@@ -217,6 +232,7 @@ __global__ void __launch_bounds__(kThreads, CSWIN_GEMM_MINB) linear_tc_kernel(co
     uint8_t* stg = Epi + (warp - 2) * 2048;
     const uint32_t stg_u32 = smem_u32(stg);
     const int nunits = (BN + 31) >> 5;
+    const int rows_valid = P.conv ? P.cv_rows : BM;     // implicit conv: an M tile may hold fewer than 128 output pixels
     int it = 0;
     for (int tile = kPersist ? (int)blockIdx.x : 0; tile < (kPersist ? P.ntiles : 1); tile += kPersist ? (int)gridDim.x : 1, ++it) {
     const int buf = kPersist ? (it & 1) : 0;
@@ -423,7 +439,7 @@ __global__ void __launch_bounds__(kThreads, CSWIN_GEMM_MINB) linear_tc_kernel(co
         if (pass == 0 && P.res != nullptr) { PSTAMP(12 + (int)((rv[0].x & 1) & 0)); }
         uint4 x = w[pass];
         float st1 = 0.f, st2 = 0.f;
-        if (m < P.M && col_ok) {
+        if (m < P.M && col_ok && q * 32 + r < rows_valid) {
           __nv_bfloat16* dst = P.out + m * P.ldo + n;
           if (vec) {
             if (P.res != nullptr) {
@@ -463,7 +479,7 @@ __global__ void __launch_bounds__(kThreads, CSWIN_GEMM_MINB) linear_tc_kernel(co
       asm volatile("bar.sync 1, 256;" ::: "memory");      // all 8 epilogue warps have accumulated their units
       const int r = tid - 64;
       if (r < BM) {
-        if (m0 + r < P.M) {
+        if (m0 + r < P.M && r < rows_valid) {
           float* dst = P.stats_out + ((m0 + r) * nt_n + n_tile) * 2;
           dst[0] = sStat[r * 2]; dst[1] = sStat[r * 2 + 1];
         }
@@ -563,7 +579,27 @@ int linear_tc_stats_parts(int64_t M, int N, int K, int act) {
   return (N + cfg.bn - 1) / cfg.bn;
 }
 
-int linear_fwd_tc(const cswin_linear_args_t* a, cudaStream_t stream, bool* handled) {
+// geometry of an implicit-GEMM convolution over a (B, H, W, C) token image (cswin_conv_tokens_fwd); a->a = image base, a->lda = token stride
+struct ConvGeom { int B, H, W, C, KH, KW, stride, pad, OH, OW; int64_t x_bs; };
+
+static int linear_fwd_tc_impl(const cswin_linear_args_t* a, const ConvGeom* cv, cudaStream_t stream, bool* handled);
+
+int linear_fwd_tc(const cswin_linear_args_t* a, cudaStream_t stream, bool* handled) { return linear_fwd_tc_impl(a, nullptr, stream, handled); }
+
+// out (B OH OW, N) = conv(x (B, H W, C) token image, w (N, KH KW C) in (ky, kx, c) order) + bias: the Linear kernel with its A operand
+// fetched as strided 4-D TMA boxes of the image (no column matrix).  *handled = false when the shape is outside the envelope.
+int conv_tokens_fwd_tc(const void* x, int64_t x_bs, int64_t x_ts, const void* w, int64_t ldw, const void* bias, void* out, int64_t ldo,
+                       int B, int H, int W, int C, int N, int KH, int KW, int stride, int pad, cudaStream_t stream, bool* handled) {
+  *handled = false;
+  ConvGeom g{B, H, W, C, KH, KW, stride, pad, (H + 2 * pad - KH) / stride + 1, (W + 2 * pad - KW) / stride + 1, x_bs};
+  if (C % BK != 0 || g.OH <= 0 || g.OW <= 0 || g.OW > BM || stride < 1 || stride > 8 || g.OW * stride > 256) return CSWIN_OK;
+  cswin_linear_args_t a = {};
+  a.a = x; a.lda = x_ts; a.K1 = KH * KW * C; a.w = w; a.ldw = ldw; a.bias = bias; a.out = out; a.ldo = ldo;
+  a.M = (int64_t)B * g.OH * g.OW; a.N = N;
+  return linear_fwd_tc_impl(&a, &g, stream, handled);
+}
+
+static int linear_fwd_tc_impl(const cswin_linear_args_t* a, const ConvGeom* cv, cudaStream_t stream, bool* handled) {
   *handled = false;
   if (a->ln_gamma != nullptr) return CSWIN_OK;                               // LayerNorm prologue: SIMT kernel (host calls LN first on the bf16 path)
   const int K = a->K1 + a->K2;
@@ -582,7 +618,21 @@ int linear_fwd_tc(const cswin_linear_args_t* a, cudaStream_t stream, bool* handl
   P.nkb1 = (a->K1 + BK - 1) / BK;
   P.nkb = P.nkb1 + (a->K2 + BK - 1) / BK;
   P.w_kn = a->w_layout;
-  const TileCfg cfg = pick_tile(a->M, a->N, P.nkb, a->act, sm_count(), a->w_layout != 0);
+  TileCfg cfg = pick_tile(a->M, a->N, P.nkb, a->act, sm_count(), a->w_layout != 0);
+  P.conv = 0; P.cv_rows = BM; P.cv_tpi = 1; P.cv_nb = 1; P.cv_bh = 1; P.cv_stride = 1; P.cv_pad = 0; P.cv_KW = 1; P.cv_cblk = 1;
+  if (cv != nullptr) {
+    // M tile = whole images (OH OW nb <= 128) or bh full output rows of one image (bh | OH, bh OW <= 128)
+    int nb = 1, bh = cv->OH;
+    if (cv->OH * cv->OW <= BM) { nb = BM / (cv->OH * cv->OW); if (nb > cv->B) nb = cv->B; if (nb > 256) nb = 256; }
+    else { bh = BM / cv->OW; while (bh > 1 && cv->OH % bh) --bh; }
+    if (bh * cv->stride > 256) return CSWIN_OK;
+    P.conv = 1; P.cv_nb = nb; P.cv_bh = bh; P.cv_rows = nb * bh * cv->OW; P.cv_tpi = cv->OH / bh;
+    P.cv_stride = cv->stride; P.cv_pad = cv->pad; P.cv_KW = cv->KW; P.cv_cblk = cv->C / BK;
+    cfg.persist = 0;
+    // the grid is (M tiles of cv_rows rows) x (N tiles): re-pick BN for the real tile count
+    cfg = pick_tile(((a->M + P.cv_rows - 1) / P.cv_rows) * BM, a->N, P.nkb, a->act, sm_count(), false);
+    cfg.persist = 0;
+  }
   P.BN = cfg.bn;
   P.stages = cfg.stages;
   P.tmem_cols = tmem_cols_for(P.BN);
@@ -595,7 +645,7 @@ int linear_fwd_tc(const cswin_linear_args_t* a, cudaStream_t stream, bool* handl
   P.trace = g_trace.load(std::memory_order_relaxed);
   P.vec_ok = aligned16(a->out) && (a->ldo * 2) % 16 == 0 &&
              (a->residual == nullptr || (aligned16(a->residual) && (a->ldr * 2) % 16 == 0));
-  P.tma_out = P.vec_ok && a->N % 8 == 0 && !no_tma_out();
+  P.tma_out = P.vec_ok && a->N % 8 == 0 && !no_tma_out() && P.cv_rows == BM;     // partial conv tiles: predicated stores
   if (P.tma_out) {
     const uint64_t dims[2] = {(uint64_t)a->N, (uint64_t)a->M}, str[1] = {(uint64_t)a->ldo * 2};
     const uint32_t box[2] = {32, 32};
@@ -603,7 +653,15 @@ int linear_fwd_tc(const cswin_linear_args_t* a, cudaStream_t stream, bool* handl
   }
   if (a->stats_out != nullptr && !P.vec_ok) { set_error("linear_fwd: stats_out needs 16-byte aligned output rows"); return CSWIN_ERR_UNSUPPORTED; }
 
-  {
+  if (cv != nullptr) {          // (channel, x, y, image) view of the token image, traversed with the conv stride along x and y
+    const uint64_t dims[4] = {(uint64_t)cv->C, (uint64_t)cv->W, (uint64_t)cv->H, (uint64_t)cv->B};
+    const uint64_t str[3] = {(uint64_t)a->lda * 2, (uint64_t)a->lda * 2 * cv->W, (uint64_t)cv->x_bs * 2};
+    const uint32_t s = (uint32_t)cv->stride;
+    const uint32_t box[4] = {BK, (uint32_t)cv->OW * s, (uint32_t)P.cv_bh * s, (uint32_t)P.cv_nb};
+    const uint32_t es[4] = {1, s, s, 1};
+    if ((cv->x_bs * 2) % 16) return CSWIN_OK;
+    if (!tc::make_tensor_map_bf16(&P.map_a, a->a, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, es)) return CSWIN_ERR_CUDA;
+  } else {
     const uint64_t dims[2] = {(uint64_t)a->K1, (uint64_t)a->M};
     const uint64_t str[1] = {(uint64_t)a->lda * 2};
     const uint32_t box[2] = {BK, BM};
@@ -652,7 +710,7 @@ int linear_fwd_tc(const cswin_linear_args_t* a, cudaStream_t stream, bool* handl
     for (Kern k : kerns) CSWIN_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured.store(1, std::memory_order_release);
   }
-  dim3 grid((unsigned)((a->M + BM - 1) / BM), (unsigned)((a->N + P.BN - 1) / P.BN));
+  dim3 grid((unsigned)((a->M + P.cv_rows - 1) / P.cv_rows), (unsigned)((a->N + P.BN - 1) / P.BN));
   const int variant = (a->ln_stats != nullptr ? 1 : 0) | (a->stats_out != nullptr ? 2 : 0);
   Kern kern = train ? kerns[4] : kerns[variant];
   if (cfg.persist && !train && P.tma_out) {             // persistent form: 1-D grid of resident CTAs, two accumulator buffers

@@ -21,7 +21,8 @@ EncodeTiledFn encode_tiled_fn();   // nullptr if the driver does not expose cuTe
 
 // bf16 tensor map of rank `rank`; dims / strides innermost first, strides in BYTES for dims 1..rank-1.
 bool make_tensor_map_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
-                          const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swizzle);
+                          const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swizzle,
+                          const uint32_t* elem_strides = nullptr);   // traversal strides (a box of extent e loads ceil(e / stride) elements)
 
 #ifdef __CUDACC__
 // ------------------------------------------------------------------------------------------------

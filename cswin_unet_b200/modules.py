@@ -109,6 +109,9 @@ class DropPath(nn.Module):
 FUSE_MLP = os.environ.get("CSWIN_FUSE_MLP", "1") != "0"
 FUSE_MLP_MAX_DIM = int(os.environ.get("CSWIN_FUSE_MLP_MAX_DIM", "64"))
 FOLD_LN = os.environ.get("CSWIN_FOLD_LN", "1") != "0"     # LayerNorm folded into the tcgen05 Linear epilogue (bf16 inference)
+# Merge_Block / CARAFE.encoder convolutions as implicit GEMMs (cswin_conv_tokens_fwd: strided TMA boxes of the token image, no
+# column matrix) where the channel count allows (C % 64 == 0); CSWIN_IMPLICIT_CONV=0 restores im2col + Linear (A/B switch)
+IMPLICIT_CONV = os.environ.get("CSWIN_IMPLICIT_CONV", "1") != "0"
 # [LN1 -> qkv -> both LePE attention branches] as one kernel (csrc/qkv_attn_tc.cu) where the block shape allows it.  Bit-identical
 # to the composed path, one launch and the (B, L, 3C) qkv round trip fewer per block — and still SLOWER in the forward on B200
 # (17,433 vs 18,984 slices/s, profiles/r02_sweep_streams.log): with 24 images there are only 192 (image, branch, head pair, window)
@@ -552,8 +555,10 @@ class Merge_Block(_Native):
             return y.view(B, ((H + 2 - 3) // 2 + 1) ** 2, -1)
         dt = x.dtype
         wk = self._w("conv.w", self.conv.weight, dt, lambda t: t.permute(0, 2, 3, 1).reshape(t.shape[0], -1))
-        col = ops.im2col_tokens(x, H, W, 3, 3, 2, 1)
-        y = ops.linear(col, wk, self._w("conv.b", self.conv.bias, dt))
+        y = ops.conv_tokens(x, H, W, wk, self._w("conv.b", self.conv.bias, dt), 3, 3, 2, 1) if IMPLICIT_CONV and Cn % 64 == 0 else None
+        if y is None:
+            col = ops.im2col_tokens(x, H, W, 3, 3, 2, 1)
+            y = ops.linear(col, wk, self._w("conv.b", self.conv.bias, dt))
         y = ops.layernorm_with_row_stats(y, self._w("n.w", self.norm.weight, dt), self._w("n.b", self.norm.bias, dt), self.norm.eps)
         Ho = (H + 2 - 3) // 2 + 1
         v = y.view(B, Ho * Ho, -1)
@@ -596,10 +601,12 @@ class CARAFE(_Native):
                            lambda a, b: torch.cat([a.to(dt), torch.zeros(b.shape[0], dtype=dt, device=a.device)]))
             y = ops.linear(x, wcat, bcat)                                               # (B, L, C/4 + Nz): [down(x) | z(x)], no bias on z yet
             d, z = y[..., :nd], y[..., nd:]
-        col = ops.im2col_tokens(d, H, W, 3, 3, 1, 1)
-        enc = ops.linear(col, self._w("enc.w", self.encoder.weight, dt,
-                                      lambda t: t.permute(0, 2, 3, 1).reshape(t.shape[0], -1)),
-                         self._w("enc.b", self.encoder.bias, dt))                       # (B*L, 9 s^2)
+        we = self._w("enc.w", self.encoder.weight, dt, lambda t: t.permute(0, 2, 3, 1).reshape(t.shape[0], -1))
+        be = self._w("enc.b", self.encoder.bias, dt)
+        enc = ops.conv_tokens(d, H, W, we, be, 3, 3, 1, 1) if IMPLICIT_CONV and d.shape[-1] % 64 == 0 else None
+        if enc is None:
+            col = ops.im2col_tokens(d, H, W, 3, 3, 1, 1)
+            enc = ops.linear(col, we, be)                                               # (B*L, 9 s^2)
         return enc if z_weight is None else (enc, z)
 
     def _kernel_logits_tape(self, x: Tensor, H: int, W: int) -> Tensor:

@@ -372,6 +372,24 @@ def stage_forward(x: Tensor, stats_in: Tensor, blocks: Sequence[dict], reso: int
     return x
 
 
+def conv_tokens(x: Tensor, H: int, W: int, w: Tensor, bias: Optional[Tensor], KH: int, KW: int, stride: int, pad: int) -> Optional[Tensor]:
+    """Convolution over the token image x (B, H*W, C) as an implicit GEMM on the tcgen05 Linear (cswin_conv_tokens_fwd): w (N, KH*KW*C)
+    in (ky, kx, c) order.  Returns (B*OH*OW, N) bf16, or None outside the kernel's envelope (the caller composes im2col + linear)."""
+    _need_cuda(x, w, bias)
+    if x.dtype != torch.bfloat16 or x.dim() != 3 or x.stride(2) != 1:
+        return None
+    B, L, Cn = x.shape
+    assert L == H * W and w.dim() == 2 and w.stride(1) == 1 and w.shape[1] == KH * KW * Cn and w.dtype == x.dtype
+    OH, OW = (H + 2 * pad - KH) // stride + 1, (W + 2 * pad - KW) // stride + 1
+    N = w.shape[0]
+    out = torch.empty((B * OH * OW, N), dtype=x.dtype, device=x.device)
+    handled = C.c_int32(0)
+    check(lib().cswin_conv_tokens_fwd(x.data_ptr(), x.stride(0), x.stride(1), w.data_ptr(), w.stride(0), _ptr(bias), out.data_ptr(),
+                                      out.stride(0), B, H, W, Cn, N, KH, KW, stride, pad, BF16, _stream(), C.byref(handled)),
+          "cswin_conv_tokens_fwd")
+    return out if handled.value else None
+
+
 def stem_fused(x: Tensor, w_packed: Tensor, bias: Tensor, gamma: Tensor, beta: Tensor, eps: float) -> Optional[Tensor]:
     """Conv2d(3, 64, 7, 4, 2) + token layout + LayerNorm(64) in one tcgen05 launch (cswin_stem_fwd).  x (B, 3, H, W) fp32 / bf16,
     w_packed (64, 192) bf16, bias / gamma / beta (64) fp32.  Returns (B, Ho Wo, 64) bf16 carrying `_cswin_stats`, or None when the

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define CSWIN_ABI_VERSION 7
+#define CSWIN_ABI_VERSION 8
 
 typedef struct CUstream_st* cswin_stream_t; /* == cudaStream_t */
 
@@ -351,6 +351,20 @@ int cswin_im2col_tokens(const void* x, int64_t x_bs, int64_t x_ts, void* col, in
 int cswin_im2col_nchw(const void* x, int32_t x_is_f32, void* col, int64_t ldcol, int32_t B, int32_t C, int32_t H,
                       int32_t W, int32_t KH, int32_t KW, int32_t stride, int32_t pad, int32_t dtype,
                       cswin_stream_t stream);
+
+/* ---- convolution over a token image as an IMPLICIT GEMM (bf16 / tcgen05 only): no column matrix --------------------------------
+ * replaces the NCHW copy + nn.Conv2d of Merge_Block.conv (networks/cswin_unet.py:214-216: 3x3 stride 2 padding 1) and of
+ * CARAFE.encoder (:240-241: 3x3 stride 1 padding 1) — and cswin_im2col_tokens + cswin_linear_fwd of this library:
+ *   out[(b, oy, ox), n] = bias[n] + sum_{ky, kx, c} x[b, oy*stride + ky - pad, ox*stride + kx - pad, c] * w[n, (ky*KW + kx)*C + c]
+ * The tcgen05 Linear kernel fetches its A operand as strided 4-D TMA boxes (64 channels, OW pixels every `stride`-th, bh rows every
+ * `stride`-th, nb images) of the (B, H, W, C) image, one box per (tap, 64-channel block); padding is the TMA's out-of-bounds zero fill.
+ *   x   : (B, H*W, C) token-major bf16, x_bs / x_ts = image / token strides in elements (16-byte multiples), C % 64 == 0
+ *   w   : (N, KH*KW*C) bf16, row pitch ldw — conv.weight.permute(0, 2, 3, 1) flattened;  bias : (N) bf16 or NULL
+ *   out : (B*OH*OW, N) bf16, row pitch ldo;  OH = (H + 2 pad - KH) / stride + 1
+ * *handled = 0 (nothing launched) outside the envelope (C % 64 != 0, OW > 128, ...): the caller composes im2col + Linear. */
+int cswin_conv_tokens_fwd(const void* x, int64_t x_bs, int64_t x_ts, const void* w, int64_t ldw, const void* bias, void* out,
+                          int64_t ldo, int32_t B, int32_t H, int32_t W, int32_t C, int32_t N, int32_t KH, int32_t KW, int32_t stride,
+                          int32_t pad, int32_t dtype, cswin_stream_t stream, int32_t* handled);
 
 /* ------------------------------------------------------------------------------------------------
  * CARAFE content-aware reassembly.  Replaces cswin_unet.py:242-263 (pixel_shuffle, softmax over the 9 taps,

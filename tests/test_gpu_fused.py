@@ -158,3 +158,59 @@ def test_stem_fused_equals_composed_and_oracle(B, S, in_dtype, monkeypatch):
     print(f"[stem fused B={B} S={S} {in_dtype}] max-abs vs fp64: fused {ef:.3e}, composed {ec:.3e}; fused vs composed {d:.3e}; stats error {es:.2e}")
     assert outs[True][0].shape == ref.shape and torch.isfinite(outs[True][0]).all()
     assert ef <= 1.25 * ec + 2e-3 and d <= 6e-2 and es <= 2e-3
+
+
+# B, H (= W), C, N, stride, view: Merge_Block shapes of the 224^2 and 512^2 configurations (stride 2), CARAFE.encoder shapes
+# (stride 1), M tiles of whole images (7x7 outputs: two images per tile, odd B leaves a ragged tile), of 7 / 4 / 2 output rows,
+# full 128-row tiles (TMA-store epilogue), an input that is a column view of a wider buffer (CARAFE's [down | z] Linear)
+CONV_CASES = [(3, 56, 64, 128, 2, False), (2, 28, 128, 256, 2, False), (5, 14, 256, 512, 2, False), (24, 14, 256, 512, 2, False),
+              (3, 14, 64, 36, 1, True), (5, 7, 128, 36, 1, True), (1, 128, 64, 128, 2, False), (2, 64, 128, 256, 2, False),
+              (2, 32, 256, 512, 2, False), (1, 20, 64, 72, 1, False)]
+
+
+@pytest.mark.parametrize("B,H,C,N,stride,view", CONV_CASES)
+def test_conv_tokens_implicit_gemm_equals_im2col_path_and_fp64(B, H, C, N, stride, view):
+    """cswin_conv_tokens_fwd (gemm_tc.cu, implicit GEMM: the A operand is fetched as strided 4-D TMA boxes of the token image) for
+    Merge_Block.conv (cswin_unet.py:214-216) and CARAFE.encoder (:240-241): bit-identical to cswin_im2col_tokens + cswin_linear_fwd
+    (same MMA order) and within bf16 rounding of torch's fp64 conv2d."""
+    g = torch.Generator().manual_seed(B * 1000 + H * 10 + C + N)
+    xw = torch.randn(B, H * H, C + (64 if view else 0), generator=g).bfloat16().to(DEV)
+    x = xw[..., :C]
+    w4 = (torch.randn(N, C, 3, 3, generator=g) / (9 * C) ** 0.5).bfloat16()
+    bias = (0.1 * torch.randn(N, generator=g)).bfloat16()
+    wk = w4.permute(0, 2, 3, 1).reshape(N, -1).contiguous().to(DEV)
+    n0, t0 = cw.launch_count(), cw.tc_launch_count()
+    y = ops.conv_tokens(x, H, H, wk, bias.to(DEV), 3, 3, stride, 1)
+    assert y is not None and cw.launch_count() == n0 + 1 and cw.tc_launch_count() == t0 + 1      # one tcgen05 launch, no gather
+    col = ops.im2col_tokens(x, H, H, 3, 3, stride, 1)
+    y2 = ops.linear(col, wk, bias.to(DEV))
+    OH = (H + 2 - 3) // stride + 1
+    assert y.shape == y2.shape == (B * OH * OH, N)
+    assert torch.equal(y, y2), (y.float() - y2.float()).abs().max().item()
+    xi = x.float().cpu().double().view(B, H, H, C).permute(0, 3, 1, 2)
+    ref = torch.nn.functional.conv2d(xi, w4.double(), bias.double(), stride=stride, padding=1).permute(0, 2, 3, 1).reshape(B * OH * OH, N)
+    err = (y.float().cpu().double() - ref).abs().max().item()
+    assert err <= 3e-2, err
+
+
+def test_conv_tokens_outside_the_envelope_is_declined_not_faked():
+    x = torch.randn(2, 28 * 28, 32, device=DEV).bfloat16()                      # 32 channels: a 64-wide K block would span two taps
+    wk = torch.randn(36, 9 * 32, device=DEV).bfloat16()
+    n0 = cw.launch_count()
+    assert ops.conv_tokens(x, 28, 28, wk, None, 3, 3, 1, 1) is None and cw.launch_count() == n0
+    assert ops.conv_tokens(x.float(), 28, 28, wk.float(), None, 3, 3, 1, 1) is None  # fp32: the SIMT path composes im2col + Linear
+
+
+def test_merge_block_and_carafe_use_the_implicit_conv(monkeypatch):
+    """Merge_Block / CARAFE forward with the implicit-GEMM conv vs the im2col path: identical outputs, fewer launches."""
+    for mod, reso in ((cw.Merge_Block(64, 128), 56), (cw.Merge_Block(256, 512), 14), (cw.CARAFE(256, 128), 14), (cw.CARAFE(512, 256), 7)):
+        mod = mod.to(DEV).eval()
+        x = torch.randn(3, reso * reso, mod.conv.in_channels if hasattr(mod, "conv") else mod.down.in_channels, device=DEV).bfloat16()
+        res = {}
+        for on in (True, False):
+            monkeypatch.setattr(modules, "IMPLICIT_CONV", on)
+            n0 = cw.launch_count()
+            with torch.no_grad():
+                res[on] = (mod(x), cw.launch_count() - n0)
+        assert res[True][1] == res[False][1] - 1
+        assert torch.equal(res[True][0], res[False][0])
