@@ -40,6 +40,7 @@ struct TcBranch {
   __nv_bfloat16* out; const __nv_bfloat16* cw; const __nv_bfloat16* cb; float* lse;
   int64_t o_bs, o_ts;
   int heads, hs, ws, nww, nwin, N, tile_begin, nprob;
+  uint32_t m_heads, m_nwin, m_nww, m_ws;      // floor(2^32 / d) + 1: x / d == __umulhi(x, m) for the index ranges of this kernel
 };
 struct alignas(64) TcParams {
   CUtensorMap map[2][3];     // [branch][q,k,v]
@@ -61,6 +62,8 @@ constexpr int kSmemBytesWide = 5 * kOperandBytes + 2 * 9 * 32 * 4 + 2 * 32 * 4 +
 __device__ __forceinline__ uint32_t v_chunk_addr(uint32_t vbase, int row, int chunk) {
   return vbase + row * kRowBytes + (((chunk ^ (row >> 1)) & 3) << 4);          // Swizzle<2,4,3> (64-byte swizzle)
 }
+// x / d for d > 1 through the precomputed multiplier (exact while x * d < 2^32); d == 1 passes x through
+__device__ __forceinline__ int fast_div(int x, int d, uint32_t m) { return d == 1 ? x : (int)__umulhi((uint32_t)x, m); }
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -79,8 +82,8 @@ __global__ void __launch_bounds__(kThreads, kWide ? 2 : 3) lepe_attn_fwd_tc_kern
   uint8_t* Qs = smem;
   uint8_t* Ks = smem + kOperandBytes;
   uint8_t* Vs = Ks + kKvBytes;
-  float* Wt = reinterpret_cast<float*>(Vs + kKvBytes);                 // [2][9][32]
-  float* Bc = Wt + 2 * 9 * 32;                                        // [2][32]
+  __nv_bfloat16* Wt = reinterpret_cast<__nv_bfloat16*>(Vs + kKvBytes);  // [2][9][32] bf16 (tap-major copy of the (32, 3, 3) conv weights)
+  float* Bc = reinterpret_cast<float*>(Wt + 2 * 9 * 32 * 2);           // [2][32]   (the region is sized for the former fp32 copy)
   float* Xmax = Bc + 2 * 32;                                          // [2 halves][128 rows]
   float* Xsum = Xmax;                                                 // reused after the max exchange
   uint64_t* bars = reinterpret_cast<uint64_t*>(Xmax + 2 * 128);       // tma, s, o
@@ -96,23 +99,24 @@ __global__ void __launch_bounds__(kThreads, kWide ? 2 : 3) lepe_attn_fwd_tc_kern
   const int tile = blockIdx.x - br.tile_begin;
   const int N = br.N, hs = br.hs, ws = br.ws;
   const int slots = (!kWide && N <= 64) ? 2 : 1;
-  const int slot_rows = kTileRows / slots;
+  const int slot_rows = slots == 2 ? kTileRows / 2 : kTileRows;
   const int qt = kWide ? (tile & 1) : 0;                             // wide: which 128-row query tile of the problem
   const int p0 = kWide ? (tile >> 1) : tile * slots;
   const int np = min(slots, br.nprob - p0);
   const int kext = (slots == 2) ? 128 : ((N + 15) & ~15);            // kv extent fed to the P.V MMA
 
-  const int slot = row / slot_rows;            // warp-uniform
+  const int slot = slots == 2 ? row >> 6 : 0;  // warp-uniform
   const int n = row - slot * slot_rows + qt * kTileRows;             // token index inside the window
 
   // (batch, window, head) of my slot, and of both slots for the TMA-issuing thread
   int mb, mih, miw, mhead;
   {
-    int local = p0 + min(slot, np - 1);
-    mhead = local % br.heads; local /= br.heads;
-    const int win = local % br.nwin;
-    mb = local / br.nwin;
-    mih = win / br.nww; miw = win - mih * br.nww;
+    const int local = p0 + min(slot, np - 1);
+    const int lw = fast_div(local, br.heads, br.m_heads);
+    mhead = local - lw * br.heads;
+    mb = fast_div(lw, br.nwin, br.m_nwin);
+    const int win = lw - mb * br.nwin;
+    mih = fast_div(win, br.nww, br.m_nww); miw = win - mih * br.nww;
   }
 
   const uint32_t bar_tma = smem_u32(&bars[0]), bar_s = smem_u32(&bars[1]), bar_o = smem_u32(&bars[2]);
@@ -122,25 +126,26 @@ __global__ void __launch_bounds__(kThreads, kWide ? 2 : 3) lepe_attn_fwd_tc_kern
   // zero the V rows the P.V MMA reads but TMA does not write (0 * stale-NaN would poison O)
   for (int i = tid; i < kKvRows * 4; i += kThreads) {
     const int r = i >> 2;
-    const int s = kWide ? 0 : r / slot_rows, rn = r - s * slot_rows;
+    const int s = (kWide || slots == 1) ? 0 : r >> 6, rn = r - s * slot_rows;
     if (r < kext && (s >= np || rn >= N)) *reinterpret_cast<uint4*>(Vs + i * 16) = make_uint4(0, 0, 0, 0);
   }
-  // stage the LePE weights of the head(s) of this tile: 288 contiguous bf16 per head -> Wt[slot][tap][ch] fp32
+  // stage the LePE weights of the head(s) of this tile: 288 contiguous bf16 per head -> Wt[slot][tap][ch] (still bf16: FHFMA.BF16)
   if (tid < np * 36) {
-    const int s = tid / 36, i = tid - s * 36;                         // 36 x 16-byte chunks per head
-    int local = p0 + s;
-    const int hd = local % br.heads;
+    const int s = tid >= 36 ? 1 : 0, i = tid - s * 36;                // 36 x 16-byte chunks per head
+    const int local = p0 + s;
+    const int hd = local - fast_div(local, br.heads, br.m_heads) * br.heads;
     const uint4 raw = *reinterpret_cast<const uint4*>(br.cw + (size_t)hd * 288 + i * 8);
     const uint32_t w4[4] = {raw.x, raw.y, raw.z, raw.w};
+    unsigned short* wt16 = reinterpret_cast<unsigned short*>(Wt);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const int idx = i * 8 + e;                                       // = ch * 9 + tap
-      const int ch = idx / 9, t = idx - ch * 9;
-      Wt[(s * 9 + t) * 32 + ch] = (e & 1) ? bf16_hi(w4[e >> 1]) : bf16_lo(w4[e >> 1]);
+      const int ch = (idx * 7282) >> 16, t = idx - ch * 9;             // idx / 9 for idx < 288
+      wt16[(s * 9 + t) * 32 + ch] = (unsigned short)((e & 1) ? (w4[e >> 1] >> 16) : (w4[e >> 1] & 0xffffu));
     }
   } else if (tid >= 128 && tid < 128 + np * 32) {
     const int s = (tid - 128) >> 5, ch = tid & 31;
-    const int hd = (p0 + s) % br.heads;
+    const int hd = (p0 + s) - fast_div(p0 + s, br.heads, br.m_heads) * br.heads;
     Bc[s * 32 + ch] = __bfloat162float(br.cb[hd * 32 + ch]);
   }
   fence_proxy_async();
@@ -154,21 +159,22 @@ __global__ void __launch_bounds__(kThreads, kWide ? 2 : 3) lepe_attn_fwd_tc_kern
   if (warp == 0 && elect_one()) {     // one elected lane, warp-uniform datapath for the TMA / tcgen05 issue
     mbar_expect_tx(bar_tma, kWide ? (uint32_t)((2 * N + kTileRows) * kRowBytes) : (uint32_t)(np * 3 * N * kRowBytes));
     if (kWide) {                      // q: rows [128 qt, +128) of the window (a box of 128 / W_sp window rows); k, v: the window
-      int local = p0;
-      const int hd = local % br.heads; local /= br.heads;
-      const int win = local % br.nwin;
-      const int b = local / br.nwin;
-      const int ih = win / br.nww, iw = win - ih * br.nww;
-      tma_load_4d(smem_u32(Qs), &P.map[bi][0], bar_tma, hd * 32, iw * ws, ih * hs + qt * (kTileRows / ws), b);
+      const int lw = fast_div(p0, br.heads, br.m_heads);
+      const int hd = p0 - lw * br.heads;
+      const int b = fast_div(lw, br.nwin, br.m_nwin);
+      const int win = lw - b * br.nwin;
+      const int ih = fast_div(win, br.nww, br.m_nww), iw = win - ih * br.nww;
+      tma_load_4d(smem_u32(Qs), &P.map[bi][0], bar_tma, hd * 32, iw * ws, ih * hs + qt * fast_div(kTileRows, ws, br.m_ws), b);
       tma_load_4d(smem_u32(Ks), &P.map[bi][1], bar_tma, hd * 32, iw * ws, ih * hs, b);
       tma_load_4d(smem_u32(Vs), &P.map[bi][2], bar_tma, hd * 32, iw * ws, ih * hs, b);
     }
     for (int s = 0; s < (kWide ? 0 : np); ++s) {
-      int local = p0 + s;
-      const int hd = local % br.heads; local /= br.heads;
-      const int win = local % br.nwin;
-      const int b = local / br.nwin;
-      const int ih = win / br.nww, iw = win - ih * br.nww;
+      const int local = p0 + s;
+      const int lw = fast_div(local, br.heads, br.m_heads);
+      const int hd = local - lw * br.heads;
+      const int b = fast_div(lw, br.nwin, br.m_nwin);
+      const int win = lw - b * br.nwin;
+      const int ih = fast_div(win, br.nww, br.m_nww), iw = win - ih * br.nww;
       const int c0 = hd * 32, c1 = iw * ws, c2 = ih * hs, c3 = b;
       const uint32_t off = s * slot_rows * kRowBytes;
       tma_load_4d(smem_u32(Qs) + off, &P.map[bi][0], bar_tma, c0, c1, c2, c3);
@@ -201,13 +207,21 @@ __global__ void __launch_bounds__(kThreads, kWide ? 2 : 3) lepe_attn_fwd_tc_kern
     uint32_t v[32];
     tmem_ld32(trow + cbeg + 32 * c, v);
     tmem_wait_ld();
-    const int lim = N - (kbeg + 32 * c);                     // valid columns in this chunk
+    const int lim = N - (kbeg + 32 * c);                     // valid columns in this chunk (warp-uniform)
     if (lim >= 32) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
     } else {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) if (j < lim) mx = fmaxf(mx, __uint_as_float(v[j]));
+      for (int g8 = 0; g8 < 4; ++g8) {                       // groups of 8 columns: whole, ragged or beyond the keys
+        if (8 * g8 + 8 <= lim) {
+#pragma unroll
+          for (int j = 8 * g8; j < 8 * g8 + 8; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
+        } else if (8 * g8 < lim) {
+#pragma unroll
+          for (int j = 8 * g8; j < 8 * g8 + 8; ++j) if (j < lim) mx = fmaxf(mx, __uint_as_float(v[j]));
+        }
+      }
     }
   }
   Xmax[half * 128 + row] = mx;
@@ -234,12 +248,30 @@ __global__ void __launch_bounds__(kThreads, kWide ? 2 : 3) lepe_attn_fwd_tc_kern
           pk[c][j >> 1] = pack_bf16x2(e.x, e.y);
         }
       } else {
+        // ragged chunk: whole groups of 8 columns take the packed path, the one ragged group is predicated, groups beyond the
+        // keys only write zeros — `lim` is warp-uniform, so these are real (non-divergent) branches, not predicated-off work
 #pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          const float e0 = (j < lim) ? ex2_approx(fmaf(__uint_as_float(v[j]), P.scale_log2e, -mxs)) : 0.f;
-          const float e1 = (j + 1 < lim) ? ex2_approx(fmaf(__uint_as_float(v[j + 1]), P.scale_log2e, -mxs)) : 0.f;
-          sum += e0 + e1;
-          pk[c][j >> 1] = pack_bf16x2(e0, e1);
+        for (int g8 = 0; g8 < 4; ++g8) {
+          if (8 * g8 + 8 <= lim) {
+#pragma unroll
+            for (int j = 8 * g8; j < 8 * g8 + 8; j += 2) {
+              const float2 t = ffma2(make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), sl2, nmxs2);
+              const float2 e = make_float2(ex2_approx(t.x), ex2_approx(t.y));
+              sum2 = fadd2(sum2, e);
+              pk[c][j >> 1] = pack_bf16x2(e.x, e.y);
+            }
+          } else if (8 * g8 < lim) {
+#pragma unroll
+            for (int j = 8 * g8; j < 8 * g8 + 8; j += 2) {
+              const float e0 = (j < lim) ? ex2_approx(fmaf(__uint_as_float(v[j]), P.scale_log2e, -mxs)) : 0.f;
+              const float e1 = (j + 1 < lim) ? ex2_approx(fmaf(__uint_as_float(v[j + 1]), P.scale_log2e, -mxs)) : 0.f;
+              sum += e0 + e1;
+              pk[c][j >> 1] = pack_bf16x2(e0, e1);
+            }
+          } else {
+#pragma unroll
+            for (int j = 8 * g8; j < 8 * g8 + 8; j += 2) pk[c][j >> 1] = 0u;
+          }
         }
       }
     }
@@ -276,7 +308,7 @@ __global__ void __launch_bounds__(kThreads, kWide ? 2 : 3) lepe_attn_fwd_tc_kern
   // ---- LePE for my token, channels [16*half, 16*half+16), overlapped with the P.V MMA ----
   mbar_wait(bar_tma, 0);                                     // (already complete) acquire the TMA-written V tile
   const bool valid = slot < np && n < N;
-  const int r = n / ws, c = n - r * ws;
+  const int r = fast_div(n, ws, br.m_ws), c = n - r * ws;
   float2 lp[8];                                              // 16 channels as packed fp32 pairs (FFMA2)
   {
     const float2* bc = reinterpret_cast<const float2*>(Bc + min(slot, np - 1) * 32 + half * 16);
@@ -285,23 +317,23 @@ __global__ void __launch_bounds__(kThreads, kWide ? 2 : 3) lepe_attn_fwd_tc_kern
   }
   if (valid) {
     const uint32_t vbase = smem_u32(Vs);
-    const float* wt = Wt + slot * 9 * 32 + half * 16;
+    const uint32_t wbase = smem_u32(Wt) + (uint32_t)(slot * 9 * 32 + half * 16) * 2u;
 #pragma unroll
     for (int t = 0; t < 9; ++t) {
       const int rr = r + t / 3 - 1, cc = c + t % 3 - 1;
       if (rr >= 0 && rr < hs && cc >= 0 && cc < ws) {
         const int vr = slot * slot_rows + rr * ws + cc;
 #pragma unroll
-        for (int ch = 0; ch < 2; ++ch) {
-          uint4 vv;
+        for (int ch = 0; ch < 2; ++ch) {                     // 8 channels: one 16-byte V chunk x one 16-byte weight chunk, 8 FHFMA.BF16
+          uint4 vv, ww;
           asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(vv.x), "=r"(vv.y), "=r"(vv.z), "=r"(vv.w)
                        : "r"(v_chunk_addr(vbase, vr, half * 2 + ch)));
-          const float4 w0 = *reinterpret_cast<const float4*>(wt + t * 32 + ch * 8);
-          const float4 w1 = *reinterpret_cast<const float4*>(wt + t * 32 + ch * 8 + 4);
-          lp[ch * 4 + 0] = ffma2(make_float2(w0.x, w0.y), make_float2(bf16_lo(vv.x), bf16_hi(vv.x)), lp[ch * 4 + 0]);
-          lp[ch * 4 + 1] = ffma2(make_float2(w0.z, w0.w), make_float2(bf16_lo(vv.y), bf16_hi(vv.y)), lp[ch * 4 + 1]);
-          lp[ch * 4 + 2] = ffma2(make_float2(w1.x, w1.y), make_float2(bf16_lo(vv.z), bf16_hi(vv.z)), lp[ch * 4 + 2]);
-          lp[ch * 4 + 3] = ffma2(make_float2(w1.z, w1.w), make_float2(bf16_lo(vv.w), bf16_hi(vv.w)), lp[ch * 4 + 3]);
+          asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(ww.x), "=r"(ww.y), "=r"(ww.z), "=r"(ww.w)
+                       : "r"(wbase + (uint32_t)(t * 64 + ch * 16)));
+          lp[ch * 4 + 0].x = fhfma_lo(vv.x, ww.x, lp[ch * 4 + 0].x); lp[ch * 4 + 0].y = fhfma_hi(vv.x, ww.x, lp[ch * 4 + 0].y);
+          lp[ch * 4 + 1].x = fhfma_lo(vv.y, ww.y, lp[ch * 4 + 1].x); lp[ch * 4 + 1].y = fhfma_hi(vv.y, ww.y, lp[ch * 4 + 1].y);
+          lp[ch * 4 + 2].x = fhfma_lo(vv.z, ww.z, lp[ch * 4 + 2].x); lp[ch * 4 + 2].y = fhfma_hi(vv.z, ww.z, lp[ch * 4 + 2].y);
+          lp[ch * 4 + 3].x = fhfma_lo(vv.w, ww.w, lp[ch * 4 + 3].x); lp[ch * 4 + 3].y = fhfma_hi(vv.w, ww.w, lp[ch * 4 + 3].y);
         }
       }
     }
@@ -378,6 +410,8 @@ int lepe_attention_fwd_tc(const cswin_lepe_branch_t* brs, int nb, int B, int res
     d.heads = s.heads; d.hs = s.H_sp; d.ws = s.W_sp; d.nww = reso / s.W_sp;
     d.nwin = (reso / s.H_sp) * (reso / s.W_sp); d.N = s.H_sp * s.W_sp;
     d.nprob = B * d.nwin * d.heads;
+    auto magic = [](int dv) { return dv > 1 ? (uint32_t)((0x100000000ull / (uint64_t)dv) + 1) : 0u; };
+    d.m_heads = magic(d.heads); d.m_nwin = magic(d.nwin); d.m_nww = magic(d.nww); d.m_ws = magic(d.ws);
     d.tile_begin = tiles;
     const int slots = d.N <= 64 ? 2 : 1;
     tiles += wide ? 2 * d.nprob : (d.nprob + slots - 1) / slots;

@@ -240,6 +240,19 @@ __device__ __forceinline__ float gelu_grad_fast(float x) {
   return fmaf(x * 0.39894228040143267794f, e, fmaf(0.5f, t, 0.5f));
 }
 
+// ---- mixed-precision FMA (FHFMA.BF16): c += a.lo * b.lo / a.hi * b.hi with bf16 halves of packed registers and an fp32 accumulator;
+//      the product of two bf16 is exact in fp32, so this equals unpack + FFMA bit for bit, without the unpack instructions ----
+__device__ __forceinline__ float fhfma_lo(uint32_t a, uint32_t b, float c) {
+  const unsigned short x = (unsigned short)(a & 0xffffu), y = (unsigned short)(b & 0xffffu);
+  asm("fma.rn.f32.bf16 %0, %1, %2, %0;" : "+f"(c) : "h"(x), "h"(y));
+  return c;
+}
+__device__ __forceinline__ float fhfma_hi(uint32_t a, uint32_t b, float c) {
+  const unsigned short x = (unsigned short)(a >> 16), y = (unsigned short)(b >> 16);
+  asm("fma.rn.f32.bf16 %0, %1, %2, %0;" : "+f"(c) : "h"(x), "h"(y));
+  return c;
+}
+
 // ---- packed fp32 pairs (Blackwell FFMA2 / FADD2 / FMUL2: two fp32 operations per issue slot) ----
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
   float2 d;
