@@ -108,6 +108,9 @@ class DropPath(nn.Module):
 # (batch 24): dim 64 fused 71.3 us vs 76.8 us composed; dim 128 45.5 vs 44.3; dim 256 44.6 vs 38.8 -> default 64.
 FUSE_MLP = os.environ.get("CSWIN_FUSE_MLP", "1") != "0"
 FUSE_MLP_MAX_DIM = int(os.environ.get("CSWIN_FUSE_MLP_MAX_DIM", "64"))
+# ... and for at most this many rows: the fused kernel shortens the latency chain of a small launch (batch 24: 75 k rows at stage 1),
+# in the throughput regime the two composed Linears (16 epilogue warps per SM) are faster (batch 96, 301 k rows: 30.8 k -> 31.3 k slices/s)
+FUSE_MLP_MAX_ROWS = int(os.environ.get("CSWIN_FUSE_MLP_MAX_ROWS", "150000"))
 FOLD_LN = os.environ.get("CSWIN_FOLD_LN", "1") != "0"     # LayerNorm folded into the tcgen05 Linear epilogue (bf16 inference)
 # Merge_Block / CARAFE.encoder convolutions as implicit GEMMs (cswin_conv_tokens_fwd: strided TMA boxes of the token image, no
 # column matrix) where the channel count allows (C % 64 == 0); CSWIN_IMPLICIT_CONV=0 restores im2col + Linear (A/B switch)
@@ -415,7 +418,7 @@ class CSWinBlock(_Native):
             x1, st1 = ops.linear(att, w("proj.w", self.proj.weight, dt), w("proj.b", self.proj.bias, dt), residual=x,
                                  sample_scale=self._sample_scale(x), rows_per_sample=L, want_stats=True)
             w1, cs1, b1 = self._folded("fc1", self.mlp.fc1, self.norm2)
-            if (FUSE_MLP and Cn <= FUSE_MLP_MAX_DIM and self._sample_scale(x) is None
+            if (FUSE_MLP and Cn <= FUSE_MLP_MAX_DIM and B * L <= FUSE_MLP_MAX_ROWS and self._sample_scale(x) is None
                     and ops.mlp_supported(Cn, self.mlp.fc1.out_features)):
                 # fc1 + GELU + fc2 + residual in one launch; the hidden activation stays in TMEM / shared memory
                 y, st2 = ops.mlp_fused(x1, w1, cs1, b1, w("fc2.w", self.mlp.fc2.weight, dt),
@@ -588,21 +591,34 @@ class CARAFE(_Native):
         resolution, `out.weight` or the folded head) ONE Linear computes [down | z] from x — both read the same rows — and the
         method returns (logits, z) with z a column view of that Linear's output."""
         dt = x.dtype
-        wd = self._w("down.w", self.down.weight, dt, lambda t: t.reshape(t.shape[0], -1))
-        bd = self._w("down.b", self.down.bias, dt)
+        nd0 = self.down.weight.shape[0]
+        # fewer than 64 compressed channels (C/4 = 16 / 32 at 56^2 / 28^2): `down` is given zero rows up to 64 outputs and the encoder
+        # zero input channels to match, so that the 3x3 encoder runs as an implicit GEMM straight from the token image (K blocks of
+        # one tap x 64 channels) — the zero channels add exact zeros; cheaper than writing and re-reading a column matrix
+        pad_to = 64 if (IMPLICIT_CONV and dt == torch.bfloat16 and nd0 < 64) else nd0
+        F = torch.nn.functional
+        if pad_to == nd0:
+            wd = self._w("down.w", self.down.weight, dt, lambda t: t.reshape(t.shape[0], -1))
+            bd = self._w("down.b", self.down.bias, dt)
+            we = self._w("enc.w", self.encoder.weight, dt, lambda t: t.permute(0, 2, 3, 1).reshape(t.shape[0], -1))
+        else:
+            wd = self._w("down.w.p64", self.down.weight, dt, lambda t: F.pad(t.reshape(t.shape[0], -1), (0, 0, 0, pad_to - nd0)))
+            bd = self._w("down.b.p64", self.down.bias, dt, lambda t: F.pad(t, (0, pad_to - nd0)))
+            we = self._w("enc.w.p64", self.encoder.weight, dt,
+                         lambda t: F.pad(t.permute(0, 2, 3, 1), (0, pad_to - nd0)).reshape(t.shape[0], -1))
+        be = self._w("enc.b", self.encoder.bias, dt)
         z = None
         if z_weight is None:
             d = ops.linear(x, wd, bd)                                                   # (B, L, C/4)
         else:
             nd, nz = wd.shape[0], z_weight.shape[0]
-            wcat = self._w("downz.w." + z_key, (self.down.weight, z_weight), dt,
-                           lambda a, b: torch.cat([a.reshape(a.shape[0], -1).to(dt), b.reshape(b.shape[0], -1).to(dt)], 0))
-            bcat = self._w("downz.b." + z_key, (self.down.bias, z_weight), dt,
-                           lambda a, b: torch.cat([a.to(dt), torch.zeros(b.shape[0], dtype=dt, device=a.device)]))
+            pk = "" if pad_to == nd0 else ".p64"
+            wcat = self._w("downz.w." + z_key + pk, (self.down.weight, z_weight), dt,
+                           lambda a, b: torch.cat([F.pad(a.reshape(a.shape[0], -1).to(dt), (0, 0, 0, pad_to - nd0)), b.reshape(b.shape[0], -1).to(dt)], 0))
+            bcat = self._w("downz.b." + z_key + pk, (self.down.bias, z_weight), dt,
+                           lambda a, b: torch.cat([F.pad(a.to(dt), (0, pad_to - nd0)), torch.zeros(b.shape[0], dtype=dt, device=a.device)]))
             y = ops.linear(x, wcat, bcat)                                               # (B, L, C/4 + Nz): [down(x) | z(x)], no bias on z yet
             d, z = y[..., :nd], y[..., nd:]
-        we = self._w("enc.w", self.encoder.weight, dt, lambda t: t.permute(0, 2, 3, 1).reshape(t.shape[0], -1))
-        be = self._w("enc.b", self.encoder.bias, dt)
         enc = ops.conv_tokens(d, H, W, we, be, 3, 3, 1, 1) if IMPLICIT_CONV and d.shape[-1] % 64 == 0 else None
         if enc is None:
             col = ops.im2col_tokens(d, H, W, 3, 3, 1, 1)

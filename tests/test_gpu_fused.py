@@ -214,3 +214,23 @@ def test_merge_block_and_carafe_use_the_implicit_conv(monkeypatch):
                 res[on] = (mod(x), cw.launch_count() - n0)
         assert res[True][1] == res[False][1] - 1
         assert torch.equal(res[True][0], res[False][0])
+
+
+def test_carafe_with_few_compressed_channels_pads_them_for_the_implicit_conv(monkeypatch):
+    """C/4 = 16 / 32 compressed channels (CARAFE4 at 56^2, CARAFE at 28^2): `down` gets zero rows up to 64 outputs and the encoder zero
+    input channels, so the 3x3 encoder is an implicit GEMM too.  Same values up to the accumulation order (the zero channels add
+    exact zeros), one launch fewer than the im2col path."""
+    for mod, reso in ((cw.CARAFE(128, 64), 28), (cw.CARAFE4(64, 64), 56)):
+        mod = mod.to(DEV).eval()
+        sd = {k: torch.from_numpy(synth.synth_tensor(f"carafe_pad/{reso}/" + k, tuple(v.shape), 3)) for k, v in mod.state_dict().items()}
+        mod.load_state_dict(sd, strict=True)
+        x = torch.randn(2, reso * reso, mod.down.in_channels, device=DEV).bfloat16()
+        res = {}
+        for on in (True, False):
+            monkeypatch.setattr(modules, "IMPLICIT_CONV", on)
+            n0 = cw.launch_count()
+            with torch.no_grad():
+                res[on] = (mod(x).float(), cw.launch_count() - n0)
+        assert res[True][1] == res[False][1] - 1
+        d = (res[True][0] - res[False][0]).abs().max().item()
+        assert d <= 2e-2 * max(1.0, res[False][0].abs().max().item()), d
