@@ -73,8 +73,13 @@ __device__ __forceinline__ float2 gelu_grad_pair(uint32_t zz) {
 // in L2).  The operand ring runs on across tiles, the accumulator is double-buffered in TMEM (2 x acc_stride columns) and the
 // epilogue staging no longer aliases the ring: the TMA / MMA warps work on tile i+1 while the epilogue warps drain tile i, and
 // barrier init / TMEM allocation / descriptor prefetch are paid once per CTA.  Used when a launch is more than one wave of CTAs.
-template <bool kFold, bool kStats, bool kTrain = false, bool kPersist = false>
-__global__ void __launch_bounds__(kThreads, CSWIN_GEMM_MINB) linear_tc_kernel(const __grid_constant__ GemmTcParams P) {
+//
+// kEW = 16 (persistent form only): ONE CTA per SM with 16 epilogue warps (640 threads), 128 x BN <= 256 tiles, both 256-column halves of
+// TMEM as the two accumulator buffers and a 3..8 stage ring — the same 16 epilogue warps per SM as two 320-thread CTAs, but they never
+// wait for operands: while they drain tile i the producer already has all K blocks of tile i + 1 in flight.
+template <bool kFold, bool kStats, bool kTrain = false, bool kPersist = false, int kEW = 8>
+__global__ void __launch_bounds__(64 + 32 * kEW, kEW == 16 ? 1 : CSWIN_GEMM_MINB) linear_tc_kernel(const __grid_constant__ GemmTcParams P) {
+  constexpr int kUS = kEW / 4;                           // unit stride: epilogue warps per TMEM lane quadrant
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for the 128-byte swizzle; plain pointer arithmetic keeps the shared address space (LDS/STS)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -87,7 +92,7 @@ __global__ void __launch_bounds__(kThreads, CSWIN_GEMM_MINB) linear_tc_kernel(co
   const size_t ring = (size_t)S * (a_bytes + w_bytes);
   uint8_t* Epi = kPersist ? smem + ring : smem;                          // persistent form: own 16 KB behind the ring
   constexpr int kCB = kPersist ? 2 : 1;                                  // column-constant buffers (one per accumulator buffer)
-  float* sBias = reinterpret_cast<float*>(smem + ring + (kPersist ? 8 * 2048 : 0));   // [kCB][256] fp32
+  float* sBias = reinterpret_cast<float*>(smem + ring + (kPersist ? kEW * 2048 : 0));   // [kCB][256] fp32
   float* sCs = sBias + kCB * 256;                                        // [kCB][256] folded-LayerNorm column sums
   float* sStat = sCs + kCB * 256;                                        // [128][2] per-row (sum, sum^2) of this tile's output
   uint64_t* bars = reinterpret_cast<uint64_t*>(sStat + 256);             // full[8], empty[8], acc_full[2], acc_empty[2]
@@ -115,7 +120,7 @@ __global__ void __launch_bounds__(kThreads, CSWIN_GEMM_MINB) linear_tc_kernel(co
   if (warp == 0 && elect_one()) {
     for (int s = 0; s < S; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
     mbar_init(acc_full(0), 1);
-    if (kPersist) { mbar_init(acc_full(1), 1); mbar_init(acc_empty(0), 8); mbar_init(acc_empty(1), 8); }
+    if (kPersist) { mbar_init(acc_full(1), 1); mbar_init(acc_empty(0), kEW); mbar_init(acc_empty(1), kEW); }
     fence_barrier_init();
     fence_proxy_async();
     tma_prefetch_desc(&P.map_w);
@@ -227,8 +232,8 @@ __global__ void __launch_bounds__(kThreads, CSWIN_GEMM_MINB) linear_tc_kernel(co
       sBias[tid - 64] = bias_r;
       if (kFold) sCs[tid - 64] = cs_r;
     }
-    if (kStats) sStat[tid - 64] = 0.f;
-    if (!kPersist) asm volatile("bar.sync 1, 256;" ::: "memory");      // the 8 epilogue warps only
+    if (kStats && tid - 64 < 256) sStat[tid - 64] = 0.f;
+    if (!kPersist) asm volatile("bar.sync 1, %0;" ::"n"(32 * kEW) : "memory");      // the epilogue warps only
     uint8_t* stg = Epi + (warp - 2) * 2048;
     const uint32_t stg_u32 = smem_u32(stg);
     const int nunits = (BN + 31) >> 5;
@@ -244,14 +249,16 @@ __global__ void __launch_bounds__(kThreads, CSWIN_GEMM_MINB) linear_tc_kernel(co
         b = P.bias_f32 != nullptr ? P.bias_f32[n] : P.bias != nullptr ? __bfloat162float(P.bias[n]) : 0.f;
         if (kFold) c = P.ln_cs[n];
       }
-      sBias[buf * 256 + j] = b;
-      if (kFold) sCs[buf * 256 + j] = c;
-      asm volatile("bar.sync 1, 256;" ::: "memory");    // also orders the previous tile's statistics hand-off
+      if (j < 256) {
+        sBias[buf * 256 + j] = b;
+        if (kFold) sCs[buf * 256 + j] = c;
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * kEW) : "memory");    // also orders the previous tile's statistics hand-off
     }
     const float* sB = sBias + buf * 256;
     const float* sC = sCs + buf * 256;
     if (P.res != nullptr && P.vec_ok) {                 // pull this thread's residual segments towards L1 while the MMAs run
-      for (int u = ch; u < ((BN + 31) >> 5); u += 2) {
+      for (int u = ch; u < ((BN + 31) >> 5); u += kUS) {
         const int n = n0 + u * 32 + (lane & 3) * 8;
 #pragma unroll
         for (int pass = 0; pass < 4; ++pass) {
@@ -277,7 +284,7 @@ __global__ void __launch_bounds__(kThreads, CSWIN_GEMM_MINB) linear_tc_kernel(co
       // ---- fast path (16-byte aligned rows, N % 8 == 0): everything happens in the accumulator layout (thread = row): bias /
       //      GELU / scale -> bf16 -> residual add (packed bf16x2) -> row statistics -> 64B-swizzled staging box -> one TMA
       //      store per 32 x 32 unit.  No shared-memory read-back, no per-thread global stores, ragged edges clipped by TMA.
-      for (int u = ch; u < nunits; u += 2) {
+      for (int u = ch; u < nunits; u += kUS) {
         uint32_t v[32];
         PSTAMP(8);
         tmem_ld32(trow + u * 32, v);
@@ -292,7 +299,7 @@ __global__ void __launch_bounds__(kThreads, CSWIN_GEMM_MINB) linear_tc_kernel(co
         }
         tmem_wait_ld();
         PSTAMP(9);
-        if (kPersist && u + 2 >= nunits) {                // last unit of this warp: the accumulator buffer is free for tile i + 2
+        if (kPersist && u + kUS >= nunits) {                // last unit of this warp: the accumulator buffer is free for tile i + 2
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(acc_empty(buf));
@@ -370,7 +377,7 @@ __global__ void __launch_bounds__(kThreads, CSWIN_GEMM_MINB) linear_tc_kernel(co
       __syncwarp();
       if (kPersist && ch >= nunits && lane == 0) mbar_arrive(acc_empty(buf));   // BN <= 32: this warp had no unit, it still signs off
     } else
-    for (int u = ch; u < nunits; u += 2) {
+    for (int u = ch; u < nunits; u += kUS) {
       uint32_t v[32];
       PSTAMP(8);
       tmem_ld32(trow + u * 32, v);
@@ -476,7 +483,7 @@ __global__ void __launch_bounds__(kThreads, CSWIN_GEMM_MINB) linear_tc_kernel(co
       __syncwarp();
     }
     if (kStats) {
-      asm volatile("bar.sync 1, 256;" ::: "memory");      // all 8 epilogue warps have accumulated their units
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * kEW) : "memory");      // all epilogue warps have accumulated their units
       const int r = tid - 64;
       if (r < BM) {
         if (m0 + r < P.M && r < rows_valid) {
@@ -504,20 +511,20 @@ size_t smem_bytes(int bn, int stages) {
 }
 int tmem_cols_for(int bn) { return bn <= 64 ? 64 : bn <= 128 ? 128 : 256; }      // the epilogue reads whole 64-col groups
 
-size_t smem_bytes_persist(int bn, int stages) {                                   // + own staging, second column-constant buffer
-  return smem_bytes(bn, stages) + 8 * 2048 + 2 * 1024;
+size_t smem_bytes_persist(int bn, int stages, int ew = 8) {                       // + own staging, second column-constant buffer
+  return smem_bytes(bn, stages) + (size_t)ew * 2048 + 2 * 1024;
 }
 // CSWIN_GEMM_PERSIST=0 switches the persistent form off (A/B runs); =2 forces it wherever it is legal
 int persist_mode() { static const int v = [] { const char* e = getenv("CSWIN_GEMM_PERSIST"); return e ? atoi(e) : 1; }(); return v; }
 
-struct TileCfg { int bn, stages; int persist, grid; };
+struct TileCfg { int bn, stages; int persist, grid; int ew = 8; };
 
 // Tile-shape choice.  At cswin_tiny sizes a Linear is a handful of waves at most, so the launch is latency- not
 // throughput-bound: the model below (constants fitted to L2-warm CUDA-event timings on B200, microseconds) trades the
 // number of waves against per-tile latency = fixed setup + K-loop (faster with a deeper ring) + epilogue (per 64
 // columns; GELU costs ~2x).  The ring depth is whatever fits once the CTAs that must share an SM are accounted for.
 // CSWIN_GEMM_BN=<n> forces BN for experiments.
-TileCfg pick_tile(int64_t M, int N, int nkb, int act, int sms, bool w_kn) {
+TileCfg pick_tile(int64_t M, int N, int nkb, int act, int sms, bool w_kn, bool allow_persist = true) {
   static const int forced = [] { const char* e = getenv("CSWIN_GEMM_BN"); return e ? atoi(e) : 0; }();
   // CSWIN_GEMM_SMEM_CAP_KB: per-CTA shared-memory ceiling, so that a CTA of the NEXT kernel (PDL) fits next to the resident ones
   static const int env_cap = [] { const char* e = getenv("CSWIN_GEMM_SMEM_CAP_KB"); return e ? atoi(e) : -1; }();
@@ -554,7 +561,7 @@ TileCfg pick_tile(int64_t M, int N, int nkb, int act, int sms, bool w_kn) {
   // loop: 301056x64x64 40 -> 29 us, 301056x16x64 23 -> 13, 75264x128x512 28 -> 24); loses where BN would have to shrink from
   // 192 / 256 (more tiles re-reading A) and for the GELU epilogues, which are instruction-issue bound either way — those keep
   // the one-tile form.
-  const int pm = persist_mode();
+  const int pm = allow_persist ? persist_mode() : 0;
   if (pm == 2 || (pm != 0 && best_waves > 1 && best.bn <= 128 && act == 0)) {
     int bn = best.bn > 128 ? 128 : best.bn;
     if (best.bn > 128 && N % 128 != 0) bn = (N % 96 == 0 && !w_kn) ? 96 : 64;
@@ -566,6 +573,28 @@ TileCfg pick_tile(int64_t M, int N, int nkb, int act, int sms, bool w_kn) {
       if (smem_bytes_persist(bn, st) <= 113 * 1024 && tiles <= 0x7fffffff) {
         const int64_t slots = (int64_t)sms * 2;
         best = TileCfg{bn, st, 1, (int)(tiles < slots ? tiles : slots)};
+      }
+    }
+  }
+  // The one-CTA-per-SM persistent form with 16 epilogue warps (kEW = 16): EXPERIMENT, only with CSWIN_GEMM_PERSIST=3.  Measured on
+  // B200 (profiles/r02_linear_persist_forms.log): 18816x1024x256 GELU 21.4 vs 20.7 us, 18816x768x256 13.9 vs 14.1, 75264x512x128 GELU
+  // 39.6 vs 34.2, 301056x192x64 56.6 vs 42.7 — never ahead.  The epilogue warps are bound by their own dependent chains (0.4-0.5 IPC per
+  // scheduler with 4 warps each, 96 registers per thread cap the SM at 20 warps), not by waiting for operands, so overlapping the
+  // mainloop with the epilogue buys nothing once two CTAs share an SM.
+  if (pm == 3) {
+    int bn2 = 0;
+    if (n16 <= 256) bn2 = n16;
+    else { const int c2[] = {256, 192, 128}; for (int c : c2) if (N % c == 0) { bn2 = c; break; } }
+    if (bn2 != 0 && w_kn && bn2 % 64) bn2 = 0;
+    if (bn2 != 0) {
+      const int64_t tiles2 = mt * ((N + bn2 - 1) / bn2);
+      if ((tiles2 >= 2 * (int64_t)sms || (pm == 3 && tiles2 >= sms)) && tiles2 <= 0x7fffffff) {
+        int st = 1;
+        while (st < kMaxStages && st < 2 * nkb && smem_bytes_persist(bn2, st + 1, 16) <= 227 * 1024) ++st;
+        if (smem_bytes_persist(bn2, st, 16) <= 227 * 1024) {
+          best = TileCfg{bn2, st, 1, (int)(tiles2 < sms ? tiles2 : sms)};
+          best.ew = 16;
+        }
       }
     }
   }
@@ -618,7 +647,8 @@ static int linear_fwd_tc_impl(const cswin_linear_args_t* a, const ConvGeom* cv, 
   P.nkb1 = (a->K1 + BK - 1) / BK;
   P.nkb = P.nkb1 + (a->K2 + BK - 1) / BK;
   P.w_kn = a->w_layout;
-  TileCfg cfg = pick_tile(a->M, a->N, P.nkb, a->act, sm_count(), a->w_layout != 0);
+  // (the training epilogues — aux output, act 2 — exist in the one-tile form only)
+  TileCfg cfg = pick_tile(a->M, a->N, P.nkb, a->act, sm_count(), a->w_layout != 0, !(a->aux_out != nullptr || a->act == 2));
   P.conv = 0; P.cv_rows = BM; P.cv_tpi = 1; P.cv_nb = 1; P.cv_bh = 1; P.cv_stride = 1; P.cv_pad = 0; P.cv_KW = 1; P.cv_cblk = 1;
   if (cv != nullptr) {
     // M tile = whole images (OH OW nb <= 128) or bh full output rows of one image (bh | OH, bh OW <= 128)
@@ -701,10 +731,12 @@ static int linear_fwd_tc_impl(const cswin_linear_args_t* a, const ConvGeom* cv, 
     }
   }
   using Kern = void (*)(const GemmTcParams);
-  static const Kern kerns[9] = {linear_tc_kernel<false, false>, linear_tc_kernel<true, false>, linear_tc_kernel<false, true>,
-                                linear_tc_kernel<true, true>, linear_tc_kernel<false, false, true>,
-                                linear_tc_kernel<false, false, false, true>, linear_tc_kernel<true, false, false, true>,
-                                linear_tc_kernel<false, true, false, true>, linear_tc_kernel<true, true, false, true>};
+  static const Kern kerns[13] = {linear_tc_kernel<false, false>, linear_tc_kernel<true, false>, linear_tc_kernel<false, true>,
+                                 linear_tc_kernel<true, true>, linear_tc_kernel<false, false, true>,
+                                 linear_tc_kernel<false, false, false, true>, linear_tc_kernel<true, false, false, true>,
+                                 linear_tc_kernel<false, true, false, true>, linear_tc_kernel<true, true, false, true>,
+                                 linear_tc_kernel<false, false, false, true, 16>, linear_tc_kernel<true, false, false, true, 16>,
+                                 linear_tc_kernel<false, true, false, true, 16>, linear_tc_kernel<true, true, false, true, 16>};
   static std::atomic<int> configured{0};
   if (!configured.load(std::memory_order_acquire)) {
     for (Kern k : kerns) CSWIN_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -712,14 +744,16 @@ static int linear_fwd_tc_impl(const cswin_linear_args_t* a, const ConvGeom* cv, 
   }
   dim3 grid((unsigned)((a->M + P.cv_rows - 1) / P.cv_rows), (unsigned)((a->N + P.BN - 1) / P.BN));
   const int variant = (a->ln_stats != nullptr ? 1 : 0) | (a->stats_out != nullptr ? 2 : 0);
+  unsigned threads = kThreads;
   Kern kern = train ? kerns[4] : kerns[variant];
   if (cfg.persist && !train && P.tma_out) {             // persistent form: 1-D grid of resident CTAs, two accumulator buffers
-    kern = kerns[5 + variant];
+    kern = kerns[(cfg.ew == 16 ? 9 : 5) + variant];
     grid = dim3((unsigned)cfg.grid);
     P.tmem_cols = 2 * P.acc_stride;
-    smem = smem_bytes_persist(P.BN, P.stages);
+    smem = smem_bytes_persist(P.BN, P.stages, cfg.ew);
+    threads = 64 + 32 * cfg.ew;
   }
-  CSWIN_CUDA_OK(launch_pdl(kern, grid, dim3(kThreads), smem, stream, P));
+  CSWIN_CUDA_OK(launch_pdl(kern, grid, dim3(threads), smem, stream, P));
   CSWIN_LAUNCH_CHECK();
   g_tc_launches.fetch_add(1, std::memory_order_relaxed);
   *handled = true;
