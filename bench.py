@@ -40,6 +40,7 @@ sys.path.insert(0, ROOT)
 METRIC = "CSWin-UNet-tiny 224^2 slices/sec (bf16 fwd)"
 UNIT = "slices/s"
 BATCH = 24                         # BASELINE configs[2]: the train step's batch, and the latency point of the forward
+CPU_CHUNK = 24                     # sub-batch the CPU reference arm processes a step in (its faster batching on the host cores)
 FWD_BATCH = 96                     # slices per forward step of the headline (throughput point, see the module docstring)
 GFLOP_PER_SLICE_FWD = 10.028       # BASELINE.md section 2 (FlopCounterMode on the unmodified reference)
 # dram__bytes_read.sum + dram__bytes_write.sum of lepe_attn_fwd_tc_kernel, ncu --set full, batch 24, summed over the 26 launches
@@ -152,11 +153,13 @@ def cpu_forward_rate(budget_s: float, batch: int, min_iters: int = 2):
         O, sd = oracle_model()
         kind, fwd = "port", (lambda t: O.cswin_unet_forward(sd, t))
     x = torch.from_numpy(synth.synth_image_batch(batch, 3, 224, seed=0, kind="ct"))
+    chunks = list(x.split(CPU_CHUNK))                          # sub-batches of 24: the reference's faster batching on the host
     with torch.no_grad():
         fwd(x[:2])                                             # warm-up
         t0 = time.perf_counter(); n = 0
         while n < min_iters or (time.perf_counter() - t0) < budget_s:
-            fwd(x)
+            for c in chunks:
+                fwd(c)
             n += 1
         dt = time.perf_counter() - t0
     return n * batch / dt, cores, n, dt, kind
@@ -222,20 +225,26 @@ def run_reference(args):
     # bounded sample per step so that K+W steps end within minutes on any host: a batch of 96 slices is ~1.5 s on 16 cores
     sample = args.batch
     x = torch.from_numpy(synth.synth_image_batch(sample, 3, 224, seed=0, kind="ct"))
+    # the step's slices go through the reference in sub-batches of 24: its faster batching on the host (one batch-96 forward runs at
+    # 42-52 slices/s on 16 cores, four batch-24 forwards at 64-72; its own evaluation loop feeds ONE slice at a time: 13 slices/s)
+    chunks = list(x.split(CPU_CHUNK))
     with torch.no_grad():
         for _ in range(args.warmup):
-            fwd(x)
+            for c in chunks:
+                fwd(c)
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            fwd(x)
+            for c in chunks:
+                fwd(c)
         dt = time.perf_counter() - t0
     value = args.steps * sample / dt
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"cswin_tiny_224_lite eval forward, batch {sample} per step, 3x224x224 synthetic slices, " + what},
+            "config": {"workload": f"cswin_tiny_224_lite eval forward, {sample} slices per step (as {len(chunks)} forwards of {CPU_CHUNK}: the CPU's faster batching), "
+                                   "3x224x224 synthetic slices, " + what},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
-                             "sample": f"{args.steps} steps x {sample} slices, torch CPU fp32, {cores} threads"},
+                             "sample": f"{args.steps} steps x {sample} slices ({len(chunks)} forwards of {CPU_CHUNK} each), torch CPU fp32, {cores} threads"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
     return 0
@@ -435,8 +444,13 @@ def run_native(args):
     sampler = ClockSampler(local)
     barrier()
     sampler.start()
+    prof = os.environ.get("CSWIN_BENCH_PROFILER") == "1"          # `ncu --profile-from-start off`: record exactly the timed region
+    if prof:
+        torch.cuda.profiler.start()
     e0, e1 = timed_steps(args.steps, list(range(K)))
     barrier()
+    if prof:
+        torch.cuda.profiler.stop()
     clocks = sampler.stop()
     ms = e0.elapsed_time(e1)
     if world > 1:
@@ -704,7 +718,7 @@ def run_native(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, cores, n, dt, kind = cpu_forward_rate(args.cpu_budget, B)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
-                                "sample": f"{n} forwards of batch {B} in {dt:.1f} s, "
+                                "sample": f"{n} x {B} slices (as forwards of batch {min(B, CPU_CHUNK)}) in {dt:.1f} s, "
                                           f"{'unmodified reference' if kind == 'reference' else 'oracle port'} (torch CPU fp32), {cores} threads"}
         try:                                                       # batch-1 forward and one train step on the host cores
             ex = cpu_extra_rates()

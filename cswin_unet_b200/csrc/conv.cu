@@ -196,9 +196,11 @@ __global__ void __launch_bounds__(256) carafe_reassemble_warp_kernel(const __nv_
   const int64_t pix = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (pix >= npix) return;
   const int s2 = up * up;
-  const int x0 = (int)(pix % W);
-  const int y0 = (int)((pix / W) % H);
-  const int64_t b = pix / ((int64_t)W * H);
+  const int p32 = (int)pix;                             // (the launcher keeps npix < 2^31: 32-bit divisions, a 64-bit one is ~100 instructions)
+  const int prow = p32 / W;
+  const int x0 = p32 - prow * W;
+  const int64_t b = prow / H;
+  const int y0 = prow - (int)b * H;
   float zr[9][V];
 #pragma unroll
   for (int t = 0; t < 9; ++t) {
@@ -326,9 +328,11 @@ __global__ void __launch_bounds__(256) carafe_head_up4_kernel(const __nv_bfloat1
   const int xgroups = (W + 7) >> 3;
   const int64_t wid = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (wid >= (int64_t)B * H * xgroups) return;
-  const int xg = (int)(wid % xgroups);
-  const int y0 = (int)((wid / xgroups) % H);
-  const int b = (int)(wid / ((int64_t)xgroups * H));
+  const int w32 = (int)wid;                             // (< 2^31 warps: 32-bit divisions)
+  const int wrow = w32 / xgroups;
+  const int xg = w32 - wrow * xgroups;
+  const int b = wrow / H;
+  const int y0 = wrow - b * H;
   const int x0 = xg * 8 + (lane >> 2), ay = lane & 3;
   if (x0 >= W) return;
   const int64_t pix = ((int64_t)b * H + y0) * W + x0;
@@ -410,7 +414,7 @@ int carafe_head_fwd(const void* enc, int64_t ldenc, const void* z, int64_t ldz, 
   if (total == 0) return CSWIN_OK;
   const unsigned grid = (unsigned)std::min<int64_t>(ceil_div64(total, 256), (int64_t)sm_count() * 32);
   const int zvec = dtype == CSWIN_BF16 && ldz >= 16 && (ldz * 2) % 16 == 0 && reinterpret_cast<uintptr_t>(z) % 16 == 0;
-  if (zvec && up == 4 && C == 9 && (ldenc * 2) % 8 == 0 && reinterpret_cast<uintptr_t>(enc) % 8 == 0 &&
+  if (zvec && up == 4 && C == 9 && total < 0x7fffffff && (ldenc * 2) % 8 == 0 && reinterpret_cast<uintptr_t>(enc) % 8 == 0 &&
       reinterpret_cast<uintptr_t>(logits) % 16 == 0 && reinterpret_cast<uintptr_t>(labels) % 4 == 0) {
     const unsigned g4 = (unsigned)ceil_div64((int64_t)B * H * ((W + 7) / 8), 8);
     const __nv_bfloat16 *e_ = (const __nv_bfloat16*)enc, *z_ = (const __nv_bfloat16*)z, *b_ = (const __nv_bfloat16*)bias;
@@ -489,7 +493,7 @@ int carafe_reassemble_fwd(const void* enc, int64_t ldenc, const void* z, int64_t
   if (pixels == 0) return CSWIN_OK;
   const size_t smem = sizeof(float) * ((size_t)9 * C + (size_t)up * up * 9);
   CSWIN_REQUIRE(smem <= 48 * 1024, CSWIN_ERR_UNSUPPORTED, "carafe_reassemble: C=%d too large", C);
-  if (dtype == CSWIN_BF16 && !nchw_out && !y_is_f32 && up * up <= 32 && (C == 64 || C == 128 || C == 256) &&
+  if (dtype == CSWIN_BF16 && !nchw_out && !y_is_f32 && up * up <= 32 && (C == 64 || C == 128 || C == 256) && pixels < 0x7fffffff &&
       ldz % 2 == 0 && ldy % 2 == 0 && reinterpret_cast<uintptr_t>(z) % 4 == 0 && reinterpret_cast<uintptr_t>(y) % 4 == 0) {
     const unsigned g2 = (unsigned)ceil_div64(pixels, 8);
     const __nv_bfloat16 *e_ = (const __nv_bfloat16*)enc, *z_ = (const __nv_bfloat16*)z, *b_ = (const __nv_bfloat16*)bias;

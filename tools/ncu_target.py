@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Tiny driver for `ncu --set full`: runs a few launches of one op at one shape.
-usage: ncu_target.py attn <stage 1-4> <B> | attn512 <stage 1-4> <B> | block_infer <stage> <B> | block_train <stage> <B> | linear <M> <N> <K> [act] [res]"""
+usage: ncu_target.py attn <stage 1-4> <B> | attn512 <stage 1-4> <B> | block_infer <stage> <B> | block_train <stage> <B> | conv <B> <H> <C> <N> <stride> | linear <M> <N> <K> [act] [res]"""
 import os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -40,6 +40,12 @@ elif kind == "block_train":          # forward + backward of one CSWinBlock (bf1
     x = torch.randn(B, reso * reso, C, device=DEV, dtype=torch.bfloat16, requires_grad=True)
     def fn():
         y = blk(x); y.sum().backward()
+elif kind == "conv":                 # implicit-GEMM conv over a token image (Merge_Block: stride 2; CARAFE.encoder: stride 1): conv B H C N stride
+    B, H, C, N, stride = [int(v) for v in sys.argv[2:7]]
+    x = torch.randn(B, H * H, C, device=DEV, dtype=torch.bfloat16)
+    w = torch.randn(N, 9 * C, device=DEV, dtype=torch.bfloat16) / (9 * C) ** 0.5
+    bias = torch.randn(N, device=DEV, dtype=torch.bfloat16)
+    fn = lambda: ops.conv_tokens(x, H, H, w, bias, 3, 3, stride, 1)
 else:
     M, N, K = int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])
     act = int(sys.argv[5]) if len(sys.argv) > 5 else 0
