@@ -47,6 +47,9 @@ GFLOP_PER_SLICE_FWD = 10.028       # BASELINE.md section 2 (FlopCounterMode on t
 # of one forward (2 x 28.95 MB + 4 x 14.50 MB + 18 x 7.28 MB + 2 x 3.67 MB read, ~0 written inside the kernel: the output
 # stays in L2): profiles/r01_ncu_full_summary_v2.txt.  Reads equal the algorithmic q,k,v bytes exactly (no re-reads).
 ATTN_DRAM_TRAFFIC_PER_FORWARD = 254_194_000
+# the same at batch 96 (profiles/r02_ncu_full_b96_summary.txt): 2 x (228.83 + 30.02) + 4 x (57.85 + 1.51) + 18 x 28.95 + 2 x 14.50 MB: the
+# stage-1 output (154 MB per launch with q, k, v) no longer stays in L2; algorithmic bytes are 1,348.7 MB
+ATTN_DRAM_TRAFFIC = {24: ATTN_DRAM_TRAFFIC_PER_FORWARD, 96: 1_305_240_000}
 
 
 def peaks():
@@ -501,30 +504,36 @@ def run_native(args):
     #      arguments and buffers as one real forward, L2-warm like in the step), timed with CUDA events ----
     pk = peaks()
 
-    def family_ms(fn_name, reps=20):
+    def family_ms(fn_names, reps=20):
+        """(ms per forward, calls) of the launches that the ops `fn_names` make in one forward; a call is (fn, args, kwargs)."""
+        fn_names = [fn_names] if isinstance(fn_names, str) else list(fn_names)
         calls = []
-        orig = getattr(ops, fn_name)
+        origs = {n: getattr(ops, n) for n in fn_names}
 
-        def rec(*a, **k):
-            calls.append((a, k))
-            return orig(*a, **k)
-        setattr(ops, fn_name, rec)
+        def mk(n):
+            def rec(*a, **k):
+                calls.append((origs[n], a, k))
+                return origs[n](*a, **k)
+            return rec
+        for n in fn_names:
+            setattr(ops, n, mk(n))
         try:
             with torch.no_grad():
                 model(pool[0])
         finally:
-            setattr(ops, fn_name, orig)
+            for n in fn_names:
+                setattr(ops, n, origs[n])
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
         s2 = torch.cuda.Stream()
         s2.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s2), torch.no_grad():
-            for a, k in calls:
-                orig(*a, **k)
+            for f, a, k in calls:
+                f(*a, **k)
         torch.cuda.current_stream().wait_stream(s2)
         with torch.no_grad(), torch.cuda.graph(g):
-            for a, k in calls:
-                orig(*a, **k)
+            for f, a, k in calls:
+                f(*a, **k)
         g.replay()
         torch.cuda.synchronize()
         a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -540,11 +549,11 @@ def run_native(args):
     att_gbs = att_bytes / (att_total_ms * 1e-3) / 1e9
     roofline_attention = {"kernel": "lepe_attn_fwd_tc_kernel (fused LePE stripe attention; 26 launches per forward, both branches per launch)",
                 "bound": "hbm", "achieved": att_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": att_gbs / pk["hbm_gbs"],
-                "traffic": ATTN_DRAM_TRAFFIC_PER_FORWARD, "peak_source": pk["source"], "bytes_per_forward": att_bytes,
+                "traffic": ATTN_DRAM_TRAFFIC.get(B), "peak_source": pk["source"], "bytes_per_forward": att_bytes,
                 "ms_per_forward": att_total_ms, "launches_per_forward": len(att_calls),
                 "how": "CUDA graph of the 26 attention launches of one forward (real buffers, L2-warm as in the step), "
                        "CUDA events over 20 replays"}
-    lin_total_ms, lin_calls = family_ms("linear")
+    lin_total_ms, lin_calls = family_ms(["linear", "conv_tokens"])      # conv_tokens = the same kernel fetching its A operand from the token image
     # the same family with K copies of that graph in flight (own streams), as in the timed region of `value`
     lin_inflight_ms = None
     if K > 1:
@@ -555,8 +564,8 @@ def run_native(args):
                 with torch.no_grad(), torch.cuda.stream(streams[k]):
                     g2 = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(g2, stream=streams[k]):
-                        for a, kw in lin_calls:
-                            ops.linear(*a, **kw)
+                        for f, a, kw in lin_calls:
+                            f(*a, **kw)
                 gs.append(g2)
             torch.cuda.synchronize()
             cur = torch.cuda.current_stream()
@@ -582,13 +591,18 @@ def run_native(args):
         finally:
             cwlib.set_option(cwlib.OPT_GEMM_SMEM_CAP_KB, 0)
     lin_flops = 0.0
-    for a, k in lin_calls:
+    for f, a, k in lin_calls:
+        if f is ops.conv_tokens:                                   # (x, H, W, w, bias, KH, KW, stride, pad): M = B OH OW, N x K = w.shape
+            x_, H_, W_, w_, _, KH_, KW_, st_, pd_ = a
+            m = x_.shape[0] * ((H_ + 2 * pd_ - KH_) // st_ + 1) * ((W_ + 2 * pd_ - KW_) // st_ + 1)
+            lin_flops += 2.0 * m * w_.shape[0] * w_.shape[1]
+            continue
         kk = a[1].shape[1]
         m = a[0].numel() // a[0].shape[-1]
         lin_flops += 2.0 * m * kk * (k.get("n_out") or a[1].shape[0])
     # the DOMINANT kernel of the step (about half of the forward's device time): the tcgen05 Linear family
-    roofline = {"kernel": "linear_tc_kernel (tcgen05 Linear + fused LayerNorm / bias / GELU / residual epilogue; every nn.Linear, 1x1 and "
-                          "im2col'ed conv of the forward)", "bound": "tensor",
+    roofline = {"kernel": "linear_tc_kernel (tcgen05 Linear + fused LayerNorm / bias / GELU / residual epilogue; every nn.Linear, 1x1 conv and "
+                          "(as an implicit GEMM) 3x3 conv of the forward)", "bound": "tensor",
                 "achieved": lin_flops / (lin_total_ms * 1e-3) / 1e12, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
                 "frac": lin_flops / (lin_total_ms * 1e-3) / 1e12 / pk["bf16_tflops"], "traffic": None, "peak_source": pk["source"] + " (burst)",
                 "launches_per_forward": len(lin_calls), "ms_per_forward": lin_total_ms, "flops_per_forward": lin_flops,
