@@ -244,7 +244,13 @@ def load_named(module, prefix, seed):
 BLOCKS = ((64, 56, 2, 1, False), (128, 28, 4, 2, False), (256, 14, 8, 7, False), (512, 7, 16, 7, True))
 
 
-@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-4), (torch.bfloat16, 1.5e-1)])
+# bf16: inputs, weights and 5 intermediate activations of a block are rounded to bf16 (2^-9 relative each).  The bound is RELATIVE to
+# the largest golden activation of the block: measured 0.6-0.7e-2 of it on B200 (smoke() prints it) — 2.5e-2 leaves room for other seeds
+# and still fails a kernel that is wrong in any visible way (the old absolute 1.5e-1 did not).
+BF16_BLOCK_REL = 2.5e-2
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-4), (torch.bfloat16, None)])
 def test_block_vs_golden(dtype, tol):
     z = G.load("block")
     for (dim, reso, heads, split, last) in BLOCKS:
@@ -254,8 +260,9 @@ def test_block_vs_golden(dtype, tol):
         with torch.no_grad():
             y = m(x)
         assert y.dtype == dtype
-        # bf16: inputs, weights, and 5 intermediate activations are rounded to bf16; |y| reaches ~8
-        G.compare(z, f"d{dim}", y.float().cpu().numpy(), atol=tol)
+        scale = float(np.abs(z[f"d{dim}.rows"].astype(np.float64)).max())
+        err = G.compare(z, f"d{dim}", y.float().cpu().numpy(), atol=tol if tol is not None else BF16_BLOCK_REL * scale)
+        print(f"[block {dim} {dtype}] max-abs {err:.3e}, max |golden| {scale:.2f}, relative {err / scale:.2e}")
 
 
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-4), (torch.bfloat16, 6e-2)])
@@ -499,7 +506,9 @@ def test_512px_config_blocks_fp32_and_bf16_vs_oracle():
             y32 = m(x).cpu().double()
             y16 = m(x.bfloat16()).float().cpu().double()
         assert (y32 - ref).abs().max().item() <= 1e-4, dim
-        assert (y16 - ref).abs().max().item() <= 2e-1, dim
+        e16, scale = (y16 - ref).abs().max().item(), ref.abs().max().item()
+        print(f"[512^2 block {dim}] bf16 max-abs {e16:.3e}, max |ref| {scale:.2f}, relative {e16 / scale:.2e}")
+        assert e16 <= BF16_BLOCK_REL * scale, (dim, e16, scale)
 
 
 @pytest.mark.parametrize("M,C,N,act,mean", [(3136 * 2, 64, 192, 0, 0.0), (784, 128, 512, 1, 0.7), (196 * 3, 256, 768, 0, -1.5),
