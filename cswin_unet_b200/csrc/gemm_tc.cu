@@ -5,16 +5,25 @@
 // Replaces nn.Linear and the separate element-wise kernels of the reference around it (networks/cswin_unet.py:169,
 // :177-178, Mlp :22-26 + :179, concat_linear :509-527, and the 1x1 / im2col'ed convs :216, :240-241, :264, :339, :542).
 //
-// One 128 x BN output tile per CTA (BN = 16..256, picked so that the grid covers the 148 SMs at least twice where the
-// problem allows), K consumed in 64-wide blocks (128-byte rows, 128-byte swizzle) through a 1..4 stage TMA -> smem
-// ring.  Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread tcgen05.mma issuer,
-// warps 2..5 = epilogue.  The two-source form ([skip | x] for the decoder's concat Linears) switches tensor maps
-// at the K1 boundary, so the concatenated activation is never materialised.  Ragged M / N / K tails are handled by
-// TMA out-of-bounds zero fill on the loads and by predicated stores.
+// One 128 x BN output tile per CTA (BN = 16..256, picked by a latency model so that the grid covers the 148 SMs at least twice where
+// the problem allows), K consumed in 64-wide blocks (128-byte rows, 128-byte swizzle) through a 1..8 stage TMA -> smem ring.  Warp
+// roles: warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread tcgen05.mma issuer (elect.sync lane), warps 2..9 = epilogue.
+// The two-source form ([skip | x] for the decoder's concat Linears) switches tensor maps at the K1 boundary, so the concatenated
+// activation is never materialised.  Ragged M / N / K tails are handled by TMA out-of-bounds zero fill on the loads and by TMA clipping
+// (or predicated stores) on the way out.
 //
-// Epilogue (per warp = 32 accumulator rows, 64 columns at a time): tcgen05.ld -> bias / GELU(erf) / DropPath scale in
-// fp32 registers -> fp32 staging tile in shared memory (XOR-swizzled 16-byte chunks, conflict-free) -> read back
-// row-contiguous so that the residual load and the output store are fully coalesced 16-byte accesses.
+// Epilogue, in the accumulator layout (thread = row), per 32-column unit: tcgen05.ld -> folded LayerNorm / bias / GELU / DropPath scale
+// in fp32 registers (packed FFMA2) -> bf16 -> packed residual add -> row statistics for the next folded LayerNorm -> 64-byte-swizzled
+// staging box -> one TMA store per 32 x 32 unit.  Outputs whose rows are not 16-byte aligned take the older path (fp32 staging read back
+// row-contiguous, predicated 16-byte stores).
+//
+// Forms of the same kernel (template / runtime parameters, see the comments at each):
+//   kPersist      resident CTAs walk the tiles, accumulator double-buffered in TMEM, ring running across tiles (multi-wave launches
+//                 with a light epilogue); kEW = 16: the one-CTA-per-SM variant with 16 epilogue warps (experiment);
+//   P.conv        implicit-GEMM convolution: the A operand is fetched as strided 4-D TMA boxes of a (B, H, W, C) token image
+//                 (cswin_conv_tokens_fwd: Merge_Block.conv, CARAFE.encoder — networks/cswin_unet.py:214-216, :240-241);
+//   kTrain        the two training-only epilogues (aux pre-activation output, multiply by GELU'(z));
+//   P.w_kn        weights read as (K, N) row-major = MN-major B operand (data gradient dA = dZ W).
 #include <climits>
 #include <cstdlib>
 
