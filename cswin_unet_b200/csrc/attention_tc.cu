@@ -28,6 +28,8 @@
 // (window, head) problem is two tiles of 128 query rows, each against all N keys: K / V tiles of 256 rows, S = 128 x 256
 // fp32 in TMEM columns [0,256), P (bf16) back into columns [0,128), O into columns [128,160) (S is dead by then); each of
 // the two threads of a row owns 128 key columns.  Needs 128 % W_sp == 0 so that a query tile is a rectangular TMA box.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -70,8 +72,12 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
-template <bool kWide>
-__global__ void __launch_bounds__(kThreads, kWide ? 2 : 3) lepe_attn_fwd_tc_kernel(const __grid_constant__ TcParams P) {
+// kMinB = CTAs per SM the register budget is sized for.  3 (80 registers) for launches of at most one wave: the tile's own latency is
+// what counts (stage 3 at batch 24: 7.4 us vs 9.2 us with the spills of the 64-register build); 4 (64 registers, 252 bytes of spill
+// stores) for multi-wave launches, where a fourth resident tile hides more latency than the spills cost (batch 96: 757 -> 713 us for the
+// 26 launches of a forward).  The launcher picks by tile count.
+template <bool kWide, int kMinB>
+__global__ void __launch_bounds__(kThreads, kMinB) lepe_attn_fwd_tc_kernel(const __grid_constant__ TcParams P) {
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment by pointer arithmetic on the shared array: keeps the shared address space (LDS / STS, not generic LD / ST)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -426,8 +432,11 @@ int lepe_attention_fwd_tc(const cswin_lepe_branch_t* brs, int nb, int B, int res
   }
   if (nb == 1) P.br[1] = P.br[0];
   static_assert(kSmemBytes <= 48 * 1024 && kSmemBytesWide <= 48 * 1024, "dynamic smem must stay under the no-opt-in limit");
-  if (wide) CSWIN_CUDA_OK(launch_pdl(lepe_attn_fwd_tc_kernel<true>, dim3(tiles), dim3(kThreads), (size_t)kSmemBytesWide, stream, P));
-  else CSWIN_CUDA_OK(launch_pdl(lepe_attn_fwd_tc_kernel<false>, dim3(tiles), dim3(kThreads), (size_t)kSmemBytes, stream, P));
+  static const int forced_minb = [] { const char* e = getenv("CSWIN_ATTN_MINB"); return e ? atoi(e) : 0; }();     // A/B switch (3 / 4)
+  const bool four = forced_minb ? forced_minb == 4 : tiles > 3 * sm_count();
+  if (wide) CSWIN_CUDA_OK(launch_pdl(lepe_attn_fwd_tc_kernel<true, 2>, dim3(tiles), dim3(kThreads), (size_t)kSmemBytesWide, stream, P));
+  else if (four) CSWIN_CUDA_OK(launch_pdl(lepe_attn_fwd_tc_kernel<false, 4>, dim3(tiles), dim3(kThreads), (size_t)kSmemBytes, stream, P));
+  else CSWIN_CUDA_OK(launch_pdl(lepe_attn_fwd_tc_kernel<false, 3>, dim3(tiles), dim3(kThreads), (size_t)kSmemBytes, stream, P));
   CSWIN_LAUNCH_CHECK();
   g_tc_launches.fetch_add(1, std::memory_order_relaxed);
   *handled = true;
