@@ -7,6 +7,8 @@
 //  carafe_reassemble : pixel_shuffle + softmax over the 9 taps + 3x3 neighbourhood re-assembly + pixel_shuffle
 //                  (:242-263 / :292-313), run on the output of the 1x1 `out` conv taken at LOW resolution (see
 //                  cswin_b200.h).  All three are HBM-bound streaming kernels.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace cswin {
@@ -248,6 +250,84 @@ __global__ void __launch_bounds__(256) carafe_reassemble_warp_kernel(const __nv_
     for (int e = 0; e < V; e += 2) {
       const __nv_bfloat162 pk = __floats2bfloat162_rn(acc[e], acc[e + 1]);
       *reinterpret_cast<__nv_bfloat162*>(dst + e) = pk;
+    }
+  }
+}
+
+// Same re-assembly with LPP = C / 8 lanes per low-resolution pixel (8 channels = one 16-byte load per lane and tap) and 32 / LPP pixels
+// per warp: for C = 64 the warp-per-pixel kernel above moves 4 bytes per lane and spends most of its instructions on per-pixel index
+// math and the 9-tap softmax; here those are shared by 4 (C = 64) or 2 (C = 128) pixels per warp.  Needs up^2 <= LPP (the lanes
+// gl < up^2 of a group own one sub-pixel's softmax each).  Same arithmetic, same order of accumulation as the kernel above.
+template <int LPP>
+__global__ void __launch_bounds__(256) carafe_reassemble_grp_kernel(const __nv_bfloat16* __restrict__ enc, int64_t ldenc,
+                                                                     const __nv_bfloat16* __restrict__ z, int64_t ldz,
+                                                                     const __nv_bfloat16* __restrict__ bias,
+                                                                     __nv_bfloat16* __restrict__ y, int64_t ldy, int64_t npix,
+                                                                     int H, int W, int up) {
+  pdl_trigger();
+  pdl_wait();
+  constexpr int PPW = 32 / LPP;
+  const int lane = threadIdx.x & 31, grp = lane / LPP, gl = lane - grp * LPP;
+  const int64_t pix_raw = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * PPW + grp;
+  const bool live = pix_raw < npix;
+  const int p32 = (int)(live ? pix_raw : npix - 1);     // (npix < 2^31, checked by the launcher); idle groups shadow the last pixel
+  const int s2 = up * up;
+  const int prow = p32 / W;
+  const int x0 = p32 - prow * W;
+  const int b = prow / H;
+  const int y0 = prow - b * H;
+  float zr[9][8];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const int yy = y0 + t / 3 - 1, xx = x0 + t % 3 - 1;
+    uint4 u = make_uint4(0, 0, 0, 0);
+    if (yy >= 0 && yy < H && xx >= 0 && xx < W)
+      u = *reinterpret_cast<const uint4*>(z + (((int64_t)b * H + yy) * W + xx) * ldz + gl * 8);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { zr[t][2 * e] = __uint_as_float(w[e] << 16); zr[t][2 * e + 1] = __uint_as_float(w[e] & 0xffff0000u); }
+  }
+  float kt[9];
+  {
+    const int ae = gl < s2 ? gl : 0;
+    float mx = -INFINITY;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) { kt[t] = __bfloat162float(enc[(int64_t)p32 * ldenc + t * s2 + ae]); mx = fmaxf(mx, kt[t]); }
+    float sum = 0.f;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) { kt[t] = expf(kt[t] - mx); sum += kt[t]; }
+    const float inv = 1.0f / sum;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) kt[t] *= inv;
+  }
+  float bv[8];
+  {
+    const uint4 u = *reinterpret_cast<const uint4*>(bias + gl * 8);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { bv[2 * e] = __uint_as_float(w[e] << 16); bv[2 * e + 1] = __uint_as_float(w[e] & 0xffff0000u); }
+  }
+  const int Wo = W * up;
+  for (int ae = 0; ae < s2; ++ae) {
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = bv[e];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const float k = __shfl_sync(0xffffffffu, kt[t], grp * LPP + ae);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] = fmaf(k, zr[t][e], acc[e]);
+    }
+    if (live) {
+      const int oy = y0 * up + ae / up, ox = x0 * up + ae % up;
+      __nv_bfloat16* dst = y + (((int64_t)b * H * up + oy) * Wo + ox) * ldy + gl * 8;
+      uint32_t o[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const __nv_bfloat162 pk = __floats2bfloat162_rn(acc[2 * e], acc[2 * e + 1]);
+        o[e] = *reinterpret_cast<const uint32_t*>(&pk);
+      }
+      *reinterpret_cast<uint4*>(dst) = make_uint4(o[0], o[1], o[2], o[3]);
     }
   }
 }
@@ -497,6 +577,18 @@ int carafe_reassemble_fwd(const void* enc, int64_t ldenc, const void* z, int64_t
       ldz % 2 == 0 && ldy % 2 == 0 && reinterpret_cast<uintptr_t>(z) % 4 == 0 && reinterpret_cast<uintptr_t>(y) % 4 == 0) {
     const unsigned g2 = (unsigned)ceil_div64(pixels, 8);
     const __nv_bfloat16 *e_ = (const __nv_bfloat16*)enc, *z_ = (const __nv_bfloat16*)z, *b_ = (const __nv_bfloat16*)bias;
+    // several pixels per warp with 16-byte loads where the rows allow it (CSWIN_CARAFE_GROUPED=0: the warp-per-pixel kernel, A/B switch)
+    static const bool grouped = [] { const char* e = getenv("CSWIN_CARAFE_GROUPED"); return !(e && e[0] == '0'); }();
+    const bool al16 = (ldz * 2) % 16 == 0 && (ldy * 2) % 16 == 0 && reinterpret_cast<uintptr_t>(z) % 16 == 0 &&
+                      reinterpret_cast<uintptr_t>(y) % 16 == 0 && reinterpret_cast<uintptr_t>(bias) % 16 == 0;
+    if (grouped && al16 && (C == 64 || C == 128) && up * up <= C / 8) {
+      const int ppw = 32 / (C / 8);
+      const unsigned gg = (unsigned)ceil_div64(pixels, 8 * ppw);
+      if (C == 64) CSWIN_CUDA_OK(launch_pdl(carafe_reassemble_grp_kernel<8>, dim3(gg), dim3(256), (size_t)(0), s, e_, ldenc, z_, ldz, b_, (__nv_bfloat16*)y, ldy, pixels, H, W, up));
+      else CSWIN_CUDA_OK(launch_pdl(carafe_reassemble_grp_kernel<16>, dim3(gg), dim3(256), (size_t)(0), s, e_, ldenc, z_, ldz, b_, (__nv_bfloat16*)y, ldy, pixels, H, W, up));
+      CSWIN_LAUNCH_CHECK();
+      return CSWIN_OK;
+    }
     if (C == 64) CSWIN_CUDA_OK(launch_pdl(carafe_reassemble_warp_kernel<2>, dim3(g2), dim3(256), (size_t)(0), s, e_, ldenc, z_, ldz, b_, (__nv_bfloat16*)y, ldy, pixels, H, W, up));
     else if (C == 128) CSWIN_CUDA_OK(launch_pdl(carafe_reassemble_warp_kernel<4>, dim3(g2), dim3(256), (size_t)(0), s, e_, ldenc, z_, ldz, b_, (__nv_bfloat16*)y, ldy, pixels, H, W, up));
     else CSWIN_CUDA_OK(launch_pdl(carafe_reassemble_warp_kernel<8>, dim3(g2), dim3(256), (size_t)(0), s, e_, ldenc, z_, ldz, b_, (__nv_bfloat16*)y, ldy, pixels, H, W, up));
