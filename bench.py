@@ -12,8 +12,10 @@ native arm  : a "step" is one bf16 forward of cswin_tiny_224_lite over one batch
               `value`  = slices/s with the inputs resident in HBM (8 rotating batches = 462 MB > L2),
               `e2e`    = same metric through the public nn.Module call with HOST (pinned) inputs: H2D copy of the
                          batch, forward, argmax label map, D2H of the label map, every step,
-              `roofline` = fused LePE attention kernel family: algorithmic bytes / CUDA-event time vs measured HBM peak,
-              `cpu_baseline` = the CPU oracle (port of the reference's PyTorch path) on this box's host cores.
+              `roofline` = the dominant kernel family (tcgen05 Linear incl. the implicit-GEMM convs): algorithmic flops / CUDA-event
+                         time vs the measured bf16 peak; `roofline_attention` = fused LePE attention family: algorithmic bytes / time
+                         vs the measured HBM peak; `roofline_model` = the whole forward,
+              `cpu_baseline` = the unmodified reference (baseline/_ref; the oracle port if it did not travel) on this box's host cores.
 reference arm: the reference's own CPU path on all host cores, same metric / config; rank 0 only.  It is the UNMODIFIED
               reference (baseline/_ref/networks/cswin_unet.py, copied verbatim by build(); kind "reference") when that copy
               travelled with the snapshot, else the oracle port (kind "port").
